@@ -1,0 +1,316 @@
+/*
+ * avif_b200.h -- C ABI of the B200-native pixel-reformat + alpha path.
+ *
+ * This library replaces ONE path of libavif (the reference): RGB<->YUV reformat,
+ * alpha reformat and alpha (un)premultiply.  Every entry point below is the
+ * symbol a libavif caller already binds; the struct layouts and enum values are
+ * ABI-compatible with the reference's public header so that a program compiled
+ * against the reference's <avif/avif.h> can link (or LD_PRELOAD) this library
+ * for these calls without recompiling.  Layout compatibility is pinned by
+ * tests/test_abi_layout.py (compiled against the reference header when present).
+ *
+ * Reference interface replaced (file:line relative to the reference tree):
+ *   avifImageYUVToRGB               include/avif/avif.h:1040   src/reformat.c:1649
+ *   avifImageRGBToYUV               include/avif/avif.h:1039   src/reformat.c:221
+ *   avifRGBImagePremultiplyAlpha    include/avif/avif.h:1045   src/alpha.c:151
+ *   avifRGBImageUnpremultiplyAlpha  include/avif/avif.h:1046   src/alpha.c:338
+ *   avifReformatAlpha/avifFillAlpha include/avif/internal.h:277-278  src/alpha.c:9,37
+ *   avif{FullToLimited,LimitedToFull}{Y,UV}  include/avif/avif.h:1051-1054  src/reformat.c:1778-1840
+ *   avifRGBImage helpers            include/avif/avif.h:971-973,1031-1036  src/avif.c:670-760
+ *   avifLibYUVVersion               include/avif/avif.h:152   (returns 0: no libyuv here)
+ *
+ * Pointers in avifImage / avifRGBImage may be HOST pointers (the reference's
+ * contract; data is staged over PCIe) or DEVICE pointers (resident planes; no
+ * copies) -- the library classifies every plane pointer through CUDA UVA.
+ * There is no CPU fallback: without a usable CUDA device every conversion entry
+ * point returns AVIF_RESULT_UNKNOWN_ERROR.
+ *
+ * If the reference's own <avif/avif.h> was included first, its definitions are
+ * used and only the avifB200* extensions are declared here.
+ */
+#ifndef AVIF_B200_H
+#define AVIF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(AVIF_B200_BUILDING)
+#define AVIF_B200_API __attribute__((visibility("default")))
+#else
+#define AVIF_B200_API
+#endif
+
+#ifndef AVIF_AVIF_H /* reference header not included: provide ABI-identical definitions */
+
+typedef int avifBool;
+#define AVIF_TRUE 1
+#define AVIF_FALSE 0
+
+#define AVIF_PLANE_COUNT_YUV 3
+enum { AVIF_CHAN_Y = 0, AVIF_CHAN_U = 1, AVIF_CHAN_V = 2, AVIF_CHAN_A = 3 };
+enum { AVIF_PLANES_YUV = 1 << 0, AVIF_PLANES_A = 1 << 1, AVIF_PLANES_ALL = 0xff };
+typedef uint32_t avifPlanesFlags;
+
+/* Only the result codes this path can return are named; values match avif.h:163-203. */
+typedef enum avifResult {
+    AVIF_RESULT_OK = 0,
+    AVIF_RESULT_UNKNOWN_ERROR = 1,
+    AVIF_RESULT_REFORMAT_FAILED = 5,
+    AVIF_RESULT_INVALID_ARGUMENT = 24,
+    AVIF_RESULT_NOT_IMPLEMENTED = 25,
+    AVIF_RESULT_OUT_OF_MEMORY = 26,
+    AVIF_RESULT_INTERNAL_ERROR = 29
+} avifResult;
+
+typedef enum avifPixelFormat {
+    AVIF_PIXEL_FORMAT_NONE = 0,
+    AVIF_PIXEL_FORMAT_YUV444,
+    AVIF_PIXEL_FORMAT_YUV422,
+    AVIF_PIXEL_FORMAT_YUV420,
+    AVIF_PIXEL_FORMAT_YUV400,
+    AVIF_PIXEL_FORMAT_COUNT
+} avifPixelFormat;
+
+typedef struct avifPixelFormatInfo {
+    avifBool monochrome;
+    int chromaShiftX;
+    int chromaShiftY;
+} avifPixelFormatInfo;
+
+typedef enum avifChromaSamplePosition {
+    AVIF_CHROMA_SAMPLE_POSITION_UNKNOWN = 0,
+    AVIF_CHROMA_SAMPLE_POSITION_VERTICAL = 1,
+    AVIF_CHROMA_SAMPLE_POSITION_COLOCATED = 2,
+    AVIF_CHROMA_SAMPLE_POSITION_RESERVED = 3
+} avifChromaSamplePosition;
+
+typedef enum avifRange { AVIF_RANGE_LIMITED = 0, AVIF_RANGE_FULL = 1 } avifRange;
+
+/* CICP code points (ITU-T H.273) used by this path. */
+enum {
+    AVIF_COLOR_PRIMARIES_UNKNOWN = 0,
+    AVIF_COLOR_PRIMARIES_BT709 = 1,
+    AVIF_COLOR_PRIMARIES_UNSPECIFIED = 2,
+    AVIF_COLOR_PRIMARIES_BT470M = 4,
+    AVIF_COLOR_PRIMARIES_BT470BG = 5,
+    AVIF_COLOR_PRIMARIES_BT601 = 6,
+    AVIF_COLOR_PRIMARIES_SMPTE240 = 7,
+    AVIF_COLOR_PRIMARIES_GENERIC_FILM = 8,
+    AVIF_COLOR_PRIMARIES_BT2020 = 9,
+    AVIF_COLOR_PRIMARIES_XYZ = 10,
+    AVIF_COLOR_PRIMARIES_SMPTE431 = 11,
+    AVIF_COLOR_PRIMARIES_SMPTE432 = 12,
+    AVIF_COLOR_PRIMARIES_EBU3213 = 22
+};
+typedef uint16_t avifColorPrimaries;
+typedef uint16_t avifTransferCharacteristics;
+enum {
+    AVIF_MATRIX_COEFFICIENTS_IDENTITY = 0,
+    AVIF_MATRIX_COEFFICIENTS_BT709 = 1,
+    AVIF_MATRIX_COEFFICIENTS_UNSPECIFIED = 2,
+    AVIF_MATRIX_COEFFICIENTS_FCC = 4,
+    AVIF_MATRIX_COEFFICIENTS_BT470BG = 5,
+    AVIF_MATRIX_COEFFICIENTS_BT601 = 6,
+    AVIF_MATRIX_COEFFICIENTS_SMPTE240 = 7,
+    AVIF_MATRIX_COEFFICIENTS_YCGCO = 8,
+    AVIF_MATRIX_COEFFICIENTS_BT2020_NCL = 9,
+    AVIF_MATRIX_COEFFICIENTS_BT2020_CL = 10,
+    AVIF_MATRIX_COEFFICIENTS_SMPTE2085 = 11,
+    AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_NCL = 12,
+    AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_CL = 13,
+    AVIF_MATRIX_COEFFICIENTS_ICTCP = 14,
+    AVIF_MATRIX_COEFFICIENTS_YCGCO_RE = 16,
+    AVIF_MATRIX_COEFFICIENTS_YCGCO_RO = 17,
+    AVIF_MATRIX_COEFFICIENTS_LAST
+};
+typedef uint16_t avifMatrixCoefficients;
+
+/* Members this path never touches are kept only so that sizeof/offsetof match avif.h:777-851. */
+typedef struct avifRWData { uint8_t * data; size_t size; } avifRWData;
+typedef struct avifContentLightLevelInformationBox { uint16_t maxCLL, maxPALL; } avifContentLightLevelInformationBox;
+typedef uint32_t avifTransformFlags;
+typedef struct avifPixelAspectRatioBox { uint32_t hSpacing, vSpacing; } avifPixelAspectRatioBox;
+typedef struct avifCleanApertureBox {
+    uint32_t widthN, widthD, heightN, heightD, horizOffN, horizOffD, vertOffN, vertOffD;
+} avifCleanApertureBox;
+typedef struct avifImageRotation { uint8_t angle; } avifImageRotation;
+typedef struct avifImageMirror { uint8_t axis; } avifImageMirror;
+typedef struct avifCropRect { uint32_t x, y, width, height; } avifCropRect;
+struct avifImageItemProperty;
+struct avifGainMap;
+
+typedef struct avifImage {
+    uint32_t width;
+    uint32_t height;
+    uint32_t depth; /* 8, 10, 12 or 16; samples are uint16_t (low bits) when depth > 8 */
+
+    avifPixelFormat yuvFormat;
+    avifRange yuvRange;
+    avifChromaSamplePosition yuvChromaSamplePosition;
+    uint8_t * yuvPlanes[AVIF_PLANE_COUNT_YUV];
+    uint32_t yuvRowBytes[AVIF_PLANE_COUNT_YUV];
+    avifBool imageOwnsYUVPlanes;
+
+    uint8_t * alphaPlane;
+    uint32_t alphaRowBytes;
+    avifBool imageOwnsAlphaPlane;
+    avifBool alphaPremultiplied;
+
+    avifRWData icc;
+
+    avifColorPrimaries colorPrimaries;
+    avifTransferCharacteristics transferCharacteristics;
+    avifMatrixCoefficients matrixCoefficients;
+
+    avifContentLightLevelInformationBox clli;
+    avifTransformFlags transformFlags;
+    avifPixelAspectRatioBox pasp;
+    avifCleanApertureBox clap;
+    avifImageRotation irot;
+    avifImageMirror imir;
+    avifRWData exif;
+    avifRWData xmp;
+    struct avifImageItemProperty * properties;
+    size_t numProperties;
+    struct avifGainMap * gainMap;
+} avifImage;
+
+typedef enum avifRGBFormat {
+    AVIF_RGB_FORMAT_RGB = 0,
+    AVIF_RGB_FORMAT_RGBA,
+    AVIF_RGB_FORMAT_ARGB,
+    AVIF_RGB_FORMAT_BGR,
+    AVIF_RGB_FORMAT_BGRA,
+    AVIF_RGB_FORMAT_ABGR,
+    AVIF_RGB_FORMAT_RGB_565, /* YUV->RGB only, depth 8 */
+    AVIF_RGB_FORMAT_GRAY,
+    AVIF_RGB_FORMAT_GRAYA,
+    AVIF_RGB_FORMAT_AGRAY,
+    AVIF_RGB_FORMAT_COUNT
+} avifRGBFormat;
+
+typedef enum avifChromaUpsampling {
+    AVIF_CHROMA_UPSAMPLING_AUTOMATIC = 0,    /* bilinear (no libyuv in this build) */
+    AVIF_CHROMA_UPSAMPLING_FASTEST = 1,      /* nearest */
+    AVIF_CHROMA_UPSAMPLING_BEST_QUALITY = 2, /* bilinear */
+    AVIF_CHROMA_UPSAMPLING_NEAREST = 3,
+    AVIF_CHROMA_UPSAMPLING_BILINEAR = 4
+} avifChromaUpsampling;
+
+typedef enum avifChromaDownsampling {
+    AVIF_CHROMA_DOWNSAMPLING_AUTOMATIC = 0,
+    AVIF_CHROMA_DOWNSAMPLING_FASTEST = 1,
+    AVIF_CHROMA_DOWNSAMPLING_BEST_QUALITY = 2,
+    AVIF_CHROMA_DOWNSAMPLING_AVERAGE = 3,
+    AVIF_CHROMA_DOWNSAMPLING_SHARP_YUV = 4 /* 4:2:0: NOT_IMPLEMENTED (no libsharpyuv), as reformat.c:256-261 */
+} avifChromaDownsampling;
+
+typedef struct avifRGBImage {
+    uint32_t width;
+    uint32_t height;
+    uint32_t depth; /* 8, 10, 12, 16 */
+    avifRGBFormat format;
+    avifChromaUpsampling chromaUpsampling;
+    avifChromaDownsampling chromaDownsampling;
+    avifBool avoidLibYUV; /* accepted, ignored: results are always the built-in (precise) path's */
+    avifBool ignoreAlpha;
+    avifBool alphaPremultiplied;
+    avifBool isFloat; /* half-float output, depth must be 16 */
+    int maxThreads;   /* hint only; negative values are rejected like the reference */
+
+    uint8_t * pixels;
+    uint32_t rowBytes;
+} avifRGBImage;
+
+/* ---- the reference's public entry points for this path (same names, same semantics) ---- */
+AVIF_B200_API avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb);
+AVIF_B200_API avifResult avifImageRGBToYUV(avifImage * image, const avifRGBImage * rgb);
+AVIF_B200_API avifResult avifRGBImagePremultiplyAlpha(avifRGBImage * rgb);
+AVIF_B200_API avifResult avifRGBImageUnpremultiplyAlpha(avifRGBImage * rgb);
+
+AVIF_B200_API int avifFullToLimitedY(uint32_t depth, int v);
+AVIF_B200_API int avifFullToLimitedUV(uint32_t depth, int v);
+AVIF_B200_API int avifLimitedToFullY(uint32_t depth, int v);
+AVIF_B200_API int avifLimitedToFullUV(uint32_t depth, int v);
+
+AVIF_B200_API uint32_t avifRGBFormatChannelCount(avifRGBFormat format);
+AVIF_B200_API avifBool avifRGBFormatHasAlpha(avifRGBFormat format);
+AVIF_B200_API avifBool avifRGBFormatIsGray(avifRGBFormat format);
+AVIF_B200_API void avifRGBImageSetDefaults(avifRGBImage * rgb, const avifImage * image);
+AVIF_B200_API uint32_t avifRGBImagePixelSize(const avifRGBImage * rgb);
+AVIF_B200_API avifResult avifRGBImageAllocatePixels(avifRGBImage * rgb);
+AVIF_B200_API void avifRGBImageFreePixels(avifRGBImage * rgb);
+AVIF_B200_API void avifGetPixelFormatInfo(avifPixelFormat format, avifPixelFormatInfo * info);
+AVIF_B200_API unsigned int avifLibYUVVersion(void);
+
+#endif /* AVIF_AVIF_H */
+
+/* ---- internal seam of the reference (include/avif/internal.h:259-278), exported for drop-in at B-2 ---- */
+#ifndef AVIF_INTERNAL_H
+typedef struct avifAlphaParams {
+    uint32_t width;
+    uint32_t height;
+
+    uint32_t srcDepth;
+    const uint8_t * srcPlane;
+    uint32_t srcRowBytes;
+    uint32_t srcOffsetBytes;
+    uint32_t srcPixelBytes;
+
+    uint32_t dstDepth;
+    uint8_t * dstPlane;
+    uint32_t dstRowBytes;
+    uint32_t dstOffsetBytes;
+    uint32_t dstPixelBytes;
+} avifAlphaParams;
+AVIF_B200_API void avifFillAlpha(const avifAlphaParams * params);
+AVIF_B200_API void avifReformatAlpha(const avifAlphaParams * params);
+#endif
+
+/* ---- B200 extensions (not in the reference) ----------------------------------------------- */
+
+/* Stream-ordered variants: every plane / pixel pointer MUST be a device pointer on the current
+ * device; nothing is copied, nothing is synchronised; the kernels are enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).  Same validation and result
+ * codes as the synchronous entry points.  avifB200ImageRGBToYUVAsync requires the destination
+ * planes to exist already (it cannot malloc device memory behind the caller's back). */
+AVIF_B200_API avifResult avifB200ImageYUVToRGBAsync(const avifImage * image, avifRGBImage * rgb, void * stream);
+AVIF_B200_API avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avifRGBImage * rgb, void * stream);
+AVIF_B200_API avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
+AVIF_B200_API avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
+
+/* Range conversion of a whole alpha plane (reference: avifImageLimitedToFullAlpha, src/read.c:6724-6764,
+ * integer avifLimitedToFullY per sample).  Host or device pointers. */
+AVIF_B200_API avifResult avifB200ImageLimitedToFullAlpha(avifImage * image);
+
+/* Grid plane staging (reference: avifImageCopySamples src/avif.c:187-225 as used by
+ * avifDecoderDataCopyTileToImage src/read.c:1823-1878, and avifImageCopyAndPad src/write.c:1151-1205).
+ * Device pointers, stream-ordered. */
+AVIF_B200_API avifResult avifB200ImageCopySamplesAsync(avifImage * dst, const avifImage * src, avifPlanesFlags planes, void * stream);
+AVIF_B200_API avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, void * stream);
+
+/* Pinned host memory helpers for callers that want full PCIe rate on the host-pointer path. */
+AVIF_B200_API void * avifB200AllocPinned(size_t size);
+AVIF_B200_API void avifB200FreePinned(void * p);
+
+/* Selects which kernels serve subsequent calls made by THIS thread: 0 = automatic (vectorised kernels
+ * when alignment allows, else the generic kernel), 1 = force the generic byte-addressed kernel.
+ * Used by the parity tests to check both implementations against the oracle. */
+AVIF_B200_API void avifB200SetKernelPolicy(int policy);
+/* Number of kernels this library has launched from the calling thread since the last reset. */
+AVIF_B200_API uint64_t avifB200KernelLaunchCount(void);
+AVIF_B200_API void avifB200ResetKernelLaunchCount(void);
+/* Name of the kernel variant chosen by the most recent conversion on this thread (static string). */
+AVIF_B200_API const char * avifB200LastKernelName(void);
+/* 1 if a CUDA device is usable, else 0 (conversions then fail with AVIF_RESULT_UNKNOWN_ERROR). */
+AVIF_B200_API int avifB200DeviceAvailable(void);
+AVIF_B200_API const char * avifB200Version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVIF_B200_H */
