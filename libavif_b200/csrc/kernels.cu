@@ -1,0 +1,657 @@
+/*
+ * kernels.cu -- hand-written sm_100a kernels of the reformat + alpha path and their launchers.
+ *
+ * Every kernel here is a per-pixel affine map: HBM-bound byte/short traffic, no tensor cores.  Design rules:
+ *   - one fused pass per call: alpha channel, colour conversion, (un)premultiply, F16 and packing all happen
+ *     in registers between one read of the source planes and one write of the destination (the reference
+ *     makes up to four passes over the RGB buffer, src/reformat.c:1445-1593);
+ *   - planar inputs are read with lane-contiguous (coalesced) accesses, all loads of a warp tile are issued
+ *     before any arithmetic so that >= 48 B per thread are in flight;
+ *   - interleaved outputs (1,2,3,4,6,8 bytes per pixel) are packed into a per-warp shared-memory tile and
+ *     leave the SM as 16-byte, fully coalesced vector stores regardless of the pixel format;
+ *   - arbitrary pointer alignment / row strides (view rectangles) are handled by the same kernels through a
+ *     narrower copy-out granularity; a byte-addressed one-thread-per-pixel kernel exists as an independent
+ *     second implementation for cross-checking (avifB200SetKernelPolicy(1)).
+ *
+ * Arithmetic lives in pixel_math.cuh and mirrors the reference bit for bit.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pixel_math.cuh"
+#include "plan.h"
+
+namespace ab {
+
+static thread_local uint64_t g_launches = 0;
+
+/* ---------------------------------------------------------------------------------------------- */
+/* sample access                                                                                   */
+
+template <typename T>
+__device__ __forceinline__ uint32_t ld_sample(const uint8_t * row, uint32_t x)
+{
+    return (uint32_t)__ldg(reinterpret_cast<const T *>(row) + x);
+}
+/* YUV/alpha codes feeding arithmetic: 16-bit containers are clamped to yuvMax (ref: src/reformat.c:712, :1005) */
+template <typename YT>
+__device__ __forceinline__ uint32_t ld_code(const uint8_t * row, uint32_t x, uint32_t yuvMax)
+{
+    const uint32_t v = ld_sample<YT>(row, x);
+    return (sizeof(YT) == 2) ? min(v, yuvMax) : v;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_chan(uint8_t * p, uint32_t v)
+{
+    *reinterpret_cast<T *>(p) = (T)v;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* YUV -> RGB: one pixel                                                                           */
+
+struct PixelIn {
+    uint32_t y;          /* luma code (clamped) */
+    float cb, cr;        /* normalised (and, for bilinear, already blended) chroma */
+    uint32_t u, v;       /* raw chroma codes (identity8 shuffle only) */
+    uint32_t aRaw;       /* source alpha sample, unclamped (alpha channel copy, ref: src/alpha.c:56) */
+    uint32_t aDst;       /* alpha already present in the destination (AB_ALPHA_KEEP) */
+};
+
+struct PixelOut {
+    uint32_t c0, c1, c2; /* R,G,B codes -- or gray in c0 -- or the RGB565 word in c0 */
+    uint32_t a;
+};
+
+template <bool PLAIN>
+__device__ __forceinline__ PixelOut convert_pixel(const PixelIn & in, bool hasChroma, const AbY2RJob & J)
+{
+    PixelOut o;
+    /* alpha channel value (ref: src/reformat.c:1464-1486 -> src/alpha.c:9-149) */
+    if (J.alphaWrite == AB_ALPHA_COPY) {
+        o.a = J.alphaRescale ? alpha_rescale(in.aRaw, J.yuvMaxF, J.rgbMaxF, J.rgbMax) : in.aRaw;
+    } else if (J.alphaWrite == AB_ALPHA_FILL) {
+        o.a = J.rgbMax;
+    } else {
+        o.a = in.aDst;
+    }
+
+    if (!PLAIN && J.mode == AB_MODE_IDENTITY8_SHUFFLE) { /* ref: src/reformat.c:1278-1309 */
+        o.c0 = in.v;
+        o.c1 = in.y;
+        o.c2 = in.u;
+    } else {
+        const float Y = norm_y(in.y, J);
+        if (!PLAIN && J.isGray) { /* ref: src/reformat.c:888-892 */
+            float g = clamp01(Y), g1 = g, g2 = g;
+            if (J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) alpha_float(g, g1, g2, min(in.aRaw, J.yuvMax), J);
+            o.c0 = quant_rgb(g, J.rgbMaxF);
+            o.c1 = o.c2 = 0;
+        } else {
+            RGBf c;
+            if (PLAIN) {
+                if (hasChroma) {
+                    c.r = __fadd_rn(Y, __fmul_rn(J.c1, in.cr));
+                    c.b = __fadd_rn(Y, __fmul_rn(J.c2, in.cb));
+                    const float t = __fmul_rn(2.0f, __fadd_rn(__fmul_rn(J.c3, in.cr), __fmul_rn(J.c4, in.cb)));
+                    c.g = __fsub_rn(Y, div_const(t, J.kg));
+                } else {
+                    c.r = c.g = c.b = Y;
+                }
+            } else {
+                c = yuv_to_rgb_norm(Y, in.cb, in.cr, in.y, hasChroma, J);
+            }
+            float r = clamp01(c.r), g = clamp01(c.g), b = clamp01(c.b);
+            if (!PLAIN && (J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL)) alpha_float(r, g, b, min(in.aRaw, J.yuvMax), J);
+            o.c0 = quant_rgb(r, J.rgbMaxF);
+            o.c1 = quant_rgb(g, J.rgbMaxF);
+            o.c2 = quant_rgb(b, J.rgbMaxF);
+        }
+    }
+    if (!PLAIN) {
+        if (J.alphaMul == AB_MUL_INT_PREMUL || J.alphaMul == AB_MUL_INT_UNPREMUL) { /* ref: src/reformat.c:1575-1585 -> src/alpha.c */
+            const bool un = (J.alphaMul == AB_MUL_INT_UNPREMUL);
+            o.c0 = alpha_int(o.c0, o.a, J.rgbMax, J.rgbMaxF, un);
+            o.c1 = alpha_int(o.c1, o.a, J.rgbMax, J.rgbMaxF, un);
+            o.c2 = alpha_int(o.c2, o.a, J.rgbMax, J.rgbMaxF, un);
+        }
+        if (J.toF16) { /* ref: src/reformat.c:1419-1443: every channel, alpha included */
+            o.c0 = to_f16_bits(o.c0, J.f16mul);
+            o.c1 = to_f16_bits(o.c1, J.f16mul);
+            o.c2 = to_f16_bits(o.c2, J.f16mul);
+            o.a = to_f16_bits(o.a, J.f16mul);
+        }
+        if (J.is565) o.c0 = pack565(o.c0, o.c1, o.c2);
+    }
+    return o;
+}
+
+/* place one converted pixel at `px` (global or shared memory) */
+template <typename RT, bool PLAIN>
+__device__ __forceinline__ void store_pixel(uint8_t * px, const PixelOut & o, const AbY2RJob & J)
+{
+    if (!PLAIN && J.is565) {
+        st_chan<uint16_t>(px, o.c0);
+        return;
+    }
+    if (!PLAIN && J.isGray) {
+        st_chan<RT>(px + J.offGray, o.c0);
+    } else {
+        st_chan<RT>(px + J.offR, o.c0);
+        st_chan<RT>(px + J.offG, o.c1);
+        st_chan<RT>(px + J.offB, o.c2);
+    }
+    if (J.hasAlphaChan) st_chan<RT>(px + J.offA, o.a);
+}
+
+/* gather the inputs of pixel (i,j) */
+template <typename YT, typename RT, int CHROMA>
+__device__ __forceinline__ PixelIn load_pixel(uint32_t i, uint32_t j, const AbY2RJob & J)
+{
+    PixelIn in;
+    in.cb = in.cr = 0.5f;
+    in.u = in.v = 0;
+    in.aRaw = 0;
+    in.aDst = 0;
+    in.y = ld_code<YT>(J.y + (int64_t)j * J.yRB, i, J.yuvMax);
+    if (CHROMA == AB_CHROMA_FULL || CHROMA == AB_CHROMA_NEAREST) {
+        const uint32_t ui = i >> J.shiftX, uj = j >> J.shiftY;
+        in.u = ld_code<YT>(J.u + (int64_t)uj * J.uRB, ui, J.yuvMax);
+        in.v = ld_code<YT>(J.v + (int64_t)uj * J.vRB, ui, J.yuvMax);
+        in.cb = norm_uv(in.u, J);
+        in.cr = norm_uv(in.v, J);
+    } else if (CHROMA == AB_CHROMA_BILINEAR) {
+        /* neighbour choice with edge replication, ref: src/reformat.c:766-795 */
+        const uint32_t ui = i >> 1, uj = j >> J.shiftY;
+        int dc, dr;
+        if (i == 0 || (i == J.width - 1 && (i & 1))) dc = 0;
+        else dc = (i & 1) ? 1 : -1;
+        if (!J.vertBlend || j == 0 || (j == J.height - 1 && (j & 1))) dr = 0;
+        else dr = (j & 1) ? 1 : -1;
+        const uint8_t * u0 = J.u + (int64_t)uj * J.uRB;
+        const uint8_t * v0 = J.v + (int64_t)uj * J.vRB;
+        const uint8_t * u1 = u0 + (int64_t)dr * J.uRB;
+        const uint8_t * v1 = v0 + (int64_t)dr * J.vRB;
+        const uint32_t ub = (uint32_t)((int)ui + dc);
+        const float u00 = norm_uv(ld_code<YT>(u0, ui, J.yuvMax), J), u10 = norm_uv(ld_code<YT>(u0, ub, J.yuvMax), J);
+        const float u01 = norm_uv(ld_code<YT>(u1, ui, J.yuvMax), J), u11 = norm_uv(ld_code<YT>(u1, ub, J.yuvMax), J);
+        const float v00 = norm_uv(ld_code<YT>(v0, ui, J.yuvMax), J), v10 = norm_uv(ld_code<YT>(v0, ub, J.yuvMax), J);
+        const float v01 = norm_uv(ld_code<YT>(v1, ui, J.yuvMax), J), v11 = norm_uv(ld_code<YT>(v1, ub, J.yuvMax), J);
+        in.cb = bilinear4(u00, u10, u01, u11);
+        in.cr = bilinear4(v00, v10, v01, v11);
+    }
+    if (J.a) in.aRaw = ld_sample<YT>(J.a + (int64_t)j * J.aRB, i);
+    if (J.alphaWrite == AB_ALPHA_KEEP && J.hasAlphaChan) {
+        in.aDst = ld_sample<RT>(J.rgb + (int64_t)j * J.rgbRB + (int64_t)i * J.pixBytes + J.offA, 0);
+    }
+    return in;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* generic kernel: one thread per pixel, direct byte-addressed stores (any alignment, any stride)   */
+
+template <typename YT, typename RT>
+__global__ void __launch_bounds__(256) y2r_generic_kernel(const __grid_constant__ AbY2RJob J)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = J.rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= J.width || j >= J.rowEnd) return;
+    PixelIn in;
+    switch (J.chroma) {
+        case AB_CHROMA_FULL: in = load_pixel<YT, RT, AB_CHROMA_FULL>(i, j, J); break;
+        case AB_CHROMA_NEAREST: in = load_pixel<YT, RT, AB_CHROMA_NEAREST>(i, j, J); break;
+        case AB_CHROMA_BILINEAR: in = load_pixel<YT, RT, AB_CHROMA_BILINEAR>(i, j, J); break;
+        default: in = load_pixel<YT, RT, AB_CHROMA_NONE>(i, j, J); break;
+    }
+    const PixelOut o = convert_pixel<false>(in, J.chroma != AB_CHROMA_NONE, J);
+    store_pixel<RT, false>(J.rgb + (int64_t)j * J.rgbRB + (int64_t)i * J.pixBytes, o, J);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* tiled kernel: a warp converts 256 consecutive pixels of one row; the packed pixels are staged in   */
+/* shared memory and written out as 16-byte coalesced vectors                                        */
+
+constexpr int kTilePx = 256;   /* pixels per warp tile */
+constexpr int kPxPerLane = 8;  /* kTilePx / 32 */
+constexpr int kWarpsPerBlock = 8;
+
+/* copy `n` bytes of a warp's staging tile to global memory with the widest granularity the address allows */
+__device__ __forceinline__ void warp_copy_out(uint8_t * __restrict__ dst, const uint8_t * __restrict__ stage, uint32_t n, uint32_t lane)
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(dst);
+    if ((addr & 15) == 0) {
+        const uint32_t nv = n >> 4;
+        const uint4 * s = reinterpret_cast<const uint4 *>(stage);
+        uint4 * d = reinterpret_cast<uint4 *>(dst);
+        for (uint32_t k = lane; k < nv; k += 32) d[k] = s[k];
+        for (uint32_t b = (nv << 4) + lane; b < n; b += 32) dst[b] = stage[b];
+    } else if ((addr & 3) == 0) {
+        const uint32_t nv = n >> 2;
+        const uint32_t * s = reinterpret_cast<const uint32_t *>(stage);
+        uint32_t * d = reinterpret_cast<uint32_t *>(dst);
+        for (uint32_t k = lane; k < nv; k += 32) d[k] = s[k];
+        for (uint32_t b = (nv << 2) + lane; b < n; b += 32) dst[b] = stage[b];
+    } else {
+        for (uint32_t b = lane; b < n; b += 32) dst[b] = stage[b];
+    }
+}
+
+template <typename YT, typename RT, int CHROMA, bool PLAIN>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) y2r_tiled_kernel(const __grid_constant__ AbY2RJob J)
+{
+    __shared__ __align__(16) uint8_t stageAll[kWarpsPerBlock][kTilePx * 4 * sizeof(RT)];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t j = J.rowBegin + blockIdx.y * kWarpsPerBlock + warp;
+    if (j >= J.rowEnd) return; /* warp-uniform */
+    const uint32_t x0 = blockIdx.x * kTilePx;
+    uint8_t * stage = stageAll[warp];
+
+    PixelIn in[kPxPerLane];
+#pragma unroll
+    for (int k = 0; k < kPxPerLane; ++k) {
+        const uint32_t i = x0 + lane + 32 * k;
+        if (i < J.width) in[k] = load_pixel<YT, RT, CHROMA>(i, j, J);
+    }
+#pragma unroll
+    for (int k = 0; k < kPxPerLane; ++k) {
+        const uint32_t p = lane + 32 * k;
+        if (x0 + p < J.width) {
+            const PixelOut o = convert_pixel<PLAIN>(in[k], CHROMA != AB_CHROMA_NONE, J);
+            store_pixel<RT, PLAIN>(stage + p * J.pixBytes, o, J);
+        }
+    }
+    __syncwarp();
+    const uint32_t npx = min((uint32_t)kTilePx, J.width - x0);
+    warp_copy_out(J.rgb + (int64_t)j * J.rgbRB + (int64_t)x0 * J.pixBytes, stage, npx * J.pixBytes, lane);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* RGB -> YUV                                                                                      */
+
+struct YUVf {
+    float y, u, v;
+};
+
+template <typename RT>
+__device__ __forceinline__ YUVf rgb_pixel_to_yuv(const uint8_t * px, const AbR2YJob & J)
+{
+    YUVf o;
+    const float m = J.rgbMaxF;
+    if (J.isGray) { /* ref: src/reformat.c:479-511 */
+        float g = __fdiv_rn(u2f(ld_sample<RT>(px + J.offGray, 0)), m);
+        if (J.alphaMul != AB_MUL_NONE) {
+            const float a = __fdiv_rn(u2f(ld_sample<RT>(px + J.offA, 0)), m);
+            if (a == 0.0f) g = 0.0f;
+            else if (a < 1.0f) g = (J.alphaMul == AB_MUL_FLOAT_MUL) ? __fmul_rn(g, a) : min1(__fdiv_rn(g, a));
+        }
+        o.y = g;
+        o.u = o.v = 0.0f;
+        return o;
+    }
+    float r = __fdiv_rn(u2f(ld_sample<RT>(px + J.offR, 0)), m); /* true divisions, ref: :312-323 */
+    float g = __fdiv_rn(u2f(ld_sample<RT>(px + J.offG, 0)), m);
+    float b = __fdiv_rn(u2f(ld_sample<RT>(px + J.offB, 0)), m);
+    if (J.alphaMul != AB_MUL_NONE) { /* ref: :325-358 */
+        const float a = __fdiv_rn(u2f(ld_sample<RT>(px + J.offA, 0)), m);
+        if (a == 0.0f) {
+            r = g = b = 0.0f;
+        } else if (a < 1.0f) {
+            if (J.alphaMul == AB_MUL_FLOAT_MUL) {
+                r = __fmul_rn(r, a);
+                g = __fmul_rn(g, a);
+                b = __fmul_rn(b, a);
+            } else {
+                r = min1(__fdiv_rn(r, a));
+                g = min1(__fdiv_rn(g, a));
+                b = min1(__fdiv_rn(b, a));
+            }
+        }
+    }
+    if (J.mode == AB_MODE_COEFF) { /* ref: :383-386 */
+        const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, r), __fmul_rn(J.kg, g)), __fmul_rn(J.kb, b));
+        o.y = Y;
+        o.u = __fdiv_rn(__fsub_rn(b, Y), J.du);
+        o.v = __fdiv_rn(__fsub_rn(r, Y), J.dv);
+    } else if (J.mode == AB_MODE_IDENTITY) { /* ref: :361-365 */
+        o.y = g;
+        o.u = b;
+        o.v = r;
+    } else if (J.mode == AB_MODE_YCGCO) { /* ref: :366-370 */
+        const float s = __fmul_rn(0.25f, __fadd_rn(r, b));
+        o.y = __fadd_rn(__fmul_rn(0.5f, g), s);
+        o.u = __fsub_rn(__fmul_rn(0.5f, g), s);
+        o.v = __fmul_rn(0.5f, __fsub_rn(r, b));
+    } else { /* YCgCo-Re/Ro, ref: :371-381 */
+        float t0 = __fmul_rn(r, m), t1 = __fmul_rn(g, m), t2 = __fmul_rn(b, m);
+        t0 = (t0 < 0.0f) ? 0.0f : ((m < t0) ? m : t0);
+        t1 = (t1 < 0.0f) ? 0.0f : ((m < t1) ? m : t1);
+        t2 = (t2 < 0.0f) ? 0.0f : ((m < t2) ? m : t2);
+        const int R = (int)round_half_up(t0), G = (int)round_half_up(t1), B = (int)round_half_up(t2);
+        const int Co = R - B;
+        const int t = B + (Co >> 1);
+        const int Cg = G - t;
+        o.y = __fdiv_rn((float)(t + (Cg >> 1)), J.rangeYdiv);
+        o.u = __fdiv_rn((float)Cg, J.rangeUVdiv);
+        o.v = __fdiv_rn((float)Co, J.rangeUVdiv);
+    }
+    return o;
+}
+
+/* ref: src/reformat.c:197-219 */
+__device__ __forceinline__ uint32_t quant_yuv(float v, float range, float bias, uint32_t yuvMax)
+{
+    const int q = (int)round_half_up(__fadd_rn(__fmul_rn(v, range), bias));
+    return (uint32_t)min(max(q, 0), (int)yuvMax);
+}
+
+/* one thread = one 2x2 block, exactly the reference's block walk (ref: src/reformat.c:295-470) */
+template <typename RT, typename YT>
+__global__ void __launch_bounds__(256) r2y_block_kernel(const __grid_constant__ AbR2YJob J)
+{
+    const uint32_t oi = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t oj = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    if (oi >= J.width || oj >= J.height) return;
+    const uint32_t bw = (oi + 1 >= J.width) ? 1 : 2, bh = (oj + 1 >= J.height) ? 1 : 2;
+    float bu[2][2], bv[2][2]; /* [bj][bi] */
+#pragma unroll
+    for (uint32_t bj = 0; bj < 2; ++bj) {
+#pragma unroll
+        for (uint32_t bi = 0; bi < 2; ++bi) {
+            bu[bj][bi] = bv[bj][bi] = 0.0f;
+            if (bj < bh && bi < bw) {
+                const uint32_t i = oi + bi, j = oj + bj;
+                const uint8_t * px = J.rgb + (int64_t)j * J.rgbRB + (int64_t)i * J.pixBytes;
+                const YUVf c = rgb_pixel_to_yuv<RT>(px, J);
+                bu[bj][bi] = c.u;
+                bv[bj][bi] = c.v;
+                st_chan<YT>(J.y + (int64_t)j * J.yRB + (int64_t)i * sizeof(YT), quant_yuv(c.y, J.rangeY, J.biasY, J.yuvMax));
+                if (J.hasChroma && !J.isGray && J.shiftX == 0) { /* 4:4:4 */
+                    st_chan<YT>(J.u + (int64_t)j * J.uRB + (int64_t)i * sizeof(YT), quant_yuv(c.u, J.rangeUV, J.biasUV, J.yuvMax));
+                    st_chan<YT>(J.v + (int64_t)j * J.vRB + (int64_t)i * sizeof(YT), quant_yuv(c.v, J.rangeUV, J.biasUV, J.yuvMax));
+                }
+                if (J.alphaWrite == AB_ALPHA_COPY) { /* ref: :545-569 -> src/alpha.c:37-149 */
+                    const uint32_t a = ld_sample<RT>(px + J.offA, 0);
+                    st_chan<YT>(J.a + (int64_t)j * J.aRB + (int64_t)i * sizeof(YT),
+                                J.alphaRescale ? alpha_rescale(a, J.rgbMaxF, J.yuvMaxF, J.yuvMax) : a);
+                } else if (J.alphaWrite == AB_ALPHA_FILL) {
+                    st_chan<YT>(J.a + (int64_t)j * J.aRB + (int64_t)i * sizeof(YT), J.yuvMax);
+                }
+            }
+        }
+    }
+    if (!J.hasChroma || J.isGray || J.shiftX == 0) return;
+    if (J.shiftY) { /* 4:2:0: ordered sum TL,TR,BL,BR over the samples that exist (ref: :413-440) */
+        float su = 0.0f, sv = 0.0f;
+#pragma unroll
+        for (uint32_t bj = 0; bj < 2; ++bj)
+#pragma unroll
+            for (uint32_t bi = 0; bi < 2; ++bi)
+                if (bj < bh && bi < bw) {
+                    su = __fadd_rn(su, bu[bj][bi]);
+                    sv = __fadd_rn(sv, bv[bj][bi]);
+                }
+        const float n = (float)(bw * bh);
+        const uint32_t ui = oi >> 1, uj = oj >> 1;
+        st_chan<YT>(J.u + (int64_t)uj * J.uRB + (int64_t)ui * sizeof(YT), quant_yuv(__fdiv_rn(su, n), J.rangeUV, J.biasUV, J.yuvMax));
+        st_chan<YT>(J.v + (int64_t)uj * J.vRB + (int64_t)ui * sizeof(YT), quant_yuv(__fdiv_rn(sv, n), J.rangeUV, J.biasUV, J.yuvMax));
+    } else { /* 4:2:2: per-row pair (ref: :441-467) */
+#pragma unroll
+        for (uint32_t bj = 0; bj < 2; ++bj) {
+            if (bj >= bh) break;
+            float su = 0.0f, sv = 0.0f;
+#pragma unroll
+            for (uint32_t bi = 0; bi < 2; ++bi)
+                if (bi < bw) {
+                    su = __fadd_rn(su, bu[bj][bi]);
+                    sv = __fadd_rn(sv, bv[bj][bi]);
+                }
+            const float n = (float)bw;
+            const uint32_t ui = oi >> 1, uj = oj + bj;
+            st_chan<YT>(J.u + (int64_t)uj * J.uRB + (int64_t)ui * sizeof(YT), quant_yuv(__fdiv_rn(su, n), J.rangeUV, J.biasUV, J.yuvMax));
+            st_chan<YT>(J.v + (int64_t)uj * J.vRB + (int64_t)ui * sizeof(YT), quant_yuv(__fdiv_rn(sv, n), J.rangeUV, J.biasUV, J.yuvMax));
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* standalone passes                                                                               */
+
+/* ref: src/alpha.c:9-149 */
+template <typename ST, typename DT>
+__global__ void __launch_bounds__(256) alpha_kernel(const __grid_constant__ AbAlphaJob J)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= J.width || j >= J.height) return;
+    uint8_t * d = J.dst + J.dstOff + (int64_t)j * J.dstRB + (int64_t)i * J.dstPix;
+    if (!J.src) {
+        st_chan<DT>(d, (J.dstDepth > 8) ? ((1u << J.dstDepth) - 1) : 255u);
+        return;
+    }
+    const uint32_t a = ld_sample<ST>(J.src + J.srcOff + (int64_t)j * J.srcRB + (int64_t)i * J.srcPix, 0);
+    if (J.srcDepth == J.dstDepth) {
+        st_chan<DT>(d, a);
+    } else {
+        const uint32_t srcMax = (1u << J.srcDepth) - 1, dstMax = (1u << J.dstDepth) - 1;
+        st_chan<DT>(d, alpha_rescale(a, (float)srcMax, (float)dstMax, dstMax));
+    }
+}
+
+/* ref: src/alpha.c:151-535, in place */
+template <typename RT>
+__global__ void __launch_bounds__(256) premultiply_kernel(const __grid_constant__ AbRgbPassJob J)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= J.width || j >= J.height) return;
+    RT * px = reinterpret_cast<RT *>(J.pixels + (int64_t)j * J.rowBytes) + (size_t)i * J.nChan;
+    const uint32_t max = (1u << J.depth) - 1;
+    const float maxF = (float)max;
+    const uint32_t a = px[J.aIdx];
+    if (a >= max) return;
+    for (int c = 0; c < J.nColor; ++c) {
+        RT * cp = px + J.cIdx[c];
+        *cp = (RT)alpha_int(*cp, a, max, maxF, J.unmultiply != 0);
+    }
+}
+
+/* ref: src/reformat.c:1419-1443, in place over width*channels samples per row */
+__global__ void __launch_bounds__(256) f16_kernel(const __grid_constant__ AbRgbPassJob J)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= J.width * J.nChan || j >= J.height) return;
+    uint16_t * p = reinterpret_cast<uint16_t *>(J.pixels + (int64_t)j * ((J.rowBytes >> 1) << 1)) + i;
+    *p = (uint16_t)to_f16_bits(*p, J.f16mul);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(T * dst, size_t count, T value)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dst[k] = value;
+}
+
+/* ref: src/read.c:6724-6764 */
+template <typename T>
+__global__ void __launch_bounds__(256) limited_to_full_kernel(uint8_t * plane, int64_t rowBytes, uint32_t width, uint32_t height, uint32_t depth)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= width || j >= height) return;
+    T * p = reinterpret_cast<T *>(plane + (int64_t)j * rowBytes) + i;
+    *p = (T)limited_to_full_y(depth, (int)*p);
+}
+
+/* plane copy with replicate padding of the right/bottom borders (ref: src/write.c:1151-1205) */
+template <typename T>
+__global__ void __launch_bounds__(256) copy_pad_kernel(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t srcH, uint8_t * dst, int64_t dstRB,
+                                                       uint32_t dstW, uint32_t dstH)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= dstW || j >= dstH) return;
+    const uint32_t si = min(i, srcW - 1), sj = min(j, srcH - 1);
+    reinterpret_cast<T *>(dst + (int64_t)j * dstRB)[i] = reinterpret_cast<const T *>(src + (int64_t)sj * srcRB)[si];
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* launch helpers                                                                                  */
+
+static inline int finish_launch()
+{
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+static inline dim3 grid2d(uint32_t w, uint32_t h, dim3 block) { return dim3((w + block.x - 1) / block.x, (h + block.y - 1) / block.y); }
+
+template <typename YT, typename RT>
+static int launch_y2r_typed(const AbY2RJob & J, cudaStream_t st, int forceGeneric, const char ** name)
+{
+    const uint32_t rows = J.rowEnd - J.rowBegin;
+    if (rows == 0 || J.width == 0) return 0;
+    if (forceGeneric) {
+        const dim3 block(64, 4);
+        y2r_generic_kernel<YT, RT><<<grid2d(J.width, rows, block), block, 0, st>>>(J);
+        if (name) *name = "y2r_generic";
+        return finish_launch();
+    }
+    const dim3 grid((J.width + kTilePx - 1) / kTilePx, (rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const dim3 block(kWarpsPerBlock * 32);
+    const bool plain = J.mode == AB_MODE_COEFF && J.alphaMul == AB_MUL_NONE && !J.toF16 && !J.is565 && !J.isGray;
+#define AB_LAUNCH(CH, PL, NAME)                                                \
+    do {                                                                       \
+        y2r_tiled_kernel<YT, RT, CH, PL><<<grid, block, 0, st>>>(J);           \
+        if (name) *name = NAME;                                                \
+    } while (0)
+    switch (J.chroma) {
+        case AB_CHROMA_FULL:
+            if (plain) AB_LAUNCH(AB_CHROMA_FULL, true, "y2r_tiled_444_plain");
+            else AB_LAUNCH(AB_CHROMA_FULL, false, "y2r_tiled_444_general");
+            break;
+        case AB_CHROMA_NEAREST:
+            if (plain) AB_LAUNCH(AB_CHROMA_NEAREST, true, "y2r_tiled_nearest_plain");
+            else AB_LAUNCH(AB_CHROMA_NEAREST, false, "y2r_tiled_nearest_general");
+            break;
+        case AB_CHROMA_BILINEAR:
+            if (plain) AB_LAUNCH(AB_CHROMA_BILINEAR, true, "y2r_tiled_bilinear_plain");
+            else AB_LAUNCH(AB_CHROMA_BILINEAR, false, "y2r_tiled_bilinear_general");
+            break;
+        default:
+            if (plain) AB_LAUNCH(AB_CHROMA_NONE, true, "y2r_tiled_mono_plain");
+            else AB_LAUNCH(AB_CHROMA_NONE, false, "y2r_tiled_mono_general");
+            break;
+    }
+#undef AB_LAUNCH
+    return finish_launch();
+}
+
+} // namespace ab
+
+using namespace ab;
+
+extern "C" {
+
+int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (job->yuvBytes == 2) {
+        return job->rgbBytes == 2 ? launch_y2r_typed<uint16_t, uint16_t>(*job, st, forceGeneric, kernelName)
+                                  : launch_y2r_typed<uint16_t, uint8_t>(*job, st, forceGeneric, kernelName);
+    }
+    return job->rgbBytes == 2 ? launch_y2r_typed<uint8_t, uint16_t>(*job, st, forceGeneric, kernelName)
+                              : launch_y2r_typed<uint8_t, uint8_t>(*job, st, forceGeneric, kernelName);
+}
+
+int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName)
+{
+    (void)forceGeneric;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (job->width == 0 || job->height == 0) return 0;
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d((job->width + 1) / 2, (job->height + 1) / 2, block);
+    if (job->rgbBytes == 2) {
+        if (job->yuvBytes == 2) r2y_block_kernel<uint16_t, uint16_t><<<grid, block, 0, st>>>(*job);
+        else r2y_block_kernel<uint16_t, uint8_t><<<grid, block, 0, st>>>(*job);
+    } else {
+        if (job->yuvBytes == 2) r2y_block_kernel<uint8_t, uint16_t><<<grid, block, 0, st>>>(*job);
+        else r2y_block_kernel<uint8_t, uint8_t><<<grid, block, 0, st>>>(*job);
+    }
+    if (kernelName) *kernelName = "r2y_block";
+    return finish_launch();
+}
+
+int abLaunchAlpha(const AbAlphaJob * job, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (job->width == 0 || job->height == 0) return 0;
+    const dim3 block(64, 4);
+    const dim3 grid = grid2d(job->width, job->height, block);
+    const bool s16 = job->src && job->srcDepth > 8, d16 = job->dstDepth > 8;
+    if (s16 && d16) alpha_kernel<uint16_t, uint16_t><<<grid, block, 0, st>>>(*job);
+    else if (s16) alpha_kernel<uint16_t, uint8_t><<<grid, block, 0, st>>>(*job);
+    else if (d16) alpha_kernel<uint8_t, uint16_t><<<grid, block, 0, st>>>(*job);
+    else alpha_kernel<uint8_t, uint8_t><<<grid, block, 0, st>>>(*job);
+    return finish_launch();
+}
+
+int abLaunchPremultiply(const AbRgbPassJob * job, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (job->width == 0 || job->height == 0) return 0;
+    const dim3 block(64, 4);
+    const dim3 grid = grid2d(job->width, job->height, block);
+    if (job->depth > 8) premultiply_kernel<uint16_t><<<grid, block, 0, st>>>(*job);
+    else premultiply_kernel<uint8_t><<<grid, block, 0, st>>>(*job);
+    return finish_launch();
+}
+
+int abLaunchToF16(const AbRgbPassJob * job, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (job->width == 0 || job->height == 0) return 0;
+    const dim3 block(64, 4);
+    f16_kernel<<<grid2d(job->width * job->nChan, job->height, block), block, 0, st>>>(*job);
+    return finish_launch();
+}
+
+int abLaunchFill16(uint8_t * dst, size_t count16, uint32_t value, void * stream)
+{
+    if (count16 == 0) return 0;
+    fill_kernel<uint16_t><<<(unsigned)((count16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint16_t *>(dst), count16, (uint16_t)value);
+    return finish_launch();
+}
+
+int abLaunchFill8(uint8_t * dst, size_t count, uint32_t value, void * stream)
+{
+    if (count == 0) return 0;
+    fill_kernel<uint8_t><<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, count, (uint8_t)value);
+    return finish_launch();
+}
+
+int abLaunchLimitedToFull(uint8_t * plane, int64_t rowBytes, uint32_t width, uint32_t height, uint32_t depth, void * stream)
+{
+    if (width == 0 || height == 0) return 0;
+    const dim3 block(64, 4);
+    const dim3 grid = grid2d(width, height, block);
+    if (depth > 8) limited_to_full_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)stream>>>(plane, rowBytes, width, height, depth);
+    else limited_to_full_kernel<uint8_t><<<grid, block, 0, (cudaStream_t)stream>>>(plane, rowBytes, width, height, depth);
+    return finish_launch();
+}
+
+int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t srcH, uint8_t * dst, int64_t dstRB, uint32_t dstW,
+                    uint32_t dstH, uint32_t bytesPerSample, void * stream)
+{
+    if (dstW == 0 || dstH == 0 || srcW == 0 || srcH == 0) return 0;
+    const dim3 block(64, 4);
+    const dim3 grid = grid2d(dstW, dstH, block);
+    if (bytesPerSample == 2) copy_pad_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)stream>>>(src, srcRB, srcW, srcH, dst, dstRB, dstW, dstH);
+    else copy_pad_kernel<uint8_t><<<grid, block, 0, (cudaStream_t)stream>>>(src, srcRB, srcW, srcH, dst, dstRB, dstW, dstH);
+    return finish_launch();
+}
+
+uint64_t abLaunchCount(void) { return g_launches; }
+void abLaunchCountReset(void) { g_launches = 0; }
+
+} // extern "C"

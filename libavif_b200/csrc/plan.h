@@ -1,0 +1,134 @@
+/*
+ * plan.h -- plain-data job descriptors handed from the host shim (shim.c, C) to the CUDA launchers
+ * (kernels.cu).  A descriptor holds DEVICE pointers only and every constant the per-pixel arithmetic
+ * needs, derived on the host exactly as the reference derives them (float, one rounding per operator).
+ *
+ * Which reference variant a call must mirror (fast loop + integer post-pass vs. the general loop with
+ * in-float alpha) is decided on the host and encoded in `alphaMul`/`mode`/`chroma`;
+ * the kernels never re-derive policy.
+ */
+#ifndef AVIF_B200_PLAN_H
+#define AVIF_B200_PLAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AB_MODE_COEFF = 0, AB_MODE_IDENTITY = 1, AB_MODE_YCGCO = 2, AB_MODE_YCGCO_R = 3, AB_MODE_IDENTITY8_SHUFFLE = 4 };
+enum { AB_CHROMA_NONE = 0, AB_CHROMA_FULL = 1, AB_CHROMA_NEAREST = 2, AB_CHROMA_BILINEAR = 3 };
+enum { AB_ALPHA_KEEP = 0, AB_ALPHA_COPY = 1, AB_ALPHA_FILL = 2 };
+/* alpha (un)multiply flavours: the reference does it either in normalised float inside the general loop
+ * (reformat.c:894-947) or as an integer-domain post-pass on the quantised pixels (alpha.c:151-535). */
+enum { AB_MUL_NONE = 0, AB_MUL_FLOAT_MUL = 1, AB_MUL_FLOAT_UNMUL = 2, AB_MUL_INT_PREMUL = 3, AB_MUL_INT_UNPREMUL = 4 };
+
+/* Exact division by a call-constant divisor d:  q = x*r; e = fma(-q,d,x); q' = fma(e,r,q) with r = RN(1/d).
+ * `exact` is set by the host only for divisors whose (x,d) domain has been verified exhaustively to give the
+ * IEEE-754 correctly rounded quotient (tests/test_division.py); otherwise the kernels use __fdiv_rn. */
+typedef struct AbDiv {
+    float d;   /* divisor */
+    float r;   /* RN(1/d) */
+    int exact; /* 1: the 3-op sequence is proven == x/d on this call's domain */
+    int pad;
+} AbDiv;
+
+typedef struct AbY2RJob {
+    const uint8_t * y;
+    const uint8_t * u;
+    const uint8_t * v;
+    const uint8_t * a; /* source alpha plane (may be NULL) */
+    uint8_t * rgb;
+    int64_t yRB, uRB, vRB, aRB, rgbRB; /* row strides in bytes */
+    uint32_t width, height;            /* extent of the colour loop (image dims) */
+    uint32_t rowBegin, rowEnd;         /* rows [rowBegin,rowEnd) are converted by this launch (band pipelining) */
+    uint32_t yuvMax, rgbMax;
+    float yuvMaxF, rgbMaxF;
+    float biasY, biasUV;
+    AbDiv rangeY, rangeUV; /* identity mode: UV uses Y's bias/range (reformat.c:587-589) */
+    AbDiv kg;
+    float c1, c2, c3, c4; /* 2(1-kr), 2(1-kb), kr(1-kr), kb(1-kb) as float constants (reformat.c:1014-1016) */
+    float f16mul;         /* 2^-112 * (1/65535)  (reformat.c:1429-1430) */
+    uint8_t yuvBytes, rgbBytes; /* bytes per sample / per channel */
+    uint8_t chroma;             /* AB_CHROMA_* */
+    uint8_t vertBlend;          /* bilinear also blends rows (4:2:0); 0 for 4:2:2 */
+    uint8_t shiftX, shiftY;
+    uint8_t mode;       /* AB_MODE_* */
+    uint8_t rgbFormat;  /* avifRGBFormat */
+    uint8_t pixBytes, offR, offG, offB, offA, offGray;
+    uint8_t nChan;      /* channels per pixel (565 counts as 1 x u16) */
+    uint8_t isGray, is565, hasAlphaChan;
+    uint8_t alphaWrite; /* AB_ALPHA_* : what lands in the RGB alpha channel */
+    uint8_t alphaRescale; /* 1: source alpha depth != rgb depth -> float rescale (alpha.c:93-97) */
+    uint8_t alphaMul;   /* AB_MUL_* */
+    uint8_t toF16;
+} AbY2RJob;
+
+typedef struct AbR2YJob {
+    const uint8_t * rgb;
+    uint8_t * y;
+    uint8_t * u;
+    uint8_t * v;
+    uint8_t * a; /* destination alpha plane (may be NULL) */
+    int64_t rgbRB, yRB, uRB, vRB, aRB;
+    uint32_t width, height;
+    uint32_t yuvMax, rgbMax;
+    float yuvMaxF, rgbMaxF;
+    float biasY, biasUV, rangeY, rangeUV; /* identity: UV quantised with Y's (reformat.c:212-213) */
+    float rangeYdiv, rangeUVdiv;          /* divisors of the YCgCo-R branch: always the true Y / UV ranges (reformat.c:379-381) */
+    float kr, kg, kb;
+    float du, dv; /* 2(1-kb), 2(1-kr) */
+    uint8_t rgbBytes, yuvBytes;
+    uint8_t shiftX, shiftY; /* chroma subsampling of the destination; both 0 for 4:4:4 */
+    uint8_t hasChroma;      /* 0 for 4:0:0 */
+    uint8_t mode;
+    uint8_t pixBytes, offR, offG, offB, offA, offGray;
+    uint8_t isGray;
+    uint8_t alphaMul;   /* AB_MUL_NONE / FLOAT_MUL / FLOAT_UNMUL */
+    uint8_t alphaWrite; /* AB_ALPHA_KEEP (no plane) / COPY (from RGB alpha) / FILL */
+    uint8_t alphaRescale;
+} AbR2YJob;
+
+/* avifAlphaParams with device pointers (alpha.c:9-149) */
+typedef struct AbAlphaJob {
+    const uint8_t * src; /* NULL: fill opaque */
+    uint8_t * dst;
+    int64_t srcRB, dstRB;
+    uint32_t width, height;
+    uint32_t srcDepth, dstDepth;
+    uint32_t srcOff, srcPix, dstOff, dstPix;
+} AbAlphaJob;
+
+/* in-place passes over an interleaved RGB(A) buffer */
+typedef struct AbRgbPassJob {
+    uint8_t * pixels;
+    int64_t rowBytes;
+    uint32_t width, height;
+    uint32_t depth;
+    uint8_t aIdx, nColor, nChan; /* channel indices, alpha.c:173-333 */
+    uint8_t cIdx[3];
+    uint8_t unmultiply;
+    float f16mul;
+} AbRgbPassJob;
+
+/* Launchers (kernels.cu).  `stream` is a cudaStream_t.  Return 0 on success, else a cudaError_t value.
+ * `forceGeneric` selects the byte-addressed reference kernel instead of the tiled/vectorised one. */
+int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName);
+int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName);
+int abLaunchAlpha(const AbAlphaJob * job, void * stream);
+int abLaunchPremultiply(const AbRgbPassJob * job, void * stream);
+int abLaunchToF16(const AbRgbPassJob * job, void * stream);
+int abLaunchFill16(uint8_t * dst, size_t count16, uint32_t value, void * stream); /* avifMemset16, reformat.c:17-23 */
+int abLaunchFill8(uint8_t * dst, size_t count, uint32_t value, void * stream);
+int abLaunchLimitedToFull(uint8_t * plane, int64_t rowBytes, uint32_t width, uint32_t height, uint32_t depth, void * stream);
+int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t srcH, uint8_t * dst, int64_t dstRB, uint32_t dstW,
+                    uint32_t dstH, uint32_t bytesPerSample, void * stream);
+/* number of kernel launches issued by the calling thread through the functions above */
+uint64_t abLaunchCount(void);
+void abLaunchCountReset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

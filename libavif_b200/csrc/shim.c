@@ -1,0 +1,1022 @@
+/*
+ * shim.c -- host side of the B200 reformat path: the reference's public entry points (same names, argument
+ * meaning, result codes) implemented as validation + constant derivation + variant classification on the
+ * CPU, and fused CUDA kernels (kernels.cu) for every byte of pixel work.  Plain C, like the reference.
+ *
+ * Host logic mirrored here (file:line in the reference tree):
+ *   avifPrepareReformatState / avifGet{RGB,YUV}ColorSpaceInfo   src/reformat.c:32-194
+ *   avifCalcYUVCoefficients, avifColorPrimariesComputeYCoeffs   src/colr.c:137-186, :517-542
+ *   avifImageYUVToRGB / avifImageYUVToRGBImpl control flow      src/reformat.c:1445-1593, :1649-1748
+ *   avifImageRGBToYUV control flow                              src/reformat.c:221-273, :545-569
+ *   avifImageAllocatePlanes, avifRGBImage helpers               src/avif.c:431-489, :670-741
+ *
+ * Plane / pixel pointers may be host or device memory (classified through UVA).  Host data is staged into a
+ * per-thread device arena with 256-byte aligned pitches; there is NO CPU fallback for the pixel work.
+ */
+#define AVIF_B200_BUILDING
+#include "avif_b200.h"
+
+#include <cuda_runtime_api.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "plan.h"
+
+#define AB_VERSION "libavif_b200 0.1 (sm_100a)"
+
+/* ------------------------------------------------------------------------------------------ */
+/* small host helpers (src/avif.c)                                                             */
+
+avifBool avifRGBFormatIsGray(avifRGBFormat f)
+{
+    return f == AVIF_RGB_FORMAT_GRAY || f == AVIF_RGB_FORMAT_GRAYA || f == AVIF_RGB_FORMAT_AGRAY;
+}
+avifBool avifRGBFormatHasAlpha(avifRGBFormat f)
+{
+    return f != AVIF_RGB_FORMAT_RGB && f != AVIF_RGB_FORMAT_BGR && f != AVIF_RGB_FORMAT_RGB_565 && f != AVIF_RGB_FORMAT_GRAY;
+}
+uint32_t avifRGBFormatChannelCount(avifRGBFormat f)
+{
+    if (f == AVIF_RGB_FORMAT_GRAY) return 1;
+    if (f == AVIF_RGB_FORMAT_GRAYA || f == AVIF_RGB_FORMAT_AGRAY) return 2;
+    return avifRGBFormatHasAlpha(f) ? 4 : 3;
+}
+uint32_t avifRGBImagePixelSize(const avifRGBImage * rgb)
+{
+    if (rgb->format == AVIF_RGB_FORMAT_RGB_565) return 2;
+    return avifRGBFormatChannelCount(rgb->format) * ((rgb->depth > 8) ? 2 : 1);
+}
+void avifRGBImageSetDefaults(avifRGBImage * rgb, const avifImage * image)
+{
+    rgb->width = image->width;
+    rgb->height = image->height;
+    rgb->depth = image->depth;
+    rgb->format = AVIF_RGB_FORMAT_RGBA;
+    rgb->chromaUpsampling = AVIF_CHROMA_UPSAMPLING_AUTOMATIC;
+    rgb->chromaDownsampling = AVIF_CHROMA_DOWNSAMPLING_AUTOMATIC;
+    rgb->avoidLibYUV = AVIF_FALSE;
+    rgb->ignoreAlpha = AVIF_FALSE;
+    rgb->alphaPremultiplied = AVIF_FALSE;
+    rgb->isFloat = AVIF_FALSE;
+    rgb->maxThreads = 1;
+    rgb->pixels = NULL;
+    rgb->rowBytes = 0;
+}
+void avifRGBImageFreePixels(avifRGBImage * rgb)
+{
+    free(rgb->pixels); /* avifFree == free (src/mem.c) */
+    rgb->pixels = NULL;
+    rgb->rowBytes = 0;
+}
+avifResult avifRGBImageAllocatePixels(avifRGBImage * rgb)
+{
+    avifRGBImageFreePixels(rgb);
+    if (rgb->width == 0 || rgb->height == 0) return AVIF_RESULT_INVALID_ARGUMENT;
+    const uint32_t pixelSize = avifRGBImagePixelSize(rgb);
+    if (rgb->width > UINT32_MAX / pixelSize) return AVIF_RESULT_INVALID_ARGUMENT;
+    const uint32_t rowBytes = rgb->width * pixelSize;
+    if (rgb->height > PTRDIFF_MAX / rowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
+    rgb->pixels = (uint8_t *)malloc((size_t)rowBytes * rgb->height);
+    if (!rgb->pixels) return AVIF_RESULT_OUT_OF_MEMORY;
+    rgb->rowBytes = rowBytes;
+    return AVIF_RESULT_OK;
+}
+void avifGetPixelFormatInfo(avifPixelFormat format, avifPixelFormatInfo * info)
+{
+    memset(info, 0, sizeof(*info));
+    switch (format) {
+        case AVIF_PIXEL_FORMAT_YUV422: info->chromaShiftX = 1; break;
+        case AVIF_PIXEL_FORMAT_YUV420: info->chromaShiftX = 1; info->chromaShiftY = 1; break;
+        case AVIF_PIXEL_FORMAT_YUV400: info->monochrome = AVIF_TRUE; info->chromaShiftX = 1; info->chromaShiftY = 1; break;
+        default: break;
+    }
+}
+unsigned int avifLibYUVVersion(void) { return 0; }
+
+/* limited <-> full integer helpers (src/reformat.c:1750-1840): scalar host API, also run per-sample on the
+ * device by avifB200ImageLimitedToFullAlpha */
+static int rangeRow(uint32_t depth, int uv, int * lo, int * hi, int * full)
+{
+    switch (depth) {
+        case 8: *lo = 16; *hi = uv ? 240 : 235; *full = 255; return 1;
+        case 10: *lo = 64; *hi = uv ? 960 : 940; *full = 1023; return 1;
+        case 12: *lo = 256; *hi = uv ? 3840 : 3760; *full = 4095; return 1;
+        default: return 0;
+    }
+}
+static int limToFull(uint32_t depth, int uv, int v)
+{
+    int lo, hi, full;
+    if (!rangeRow(depth, uv, &lo, &hi, &full)) return v;
+    v = (((v - lo) * full) + ((hi - lo) / 2)) / (hi - lo);
+    return v < 0 ? 0 : (v > full ? full : v);
+}
+static int fullToLim(uint32_t depth, int uv, int v)
+{
+    int lo, hi, full;
+    if (!rangeRow(depth, uv, &lo, &hi, &full)) return v;
+    v = (((v * (hi - lo)) + (full / 2)) / full) + lo;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+int avifLimitedToFullY(uint32_t depth, int v) { return limToFull(depth, 0, v); }
+int avifLimitedToFullUV(uint32_t depth, int v) { return limToFull(depth, 1, v); }
+int avifFullToLimitedY(uint32_t depth, int v) { return fullToLim(depth, 0, v); }
+int avifFullToLimitedUV(uint32_t depth, int v) { return fullToLim(depth, 1, v); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* per-thread CUDA context: stream + staging arena                                             */
+
+typedef struct AbCtx {
+    int ready;
+    cudaStream_t stream;
+    uint8_t * arena;
+    size_t arenaCap;
+    int policy; /* 0 auto, 1 force generic kernels */
+    const char * lastKernel;
+} AbCtx;
+static _Thread_local AbCtx tls;
+
+static avifResult cudaToResult(int err)
+{
+    if (err == cudaSuccess) return AVIF_RESULT_OK;
+    (void)cudaGetLastError();
+    return (err == cudaErrorMemoryAllocation) ? AVIF_RESULT_OUT_OF_MEMORY : AVIF_RESULT_UNKNOWN_ERROR;
+}
+#define AB_CUDA(call)                                      \
+    do {                                                   \
+        const int abErr_ = (int)(call);                    \
+        if (abErr_ != cudaSuccess) return cudaToResult(abErr_); \
+    } while (0)
+
+int avifB200DeviceAvailable(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n > 0;
+}
+const char * avifB200Version(void) { return AB_VERSION; }
+void avifB200SetKernelPolicy(int policy) { tls.policy = policy; }
+uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
+void avifB200ResetKernelLaunchCount(void) { abLaunchCountReset(); }
+const char * avifB200LastKernelName(void) { return tls.lastKernel ? tls.lastKernel : ""; }
+
+void * avifB200AllocPinned(size_t size)
+{
+    void * p = NULL;
+    if (cudaHostAlloc(&p, size, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return NULL;
+    }
+    return p;
+}
+void avifB200FreePinned(void * p)
+{
+    if (p) (void)cudaFreeHost(p);
+}
+
+static avifResult ctxInit(void)
+{
+    if (tls.ready) return AVIF_RESULT_OK;
+    if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR; /* no CPU fallback by design */
+    AB_CUDA(cudaStreamCreateWithFlags(&tls.stream, cudaStreamNonBlocking));
+    tls.ready = 1;
+    return AVIF_RESULT_OK;
+}
+
+/* grow-only device arena; contents are dead between calls */
+static avifResult arenaReserve(size_t bytes)
+{
+    if (bytes <= tls.arenaCap) return AVIF_RESULT_OK;
+    if (tls.arena) {
+        AB_CUDA(cudaStreamSynchronize(tls.stream));
+        AB_CUDA(cudaFree(tls.arena));
+        tls.arena = NULL;
+        tls.arenaCap = 0;
+    }
+    const size_t cap = bytes + (bytes >> 3) + (1u << 20);
+    AB_CUDA(cudaMalloc((void **)&tls.arena, cap));
+    tls.arenaCap = cap;
+    return AVIF_RESULT_OK;
+}
+
+static int ptrOnDevice(const void * p)
+{
+    struct cudaPointerAttributes at;
+    if (!p) return 0;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+/* One 2-D byte region that must be visible to a kernel.  Host regions get a slot in the arena. */
+typedef struct AbRegion {
+    uint8_t * user;     /* caller's pointer (host or device) */
+    int64_t userRB;     /* caller's row stride */
+    size_t rowUsed;     /* bytes per row the path touches */
+    uint32_t rows;
+    int onDevice;
+    uint8_t * dev;      /* pointer the kernel uses */
+    int64_t devRB;
+    int present;
+    int exactPitch;     /* keep the caller's pitch and copy rows*pitch as one block (gray chroma fill) */
+} AbRegion;
+
+static void regionInit(AbRegion * r, const void * user, int64_t rb, size_t rowUsed, uint32_t rows, int assumeDevice)
+{
+    memset(r, 0, sizeof(*r));
+    if (!user) return;
+    r->present = 1;
+    r->user = (uint8_t *)user;
+    r->userRB = rb;
+    r->rowUsed = rowUsed;
+    r->rows = rows;
+    r->onDevice = assumeDevice ? 1 : ptrOnDevice(user);
+}
+
+static size_t regionArenaBytes(const AbRegion * r)
+{
+    if (!r->present || r->onDevice) return 0;
+    if (r->exactPitch) return alignUp((size_t)r->userRB * r->rows, 256);
+    return alignUp(r->rowUsed, 256) * r->rows;
+}
+
+static void regionPlace(AbRegion * r, uint8_t ** cursor)
+{
+    if (!r->present) return;
+    if (r->onDevice) {
+        r->dev = r->user;
+        r->devRB = r->userRB;
+        return;
+    }
+    r->dev = *cursor;
+    r->devRB = r->exactPitch ? r->userRB : (int64_t)alignUp(r->rowUsed, 256);
+    *cursor += regionArenaBytes(r);
+}
+
+static int regionUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
+{
+    if (!r->present || r->onDevice || row1 <= row0) return cudaSuccess;
+    if (r->userRB == 0 || r->rowUsed == 0) { /* stride-0 plane (every row aliases row 0): upload the single row */
+        return (int)cudaMemcpyAsync(r->dev, r->user, r->rowUsed, cudaMemcpyHostToDevice, st);
+    }
+    return (int)cudaMemcpy2DAsync(r->dev + (int64_t)row0 * r->devRB, (size_t)r->devRB, r->user + (int64_t)row0 * r->userRB, (size_t)r->userRB,
+                                  r->rowUsed, row1 - row0, cudaMemcpyHostToDevice, st);
+}
+
+static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
+{
+    if (!r->present || r->onDevice || row1 <= row0) return cudaSuccess;
+    if (r->exactPitch) {
+        return (int)cudaMemcpyAsync(r->user + (int64_t)row0 * r->userRB, r->dev + (int64_t)row0 * r->devRB, (size_t)r->userRB * (row1 - row0),
+                                    cudaMemcpyDeviceToHost, st);
+    }
+    return (int)cudaMemcpy2DAsync(r->user + (int64_t)row0 * r->userRB, (size_t)r->userRB, r->dev + (int64_t)row0 * r->devRB, (size_t)r->devRB,
+                                  r->rowUsed, row1 - row0, cudaMemcpyDeviceToHost, st);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* reformat state (src/reformat.c:32-194)                                                      */
+
+typedef struct AbState {
+    /* rgb */
+    uint32_t rgbChanBytes, rgbPixBytes, offR, offG, offB, offA, offGray;
+    int rgbMax;
+    float rgbMaxF;
+    /* yuv */
+    float kr, kg, kb;
+    uint32_t yuvChanBytes;
+    int yuvMax;
+    float biasY, biasUV, rangeY, rangeUV;
+    int shiftX, shiftY;
+    int mode; /* AB_MODE_COEFF / IDENTITY / YCGCO / YCGCO_R */
+} AbState;
+
+/* H.273 eq. 32-37 in float, same association as src/colr.c:517-542 */
+static void chromaDerivedKrKb(avifColorPrimaries cp, float * outKr, float * outKb)
+{
+    static const struct {
+        uint16_t id;
+        float v[8]; /* rX rY gX gY bX bY wX wY (src/colr.c:16-28) */
+    } table[] = {
+        { AVIF_COLOR_PRIMARIES_BT709, { 0.64f, 0.33f, 0.3f, 0.6f, 0.15f, 0.06f, 0.3127f, 0.329f } },
+        { AVIF_COLOR_PRIMARIES_BT470M, { 0.67f, 0.33f, 0.21f, 0.71f, 0.14f, 0.08f, 0.310f, 0.316f } },
+        { AVIF_COLOR_PRIMARIES_BT470BG, { 0.64f, 0.33f, 0.29f, 0.60f, 0.15f, 0.06f, 0.3127f, 0.3290f } },
+        { AVIF_COLOR_PRIMARIES_BT601, { 0.630f, 0.340f, 0.310f, 0.595f, 0.155f, 0.070f, 0.3127f, 0.3290f } },
+        { AVIF_COLOR_PRIMARIES_SMPTE240, { 0.630f, 0.340f, 0.310f, 0.595f, 0.155f, 0.070f, 0.3127f, 0.3290f } },
+        { AVIF_COLOR_PRIMARIES_GENERIC_FILM, { 0.681f, 0.319f, 0.243f, 0.692f, 0.145f, 0.049f, 0.310f, 0.316f } },
+        { AVIF_COLOR_PRIMARIES_BT2020, { 0.708f, 0.292f, 0.170f, 0.797f, 0.131f, 0.046f, 0.3127f, 0.3290f } },
+        { AVIF_COLOR_PRIMARIES_XYZ, { 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.3333f, 0.3333f } },
+        { AVIF_COLOR_PRIMARIES_SMPTE431, { 0.680f, 0.320f, 0.265f, 0.690f, 0.150f, 0.060f, 0.314f, 0.351f } },
+        { AVIF_COLOR_PRIMARIES_SMPTE432, { 0.680f, 0.320f, 0.265f, 0.690f, 0.150f, 0.060f, 0.3127f, 0.3290f } },
+        { AVIF_COLOR_PRIMARIES_EBU3213, { 0.630f, 0.340f, 0.295f, 0.605f, 0.155f, 0.077f, 0.3127f, 0.3290f } },
+    };
+    const float * v = table[0].v; /* unknown -> BT.709 primaries (src/colr.c:41-42) */
+    for (size_t k = 0; k < sizeof(table) / sizeof(table[0]); ++k) {
+        if (table[k].id == cp) {
+            v = table[k].v;
+            break;
+        }
+    }
+    const float rX = v[0], rY = v[1], gX = v[2], gY = v[3], bX = v[4], bY = v[5], wX = v[6], wY = v[7];
+    const float rZ = 1.0f - (rX + rY), gZ = 1.0f - (gX + gY), bZ = 1.0f - (bX + bY), wZ = 1.0f - (wX + wY);
+    const float denom = wY * (rX * (gY * bZ - bY * gZ) + gX * (bY * rZ - rY * bZ) + bX * (rY * gZ - gY * rZ));
+    *outKr = (rY * (wX * (gY * bZ - bY * gZ) + wY * (bX * gZ - gX * bZ) + wZ * (gX * bY - bX * gY))) / denom;
+    *outKb = (bY * (wX * (rY * gZ - gY * rZ) + wY * (gX * rZ - rX * gZ) + wZ * (rX * gY - gX * rY))) / denom;
+}
+
+static void calcCoefficients(const avifImage * image, float * kr, float * kg, float * kb)
+{
+    float r = 0.299f, b = 0.114f; /* unspecified / unknown MC -> BT.601 (src/colr.c:173-175) */
+    switch (image->matrixCoefficients) {
+        case AVIF_MATRIX_COEFFICIENTS_BT709: r = 0.2126f; b = 0.0722f; break;
+        case AVIF_MATRIX_COEFFICIENTS_FCC: r = 0.30f; b = 0.11f; break;
+        case AVIF_MATRIX_COEFFICIENTS_SMPTE240: r = 0.212f; b = 0.087f; break;
+        case AVIF_MATRIX_COEFFICIENTS_BT2020_NCL: r = 0.2627f; b = 0.0593f; break;
+        case AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_NCL: chromaDerivedKrKb(image->colorPrimaries, &r, &b); break;
+        default: break; /* BT.470BG, BT.601 and everything else: BT.601 numbers */
+    }
+    *kr = r;
+    *kb = b;
+    *kg = 1.0f - r - b;
+}
+
+static int prepareState(const avifImage * image, const avifRGBImage * rgb, AbState * s)
+{
+    const unsigned mc = image->matrixCoefficients;
+    if (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE && image->depth - 2 != rgb->depth) return 0;
+    if (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO && image->depth - 1 != rgb->depth) return 0;
+
+    if (rgb->depth != 8 && rgb->depth != 10 && rgb->depth != 12 && rgb->depth != 16) return 0;
+    if (rgb->isFloat && rgb->depth != 16) return 0;
+    if (rgb->format == AVIF_RGB_FORMAT_RGB_565 && rgb->depth != 8) return 0;
+    if ((int)rgb->format < AVIF_RGB_FORMAT_RGB || rgb->format >= AVIF_RGB_FORMAT_COUNT) return 0;
+
+    const uint32_t cb = (rgb->depth > 8) ? 2 : 1;
+    s->rgbChanBytes = cb;
+    s->rgbPixBytes = avifRGBImagePixelSize(rgb);
+    s->offR = s->offG = s->offB = s->offA = s->offGray = 0;
+    /* channel order as byte offsets (src/reformat.c:53-111) */
+    static const int8_t order[AVIF_RGB_FORMAT_COUNT][5] = {
+        /*            R   G   B   A  Gray */
+        /* RGB   */ { 0, 1, 2, -1, -1 },
+        /* RGBA  */ { 0, 1, 2, 3, -1 },
+        /* ARGB  */ { 1, 2, 3, 0, -1 },
+        /* BGR   */ { 2, 1, 0, -1, -1 },
+        /* BGRA  */ { 2, 1, 0, 3, -1 },
+        /* ABGR  */ { 3, 2, 1, 0, -1 },
+        /* 565   */ { 0, 0, 0, -1, -1 },
+        /* GRAY  */ { -1, -1, -1, -1, 0 },
+        /* GRAYA */ { -1, -1, -1, 1, 0 },
+        /* AGRAY */ { -1, -1, -1, 0, 1 },
+    };
+    const int8_t * o = order[rgb->format];
+    if (o[0] > 0) s->offR = (uint32_t)o[0] * cb;
+    if (o[1] > 0) s->offG = (uint32_t)o[1] * cb;
+    if (o[2] > 0) s->offB = (uint32_t)o[2] * cb;
+    if (o[3] > 0) s->offA = (uint32_t)o[3] * cb;
+    if (o[4] > 0) s->offGray = (uint32_t)o[4] * cb;
+    s->rgbMax = (1 << rgb->depth) - 1;
+    s->rgbMaxF = (float)s->rgbMax;
+
+    if (image->depth != 8 && image->depth != 10 && image->depth != 12 && image->depth != 16) return 0;
+    if (image->yuvFormat < AVIF_PIXEL_FORMAT_YUV444 || image->yuvFormat >= AVIF_PIXEL_FORMAT_COUNT) return 0;
+    if (image->yuvRange != AVIF_RANGE_LIMITED && image->yuvRange != AVIF_RANGE_FULL) return 0;
+    const int ycgcoFamily = (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO);
+    if (mc == 3 || (ycgcoFamily && image->yuvRange == AVIF_RANGE_LIMITED) || mc == AVIF_MATRIX_COEFFICIENTS_BT2020_CL ||
+        mc == AVIF_MATRIX_COEFFICIENTS_SMPTE2085 || mc == AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_CL || mc == AVIF_MATRIX_COEFFICIENTS_ICTCP ||
+        mc >= AVIF_MATRIX_COEFFICIENTS_LAST) {
+        return 0;
+    }
+    if (mc == AVIF_MATRIX_COEFFICIENTS_IDENTITY && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV444 && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV400) {
+        return 0;
+    }
+    avifPixelFormatInfo fi;
+    avifGetPixelFormatInfo(image->yuvFormat, &fi);
+    s->shiftX = fi.chromaShiftX;
+    s->shiftY = fi.chromaShiftY;
+    calcCoefficients(image, &s->kr, &s->kg, &s->kb);
+    s->yuvChanBytes = (image->depth > 8) ? 2 : 1;
+    s->yuvMax = (1 << image->depth) - 1;
+    const int limited = (image->yuvRange == AVIF_RANGE_LIMITED);
+    s->biasY = limited ? (float)(16 << (image->depth - 8)) : 0.0f;
+    s->biasUV = (float)(1 << (image->depth - 1));
+    s->rangeY = (float)(limited ? (219 << (image->depth - 8)) : s->yuvMax);
+    s->rangeUV = (float)(limited ? (224 << (image->depth - 8)) : s->yuvMax);
+
+    s->mode = AB_MODE_COEFF;
+    if (mc == AVIF_MATRIX_COEFFICIENTS_IDENTITY) s->mode = AB_MODE_IDENTITY;
+    else if (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO) s->mode = AB_MODE_YCGCO;
+    else if (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO) s->mode = AB_MODE_YCGCO_R;
+    if (s->mode != AB_MODE_COEFF) s->kr = s->kg = s->kb = 0.0f;
+    return 1;
+}
+
+static AbDiv makeDiv(float d)
+{
+    AbDiv v;
+    v.d = d;
+    v.r = 1.0f / d;
+    v.exact = 0; /* enabled per divisor once verified: see abDivisorVerified() */
+    v.pad = 0;
+    return v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* in-place RGB passes (premultiply / unpremultiply / F16)                                      */
+
+static int premulLayout(avifRGBFormat f, AbRgbPassJob * job)
+{
+    switch (f) {
+        case AVIF_RGB_FORMAT_RGBA:
+        case AVIF_RGB_FORMAT_BGRA: job->aIdx = 3; job->cIdx[0] = 0; job->cIdx[1] = 1; job->cIdx[2] = 2; job->nColor = 3; job->nChan = 4; return 1;
+        case AVIF_RGB_FORMAT_ARGB:
+        case AVIF_RGB_FORMAT_ABGR: job->aIdx = 0; job->cIdx[0] = 1; job->cIdx[1] = 2; job->cIdx[2] = 3; job->nColor = 3; job->nChan = 4; return 1;
+        case AVIF_RGB_FORMAT_GRAYA: job->aIdx = 1; job->cIdx[0] = 0; job->nColor = 1; job->nChan = 2; return 1;
+        case AVIF_RGB_FORMAT_AGRAY: job->aIdx = 0; job->cIdx[0] = 1; job->nColor = 1; job->nChan = 2; return 1;
+        default: return 0;
+    }
+}
+
+static float f16Multiplier(uint32_t depth)
+{
+    const float scale = 1.0f / ((1 << depth) - 1); /* src/reformat.c:1429-1430 */
+    return 1.9259299444e-34f * scale;
+}
+
+/* src/alpha.c:151-336 / :338-535 */
+static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * userStream, int async)
+{
+    if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_REFORMAT_FAILED;
+    if (!avifRGBFormatHasAlpha(rgb->format)) return unmultiply ? AVIF_RESULT_REFORMAT_FAILED : AVIF_RESULT_INVALID_ARGUMENT;
+    AbRgbPassJob job;
+    memset(&job, 0, sizeof(job));
+    if (!premulLayout(rgb->format, &job)) return AVIF_RESULT_NOT_IMPLEMENTED;
+    if (rgb->depth < 8 || rgb->depth > 16) return AVIF_RESULT_REFORMAT_FAILED; /* the reference asserts */
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+
+    AbRegion px;
+    regionInit(&px, rgb->pixels, rgb->rowBytes, (size_t)rgb->width * avifRGBImagePixelSize(rgb), rgb->height, async);
+    if (!async) {
+        res = arenaReserve(regionArenaBytes(&px));
+        if (res != AVIF_RESULT_OK) return res;
+    }
+    uint8_t * cursor = tls.arena;
+    regionPlace(&px, &cursor);
+    AB_CUDA(regionUpload(&px, 0, px.rows, st));
+    job.pixels = px.dev;
+    job.rowBytes = px.devRB;
+    job.width = rgb->width;
+    job.height = rgb->height;
+    job.depth = rgb->depth;
+    job.unmultiply = (uint8_t)unmultiply;
+    AB_CUDA(abLaunchPremultiply(&job, st));
+    tls.lastKernel = unmultiply ? "unpremultiply" : "premultiply";
+    AB_CUDA(regionDownload(&px, 0, px.rows, st));
+    if (!async) AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifRGBImagePremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 0, NULL, 0); }
+avifResult avifRGBImageUnpremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 1, NULL, 0); }
+avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 0, stream, 1); }
+avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 1, stream, 1); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* alpha plane <-> channel (src/alpha.c:9-149); void like the reference: failures cannot be reported */
+
+static void alphaCommon(const avifAlphaParams * p, int fill)
+{
+    if (ctxInit() != AVIF_RESULT_OK || p->width == 0 || p->height == 0) return;
+    cudaStream_t st = tls.stream;
+    const uint32_t dcb = (p->dstDepth > 8) ? 2 : 1, scb = (p->srcDepth > 8) ? 2 : 1;
+    AbRegion src, dst;
+    regionInit(&dst, p->dstPlane, p->dstRowBytes, (size_t)p->dstOffsetBytes + (size_t)(p->width - 1) * p->dstPixelBytes + dcb, p->height, 0);
+    regionInit(&src, fill ? NULL : p->srcPlane, p->srcRowBytes, (size_t)p->srcOffsetBytes + (size_t)(p->width - 1) * p->srcPixelBytes + scb, p->height, 0);
+    if (arenaReserve(regionArenaBytes(&src) + regionArenaBytes(&dst)) != AVIF_RESULT_OK) return;
+    uint8_t * cursor = tls.arena;
+    regionPlace(&src, &cursor);
+    regionPlace(&dst, &cursor);
+    if (regionUpload(&src, 0, src.rows, st) != cudaSuccess) return;
+    if (regionUpload(&dst, 0, dst.rows, st) != cudaSuccess) return; /* untouched channels must survive the round trip */
+    AbAlphaJob job;
+    memset(&job, 0, sizeof(job));
+    job.src = fill ? NULL : src.dev;
+    job.dst = dst.dev;
+    job.srcRB = src.devRB;
+    job.dstRB = dst.devRB;
+    job.width = p->width;
+    job.height = p->height;
+    job.srcDepth = fill ? p->dstDepth : p->srcDepth;
+    job.dstDepth = p->dstDepth;
+    job.srcOff = p->srcOffsetBytes;
+    job.srcPix = p->srcPixelBytes;
+    job.dstOff = p->dstOffsetBytes;
+    job.dstPix = p->dstPixelBytes;
+    if (abLaunchAlpha(&job, st) != cudaSuccess) return;
+    tls.lastKernel = fill ? "alpha_fill" : "alpha_reformat";
+    if (regionDownload(&dst, 0, dst.rows, st) != cudaSuccess) return;
+    (void)cudaStreamSynchronize(st);
+}
+
+void avifFillAlpha(const avifAlphaParams * params) { alphaCommon(params, 1); }
+void avifReformatAlpha(const avifAlphaParams * params) { alphaCommon(params, 0); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* YUV -> RGB                                                                                  */
+
+static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+{
+    /* src/reformat.c:1649-1677 */
+    if (!image->yuvPlanes[AVIF_CHAN_Y] || rgb->maxThreads < 0) return AVIF_RESULT_REFORMAT_FAILED;
+    AbState s;
+    if (!prepareState(image, rgb, &s)) return AVIF_RESULT_REFORMAT_FAILED;
+    if (!rgb->pixels) return AVIF_RESULT_REFORMAT_FAILED; /* the reference would dereference NULL */
+
+    const int rgbHasAlpha = avifRGBFormatHasAlpha(rgb->format);
+    const int rgbIsGray = avifRGBFormatIsGray(rgb->format);
+    int alphaMode = 0; /* 0 no-op, 1 multiply, 2 unmultiply */
+    if (image->alphaPlane) {
+        if (!rgbHasAlpha || rgb->ignoreAlpha) {
+            if (!image->alphaPremultiplied) alphaMode = 1;
+        } else if (!image->alphaPremultiplied && rgb->alphaPremultiplied) {
+            alphaMode = 1;
+        } else if (image->alphaPremultiplied && !rgb->alphaPremultiplied) {
+            alphaMode = 2;
+        }
+    }
+    /* rgb->maxThreads only splits rows in the reference and never changes results (:1679-1747): a hint here. */
+
+    /* src/reformat.c:1449-1450, :1475 */
+    const int reformatAlpha = rgbHasAlpha && (!rgb->ignoreAlpha || alphaMode != 0);
+    const int srcAlphaUsable = image->alphaPlane && image->alphaRowBytes;
+
+    /* variant classification, src/reformat.c:1496-1567 */
+    const int nearest = (rgb->chromaUpsampling == AVIF_CHROMA_UPSAMPLING_FASTEST) || (rgb->chromaUpsampling == AVIF_CHROMA_UPSAMPLING_NEAREST);
+    const int hasColorByStride = image->yuvRowBytes[AVIF_CHAN_U] && image->yuvRowBytes[AVIF_CHAN_V] && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV400;
+    int fast = 0, shuffle = 0;
+    if (!rgbIsGray && (!hasColorByStride || image->yuvFormat == AVIF_PIXEL_FORMAT_YUV444 || nearest) && (alphaMode == 0 || rgbHasAlpha)) {
+        if (s.mode == AB_MODE_IDENTITY) {
+            if (image->depth == 8 && rgb->depth == 8 && image->yuvFormat == AVIF_PIXEL_FORMAT_YUV444 && image->yuvRange == AVIF_RANGE_FULL) {
+                fast = 1;
+                shuffle = 1;
+            }
+        } else if (s.mode == AB_MODE_COEFF) {
+            fast = 1;
+        }
+    }
+    int hasChroma;
+    if (fast) {
+        hasChroma = hasColorByStride; /* :1496-1497 picks the Color or Mono loop */
+        if (hasChroma && (!image->yuvPlanes[AVIF_CHAN_U] || !image->yuvPlanes[AVIF_CHAN_V])) return AVIF_RESULT_REFORMAT_FAILED; /* reference: NULL deref */
+    } else {
+        hasChroma = image->yuvPlanes[AVIF_CHAN_U] && image->yuvPlanes[AVIF_CHAN_V] && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV400; /* :676 */
+    }
+
+    AbY2RJob job;
+    memset(&job, 0, sizeof(job));
+    job.width = image->width;
+    job.height = image->height;
+    job.yuvMax = (uint32_t)s.yuvMax;
+    job.rgbMax = (uint32_t)s.rgbMax;
+    job.yuvMaxF = (float)s.yuvMax;
+    job.rgbMaxF = s.rgbMaxF;
+    job.biasY = s.biasY;
+    job.rangeY = makeDiv(s.rangeY);
+    if (s.mode == AB_MODE_IDENTITY) { /* chroma shares the luma table, :587-589 */
+        job.biasUV = s.biasY;
+        job.rangeUV = makeDiv(s.rangeY);
+    } else {
+        job.biasUV = s.biasUV;
+        job.rangeUV = makeDiv(s.rangeUV);
+    }
+    job.kg = makeDiv(s.kg);
+    job.c1 = 2 * (1 - s.kr);
+    job.c2 = 2 * (1 - s.kb);
+    job.c3 = s.kr * (1 - s.kr);
+    job.c4 = s.kb * (1 - s.kb);
+    job.f16mul = f16Multiplier(rgb->depth);
+    job.yuvBytes = (uint8_t)s.yuvChanBytes;
+    job.rgbBytes = (uint8_t)s.rgbChanBytes;
+    job.shiftX = (uint8_t)s.shiftX;
+    job.shiftY = (uint8_t)s.shiftY;
+    if (!hasChroma) {
+        job.chroma = AB_CHROMA_NONE;
+    } else if (image->yuvFormat == AVIF_PIXEL_FORMAT_YUV444) {
+        job.chroma = AB_CHROMA_FULL;
+        job.shiftX = job.shiftY = 0;
+    } else if (nearest) {
+        job.chroma = AB_CHROMA_NEAREST;
+    } else {
+        job.chroma = AB_CHROMA_BILINEAR;
+        job.vertBlend = (image->yuvFormat == AVIF_PIXEL_FORMAT_YUV420);
+    }
+    job.mode = (uint8_t)(shuffle ? AB_MODE_IDENTITY8_SHUFFLE : s.mode);
+    job.rgbFormat = (uint8_t)rgb->format;
+    job.pixBytes = (uint8_t)s.rgbPixBytes;
+    job.offR = (uint8_t)s.offR;
+    job.offG = (uint8_t)s.offG;
+    job.offB = (uint8_t)s.offB;
+    job.offA = (uint8_t)s.offA;
+    job.offGray = (uint8_t)s.offGray;
+    job.nChan = (uint8_t)((rgb->format == AVIF_RGB_FORMAT_RGB_565) ? 1 : avifRGBFormatChannelCount(rgb->format));
+    job.isGray = (uint8_t)rgbIsGray;
+    job.is565 = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_RGB_565);
+    job.hasAlphaChan = (uint8_t)rgbHasAlpha;
+    job.alphaWrite = (uint8_t)(!reformatAlpha ? AB_ALPHA_KEEP : (srcAlphaUsable ? AB_ALPHA_COPY : AB_ALPHA_FILL));
+    job.alphaRescale = (uint8_t)(image->depth != rgb->depth);
+    if (alphaMode == 0) job.alphaMul = AB_MUL_NONE;
+    else if (fast) job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_INT_PREMUL : AB_MUL_INT_UNPREMUL);
+    else job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL);
+    job.toF16 = (uint8_t)(rgb->isFloat ? 1 : 0);
+
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+
+    /* the alpha channel / post-passes iterate over rgb->width x rgb->height, the colour loop over the image's
+     * (src/reformat.c:1467-1468 vs :686,:703).  When they agree (always, for sane callers) everything is one kernel. */
+    const int sameDims = (rgb->width == image->width) && (rgb->height == image->height);
+    const uint32_t rgbRows = (rgb->height > image->height) ? rgb->height : image->height;
+    const uint32_t rgbCols = (rgb->width > image->width) ? rgb->width : image->width;
+
+    const uint32_t cw = (uint32_t)(((uint64_t)image->width + s.shiftX) >> s.shiftX);
+    const uint32_t ch = (uint32_t)(((uint64_t)image->height + s.shiftY) >> s.shiftY);
+    AbRegion ry, ru, rv, ra, rrgb;
+    regionInit(&ry, image->yuvPlanes[0], image->yuvRowBytes[0], (size_t)image->width * s.yuvChanBytes, image->height, async);
+    regionInit(&ru, hasChroma ? image->yuvPlanes[1] : NULL, image->yuvRowBytes[1], (size_t)cw * s.yuvChanBytes, ch, async);
+    regionInit(&rv, hasChroma ? image->yuvPlanes[2] : NULL, image->yuvRowBytes[2], (size_t)cw * s.yuvChanBytes, ch, async);
+    const int needSrcAlpha = (job.alphaWrite == AB_ALPHA_COPY) || job.alphaMul == AB_MUL_FLOAT_MUL || job.alphaMul == AB_MUL_FLOAT_UNMUL;
+    const uint32_t aCols = sameDims ? image->width : ((job.alphaWrite == AB_ALPHA_COPY) ? rgbCols : image->width);
+    const uint32_t aRows = sameDims ? image->height : ((job.alphaWrite == AB_ALPHA_COPY) ? rgbRows : image->height);
+    regionInit(&ra, needSrcAlpha ? image->alphaPlane : NULL, image->alphaRowBytes, (size_t)aCols * s.yuvChanBytes, aRows, async);
+    regionInit(&rrgb, rgb->pixels, rgb->rowBytes, (size_t)rgbCols * s.rgbPixBytes, rgbRows, async);
+
+    if (!async) {
+        res = arenaReserve(regionArenaBytes(&ry) + regionArenaBytes(&ru) + regionArenaBytes(&rv) + regionArenaBytes(&ra) + regionArenaBytes(&rrgb));
+        if (res != AVIF_RESULT_OK) return res;
+    }
+    uint8_t * cursor = tls.arena;
+    regionPlace(&ry, &cursor);
+    regionPlace(&ru, &cursor);
+    regionPlace(&rv, &cursor);
+    regionPlace(&ra, &cursor);
+    regionPlace(&rrgb, &cursor);
+
+    AB_CUDA(regionUpload(&ry, 0, ry.rows, st));
+    AB_CUDA(regionUpload(&ru, 0, ru.rows, st));
+    AB_CUDA(regionUpload(&rv, 0, rv.rows, st));
+    AB_CUDA(regionUpload(&ra, 0, ra.rows, st));
+    const int keepsDstBytes = (job.alphaWrite == AB_ALPHA_KEEP && rgbHasAlpha) || !sameDims;
+    if (keepsDstBytes) AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st)); /* bytes the path must leave untouched */
+
+    job.y = ry.dev;
+    job.yRB = ry.devRB;
+    job.u = ru.dev;
+    job.uRB = ru.devRB;
+    job.v = rv.dev;
+    job.vRB = rv.devRB;
+    job.a = ra.dev;
+    job.aRB = ra.present ? ((image->alphaRowBytes == 0) ? 0 : ra.devRB) : 0;
+    job.rgb = rrgb.dev;
+    job.rgbRB = rrgb.devRB;
+    job.rowBegin = 0;
+    job.rowEnd = image->height;
+
+    const char * kname = "";
+    if (sameDims) {
+        AB_CUDA(abLaunchY2R(&job, st, tls.policy == 1, &kname));
+    } else {
+        /* faithful multi-pass composition for mismatched extents */
+        const uint8_t intMul = (job.alphaMul == AB_MUL_INT_PREMUL || job.alphaMul == AB_MUL_INT_UNPREMUL) ? job.alphaMul : 0;
+        if (reformatAlpha) {
+            AbAlphaJob aj;
+            memset(&aj, 0, sizeof(aj));
+            aj.src = (job.alphaWrite == AB_ALPHA_COPY) ? ra.dev : NULL;
+            aj.dst = rrgb.dev;
+            aj.srcRB = job.aRB;
+            aj.dstRB = rrgb.devRB;
+            aj.width = rgb->width;
+            aj.height = rgb->height;
+            aj.srcDepth = image->depth;
+            aj.dstDepth = rgb->depth;
+            aj.srcOff = 0;
+            aj.srcPix = s.yuvChanBytes;
+            aj.dstOff = s.offA;
+            aj.dstPix = s.rgbPixBytes;
+            AB_CUDA(abLaunchAlpha(&aj, st));
+        }
+        AbY2RJob cj = job;
+        cj.alphaWrite = AB_ALPHA_KEEP;
+        if (intMul) cj.alphaMul = AB_MUL_NONE;
+        cj.toF16 = 0;
+        AB_CUDA(abLaunchY2R(&cj, st, tls.policy == 1, &kname));
+        AbRgbPassJob pj;
+        memset(&pj, 0, sizeof(pj));
+        pj.pixels = rrgb.dev;
+        pj.rowBytes = rrgb.devRB;
+        pj.width = rgb->width;
+        pj.height = rgb->height;
+        pj.depth = rgb->depth;
+        if (intMul && premulLayout(rgb->format, &pj)) {
+            pj.unmultiply = (uint8_t)(intMul == AB_MUL_INT_UNPREMUL);
+            AB_CUDA(abLaunchPremultiply(&pj, st));
+        }
+        if (rgb->isFloat) {
+            pj.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
+            pj.f16mul = job.f16mul;
+            AB_CUDA(abLaunchToF16(&pj, st));
+        }
+        kname = "y2r_multipass";
+    }
+    tls.lastKernel = kname;
+
+    AB_CUDA(regionDownload(&rrgb, 0, rrgb.rows, st));
+    if (!async) AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
+avifResult avifB200ImageYUVToRGBAsync(const avifImage * image, avifRGBImage * rgb, void * stream) { return yuvToRgbCommon(image, rgb, stream, 1); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* RGB -> YUV                                                                                  */
+
+/* src/avif.c:431-489: missing planes are malloc'ed and owned by the image; existing ones are kept */
+static avifResult allocatePlanes(avifImage * image, int withAlpha)
+{
+    if (image->width == 0 || image->height == 0 || image->depth == 0 || image->depth > 16) return AVIF_RESULT_INVALID_ARGUMENT;
+    const uint32_t cs = (image->depth > 8) ? 2 : 1;
+    if (image->width > UINT32_MAX / cs) return AVIF_RESULT_INVALID_ARGUMENT;
+    const uint32_t fullRowBytes = cs * image->width;
+    if (image->height > PTRDIFF_MAX / fullRowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
+    const size_t fullSize = (size_t)fullRowBytes * image->height;
+    if (image->yuvFormat != AVIF_PIXEL_FORMAT_NONE) {
+        avifPixelFormatInfo fi;
+        avifGetPixelFormatInfo(image->yuvFormat, &fi);
+        image->imageOwnsYUVPlanes = AVIF_TRUE;
+        if (!image->yuvPlanes[AVIF_CHAN_Y]) {
+            image->yuvPlanes[AVIF_CHAN_Y] = (uint8_t *)malloc(fullSize);
+            if (!image->yuvPlanes[AVIF_CHAN_Y]) return AVIF_RESULT_OUT_OF_MEMORY;
+            image->yuvRowBytes[AVIF_CHAN_Y] = fullRowBytes;
+        }
+        if (!fi.monochrome) {
+            const uint32_t w = (uint32_t)(((uint64_t)image->width + fi.chromaShiftX) >> fi.chromaShiftX);
+            const uint32_t h = (uint32_t)(((uint64_t)image->height + fi.chromaShiftY) >> fi.chromaShiftY);
+            for (int p = AVIF_CHAN_U; p <= AVIF_CHAN_V; ++p) {
+                if (!image->yuvPlanes[p]) {
+                    image->yuvPlanes[p] = (uint8_t *)malloc((size_t)cs * w * h);
+                    if (!image->yuvPlanes[p]) return AVIF_RESULT_OUT_OF_MEMORY;
+                    image->yuvRowBytes[p] = cs * w;
+                }
+            }
+        }
+    }
+    if (withAlpha) {
+        image->imageOwnsAlphaPlane = AVIF_TRUE;
+        if (!image->alphaPlane) {
+            image->alphaPlane = (uint8_t *)malloc(fullSize);
+            if (!image->alphaPlane) return AVIF_RESULT_OUT_OF_MEMORY;
+            image->alphaRowBytes = fullRowBytes;
+        }
+    }
+    return AVIF_RESULT_OK;
+}
+
+static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+{
+    /* src/reformat.c:221-273 */
+    if (!rgb->pixels || rgb->format == AVIF_RGB_FORMAT_RGB_565) return AVIF_RESULT_REFORMAT_FAILED;
+    AbState s;
+    if (!prepareState(image, rgb, &s)) return AVIF_RESULT_REFORMAT_FAILED;
+    if (rgb->isFloat) return AVIF_RESULT_NOT_IMPLEMENTED;
+
+    const int hasAlpha = avifRGBFormatHasAlpha(rgb->format) && !rgb->ignoreAlpha;
+    const int wantAlphaPlane = hasAlpha;
+    const int monochrome = (image->yuvFormat == AVIF_PIXEL_FORMAT_YUV400);
+    const int planesMissing = !image->yuvPlanes[0] || (!monochrome && (!image->yuvPlanes[1] || !image->yuvPlanes[2])) || (wantAlphaPlane && !image->alphaPlane);
+    if (planesMissing) {
+        /* Missing planes are malloc'ed host memory owned by the image, like the reference.  That is only
+         * meaningful when the call may stage through the host. */
+        if (async || ptrOnDevice(rgb->pixels)) return AVIF_RESULT_INVALID_ARGUMENT;
+    }
+    avifResult res = allocatePlanes(image, wantAlphaPlane);
+    if (res != AVIF_RESULT_OK) return res;
+
+    int alphaMode = 0;
+    if (hasAlpha) {
+        if (!rgb->alphaPremultiplied && image->alphaPremultiplied) alphaMode = 1;
+        else if (rgb->alphaPremultiplied && !image->alphaPremultiplied) alphaMode = 2;
+    }
+    const int isGray = avifRGBFormatIsGray(rgb->format);
+    if (!isGray && rgb->chromaDownsampling == AVIF_CHROMA_DOWNSAMPLING_SHARP_YUV && image->yuvFormat == AVIF_PIXEL_FORMAT_YUV420) {
+        return AVIF_RESULT_NOT_IMPLEMENTED; /* no libsharpyuv: src/reformat.c:256-261, src/reformat_libsharpyuv.c:75-83 */
+    }
+
+    AbR2YJob job;
+    memset(&job, 0, sizeof(job));
+    job.width = image->width;
+    job.height = image->height;
+    job.yuvMax = (uint32_t)s.yuvMax;
+    job.rgbMax = (uint32_t)s.rgbMax;
+    job.yuvMaxF = (float)s.yuvMax;
+    job.rgbMaxF = s.rgbMaxF;
+    job.biasY = s.biasY;
+    job.rangeY = s.rangeY;
+    if (s.mode == AB_MODE_IDENTITY) { /* :212-213 */
+        job.biasUV = s.biasY;
+        job.rangeUV = s.rangeY;
+    } else {
+        job.biasUV = s.biasUV;
+        job.rangeUV = s.rangeUV;
+    }
+    job.rangeYdiv = s.rangeY;
+    job.rangeUVdiv = s.rangeUV;
+    job.kr = s.kr;
+    job.kg = s.kg;
+    job.kb = s.kb;
+    job.du = 2 * (1 - s.kb);
+    job.dv = 2 * (1 - s.kr);
+    job.rgbBytes = (uint8_t)s.rgbChanBytes;
+    job.yuvBytes = (uint8_t)s.yuvChanBytes;
+    job.hasChroma = (uint8_t)!monochrome;
+    job.shiftX = (uint8_t)(monochrome ? 0 : s.shiftX);
+    job.shiftY = (uint8_t)(monochrome ? 0 : s.shiftY);
+    job.mode = (uint8_t)s.mode;
+    job.pixBytes = (uint8_t)s.rgbPixBytes;
+    job.offR = (uint8_t)s.offR;
+    job.offG = (uint8_t)s.offG;
+    job.offB = (uint8_t)s.offB;
+    job.offA = (uint8_t)s.offA;
+    job.offGray = (uint8_t)s.offGray;
+    job.isGray = (uint8_t)isGray;
+    job.alphaMul = (uint8_t)((alphaMode == 0) ? AB_MUL_NONE : ((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL));
+    const int writeAlphaPlane = image->alphaPlane && image->alphaRowBytes; /* :545 */
+    job.alphaWrite = (uint8_t)(!writeAlphaPlane ? AB_ALPHA_KEEP : (hasAlpha ? AB_ALPHA_COPY : AB_ALPHA_FILL));
+    job.alphaRescale = (uint8_t)(image->depth != rgb->depth);
+
+    res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+
+    const uint32_t cw = (uint32_t)(((uint64_t)image->width + s.shiftX) >> s.shiftX);
+    const uint32_t ch = (uint32_t)(((uint64_t)image->height + s.shiftY) >> s.shiftY);
+    /* gray input: existing chroma planes become constant "half", padding included (:520-542) */
+    const int grayChromaFill = isGray;
+    AbRegion rrgb, ry, ru, rv, ra;
+    regionInit(&rrgb, rgb->pixels, rgb->rowBytes, (size_t)image->width * s.rgbPixBytes, image->height, async);
+    regionInit(&ry, image->yuvPlanes[0], image->yuvRowBytes[0], (size_t)image->width * s.yuvChanBytes, image->height, async);
+    const int useU = grayChromaFill ? (image->yuvPlanes[1] != NULL) : !monochrome;
+    const int useV = grayChromaFill ? (image->yuvPlanes[2] != NULL) : !monochrome;
+    regionInit(&ru, useU ? image->yuvPlanes[1] : NULL, image->yuvRowBytes[1], (size_t)cw * s.yuvChanBytes, ch, async);
+    regionInit(&rv, useV ? image->yuvPlanes[2] : NULL, image->yuvRowBytes[2], (size_t)cw * s.yuvChanBytes, ch, async);
+    if (grayChromaFill) {
+        ru.exactPitch = 1;
+        rv.exactPitch = 1;
+    }
+    regionInit(&ra, writeAlphaPlane ? image->alphaPlane : NULL, image->alphaRowBytes, (size_t)image->width * s.yuvChanBytes, image->height, async);
+
+    if (!async) {
+        res = arenaReserve(regionArenaBytes(&rrgb) + regionArenaBytes(&ry) + regionArenaBytes(&ru) + regionArenaBytes(&rv) + regionArenaBytes(&ra));
+        if (res != AVIF_RESULT_OK) return res;
+    }
+    uint8_t * cursor = tls.arena;
+    regionPlace(&rrgb, &cursor);
+    regionPlace(&ry, &cursor);
+    regionPlace(&ru, &cursor);
+    regionPlace(&rv, &cursor);
+    regionPlace(&ra, &cursor);
+    AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st));
+
+    job.rgb = rrgb.dev;
+    job.rgbRB = rrgb.devRB;
+    job.y = ry.dev;
+    job.yRB = ry.devRB;
+    job.u = ru.dev;
+    job.uRB = ru.devRB;
+    job.v = rv.dev;
+    job.vRB = rv.devRB;
+    job.a = ra.dev;
+    job.aRB = ra.devRB;
+
+    const char * kname = "";
+    AB_CUDA(abLaunchR2Y(&job, st, tls.policy == 1, &kname));
+    tls.lastKernel = kname;
+    if (grayChromaFill) {
+        const int half = 1 << (image->depth - 1);
+        AbRegion * pr[2] = { &ru, &rv };
+        for (int k = 0; k < 2; ++k) {
+            if (!pr[k]->present) continue;
+            const size_t bytes = (size_t)ch * (size_t)pr[k]->userRB;
+            if (s.yuvChanBytes > 1) AB_CUDA(abLaunchFill16(pr[k]->dev, bytes / 2, (uint32_t)half, st));
+            else AB_CUDA(abLaunchFill8(pr[k]->dev, bytes, (uint32_t)half, st));
+        }
+    }
+
+    AB_CUDA(regionDownload(&ry, 0, ry.rows, st));
+    AB_CUDA(regionDownload(&ru, 0, ru.rows, st));
+    AB_CUDA(regionDownload(&rv, 0, rv.rows, st));
+    AB_CUDA(regionDownload(&ra, 0, ra.rows, st));
+    if (!async) AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifImageRGBToYUV(avifImage * image, const avifRGBImage * rgb) { return rgbToYuvCommon(image, rgb, NULL, 0); }
+avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avifRGBImage * rgb, void * stream) { return rgbToYuvCommon(image, rgb, stream, 1); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* "next" rows: alpha range expansion and grid plane staging                    */
+
+/* src/read.c:6724-6764 */
+avifResult avifB200ImageLimitedToFullAlpha(avifImage * image)
+{
+    if (!image->alphaPlane) return AVIF_RESULT_OK;
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    cudaStream_t st = tls.stream;
+    const uint32_t cb = (image->depth > 8) ? 2 : 1;
+    AbRegion ra;
+    regionInit(&ra, image->alphaPlane, image->alphaRowBytes, (size_t)image->width * cb, image->height, 0);
+    res = arenaReserve(regionArenaBytes(&ra));
+    if (res != AVIF_RESULT_OK) return res;
+    uint8_t * cursor = tls.arena;
+    regionPlace(&ra, &cursor);
+    AB_CUDA(regionUpload(&ra, 0, ra.rows, st));
+    AB_CUDA(abLaunchLimitedToFull(ra.dev, ra.devRB, image->width, image->height, image->depth, st));
+    tls.lastKernel = "limited_to_full";
+    AB_CUDA(regionDownload(&ra, 0, ra.rows, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
+}
+
+static void planeGeometry(const avifImage * im, int plane, uint32_t * w, uint32_t * h)
+{
+    avifPixelFormatInfo fi;
+    avifGetPixelFormatInfo(im->yuvFormat, &fi);
+    if (plane == AVIF_CHAN_Y || plane == AVIF_CHAN_A) {
+        *w = im->width;
+        *h = im->height;
+    } else if (fi.monochrome) {
+        *w = *h = 0;
+    } else {
+        *w = (uint32_t)(((uint64_t)im->width + fi.chromaShiftX) >> fi.chromaShiftX);
+        *h = (uint32_t)(((uint64_t)im->height + fi.chromaShiftY) >> fi.chromaShiftY);
+    }
+}
+
+/* src/avif.c:187-225: row-wise copy of the src-sized area of every selected plane (device, stream-ordered) */
+avifResult avifB200ImageCopySamplesAsync(avifImage * dst, const avifImage * src, avifPlanesFlags planes, void * stream)
+{
+    if (dst->depth != src->depth || dst->yuvFormat != src->yuvFormat) return AVIF_RESULT_INVALID_ARGUMENT;
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    const size_t bps = (src->depth > 8) ? 2 : 1;
+    for (int c = AVIF_CHAN_Y; c <= AVIF_CHAN_A; ++c) {
+        const int isAlpha = (c == AVIF_CHAN_A);
+        if (isAlpha ? !(planes & AVIF_PLANES_A) : !(planes & AVIF_PLANES_YUV)) continue;
+        const uint8_t * sp = isAlpha ? src->alphaPlane : src->yuvPlanes[c];
+        uint8_t * dp = isAlpha ? dst->alphaPlane : dst->yuvPlanes[c];
+        const size_t srb = isAlpha ? src->alphaRowBytes : src->yuvRowBytes[c];
+        const size_t drb = isAlpha ? dst->alphaRowBytes : dst->yuvRowBytes[c];
+        if (!sp || !dp) continue;
+        uint32_t w, h;
+        planeGeometry(src, c, &w, &h);
+        if (!w || !h) continue;
+        AB_CUDA(cudaMemcpy2DAsync(dp, drb, sp, srb, (size_t)w * bps, h, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return AVIF_RESULT_OK;
+}
+
+/* src/write.c:1151-1205: copy into a larger cell, replicating the last column / row */
+avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, void * stream)
+{
+    if (dst->depth != src->depth || dst->yuvFormat != src->yuvFormat || dst->width < src->width || dst->height < src->height) {
+        return AVIF_RESULT_INVALID_ARGUMENT;
+    }
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    const uint32_t bps = (src->depth > 8) ? 2 : 1;
+    for (int c = AVIF_CHAN_Y; c <= AVIF_CHAN_A; ++c) {
+        const int isAlpha = (c == AVIF_CHAN_A);
+        const uint8_t * sp = isAlpha ? src->alphaPlane : src->yuvPlanes[c];
+        uint8_t * dp = isAlpha ? dst->alphaPlane : dst->yuvPlanes[c];
+        if (!sp || !dp) continue;
+        uint32_t sw, sh, dw, dh;
+        planeGeometry(src, c, &sw, &sh);
+        planeGeometry(dst, c, &dw, &dh);
+        if (!sw || !sh) continue;
+        AB_CUDA(abLaunchCopyPad(sp, isAlpha ? src->alphaRowBytes : src->yuvRowBytes[c], sw, sh, dp, isAlpha ? dst->alphaRowBytes : dst->yuvRowBytes[c], dw,
+                                dh, bps, stream));
+    }
+    tls.lastKernel = "copy_pad";
+    return AVIF_RESULT_OK;
+}

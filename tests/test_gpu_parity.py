@@ -1,0 +1,164 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs.
+Bit-exact (integer code values) everywhere."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from libavif_b200 import abi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_y2r(product, oracle, spec, seed, device=None, policy=0):
+    ro, bo = util.yuv_to_rgb(oracle, spec, seed)
+    product.avifB200SetKernelPolicy(policy)
+    try:
+        rp, bp = util.yuv_to_rgb(product, spec, seed, device=device)
+    finally:
+        product.avifB200SetKernelPolicy(0)
+    assert rp == ro, f"result code {rp} vs oracle {ro} for {spec.ident()}"
+    if ro == abi.AVIF_RESULT_OK:
+        mm = util.first_mismatch(bo, bp)
+        assert mm is None, f"{spec.ident()} [{product.avifB200LastKernelName().decode()}]: {mm}"
+    return ro
+
+
+def _check_r2y(product, oracle, spec, seed, device=None, policy=0):
+    ro, po = util.rgb_to_yuv(oracle, spec, seed)
+    product.avifB200SetKernelPolicy(policy)
+    try:
+        rp, pp = util.rgb_to_yuv(product, spec, seed, device=device)
+    finally:
+        product.avifB200SetKernelPolicy(0)
+    assert rp == ro, f"result code {rp} vs oracle {ro} for {spec.ident()}"
+    if ro == abi.AVIF_RESULT_OK:
+        for p in range(4):
+            assert (po[p] is None) == (pp[p] is None)
+            if po[p] is not None:
+                mm = util.first_mismatch(po[p], pp[p])
+                assert mm is None, f"{spec.ident()} plane {p}: {mm}"
+    return ro
+
+
+@pytest.mark.parametrize("policy", [0, 1], ids=["tiled", "generic"])
+def test_y2r_sweep_host_pointers(gpu_product, oracle, policy):
+    n_ok = 0
+    for k, spec in enumerate(util.random_y2r_specs(700, seed=21 + policy)):
+        n_ok += _check_y2r(gpu_product, oracle, spec, 3000 + k, policy=policy) == abi.AVIF_RESULT_OK
+    assert n_ok > 450
+
+
+def test_y2r_sweep_device_pointers(gpu_product, oracle):
+    n_ok = 0
+    for k, spec in enumerate(util.random_y2r_specs(300, seed=23)):
+        n_ok += _check_y2r(gpu_product, oracle, spec, 4000 + k, device="cuda:0") == abi.AVIF_RESULT_OK
+    assert n_ok > 180
+
+
+def test_y2r_wide_tiles(gpu_product, oracle):
+    """Widths around the 256-pixel warp tile and the 16-byte copy-out granularity, odd heights, padded rows."""
+    sizes = [(255, 3), (256, 2), (257, 5), (511, 4), (513, 3), (1023, 2), (1025, 3), (1920, 6), (33, 17)]
+    for k, spec in enumerate(util.random_y2r_specs(160, seed=24, sizes=sizes)):
+        _check_y2r(gpu_product, oracle, spec, 5000 + k)
+
+
+def test_y2r_unaligned_device_views(gpu_product, oracle):
+    """View-rectangle style inputs: plane / pixel pointers that are only sample-aligned."""
+    import dataclasses
+    for k, spec in enumerate(util.random_y2r_specs(120, seed=25, sizes=[(67, 9), (300, 4), (129, 6)])):
+        bps_y = 2 if spec.depth > 8 else 1
+        bps_r = 2 if spec.rgb_depth > 8 else 1
+        spec = dataclasses.replace(spec, yuv_off=bps_y * (1 + k % 3), rgb_off=bps_r * (1 + k % 5), yuv_pad=2 * (k % 4), rgb_pad=2 * (k % 3))
+        _check_y2r(gpu_product, oracle, spec, 6000 + k, device="cuda:0")
+
+
+def test_r2y_sweep_host_pointers(gpu_product, oracle):
+    n_ok = 0
+    for k, spec in enumerate(util.random_r2y_specs(700, seed=31)):
+        n_ok += _check_r2y(gpu_product, oracle, spec, 7000 + k) == abi.AVIF_RESULT_OK
+    assert n_ok > 450
+
+
+def test_r2y_sweep_device_pointers(gpu_product, oracle):
+    for k, spec in enumerate(util.random_r2y_specs(250, seed=32, sizes=[(64, 8), (65, 9), (127, 3), (258, 5), (1, 1), (2, 2), (513, 2)])):
+        _check_r2y(gpu_product, oracle, spec, 8000 + k, device="cuda:0")
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12, 16])
+@pytest.mark.parametrize("un", [0, 1], ids=["premultiply", "unpremultiply"])
+def test_premultiply_in_place(gpu_product, oracle, depth, un):
+    for fmt in [abi.AVIF_RGB_FORMAT_RGBA, abi.AVIF_RGB_FORMAT_BGRA, abi.AVIF_RGB_FORMAT_ARGB, abi.AVIF_RGB_FORMAT_ABGR,
+                abi.AVIF_RGB_FORMAT_GRAYA, abi.AVIF_RGB_FORMAT_AGRAY, abi.AVIF_RGB_FORMAT_RGB, abi.AVIF_RGB_FORMAT_GRAY]:
+        for device in (None, "cuda:0"):
+            spec = util.Spec(w=301, h=7, rgb_depth=depth, rgb_fmt=fmt, rgb_pad=6, garbage=True)
+            outs = []
+            for lib, dev in ((oracle, None), (gpu_product, device)):
+                rgb = util.make_rgb_src(spec, seed=90 + depth, device=dev)
+                fn = lib.avifRGBImageUnpremultiplyAlpha if un else lib.avifRGBImagePremultiplyAlpha
+                outs.append((fn(rgb.ptr()), rgb.full_bytes().copy()))
+            assert outs[0][0] == outs[1][0]
+            assert util.first_mismatch(outs[0][1], outs[1][1]) is None
+
+
+def _golden(product, oracle, w, h, depth, fmt, rng, mc, alpha, iprem, rgb_depth, rgb_fmt, ups, rprem, seed, device):
+    from libavif_b200.images import RGBImage, YUVImage
+    host = YUVImage(w, h, depth, fmt, rng, mc, alpha=alpha, alpha_premultiplied=iprem)
+    util.xorshift_fill_image(oracle, host, seed)
+    in_hash = util.fnv1a64(oracle, host.payload_bytes())
+    img = host
+    if device:
+        img = YUVImage(w, h, depth, fmt, rng, mc, alpha=alpha, alpha_premultiplied=iprem, device=device)
+        for p in host.present_planes():
+            img.bufs[p].set(host.bufs[p].host())
+    rgb = RGBImage(w, h, rgb_depth, rgb_fmt, upsampling=ups, alpha_premultiplied=rprem, device=device)
+    assert product.avifImageYUVToRGB(img.ptr(), rgb.ptr()) == 0
+    return in_hash, util.fnv1a64(oracle, rgb.payload_bytes()), rgb
+
+
+GOLDEN = {  # SURVEY.md Appendix C (reference outputs recorded from the compiled reference)
+    "G1a": ((1920, 1080, 8, 3, 0, 6, False, False, 8, 1, 4, False, 1), 0xd8c41c5edae2a9db, 0xbe2d9874701b4ce2),
+    "G1b": ((1920, 1080, 8, 3, 0, 6, False, False, 8, 1, 3, False, 1), 0xd8c41c5edae2a9db, 0x0d2f2eb74b548364),
+    "G2a": ((3840, 2160, 10, 1, 1, 1, True, False, 10, 1, 0, True, 2), 0x003e7888b2412f05, 0xf47a37093a2029be),
+    "G3": ((7680, 4320, 12, 3, 0, 9, True, True, 12, 1, 4, False, 3), 0x1b1d7742e04261dc, 0xa520172ab021d8f7),
+    "G5": ((3840, 2160, 10, 3, 0, 1, False, False, 16, 0, 0, False, 5), 0x90804e1e3df1c849, 0x8512bd6346d339c7),
+    "GN": ((7680, 4320, 10, 1, 1, 1, False, False, 10, 1, 0, False, 7), 0x19734f45d63ebb3e, 0x3294f95469fdc527),
+}
+
+
+@pytest.mark.parametrize("name", list(GOLDEN))
+@pytest.mark.parametrize("device", [None, "cuda:0"], ids=["host", "device"])
+def test_full_size_golden_hashes(gpu_product, oracle, name, device):
+    """BASELINE.json's full-size configurations: whole-frame FNV-1a-64 of the CUDA output == the reference's."""
+    args, want_in, want_out = GOLDEN[name]
+    got_in, got_out, _ = _golden(gpu_product, oracle, *args, device=device)
+    assert got_in == want_in
+    assert got_out == want_out, f"{name}: {got_out:016x} != {want_out:016x} ({gpu_product.avifB200LastKernelName().decode()})"
+
+
+def test_c2_round_trip_golden(gpu_product, oracle):
+    """C2: G2a output (RGBA10 premultiplied) -> 4:4:4 10-bit straight alpha; hash over Y,U,V,A == G2b."""
+    from libavif_b200.images import YUVImage
+    args, _, _ = GOLDEN["G2a"]
+    _, _, rgb = _golden(gpu_product, oracle, *args, device=None)
+    back = YUVImage(3840, 2160, 10, abi.AVIF_PIXEL_FORMAT_YUV444, abi.AVIF_RANGE_FULL, abi.MC_BT709, alpha=True, alpha_premultiplied=False)
+    assert gpu_product.avifImageRGBToYUV(back.ptr(), rgb.ptr()) == 0
+    assert util.fnv1a64(oracle, back.payload_bytes()) == 0x1f2ee19d048166ce
+
+
+def test_exhaustive_8bit_yuv_cube(gpu_product, oracle):
+    """Every (Y,U,V) triple at depth 8 (2^24 pixels) through the fast 4:4:4 path, limited BT.601 -> RGBA8."""
+    from libavif_b200.images import RGBImage, YUVImage
+    w, h = 4096, 4096
+    idx = np.arange(w * h, dtype=np.uint32).reshape(h, w)
+    outs = []
+    for lib in (oracle, gpu_product):
+        img = YUVImage(w, h, 8, abi.AVIF_PIXEL_FORMAT_YUV444, abi.AVIF_RANGE_LIMITED, abi.MC_BT601)
+        img.bufs[0].set((idx & 255).astype(np.uint8))
+        img.bufs[1].set(((idx >> 8) & 255).astype(np.uint8))
+        img.bufs[2].set(((idx >> 16) & 255).astype(np.uint8))
+        rgb = RGBImage(w, h, 8, abi.AVIF_RGB_FORMAT_RGBA)
+        assert lib.avifImageYUVToRGB(img.ptr(), rgb.ptr()) == 0
+        outs.append(rgb.payload_bytes().copy())
+    assert util.first_mismatch(outs[0], outs[1]) is None
