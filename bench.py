@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- measurement harness of the B200 reformat path (contract: see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1], "C2"): avifImageYUVToRGB + avifImageRGBToYUV round trip of 3840x2160 4:4:4 10-bit
+BT.709 full-range frames with an alpha plane (straight) <-> RGBA 10-bit premultiplied.  One step = one pass of the hot
+path over a batch of B distinct synthetic frames (forward conversion of every frame, then the backward conversion of
+every result); the batch working set (B x 265 MB) is far larger than the 126 MB L2, so no flush is needed.
+
+  value      : Mpixels/s, device-resident planes, CUDA events on the launching stream (each direction counts W*H px)
+  e2e        : same metric through the public C-ABI (avifImageYUVToRGB / avifImageRGBToYUV) with pinned HOST buffers,
+               host<->device copies inside the timed region
+  roofline   : dominant kernel's algorithmic bytes / its mean launch time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the reference's own CPU code (oracle/_ref, else the oracle port) on the host cores
+
+N > 1 (torchrun): frames shard across ranks with no data-path collective (weak scaling); time = max over ranks.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, DEPTH = 3840, 2160, 10
+PX = W * H
+ALG_BYTES_PER_PX = 16  # C2, either direction: 4 planes x 2 B read/written + 8 B RGBA16 written/read
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per step (device-resident leg)")
+    ap.add_argument("--e2e-batch", type=int, default=4, help="frames per step (host-buffer leg)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE configs (kernel-only) into 'extras'")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs during the timed regions
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self._stop, self._thr = index, [], set(), threading.Event(), None
+        self.max_sm = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic frames (SURVEY.md Appendix D distribution: uniform codes), generated with torch on the target memory
+
+
+def c2_specs(abi):
+    img = dict(width=W, height=H, depth=DEPTH, yuv_format=abi.AVIF_PIXEL_FORMAT_YUV444, yuv_range=abi.AVIF_RANGE_FULL,
+               mc=abi.MC_BT709, alpha=True, alpha_premultiplied=False)
+    rgb = dict(width=W, height=H, depth=DEPTH, fmt=abi.AVIF_RGB_FORMAT_RGBA, alpha_premultiplied=True)
+    return img, rgb
+
+
+def fill_uniform(img, seed):
+    """uniform random codes in [0, 2^depth) written straight into the image's buffers (host numpy or device torch)."""
+    import numpy as np
+    import torch
+    mask = (1 << img.c.depth) - 1
+    for p in img.present_planes():
+        b = img.bufs[p]
+        n16 = b.nbytes // 2
+        if b.device is None:
+            rs = np.random.RandomState(seed * 7 + p)
+            b.flat[b.offset:b.offset + b.nbytes].view(np.uint16)[:] = rs.randint(0, mask + 1, size=n16, dtype=np.uint16)
+        else:
+            g = torch.Generator(device=b.device)
+            g.manual_seed(seed * 7 + p)
+            v = torch.randint(0, mask + 1, (n16,), generator=g, device=b.device, dtype=torch.int32).to(torch.int16)
+            b._t[b.offset:b.offset + b.nbytes].view(torch.int16).copy_(v)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU code on the host cores
+
+
+def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
+    """Times C2 round trips of the reference CPU implementation with one frame per host thread.
+    Returns dict(value Mpx/s, ms_per_step, cores, kind, sample)."""
+    import concurrent.futures as cf
+    import numpy as np
+    from libavif_b200 import abi
+    from libavif_b200.images import RGBImage, YUVImage
+    from oracle import loader
+    ref = loader.load_reference()
+    kind = "reference"
+    if ref is None:
+        ref, kind = loader.load_oracle(), "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(cores, max_threads or cores))
+    ispec, rspec = c2_specs(abi)
+    # one shared read-only input frame; per-thread outputs (the conversion never writes its inputs)
+    src = YUVImage(**ispec)
+    fill_uniform(src, 1)
+    work = []
+    for _ in range(threads):
+        rgb = RGBImage(**rspec)
+        back = YUVImage(**ispec)
+        work.append((rgb, back))
+
+    def one(k):
+        rgb, back = work[k]
+        r1 = ref.avifImageYUVToRGB(src.ptr(), rgb.ptr())
+        r2 = ref.avifImageRGBToYUV(back.ptr(), rgb.ptr())
+        return r1 | r2
+
+    pool = cf.ThreadPoolExecutor(max_workers=threads)
+
+    def step():
+        assert all(r == 0 for r in pool.map(one, range(threads)))
+
+    for _ in range(warmup):
+        step()
+    t_all, done = [], 0
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        t_all.append(time.perf_counter() - t0)
+        done += 1
+        if seconds_budget and time.perf_counter() - t_start > seconds_budget:
+            break
+    pool.shutdown()
+    total = sum(t_all)
+    px = done * threads * 2 * PX
+    return {"value": px / total / 1e6, "unit": "Mpixels/s", "ms_per_step": 1e3 * total / done, "cores": threads, "kind": kind,
+            "steps_done": done,
+            "sample": f"{done} steps x {threads} concurrent C2 round trips (one 3840x2160 frame per host thread, maxThreads=1), "
+                      f"{'reference sources compiled -O3 (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    r = cpu_round_trips(seconds_budget=150, steps=args.steps, warmup=min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": "Mpixels/s YUV<->RGB (C2 round trip 3840x2160 4:4:4 10-bit + alpha premultiply)",
+        "value": r["value"], "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": min(args.warmup, 2),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2 round trip: avifImageYUVToRGB + avifImageRGBToYUV, 3840x2160 YUV444 10-bit BT.709 full + alpha, RGBA10 premultiplied",
+                   "frames_per_step": r["cores"], "pixel_count": "each direction counts W*H"},
+        "cpu_baseline": {"value": r["value"], "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# B200 arm
+
+
+def run_b200(args):
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    import libavif_b200 as L
+    from libavif_b200 import abi
+    from libavif_b200.images import RGBImage, YUVImage
+
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    lib = L.lib()
+    if not L.device_available():
+        raise SystemExit("bench.py: libavif_b200 sees no CUDA device (there is no CPU fallback)")
+    torch.zeros(1, device=dev)  # make torch's context current before the library's first call
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    ispec, rspec = c2_specs(abi)
+
+    # ---------------- device-resident leg ----------------
+    B = args.batch
+    frames = []
+    for f in range(B):
+        src = YUVImage(device=dev, **ispec)
+        fill_uniform(src, 100 + rank * 1000 + f)
+        rgb = RGBImage(device=dev, **rspec)
+        back = YUVImage(device=dev, **ispec)
+        frames.append((src, rgb, back))
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(record=None):
+        e0 = ev() if record is not None else None
+        if e0:
+            e0.record(stream)
+        for src, rgb, _ in frames:
+            r = lib.avifB200ImageYUVToRGBAsync(src.ptr(), rgb.ptr(), sptr)
+            assert r == 0, r
+        e1 = ev() if record is not None else None
+        if e1:
+            e1.record(stream)
+        for _, rgb, back in frames:
+            r = lib.avifB200ImageRGBToYUVAsync(back.ptr(), rgb.ptr(), sptr)
+            assert r == 0, r
+        if record is not None:
+            e2 = ev()
+            e2.record(stream)
+            record.append((e0, e1, e2))
+
+    for _ in range(args.warmup):
+        step()
+    kfwd = lib.avifB200LastKernelName  # noqa
+    step()
+    torch.cuda.synchronize()
+    # names of the two kernels of the step
+    lib.avifB200ImageYUVToRGBAsync(frames[0][0].ptr(), frames[0][1].ptr(), sptr)
+    name_fwd = lib.avifB200LastKernelName().decode()
+    lib.avifB200ImageRGBToYUVAsync(frames[0][2].ptr(), frames[0][1].ptr(), sptr)
+    name_back = lib.avifB200LastKernelName().decode()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.avifB200ResetKernelLaunchCount()
+    rec = []
+    sampler.start()
+    t_begin, t_end = ev(), ev()
+    t_begin.record(stream)
+    for _ in range(args.steps):
+        step(rec)
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop()
+    if world > 1:
+        dist.barrier()
+    launches = int(lib.avifB200KernelLaunchCount())
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / (len(rec) * B)
+    back_ms = sum(b.elapsed_time(c) for _, b, c in rec) / (len(rec) * B)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * args.steps * B * 2 * PX / (elapsed_ms * 1e-3) / 1e6
+
+    # ---------------- host-buffer (end-to-end) leg ----------------
+    Be = args.e2e_batch
+    hframes = []
+    for f in range(Be):
+        src = YUVImage(pinned=True, **ispec)
+        fill_uniform(src, 500 + rank * 1000 + f)
+        rgb = RGBImage(pinned=True, **rspec)
+        back = YUVImage(pinned=True, **ispec)
+        hframes.append((src, rgb, back))
+
+    def e2e_step():
+        for src, rgb, back in hframes:
+            assert lib.avifImageYUVToRGB(src.ptr(), rgb.ptr()) == 0
+            assert lib.avifImageRGBToYUV(back.ptr(), rgb.ptr()) == 0
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 20))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous API: returns when the results are in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * e2e_steps * Be * 2 * PX / e2e_s / 1e6
+    plane_bytes = PX * 2
+    h2d = Be * (4 * plane_bytes + 4 * plane_bytes)  # fwd: Y,U,V,A ; back: RGBA16
+    d2h = Be * (4 * plane_bytes + 4 * plane_bytes)  # fwd: RGBA16  ; back: Y,U,V,A
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_gbs, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        peak_gbs = 6650.0
+    alg = ALG_BYTES_PER_PX * PX
+    kern = {
+        name_fwd: {"direction": "YUVToRGB", "ms_per_launch": fwd_ms, "achieved_gbs": alg / (fwd_ms * 1e-3) / 1e9},
+        name_back: {"direction": "RGBToYUV", "ms_per_launch": back_ms, "achieved_gbs": alg / (back_ms * 1e-3) / 1e9},
+    }
+    dom = name_fwd if fwd_ms >= back_ms else name_back
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+                "frac": kern[dom]["achieved_gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "kernels": kern}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_round_trips(seconds_budget=20, steps=3, warmup=1)
+        cpu = {"value": r["value"], "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    extras = run_extras(lib, dev, sptr, stream, peak_gbs) if args.extras else None
+
+    line = {
+        "metric": "Mpixels/s YUV<->RGB (C2 round trip 3840x2160 4:4:4 10-bit + alpha premultiply)",
+        "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 round trip: avifImageYUVToRGB + avifImageRGBToYUV, 3840x2160 YUV444 10-bit BT.709 full + alpha, RGBA10 premultiplied",
+                   "frames_per_step_per_gpu": B, "pixel_count": "each direction counts W*H",
+                   "l2": f"inputs larger than L2: {B} distinct frames x 265 MB per step", "sharding": "frames across ranks, no collective"},
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "frames_per_step_per_gpu": Be, "steps": e2e_steps, "host_memory": "pinned", "api": "avifImageYUVToRGB / avifImageRGBToYUV (C-ABI, host pointers)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+    }
+    if extras:
+        line["extras"] = extras
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(lib, dev, sptr, stream, peak_gbs):
+    """Kernel-only timings of the other BASELINE.json configurations (device-resident, CUDA events, 4 rotating frames)."""
+    import torch
+    from libavif_b200 import abi
+    from libavif_b200.images import RGBImage, YUVImage
+    A = abi
+    cfgs = {
+        # name: (w, h, depth, fmt, range, mc, alpha, img_premult, rgb_depth, rgb_fmt, upsampling, rgb_premult, alg bytes/px)
+        "NS_8K_444_10b_RGBA10": (7680, 4320, 10, A.AVIF_PIXEL_FORMAT_YUV444, 1, 1, False, False, 10, A.AVIF_RGB_FORMAT_RGBA, 0, False, 14),
+        "C1_1080p_420_8b_RGBA8_bilinear": (1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 0, 6, False, False, 8, A.AVIF_RGB_FORMAT_RGBA, 4, False, 5.5),
+        "C1_1080p_420_8b_RGBA8_nearest": (1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 0, 6, False, False, 8, A.AVIF_RGB_FORMAT_RGBA, 3, False, 5.5),
+        "C3_8K_420_12b_bilinear_unmultiply": (7680, 4320, 12, A.AVIF_PIXEL_FORMAT_YUV420, 0, 9, True, True, 12, A.AVIF_RGB_FORMAT_RGBA, 4, False, 13),
+        "C5_4K_420_10b_RGB16_bilinear": (3840, 2160, 10, A.AVIF_PIXEL_FORMAT_YUV420, 0, 1, False, False, 16, A.AVIF_RGB_FORMAT_RGB, 0, False, 9),
+        "C5_4K_420_10b_RGB16_nearest": (3840, 2160, 10, A.AVIF_PIXEL_FORMAT_YUV420, 0, 1, False, False, 16, A.AVIF_RGB_FORMAT_RGB, 3, False, 9),
+    }
+    out = {}
+    for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in cfgs.items():
+        nf = 4 if w >= 3840 else 16
+        fr = []
+        for f in range(nf):
+            img = YUVImage(w, h, d, fmt, rng, mc, alpha=alpha, alpha_premultiplied=ip, device=dev)
+            for p in img.present_planes():
+                b = img.bufs[p]
+                g = torch.Generator(device=dev)
+                g.manual_seed(f * 13 + p)
+                if d > 8:
+                    v = torch.randint(0, 1 << d, (b.nbytes // 2,), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
+                    b._t[:b.nbytes].view(torch.int16).copy_(v)
+                else:
+                    b._t[:b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
+            rgb = RGBImage(w, h, rd, rf, upsampling=ups, alpha_premultiplied=rp, device=dev)
+            fr.append((img, rgb))
+        for img, rgb in fr:
+            assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            for img, rgb in fr:
+                lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * nf)
+        gbs = bpp * w * h / (ms * 1e-3) / 1e9
+        out[name] = {"kernel": lib.avifB200LastKernelName().decode(), "us_per_frame": ms * 1e3, "Mpixels_per_s": w * h / (ms * 1e-3) / 1e6,
+                     "alg_bytes_per_px": bpp, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
+        del fr
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -297,15 +297,22 @@ AVIF_B200_API avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avi
 AVIF_B200_API void * avifB200AllocPinned(size_t size);
 AVIF_B200_API void avifB200FreePinned(void * p);
 
-/* Selects which kernels serve subsequent calls made by THIS thread: 0 = automatic (vectorised kernels
- * when alignment allows, else the generic kernel), 1 = force the generic byte-addressed kernel.
- * Used by the parity tests to check both implementations against the oracle. */
+/* Selects which kernels serve subsequent calls made by THIS thread (bit field): bit 0 = use the byte-addressed
+ * one-thread-per-pixel kernels instead of the tiled/vectorised ones; bit 1 = use IEEE division instructions instead
+ * of the verified constant-division sequence.  0 = production.  Used by the parity tests to check every
+ * implementation against the oracle. */
 AVIF_B200_API void avifB200SetKernelPolicy(int policy);
 /* Number of kernels this library has launched from the calling thread since the last reset. */
 AVIF_B200_API uint64_t avifB200KernelLaunchCount(void);
 AVIF_B200_API void avifB200ResetKernelLaunchCount(void);
 /* Name of the kernel variant chosen by the most recent conversion on this thread (static string). */
 AVIF_B200_API const char * avifB200LastKernelName(void);
+/* The kernels divide by call constants (code ranges, kg, 2(1-kb), 2^depth-1) with a 3-operation sequence that is
+ * proven equal to IEEE division for the divisors listed in csrc/verified_divisors.h; any other divisor uses the
+ * hardware's IEEE division.  These expose that list and re-run the exhaustive proof on the device. */
+AVIF_B200_API size_t avifB200VerifiedDivisorCount(void);
+AVIF_B200_API uint32_t avifB200VerifiedDivisorBits(size_t index);
+AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches);
 /* 1 if a CUDA device is usable, else 0 (conversions then fail with AVIF_RESULT_UNKNOWN_ERROR). */
 AVIF_B200_API int avifB200DeviceAvailable(void);
 AVIF_B200_API const char * avifB200Version(void);

@@ -143,6 +143,9 @@ PROTOTYPES = {
     "avifB200KernelLaunchCount": (C.c_uint64, []),
     "avifB200ResetKernelLaunchCount": (None, []),
     "avifB200LastKernelName": (C.c_char_p, []),
+    "avifB200VerifiedDivisorCount": (C.c_size_t, []),
+    "avifB200VerifiedDivisorBits": (C.c_uint32, [C.c_size_t]),
+    "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200DeviceAvailable": (C.c_int, []),
     "avifB200Version": (C.c_char_p, []),
 }

@@ -69,7 +69,7 @@ __device__ __forceinline__ PixelOut convert_pixel(const PixelIn & in, bool hasCh
     PixelOut o;
     /* alpha channel value (ref: src/reformat.c:1464-1486 -> src/alpha.c:9-149) */
     if (J.alphaWrite == AB_ALPHA_COPY) {
-        o.a = J.alphaRescale ? alpha_rescale(in.aRaw, J.yuvMaxF, J.rgbMaxF, J.rgbMax) : in.aRaw;
+        o.a = J.alphaRescale ? alpha_rescale(in.aRaw, J.yuvMaxDiv, J.rgbMaxF, J.rgbMax) : in.aRaw;
     } else if (J.alphaWrite == AB_ALPHA_FILL) {
         o.a = J.rgbMax;
     } else {
@@ -111,9 +111,9 @@ __device__ __forceinline__ PixelOut convert_pixel(const PixelIn & in, bool hasCh
     if (!PLAIN) {
         if (J.alphaMul == AB_MUL_INT_PREMUL || J.alphaMul == AB_MUL_INT_UNPREMUL) { /* ref: src/reformat.c:1575-1585 -> src/alpha.c */
             const bool un = (J.alphaMul == AB_MUL_INT_UNPREMUL);
-            o.c0 = alpha_int(o.c0, o.a, J.rgbMax, J.rgbMaxF, un);
-            o.c1 = alpha_int(o.c1, o.a, J.rgbMax, J.rgbMaxF, un);
-            o.c2 = alpha_int(o.c2, o.a, J.rgbMax, J.rgbMaxF, un);
+            o.c0 = alpha_int(o.c0, o.a, J.rgbMax, J.rgbMaxDiv, un);
+            o.c1 = alpha_int(o.c1, o.a, J.rgbMax, J.rgbMaxDiv, un);
+            o.c2 = alpha_int(o.c2, o.a, J.rgbMax, J.rgbMaxDiv, un);
         }
         if (J.toF16) { /* ref: src/reformat.c:1419-1443: every channel, alpha included */
             o.c0 = to_f16_bits(o.c0, J.f16mul);
@@ -144,6 +144,30 @@ __device__ __forceinline__ void store_pixel(uint8_t * px, const PixelOut & o, co
     if (J.hasAlphaChan) st_chan<RT>(px + J.offA, o.a);
 }
 
+/* blended chroma of pixel (i,j): 4 taps per plane with the reference's neighbour choice and edge replication
+ * (ref: src/reformat.c:766-838) */
+template <typename YT>
+__device__ __forceinline__ void bilinear_chroma(uint32_t i, uint32_t j, const AbY2RJob & J, float & cb, float & cr)
+{
+    const uint32_t ui = i >> 1, uj = j >> J.shiftY;
+    int dc, dr;
+    if (i == 0 || (i == J.width - 1 && (i & 1))) dc = 0;
+    else dc = (i & 1) ? 1 : -1;
+    if (!J.vertBlend || j == 0 || (j == J.height - 1 && (j & 1))) dr = 0;
+    else dr = (j & 1) ? 1 : -1;
+    const uint8_t * u0 = J.u + (int64_t)uj * J.uRB;
+    const uint8_t * v0 = J.v + (int64_t)uj * J.vRB;
+    const uint8_t * u1 = u0 + (int64_t)dr * J.uRB;
+    const uint8_t * v1 = v0 + (int64_t)dr * J.vRB;
+    const uint32_t ub = (uint32_t)((int)ui + dc);
+    const float u00 = norm_uv(ld_code<YT>(u0, ui, J.yuvMax), J), u10 = norm_uv(ld_code<YT>(u0, ub, J.yuvMax), J);
+    const float u01 = norm_uv(ld_code<YT>(u1, ui, J.yuvMax), J), u11 = norm_uv(ld_code<YT>(u1, ub, J.yuvMax), J);
+    const float v00 = norm_uv(ld_code<YT>(v0, ui, J.yuvMax), J), v10 = norm_uv(ld_code<YT>(v0, ub, J.yuvMax), J);
+    const float v01 = norm_uv(ld_code<YT>(v1, ui, J.yuvMax), J), v11 = norm_uv(ld_code<YT>(v1, ub, J.yuvMax), J);
+    cb = bilinear4(u00, u10, u01, u11);
+    cr = bilinear4(v00, v10, v01, v11);
+}
+
 /* gather the inputs of pixel (i,j) */
 template <typename YT, typename RT, int CHROMA>
 __device__ __forceinline__ PixelIn load_pixel(uint32_t i, uint32_t j, const AbY2RJob & J)
@@ -161,24 +185,7 @@ __device__ __forceinline__ PixelIn load_pixel(uint32_t i, uint32_t j, const AbY2
         in.cb = norm_uv(in.u, J);
         in.cr = norm_uv(in.v, J);
     } else if (CHROMA == AB_CHROMA_BILINEAR) {
-        /* neighbour choice with edge replication, ref: src/reformat.c:766-795 */
-        const uint32_t ui = i >> 1, uj = j >> J.shiftY;
-        int dc, dr;
-        if (i == 0 || (i == J.width - 1 && (i & 1))) dc = 0;
-        else dc = (i & 1) ? 1 : -1;
-        if (!J.vertBlend || j == 0 || (j == J.height - 1 && (j & 1))) dr = 0;
-        else dr = (j & 1) ? 1 : -1;
-        const uint8_t * u0 = J.u + (int64_t)uj * J.uRB;
-        const uint8_t * v0 = J.v + (int64_t)uj * J.vRB;
-        const uint8_t * u1 = u0 + (int64_t)dr * J.uRB;
-        const uint8_t * v1 = v0 + (int64_t)dr * J.vRB;
-        const uint32_t ub = (uint32_t)((int)ui + dc);
-        const float u00 = norm_uv(ld_code<YT>(u0, ui, J.yuvMax), J), u10 = norm_uv(ld_code<YT>(u0, ub, J.yuvMax), J);
-        const float u01 = norm_uv(ld_code<YT>(u1, ui, J.yuvMax), J), u11 = norm_uv(ld_code<YT>(u1, ub, J.yuvMax), J);
-        const float v00 = norm_uv(ld_code<YT>(v0, ui, J.yuvMax), J), v10 = norm_uv(ld_code<YT>(v0, ub, J.yuvMax), J);
-        const float v01 = norm_uv(ld_code<YT>(v1, ui, J.yuvMax), J), v11 = norm_uv(ld_code<YT>(v1, ub, J.yuvMax), J);
-        in.cb = bilinear4(u00, u10, u01, u11);
-        in.cr = bilinear4(v00, v10, v01, v11);
+        bilinear_chroma<YT>(i, j, J, in.cb, in.cr);
     }
     if (J.a) in.aRaw = ld_sample<YT>(J.a + (int64_t)j * J.aRB, i);
     if (J.alphaWrite == AB_ALPHA_KEEP && J.hasAlphaChan) {
@@ -208,11 +215,14 @@ __global__ void __launch_bounds__(256) y2r_generic_kernel(const __grid_constant_
 }
 
 /* ---------------------------------------------------------------------------------------------- */
-/* tiled kernel: a warp converts 256 consecutive pixels of one row; the packed pixels are staged in   */
-/* shared memory and written out as 16-byte coalesced vectors                                        */
+/* tiled kernel: a warp converts 256 consecutive pixels of one row.  Lane l owns the pixel PAIRS          */
+/* l, l+32, l+64, l+96 of the tile: a pair is one 32-bit (16-bit samples) or 16-bit (8-bit samples) load  */
+/* per plane, one shared chroma sample for 4:2:x, and one 16/12/8/6/4/2-byte packed shared-memory store.  */
+/* All loads of the tile are issued before any arithmetic; the packed tile then leaves the SM as 16-byte   */
+/* coalesced vector stores whatever the pixel format.                                                      */
 
-constexpr int kTilePx = 256;   /* pixels per warp tile */
-constexpr int kPxPerLane = 8;  /* kTilePx / 32 */
+constexpr int kTilePx = 256;       /* pixels per warp tile */
+constexpr int kPairsPerLane = 4;   /* kTilePx / 2 / 32 */
 constexpr int kWarpsPerBlock = 8;
 
 /* copy `n` bytes of a warp's staging tile to global memory with the widest granularity the address allows */
@@ -236,6 +246,115 @@ __device__ __forceinline__ void warp_copy_out(uint8_t * __restrict__ dst, const 
     }
 }
 
+/* two horizontally adjacent samples of one plane row, x even; `both` = the second one exists */
+template <typename T>
+__device__ __forceinline__ void ld_pair(const uint8_t * row, uint32_t x, bool both, bool aligned, uint32_t & s0, uint32_t & s1)
+{
+    if (both && aligned) {
+        if (sizeof(T) == 2) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row) + (x >> 1));
+            s0 = w & 0xFFFFu;
+            s1 = w >> 16;
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint16_t *>(row) + (x >> 1));
+            s0 = w & 0xFFu;
+            s1 = w >> 8;
+        }
+    } else {
+        s0 = ld_sample<T>(row, x);
+        s1 = both ? ld_sample<T>(row, x + 1) : 0;
+    }
+}
+
+/* memory-order channel list of one converted pixel: n values of sizeof(RT) bytes each */
+template <bool PLAIN>
+__device__ __forceinline__ int channel_list(const PixelOut & o, const AbY2RJob & J, uint32_t ch[4])
+{
+    if (!PLAIN && (J.is565 || J.isGray)) {
+        if (J.is565 || !J.hasAlphaChan) {
+            ch[0] = o.c0;
+            return 1;
+        }
+        ch[0] = J.alphaFirst ? o.a : o.c0;
+        ch[1] = J.alphaFirst ? o.c0 : o.a;
+        return 2;
+    }
+    const uint32_t first = J.swapRB ? o.c2 : o.c0, last = J.swapRB ? o.c0 : o.c2;
+    if (!J.hasAlphaChan) {
+        ch[0] = first;
+        ch[1] = o.c1;
+        ch[2] = last;
+        return 3;
+    }
+    if (J.alphaFirst) {
+        ch[0] = o.a;
+        ch[1] = first;
+        ch[2] = o.c1;
+        ch[3] = last;
+    } else {
+        ch[0] = first;
+        ch[1] = o.c1;
+        ch[2] = last;
+        ch[3] = o.a;
+    }
+    return 4;
+}
+
+/* pack one pixel pair (or the single last pixel of an odd row) into the staging tile at pixel index p0 */
+template <typename RT, bool PLAIN>
+__device__ __forceinline__ void stage_pair(uint8_t * stage, uint32_t p0, const PixelOut & o0, const PixelOut & o1, bool both, const AbY2RJob & J)
+{
+    uint32_t a[4], b[4];
+    const int n = channel_list<PLAIN>(o0, J, a);
+    channel_list<PLAIN>(o1, J, b);
+    const bool wide = (sizeof(RT) == 2) || (!PLAIN && J.is565); /* 16-bit units */
+    uint8_t * px = stage + p0 * J.pixBytes;
+    if (!both) { /* odd tail: plain per-channel stores */
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < n) {
+                if (wide) st_chan<uint16_t>(px + 2 * c, a[c]);
+                else st_chan<uint8_t>(px + c, a[c]);
+            }
+        }
+        return;
+    }
+    if (wide) {
+        if (n == 4) {
+            *reinterpret_cast<uint4 *>(px) = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+        } else if (n == 3) {
+            uint32_t * w = reinterpret_cast<uint32_t *>(px); /* 12 bytes per pair: 4-byte aligned */
+            w[0] = a[0] | (a[1] << 16);
+            w[1] = a[2] | (b[0] << 16);
+            w[2] = b[1] | (b[2] << 16);
+        } else if (n == 2) {
+            *reinterpret_cast<uint2 *>(px) = make_uint2(a[0] | (a[1] << 16), b[0] | (b[1] << 16));
+        } else {
+            *reinterpret_cast<uint32_t *>(px) = a[0] | (b[0] << 16);
+        }
+    } else {
+        if (n == 4) {
+            *reinterpret_cast<uint2 *>(px) = make_uint2(a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24), b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24));
+        } else if (n == 3) {
+            uint16_t * h = reinterpret_cast<uint16_t *>(px); /* 6 bytes per pair: 2-byte aligned */
+            h[0] = (uint16_t)(a[0] | (a[1] << 8));
+            h[1] = (uint16_t)(a[2] | (b[0] << 8));
+            h[2] = (uint16_t)(b[1] | (b[2] << 8));
+        } else if (n == 2) {
+            *reinterpret_cast<uint32_t *>(px) = a[0] | (a[1] << 8) | (b[0] << 16) | (b[1] << 24);
+        } else {
+            *reinterpret_cast<uint16_t *>(px) = (uint16_t)(a[0] | (b[0] << 8));
+        }
+    }
+}
+
+struct PairIn {
+    uint32_t y0, y1;
+    uint32_t u0, u1, v0, v1; /* raw chroma codes: one per pixel (4:4:4) or u0/v0 shared (nearest) */
+    uint32_t a0, a1;
+    float cb0, cr0, cb1, cr1; /* bilinear only: blended normalised chroma */
+};
+
 template <typename YT, typename RT, int CHROMA, bool PLAIN>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) y2r_tiled_kernel(const __grid_constant__ AbY2RJob J)
 {
@@ -245,20 +364,79 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) y2r_tiled_kernel(const __
     if (j >= J.rowEnd) return; /* warp-uniform */
     const uint32_t x0 = blockIdx.x * kTilePx;
     uint8_t * stage = stageAll[warp];
+    const bool aligned = J.pairAligned != 0;
 
-    PixelIn in[kPxPerLane];
+    const uint8_t * rowY = J.y + (int64_t)j * J.yRB;
+    const uint8_t * rowA = J.a ? J.a + (int64_t)j * J.aRB : nullptr;
+    const uint32_t uj = j >> J.shiftY;
+    const uint8_t * rowU = (CHROMA != AB_CHROMA_NONE) ? J.u + (int64_t)uj * J.uRB : nullptr;
+    const uint8_t * rowV = (CHROMA != AB_CHROMA_NONE) ? J.v + (int64_t)uj * J.vRB : nullptr;
+    const bool keepAlpha = (J.alphaWrite == AB_ALPHA_KEEP) && J.hasAlphaChan;
+
+    PairIn in[kPairsPerLane];
 #pragma unroll
-    for (int k = 0; k < kPxPerLane; ++k) {
-        const uint32_t i = x0 + lane + 32 * k;
-        if (i < J.width) in[k] = load_pixel<YT, RT, CHROMA>(i, j, J);
+    for (int k = 0; k < kPairsPerLane; ++k) {
+        const uint32_t i0 = x0 + 2 * (lane + 32 * k);
+        PairIn & p = in[k];
+        p.y0 = p.y1 = p.u0 = p.u1 = p.v0 = p.v1 = p.a0 = p.a1 = 0;
+        p.cb0 = p.cr0 = p.cb1 = p.cr1 = 0.5f;
+        if (i0 >= J.width) continue;
+        const bool both = (i0 + 1 < J.width);
+        ld_pair<YT>(rowY, i0, both, aligned, p.y0, p.y1);
+        if (CHROMA == AB_CHROMA_FULL) {
+            ld_pair<YT>(rowU, i0, both, aligned, p.u0, p.u1);
+            ld_pair<YT>(rowV, i0, both, aligned, p.v0, p.v1);
+        } else if (CHROMA == AB_CHROMA_NEAREST) {
+            p.u0 = ld_sample<YT>(rowU, i0 >> 1);
+            p.v0 = ld_sample<YT>(rowV, i0 >> 1);
+        } else if (CHROMA == AB_CHROMA_BILINEAR) {
+            bilinear_chroma<YT>(i0, j, J, p.cb0, p.cr0);
+            if (both) bilinear_chroma<YT>(i0 + 1, j, J, p.cb1, p.cr1);
+        }
+        if (rowA) ld_pair<YT>(rowA, i0, both, aligned, p.a0, p.a1);
+        if (keepAlpha) {
+            const uint8_t * d = J.rgb + (int64_t)j * J.rgbRB + (int64_t)i0 * J.pixBytes + J.offA;
+            p.a0 = ld_sample<RT>(d, 0);
+            if (both) p.a1 = ld_sample<RT>(d + J.pixBytes, 0);
+        }
     }
 #pragma unroll
-    for (int k = 0; k < kPxPerLane; ++k) {
-        const uint32_t p = lane + 32 * k;
-        if (x0 + p < J.width) {
-            const PixelOut o = convert_pixel<PLAIN>(in[k], CHROMA != AB_CHROMA_NONE, J);
-            store_pixel<RT, PLAIN>(stage + p * J.pixBytes, o, J);
+    for (int k = 0; k < kPairsPerLane; ++k) {
+        const uint32_t pidx = 2 * (lane + 32 * k);
+        const uint32_t i0 = x0 + pidx;
+        if (i0 >= J.width) continue;
+        const bool both = (i0 + 1 < J.width);
+        const PairIn & p = in[k];
+        PixelIn q0, q1;
+        q0.y = (sizeof(YT) == 2) ? min(p.y0, J.yuvMax) : p.y0;
+        q1.y = (sizeof(YT) == 2) ? min(p.y1, J.yuvMax) : p.y1;
+        q0.cb = q0.cr = q1.cb = q1.cr = 0.5f;
+        q0.u = q0.v = q1.u = q1.v = 0;
+        if (CHROMA == AB_CHROMA_FULL) {
+            q0.u = (sizeof(YT) == 2) ? min(p.u0, J.yuvMax) : p.u0;
+            q0.v = (sizeof(YT) == 2) ? min(p.v0, J.yuvMax) : p.v0;
+            q1.u = (sizeof(YT) == 2) ? min(p.u1, J.yuvMax) : p.u1;
+            q1.v = (sizeof(YT) == 2) ? min(p.v1, J.yuvMax) : p.v1;
+            q0.cb = norm_uv(q0.u, J);
+            q0.cr = norm_uv(q0.v, J);
+            q1.cb = norm_uv(q1.u, J);
+            q1.cr = norm_uv(q1.v, J);
+        } else if (CHROMA == AB_CHROMA_NEAREST) {
+            q0.u = q1.u = (sizeof(YT) == 2) ? min(p.u0, J.yuvMax) : p.u0;
+            q0.v = q1.v = (sizeof(YT) == 2) ? min(p.v0, J.yuvMax) : p.v0;
+            q0.cb = q1.cb = norm_uv(q0.u, J);
+            q0.cr = q1.cr = norm_uv(q0.v, J);
+        } else if (CHROMA == AB_CHROMA_BILINEAR) {
+            q0.cb = p.cb0;
+            q0.cr = p.cr0;
+            q1.cb = p.cb1;
+            q1.cr = p.cr1;
         }
+        q0.aRaw = q0.aDst = p.a0;
+        q1.aRaw = q1.aDst = p.a1;
+        const PixelOut o0 = convert_pixel<PLAIN>(q0, CHROMA != AB_CHROMA_NONE, J);
+        const PixelOut o1 = convert_pixel<PLAIN>(q1, CHROMA != AB_CHROMA_NONE, J);
+        stage_pair<RT, PLAIN>(stage, pidx, o0, o1, both, J);
     }
     __syncwarp();
     const uint32_t npx = min((uint32_t)kTilePx, J.width - x0);
@@ -272,15 +450,20 @@ struct YUVf {
     float y, u, v;
 };
 
-template <typename RT>
-__device__ __forceinline__ YUVf rgb_pixel_to_yuv(const uint8_t * px, const AbR2YJob & J)
+struct RgbCodes {
+    uint32_t r, g, b, a; /* gray input: the gray code is in r */
+};
+
+/* ref: src/reformat.c:311-387 (colour) and :479-511 (gray), one pixel, codes already in registers */
+__device__ __forceinline__ YUVf rgb_codes_to_yuv(const RgbCodes & px, const AbR2YJob & J)
 {
     YUVf o;
     const float m = J.rgbMaxF;
-    if (J.isGray) { /* ref: src/reformat.c:479-511 */
-        float g = __fdiv_rn(u2f(ld_sample<RT>(px + J.offGray, 0)), m);
+    float a = 1.0f;
+    if (J.alphaMul != AB_MUL_NONE) a = div_const(u2f(px.a), J.rgbMaxDiv);
+    if (J.isGray) {
+        float g = div_const(u2f(px.r), J.rgbMaxDiv);
         if (J.alphaMul != AB_MUL_NONE) {
-            const float a = __fdiv_rn(u2f(ld_sample<RT>(px + J.offA, 0)), m);
             if (a == 0.0f) g = 0.0f;
             else if (a < 1.0f) g = (J.alphaMul == AB_MUL_FLOAT_MUL) ? __fmul_rn(g, a) : min1(__fdiv_rn(g, a));
         }
@@ -288,11 +471,10 @@ __device__ __forceinline__ YUVf rgb_pixel_to_yuv(const uint8_t * px, const AbR2Y
         o.u = o.v = 0.0f;
         return o;
     }
-    float r = __fdiv_rn(u2f(ld_sample<RT>(px + J.offR, 0)), m); /* true divisions, ref: :312-323 */
-    float g = __fdiv_rn(u2f(ld_sample<RT>(px + J.offG, 0)), m);
-    float b = __fdiv_rn(u2f(ld_sample<RT>(px + J.offB, 0)), m);
+    float r = div_const(u2f(px.r), J.rgbMaxDiv); /* c / rgbMaxF: true quotients, ref: :312-323 */
+    float g = div_const(u2f(px.g), J.rgbMaxDiv);
+    float b = div_const(u2f(px.b), J.rgbMaxDiv);
     if (J.alphaMul != AB_MUL_NONE) { /* ref: :325-358 */
-        const float a = __fdiv_rn(u2f(ld_sample<RT>(px + J.offA, 0)), m);
         if (a == 0.0f) {
             r = g = b = 0.0f;
         } else if (a < 1.0f) {
@@ -310,8 +492,8 @@ __device__ __forceinline__ YUVf rgb_pixel_to_yuv(const uint8_t * px, const AbR2Y
     if (J.mode == AB_MODE_COEFF) { /* ref: :383-386 */
         const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, r), __fmul_rn(J.kg, g)), __fmul_rn(J.kb, b));
         o.y = Y;
-        o.u = __fdiv_rn(__fsub_rn(b, Y), J.du);
-        o.v = __fdiv_rn(__fsub_rn(r, Y), J.dv);
+        o.u = div_const(__fsub_rn(b, Y), J.du);
+        o.v = div_const(__fsub_rn(r, Y), J.dv);
     } else if (J.mode == AB_MODE_IDENTITY) { /* ref: :361-365 */
         o.y = g;
         o.u = b;
@@ -337,49 +519,187 @@ __device__ __forceinline__ YUVf rgb_pixel_to_yuv(const uint8_t * px, const AbR2Y
     return o;
 }
 
-/* ref: src/reformat.c:197-219 */
+/* ref: src/reformat.c:197-219: clamp((int)floorf(v*range + bias + 0.5f), 0, yuvMax) */
 __device__ __forceinline__ uint32_t quant_yuv(float v, float range, float bias, uint32_t yuvMax)
 {
     const int q = (int)round_half_up(__fadd_rn(__fmul_rn(v, range), bias));
     return (uint32_t)min(max(q, 0), (int)yuvMax);
 }
 
-/* one thread = one 2x2 block, exactly the reference's block walk (ref: src/reformat.c:295-470) */
-template <typename RT, typename YT>
+template <typename RT>
+__device__ __forceinline__ RgbCodes load_rgb_scalar(const uint8_t * px, const AbR2YJob & J)
+{
+    RgbCodes c;
+    c.r = c.g = c.b = c.a = 0;
+    if (J.isGray) {
+        c.r = ld_sample<RT>(px + J.offGray, 0);
+    } else {
+        c.r = ld_sample<RT>(px + J.offR, 0);
+        c.g = ld_sample<RT>(px + J.offG, 0);
+        c.b = ld_sample<RT>(px + J.offB, 0);
+    }
+    if (J.hasAlphaChan) c.a = ld_sample<RT>(px + J.offA, 0);
+    return c;
+}
+
+/* memory-order channel values -> named channels (inverse of channel_list) */
+__device__ __forceinline__ RgbCodes name_channels(const uint32_t ch[4], const AbR2YJob & J)
+{
+    RgbCodes c;
+    c.g = c.b = c.a = 0;
+    if (J.isGray) {
+        if (J.nChan == 1) {
+            c.r = ch[0];
+        } else {
+            c.r = J.alphaFirst ? ch[1] : ch[0];
+            c.a = J.alphaFirst ? ch[0] : ch[1];
+        }
+        return c;
+    }
+    uint32_t x0, x1, x2;
+    if (J.nChan == 4 && J.alphaFirst) {
+        c.a = ch[0];
+        x0 = ch[1];
+        x1 = ch[2];
+        x2 = ch[3];
+    } else {
+        x0 = ch[0];
+        x1 = ch[1];
+        x2 = ch[2];
+        if (J.nChan == 4) c.a = ch[3];
+    }
+    c.r = J.swapRB ? x2 : x0;
+    c.g = x1;
+    c.b = J.swapRB ? x0 : x2;
+    return c;
+}
+
+/* two horizontally adjacent pixels with one vector load (rgb base/stride aligned to the pair size) */
+template <typename RT>
+__device__ __forceinline__ void load_rgb_pair_vec(const uint8_t * px, const AbR2YJob & J, RgbCodes & p0, RgbCodes & p1)
+{
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    const uint32_t pairBytes = 2u * J.pixBytes;
+    if (pairBytes == 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(px));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if (pairBytes == 12) {
+        const uint32_t * q = reinterpret_cast<const uint32_t *>(px);
+        w[0] = __ldg(q); w[1] = __ldg(q + 1); w[2] = __ldg(q + 2);
+    } else if (pairBytes == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(px));
+        w[0] = v.x; w[1] = v.y;
+    } else if (pairBytes == 6) {
+        const uint16_t * q = reinterpret_cast<const uint16_t *>(px);
+        w[0] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 16);
+        w[1] = __ldg(q + 2);
+    } else if (pairBytes == 4) {
+        w[0] = __ldg(reinterpret_cast<const uint32_t *>(px));
+    } else {
+        w[0] = __ldg(reinterpret_cast<const uint16_t *>(px));
+    }
+    uint32_t a[4] = { 0, 0, 0, 0 }, b[4] = { 0, 0, 0, 0 };
+    const int n = J.nChan;
+    if (sizeof(RT) == 2) { /* unit k of the pair = 16 bits at w[k/2] */
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < n) {
+                a[k] = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                const int kb = k + n;
+                b[k] = (w[kb >> 1] >> ((kb & 1) * 16)) & 0xFFFFu;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < n) {
+                a[k] = (w[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                const int kb = k + n;
+                b[k] = (w[kb >> 2] >> ((kb & 3) * 8)) & 0xFFu;
+            }
+        }
+    }
+    p0 = name_channels(a, J);
+    p1 = name_channels(b, J);
+}
+
+/* store one or two horizontally adjacent samples of a plane row */
+template <typename YT>
+__device__ __forceinline__ void st_pair(uint8_t * row, uint32_t x, uint32_t s0, uint32_t s1, bool both, bool aligned)
+{
+    if (both && aligned) {
+        if (sizeof(YT) == 2) reinterpret_cast<uint32_t *>(row)[x >> 1] = s0 | (s1 << 16);
+        else reinterpret_cast<uint16_t *>(row)[x >> 1] = (uint16_t)(s0 | (s1 << 8));
+    } else {
+        reinterpret_cast<YT *>(row)[x] = (YT)s0;
+        if (both) reinterpret_cast<YT *>(row)[x + 1] = (YT)s1;
+    }
+}
+
+/* One thread = one 2x2 block, exactly the reference's block walk (ref: src/reformat.c:295-470).  Lanes own
+ * horizontally consecutive blocks, so a warp reads two row segments of 64 pixels with one vector load per
+ * pixel pair and writes Y/A (and 4:4:4 chroma) as packed pairs, subsampled chroma as one sample per lane.
+ * VEC=false is the byte-addressed variant (any alignment; also the cross-check implementation). */
+template <typename RT, typename YT, bool VEC>
 __global__ void __launch_bounds__(256) r2y_block_kernel(const __grid_constant__ AbR2YJob J)
 {
     const uint32_t oi = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const uint32_t oj = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
     if (oi >= J.width || oj >= J.height) return;
-    const uint32_t bw = (oi + 1 >= J.width) ? 1 : 2, bh = (oj + 1 >= J.height) ? 1 : 2;
-    float bu[2][2], bv[2][2]; /* [bj][bi] */
+    const bool both = (oi + 1 < J.width);
+    const uint32_t bh = (oj + 1 >= J.height) ? 1 : 2;
+    const bool srcVec = VEC && J.srcPairAligned && both;
+    const bool dstVec = VEC && J.dstPairAligned;
+    const bool full444 = J.hasChroma && !J.isGray && J.shiftX == 0;
+
+    RgbCodes px[2][2];
 #pragma unroll
     for (uint32_t bj = 0; bj < 2; ++bj) {
-#pragma unroll
-        for (uint32_t bi = 0; bi < 2; ++bi) {
-            bu[bj][bi] = bv[bj][bi] = 0.0f;
-            if (bj < bh && bi < bw) {
-                const uint32_t i = oi + bi, j = oj + bj;
-                const uint8_t * px = J.rgb + (int64_t)j * J.rgbRB + (int64_t)i * J.pixBytes;
-                const YUVf c = rgb_pixel_to_yuv<RT>(px, J);
-                bu[bj][bi] = c.u;
-                bv[bj][bi] = c.v;
-                st_chan<YT>(J.y + (int64_t)j * J.yRB + (int64_t)i * sizeof(YT), quant_yuv(c.y, J.rangeY, J.biasY, J.yuvMax));
-                if (J.hasChroma && !J.isGray && J.shiftX == 0) { /* 4:4:4 */
-                    st_chan<YT>(J.u + (int64_t)j * J.uRB + (int64_t)i * sizeof(YT), quant_yuv(c.u, J.rangeUV, J.biasUV, J.yuvMax));
-                    st_chan<YT>(J.v + (int64_t)j * J.vRB + (int64_t)i * sizeof(YT), quant_yuv(c.v, J.rangeUV, J.biasUV, J.yuvMax));
-                }
-                if (J.alphaWrite == AB_ALPHA_COPY) { /* ref: :545-569 -> src/alpha.c:37-149 */
-                    const uint32_t a = ld_sample<RT>(px + J.offA, 0);
-                    st_chan<YT>(J.a + (int64_t)j * J.aRB + (int64_t)i * sizeof(YT),
-                                J.alphaRescale ? alpha_rescale(a, J.rgbMaxF, J.yuvMaxF, J.yuvMax) : a);
-                } else if (J.alphaWrite == AB_ALPHA_FILL) {
-                    st_chan<YT>(J.a + (int64_t)j * J.aRB + (int64_t)i * sizeof(YT), J.yuvMax);
-                }
+        if (bj < bh) {
+            const uint8_t * p = J.rgb + (int64_t)(oj + bj) * J.rgbRB + (int64_t)oi * J.pixBytes;
+            if (srcVec) {
+                load_rgb_pair_vec<RT>(p, J, px[bj][0], px[bj][1]);
+            } else {
+                px[bj][0] = load_rgb_scalar<RT>(p, J);
+                if (both) px[bj][1] = load_rgb_scalar<RT>(p + J.pixBytes, J);
             }
         }
     }
+
+    float bu[2][2], bv[2][2]; /* [bj][bi] */
+#pragma unroll
+    for (uint32_t bj = 0; bj < 2; ++bj) {
+        bu[bj][0] = bu[bj][1] = bv[bj][0] = bv[bj][1] = 0.0f;
+        if (bj >= bh) continue;
+        const uint32_t j = oj + bj;
+        uint32_t yq[2] = { 0, 0 }, uq[2] = { 0, 0 }, vq[2] = { 0, 0 }, aq[2] = { 0, 0 };
+#pragma unroll
+        for (uint32_t bi = 0; bi < 2; ++bi) {
+            if (bi == 1 && !both) continue;
+            const YUVf c = rgb_codes_to_yuv(px[bj][bi], J);
+            bu[bj][bi] = c.u;
+            bv[bj][bi] = c.v;
+            yq[bi] = quant_yuv(c.y, J.rangeY, J.biasY, J.yuvMax);
+            if (full444) {
+                uq[bi] = quant_yuv(c.u, J.rangeUV, J.biasUV, J.yuvMax);
+                vq[bi] = quant_yuv(c.v, J.rangeUV, J.biasUV, J.yuvMax);
+            }
+            if (J.alphaWrite == AB_ALPHA_COPY) { /* ref: :545-569 -> src/alpha.c:37-149 */
+                const uint32_t a = px[bj][bi].a;
+                aq[bi] = J.alphaRescale ? alpha_rescale(a, J.rgbMaxDiv, J.yuvMaxF, J.yuvMax) : a;
+            } else {
+                aq[bi] = J.yuvMax;
+            }
+        }
+        st_pair<YT>(J.y + (int64_t)j * J.yRB, oi, yq[0], yq[1], both, dstVec);
+        if (full444) {
+            st_pair<YT>(J.u + (int64_t)j * J.uRB, oi, uq[0], uq[1], both, dstVec);
+            st_pair<YT>(J.v + (int64_t)j * J.vRB, oi, vq[0], vq[1], both, dstVec);
+        }
+        if (J.alphaWrite != AB_ALPHA_KEEP) st_pair<YT>(J.a + (int64_t)j * J.aRB, oi, aq[0], aq[1], both, dstVec);
+    }
     if (!J.hasChroma || J.isGray || J.shiftX == 0) return;
+    const uint32_t bw = both ? 2 : 1;
     if (J.shiftY) { /* 4:2:0: ordered sum TL,TR,BL,BR over the samples that exist (ref: :413-440) */
         float su = 0.0f, sv = 0.0f;
 #pragma unroll
@@ -433,7 +753,11 @@ __global__ void __launch_bounds__(256) alpha_kernel(const __grid_constant__ AbAl
         st_chan<DT>(d, a);
     } else {
         const uint32_t srcMax = (1u << J.srcDepth) - 1, dstMax = (1u << J.dstDepth) - 1;
-        st_chan<DT>(d, alpha_rescale(a, (float)srcMax, (float)dstMax, dstMax));
+        AbDiv sd;
+        sd.d = (float)srcMax;
+        sd.r = 0.0f;
+        sd.exact = 0;
+        st_chan<DT>(d, alpha_rescale(a, sd, (float)dstMax, dstMax));
     }
 }
 
@@ -446,12 +770,11 @@ __global__ void __launch_bounds__(256) premultiply_kernel(const __grid_constant_
     if (i >= J.width || j >= J.height) return;
     RT * px = reinterpret_cast<RT *>(J.pixels + (int64_t)j * J.rowBytes) + (size_t)i * J.nChan;
     const uint32_t max = (1u << J.depth) - 1;
-    const float maxF = (float)max;
     const uint32_t a = px[J.aIdx];
     if (a >= max) return;
     for (int c = 0; c < J.nColor; ++c) {
         RT * cp = px + J.cIdx[c];
-        *cp = (RT)alpha_int(*cp, a, max, maxF, J.unmultiply != 0);
+        *cp = (RT)alpha_int(*cp, a, max, J.maxDiv, J.unmultiply != 0);
     }
 }
 
@@ -493,6 +816,24 @@ __global__ void __launch_bounds__(256) copy_pad_kernel(const uint8_t * src, int6
     if (i >= dstW || j >= dstH) return;
     const uint32_t si = min(i, srcW - 1), sj = min(j, srcH - 1);
     reinterpret_cast<T *>(dst + (int64_t)j * dstRB)[i] = reinterpret_cast<const T *>(src + (int64_t)sj * srcRB)[si];
+}
+
+/* self-test of div_const's fast form: all 2^32 binary32 patterns x with x == +0 or 2^-60 <= |x| <= 2^60 */
+__global__ void __launch_bounds__(256) div_selftest_kernel(float d, float r, unsigned long long * mismatches)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+        const uint32_t u = (uint32_t)b;
+        const float x = __uint_as_float(u);
+        const float ax = fabsf(x);
+        if (!(u == 0u || (ax >= 8.6736173798840355e-19f && ax <= 1152921504606846976.0f))) continue;
+        const float q = __fmul_rn(x, r);
+        const float e = __fmaf_rn(-q, d, x);
+        const float fast = __fmaf_rn(e, r, q);
+        if (__float_as_uint(fast) != __float_as_uint(__fdiv_rn(x, d))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -566,19 +907,24 @@ int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const cha
 
 int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
-    (void)forceGeneric;
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->height == 0) return 0;
     const dim3 block(32, 8);
     const dim3 grid = grid2d((job->width + 1) / 2, (job->height + 1) / 2, block);
+#define AB_R2Y(RT, YT)                                                                      \
+    do {                                                                                    \
+        if (forceGeneric) r2y_block_kernel<RT, YT, false><<<grid, block, 0, st>>>(*job);    \
+        else r2y_block_kernel<RT, YT, true><<<grid, block, 0, st>>>(*job);                  \
+    } while (0)
     if (job->rgbBytes == 2) {
-        if (job->yuvBytes == 2) r2y_block_kernel<uint16_t, uint16_t><<<grid, block, 0, st>>>(*job);
-        else r2y_block_kernel<uint16_t, uint8_t><<<grid, block, 0, st>>>(*job);
+        if (job->yuvBytes == 2) AB_R2Y(uint16_t, uint16_t);
+        else AB_R2Y(uint16_t, uint8_t);
     } else {
-        if (job->yuvBytes == 2) r2y_block_kernel<uint8_t, uint16_t><<<grid, block, 0, st>>>(*job);
-        else r2y_block_kernel<uint8_t, uint8_t><<<grid, block, 0, st>>>(*job);
+        if (job->yuvBytes == 2) AB_R2Y(uint8_t, uint16_t);
+        else AB_R2Y(uint8_t, uint8_t);
     }
-    if (kernelName) *kernelName = "r2y_block";
+#undef AB_R2Y
+    if (kernelName) *kernelName = forceGeneric ? "r2y_block_generic" : "r2y_block_vec";
     return finish_launch();
 }
 
@@ -649,6 +995,23 @@ int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t 
     if (bytesPerSample == 2) copy_pad_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)stream>>>(src, srcRB, srcW, srcH, dst, dstRB, dstW, dstH);
     else copy_pad_kernel<uint8_t><<<grid, block, 0, (cudaStream_t)stream>>>(src, srcRB, srcW, srcH, dst, dstRB, dstW, dstH);
     return finish_launch();
+}
+
+int abDivSelfTest(float d, unsigned long long * mismatches, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long * dev = nullptr;
+    int err = (int)cudaMalloc((void **)&dev, sizeof(*dev));
+    if (err) return err;
+    err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
+    if (!err) {
+        div_selftest_kernel<<<148 * 16, 256, 0, st>>>(d, 1.0f / d, dev);
+        err = finish_launch();
+    }
+    if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);
+    if (!err) err = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return err;
 }
 
 uint64_t abLaunchCount(void) { return g_launches; }

@@ -48,8 +48,10 @@ typedef struct AbY2RJob {
     float biasY, biasUV;
     AbDiv rangeY, rangeUV; /* identity mode: UV uses Y's bias/range (reformat.c:587-589) */
     AbDiv kg;
+    AbDiv yuvMaxDiv, rgbMaxDiv; /* (2^depth - 1) as divisors: alpha normalisation / rescale / premultiply */
     float c1, c2, c3, c4; /* 2(1-kr), 2(1-kb), kr(1-kr), kb(1-kb) as float constants (reformat.c:1014-1016) */
     float f16mul;         /* 2^-112 * (1/65535)  (reformat.c:1429-1430) */
+    float magicBiasY, magicBiasUV; /* 2^23 + bias: (float)cp - bias == as_float(cp | 0x4B000000) - magicBias, exactly */
     uint8_t yuvBytes, rgbBytes; /* bytes per sample / per channel */
     uint8_t chroma;             /* AB_CHROMA_* */
     uint8_t vertBlend;          /* bilinear also blends rows (4:2:0); 0 for 4:2:2 */
@@ -63,6 +65,9 @@ typedef struct AbY2RJob {
     uint8_t alphaRescale; /* 1: source alpha depth != rgb depth -> float rescale (alpha.c:93-97) */
     uint8_t alphaMul;   /* AB_MUL_* */
     uint8_t toF16;
+    uint8_t swapRB;      /* B before R in memory (BGR, BGRA, ABGR) */
+    uint8_t alphaFirst;  /* alpha precedes colour / gray (ARGB, ABGR, AGRAY) */
+    uint8_t pairAligned; /* every source plane base and stride is a multiple of 2*yuvBytes: pixel pairs load as one word */
 } AbY2RJob;
 
 typedef struct AbR2YJob {
@@ -78,7 +83,8 @@ typedef struct AbR2YJob {
     float biasY, biasUV, rangeY, rangeUV; /* identity: UV quantised with Y's (reformat.c:212-213) */
     float rangeYdiv, rangeUVdiv;          /* divisors of the YCgCo-R branch: always the true Y / UV ranges (reformat.c:379-381) */
     float kr, kg, kb;
-    float du, dv; /* 2(1-kb), 2(1-kr) */
+    AbDiv du, dv;     /* 2(1-kb), 2(1-kr) (reformat.c:385-386) */
+    AbDiv rgbMaxDiv;  /* c / rgbMaxF (reformat.c:312-323) */
     uint8_t rgbBytes, yuvBytes;
     uint8_t shiftX, shiftY; /* chroma subsampling of the destination; both 0 for 4:4:4 */
     uint8_t hasChroma;      /* 0 for 4:0:0 */
@@ -88,6 +94,9 @@ typedef struct AbR2YJob {
     uint8_t alphaMul;   /* AB_MUL_NONE / FLOAT_MUL / FLOAT_UNMUL */
     uint8_t alphaWrite; /* AB_ALPHA_KEEP (no plane) / COPY (from RGB alpha) / FILL */
     uint8_t alphaRescale;
+    uint8_t nChan, swapRB, alphaFirst, hasAlphaChan;
+    uint8_t srcPairAligned; /* rgb base and stride allow one vector load per pixel pair */
+    uint8_t dstPairAligned; /* every destination plane base and stride is a multiple of 2*yuvBytes */
 } AbR2YJob;
 
 /* avifAlphaParams with device pointers (alpha.c:9-149) */
@@ -106,6 +115,7 @@ typedef struct AbRgbPassJob {
     int64_t rowBytes;
     uint32_t width, height;
     uint32_t depth;
+    AbDiv maxDiv; /* 2^depth - 1 */
     uint8_t aIdx, nColor, nChan; /* channel indices, alpha.c:173-333 */
     uint8_t cIdx[3];
     uint8_t unmultiply;
@@ -124,6 +134,8 @@ int abLaunchFill8(uint8_t * dst, size_t count, uint32_t value, void * stream);
 int abLaunchLimitedToFull(uint8_t * plane, int64_t rowBytes, uint32_t width, uint32_t height, uint32_t depth, void * stream);
 int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t srcH, uint8_t * dst, int64_t dstRB, uint32_t dstW,
                     uint32_t dstH, uint32_t bytesPerSample, void * stream);
+/* exhaustive device check of div_const's fast form for divisor d (counts x whose result differs from x/d) */
+int abDivSelfTest(float d, unsigned long long * mismatches, void * stream);
 /* number of kernel launches issued by the calling thread through the functions above */
 uint64_t abLaunchCount(void);
 void abLaunchCountReset(void);

@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include "plan.h"
+#include "verified_divisors.h"
 
 #define AB_VERSION "libavif_b200 0.1 (sm_100a)"
 
@@ -136,6 +137,7 @@ typedef struct AbCtx {
     const char * lastKernel;
 } AbCtx;
 static _Thread_local AbCtx tls;
+static _Thread_local int tlsExactDivision = 0; /* 1: always use IEEE division instructions (tests cross-check both forms) */
 
 static avifResult cudaToResult(int err)
 {
@@ -149,6 +151,8 @@ static avifResult cudaToResult(int err)
         if (abErr_ != cudaSuccess) return cudaToResult(abErr_); \
     } while (0)
 
+static avifResult ctxInit(void);
+
 int avifB200DeviceAvailable(void)
 {
     int n = 0;
@@ -159,10 +163,30 @@ int avifB200DeviceAvailable(void)
     return n > 0;
 }
 const char * avifB200Version(void) { return AB_VERSION; }
-void avifB200SetKernelPolicy(int policy) { tls.policy = policy; }
+void avifB200SetKernelPolicy(int policy)
+{
+    /* bit 0: generic byte-addressed kernels; bit 1: IEEE division instructions instead of the verified 3-op form */
+    tls.policy = policy & 1;
+    tlsExactDivision = (policy >> 1) & 1;
+}
 uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
 void avifB200ResetKernelLaunchCount(void) { abLaunchCountReset(); }
 const char * avifB200LastKernelName(void) { return tls.lastKernel ? tls.lastKernel : ""; }
+
+/* verified_divisors.h as data + the on-device exhaustive re-check used by tests/test_gpu_division.py */
+size_t avifB200VerifiedDivisorCount(void) { return sizeof(kAbVerifiedDivisors) / sizeof(kAbVerifiedDivisors[0]); }
+uint32_t avifB200VerifiedDivisorBits(size_t index) { return index < avifB200VerifiedDivisorCount() ? kAbVerifiedDivisors[index] : 0; }
+avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches)
+{
+    float d;
+    memcpy(&d, &divisorBits, sizeof(d));
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    unsigned long long bad = 0;
+    AB_CUDA(abDivSelfTest(d, &bad, tls.stream));
+    *mismatches = bad;
+    return AVIF_RESULT_OK;
+}
 
 void * avifB200AllocPinned(size_t size)
 {
@@ -419,12 +443,27 @@ static int prepareState(const avifImage * image, const avifRGBImage * rgb, AbSta
     return 1;
 }
 
+/* binary search of the exhaustively verified divisors (verified_divisors.h) */
+static int divisorVerified(float d)
+{
+    uint32_t bits;
+    memcpy(&bits, &d, sizeof(bits));
+    size_t lo = 0, hi = sizeof(kAbVerifiedDivisors) / sizeof(kAbVerifiedDivisors[0]);
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (kAbVerifiedDivisors[mid] == bits) return 1;
+        if (kAbVerifiedDivisors[mid] < bits) lo = mid + 1;
+        else hi = mid;
+    }
+    return 0;
+}
+
 static AbDiv makeDiv(float d)
 {
     AbDiv v;
     v.d = d;
     v.r = 1.0f / d;
-    v.exact = 0; /* enabled per divisor once verified: see abDivisorVerified() */
+    v.exact = !tlsExactDivision && divisorVerified(d);
     v.pad = 0;
     return v;
 }
@@ -478,6 +517,7 @@ static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * u
     job.width = rgb->width;
     job.height = rgb->height;
     job.depth = rgb->depth;
+    job.maxDiv = makeDiv((float)((1u << rgb->depth) - 1));
     job.unmultiply = (uint8_t)unmultiply;
     AB_CUDA(abLaunchPremultiply(&job, st));
     tls.lastKernel = unmultiply ? "unpremultiply" : "premultiply";
@@ -600,11 +640,15 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
         job.rangeUV = makeDiv(s.rangeUV);
     }
     job.kg = makeDiv(s.kg);
+    job.yuvMaxDiv = makeDiv((float)s.yuvMax);
+    job.rgbMaxDiv = makeDiv(s.rgbMaxF);
     job.c1 = 2 * (1 - s.kr);
     job.c2 = 2 * (1 - s.kb);
     job.c3 = s.kr * (1 - s.kr);
     job.c4 = s.kb * (1 - s.kb);
     job.f16mul = f16Multiplier(rgb->depth);
+    job.magicBiasY = 8388608.0f + job.biasY;
+    job.magicBiasUV = 8388608.0f + job.biasUV;
     job.yuvBytes = (uint8_t)s.yuvChanBytes;
     job.rgbBytes = (uint8_t)s.rgbChanBytes;
     job.shiftX = (uint8_t)s.shiftX;
@@ -638,6 +682,8 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     else if (fast) job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_INT_PREMUL : AB_MUL_INT_UNPREMUL);
     else job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL);
     job.toF16 = (uint8_t)(rgb->isFloat ? 1 : 0);
+    job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
+    job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);
 
     avifResult res = ctxInit();
     if (res != AVIF_RESULT_OK) return res;
@@ -691,6 +737,13 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     job.rgbRB = rrgb.devRB;
     job.rowBegin = 0;
     job.rowEnd = image->height;
+    {
+        const uintptr_t m = 2u * s.yuvChanBytes - 1;
+        uintptr_t bits = (uintptr_t)job.y | (uintptr_t)job.yRB;
+        if (job.u) bits |= (uintptr_t)job.u | (uintptr_t)job.uRB | (uintptr_t)job.v | (uintptr_t)job.vRB;
+        if (job.a) bits |= (uintptr_t)job.a | (uintptr_t)job.aRB;
+        job.pairAligned = (uint8_t)((bits & m) == 0);
+    }
 
     const char * kname = "";
     if (sameDims) {
@@ -727,6 +780,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
         pj.width = rgb->width;
         pj.height = rgb->height;
         pj.depth = rgb->depth;
+        pj.maxDiv = makeDiv(s.rgbMaxF);
         if (intMul && premulLayout(rgb->format, &pj)) {
             pj.unmultiply = (uint8_t)(intMul == AB_MUL_INT_UNPREMUL);
             AB_CUDA(abLaunchPremultiply(&pj, st));
@@ -844,8 +898,13 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     job.kr = s.kr;
     job.kg = s.kg;
     job.kb = s.kb;
-    job.du = 2 * (1 - s.kb);
-    job.dv = 2 * (1 - s.kr);
+    job.du = makeDiv(2 * (1 - s.kb));
+    job.dv = makeDiv(2 * (1 - s.kr));
+    job.rgbMaxDiv = makeDiv(s.rgbMaxF);
+    job.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
+    job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
+    job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);
+    job.hasAlphaChan = (uint8_t)avifRGBFormatHasAlpha(rgb->format);
     job.rgbBytes = (uint8_t)s.rgbChanBytes;
     job.yuvBytes = (uint8_t)s.yuvChanBytes;
     job.hasChroma = (uint8_t)!monochrome;
@@ -908,6 +967,18 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     job.a = ra.dev;
     job.aRB = ra.devRB;
 
+    {
+        /* natural alignment of one pixel pair: 16 / 8 / 4 / 2 bytes for pairs of 16 / 8 / (12|4) / (6|2) bytes */
+        const uint32_t pairBytes = 2u * s.rgbPixBytes;
+        const uintptr_t srcAlign = (pairBytes % 16 == 0) ? 16 : (pairBytes % 8 == 0) ? 8 : (pairBytes % 4 == 0) ? 4 : 2;
+        job.srcPairAligned = (uint8_t)((((uintptr_t)job.rgb | (uintptr_t)job.rgbRB) & (srcAlign - 1)) == 0);
+        const uintptr_t m = 2u * s.yuvChanBytes - 1;
+        uintptr_t bits = (uintptr_t)job.y | (uintptr_t)job.yRB;
+        if (job.u) bits |= (uintptr_t)job.u | (uintptr_t)job.uRB;
+        if (job.v) bits |= (uintptr_t)job.v | (uintptr_t)job.vRB;
+        if (job.a) bits |= (uintptr_t)job.a | (uintptr_t)job.aRB;
+        job.dstPairAligned = (uint8_t)((bits & m) == 0);
+    }
     const char * kname = "";
     AB_CUDA(abLaunchR2Y(&job, st, tls.policy == 1, &kname));
     tls.lastKernel = kname;

@@ -1,0 +1,29 @@
+"""The kernels replace divisions by call constants with q=x*r; e=fma(-q,d,x); q'=fma(e,r,q).  That is only legal where
+it equals the IEEE quotient: this test re-proves it ON THE DEVICE for every whitelisted divisor, over all 2^32 inputs."""
+import ctypes
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_every_whitelisted_divisor_exhaustively(gpu_product):
+    n = gpu_product.avifB200VerifiedDivisorCount()
+    assert n >= 50
+    for k in range(n):
+        bits = gpu_product.avifB200VerifiedDivisorBits(k)
+        bad = ctypes.c_uint64(123)
+        assert gpu_product.avifB200SelfTestDivisor(bits, ctypes.byref(bad)) == 0
+        assert bad.value == 0, f"divisor 0x{bits:08x}: {bad.value} inputs differ from IEEE division"
+
+
+def test_selftest_detects_a_bad_divisor(gpu_product):
+    """Sanity of the checker itself: for some divisors the 3-op form is NOT exact; at least one of a handful must trip."""
+    import struct
+    tripped = 0
+    for d in (3.0000002, 1.0000001, 0.3333333, 1.9999999, 123456.79):
+        bits = struct.unpack("<I", struct.pack("<f", d))[0]
+        bad = ctypes.c_uint64(0)
+        assert gpu_product.avifB200SelfTestDivisor(bits, ctypes.byref(bad)) == 0
+        tripped += bad.value > 0
+    assert tripped >= 1

@@ -42,7 +42,7 @@ def _check_r2y(product, oracle, spec, seed, device=None, policy=0):
     return ro
 
 
-@pytest.mark.parametrize("policy", [0, 1], ids=["tiled", "generic"])
+@pytest.mark.parametrize("policy", [0, 1, 2, 3], ids=["tiled", "generic", "tiled-ieee-div", "generic-ieee-div"])
 def test_y2r_sweep_host_pointers(gpu_product, oracle, policy):
     n_ok = 0
     for k, spec in enumerate(util.random_y2r_specs(700, seed=21 + policy)):
@@ -74,10 +74,11 @@ def test_y2r_unaligned_device_views(gpu_product, oracle):
         _check_y2r(gpu_product, oracle, spec, 6000 + k, device="cuda:0")
 
 
-def test_r2y_sweep_host_pointers(gpu_product, oracle):
+@pytest.mark.parametrize("policy", [0, 1, 2], ids=["vec", "generic", "vec-ieee-div"])
+def test_r2y_sweep_host_pointers(gpu_product, oracle, policy):
     n_ok = 0
-    for k, spec in enumerate(util.random_r2y_specs(700, seed=31)):
-        n_ok += _check_r2y(gpu_product, oracle, spec, 7000 + k) == abi.AVIF_RESULT_OK
+    for k, spec in enumerate(util.random_r2y_specs(700, seed=31 + policy)):
+        n_ok += _check_r2y(gpu_product, oracle, spec, 7000 + k, policy=policy) == abi.AVIF_RESULT_OK
     assert n_ok > 450
 
 
