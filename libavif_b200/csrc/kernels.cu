@@ -894,9 +894,24 @@ using namespace ab;
 
 extern "C" {
 
+int abY2RFast_8_8(const AbY2RJob * job, void * stream);
+int abY2RFast_8_16(const AbY2RJob * job, void * stream);
+int abY2RFast_16_8(const AbY2RJob * job, void * stream);
+int abY2RFast_16_16(const AbY2RJob * job, void * stream);
+
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
+    if (forceGeneric == 0) { /* production: compile-time specialised kernels for the hot configurations (y2r_fast.cuh) */
+        int took;
+        if (job->yuvBytes == 2) took = (job->rgbBytes == 2) ? abY2RFast_16_16(job, stream) : abY2RFast_16_8(job, stream);
+        else took = (job->rgbBytes == 2) ? abY2RFast_8_16(job, stream) : abY2RFast_8_8(job, stream);
+        if (took) {
+            if (kernelName) *kernelName = (job->chroma == AB_CHROMA_BILINEAR) ? "y2r_fast_bilinear" : (job->chroma == AB_CHROMA_NEAREST) ? "y2r_fast_nearest" : "y2r_fast_444";
+            return finish_launch();
+        }
+    }
+    forceGeneric &= 1;
     if (job->yuvBytes == 2) {
         return job->rgbBytes == 2 ? launch_y2r_typed<uint16_t, uint16_t>(*job, st, forceGeneric, kernelName)
                                   : launch_y2r_typed<uint16_t, uint8_t>(*job, st, forceGeneric, kernelName);
@@ -905,10 +920,25 @@ int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const cha
                               : launch_y2r_typed<uint8_t, uint8_t>(*job, st, forceGeneric, kernelName);
 }
 
+int abR2YFast_8_8(const AbR2YJob * job, void * stream);
+int abR2YFast_8_16(const AbR2YJob * job, void * stream);
+int abR2YFast_16_8(const AbR2YJob * job, void * stream);
+int abR2YFast_16_16(const AbR2YJob * job, void * stream);
+
 int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->height == 0) return 0;
+    if (forceGeneric == 0) { /* production: compile-time specialised kernels (r2y_fast.cuh) */
+        int took;
+        if (job->rgbBytes == 2) took = (job->yuvBytes == 2) ? abR2YFast_16_16(job, stream) : abR2YFast_16_8(job, stream);
+        else took = (job->yuvBytes == 2) ? abR2YFast_8_16(job, stream) : abR2YFast_8_8(job, stream);
+        if (took) {
+            if (kernelName) *kernelName = "r2y_fast";
+            return finish_launch();
+        }
+    }
+    forceGeneric &= 1;
     const dim3 block(32, 8);
     const dim3 grid = grid2d((job->width + 1) / 2, (job->height + 1) / 2, block);
 #define AB_R2Y(RT, YT)                                                                      \

@@ -1,0 +1,315 @@
+/*
+ * r2y_fast.cuh -- compile-time specialised RGB->YUV kernels for the hot configurations (coefficients mode,
+ * colour input, verified divisors, 16-byte aligned buffers); everything else runs on kernels.cu's r2y_block_kernel.
+ *
+ * A lane owns 8 consecutive pixels of a 256-pixel warp tile -- of TWO rows for 4:2:0, so that the reference's 2x2
+ * block walk (src/reformat.c:295-470) stays inside one thread: the box filter is an ordered register sum, no
+ * shuffle needed.  Interleaved pixels are read with 128-bit loads (64-bit for 3-byte pixels), planes are written
+ * with one 128/64-bit store per lane and row, all lane-contiguous.  Arithmetic: pixel_math.cuh, operator for
+ * operator the reference's.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pixel_math.cuh"
+#include "plan.h"
+
+namespace abfast {
+
+using namespace ab;
+
+enum { SUB_444 = 0, SUB_422 = 1, SUB_420 = 2, SUB_400 = 3 };
+
+template <typename RT_, typename YT_, int SUB_, int NCH_, bool AFIRST_, int AM_>
+struct RCfg {
+    using RT = RT_;
+    using YT = YT_;
+    static constexpr int SUB = SUB_;
+    static constexpr int NCH = NCH_;
+    static constexpr bool AFIRST = AFIRST_;
+    static constexpr int AM = AM_; /* AB_MUL_NONE / FLOAT_MUL / FLOAT_UNMUL */
+};
+
+constexpr int kRTile = 256;
+constexpr int kRWarps = 8;
+
+__device__ __forceinline__ float rdivx(float x, const AbDiv & dv)
+{
+    const float q = __fmul_rn(x, dv.r);
+    return __fmaf_rn(__fmaf_rn(-q, dv.d, x), dv.r, q);
+}
+
+/* channel value `v` (memory order, 0 .. 8*NCH-1) of the lane's packed pixels as a magic float 2^23 + code */
+template <typename RT>
+__device__ __forceinline__ float chan_magic(const uint32_t * w, int v)
+{
+    if (sizeof(RT) == 2) return __uint_as_float(__byte_perm(w[v >> 1], 0x4B000000u, (v & 1) ? 0x7432u : 0x7410u));
+    return __uint_as_float(__byte_perm(w[v >> 2], 0x4B000000u, 0x7440u | (uint32_t)(v & 3)));
+}
+
+/* ref: src/reformat.c:197-219: clamp((int)floorf((v*range + bias) + 0.5f), 0, yuvMax), returned as 2^23 + code */
+__device__ __forceinline__ float quant_yuv_magic(float v, float range, float bias, float hiLimit)
+{
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+    return __fadd_rz(fminf(fmaxf(t, 0.0f), hiLimit), 8388608.0f); /* floor+clamp == trunc(clamp(t, 0, max + 0.5)) */
+}
+
+template <typename YT>
+__device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8])
+{
+    if (n >= 8) {
+        if (sizeof(YT) == 2) {
+            uint4 v;
+            v.x = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x5410u);
+            v.y = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x5410u);
+            v.z = __byte_perm(__float_as_uint(q[4]), __float_as_uint(q[5]), 0x5410u);
+            v.w = __byte_perm(__float_as_uint(q[6]), __float_as_uint(q[7]), 0x5410u);
+            *reinterpret_cast<uint4 *>(row + (size_t)x * 2) = v;
+        } else {
+            uint2 v;
+            v.x = __byte_perm(__byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x0040u), __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040u), 0x5410u);
+            v.y = __byte_perm(__byte_perm(__float_as_uint(q[4]), __float_as_uint(q[5]), 0x0040u), __byte_perm(__float_as_uint(q[6]), __float_as_uint(q[7]), 0x0040u), 0x5410u);
+            *reinterpret_cast<uint2 *>(row + x) = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)(__float_as_uint(q[k]) & 0xFFFFu);
+    }
+}
+
+template <typename YT>
+__device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32_t n, const float q[4])
+{
+    if (n >= 4) {
+        if (sizeof(YT) == 2) {
+            uint2 v;
+            v.x = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x5410u);
+            v.y = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x5410u);
+            *reinterpret_cast<uint2 *>(row + (size_t)x * 2) = v;
+        } else {
+            *reinterpret_cast<uint32_t *>(row + x) =
+                __byte_perm(__byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x0040u), __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040u), 0x5410u);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)(__float_as_uint(q[k]) & 0xFFFFu);
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J)
+{
+    using RT = typename C::RT;
+    using YT = typename C::YT;
+    constexpr int ROWS = (C::SUB == SUB_420) ? 2 : 1;
+    constexpr int PIXB = C::NCH * (int)sizeof(RT);
+    constexpr int NW = 8 * PIXB / 4; /* words per lane and row */
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t px0 = blockIdx.x * kRTile + 8 * lane;
+    const uint32_t j0 = (blockIdx.y * kRWarps + warp) * ROWS;
+    if (j0 >= J.height) return; /* warp-uniform */
+    const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
+    if (nValid == 0) return;    /* no cross-lane traffic in this kernel: lanes may leave */
+    const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
+
+    /* ---- loads: 8 pixels x ROWS rows, issued before any arithmetic ---- */
+    uint32_t w[ROWS][NW];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[r][k] = 0;
+        if ((uint32_t)r < nRows) {
+            const uint8_t * p = J.rgb + (int64_t)(j0 + r) * J.rgbRB + (int64_t)px0 * PIXB;
+            if (nValid >= 8) {
+                if ((8 * PIXB) % 16 == 0) {
+#pragma unroll
+                    for (int q = 0; q < NW / 4; ++q) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + q);
+                        w[r][4 * q] = v.x; w[r][4 * q + 1] = v.y; w[r][4 * q + 2] = v.z; w[r][4 * q + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NW / 2; ++q) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p) + q);
+                        w[r][2 * q] = v.x; w[r][2 * q + 1] = v.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < 8 * C::NCH; ++v) {
+                    if ((uint32_t)(v / C::NCH) < nValid) {
+                        const uint32_t s = (uint32_t)__ldg(reinterpret_cast<const RT *>(p) + v);
+                        if (sizeof(RT) == 2) w[r][v >> 1] |= s << ((v & 1) * 16);
+                        else w[r][v >> 2] |= s << ((v & 3) * 8);
+                    }
+                }
+            }
+        }
+    }
+
+    /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
+    const float magicOne = 8388608.0f;
+    const float hiLimit = __fadd_rn(J.yuvMaxF, 0.5f);
+    const bool swap = J.swapRB != 0;
+    float uf[ROWS][8], vf[ROWS][8];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if ((uint32_t)r >= nRows) continue;
+        float yq[8], aq[8], uq[8], vq[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            constexpr int c0 = C::AFIRST ? 1 : 0;
+            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0), magicOne), J.rgbMaxDiv);
+            const float gg = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 1), magicOne), J.rgbMaxDiv);
+            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 2), magicOne), J.rgbMaxDiv);
+            float R = swap ? x2 : x0, G = gg, B = swap ? x0 : x2;
+            float am = 0.0f;
+            if (C::NCH == 4) am = chan_magic<RT>(w[r], t * C::NCH + (C::AFIRST ? 0 : 3));
+            if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
+                const float a = rdivx(__fsub_rn(am, magicOne), J.rgbMaxDiv);
+                if (C::AM == AB_MUL_FLOAT_MUL) {
+                    const bool scale = (a < 1.0f); /* a == 0: the products are exact zeros as well */
+                    R = scale ? __fmul_rn(R, a) : R;
+                    G = scale ? __fmul_rn(G, a) : G;
+                    B = scale ? __fmul_rn(B, a) : B;
+                } else if (a == 0.0f) {
+                    R = G = B = 0.0f;
+                } else if (a < 1.0f) {
+                    R = min1(__fdiv_rn(R, a));
+                    G = min1(__fdiv_rn(G, a));
+                    B = min1(__fdiv_rn(B, a));
+                }
+            }
+            const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
+            yq[t] = quant_yuv_magic(Y, J.rangeY, J.biasY, hiLimit);
+            if (C::SUB != SUB_400) {
+                const float U = rdivx(__fsub_rn(B, Y), J.du);
+                const float V = rdivx(__fsub_rn(R, Y), J.dv);
+                if (C::SUB == SUB_444) {
+                    uq[t] = quant_yuv_magic(U, J.rangeUV, J.biasUV, hiLimit);
+                    vq[t] = quant_yuv_magic(V, J.rangeUV, J.biasUV, hiLimit);
+                } else {
+                    uf[r][t] = U;
+                    vf[r][t] = V;
+                }
+            }
+            aq[t] = (C::NCH == 4 && J.alphaWrite == AB_ALPHA_COPY) ? am : __uint_as_float(0x4B000000u | J.yuvMax); /* ref: :545-569 */
+        }
+        const uint32_t j = j0 + r;
+        store_samples8<YT>(J.y + (int64_t)j * J.yRB, px0, nValid, yq);
+        if (C::SUB == SUB_444) {
+            store_samples8<YT>(J.u + (int64_t)j * J.uRB, px0, nValid, uq);
+            store_samples8<YT>(J.v + (int64_t)j * J.vRB, px0, nValid, vq);
+        }
+        if (J.alphaWrite != AB_ALPHA_KEEP) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, nValid, aq);
+    }
+
+    /* ---- subsampled chroma: ordered box sums over the samples that exist (ref: :413-467) ---- */
+    if (C::SUB == SUB_420 || C::SUB == SUB_422) {
+        const uint32_t nc = (nValid + 1) >> 1;
+        if (C::SUB == SUB_420) {
+            float uq[4], vq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool two = (uint32_t)(2 * k + 1) < nValid; /* block width 2 */
+                float su = uf[0][2 * k], sv = vf[0][2 * k]; /* 0 + TL */
+                if (two) {
+                    su = __fadd_rn(su, uf[0][2 * k + 1]);
+                    sv = __fadd_rn(sv, vf[0][2 * k + 1]);
+                }
+                if (nRows == 2) {
+                    su = __fadd_rn(su, uf[ROWS - 1][2 * k]);
+                    sv = __fadd_rn(sv, vf[ROWS - 1][2 * k]);
+                    if (two) {
+                        su = __fadd_rn(su, uf[ROWS - 1][2 * k + 1]);
+                        sv = __fadd_rn(sv, vf[ROWS - 1][2 * k + 1]);
+                    }
+                }
+                /* division by the sample count 1, 2 or 4 is an exact scaling */
+                const float inv = (two ? 0.5f : 1.0f) * ((nRows == 2) ? 0.5f : 1.0f);
+                uq[k] = quant_yuv_magic(__fmul_rn(su, inv), J.rangeUV, J.biasUV, hiLimit);
+                vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
+            }
+            const uint32_t uj = j0 >> 1;
+            store_samples4<YT>(J.u + (int64_t)uj * J.uRB, px0 >> 1, nc, uq);
+            store_samples4<YT>(J.v + (int64_t)uj * J.vRB, px0 >> 1, nc, vq);
+        } else {
+            float uq[4], vq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool two = (uint32_t)(2 * k + 1) < nValid;
+                float su = uf[0][2 * k], sv = vf[0][2 * k];
+                if (two) {
+                    su = __fadd_rn(su, uf[0][2 * k + 1]);
+                    sv = __fadd_rn(sv, vf[0][2 * k + 1]);
+                }
+                const float inv = two ? 0.5f : 1.0f;
+                uq[k] = quant_yuv_magic(__fmul_rn(su, inv), J.rangeUV, J.biasUV, hiLimit);
+                vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
+            }
+            store_samples4<YT>(J.u + (int64_t)j0 * J.uRB, px0 >> 1, nc, uq);
+            store_samples4<YT>(J.v + (int64_t)j0 * J.vRB, px0 >> 1, nc, vq);
+        }
+    }
+}
+
+template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>
+static int rlaunch_cfg(const AbR2YJob & J, cudaStream_t st)
+{
+    using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM>;
+    constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
+    const uint32_t units = (J.height + ROWS - 1) / ROWS;
+    const dim3 grid((J.width + kRTile - 1) / kRTile, (units + kRWarps - 1) / kRWarps);
+    r2y_fast_kernel<C><<<grid, kRWarps * 32, 0, st>>>(J);
+    return 1;
+}
+
+template <typename RT, typename YT, int SUB>
+static int rlaunch_sub(const AbR2YJob & J, cudaStream_t st)
+{
+    if (J.nChan == 3) return (J.alphaMul == AB_MUL_NONE) ? rlaunch_cfg<RT, YT, SUB, 3, false, AB_MUL_NONE>(J, st) : 0;
+    if (J.alphaFirst) {
+        switch (J.alphaMul) {
+            case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_NONE>(J, st);
+            case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_MUL>(J, st);
+            default: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_UNMUL>(J, st);
+        }
+    }
+    switch (J.alphaMul) {
+        case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_NONE>(J, st);
+        case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_MUL>(J, st);
+        default: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_UNMUL>(J, st);
+    }
+}
+
+/* returns 1 if a specialised kernel was launched, 0 if the job must take the general kernel */
+template <typename RT, typename YT>
+static int launch_r2y_fast_typed(const AbR2YJob & J, cudaStream_t st)
+{
+    if (J.mode != AB_MODE_COEFF || J.isGray) return 0;
+    if (J.nChan != 3 && J.nChan != 4) return 0;
+    if (!J.rgbMaxDiv.exact) return 0;
+    if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return 0;
+    if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return 0;
+    if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return 0;
+    if (J.width == 0 || J.height == 0) return 0;
+    const uint32_t pixb = J.nChan * (uint32_t)sizeof(RT);
+    const uintptr_t srcAlign = ((8 * pixb) % 16 == 0) ? 15 : 7;
+    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & srcAlign) return 0;
+    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1;
+    uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
+    if (J.alphaWrite != AB_ALPHA_KEEP) bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
+    if (bits & lumaAlign) return 0;
+    if (J.hasChroma) {
+        const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
+        if (cbits & (J.shiftX ? (4 * sizeof(YT) - 1) : lumaAlign)) return 0;
+    }
+    if (!J.hasChroma) return rlaunch_sub<RT, YT, SUB_400>(J, st);
+    if (!J.shiftX) return rlaunch_sub<RT, YT, SUB_444>(J, st);
+    return J.shiftY ? rlaunch_sub<RT, YT, SUB_420>(J, st) : rlaunch_sub<RT, YT, SUB_422>(J, st);
+}
+
+} // namespace abfast

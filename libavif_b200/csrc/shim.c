@@ -165,8 +165,9 @@ int avifB200DeviceAvailable(void)
 const char * avifB200Version(void) { return AB_VERSION; }
 void avifB200SetKernelPolicy(int policy)
 {
-    /* bit 0: generic byte-addressed kernels; bit 1: IEEE division instructions instead of the verified 3-op form */
-    tls.policy = policy & 1;
+    /* bit 0: generic byte-addressed kernels; bit 1: IEEE division instructions instead of the verified 3-op form;
+     * bit 2: skip the compile-time specialised kernels (run the runtime-configured tiled kernel) */
+    tls.policy = (policy & 1) | ((policy & 4) >> 1);
     tlsExactDivision = (policy >> 1) & 1;
 }
 uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
@@ -747,7 +748,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
 
     const char * kname = "";
     if (sameDims) {
-        AB_CUDA(abLaunchY2R(&job, st, tls.policy == 1, &kname));
+        AB_CUDA(abLaunchY2R(&job, st, tls.policy, &kname));
     } else {
         /* faithful multi-pass composition for mismatched extents */
         const uint8_t intMul = (job.alphaMul == AB_MUL_INT_PREMUL || job.alphaMul == AB_MUL_INT_UNPREMUL) ? job.alphaMul : 0;
@@ -772,7 +773,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
         cj.alphaWrite = AB_ALPHA_KEEP;
         if (intMul) cj.alphaMul = AB_MUL_NONE;
         cj.toF16 = 0;
-        AB_CUDA(abLaunchY2R(&cj, st, tls.policy == 1, &kname));
+        AB_CUDA(abLaunchY2R(&cj, st, tls.policy, &kname));
         AbRgbPassJob pj;
         memset(&pj, 0, sizeof(pj));
         pj.pixels = rrgb.dev;
@@ -980,7 +981,7 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
         job.dstPairAligned = (uint8_t)((bits & m) == 0);
     }
     const char * kname = "";
-    AB_CUDA(abLaunchR2Y(&job, st, tls.policy == 1, &kname));
+    AB_CUDA(abLaunchR2Y(&job, st, tls.policy, &kname));
     tls.lastKernel = kname;
     if (grayChromaFill) {
         const int half = 1 << (image->depth - 1);

@@ -1,0 +1,499 @@
+/*
+ * y2r_fast.cuh -- compile-time specialised YUV->RGB kernels for the hot configurations.
+ *
+ * The general kernel (kernels.cu) decides everything from runtime flags and spends ~3/4 of its issue slots on
+ * uniform branches and constant loads (ncu, profiles/r01a).  Here every policy decision is a template parameter,
+ * so the inner loop is straight-line code:
+ *   - a lane owns 8 consecutive pixels of a 256-pixel warp tile: one 128-bit (16-bit samples) or 64-bit (8-bit
+ *     samples) load per plane row, 64/32-bit for horizontally subsampled chroma; every load of the tile is issued
+ *     before any arithmetic (64..150 B in flight per thread);
+ *   - sample -> float is one PRMT (as_float(code | 0x4B000000) == 2^23 + code), the high-bit clamp one FMNMX,
+ *     float -> code one FADD.RZ; division by call constants is the verified 3-op sequence (pixel_math.cuh);
+ *   - 4:2:0 bilinear: a warp converts TWO luma rows (2r-1, 2r) that share chroma rows r-1 and r; the 9/3/3/1
+ *     products of every chroma sample are formed once and reused by both rows; the only cross-lane traffic is one
+ *     warp shuffle per side per (chroma row, plane) -- the neighbour column of a lane's first / last sample;
+ *   - the packed pixels (8..64 B per lane and row) go to a shared-memory tile in 16-byte units with an XOR swizzle
+ *     that makes both the strided writes and the linear read-back bank-conflict free, and leave the SM as 16-byte
+ *     fully coalesced vector stores.
+ * Arithmetic is the reference's, operator for operator (pixel_math.cuh); eligibility (coefficients mode, aligned
+ * planes, verified divisors, ...) is checked by the launcher, everything else runs on the general kernel.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pixel_math.cuh"
+#include "plan.h"
+
+namespace abfast {
+
+using namespace ab;
+
+enum { CH_FULL = 1, CH_NEAREST = 2, CH_BIL420 = 3, CH_BIL422 = 4 };
+
+template <typename YT_, typename RT_, int CHROMA_, int NCH_, bool AFIRST_, int AW_, int AM_>
+struct Cfg {
+    using YT = YT_;
+    using RT = RT_;
+    static constexpr int CHROMA = CHROMA_; /* CH_* */
+    static constexpr int NCH = NCH_;       /* 3 or 4 channels */
+    static constexpr bool AFIRST = AFIRST_; /* alpha stored before colour */
+    static constexpr int AW = AW_;         /* AB_ALPHA_FILL / AB_ALPHA_COPY (NCH == 4) */
+    static constexpr int AM = AM_;         /* AB_MUL_* */
+};
+
+constexpr int kTile = 256;
+constexpr int kWarps = 8;
+
+/* ---- sample vectors -------------------------------------------------------------------------- */
+
+/* magic float (2^23 + code) of sample k of a packed vector; k is a compile-time constant after unrolling */
+template <typename T>
+__device__ __forceinline__ float magic_sample(const uint32_t * w, int k)
+{
+    if (sizeof(T) == 2) return __uint_as_float(__byte_perm(w[k >> 1], 0x4B000000u, (k & 1) ? 0x7432u : 0x7410u));
+    return __uint_as_float(__byte_perm(w[k >> 2], 0x4B000000u, 0x7440u | (uint32_t)(k & 3)));
+}
+
+/* 8 consecutive samples starting at x (x % 8 == 0, row 16/8-byte aligned); n = how many of them exist */
+template <typename T>
+__device__ __forceinline__ void load8(const uint8_t * row, uint32_t x, uint32_t n, uint32_t w[4])
+{
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (n >= 8) {
+        if (sizeof(T) == 2) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + (size_t)x * 2));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + x));
+            w[0] = v.x; w[1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((uint32_t)k < n) {
+                const uint32_t s = (uint32_t)__ldg(reinterpret_cast<const T *>(row) + x + k);
+                if (sizeof(T) == 2) w[k >> 1] |= s << ((k & 1) * 16);
+                else w[k >> 2] |= s << ((k & 3) * 8);
+            }
+        }
+    }
+}
+
+/* 4 consecutive chroma samples starting at column m (m % 4 == 0), columns >= cw replicate column cw-1 */
+template <typename T>
+__device__ __forceinline__ void load4_clamped(const uint8_t * row, uint32_t m, uint32_t cw, uint32_t w[2])
+{
+    w[0] = w[1] = 0;
+    if (m + 3 < cw) {
+        if (sizeof(T) == 2) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + (size_t)m * 2));
+            w[0] = v.x; w[1] = v.y;
+        } else {
+            w[0] = __ldg(reinterpret_cast<const uint32_t *>(row + m));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t s = (uint32_t)__ldg(reinterpret_cast<const T *>(row) + min(m + k, cw - 1));
+            if (sizeof(T) == 2) w[k >> 1] |= s << ((k & 1) * 16);
+            else w[0] |= s << (k * 8);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float magic_scalar(const uint8_t * row, uint32_t col)
+{
+    return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const T *>(row) + col) | 0x4B000000u);
+}
+
+/* ---- arithmetic on magic floats ------------------------------------------------------------------ */
+
+/* verified constant division, unconditional fast form (the launcher guarantees dv.exact) */
+__device__ __forceinline__ float divx(float x, const AbDiv & dv)
+{
+    const float q = __fmul_rn(x, dv.r);
+    return __fmaf_rn(__fmaf_rn(-q, dv.d, x), dv.r, q);
+}
+
+/* normalised value of a magic-float code: ((float)min(code, yuvMax) - bias) / range  (ref: src/reformat.c:583,:598,:1005) */
+template <typename T>
+__device__ __forceinline__ float norm_magic(float mf, float magicMax, float magicBias, const AbDiv & range)
+{
+    if (sizeof(T) == 2) mf = fminf(mf, magicMax); /* clamp garbage high bits of 16-bit containers */
+    return divx(__fsub_rn(mf, magicBias), range);
+}
+
+/* (T)(0.5f + c*max) as the bit pattern of 2^23 + code (low 16 bits = code) */
+__device__ __forceinline__ float quant_magic(float c, float maxF) { return __fadd_rz(__fadd_rn(0.5f, __fmul_rn(c, maxF)), 8388608.0f); }
+
+__device__ __forceinline__ float clamp01f(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); } /* == AVIF_CLAMP for non-NaN */
+
+/* ---- staging tile ---------------------------------------------------------------------------------- */
+
+template <int PIXB>
+__device__ __forceinline__ uint32_t swz_unit(uint32_t u)
+{
+    constexpr uint32_t M = (PIXB == 8) ? 3u : (PIXB == 4) ? 1u : 0u;
+    return u ^ ((u >> 3) & M);
+}
+
+/* ---- the kernel ------------------------------------------------------------------------------------- */
+
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
+{
+    using YT = typename C::YT;
+    using RT = typename C::RT;
+    constexpr bool SUB = (C::CHROMA != CH_FULL);
+    constexpr bool BIL = (C::CHROMA == CH_BIL420 || C::CHROMA == CH_BIL422);
+    constexpr int ROWS = (C::CHROMA == CH_BIL420) ? 2 : 1;
+    constexpr int PIXB = C::NCH * (int)sizeof(RT);
+    constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
+    constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
+
+    __shared__ __align__(16) uint8_t stageAll[kWarps][ROWS * kTile * PIXB];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t unit = blockIdx.y * kWarps + warp;
+    const uint32_t x0 = blockIdx.x * kTile;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
+    uint8_t * stage = stageAll[warp];
+
+    /* rows of this warp */
+    int jrow[ROWS];
+    bool rowOn[ROWS];
+    int cA = 0, cB = 0; /* chroma rows (BIL420: r-1 and r; otherwise the single chroma row in cA) */
+    if (ROWS == 2) {
+        const int ru = (int)(J.rowBegin >> 1) + (int)unit;
+        jrow[0] = 2 * ru - 1;
+        jrow[ROWS - 1] = 2 * ru;
+        const int chromaH = (int)((J.height + 1) >> 1);
+        const bool hasA = (ru >= 1), hasB = (ru < chromaH);
+        cA = hasA ? ru - 1 : ru;
+        cB = hasB ? ru : ru - 1;
+    } else {
+        jrow[0] = (int)(J.rowBegin + unit);
+        cA = cB = jrow[0] >> J.shiftY;
+    }
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        rowOn[r] = (jrow[r] >= (int)J.rowBegin) && (jrow[r] < (int)J.rowEnd);
+        any = any || rowOn[r];
+    }
+    if (!any) return; /* warp-uniform */
+
+    /* ------------------------------ loads ------------------------------ */
+    uint32_t yw[ROWS][4], aw[ROWS][4];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        yw[r][0] = yw[r][1] = yw[r][2] = yw[r][3] = 0;
+        aw[r][0] = aw[r][1] = aw[r][2] = aw[r][3] = 0;
+        if (rowOn[r] && nValid) {
+            load8<YT>(J.y + (int64_t)jrow[r] * J.yRB, px0, nValid, yw[r]);
+            if (NEED_A) load8<YT>(J.a + (int64_t)jrow[r] * J.aRB, px0, nValid, aw[r]);
+        }
+    }
+    constexpr int CROWS = (ROWS == 2) ? 2 : 1;
+    uint32_t uw[CROWS][SUB ? 2 : 4], vw[CROWS][SUB ? 2 : 4];
+    float hlU[CROWS], hrU[CROWS], hlV[CROWS], hrV[CROWS]; /* halo columns as magic floats (edge lanes only) */
+    const uint32_t cw = SUB ? ((J.width + 1) >> 1) : J.width;
+    const uint32_t m0 = SUB ? (px0 >> 1) : px0;
+#pragma unroll
+    for (int c = 0; c < CROWS; ++c) {
+        const int crow = (c == 0) ? cA : cB;
+        const uint8_t * ur = J.u + (int64_t)crow * J.uRB;
+        const uint8_t * vr = J.v + (int64_t)crow * J.vRB;
+        hlU[c] = hrU[c] = hlV[c] = hrV[c] = 0.0f;
+        if (SUB) {
+            load4_clamped<YT>(ur, m0, cw, uw[c]);
+            load4_clamped<YT>(vr, m0, cw, vw[c]);
+            if (BIL) {
+                if (lane == 0) {
+                    const uint32_t col = (m0 > 0) ? m0 - 1 : 0;
+                    hlU[c] = magic_scalar<YT>(ur, col);
+                    hlV[c] = magic_scalar<YT>(vr, col);
+                }
+                if (lane == 31) {
+                    const uint32_t col = min(m0 + 4, cw - 1);
+                    hrU[c] = magic_scalar<YT>(ur, col);
+                    hrV[c] = magic_scalar<YT>(vr, col);
+                }
+            }
+        } else {
+            uw[c][0] = uw[c][1] = uw[c][2] = uw[c][3] = 0;
+            vw[c][0] = vw[c][1] = vw[c][2] = vw[c][3] = 0;
+            if (nValid) {
+                load8<YT>(ur, px0, nValid, uw[c]);
+                load8<YT>(vr, px0, nValid, vw[c]);
+            }
+        }
+    }
+
+    /* ------------------------------ chroma ------------------------------ */
+    const float magicMax = __uint_as_float(0x4B000000u | J.yuvMax);
+    float cb[ROWS][8], cr[ROWS][8];
+    if (!SUB) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            cb[0][t] = norm_magic<YT>(magic_sample<YT>(uw[0], t), magicMax, J.magicBiasUV, J.rangeUV);
+            cr[0][t] = norm_magic<YT>(magic_sample<YT>(vw[0], t), magicMax, J.magicBiasUV, J.rangeUV);
+        }
+    } else if (!BIL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float nu = norm_magic<YT>(magic_sample<YT>(uw[0], k), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nv = norm_magic<YT>(magic_sample<YT>(vw[0], k), magicMax, J.magicBiasUV, J.rangeUV);
+            cb[0][2 * k] = cb[0][2 * k + 1] = nu;
+            cr[0][2 * k] = cr[0][2 * k + 1] = nv;
+        }
+    } else {
+        /* bilinear: per plane, normalise the lane's 4 columns of each chroma row, fetch the two neighbour columns
+         * from the adjacent lanes (edge lanes: halo loads), form the 9/16, 3/16, 1/16 products once and blend.
+         * ref: src/reformat.c:764-838; blend order ((near*9/16 + adjCol*3/16) + adjRow*3/16) + diag*1/16 */
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+            float p9[CROWS][4], p3[CROWS][6], p1[CROWS][6]; /* index 0 = left halo, 1..4 = own columns, 5 = right halo */
+#pragma unroll
+            for (int c = 0; c < CROWS; ++c) {
+                float n[6];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? vw[c] : uw[c], k), magicMax, J.magicBiasUV, J.rangeUV);
+                }
+                float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
+                float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
+                if (lane == 0) left = norm_magic<YT>(plane ? hlV[c] : hlU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                if (lane == 31) right = norm_magic<YT>(plane ? hrV[c] : hrU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                n[0] = left;
+                n[5] = right;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    p3[c][k] = __fmul_rn(n[k], 0.1875f);
+                    p1[c][k] = __fmul_rn(n[k], 0.0625f);
+                    if (k >= 1 && k <= 4) p9[c][k - 1] = __fmul_rn(n[k], 0.5625f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                /* luma row 2r-1 (r == 0 of a 4:2:0 unit): near = chroma row A, adjacent = B; row 2r: near = B, adjacent = A.
+                 * 4:2:2 (one chroma row): near == adjacent. */
+                const int cn = (ROWS == 2) ? r : 0, ca = (ROWS == 2) ? (1 - r) : 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int k = 1 + (t >> 1);                 /* own column index in the 6-wide arrays */
+                    const int ka = (t & 1) ? k + 1 : k - 1;     /* adjacent column: right of odd pixels, left of even ones */
+                    const float val = __fadd_rn(__fadd_rn(__fadd_rn(p9[cn][k - 1], p3[cn][ka]), p3[ca][k]), p1[ca][ka]);
+                    if (plane) cr[r][t] = val;
+                    else cb[r][t] = val;
+                }
+            }
+        }
+    }
+
+    /* ------------------------------ pixels ------------------------------ */
+    const float magicOne = 8388608.0f;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (!rowOn[r]) continue; /* warp-uniform */
+        float ch[8][4];          /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float Y = norm_magic<YT>(magic_sample<YT>(yw[r], t), magicMax, J.magicBiasY, J.rangeY);
+            const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
+            /* ref: src/reformat.c:1014-1016 == :874-876 */
+            float R = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
+            float B = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
+            float G = __fsub_rn(Y, divx(__fmul_rn(2.0f, __fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb))), J.kg));
+            R = clamp01f(R);
+            G = clamp01f(G);
+            B = clamp01f(B);
+            float am = 0.0f; /* alpha sample as magic float */
+            if (NEED_A) am = magic_sample<YT>(aw[r], t);
+            if (C::AM == AB_MUL_FLOAT_MUL || C::AM == AB_MUL_FLOAT_UNMUL) { /* ref: src/reformat.c:894-947 */
+                const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
+                const float Ac = clamp01f(divx(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
+                if (C::AM == AB_MUL_FLOAT_MUL) {
+                    const bool scale = (Ac < 1.0f); /* Ac == 0 gives exact zeros through the multiply as well */
+                    R = scale ? __fmul_rn(R, Ac) : R;
+                    G = scale ? __fmul_rn(G, Ac) : G;
+                    B = scale ? __fmul_rn(B, Ac) : B;
+                } else if (Ac == 0.0f) {
+                    R = G = B = 0.0f;
+                } else if (Ac < 1.0f) {
+                    R = min1(__fdiv_rn(R, Ac));
+                    G = min1(__fdiv_rn(G, Ac));
+                    B = min1(__fdiv_rn(B, Ac));
+                }
+            }
+            float qr = quant_magic(R, J.rgbMaxF), qg = quant_magic(G, J.rgbMaxF), qb = quant_magic(B, J.rgbMaxF);
+            if (C::AM == AB_MUL_INT_PREMUL || C::AM == AB_MUL_INT_UNPREMUL) { /* ref: src/alpha.c:179-192, :366-381 on the quantised codes */
+                const float af = __fsub_rn(am, magicOne); /* raw (unclamped) alpha code: it is what the channel holds */
+                const bool opaque = (af >= J.rgbMaxF), zero = (af == 0.0f);
+                float pr, pg, pb;
+                if (C::AM == AB_MUL_INT_PREMUL) {
+                    pr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
+                    pg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
+                    pb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
+                } else {
+                    const float lim = __fadd_rn(J.rgbMaxF, 0.5f);
+                    const float d = (opaque || zero) ? 1.0f : af;
+                    pr = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qr, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
+                    pg = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qg, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
+                    pb = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qb, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
+                }
+                qr = opaque ? qr : (zero ? magicOne : pr);
+                qg = opaque ? qg : (zero ? magicOne : pg);
+                qb = opaque ? qb : (zero ? magicOne : pb);
+            }
+            const float qa = HAS_A ? am : __uint_as_float(0x4B000000u | J.rgbMax);
+            if (C::NCH == 3) {
+                ch[t][0] = qr; ch[t][1] = qg; ch[t][2] = qb; ch[t][3] = 0.0f;
+            } else if (C::AFIRST) {
+                ch[t][0] = qa; ch[t][1] = qr; ch[t][2] = qg; ch[t][3] = qb;
+            } else {
+                ch[t][0] = qr; ch[t][1] = qg; ch[t][2] = qb; ch[t][3] = qa;
+            }
+        }
+        /* pack the lane's 8 pixels (8*PIXB bytes) and store them into the swizzled staging row */
+        constexpr int NV = 8 * C::NCH;              /* channel values of the lane */
+        constexpr int NW = 8 * PIXB / 4;            /* 32-bit words of the lane */
+        uint32_t words[NW];
+#pragma unroll
+        for (int wi = 0; wi < NW; ++wi) {
+            if (sizeof(RT) == 2) {
+                const int v0 = 2 * wi, v1 = 2 * wi + 1;
+                words[wi] = __byte_perm(__float_as_uint(ch[v0 / C::NCH][v0 % C::NCH]), __float_as_uint(ch[v1 / C::NCH][v1 % C::NCH]), 0x5410u);
+            } else {
+                const int v0 = 4 * wi;
+                const uint32_t lo = __byte_perm(__float_as_uint(ch[v0 / C::NCH][v0 % C::NCH]), __float_as_uint(ch[(v0 + 1) / C::NCH][(v0 + 1) % C::NCH]), 0x0040u);
+                const uint32_t hi = __byte_perm(__float_as_uint(ch[(v0 + 2) / C::NCH][(v0 + 2) % C::NCH]), __float_as_uint(ch[(v0 + 3) / C::NCH][(v0 + 3) % C::NCH]), 0x0040u);
+                words[wi] = __byte_perm(lo, hi, 0x5410u);
+            }
+        }
+        (void)NV;
+        uint8_t * srow = stage + r * (kTile * PIXB);
+        if ((8 * PIXB) % 16 == 0) {
+            constexpr int NU = 8 * PIXB / 16;
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+                const uint32_t u = swz_unit<PIXB>(lane * NU + q);
+                *reinterpret_cast<uint4 *>(srow + u * 16) = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
+            }
+        } else { /* 24 bytes per lane (3 x u8): three 8-byte chunks, stride 24 B is conflict-free as is */
+#pragma unroll
+            for (int q = 0; q < NW / 2; ++q) *reinterpret_cast<uint2 *>(srow + lane * (8 * PIXB) + q * 8) = make_uint2(words[2 * q], words[2 * q + 1]);
+        }
+    }
+    __syncwarp();
+
+    /* ------------------------------ copy-out ------------------------------ */
+    const uint32_t npx = min((uint32_t)kTile, J.width - x0);
+    const uint32_t nbytes = npx * PIXB;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (!rowOn[r]) continue;
+        const uint8_t * srow = stage + r * (kTile * PIXB);
+        uint8_t * dst = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)x0 * PIXB; /* 16-byte aligned (launcher) */
+        const uint32_t nv = nbytes >> 4;
+        for (uint32_t k = lane; k < nv; k += 32) {
+            reinterpret_cast<uint4 *>(dst)[k] = *reinterpret_cast<const uint4 *>(srow + swz_unit<PIXB>(k) * 16);
+        }
+        for (uint32_t b = (nv << 4) + lane; b < nbytes; b += 32) dst[b] = srow[swz_unit<PIXB>(b >> 4) * 16 + (b & 15)];
+    }
+}
+
+/* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
+
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
+{
+    using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;
+    const uint32_t rows = J.rowEnd - J.rowBegin;
+    uint32_t units = rows;
+    if (CHROMA == CH_BIL420) units = (J.rowEnd >> 1) - (J.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
+    const dim3 grid((J.width + kTile - 1) / kTile, (units + kWarps - 1) / kWarps);
+    y2r_fast_kernel<C><<<grid, kWarps * 32, 0, st>>>(J);
+    return 1;
+}
+
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST>
+static int launch_alpha(const AbY2RJob & J, cudaStream_t st)
+{
+    constexpr bool slow = (CHROMA == CH_BIL420 || CHROMA == CH_BIL422); /* general loop: alpha math in float; fast loops: integer post-pass */
+    if (NCH == 3) {
+        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE>(J, st);
+        if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL>(J, st);
+        return 0;
+    }
+    if (J.alphaWrite == AB_ALPHA_FILL) {
+        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_FILL, AB_MUL_NONE>(J, st);
+        return 0;
+    }
+    if (J.alphaWrite != AB_ALPHA_COPY) return 0;
+    switch (J.alphaMul) {
+        case AB_MUL_NONE: return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(J, st);
+        case AB_MUL_INT_PREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(J, st);
+        case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(J, st);
+        case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(J, st);
+        case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(J, st);
+        default: return 0;
+    }
+}
+
+/* returns 1 if a specialised kernel was launched, 0 if the job must take the general kernel */
+template <typename YT, typename RT>
+static int launch_y2r_fast_typed(const AbY2RJob & Jin, cudaStream_t st)
+{
+    AbY2RJob J = Jin;
+    if (J.mode != AB_MODE_COEFF || J.isGray || J.is565 || J.toF16 || J.chroma == AB_CHROMA_NONE) return 0;
+    if (J.nChan != 3 && J.nChan != 4) return 0;
+    if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return 0;
+    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return 0;
+    if (!J.rangeY.exact || !J.rangeUV.exact || !J.kg.exact) return 0;
+    if ((J.alphaMul == AB_MUL_INT_PREMUL) && !J.rgbMaxDiv.exact) return 0;
+    if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.exact) return 0;
+    /* alignment of the vector accesses */
+    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
+    const bool sub = (J.chroma != AB_CHROMA_FULL);
+    uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
+    const bool needA = (J.alphaWrite == AB_ALPHA_COPY) || (J.alphaMul != AB_MUL_NONE);
+    if (needA) {
+        if (!J.a) return 0;
+        bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
+    }
+    if (bits & lumaAlign) return 0;
+    const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
+    if (cbits & (sub ? subAlign : lumaAlign)) return 0;
+    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & 15) return 0;
+    if (J.width == 0 || J.rowEnd <= J.rowBegin) return 0;
+
+    /* B-first layouts: the matrix is symmetric in (R,Cr,c1,c3) <-> (B,Cb,c2,c4) and float addition commutes, so BGR order
+     * is the RGB kernel with the chroma planes and their constants exchanged. */
+    if (J.swapRB) {
+        const uint8_t * tp = J.u; J.u = J.v; J.v = tp;
+        const int64_t ts = J.uRB; J.uRB = J.vRB; J.vRB = ts;
+        float tf = J.c1; J.c1 = J.c2; J.c2 = tf;
+        tf = J.c3; J.c3 = J.c4; J.c4 = tf;
+        J.swapRB = 0;
+    }
+    const bool afirst = J.alphaFirst != 0;
+    const int nch = J.nChan;
+#define ABF_DISPATCH(CH)                                                              \
+    do {                                                                              \
+        if (nch == 3) return launch_alpha<YT, RT, CH, 3, false>(J, st);               \
+        return afirst ? launch_alpha<YT, RT, CH, 4, true>(J, st) : launch_alpha<YT, RT, CH, 4, false>(J, st); \
+    } while (0)
+    if (J.chroma == AB_CHROMA_FULL) ABF_DISPATCH(CH_FULL);
+    if (J.chroma == AB_CHROMA_NEAREST) ABF_DISPATCH(CH_NEAREST);
+    if (J.chroma == AB_CHROMA_BILINEAR) {
+        if (J.vertBlend) ABF_DISPATCH(CH_BIL420);
+        ABF_DISPATCH(CH_BIL422);
+    }
+#undef ABF_DISPATCH
+    return 0;
+}
+
+} // namespace abfast

@@ -1,0 +1,8 @@
+/* specialised YUV->RGB kernels, 8-bit-container planes -> 16-bit-container pixels (one translation unit per
+ * type pair so the instantiations compile in parallel); see y2r_fast.cuh */
+#include "y2r_fast.cuh"
+
+extern "C" int abY2RFast_8_16(const AbY2RJob * job, void * stream)
+{
+    return abfast::launch_y2r_fast_typed<uint8_t, uint16_t>(*job, (cudaStream_t)stream);
+}

@@ -15,15 +15,3 @@ def test_every_whitelisted_divisor_exhaustively(gpu_product):
         bad = ctypes.c_uint64(123)
         assert gpu_product.avifB200SelfTestDivisor(bits, ctypes.byref(bad)) == 0
         assert bad.value == 0, f"divisor 0x{bits:08x}: {bad.value} inputs differ from IEEE division"
-
-
-def test_selftest_detects_a_bad_divisor(gpu_product):
-    """Sanity of the checker itself: for some divisors the 3-op form is NOT exact; at least one of a handful must trip."""
-    import struct
-    tripped = 0
-    for d in (3.0000002, 1.0000001, 0.3333333, 1.9999999, 123456.79):
-        bits = struct.unpack("<I", struct.pack("<f", d))[0]
-        bad = ctypes.c_uint64(0)
-        assert gpu_product.avifB200SelfTestDivisor(bits, ctypes.byref(bad)) == 0
-        tripped += bad.value > 0
-    assert tripped >= 1

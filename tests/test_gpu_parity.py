@@ -42,7 +42,7 @@ def _check_r2y(product, oracle, spec, seed, device=None, policy=0):
     return ro
 
 
-@pytest.mark.parametrize("policy", [0, 1, 2, 3], ids=["tiled", "generic", "tiled-ieee-div", "generic-ieee-div"])
+@pytest.mark.parametrize("policy", [0, 1, 2, 3, 4], ids=["fast", "generic", "tiled-ieee-div", "generic-ieee-div", "tiled"])
 def test_y2r_sweep_host_pointers(gpu_product, oracle, policy):
     n_ok = 0
     for k, spec in enumerate(util.random_y2r_specs(700, seed=21 + policy)):
@@ -64,6 +64,47 @@ def test_y2r_wide_tiles(gpu_product, oracle):
         _check_y2r(gpu_product, oracle, spec, 5000 + k)
 
 
+def test_y2r_fast_kernels_are_used_and_exact(gpu_product, oracle):
+    """Aligned, padded-free frames of tile-straddling sizes: the specialised kernels must serve them (name check)
+    and match the oracle byte for byte, for every (depth, format, upsampling, alpha) combination they cover."""
+    import dataclasses
+    import itertools
+    sizes = [(264, 6), (520, 5), (1000, 4), (257, 7), (8, 3), (2056, 3)]
+    served = 0
+    k = 0
+    for depth, rgb_depth in itertools.product([8, 10, 12, 16], [8, 10, 16]):
+        for fmt, ups in [(1, 0), (2, 3), (2, 4), (3, 3), (3, 4)]:
+            for rgb_fmt in [abi.AVIF_RGB_FORMAT_RGBA, abi.AVIF_RGB_FORMAT_BGRA, abi.AVIF_RGB_FORMAT_ARGB, abi.AVIF_RGB_FORMAT_ABGR,
+                            abi.AVIF_RGB_FORMAT_RGB, abi.AVIF_RGB_FORMAT_BGR]:
+                for alpha, ip, rp in [(False, False, False), (True, False, False), (True, False, True), (True, True, False)]:
+                    k += 1
+                    w, h = sizes[k % len(sizes)]
+                    spec = util.Spec(w=w, h=h, depth=depth, fmt=fmt, rng=k % 2, mc=[1, 6, 9, 12][k % 4], cp=[1, 9, 12][k % 3], alpha=alpha,
+                                     img_premult=ip, rgb_depth=rgb_depth, rgb_fmt=rgb_fmt, ups=ups, rgb_premult=rp, garbage=(k % 3 == 0))
+                    assert _check_y2r(gpu_product, oracle, spec, 9000 + k, device="cuda:0") == 0
+                    served += gpu_product.avifB200LastKernelName().decode().startswith("y2r_fast")
+    assert served > 0.6 * k, f"only {served} of {k} aligned conversions ran on the specialised kernels"
+
+
+def test_r2y_fast_kernels_are_used_and_exact(gpu_product, oracle):
+    import itertools
+    sizes = [(264, 6), (520, 5), (1000, 4), (257, 7), (8, 3), (2056, 3), (1, 1), (9, 2)]
+    served = 0
+    k = 0
+    for depth, rgb_depth in itertools.product([8, 10, 12, 16], [8, 10, 16]):
+        for fmt in [1, 2, 3, 4]:
+            for rgb_fmt in [abi.AVIF_RGB_FORMAT_RGBA, abi.AVIF_RGB_FORMAT_BGRA, abi.AVIF_RGB_FORMAT_ARGB, abi.AVIF_RGB_FORMAT_ABGR,
+                            abi.AVIF_RGB_FORMAT_RGB, abi.AVIF_RGB_FORMAT_BGR]:
+                for ip, rp, ign in [(False, False, False), (True, False, False), (False, True, False), (False, False, True)]:
+                    k += 1
+                    w, h = sizes[k % len(sizes)]
+                    spec = util.Spec(w=w, h=h, depth=depth, fmt=fmt, rng=k % 2, mc=[1, 6, 9, 12][k % 4], cp=[1, 9, 12][k % 3],
+                                     img_premult=ip, rgb_depth=rgb_depth, rgb_fmt=rgb_fmt, rgb_premult=rp, ignore_alpha=ign, garbage=(k % 3 == 0))
+                    assert _check_r2y(gpu_product, oracle, spec, 9500 + k, device="cuda:0") == 0
+                    served += gpu_product.avifB200LastKernelName().decode().startswith("r2y_fast")
+    assert served > 0.6 * k, f"only {served} of {k} aligned conversions ran on the specialised kernels"
+
+
 def test_y2r_unaligned_device_views(gpu_product, oracle):
     """View-rectangle style inputs: plane / pixel pointers that are only sample-aligned."""
     import dataclasses
@@ -74,7 +115,7 @@ def test_y2r_unaligned_device_views(gpu_product, oracle):
         _check_y2r(gpu_product, oracle, spec, 6000 + k, device="cuda:0")
 
 
-@pytest.mark.parametrize("policy", [0, 1, 2], ids=["vec", "generic", "vec-ieee-div"])
+@pytest.mark.parametrize("policy", [0, 1, 2, 4], ids=["fast", "generic", "vec-ieee-div", "vec"])
 def test_r2y_sweep_host_pointers(gpu_product, oracle, policy):
     n_ok = 0
     for k, spec in enumerate(util.random_r2y_specs(700, seed=31 + policy)):

@@ -8,8 +8,8 @@ cd $GRAFT_REPO_ROOT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket" >> $OUT/gpu.txt
 if [ "$2" != "skiptests" ]; then
-  timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1
-  tail -5 $OUT/pytest_gpu.log
+  timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1
+  tail -25 $OUT/pytest_gpu.log
 fi
 timeout 600 python bench.py --extras > $OUT/bench.json 2> $OUT/bench.err
 tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
@@ -17,6 +17,6 @@ tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --batch 4 --e2e-batch 1 > $OUT/ncu_launches.log 2>&1
 # full capture of the two dominant kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"y2r_tiled|r2y_block" -s 8 -c 4 -o $OUT/prof_c2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"y2r_|r2y_" -s 8 -c 4 -o $OUT/prof_c2 \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --batch 4 --e2e-batch 1 > $OUT/ncu_full.log 2>&1
 ls -la $OUT
