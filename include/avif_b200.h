@@ -313,6 +313,10 @@ AVIF_B200_API const char * avifB200LastKernelName(void);
 AVIF_B200_API size_t avifB200VerifiedDivisorCount(void);
 AVIF_B200_API uint32_t avifB200VerifiedDivisorBits(size_t index);
 AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches);
+/* Alpha unmultiply divides three colour values by the same normalised alpha; the kernels share one reciprocal
+ * between the three IEEE divisions (pixel_math.cuh: rcp_refined).  Re-checks that against the hardware's IEEE division:
+ * sampledColour == 0: every (colour code, alpha code) pair of the given depth; != 0: random colour values in [0,1]. */
+AVIF_B200_API avifResult avifB200SelfTestAlphaDivision(uint32_t depth, int sampledColour, uint64_t * mismatches);
 /* 1 if a CUDA device is usable, else 0 (conversions then fail with AVIF_RESULT_UNKNOWN_ERROR). */
 AVIF_B200_API int avifB200DeviceAvailable(void);
 AVIF_B200_API const char * avifB200Version(void);

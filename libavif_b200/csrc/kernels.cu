@@ -644,8 +644,8 @@ template <typename RT, typename YT, bool VEC>
 __global__ void __launch_bounds__(256) r2y_block_kernel(const __grid_constant__ AbR2YJob J)
 {
     const uint32_t oi = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const uint32_t oj = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
-    if (oi >= J.width || oj >= J.height) return;
+    const uint32_t oj = J.rowBegin + 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+    if (oi >= J.width || oj >= J.rowEnd) return;
     const bool both = (oi + 1 < J.width);
     const uint32_t bh = (oj + 1 >= J.height) ? 1 : 2;
     const bool srcVec = VEC && J.srcPairAligned && both;
@@ -836,6 +836,35 @@ __global__ void __launch_bounds__(256) div_selftest_kernel(float d, float r, uns
     if (bad) atomicAdd(mismatches, bad);
 }
 
+/* self-test of the shared-reciprocal division (pixel_math.cuh: rcp_refined / div_by_rcp) against __fdiv_rn:
+ * mode 0: x = c/max, a = k/max for every code pair (c, k), 0 < k < max (RGB->YUV unmultiply domain, exhaustive);
+ * mode 1: a = k/max as above, x = 65536 pseudo-random floats in [0,1] per k (YUV->RGB unmultiply domain, sampled). */
+__global__ void __launch_bounds__(256) alpha_div_selftest_kernel(uint32_t max, int mode, unsigned long long * mismatches)
+{
+    const uint64_t total = (mode == 0) ? (uint64_t)(max + 1) * (max - 1) : (uint64_t)65536 * (max - 1);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const float maxF = (float)max;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t k = 1 + (uint32_t)(i % (max - 1));
+        const uint32_t c = (uint32_t)(i / (max - 1));
+        const float a = __fdiv_rn((float)k, maxF);
+        float x;
+        if (mode == 0) {
+            x = __fdiv_rn((float)c, maxF);
+        } else {
+            uint32_t h = c * 2654435761u ^ (k * 40503u + 0x9E3779B9u);
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+            x = __fmul_rn((float)(h >> 8), 5.9604644775390625e-8f); /* 24 random bits in [0,1) */
+            if ((h & 255u) == 0) x = 1.0f;
+        }
+        if (!(a < 1.0f) || a == 0.0f) continue;
+        const float r1 = rcp_refined(a);
+        if (__float_as_uint(div_by_rcp(x, a, r1)) != __float_as_uint(__fdiv_rn(x, a))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* launch helpers                                                                                  */
 
@@ -928,7 +957,7 @@ int abR2YFast_16_16(const AbR2YJob * job, void * stream);
 int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (job->width == 0 || job->height == 0) return 0;
+    if (job->width == 0 || job->rowEnd <= job->rowBegin) return 0;
     if (forceGeneric == 0) { /* production: compile-time specialised kernels (r2y_fast.cuh) */
         int took;
         if (job->rgbBytes == 2) took = (job->yuvBytes == 2) ? abR2YFast_16_16(job, stream) : abR2YFast_16_8(job, stream);
@@ -940,7 +969,7 @@ int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const cha
     }
     forceGeneric &= 1;
     const dim3 block(32, 8);
-    const dim3 grid = grid2d((job->width + 1) / 2, (job->height + 1) / 2, block);
+    const dim3 grid = grid2d((job->width + 1) / 2, (job->rowEnd - job->rowBegin + 1) / 2, block);
 #define AB_R2Y(RT, YT)                                                                      \
     do {                                                                                    \
         if (forceGeneric) r2y_block_kernel<RT, YT, false><<<grid, block, 0, st>>>(*job);    \
@@ -1036,6 +1065,23 @@ int abDivSelfTest(float d, unsigned long long * mismatches, void * stream)
     err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
     if (!err) {
         div_selftest_kernel<<<148 * 16, 256, 0, st>>>(d, 1.0f / d, dev);
+        err = finish_launch();
+    }
+    if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);
+    if (!err) err = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return err;
+}
+
+int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long * dev = nullptr;
+    int err = (int)cudaMalloc((void **)&dev, sizeof(*dev));
+    if (err) return err;
+    err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
+    if (!err) {
+        alpha_div_selftest_kernel<<<148 * 16, 256, 0, st>>>(max, mode, dev);
         err = finish_launch();
     }
     if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);

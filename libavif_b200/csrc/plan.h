@@ -78,6 +78,7 @@ typedef struct AbR2YJob {
     uint8_t * a; /* destination alpha plane (may be NULL) */
     int64_t rgbRB, yRB, uRB, vRB, aRB;
     uint32_t width, height;
+    uint32_t rowBegin, rowEnd; /* luma rows [rowBegin,rowEnd) are converted by this launch; rowBegin is even */
     uint32_t yuvMax, rgbMax;
     float yuvMaxF, rgbMaxF;
     float biasY, biasUV, rangeY, rangeUV; /* identity: UV quantised with Y's (reformat.c:212-213) */
@@ -136,6 +137,7 @@ int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t 
                     uint32_t dstH, uint32_t bytesPerSample, void * stream);
 /* exhaustive device check of div_const's fast form for divisor d (counts x whose result differs from x/d) */
 int abDivSelfTest(float d, unsigned long long * mismatches, void * stream);
+int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, void * stream);
 /* number of kernel launches issued by the calling thread through the functions above */
 uint64_t abLaunchCount(void);
 void abLaunchCountReset(void);

@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
     constexpr int NW = 8 * PIXB / 4; /* words per lane and row */
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t px0 = blockIdx.x * kRTile + 8 * lane;
-    const uint32_t j0 = (blockIdx.y * kRWarps + warp) * ROWS;
-    if (j0 >= J.height) return; /* warp-uniform */
+    const uint32_t j0 = J.rowBegin + (blockIdx.y * kRWarps + warp) * ROWS;
+    if (j0 >= J.rowEnd) return; /* warp-uniform */
     const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
     if (nValid == 0) return;    /* no cross-lane traffic in this kernel: lanes may leave */
     const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
                 } else if (a == 0.0f) {
                     R = G = B = 0.0f;
                 } else if (a < 1.0f) {
-                    R = min1(__fdiv_rn(R, a));
-                    G = min1(__fdiv_rn(G, a));
-                    B = min1(__fdiv_rn(B, a));
+                    const float r1 = rcp_refined(a);
+                    R = min1(div_by_rcp(R, a, r1));
+                    G = min1(div_by_rcp(G, a, r1));
+                    B = min1(div_by_rcp(B, a, r1));
                 }
             }
             const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
@@ -261,7 +262,7 @@ static int rlaunch_cfg(const AbR2YJob & J, cudaStream_t st)
 {
     using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM>;
     constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
-    const uint32_t units = (J.height + ROWS - 1) / ROWS;
+    const uint32_t units = (J.rowEnd - J.rowBegin + ROWS - 1) / ROWS;
     const dim3 grid((J.width + kRTile - 1) / kRTile, (units + kRWarps - 1) / kRWarps);
     r2y_fast_kernel<C><<<grid, kRWarps * 32, 0, st>>>(J);
     return 1;
@@ -295,7 +296,7 @@ static int launch_r2y_fast_typed(const AbR2YJob & J, cudaStream_t st)
     if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return 0;
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return 0;
     if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return 0;
-    if (J.width == 0 || J.height == 0) return 0;
+    if (J.width == 0 || J.rowEnd <= J.rowBegin) return 0;
     const uint32_t pixb = J.nChan * (uint32_t)sizeof(RT);
     const uintptr_t srcAlign = ((8 * pixb) % 16 == 0) ? 15 : 7;
     if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & srcAlign) return 0;

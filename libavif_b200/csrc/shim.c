@@ -128,9 +128,13 @@ int avifFullToLimitedUV(uint32_t depth, int v) { return fullToLim(depth, 1, v); 
 /* ------------------------------------------------------------------------------------------ */
 /* per-thread CUDA context: stream + staging arena                                             */
 
+#define AB_MAX_BANDS 16
+
 typedef struct AbCtx {
     int ready;
-    cudaStream_t stream;
+    cudaStream_t stream;           /* kernels (and everything, on the unpipelined path) */
+    cudaStream_t up, down;         /* host->device / device->host copy streams of the band pipeline */
+    cudaEvent_t evUp[AB_MAX_BANDS], evKernel[AB_MAX_BANDS];
     uint8_t * arena;
     size_t arenaCap;
     int policy; /* 0 auto, 1 force generic kernels */
@@ -189,6 +193,17 @@ avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches)
     return AVIF_RESULT_OK;
 }
 
+avifResult avifB200SelfTestAlphaDivision(uint32_t depth, int sampledColour, uint64_t * mismatches)
+{
+    if (depth < 2 || depth > 16) return AVIF_RESULT_INVALID_ARGUMENT;
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    unsigned long long bad = 0;
+    AB_CUDA(abAlphaDivSelfTest((1u << depth) - 1, sampledColour ? 1 : 0, &bad, tls.stream));
+    *mismatches = bad;
+    return AVIF_RESULT_OK;
+}
+
 void * avifB200AllocPinned(size_t size)
 {
     void * p = NULL;
@@ -208,6 +223,12 @@ static avifResult ctxInit(void)
     if (tls.ready) return AVIF_RESULT_OK;
     if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR; /* no CPU fallback by design */
     AB_CUDA(cudaStreamCreateWithFlags(&tls.stream, cudaStreamNonBlocking));
+    AB_CUDA(cudaStreamCreateWithFlags(&tls.up, cudaStreamNonBlocking));
+    AB_CUDA(cudaStreamCreateWithFlags(&tls.down, cudaStreamNonBlocking));
+    for (int k = 0; k < AB_MAX_BANDS; ++k) {
+        AB_CUDA(cudaEventCreateWithFlags(&tls.evUp[k], cudaEventDisableTiming));
+        AB_CUDA(cudaEventCreateWithFlags(&tls.evKernel[k], cudaEventDisableTiming));
+    }
     tls.ready = 1;
     return AVIF_RESULT_OK;
 }
@@ -218,6 +239,7 @@ static avifResult arenaReserve(size_t bytes)
     if (bytes <= tls.arenaCap) return AVIF_RESULT_OK;
     if (tls.arena) {
         AB_CUDA(cudaStreamSynchronize(tls.stream));
+        AB_CUDA(cudaStreamSynchronize(tls.down));
         AB_CUDA(cudaFree(tls.arena));
         tls.arena = NULL;
         tls.arenaCap = 0;
@@ -305,6 +327,27 @@ static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cuda
     }
     return (int)cudaMemcpy2DAsync(r->user + (int64_t)row0 * r->userRB, (size_t)r->userRB, r->dev + (int64_t)row0 * r->devRB, (size_t)r->devRB,
                                   r->rowUsed, row1 - row0, cudaMemcpyDeviceToHost, st);
+}
+
+/* Band pipeline of the host-pointer path: the frame is cut into row bands; band b's planes go up on `up`, its
+ * kernel runs on `stream` once they (and, for vertical chroma blending, the next band's) have landed, its result
+ * goes down on `down` -- PCIe is full duplex, so a frame costs max(upload, download) instead of their sum. */
+static int planBands(uint32_t height, size_t frameBytes, uint32_t bandRows[AB_MAX_BANDS + 1])
+{
+    int n = (int)(frameBytes / ((size_t)6 << 20));
+    if (n < 1) n = 1;
+    if (n > AB_MAX_BANDS) n = AB_MAX_BANDS;
+    uint32_t per = (height + (uint32_t)n - 1) / (uint32_t)n;
+    per = (per + 1) & ~1u; /* even: chroma rows and 2x2 blocks never straddle a band */
+    if (per < 2) per = 2;
+    int count = 0;
+    uint32_t r = 0;
+    while (r < height && count < AB_MAX_BANDS) {
+        bandRows[count++] = r;
+        r += per;
+    }
+    bandRows[count] = height;
+    return count;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -719,12 +762,12 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     regionPlace(&ra, &cursor);
     regionPlace(&rrgb, &cursor);
 
-    AB_CUDA(regionUpload(&ry, 0, ry.rows, st));
-    AB_CUDA(regionUpload(&ru, 0, ru.rows, st));
-    AB_CUDA(regionUpload(&rv, 0, rv.rows, st));
-    AB_CUDA(regionUpload(&ra, 0, ra.rows, st));
     const int keepsDstBytes = (job.alphaWrite == AB_ALPHA_KEEP && rgbHasAlpha) || !sameDims;
-    if (keepsDstBytes) AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st)); /* bytes the path must leave untouched */
+    const int anyHost = !ry.onDevice || (ru.present && !ru.onDevice) || (rv.present && !rv.onDevice) || (ra.present && !ra.onDevice) || !rrgb.onDevice;
+    const size_t frameBytes = (size_t)ry.rowUsed * ry.rows + (ru.present ? 2 * (size_t)ru.rowUsed * ru.rows : 0) +
+                              (ra.present ? (size_t)ra.rowUsed * ra.rows : 0) + (size_t)rrgb.rowUsed * rrgb.rows;
+    const int pipelined = !async && anyHost && sameDims && !keepsDstBytes && frameBytes >= ((size_t)8 << 20) &&
+                          (!ra.present || image->alphaRowBytes != 0);
 
     job.y = ry.dev;
     job.yRB = ry.devRB;
@@ -745,6 +788,41 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
         if (job.a) bits |= (uintptr_t)job.a | (uintptr_t)job.aRB;
         job.pairAligned = (uint8_t)((bits & m) == 0);
     }
+
+    if (pipelined) {
+        uint32_t bands[AB_MAX_BANDS + 1];
+        const int nb = planBands(image->height, frameBytes, bands);
+        const int lookAhead = (job.chroma == AB_CHROMA_BILINEAR && job.vertBlend) ? 1 : 0;
+        const char * kname = "";
+        for (int b = 0; b < nb; ++b) {
+            const uint32_t r0 = bands[b], r1 = bands[b + 1];
+            const uint32_t c0 = r0 >> s.shiftY, c1 = (uint32_t)(((uint64_t)r1 + s.shiftY) >> s.shiftY);
+            AB_CUDA(regionUpload(&ry, r0, r1, tls.up));
+            AB_CUDA(regionUpload(&ru, c0, c1, tls.up));
+            AB_CUDA(regionUpload(&rv, c0, c1, tls.up));
+            AB_CUDA(regionUpload(&ra, r0, r1, tls.up));
+            AB_CUDA(cudaEventRecord(tls.evUp[b], tls.up));
+        }
+        for (int b = 0; b < nb; ++b) {
+            const int need = (b + lookAhead < nb) ? b + lookAhead : nb - 1;
+            AB_CUDA(cudaStreamWaitEvent(st, tls.evUp[need], 0));
+            job.rowBegin = bands[b];
+            job.rowEnd = bands[b + 1];
+            AB_CUDA(abLaunchY2R(&job, st, tls.policy, &kname));
+            AB_CUDA(cudaEventRecord(tls.evKernel[b], st));
+            AB_CUDA(cudaStreamWaitEvent(tls.down, tls.evKernel[b], 0));
+            AB_CUDA(regionDownload(&rrgb, bands[b], bands[b + 1], tls.down));
+        }
+        tls.lastKernel = kname;
+        AB_CUDA(cudaStreamSynchronize(tls.down));
+        return AVIF_RESULT_OK;
+    }
+
+    AB_CUDA(regionUpload(&ry, 0, ry.rows, st));
+    AB_CUDA(regionUpload(&ru, 0, ru.rows, st));
+    AB_CUDA(regionUpload(&rv, 0, rv.rows, st));
+    AB_CUDA(regionUpload(&ra, 0, ra.rows, st));
+    if (keepsDstBytes) AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st)); /* bytes the path must leave untouched */
 
     const char * kname = "";
     if (sameDims) {
@@ -955,8 +1033,6 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     regionPlace(&ru, &cursor);
     regionPlace(&rv, &cursor);
     regionPlace(&ra, &cursor);
-    AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st));
-
     job.rgb = rrgb.dev;
     job.rgbRB = rrgb.devRB;
     job.y = ry.dev;
@@ -967,7 +1043,8 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     job.vRB = rv.devRB;
     job.a = ra.dev;
     job.aRB = ra.devRB;
-
+    job.rowBegin = 0;
+    job.rowEnd = image->height;
     {
         /* natural alignment of one pixel pair: 16 / 8 / 4 / 2 bytes for pairs of 16 / 8 / (12|4) / (6|2) bytes */
         const uint32_t pairBytes = 2u * s.rgbPixBytes;
@@ -980,6 +1057,40 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
         if (job.a) bits |= (uintptr_t)job.a | (uintptr_t)job.aRB;
         job.dstPairAligned = (uint8_t)((bits & m) == 0);
     }
+
+    const int anyHost = !rrgb.onDevice || !ry.onDevice || (ru.present && !ru.onDevice) || (rv.present && !rv.onDevice) || (ra.present && !ra.onDevice);
+    const size_t frameBytes = (size_t)rrgb.rowUsed * rrgb.rows + (size_t)ry.rowUsed * ry.rows + (ru.present ? 2 * (size_t)ru.rowUsed * ru.rows : 0) +
+                              (ra.present ? (size_t)ra.rowUsed * ra.rows : 0);
+    if (!async && anyHost && !grayChromaFill && frameBytes >= ((size_t)8 << 20)) {
+        /* band pipeline (see planBands): pixels up, kernel, planes down, on three streams */
+        uint32_t bands[AB_MAX_BANDS + 1];
+        const int nb = planBands(image->height, frameBytes, bands);
+        const char * pname = "";
+        for (int b = 0; b < nb; ++b) {
+            AB_CUDA(regionUpload(&rrgb, bands[b], bands[b + 1], tls.up));
+            AB_CUDA(cudaEventRecord(tls.evUp[b], tls.up));
+        }
+        for (int b = 0; b < nb; ++b) {
+            const uint32_t r0 = bands[b], r1 = bands[b + 1];
+            const uint32_t c0 = r0 >> job.shiftY, c1 = (uint32_t)(((uint64_t)r1 + job.shiftY) >> job.shiftY);
+            AB_CUDA(cudaStreamWaitEvent(st, tls.evUp[b], 0));
+            job.rowBegin = r0;
+            job.rowEnd = r1;
+            AB_CUDA(abLaunchR2Y(&job, st, tls.policy, &pname));
+            AB_CUDA(cudaEventRecord(tls.evKernel[b], st));
+            AB_CUDA(cudaStreamWaitEvent(tls.down, tls.evKernel[b], 0));
+            AB_CUDA(regionDownload(&ry, r0, r1, tls.down));
+            AB_CUDA(regionDownload(&ru, c0, c1, tls.down));
+            AB_CUDA(regionDownload(&rv, c0, c1, tls.down));
+            AB_CUDA(regionDownload(&ra, r0, r1, tls.down));
+        }
+        tls.lastKernel = pname;
+        AB_CUDA(cudaStreamSynchronize(tls.down));
+        return AVIF_RESULT_OK;
+    }
+
+    AB_CUDA(regionUpload(&rrgb, 0, rrgb.rows, st));
+
     const char * kname = "";
     AB_CUDA(abLaunchR2Y(&job, st, tls.policy, &kname));
     tls.lastKernel = kname;

@@ -323,9 +323,10 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
                 } else if (Ac == 0.0f) {
                     R = G = B = 0.0f;
                 } else if (Ac < 1.0f) {
-                    R = min1(__fdiv_rn(R, Ac));
-                    G = min1(__fdiv_rn(G, Ac));
-                    B = min1(__fdiv_rn(B, Ac));
+                    const float r1 = rcp_refined(Ac);
+                    R = min1(div_by_rcp(R, Ac, r1));
+                    G = min1(div_by_rcp(G, Ac, r1));
+                    B = min1(div_by_rcp(B, Ac, r1));
                 }
             }
             float qr = quant_magic(R, J.rgbMaxF), qg = quant_magic(G, J.rgbMaxF), qb = quant_magic(B, J.rgbMaxF);
@@ -334,9 +335,14 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
                 const bool opaque = (af >= J.rgbMaxF), zero = (af == 0.0f);
                 float pr, pg, pb;
                 if (C::AM == AB_MUL_INT_PREMUL) {
-                    pr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
-                    pg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
-                    pb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), af), J.rgbMaxDiv), 0.5f), magicOne);
+                    /* a >= max leaves the code untouched and a == 0 zeroes it (src/alpha.c:180-186).  Both fall out of the
+                     * arithmetic with a clamped to max: floor(RN(RN(c*max)/max) + 0.5) == c for every code c (the product's
+                     * rounding error is < 2^-9 of a code even at 16 bits), and c*0 is 0 -- no per-channel selects needed. */
+                    const float ac = fminf(af, J.rgbMaxF);
+                    qr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+                    qg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+                    qb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+                    pr = qr; pg = qg; pb = qb;
                 } else {
                     const float lim = __fadd_rn(J.rgbMaxF, 0.5f);
                     const float d = (opaque || zero) ? 1.0f : af;
@@ -344,9 +350,11 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
                     pg = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qg, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
                     pb = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qb, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
                 }
-                qr = opaque ? qr : (zero ? magicOne : pr);
-                qg = opaque ? qg : (zero ? magicOne : pg);
-                qb = opaque ? qb : (zero ? magicOne : pb);
+                if (C::AM == AB_MUL_INT_UNPREMUL) {
+                    qr = opaque ? qr : (zero ? magicOne : pr);
+                    qg = opaque ? qg : (zero ? magicOne : pg);
+                    qb = opaque ? qb : (zero ? magicOne : pb);
+                }
             }
             const float qa = HAS_A ? am : __uint_as_float(0x4B000000u | J.rgbMax);
             if (C::NCH == 3) {

@@ -15,3 +15,13 @@ def test_every_whitelisted_divisor_exhaustively(gpu_product):
         bad = ctypes.c_uint64(123)
         assert gpu_product.avifB200SelfTestDivisor(bits, ctypes.byref(bad)) == 0
         assert bad.value == 0, f"divisor 0x{bits:08x}: {bad.value} inputs differ from IEEE division"
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12, 16])
+@pytest.mark.parametrize("sampled", [0, 1], ids=["all-code-pairs", "random-colour"])
+def test_shared_reciprocal_alpha_division(gpu_product, depth, sampled):
+    """Unmultiply shares one refined reciprocal between the three divisions by alpha: must equal IEEE division for every
+    (colour code, alpha code) pair of each depth, and on random colour values for every alpha code."""
+    bad = ctypes.c_uint64(1)
+    assert gpu_product.avifB200SelfTestAlphaDivision(depth, sampled, ctypes.byref(bad)) == 0
+    assert bad.value == 0
