@@ -283,6 +283,13 @@ AVIF_B200_API avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avi
 AVIF_B200_API avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
 AVIF_B200_API avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
 
+/* The synchronous entry points under names that do not clash with the reference's, for the internal-hook integration
+ * (seam 2) where libavif keeps its own avifImageYUVToRGB and calls these from its accelerator hooks. */
+AVIF_B200_API avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb);
+AVIF_B200_API avifResult avifB200ImageRGBToYUVHost(avifImage * image, const avifRGBImage * rgb);
+AVIF_B200_API avifResult avifB200RGBImagePremultiplyAlphaHost(avifRGBImage * rgb);
+AVIF_B200_API avifResult avifB200RGBImageUnpremultiplyAlphaHost(avifRGBImage * rgb);
+
 /* Range conversion of a whole alpha plane (reference: avifImageLimitedToFullAlpha, src/read.c:6724-6764,
  * integer avifLimitedToFullY per sample).  Host or device pointers. */
 AVIF_B200_API avifResult avifB200ImageLimitedToFullAlpha(avifImage * image);

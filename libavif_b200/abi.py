@@ -134,6 +134,10 @@ PROTOTYPES = {
     "avifB200ImageRGBToYUVAsync": (C.c_int, [_PI, _PR, C.c_void_p]),
     "avifB200RGBImagePremultiplyAlphaAsync": (C.c_int, [_PR, C.c_void_p]),
     "avifB200RGBImageUnpremultiplyAlphaAsync": (C.c_int, [_PR, C.c_void_p]),
+    "avifB200ImageYUVToRGBHost": (C.c_int, [_PI, _PR]),
+    "avifB200ImageRGBToYUVHost": (C.c_int, [_PI, _PR]),
+    "avifB200RGBImagePremultiplyAlphaHost": (C.c_int, [_PR]),
+    "avifB200RGBImageUnpremultiplyAlphaHost": (C.c_int, [_PR]),
     "avifB200ImageLimitedToFullAlpha": (C.c_int, [_PI]),
     "avifB200ImageCopySamplesAsync": (C.c_int, [_PI, _PI, C.c_uint32, C.c_void_p]),
     "avifB200ImageCopyAndPadAsync": (C.c_int, [_PI, _PI, C.c_void_p]),

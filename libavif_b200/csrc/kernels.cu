@@ -928,9 +928,18 @@ int abY2RFast_8_16(const AbY2RJob * job, void * stream);
 int abY2RFast_16_8(const AbY2RJob * job, void * stream);
 int abY2RFast_16_16(const AbY2RJob * job, void * stream);
 
+int abY2RExperiment(const AbY2RJob * job, void * stream, int variant);
+
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
+    if (forceGeneric >= 8) { /* experiment variants (bits 3-4), fall back to production when not applicable */
+        if (abY2RExperiment(job, stream, forceGeneric >> 3)) {
+            if (kernelName) *kernelName = (forceGeneric >> 3) == 1 ? "y2r_fast_444_direct" : "y2r_fast_444_uniform";
+            return finish_launch();
+        }
+        forceGeneric = 0;
+    }
     if (forceGeneric == 0) { /* production: compile-time specialised kernels for the hot configurations (y2r_fast.cuh) */
         int took;
         if (job->yuvBytes == 2) took = (job->rgbBytes == 2) ? abY2RFast_16_16(job, stream) : abY2RFast_16_8(job, stream);

@@ -171,7 +171,7 @@ void avifB200SetKernelPolicy(int policy)
 {
     /* bit 0: generic byte-addressed kernels; bit 1: IEEE division instructions instead of the verified 3-op form;
      * bit 2: skip the compile-time specialised kernels (run the runtime-configured tiled kernel) */
-    tls.policy = (policy & 1) | ((policy & 4) >> 1);
+    tls.policy = (policy & 1) | ((policy & 4) >> 1) | (policy & 0x18);
     tlsExactDivision = (policy >> 1) & 1;
 }
 uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
@@ -572,6 +572,8 @@ static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * u
 
 avifResult avifRGBImagePremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 0, NULL, 0); }
 avifResult avifRGBImageUnpremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 1, NULL, 0); }
+avifResult avifB200RGBImagePremultiplyAlphaHost(avifRGBImage * rgb) { return premultiplyCommon(rgb, 0, NULL, 0); }
+avifResult avifB200RGBImageUnpremultiplyAlphaHost(avifRGBImage * rgb) { return premultiplyCommon(rgb, 1, NULL, 0); }
 avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 0, stream, 1); }
 avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 1, stream, 1); }
 
@@ -879,6 +881,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
 }
 
 avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
+avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBAsync(const avifImage * image, avifRGBImage * rgb, void * stream) { return yuvToRgbCommon(image, rgb, stream, 1); }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1114,6 +1117,7 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
 }
 
 avifResult avifImageRGBToYUV(avifImage * image, const avifRGBImage * rgb) { return rgbToYuvCommon(image, rgb, NULL, 0); }
+avifResult avifB200ImageRGBToYUVHost(avifImage * image, const avifRGBImage * rgb) { return rgbToYuvCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avifRGBImage * rgb, void * stream) { return rgbToYuvCommon(image, rgb, stream, 1); }
 
 /* ------------------------------------------------------------------------------------------ */

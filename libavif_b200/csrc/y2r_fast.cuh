@@ -141,7 +141,10 @@ __device__ __forceinline__ uint32_t swz_unit(uint32_t u)
 
 /* ---- the kernel ------------------------------------------------------------------------------------- */
 
-template <class C>
+/* VARIANT (experiments, tools/variants.md): 0 = staged stores, per-lane range checks; 1 = direct 16-byte stores from
+ * registers (4-channel formats), no shared memory; 2 = like 0 with a warp-uniform full-tile path (unchecked vector loads,
+ * fully unrolled copy-out) */
+template <class C, int VARIANT = 0>
 __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
 {
     using YT = typename C::YT;
@@ -186,12 +189,18 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     if (!any) return; /* warp-uniform */
 
     /* ------------------------------ loads ------------------------------ */
+    const bool fullTile = (VARIANT == 2) && (x0 + kTile <= J.width); /* warp-uniform */
     uint32_t yw[ROWS][4], aw[ROWS][4];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         yw[r][0] = yw[r][1] = yw[r][2] = yw[r][3] = 0;
         aw[r][0] = aw[r][1] = aw[r][2] = aw[r][3] = 0;
-        if (rowOn[r] && nValid) {
+        if (fullTile) {
+            if (rowOn[r]) {
+                load8<YT>(J.y + (int64_t)jrow[r] * J.yRB, px0, 8, yw[r]);
+                if (NEED_A) load8<YT>(J.a + (int64_t)jrow[r] * J.aRB, px0, 8, aw[r]);
+            }
+        } else if (rowOn[r] && nValid) {
             load8<YT>(J.y + (int64_t)jrow[r] * J.yRB, px0, nValid, yw[r]);
             if (NEED_A) load8<YT>(J.a + (int64_t)jrow[r] * J.aRB, px0, nValid, aw[r]);
         }
@@ -225,7 +234,10 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
         } else {
             uw[c][0] = uw[c][1] = uw[c][2] = uw[c][3] = 0;
             vw[c][0] = vw[c][1] = vw[c][2] = vw[c][3] = 0;
-            if (nValid) {
+            if (fullTile) {
+                load8<YT>(ur, px0, 8, uw[c]);
+                load8<YT>(vr, px0, 8, vw[c]);
+            } else if (nValid) {
                 load8<YT>(ur, px0, nValid, uw[c]);
                 load8<YT>(vr, px0, nValid, vw[c]);
             }
@@ -382,6 +394,20 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
             }
         }
         (void)NV;
+        if (VARIANT == 1 && (8 * PIXB) % 16 == 0) { /* direct: the lane's 8 pixels go straight to global memory */
+            if (nValid) {
+                uint8_t * d = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
+                if (nValid == 8) {
+#pragma unroll
+                    for (int q = 0; q < NW / 4; ++q) reinterpret_cast<uint4 *>(d)[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int wi = 0; wi < NW; ++wi)
+                        if ((uint32_t)(4 * wi) < nValid * PIXB) reinterpret_cast<uint32_t *>(d)[wi] = words[wi]; /* PIXB 4 or 8: whole words */
+                }
+            }
+            continue;
+        }
         uint8_t * srow = stage + r * (kTile * PIXB);
         if ((8 * PIXB) % 16 == 0) {
             constexpr int NU = 8 * PIXB / 16;
@@ -395,9 +421,25 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
             for (int q = 0; q < NW / 2; ++q) *reinterpret_cast<uint2 *>(srow + lane * (8 * PIXB) + q * 8) = make_uint2(words[2 * q], words[2 * q + 1]);
         }
     }
+    if (VARIANT == 1 && (8 * PIXB) % 16 == 0) return;
     __syncwarp();
 
     /* ------------------------------ copy-out ------------------------------ */
+    if (fullTile) { /* whole 256-pixel tile: compile-time trip counts, no tail */
+        constexpr uint32_t NVEC = kTile * PIXB / 16;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            if (!rowOn[r]) continue;
+            const uint8_t * srow = stage + r * (kTile * PIXB);
+            uint4 * dst = reinterpret_cast<uint4 *>(J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)x0 * PIXB);
+#pragma unroll
+            for (uint32_t i = 0; i < (NVEC + 31) / 32; ++i) {
+                const uint32_t k = lane + 32 * i;
+                if (NVEC % 32 == 0 || k < NVEC) dst[k] = *reinterpret_cast<const uint4 *>(srow + swz_unit<PIXB>(k) * 16);
+            }
+        }
+        return;
+    }
     const uint32_t npx = min((uint32_t)kTile, J.width - x0);
     const uint32_t nbytes = npx * PIXB;
 #pragma unroll
@@ -415,7 +457,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 0>
 static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;
@@ -423,7 +465,7 @@ static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
     uint32_t units = rows;
     if (CHROMA == CH_BIL420) units = (J.rowEnd >> 1) - (J.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
     const dim3 grid((J.width + kTile - 1) / kTile, (units + kWarps - 1) / kWarps);
-    y2r_fast_kernel<C><<<grid, kWarps * 32, 0, st>>>(J);
+    y2r_fast_kernel<C, VARIANT><<<grid, kWarps * 32, 0, st>>>(J);
     return 1;
 }
 

@@ -11,6 +11,7 @@ if [ "$2" != "skiptests" ]; then
   timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1
   tail -25 $OUT/pytest_gpu.log
 fi
+timeout 600 python tools/experiments.py > $OUT/experiments.json 2> $OUT/experiments.err; cat $OUT/experiments.json | head -80; tail -3 $OUT/experiments.err
 timeout 600 python bench.py --extras > $OUT/bench.json 2> $OUT/bench.err
 tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
 # launch list (cold-cache, serialised: compare shares only)
