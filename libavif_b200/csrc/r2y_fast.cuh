@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
     const uint32_t px0 = blockIdx.x * kRTile + 8 * lane;
     const uint32_t j0 = J.rowBegin + (blockIdx.y * kRWarps + warp) * ROWS;
     if (j0 >= J.rowEnd) return; /* warp-uniform */
-    const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
+    const bool fullTile = (blockIdx.x * kRTile + kRTile <= J.width); /* warp-uniform: no per-lane range checks needed */
+    const uint32_t nValid = fullTile ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
     if (nValid == 0) return;    /* no cross-lane traffic in this kernel: lanes may leave */
     const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
         for (int k = 0; k < NW; ++k) w[r][k] = 0;
         if ((uint32_t)r < nRows) {
             const uint8_t * p = J.rgb + (int64_t)(j0 + r) * J.rgbRB + (int64_t)px0 * PIXB;
-            if (nValid >= 8) {
+            if (fullTile || nValid >= 8) {
                 if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
                     for (int q = 0; q < NW / 4; ++q) {
@@ -200,12 +201,13 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
             aq[t] = (C::NCH == 4 && J.alphaWrite == AB_ALPHA_COPY) ? am : __uint_as_float(0x4B000000u | J.yuvMax); /* ref: :545-569 */
         }
         const uint32_t j = j0 + r;
-        store_samples8<YT>(J.y + (int64_t)j * J.yRB, px0, nValid, yq);
+        const uint32_t ns = fullTile ? 8u : nValid;
+        store_samples8<YT>(J.y + (int64_t)j * J.yRB, px0, ns, yq);
         if (C::SUB == SUB_444) {
-            store_samples8<YT>(J.u + (int64_t)j * J.uRB, px0, nValid, uq);
-            store_samples8<YT>(J.v + (int64_t)j * J.vRB, px0, nValid, vq);
+            store_samples8<YT>(J.u + (int64_t)j * J.uRB, px0, ns, uq);
+            store_samples8<YT>(J.v + (int64_t)j * J.vRB, px0, ns, vq);
         }
-        if (J.alphaWrite != AB_ALPHA_KEEP) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, nValid, aq);
+        if (J.alphaWrite != AB_ALPHA_KEEP) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, ns, aq);
     }
 
     /* ---- subsampled chroma: ordered box sums over the samples that exist (ref: :413-467) ---- */

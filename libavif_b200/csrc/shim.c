@@ -141,6 +141,7 @@ typedef struct AbCtx {
     const char * lastKernel;
 } AbCtx;
 static _Thread_local AbCtx tls;
+static _Thread_local int tlsZeroCopy = 0;      /* experiment: kernels read / write pinned host memory directly over PCIe */
 static _Thread_local int tlsExactDivision = 0; /* 1: always use IEEE division instructions (tests cross-check both forms) */
 
 static avifResult cudaToResult(int err)
@@ -172,6 +173,7 @@ void avifB200SetKernelPolicy(int policy)
     /* bit 0: generic byte-addressed kernels; bit 1: IEEE division instructions instead of the verified 3-op form;
      * bit 2: skip the compile-time specialised kernels (run the runtime-configured tiled kernel) */
     tls.policy = (policy & 1) | ((policy & 4) >> 1) | (policy & 0x18);
+    tlsZeroCopy = (policy >> 5) & 1;
     tlsExactDivision = (policy >> 1) & 1;
 }
 uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
@@ -286,6 +288,15 @@ static void regionInit(AbRegion * r, const void * user, int64_t rb, size_t rowUs
     r->rowUsed = rowUsed;
     r->rows = rows;
     r->onDevice = assumeDevice ? 1 : ptrOnDevice(user);
+    if (!r->onDevice && tlsZeroCopy) {
+        struct cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, user) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            r->user = (uint8_t *)at.devicePointer; /* mapped pinned memory: usable by kernels as is */
+            r->onDevice = 1;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
 }
 
 static size_t regionArenaBytes(const AbRegion * r)
@@ -334,7 +345,13 @@ static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cuda
  * goes down on `down` -- PCIe is full duplex, so a frame costs max(upload, download) instead of their sum. */
 static int planBands(uint32_t height, size_t frameBytes, uint32_t bandRows[AB_MAX_BANDS + 1])
 {
-    int n = (int)(frameBytes / ((size_t)6 << 20));
+    static _Thread_local size_t bandBytes = 0;
+    if (!bandBytes) {
+        const char * e = getenv("AVIF_B200_BAND_MB"); /* tuning knob; default from profiles/r01_pcie.md */
+        const long mb = e ? atol(e) : 0;
+        bandBytes = (size_t)((mb > 0) ? mb : 6) << 20;
+    }
+    int n = (int)(frameBytes / bandBytes);
     if (n < 1) n = 1;
     if (n > AB_MAX_BANDS) n = AB_MAX_BANDS;
     uint32_t per = (height + (uint32_t)n - 1) / (uint32_t)n;

@@ -1,5 +1,6 @@
-/* Kernel-variant experiments (selected with avifB200SetKernelPolicy bits 3-4; results in profiles/): the two headline
- * 16-bit 4:4:4 configurations instantiated with VARIANT 1 (direct stores) and 2 (uniform full-tile path). */
+/* Kernel-variant experiments (selected with avifB200SetKernelPolicy bits 3-4; results in profiles/r01_variants.md): the two
+ * headline 16-bit 4:4:4 configurations instantiated with the non-production store / range-check variants
+ * (policy 8 -> VARIANT 0 staged, 16 -> VARIANT 1 direct only, 24 -> VARIANT 2 staged + uniform tiles). */
 #include "y2r_fast.cuh"
 
 using namespace abfast;
@@ -12,12 +13,14 @@ extern "C" int abY2RExperiment(const AbY2RJob * job, void * stream, int variant)
     if (J.mode != AB_MODE_COEFF || J.toF16 || J.alphaRescale || !J.rangeY.exact || !J.rangeUV.exact || !J.kg.exact || !J.rgbMaxDiv.exact) return 0;
     if ((((uintptr_t)J.y | (uintptr_t)J.yRB | (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB | (uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & 15) != 0) return 0;
     if (J.alphaWrite == AB_ALPHA_FILL && J.alphaMul == AB_MUL_NONE) {
-        if (variant == 1) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, 1>(J, st);
-        if (variant == 2) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, 2>(J, st);
+        if (variant == 1) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, 0>(J, st);
+        if (variant == 2) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, 1>(J, st);
+        if (variant == 3) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, 2>(J, st);
     }
     if (J.alphaWrite == AB_ALPHA_COPY && J.alphaMul == AB_MUL_INT_PREMUL && J.a && ((((uintptr_t)J.a | (uintptr_t)J.aRB) & 15) == 0)) {
-        if (variant == 1) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, 1>(J, st);
-        if (variant == 2) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, 2>(J, st);
+        if (variant == 1) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, 0>(J, st);
+        if (variant == 2) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, 1>(J, st);
+        if (variant == 3) return launch_cfg<uint16_t, uint16_t, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, 2>(J, st);
     }
     return 0;
 }

@@ -12,9 +12,12 @@
  *   - 4:2:0 bilinear: a warp converts TWO luma rows (2r-1, 2r) that share chroma rows r-1 and r; the 9/3/3/1
  *     products of every chroma sample are formed once and reused by both rows; the only cross-lane traffic is one
  *     warp shuffle per side per (chroma row, plane) -- the neighbour column of a lane's first / last sample;
- *   - the packed pixels (8..64 B per lane and row) go to a shared-memory tile in 16-byte units with an XOR swizzle
- *     that makes both the strided writes and the linear read-back bank-conflict free, and leave the SM as 16-byte
- *     fully coalesced vector stores.
+ *   - the lane's 8 packed pixels (24..64 B) leave as 16-byte (8-byte for 3-byte pixels) vector stores straight from
+ *     registers; lanes are contiguous, so a warp instruction covers one 0.75..2 KB span.  (A shared-memory staged
+ *     variant with XOR-swizzled, fully linear write-back measured 6 % slower on NS -- profiles/r01_variants.md --
+ *     the __syncwarp / LDS / STG chain at the end of each tile costs more issue slots than the partially filled
+ *     sectors cost L2 bandwidth; VARIANT 0 keeps it for reference.)
+ *   - full 256-pixel tiles take a warp-uniform path with no per-lane range checks.
  * Arithmetic is the reference's, operator for operator (pixel_math.cuh); eligibility (coefficients mode, aligned
  * planes, verified divisors, ...) is checked by the launcher, everything else runs on the general kernel.
  */
@@ -141,10 +144,10 @@ __device__ __forceinline__ uint32_t swz_unit(uint32_t u)
 
 /* ---- the kernel ------------------------------------------------------------------------------------- */
 
-/* VARIANT (experiments, tools/variants.md): 0 = staged stores, per-lane range checks; 1 = direct 16-byte stores from
- * registers (4-channel formats), no shared memory; 2 = like 0 with a warp-uniform full-tile path (unchecked vector loads,
- * fully unrolled copy-out) */
-template <class C, int VARIANT = 0>
+/* VARIANT: 3 (production) = direct vector stores from registers + warp-uniform full-tile path; kept for comparison
+ * (profiles/r01_variants.md): 0 = shared-memory staged stores with per-lane range checks, 1 = direct stores only,
+ * 2 = staged stores with the uniform full-tile path. */
+template <class C, int VARIANT = 3>
 __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
 {
     using YT = typename C::YT;
@@ -156,13 +159,14 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
     constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
 
-    __shared__ __align__(16) uint8_t stageAll[kWarps][ROWS * kTile * PIXB];
+    constexpr bool STAGED = (VARIANT == 0 || VARIANT == 2);
+    __shared__ __align__(16) uint8_t stageAll[STAGED ? kWarps : 1][STAGED ? ROWS * kTile * PIXB : 16];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t unit = blockIdx.y * kWarps + warp;
     const uint32_t x0 = blockIdx.x * kTile;
     const uint32_t px0 = x0 + 8 * lane;
     const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
-    uint8_t * stage = stageAll[warp];
+    uint8_t * stage = stageAll[STAGED ? warp : 0];
 
     /* rows of this warp */
     int jrow[ROWS];
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     if (!any) return; /* warp-uniform */
 
     /* ------------------------------ loads ------------------------------ */
-    const bool fullTile = (VARIANT == 2) && (x0 + kTile <= J.width); /* warp-uniform */
+    const bool fullTile = (VARIANT >= 2) && (x0 + kTile <= J.width); /* warp-uniform */
     uint32_t yw[ROWS][4], aw[ROWS][4];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -394,16 +398,26 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
             }
         }
         (void)NV;
-        if (VARIANT == 1 && (8 * PIXB) % 16 == 0) { /* direct: the lane's 8 pixels go straight to global memory */
-            if (nValid) {
+        if (VARIANT == 1 || VARIANT == 3) { /* direct: the lane's 8 pixels go straight to global memory */
+            if (fullTile || nValid == 8) {
                 uint8_t * d = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
-                if (nValid == 8) {
+                if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
                     for (int q = 0; q < NW / 4; ++q) reinterpret_cast<uint4 *>(d)[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
                 } else {
 #pragma unroll
-                    for (int wi = 0; wi < NW; ++wi)
-                        if ((uint32_t)(4 * wi) < nValid * PIXB) reinterpret_cast<uint32_t *>(d)[wi] = words[wi]; /* PIXB 4 or 8: whole words */
+                    for (int q = 0; q < NW / 2; ++q) reinterpret_cast<uint2 *>(d)[q] = make_uint2(words[2 * q], words[2 * q + 1]);
+                }
+            } else if (nValid) { /* ragged last lane of a row: 16-bit (or byte) granular */
+                uint8_t * d = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
+                if (PIXB % 2 == 0) {
+#pragma unroll
+                    for (int hw = 0; hw < 2 * NW; ++hw)
+                        if ((uint32_t)(2 * hw) < nValid * PIXB) reinterpret_cast<uint16_t *>(d)[hw] = (uint16_t)(words[hw >> 1] >> ((hw & 1) * 16));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4 * NW; ++b)
+                        if ((uint32_t)b < nValid * PIXB) d[b] = (uint8_t)(words[b >> 2] >> ((b & 3) * 8));
                 }
             }
             continue;
@@ -421,7 +435,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
             for (int q = 0; q < NW / 2; ++q) *reinterpret_cast<uint2 *>(srow + lane * (8 * PIXB) + q * 8) = make_uint2(words[2 * q], words[2 * q + 1]);
         }
     }
-    if (VARIANT == 1 && (8 * PIXB) % 16 == 0) return;
+    if (VARIANT == 1 || VARIANT == 3) return;
     __syncwarp();
 
     /* ------------------------------ copy-out ------------------------------ */
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 0>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 3>
 static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;

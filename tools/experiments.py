@@ -65,7 +65,7 @@ for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in CASES.item
             b._t[:b.nbytes].view(torch.int16).copy_(v)
         frames.append((img, RGBImage(w, h, rd, rf, upsampling=ups, alpha_premultiplied=rp, device=dev)))
     ref_hash = None
-    for pol, label in ((0, "production"), (8, "direct_stores"), (16, "uniform_full_tile")):
+    for pol, label in ((0, "production"), (8, "staged"), (16, "direct_checked"), (24, "staged_uniform")):
         lib.avifB200SetKernelPolicy(pol)
         for img, rgb in frames:
             assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
@@ -90,4 +90,36 @@ for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in CASES.item
     del frames
     torch.cuda.empty_cache()
 out["variants"] = variants
+
+# ---------------- host-pointer path: staged band pipeline vs zero-copy (kernels access pinned host memory) ----------------
+e2e = {}
+w, h, d = 3840, 2160, 10
+hsrc = YUVImage(w, h, d, 1, 1, 1, alpha=True, pinned=True)
+for p in hsrc.present_planes():
+    import numpy as np
+    b = hsrc.bufs[p]
+    b.flat[b.offset:b.offset + b.nbytes].view(np.uint16)[:] = np.random.RandomState(p).randint(0, 1024, size=b.nbytes // 2, dtype=np.uint16)
+hrgb = RGBImage(w, h, d, 1, alpha_premultiplied=True, pinned=True)
+hback = YUVImage(w, h, d, 1, 1, 1, alpha=True, pinned=True)
+ref_bytes = None
+for pol, label in ((0, "band_pipeline_default"), (32, "zero_copy")):
+    lib.avifB200SetKernelPolicy(pol)
+    for _ in range(3):
+        assert lib.avifImageYUVToRGB(hsrc.ptr(), hrgb.ptr()) == 0
+        assert lib.avifImageRGBToYUV(hback.ptr(), hrgb.ptr()) == 0
+    cur = hrgb.full_bytes().copy()
+    if ref_bytes is None:
+        ref_bytes = cur
+    t0 = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        lib.avifImageYUVToRGB(hsrc.ptr(), hrgb.ptr())
+    t1 = time.perf_counter()
+    for _ in range(n):
+        lib.avifImageRGBToYUV(hback.ptr(), hrgb.ptr())
+    t2 = time.perf_counter()
+    e2e[label] = {"y2r_ms": (t1 - t0) / n * 1e3, "r2y_ms": (t2 - t1) / n * 1e3, "Mpx_s_round_trip": 2 * w * h / ((t2 - t0) / n) / 1e6,
+                  "bytes_equal": bool((cur == ref_bytes).all())}
+lib.avifB200SetKernelPolicy(0)
+out["e2e_host_path"] = e2e
 print(json.dumps(out, indent=1))
