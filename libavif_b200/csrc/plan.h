@@ -51,6 +51,7 @@ typedef struct AbY2RJob {
     AbDiv yuvMaxDiv, rgbMaxDiv; /* (2^depth - 1) as divisors: alpha normalisation / rescale / premultiply */
     float c1, c2, c3, c4; /* 2(1-kr), 2(1-kb), kr(1-kr), kb(1-kb) as float constants (reformat.c:1014-1016) */
     float f16mul;         /* 2^-112 * (1/65535)  (reformat.c:1429-1430) */
+    uint32_t magicK;               /* 0x4B000000, passed as data so that PRMT takes it from a uniform register and keeps its selector immediate */
     float magicBiasY, magicBiasUV; /* 2^23 + bias: (float)cp - bias == as_float(cp | 0x4B000000) - magicBias, exactly */
     uint8_t yuvBytes, rgbBytes; /* bytes per sample / per channel */
     uint8_t chroma;             /* AB_CHROMA_* */
@@ -86,6 +87,7 @@ typedef struct AbR2YJob {
     float kr, kg, kb;
     AbDiv du, dv;     /* 2(1-kb), 2(1-kr) (reformat.c:385-386) */
     AbDiv rgbMaxDiv;  /* c / rgbMaxF (reformat.c:312-323) */
+    uint32_t magicK;  /* 0x4B000000 (see AbY2RJob.magicK) */
     uint8_t rgbBytes, yuvBytes;
     uint8_t shiftX, shiftY; /* chroma subsampling of the destination; both 0 for 4:4:4 */
     uint8_t hasChroma;      /* 0 for 4:0:0 */

@@ -42,10 +42,10 @@ __device__ __forceinline__ float rdivx(float x, const AbDiv & dv)
 
 /* channel value `v` (memory order, 0 .. 8*NCH-1) of the lane's packed pixels as a magic float 2^23 + code */
 template <typename RT>
-__device__ __forceinline__ float chan_magic(const uint32_t * w, int v)
+__device__ __forceinline__ float chan_magic(const uint32_t * w, int v, uint32_t K)
 {
-    if (sizeof(RT) == 2) return __uint_as_float(__byte_perm(w[v >> 1], 0x4B000000u, (v & 1) ? 0x7432u : 0x7410u));
-    return __uint_as_float(__byte_perm(w[v >> 2], 0x4B000000u, 0x7440u | (uint32_t)(v & 3)));
+    if (sizeof(RT) == 2) return __uint_as_float(__byte_perm(w[v >> 1], K, (v & 1) ? 0x7432u : 0x7410u));
+    return __uint_as_float(__byte_perm(w[v >> 2], K, 0x7440u | (uint32_t)(v & 3)));
 }
 
 /* ref: src/reformat.c:197-219: clamp((int)floorf((v*range + bias) + 0.5f), 0, yuvMax), returned as 2^23 + code */
@@ -99,8 +99,8 @@ __device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32
     }
 }
 
-template <class C>
-__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J)
+template <class C, bool FULL>
+__device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
 {
     using RT = typename C::RT;
     using YT = typename C::YT;
@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
     const uint32_t px0 = blockIdx.x * kRTile + 8 * lane;
     const uint32_t j0 = J.rowBegin + (blockIdx.y * kRWarps + warp) * ROWS;
     if (j0 >= J.rowEnd) return; /* warp-uniform */
-    const bool fullTile = (blockIdx.x * kRTile + kRTile <= J.width); /* warp-uniform: no per-lane range checks needed */
-    const uint32_t nValid = fullTile ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
+    constexpr bool fullTile = FULL; /* every lane's 8 pixels exist: no per-lane range checks */
+    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
     if (nValid == 0) return;    /* no cross-lane traffic in this kernel: lanes may leave */
     const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
 
@@ -152,6 +152,9 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
     }
 
     /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
+    const uint32_t K = J.magicK;
+    const bool copyAlpha = (C::NCH == 4) && (J.alphaWrite == AB_ALPHA_COPY), writeAlpha = (J.alphaWrite != AB_ALPHA_KEEP);
+    const float fillAlpha = __uint_as_float(0x4B000000u | J.yuvMax);
     const float magicOne = 8388608.0f;
     const float hiLimit = __fadd_rn(J.yuvMaxF, 0.5f);
     const bool swap = J.swapRB != 0;
@@ -163,12 +166,12 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             constexpr int c0 = C::AFIRST ? 1 : 0;
-            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0), magicOne), J.rgbMaxDiv);
-            const float gg = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 1), magicOne), J.rgbMaxDiv);
-            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 2), magicOne), J.rgbMaxDiv);
+            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
+            const float gg = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
+            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
             float R = swap ? x2 : x0, G = gg, B = swap ? x0 : x2;
             float am = 0.0f;
-            if (C::NCH == 4) am = chan_magic<RT>(w[r], t * C::NCH + (C::AFIRST ? 0 : 3));
+            if (C::NCH == 4) am = chan_magic<RT>(w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
             if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
                 const float a = rdivx(__fsub_rn(am, magicOne), J.rgbMaxDiv);
                 if (C::AM == AB_MUL_FLOAT_MUL) {
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
                     vf[r][t] = V;
                 }
             }
-            aq[t] = (C::NCH == 4 && J.alphaWrite == AB_ALPHA_COPY) ? am : __uint_as_float(0x4B000000u | J.yuvMax); /* ref: :545-569 */
+            aq[t] = copyAlpha ? am : fillAlpha; /* ref: :545-569 */
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
             store_samples8<YT>(J.u + (int64_t)j * J.uRB, px0, ns, uq);
             store_samples8<YT>(J.v + (int64_t)j * J.vRB, px0, ns, vq);
         }
-        if (J.alphaWrite != AB_ALPHA_KEEP) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, ns, aq);
+        if (writeAlpha) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, ns, aq);
     }
 
     /* ---- subsampled chroma: ordered box sums over the samples that exist (ref: :413-467) ---- */
@@ -257,6 +260,13 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
             store_samples4<YT>(J.v + (int64_t)j0 * J.vRB, px0 >> 1, nc, vq);
         }
     }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J)
+{
+    if (blockIdx.x * kRTile + kRTile <= J.width) r2y_fast_body<C, true>(J); /* warp-uniform */
+    else r2y_fast_body<C, false>(J);
 }
 
 template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>

@@ -349,7 +349,7 @@ static int planBands(uint32_t height, size_t frameBytes, uint32_t bandRows[AB_MA
     if (!bandBytes) {
         const char * e = getenv("AVIF_B200_BAND_MB"); /* tuning knob; default from profiles/r01_pcie.md */
         const long mb = e ? atol(e) : 0;
-        bandBytes = (size_t)((mb > 0) ? mb : 6) << 20;
+        bandBytes = (size_t)((mb > 0) ? mb : 24) << 20;
     }
     int n = (int)(frameBytes / bandBytes);
     if (n < 1) n = 1;
@@ -710,6 +710,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     job.c3 = s.kr * (1 - s.kr);
     job.c4 = s.kb * (1 - s.kb);
     job.f16mul = f16Multiplier(rgb->depth);
+    job.magicK = 0x4B000000u;
     job.magicBiasY = 8388608.0f + job.biasY;
     job.magicBiasUV = 8388608.0f + job.biasUV;
     job.yuvBytes = (uint8_t)s.yuvChanBytes;
@@ -1000,6 +1001,7 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     job.du = makeDiv(2 * (1 - s.kb));
     job.dv = makeDiv(2 * (1 - s.kr));
     job.rgbMaxDiv = makeDiv(s.rgbMaxF);
+    job.magicK = 0x4B000000u;
     job.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
     job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
     job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);

@@ -52,10 +52,10 @@ constexpr int kWarps = 8;
 
 /* magic float (2^23 + code) of sample k of a packed vector; k is a compile-time constant after unrolling */
 template <typename T>
-__device__ __forceinline__ float magic_sample(const uint32_t * w, int k)
+__device__ __forceinline__ float magic_sample(const uint32_t * w, int k, uint32_t K)
 {
-    if (sizeof(T) == 2) return __uint_as_float(__byte_perm(w[k >> 1], 0x4B000000u, (k & 1) ? 0x7432u : 0x7410u));
-    return __uint_as_float(__byte_perm(w[k >> 2], 0x4B000000u, 0x7440u | (uint32_t)(k & 3)));
+    if (sizeof(T) == 2) return __uint_as_float(__byte_perm(w[k >> 1], K, (k & 1) ? 0x7432u : 0x7410u));
+    return __uint_as_float(__byte_perm(w[k >> 2], K, 0x7440u | (uint32_t)(k & 3)));
 }
 
 /* 8 consecutive samples starting at x (x % 8 == 0, row 16/8-byte aligned); n = how many of them exist */
@@ -147,8 +147,8 @@ __device__ __forceinline__ uint32_t swz_unit(uint32_t u)
 /* VARIANT: 3 (production) = direct vector stores from registers + warp-uniform full-tile path; kept for comparison
  * (profiles/r01_variants.md): 0 = shared-memory staged stores with per-lane range checks, 1 = direct stores only,
  * 2 = staged stores with the uniform full-tile path. */
-template <class C, int VARIANT = 3>
-__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
+template <class C, int VARIANT, bool FULL>
+__device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
 {
     using YT = typename C::YT;
     using RT = typename C::RT;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     const uint32_t unit = blockIdx.y * kWarps + warp;
     const uint32_t x0 = blockIdx.x * kTile;
     const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = (px0 < J.width) ? min(8u, J.width - px0) : 0u;
+    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
     uint8_t * stage = stageAll[STAGED ? warp : 0];
 
     /* rows of this warp */
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     if (!any) return; /* warp-uniform */
 
     /* ------------------------------ loads ------------------------------ */
-    const bool fullTile = (VARIANT >= 2) && (x0 + kTile <= J.width); /* warp-uniform */
+    constexpr bool fullTile = FULL; /* every lane's 8 pixels exist: no range checks */
     uint32_t yw[ROWS][4], aw[ROWS][4];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -249,19 +249,20 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     }
 
     /* ------------------------------ chroma ------------------------------ */
+    const uint32_t K = J.magicK;
     const float magicMax = __uint_as_float(0x4B000000u | J.yuvMax);
     float cb[ROWS][8], cr[ROWS][8];
     if (!SUB) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            cb[0][t] = norm_magic<YT>(magic_sample<YT>(uw[0], t), magicMax, J.magicBiasUV, J.rangeUV);
-            cr[0][t] = norm_magic<YT>(magic_sample<YT>(vw[0], t), magicMax, J.magicBiasUV, J.rangeUV);
+            cb[0][t] = norm_magic<YT>(magic_sample<YT>(uw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
+            cr[0][t] = norm_magic<YT>(magic_sample<YT>(vw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
         }
     } else if (!BIL) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float nu = norm_magic<YT>(magic_sample<YT>(uw[0], k), magicMax, J.magicBiasUV, J.rangeUV);
-            const float nv = norm_magic<YT>(magic_sample<YT>(vw[0], k), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nu = norm_magic<YT>(magic_sample<YT>(uw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nv = norm_magic<YT>(magic_sample<YT>(vw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
             cb[0][2 * k] = cb[0][2 * k + 1] = nu;
             cr[0][2 * k] = cr[0][2 * k + 1] = nv;
         }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
                 float n[6];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? vw[c] : uw[c], k), magicMax, J.magicBiasUV, J.rangeUV);
+                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? vw[c] : uw[c], k, K), magicMax, J.magicBiasUV, J.rangeUV);
                 }
                 float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
                 float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
         float ch[8][4];          /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const float Y = norm_magic<YT>(magic_sample<YT>(yw[r], t), magicMax, J.magicBiasY, J.rangeY);
+            const float Y = norm_magic<YT>(magic_sample<YT>(yw[r], t, K), magicMax, J.magicBiasY, J.rangeY);
             const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
             /* ref: src/reformat.c:1014-1016 == :874-876 */
             float R = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
             G = clamp01f(G);
             B = clamp01f(B);
             float am = 0.0f; /* alpha sample as magic float */
-            if (NEED_A) am = magic_sample<YT>(aw[r], t);
+            if (NEED_A) am = magic_sample<YT>(aw[r], t, K);
             if (C::AM == AB_MUL_FLOAT_MUL || C::AM == AB_MUL_FLOAT_UNMUL) { /* ref: src/reformat.c:894-947 */
                 const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
                 const float Ac = clamp01f(divx(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
@@ -467,6 +468,14 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
         }
         for (uint32_t b = (nv << 4) + lane; b < nbytes; b += 32) dst[b] = srow[swz_unit<PIXB>(b >> 4) * 16 + (b & 15)];
     }
+}
+
+template <class C, int VARIANT = 3>
+__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
+{
+    /* warp-uniform choice between the unchecked full-tile body and the range-checked one (last tile of a row) */
+    if ((VARIANT >= 2) && (blockIdx.x * kTile + kTile <= J.width)) y2r_fast_body<C, VARIANT, true>(J);
+    else y2r_fast_body<C, VARIANT, false>(J);
 }
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
