@@ -139,6 +139,18 @@ def fill_uniform(img, seed):
 # reference arm / cpu baseline: the reference's own CPU code on the host cores
 
 
+def usable_cpus():
+    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     """Times C2 round trips of the reference CPU implementation with one frame per host thread.
     Returns dict(value Mpx/s, ms_per_step, cores, kind, sample)."""
@@ -151,7 +163,7 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     kind = "reference"
     if ref is None:
         ref, kind = loader.load_oracle(), "port"
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = usable_cpus()
     threads = max(1, min(cores, max_threads or cores))
     ispec, rspec = c2_specs(abi)
     # one shared read-only input frame; per-thread outputs (the conversion never writes its inputs)
@@ -171,11 +183,17 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
 
     pool = cf.ThreadPoolExecutor(max_workers=threads)
 
-    def step():
-        assert all(r == 0 for r in pool.map(one, range(threads)))
+    def step(n=None):
+        assert all(r == 0 for r in pool.map(one, range(n or threads)))
 
-    for _ in range(warmup):
+    for _ in range(max(1, warmup)):
         step()
+    # the reference arm gets its best configuration: all usable threads, or one per physical core if SMT siblings only fight
+    if threads >= 4:
+        t0 = time.perf_counter(); step(); t_all_threads = time.perf_counter() - t0
+        t0 = time.perf_counter(); step(threads // 2); t_half = time.perf_counter() - t0
+        if (threads // 2) / t_half > threads / t_all_threads * 1.05:
+            threads = threads // 2
     t_all, done = [], 0
     t_start = time.perf_counter()
     for _ in range(steps):

@@ -935,7 +935,7 @@ int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const cha
     cudaStream_t st = (cudaStream_t)stream;
     if (forceGeneric >= 8) { /* experiment variants (bits 3-4), fall back to production when not applicable */
         if (abY2RExperiment(job, stream, forceGeneric >> 3)) {
-            if (kernelName) *kernelName = (forceGeneric >> 3) == 1 ? "y2r_fast_444_staged" : (forceGeneric >> 3) == 2 ? "y2r_fast_444_direct_checked" : "y2r_fast_444_staged_uniform";
+            if (kernelName) *kernelName = "y2r_fast_one_tile_per_warp";
             return finish_launch();
         }
         forceGeneric = 0;

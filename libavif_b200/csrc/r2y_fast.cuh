@@ -99,29 +99,30 @@ __device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32
     }
 }
 
+template <class C>
+struct RTileIn {
+    static constexpr int ROWS = (C::SUB == SUB_420) ? 2 : 1;
+    static constexpr int NW = 8 * C::NCH * (int)sizeof(typename C::RT) / 4; /* words per lane and row */
+    uint32_t w[ROWS][NW];
+};
+
+/* tile = 256 pixels x ROWS rows starting at luma row j0 */
 template <class C, bool FULL>
-__device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
+__device__ __forceinline__ void load_rtile(const AbR2YJob & J, uint32_t x0, uint32_t j0, uint32_t lane, RTileIn<C> & in)
 {
     using RT = typename C::RT;
-    using YT = typename C::YT;
-    constexpr int ROWS = (C::SUB == SUB_420) ? 2 : 1;
+    constexpr int ROWS = RTileIn<C>::ROWS;
     constexpr int PIXB = C::NCH * (int)sizeof(RT);
-    constexpr int NW = 8 * PIXB / 4; /* words per lane and row */
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t px0 = blockIdx.x * kRTile + 8 * lane;
-    const uint32_t j0 = J.rowBegin + (blockIdx.y * kRWarps + warp) * ROWS;
-    if (j0 >= J.rowEnd) return; /* warp-uniform */
-    constexpr bool fullTile = FULL; /* every lane's 8 pixels exist: no per-lane range checks */
+    constexpr int NW = RTileIn<C>::NW;
+    constexpr bool fullTile = FULL;
+    const uint32_t px0 = x0 + 8 * lane;
     const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
-    if (nValid == 0) return;    /* no cross-lane traffic in this kernel: lanes may leave */
     const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
-
     /* ---- loads: 8 pixels x ROWS rows, issued before any arithmetic ---- */
-    uint32_t w[ROWS][NW];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-        for (int k = 0; k < NW; ++k) w[r][k] = 0;
+        for (int k = 0; k < NW; ++k) in.w[r][k] = 0;
         if ((uint32_t)r < nRows) {
             const uint8_t * p = J.rgb + (int64_t)(j0 + r) * J.rgbRB + (int64_t)px0 * PIXB;
             if (fullTile || nValid >= 8) {
@@ -129,13 +130,13 @@ __device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
 #pragma unroll
                     for (int q = 0; q < NW / 4; ++q) {
                         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + q);
-                        w[r][4 * q] = v.x; w[r][4 * q + 1] = v.y; w[r][4 * q + 2] = v.z; w[r][4 * q + 3] = v.w;
+                        in.w[r][4 * q] = v.x; in.w[r][4 * q + 1] = v.y; in.w[r][4 * q + 2] = v.z; in.w[r][4 * q + 3] = v.w;
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < NW / 2; ++q) {
                         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p) + q);
-                        w[r][2 * q] = v.x; w[r][2 * q + 1] = v.y;
+                        in.w[r][2 * q] = v.x; in.w[r][2 * q + 1] = v.y;
                     }
                 }
             } else {
@@ -143,13 +144,27 @@ __device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
                 for (int v = 0; v < 8 * C::NCH; ++v) {
                     if ((uint32_t)(v / C::NCH) < nValid) {
                         const uint32_t s = (uint32_t)__ldg(reinterpret_cast<const RT *>(p) + v);
-                        if (sizeof(RT) == 2) w[r][v >> 1] |= s << ((v & 1) * 16);
-                        else w[r][v >> 2] |= s << ((v & 3) * 8);
+                        if (sizeof(RT) == 2) in.w[r][v >> 1] |= s << ((v & 1) * 16);
+                        else in.w[r][v >> 2] |= s << ((v & 3) * 8);
                     }
                 }
             }
         }
     }
+
+}
+
+template <class C, bool FULL>
+__device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
+{
+    using RT = typename C::RT;
+    using YT = typename C::YT;
+    constexpr int ROWS = RTileIn<C>::ROWS;
+    constexpr bool fullTile = FULL;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
+    if (nValid == 0) return; /* no cross-lane traffic in this kernel */
+    const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
 
     /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
     const uint32_t K = J.magicK;
@@ -166,12 +181,12 @@ __device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             constexpr int c0 = C::AFIRST ? 1 : 0;
-            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
-            const float gg = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
-            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
+            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
+            const float gg = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
+            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
             float R = swap ? x2 : x0, G = gg, B = swap ? x0 : x2;
             float am = 0.0f;
-            if (C::NCH == 4) am = chan_magic<RT>(w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
+            if (C::NCH == 4) am = chan_magic<RT>(in.w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
             if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
                 const float a = rdivx(__fsub_rn(am, magicOne), J.rgbMaxDiv);
                 if (C::AM == AB_MUL_FLOAT_MUL) {
@@ -262,11 +277,43 @@ __device__ __forceinline__ void r2y_fast_body(const AbR2YJob & J)
     }
 }
 
-template <class C>
-__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J)
+/* Persistent, software-pipelined like y2r_fast_kernel: a warp strides over the 256-pixel tiles and loads tile i+1 into a
+ * second register set before converting tile i.  PERSIST = false: one tile per warp (comparison variant). */
+template <class C, bool PERSIST = true>
+__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J, const uint32_t tilesX, const uint32_t totalTiles)
 {
-    if (blockIdx.x * kRTile + kRTile <= J.width) r2y_fast_body<C, true>(J); /* warp-uniform */
-    else r2y_fast_body<C, false>(J);
+    constexpr int ROWS = RTileIn<C>::ROWS;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * kRWarps;
+    uint32_t tile = blockIdx.x * kRWarps + warp;
+    if (tile >= totalTiles) return;
+    RTileIn<C> cur, nxt;
+    uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kRTile, j0 = J.rowBegin + unit * ROWS;
+    bool full = (x0 + kRTile <= J.width);
+    if (full) load_rtile<C, true>(J, x0, j0, lane, cur);
+    else load_rtile<C, false>(J, x0, j0, lane, cur);
+    while (true) {
+        const uint32_t ntile = tile + stride;
+        const bool more = PERSIST && (ntile < totalTiles); /* warp-uniform */
+        uint32_t nx0 = 0, nj0 = 0;
+        bool nfull = false;
+        if (more) {
+            const uint32_t nunit = ntile / tilesX;
+            nx0 = (ntile - nunit * tilesX) * kRTile;
+            nj0 = J.rowBegin + nunit * ROWS;
+            nfull = (nx0 + kRTile <= J.width);
+            if (nfull) load_rtile<C, true>(J, nx0, nj0, lane, nxt);
+            else load_rtile<C, false>(J, nx0, nj0, lane, nxt);
+        }
+        if (full) convert_store_rtile<C, true>(J, x0, j0, lane, cur);
+        else convert_store_rtile<C, false>(J, x0, j0, lane, cur);
+        if (!more) break;
+        cur = nxt;
+        tile = ntile;
+        x0 = nx0;
+        j0 = nj0;
+        full = nfull;
+    }
 }
 
 template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>
@@ -275,8 +322,19 @@ static int rlaunch_cfg(const AbR2YJob & J, cudaStream_t st)
     using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM>;
     constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
     const uint32_t units = (J.rowEnd - J.rowBegin + ROWS - 1) / ROWS;
-    const dim3 grid((J.width + kRTile - 1) / kRTile, (units + kRWarps - 1) / kRWarps);
-    r2y_fast_kernel<C><<<grid, kRWarps * 32, 0, st>>>(J);
+    const uint32_t tilesX = (J.width + kRTile - 1) / kRTile;
+    const uint32_t total = tilesX * units;
+    static int resident = 0; /* blocks resident on the whole device (per instantiation) */
+    if (!resident) {
+        int dev = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C, true>, kRWarps * 32, 0);
+        resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+    }
+    uint32_t blocks = (total + kRWarps - 1) / kRWarps;
+    if (blocks > (uint32_t)resident) blocks = (uint32_t)resident;
+    r2y_fast_kernel<C, true><<<blocks, kRWarps * 32, 0, st>>>(J, tilesX, total);
     return 1;
 }
 

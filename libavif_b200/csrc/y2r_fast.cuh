@@ -17,7 +17,9 @@
  *     variant with XOR-swizzled, fully linear write-back measured 6 % slower on NS -- profiles/r01_variants.md --
  *     the __syncwarp / LDS / STG chain at the end of each tile costs more issue slots than the partially filled
  *     sectors cost L2 bandwidth; VARIANT 0 keeps it for reference.)
- *   - full 256-pixel tiles take a warp-uniform path with no per-lane range checks.
+ *   - full 256-pixel tiles take a warp-uniform path with no per-lane range checks;
+ *   - warps are persistent and software-pipelined: the loads of the next tile are issued before the current tile is
+ *     converted (see y2r_fast_kernel).
  * Arithmetic is the reference's, operator for operator (pixel_math.cuh); eligibility (coefficients mode, aligned
  * planes, verified divisors, ...) is checked by the launcher, everything else runs on the general kernel.
  */
@@ -133,120 +135,131 @@ __device__ __forceinline__ float quant_magic(float c, float maxF) { return __fad
 
 __device__ __forceinline__ float clamp01f(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); } /* == AVIF_CLAMP for non-NaN */
 
-/* ---- staging tile ---------------------------------------------------------------------------------- */
+/* ---- one warp tile: loads, then arithmetic + stores --------------------------------------------------- */
 
-template <int PIXB>
-__device__ __forceinline__ uint32_t swz_unit(uint32_t u)
-{
-    constexpr uint32_t M = (PIXB == 8) ? 3u : (PIXB == 4) ? 1u : 0u;
-    return u ^ ((u >> 3) & M);
-}
-
-/* ---- the kernel ------------------------------------------------------------------------------------- */
-
-/* VARIANT: 3 (production) = direct vector stores from registers + warp-uniform full-tile path; kept for comparison
- * (profiles/r01_variants.md): 0 = shared-memory staged stores with per-lane range checks, 1 = direct stores only,
- * 2 = staged stores with the uniform full-tile path. */
-template <class C, int VARIANT, bool FULL>
-__device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
-{
+template <class C>
+struct TileTraits {
     using YT = typename C::YT;
     using RT = typename C::RT;
-    constexpr bool SUB = (C::CHROMA != CH_FULL);
-    constexpr bool BIL = (C::CHROMA == CH_BIL420 || C::CHROMA == CH_BIL422);
-    constexpr int ROWS = (C::CHROMA == CH_BIL420) ? 2 : 1;
-    constexpr int PIXB = C::NCH * (int)sizeof(RT);
-    constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
-    constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
+    static constexpr bool SUB = (C::CHROMA != CH_FULL);
+    static constexpr bool BIL = (C::CHROMA == CH_BIL420 || C::CHROMA == CH_BIL422);
+    static constexpr int ROWS = (C::CHROMA == CH_BIL420) ? 2 : 1;
+    static constexpr int CROWS = ROWS;
+    static constexpr int PIXB = C::NCH * (int)sizeof(RT);
+    static constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
+    static constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
+    static constexpr int CW = SUB ? 2 : 4; /* words of one chroma row of the lane */
+};
 
-    constexpr bool STAGED = (VARIANT == 0 || VARIANT == 2);
-    __shared__ __align__(16) uint8_t stageAll[STAGED ? kWarps : 1][STAGED ? ROWS * kTile * PIXB : 16];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t unit = blockIdx.y * kWarps + warp;
-    const uint32_t x0 = blockIdx.x * kTile;
-    const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
-    uint8_t * stage = stageAll[STAGED ? warp : 0];
+/* everything a lane loads for one tile: packed sample words, plus the bilinear halo columns of the edge lanes */
+template <class C>
+struct TileIn {
+    using T = TileTraits<C>;
+    uint32_t yw[T::ROWS][4];
+    uint32_t aw[T::NEED_A ? T::ROWS : 1][4];
+    uint32_t uw[T::CROWS][T::CW], vw[T::CROWS][T::CW];
+    float hlU[T::BIL ? T::CROWS : 1], hrU[T::BIL ? T::CROWS : 1], hlV[T::BIL ? T::CROWS : 1], hrV[T::BIL ? T::CROWS : 1];
+};
 
-    /* rows of this warp */
-    int jrow[ROWS];
-    bool rowOn[ROWS];
-    int cA = 0, cB = 0; /* chroma rows (BIL420: r-1 and r; otherwise the single chroma row in cA) */
+/* rows of a tile: `unit` counts luma rows, or row pairs (2r-1, 2r) for 4:2:0 bilinear */
+template <class C>
+struct TileRows {
+    int jrow[TileTraits<C>::ROWS];
+    bool rowOn[TileTraits<C>::ROWS];
+    int cA, cB; /* chroma rows: r-1 and r of a bilinear 4:2:0 pair (missing ones replicate the other), else the row's own */
+    bool any;
+};
+
+template <class C>
+__device__ __forceinline__ TileRows<C> tile_rows(const AbY2RJob & J, uint32_t unit)
+{
+    constexpr int ROWS = TileTraits<C>::ROWS;
+    TileRows<C> R;
     if (ROWS == 2) {
         const int ru = (int)(J.rowBegin >> 1) + (int)unit;
-        jrow[0] = 2 * ru - 1;
-        jrow[ROWS - 1] = 2 * ru;
+        R.jrow[0] = 2 * ru - 1;
+        R.jrow[ROWS - 1] = 2 * ru;
         const int chromaH = (int)((J.height + 1) >> 1);
-        const bool hasA = (ru >= 1), hasB = (ru < chromaH);
-        cA = hasA ? ru - 1 : ru;
-        cB = hasB ? ru : ru - 1;
+        R.cA = (ru >= 1) ? ru - 1 : ru;
+        R.cB = (ru < chromaH) ? ru : ru - 1;
     } else {
-        jrow[0] = (int)(J.rowBegin + unit);
-        cA = cB = jrow[0] >> J.shiftY;
+        R.jrow[0] = (int)(J.rowBegin + unit);
+        R.cA = R.cB = R.jrow[0] >> J.shiftY;
     }
-    bool any = false;
+    R.any = false;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        rowOn[r] = (jrow[r] >= (int)J.rowBegin) && (jrow[r] < (int)J.rowEnd);
-        any = any || rowOn[r];
+        R.rowOn[r] = (R.jrow[r] >= (int)J.rowBegin) && (R.jrow[r] < (int)J.rowEnd);
+        R.any = R.any || R.rowOn[r];
     }
-    if (!any) return; /* warp-uniform */
+    return R;
+}
 
-    /* ------------------------------ loads ------------------------------ */
-    constexpr bool fullTile = FULL; /* every lane's 8 pixels exist: no range checks */
-    uint32_t yw[ROWS][4], aw[ROWS][4];
+template <class C, bool FULL>
+__device__ __forceinline__ void load_tile(const AbY2RJob & J, const TileRows<C> & R, uint32_t x0, uint32_t lane, TileIn<C> & in)
+{
+    using T = TileTraits<C>;
+    using YT = typename T::YT;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        yw[r][0] = yw[r][1] = yw[r][2] = yw[r][3] = 0;
-        aw[r][0] = aw[r][1] = aw[r][2] = aw[r][3] = 0;
-        if (fullTile) {
-            if (rowOn[r]) {
-                load8<YT>(J.y + (int64_t)jrow[r] * J.yRB, px0, 8, yw[r]);
-                if (NEED_A) load8<YT>(J.a + (int64_t)jrow[r] * J.aRB, px0, 8, aw[r]);
-            }
-        } else if (rowOn[r] && nValid) {
-            load8<YT>(J.y + (int64_t)jrow[r] * J.yRB, px0, nValid, yw[r]);
-            if (NEED_A) load8<YT>(J.a + (int64_t)jrow[r] * J.aRB, px0, nValid, aw[r]);
+    for (int r = 0; r < T::ROWS; ++r) {
+        in.yw[r][0] = in.yw[r][1] = in.yw[r][2] = in.yw[r][3] = 0;
+        if (T::NEED_A) in.aw[r][0] = in.aw[r][1] = in.aw[r][2] = in.aw[r][3] = 0;
+        if (R.rowOn[r] && (FULL || nValid)) {
+            load8<YT>(J.y + (int64_t)R.jrow[r] * J.yRB, px0, nValid, in.yw[r]);
+            if (T::NEED_A) load8<YT>(J.a + (int64_t)R.jrow[r] * J.aRB, px0, nValid, in.aw[r]);
         }
     }
-    constexpr int CROWS = (ROWS == 2) ? 2 : 1;
-    uint32_t uw[CROWS][SUB ? 2 : 4], vw[CROWS][SUB ? 2 : 4];
-    float hlU[CROWS], hrU[CROWS], hlV[CROWS], hrV[CROWS]; /* halo columns as magic floats (edge lanes only) */
-    const uint32_t cw = SUB ? ((J.width + 1) >> 1) : J.width;
-    const uint32_t m0 = SUB ? (px0 >> 1) : px0;
+    const uint32_t cw = T::SUB ? ((J.width + 1) >> 1) : J.width;
+    const uint32_t m0 = T::SUB ? (px0 >> 1) : px0;
 #pragma unroll
-    for (int c = 0; c < CROWS; ++c) {
-        const int crow = (c == 0) ? cA : cB;
+    for (int c = 0; c < T::CROWS; ++c) {
+        const int crow = (c == 0) ? R.cA : R.cB;
         const uint8_t * ur = J.u + (int64_t)crow * J.uRB;
         const uint8_t * vr = J.v + (int64_t)crow * J.vRB;
-        hlU[c] = hrU[c] = hlV[c] = hrV[c] = 0.0f;
-        if (SUB) {
-            load4_clamped<YT>(ur, m0, cw, uw[c]);
-            load4_clamped<YT>(vr, m0, cw, vw[c]);
-            if (BIL) {
+        if (T::SUB) {
+            if (FULL) { /* the lane's 4 columns exist: m0 + 3 <= 127 + 128*tile < cw */
+                load4_clamped<YT>(ur, m0, m0 + 4, in.uw[c]);
+                load4_clamped<YT>(vr, m0, m0 + 4, in.vw[c]);
+            } else {
+                load4_clamped<YT>(ur, m0, cw, in.uw[c]);
+                load4_clamped<YT>(vr, m0, cw, in.vw[c]);
+            }
+            if (T::BIL) {
+                in.hlU[c] = in.hrU[c] = in.hlV[c] = in.hrV[c] = 0.0f;
                 if (lane == 0) {
                     const uint32_t col = (m0 > 0) ? m0 - 1 : 0;
-                    hlU[c] = magic_scalar<YT>(ur, col);
-                    hlV[c] = magic_scalar<YT>(vr, col);
+                    in.hlU[c] = magic_scalar<YT>(ur, col);
+                    in.hlV[c] = magic_scalar<YT>(vr, col);
                 }
                 if (lane == 31) {
                     const uint32_t col = min(m0 + 4, cw - 1);
-                    hrU[c] = magic_scalar<YT>(ur, col);
-                    hrV[c] = magic_scalar<YT>(vr, col);
+                    in.hrU[c] = magic_scalar<YT>(ur, col);
+                    in.hrV[c] = magic_scalar<YT>(vr, col);
                 }
             }
         } else {
-            uw[c][0] = uw[c][1] = uw[c][2] = uw[c][3] = 0;
-            vw[c][0] = vw[c][1] = vw[c][2] = vw[c][3] = 0;
-            if (fullTile) {
-                load8<YT>(ur, px0, 8, uw[c]);
-                load8<YT>(vr, px0, 8, vw[c]);
-            } else if (nValid) {
-                load8<YT>(ur, px0, nValid, uw[c]);
-                load8<YT>(vr, px0, nValid, vw[c]);
+#pragma unroll
+            for (int k = 0; k < T::CW; ++k) in.uw[c][k] = in.vw[c][k] = 0;
+            if (FULL || nValid) {
+                load8<YT>(ur, px0, nValid, in.uw[c]);
+                load8<YT>(vr, px0, nValid, in.vw[c]);
             }
         }
     }
+}
+
+template <class C, bool FULL>
+__device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in)
+{
+    using T = TileTraits<C>;
+    using YT = typename T::YT;
+    using RT = typename T::RT;
+    constexpr int ROWS = T::ROWS, CROWS = T::CROWS, PIXB = T::PIXB;
+    constexpr bool SUB = T::SUB, BIL = T::BIL, HAS_A = T::HAS_A, NEED_A = T::NEED_A;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
 
     /* ------------------------------ chroma ------------------------------ */
     const uint32_t K = J.magicK;
@@ -255,14 +268,14 @@ __device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
     if (!SUB) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            cb[0][t] = norm_magic<YT>(magic_sample<YT>(uw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
-            cr[0][t] = norm_magic<YT>(magic_sample<YT>(vw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
+            cb[0][t] = norm_magic<YT>(magic_sample<YT>(in.uw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
+            cr[0][t] = norm_magic<YT>(magic_sample<YT>(in.vw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
         }
     } else if (!BIL) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float nu = norm_magic<YT>(magic_sample<YT>(uw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
-            const float nv = norm_magic<YT>(magic_sample<YT>(vw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nu = norm_magic<YT>(magic_sample<YT>(in.uw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nv = norm_magic<YT>(magic_sample<YT>(in.vw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
             cb[0][2 * k] = cb[0][2 * k + 1] = nu;
             cr[0][2 * k] = cr[0][2 * k + 1] = nv;
         }
@@ -278,12 +291,12 @@ __device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
                 float n[6];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? vw[c] : uw[c], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? in.vw[c] : in.uw[c], k, K), magicMax, J.magicBiasUV, J.rangeUV);
                 }
                 float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
                 float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
-                if (lane == 0) left = norm_magic<YT>(plane ? hlV[c] : hlU[c], magicMax, J.magicBiasUV, J.rangeUV);
-                if (lane == 31) right = norm_magic<YT>(plane ? hrV[c] : hrU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                if (lane == 0) left = norm_magic<YT>(plane ? in.hlV[c] : in.hlU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                if (lane == 31) right = norm_magic<YT>(plane ? in.hrV[c] : in.hrU[c], magicMax, J.magicBiasUV, J.rangeUV);
                 n[0] = left;
                 n[5] = right;
 #pragma unroll
@@ -314,64 +327,59 @@ __device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
     const float magicOne = 8388608.0f;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        if (!rowOn[r]) continue; /* warp-uniform */
-        float ch[8][4];          /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
+        if (!R.rowOn[r]) continue; /* warp-uniform */
+        float ch[8][4];            /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const float Y = norm_magic<YT>(magic_sample<YT>(yw[r], t, K), magicMax, J.magicBiasY, J.rangeY);
+            const float Y = norm_magic<YT>(magic_sample<YT>(in.yw[r], t, K), magicMax, J.magicBiasY, J.rangeY);
             const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
             /* ref: src/reformat.c:1014-1016 == :874-876 */
-            float R = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
-            float B = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
-            float G = __fsub_rn(Y, divx(__fmul_rn(2.0f, __fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb))), J.kg));
-            R = clamp01f(R);
-            G = clamp01f(G);
-            B = clamp01f(B);
+            float Rv = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
+            float Bv = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
+            float Gv = __fsub_rn(Y, divx(__fmul_rn(2.0f, __fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb))), J.kg));
+            Rv = clamp01f(Rv);
+            Gv = clamp01f(Gv);
+            Bv = clamp01f(Bv);
             float am = 0.0f; /* alpha sample as magic float */
-            if (NEED_A) am = magic_sample<YT>(aw[r], t, K);
+            if (NEED_A) am = magic_sample<YT>(in.aw[r], t, K);
             if (C::AM == AB_MUL_FLOAT_MUL || C::AM == AB_MUL_FLOAT_UNMUL) { /* ref: src/reformat.c:894-947 */
                 const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
                 const float Ac = clamp01f(divx(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
                 if (C::AM == AB_MUL_FLOAT_MUL) {
                     const bool scale = (Ac < 1.0f); /* Ac == 0 gives exact zeros through the multiply as well */
-                    R = scale ? __fmul_rn(R, Ac) : R;
-                    G = scale ? __fmul_rn(G, Ac) : G;
-                    B = scale ? __fmul_rn(B, Ac) : B;
+                    Rv = scale ? __fmul_rn(Rv, Ac) : Rv;
+                    Gv = scale ? __fmul_rn(Gv, Ac) : Gv;
+                    Bv = scale ? __fmul_rn(Bv, Ac) : Bv;
                 } else if (Ac == 0.0f) {
-                    R = G = B = 0.0f;
+                    Rv = Gv = Bv = 0.0f;
                 } else if (Ac < 1.0f) {
                     const float r1 = rcp_refined(Ac);
-                    R = min1(div_by_rcp(R, Ac, r1));
-                    G = min1(div_by_rcp(G, Ac, r1));
-                    B = min1(div_by_rcp(B, Ac, r1));
+                    Rv = min1(div_by_rcp(Rv, Ac, r1));
+                    Gv = min1(div_by_rcp(Gv, Ac, r1));
+                    Bv = min1(div_by_rcp(Bv, Ac, r1));
                 }
             }
-            float qr = quant_magic(R, J.rgbMaxF), qg = quant_magic(G, J.rgbMaxF), qb = quant_magic(B, J.rgbMaxF);
-            if (C::AM == AB_MUL_INT_PREMUL || C::AM == AB_MUL_INT_UNPREMUL) { /* ref: src/alpha.c:179-192, :366-381 on the quantised codes */
-                const float af = __fsub_rn(am, magicOne); /* raw (unclamped) alpha code: it is what the channel holds */
+            float qr = quant_magic(Rv, J.rgbMaxF), qg = quant_magic(Gv, J.rgbMaxF), qb = quant_magic(Bv, J.rgbMaxF);
+            if (C::AM == AB_MUL_INT_PREMUL) { /* ref: src/alpha.c:179-192 on the quantised codes */
+                /* a >= max leaves the code untouched and a == 0 zeroes it (src/alpha.c:180-186).  Both fall out of the
+                 * arithmetic with a clamped to max: floor(RN(RN(c*max)/max) + 0.5) == c for every code c (the product's
+                 * rounding error is < 2^-9 of a code even at 16 bits), and c*0 is 0 -- no per-channel selects needed. */
+                const float ac = fminf(__fsub_rn(am, magicOne), J.rgbMaxF); /* raw (unclamped) alpha code: what the channel holds */
+                qr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+                qg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+                qb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+            } else if (C::AM == AB_MUL_INT_UNPREMUL) { /* ref: src/alpha.c:366-381 */
+                const float af = __fsub_rn(am, magicOne);
                 const bool opaque = (af >= J.rgbMaxF), zero = (af == 0.0f);
-                float pr, pg, pb;
-                if (C::AM == AB_MUL_INT_PREMUL) {
-                    /* a >= max leaves the code untouched and a == 0 zeroes it (src/alpha.c:180-186).  Both fall out of the
-                     * arithmetic with a clamped to max: floor(RN(RN(c*max)/max) + 0.5) == c for every code c (the product's
-                     * rounding error is < 2^-9 of a code even at 16 bits), and c*0 is 0 -- no per-channel selects needed. */
-                    const float ac = fminf(af, J.rgbMaxF);
-                    qr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
-                    qg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
-                    qb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
-                    pr = qr; pg = qg; pb = qb;
-                } else {
-                    const float lim = __fadd_rn(J.rgbMaxF, 0.5f);
-                    const float d = (opaque || zero) ? 1.0f : af;
-                    pr = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qr, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
-                    pg = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qg, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
-                    pb = __fadd_rz(fminf(__fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(qb, magicOne), J.rgbMaxF), d), 0.5f), lim), magicOne);
-                }
-                if (C::AM == AB_MUL_INT_UNPREMUL) {
-                    qr = opaque ? qr : (zero ? magicOne : pr);
-                    qg = opaque ? qg : (zero ? magicOne : pg);
-                    qb = opaque ? qb : (zero ? magicOne : pb);
-                }
+                const float lim = __fadd_rn(J.rgbMaxF, 0.5f);
+                const float d = (opaque || zero) ? 1.0f : af;
+                const float r1 = rcp_refined(d); /* codes * max over a code: exponents within +-33, inside the guarded range */
+                const float pr = __fadd_rz(fminf(__fadd_rn(div_by_rcp(__fmul_rn(__fsub_rn(qr, magicOne), J.rgbMaxF), d, r1), 0.5f), lim), magicOne);
+                const float pg = __fadd_rz(fminf(__fadd_rn(div_by_rcp(__fmul_rn(__fsub_rn(qg, magicOne), J.rgbMaxF), d, r1), 0.5f), lim), magicOne);
+                const float pb = __fadd_rz(fminf(__fadd_rn(div_by_rcp(__fmul_rn(__fsub_rn(qb, magicOne), J.rgbMaxF), d, r1), 0.5f), lim), magicOne);
+                qr = opaque ? qr : (zero ? magicOne : pr);
+                qg = opaque ? qg : (zero ? magicOne : pg);
+                qb = opaque ? qb : (zero ? magicOne : pb);
             }
             const float qa = HAS_A ? am : __uint_as_float(0x4B000000u | J.rgbMax);
             if (C::NCH == 3) {
@@ -382,9 +390,8 @@ __device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
                 ch[t][0] = qr; ch[t][1] = qg; ch[t][2] = qb; ch[t][3] = qa;
             }
         }
-        /* pack the lane's 8 pixels (8*PIXB bytes) and store them into the swizzled staging row */
-        constexpr int NV = 8 * C::NCH;              /* channel values of the lane */
-        constexpr int NW = 8 * PIXB / 4;            /* 32-bit words of the lane */
+        /* pack the lane's 8 pixels (8*PIXB bytes) and store them: lanes are contiguous, 16-byte (8-byte for 3-byte pixels) vectors */
+        constexpr int NW = 8 * PIXB / 4; /* 32-bit words of the lane */
         uint32_t words[NW];
 #pragma unroll
         for (int wi = 0; wi < NW; ++wi) {
@@ -398,97 +405,120 @@ __device__ __forceinline__ void y2r_fast_body(const AbY2RJob & J)
                 words[wi] = __byte_perm(lo, hi, 0x5410u);
             }
         }
-        (void)NV;
-        if (VARIANT == 1 || VARIANT == 3) { /* direct: the lane's 8 pixels go straight to global memory */
-            if (fullTile || nValid == 8) {
-                uint8_t * d = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
-                if ((8 * PIXB) % 16 == 0) {
+        uint8_t * d = J.rgb + (int64_t)R.jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
+        if (FULL || nValid == 8) {
+            if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
-                    for (int q = 0; q < NW / 4; ++q) reinterpret_cast<uint4 *>(d)[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
-                } else {
+                for (int q = 0; q < NW / 4; ++q) reinterpret_cast<uint4 *>(d)[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
+            } else {
 #pragma unroll
-                    for (int q = 0; q < NW / 2; ++q) reinterpret_cast<uint2 *>(d)[q] = make_uint2(words[2 * q], words[2 * q + 1]);
-                }
-            } else if (nValid) { /* ragged last lane of a row: 16-bit (or byte) granular */
-                uint8_t * d = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
-                if (PIXB % 2 == 0) {
-#pragma unroll
-                    for (int hw = 0; hw < 2 * NW; ++hw)
-                        if ((uint32_t)(2 * hw) < nValid * PIXB) reinterpret_cast<uint16_t *>(d)[hw] = (uint16_t)(words[hw >> 1] >> ((hw & 1) * 16));
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 4 * NW; ++b)
-                        if ((uint32_t)b < nValid * PIXB) d[b] = (uint8_t)(words[b >> 2] >> ((b & 3) * 8));
-                }
+                for (int q = 0; q < NW / 2; ++q) reinterpret_cast<uint2 *>(d)[q] = make_uint2(words[2 * q], words[2 * q + 1]);
             }
-            continue;
-        }
-        uint8_t * srow = stage + r * (kTile * PIXB);
-        if ((8 * PIXB) % 16 == 0) {
-            constexpr int NU = 8 * PIXB / 16;
+        } else if (nValid) { /* ragged last lane of a row: 16-bit (or byte) granular */
+            if (PIXB % 2 == 0) {
 #pragma unroll
-            for (int q = 0; q < NU; ++q) {
-                const uint32_t u = swz_unit<PIXB>(lane * NU + q);
-                *reinterpret_cast<uint4 *>(srow + u * 16) = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
-            }
-        } else { /* 24 bytes per lane (3 x u8): three 8-byte chunks, stride 24 B is conflict-free as is */
+                for (int hw = 0; hw < 2 * NW; ++hw)
+                    if ((uint32_t)(2 * hw) < nValid * PIXB) reinterpret_cast<uint16_t *>(d)[hw] = (uint16_t)(words[hw >> 1] >> ((hw & 1) * 16));
+            } else {
 #pragma unroll
-            for (int q = 0; q < NW / 2; ++q) *reinterpret_cast<uint2 *>(srow + lane * (8 * PIXB) + q * 8) = make_uint2(words[2 * q], words[2 * q + 1]);
-        }
-    }
-    if (VARIANT == 1 || VARIANT == 3) return;
-    __syncwarp();
-
-    /* ------------------------------ copy-out ------------------------------ */
-    if (fullTile) { /* whole 256-pixel tile: compile-time trip counts, no tail */
-        constexpr uint32_t NVEC = kTile * PIXB / 16;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            if (!rowOn[r]) continue;
-            const uint8_t * srow = stage + r * (kTile * PIXB);
-            uint4 * dst = reinterpret_cast<uint4 *>(J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)x0 * PIXB);
-#pragma unroll
-            for (uint32_t i = 0; i < (NVEC + 31) / 32; ++i) {
-                const uint32_t k = lane + 32 * i;
-                if (NVEC % 32 == 0 || k < NVEC) dst[k] = *reinterpret_cast<const uint4 *>(srow + swz_unit<PIXB>(k) * 16);
+                for (int b = 0; b < 4 * NW; ++b)
+                    if ((uint32_t)b < nValid * PIXB) d[b] = (uint8_t)(words[b >> 2] >> ((b & 3) * 8));
             }
         }
-        return;
-    }
-    const uint32_t npx = min((uint32_t)kTile, J.width - x0);
-    const uint32_t nbytes = npx * PIXB;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        if (!rowOn[r]) continue;
-        const uint8_t * srow = stage + r * (kTile * PIXB);
-        uint8_t * dst = J.rgb + (int64_t)jrow[r] * J.rgbRB + (int64_t)x0 * PIXB; /* 16-byte aligned (launcher) */
-        const uint32_t nv = nbytes >> 4;
-        for (uint32_t k = lane; k < nv; k += 32) {
-            reinterpret_cast<uint4 *>(dst)[k] = *reinterpret_cast<const uint4 *>(srow + swz_unit<PIXB>(k) * 16);
-        }
-        for (uint32_t b = (nv << 4) + lane; b < nbytes; b += 32) dst[b] = srow[swz_unit<PIXB>(b >> 4) * 16 + (b & 15)];
     }
 }
 
-template <class C, int VARIANT = 3>
-__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J)
+/* ---- the kernel ------------------------------------------------------------------------------------- */
+
+/* VARIANT 3: one tile per warp (grid = tiles).  VARIANT 4 (production): persistent warps stride over the tiles and
+ * load tile i+1 into a second register set before converting tile i, so a warp always has 50-150 B of loads in flight
+ * while it computes (at 25-50 % occupancy the scheduler alone cannot hide HBM latency: ncu showed 33 % long_scoreboard
+ * + 20 % store-drain stalls on the 8K case).  Tile order = row-major, so concurrently running warps touch adjacent
+ * 256-pixel spans.  (Shared-memory staged stores were measured slower: profiles/r01_variants.md.) */
+template <class C, int VARIANT = 4>
+__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J, const uint32_t tilesX, const uint32_t totalTiles)
 {
-    /* warp-uniform choice between the unchecked full-tile body and the range-checked one (last tile of a row) */
-    if ((VARIANT >= 2) && (blockIdx.x * kTile + kTile <= J.width)) y2r_fast_body<C, VARIANT, true>(J);
-    else y2r_fast_body<C, VARIANT, false>(J);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * kWarps;
+    uint32_t tile = blockIdx.x * kWarps + warp;
+    if (tile >= totalTiles) return;
+    if (VARIANT == 3) { /* one tile per warp */
+        const uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kTile;
+        const TileRows<C> R = tile_rows<C>(J, unit);
+        if (!R.any) return;
+        TileIn<C> in;
+        if (x0 + kTile <= J.width) {
+            load_tile<C, true>(J, R, x0, lane, in);
+            convert_store_tile<C, true>(J, R, x0, lane, in);
+        } else {
+            load_tile<C, false>(J, R, x0, lane, in);
+            convert_store_tile<C, false>(J, R, x0, lane, in);
+        }
+        return;
+    }
+    /* persistent, software-pipelined: cur = tile being converted, nxt = tile whose loads are in flight */
+    TileIn<C> cur, nxt;
+    uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kTile;
+    TileRows<C> R = tile_rows<C>(J, unit);
+    bool full = (x0 + kTile <= J.width);
+    if (R.any) {
+        if (full) load_tile<C, true>(J, R, x0, lane, cur);
+        else load_tile<C, false>(J, R, x0, lane, cur);
+    }
+    while (true) {
+        const uint32_t ntile = tile + stride;
+        const bool more = ntile < totalTiles; /* warp-uniform */
+        uint32_t nunit = 0, nx0 = 0;
+        TileRows<C> NR = R;
+        bool nfull = false;
+        if (more) {
+            nunit = ntile / tilesX;
+            nx0 = (ntile - nunit * tilesX) * kTile;
+            NR = tile_rows<C>(J, nunit);
+            nfull = (nx0 + kTile <= J.width);
+            if (NR.any) {
+                if (nfull) load_tile<C, true>(J, NR, nx0, lane, nxt);
+                else load_tile<C, false>(J, NR, nx0, lane, nxt);
+            }
+        }
+        if (R.any) {
+            if (full) convert_store_tile<C, true>(J, R, x0, lane, cur);
+            else convert_store_tile<C, false>(J, R, x0, lane, cur);
+        }
+        if (!more) break;
+        cur = nxt;
+        tile = ntile;
+        unit = nunit;
+        x0 = nx0;
+        R = NR;
+        full = nfull;
+    }
 }
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 3>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 4>
 static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;
     const uint32_t rows = J.rowEnd - J.rowBegin;
     uint32_t units = rows;
     if (CHROMA == CH_BIL420) units = (J.rowEnd >> 1) - (J.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
-    const dim3 grid((J.width + kTile - 1) / kTile, (units + kWarps - 1) / kWarps);
-    y2r_fast_kernel<C, VARIANT><<<grid, kWarps * 32, 0, st>>>(J);
+    const uint32_t tilesX = (J.width + kTile - 1) / kTile;
+    const uint32_t total = tilesX * units;
+    uint32_t blocks = (total + kWarps - 1) / kWarps;
+    if (VARIANT == 4) {
+        static int resident = 0; /* blocks that fit on the whole device at once (per instantiation) */
+        if (!resident) {
+            int dev = 0, sms = 0, perSm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C, VARIANT>, kWarps * 32, 0);
+            resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+        }
+        if (blocks > (uint32_t)resident) blocks = (uint32_t)resident;
+    }
+    y2r_fast_kernel<C, VARIANT><<<blocks, kWarps * 32, 0, st>>>(J, tilesX, total);
     return 1;
 }
 

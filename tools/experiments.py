@@ -53,6 +53,8 @@ sptr = ctypes.c_void_p(stream.cuda_stream)
 CASES = {
     "NS": (7680, 4320, 10, 1, 1, 1, False, False, 10, 1, 0, False, 14),
     "C2fwd": (3840, 2160, 10, 1, 1, 1, True, False, 10, 1, 0, True, 16),
+    "C3": (7680, 4320, 12, 3, 0, 9, True, True, 12, 1, 4, False, 13),
+    "C5bil": (3840, 2160, 10, 3, 0, 1, False, False, 16, 0, 0, False, 9),
 }
 variants = {}
 for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in CASES.items():
@@ -65,7 +67,7 @@ for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in CASES.item
             b._t[:b.nbytes].view(torch.int16).copy_(v)
         frames.append((img, RGBImage(w, h, rd, rf, upsampling=ups, alpha_premultiplied=rp, device=dev)))
     ref_hash = None
-    for pol, label in ((0, "production"), (8, "staged"), (16, "direct_checked"), (24, "staged_uniform")):
+    for pol, label in ((0, "production_persistent_prefetch"), (8, "one_tile_per_warp")):
         lib.avifB200SetKernelPolicy(pol)
         for img, rgb in frames:
             assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
