@@ -267,20 +267,21 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    from libavif_b200.images import pointer_array
+    p_src, p_rgb, p_back = pointer_array([f[0] for f in frames]), pointer_array([f[1] for f in frames]), pointer_array([f[2] for f in frames])
 
     def step(record=None):
+        # one step = the library's batch entry points over the B frames: forward conversion of all, then backward of all
         e0 = ev() if record is not None else None
         if e0:
             e0.record(stream)
-        for src, rgb, _ in frames:
-            r = lib.avifB200ImageYUVToRGBAsync(src.ptr(), rgb.ptr(), sptr)
-            assert r == 0, r
+        r = lib.avifB200ImageYUVToRGBBatchAsync(p_src, p_rgb, B, sptr)
+        assert r == 0, r
         e1 = ev() if record is not None else None
         if e1:
             e1.record(stream)
-        for _, rgb, back in frames:
-            r = lib.avifB200ImageRGBToYUVAsync(back.ptr(), rgb.ptr(), sptr)
-            assert r == 0, r
+        r = lib.avifB200ImageRGBToYUVBatchAsync(p_back, p_rgb, B, sptr)
+        assert r == 0, r
         if record is not None:
             e2 = ev()
             e2.record(stream)
@@ -316,8 +317,8 @@ def run_b200(args):
         dist.barrier()
     launches = int(lib.avifB200KernelLaunchCount())
     elapsed_ms = t_begin.elapsed_time(t_end)
-    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / (len(rec) * B)
-    back_ms = sum(b.elapsed_time(c) for _, b, c in rec) / (len(rec) * B)
+    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)    # one launch converts the whole batch
+    back_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,7 +373,7 @@ def run_b200(args):
         peak_gbs, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     except Exception:
         peak_gbs = 6650.0
-    alg = ALG_BYTES_PER_PX * PX
+    alg = ALG_BYTES_PER_PX * PX * B  # per launch: the fused batch of B frames
     kern = {
         name_fwd: {"direction": "YUVToRGB", "ms_per_launch": fwd_ms, "achieved_gbs": alg / (fwd_ms * 1e-3) / 1e9},
         name_back: {"direction": "RGBToYUV", "ms_per_launch": back_ms, "achieved_gbs": alg / (back_ms * 1e-3) / 1e9},
@@ -386,7 +387,9 @@ def run_b200(args):
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
                 "frac": kern[dom]["achieved_gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "kernels": kern}
+                "algorithmic_bytes_per_launch": alg, "frames_per_launch": B, "kernels": kern}
+    if traffic is not None:
+        roofline["traffic"] = traffic * B  # profiles/traffic.json holds the per-frame DRAM bytes
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -449,20 +452,30 @@ def run_extras(lib, dev, sptr, stream, peak_gbs):
                     b._t[:b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
             rgb = RGBImage(w, h, rd, rf, upsampling=ups, alpha_premultiplied=rp, device=dev)
             fr.append((img, rgb))
-        for img, rgb in fr:
-            assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
-        torch.cuda.synchronize()
-        reps = 5
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            for img, rgb in fr:
-                lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (reps * nf)
+        from libavif_b200.images import pointer_array
+        pi, pr = pointer_array([f[0] for f in fr]), pointer_array([f[1] for f in fr])
+        res = {}
+        for mode in ("per_image_launch", "batch_launch"):
+            def go():
+                if mode == "batch_launch":
+                    assert lib.avifB200ImageYUVToRGBBatchAsync(pi, pr, nf, sptr) == 0
+                else:
+                    for img, rgb in fr:
+                        assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
+            go()
+            torch.cuda.synchronize()
+            reps = 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                go()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            res[mode] = e0.elapsed_time(e1) / (reps * nf)
+        ms = res["batch_launch"]
         gbs = bpp * w * h / (ms * 1e-3) / 1e9
-        out[name] = {"kernel": lib.avifB200LastKernelName().decode(), "us_per_frame": ms * 1e3, "Mpixels_per_s": w * h / (ms * 1e-3) / 1e6,
+        out[name] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": nf, "us_per_frame_per_image_launches": res["per_image_launch"] * 1e3,
+                     "us_per_frame": ms * 1e3, "Mpixels_per_s": w * h / (ms * 1e-3) / 1e6,
                      "alg_bytes_per_px": bpp, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
         del fr
         torch.cuda.empty_cache()

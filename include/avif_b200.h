@@ -283,6 +283,13 @@ AVIF_B200_API avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avi
 AVIF_B200_API avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
 AVIF_B200_API avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream);
 
+/* Batches of device-resident frames (config C5 of BASELINE.json: batched decode-reformat).  Frames that share format,
+ * depth, matrix, range and alpha handling are converted by ONE kernel launch per <= 24 frames: a launch costs ~4-5 us of
+ * GPU ramp-up / drain, i.e. 15 % of a 4K frame and more than half of a 1080p one.  Same validation and result codes as
+ * the per-image calls (the first failing image's code is returned; nothing is launched in that case). */
+AVIF_B200_API avifResult avifB200ImageYUVToRGBBatchAsync(const avifImage * const * images, avifRGBImage * const * rgbs, uint32_t count, void * stream);
+AVIF_B200_API avifResult avifB200ImageRGBToYUVBatchAsync(avifImage * const * images, const avifRGBImage * const * rgbs, uint32_t count, void * stream);
+
 /* The synchronous entry points under names that do not clash with the reference's, for the internal-hook integration
  * (seam 2) where libavif keeps its own avifImageYUVToRGB and calls these from its accelerator hooks. */
 AVIF_B200_API avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb);

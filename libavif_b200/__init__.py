@@ -36,4 +36,4 @@ def device_available():
     return bool(lib().avifB200DeviceAvailable())
 
 
-from .images import YUVImage, RGBImage  # noqa: E402,F401
+from .images import YUVImage, RGBImage, pointer_array  # noqa: E402,F401

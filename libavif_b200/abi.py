@@ -134,6 +134,8 @@ PROTOTYPES = {
     "avifB200ImageRGBToYUVAsync": (C.c_int, [_PI, _PR, C.c_void_p]),
     "avifB200RGBImagePremultiplyAlphaAsync": (C.c_int, [_PR, C.c_void_p]),
     "avifB200RGBImageUnpremultiplyAlphaAsync": (C.c_int, [_PR, C.c_void_p]),
+    "avifB200ImageYUVToRGBBatchAsync": (C.c_int, [C.POINTER(_PI), C.POINTER(_PR), C.c_uint32, C.c_void_p]),
+    "avifB200ImageRGBToYUVBatchAsync": (C.c_int, [C.POINTER(_PI), C.POINTER(_PR), C.c_uint32, C.c_void_p]),
     "avifB200ImageYUVToRGBHost": (C.c_int, [_PI, _PR]),
     "avifB200ImageRGBToYUVHost": (C.c_int, [_PI, _PR]),
     "avifB200RGBImagePremultiplyAlphaHost": (C.c_int, [_PR]),

@@ -923,29 +923,29 @@ using namespace ab;
 
 extern "C" {
 
-int abY2RFast_8_8(const AbY2RJob * job, void * stream);
-int abY2RFast_8_16(const AbY2RJob * job, void * stream);
-int abY2RFast_16_8(const AbY2RJob * job, void * stream);
-int abY2RFast_16_16(const AbY2RJob * job, void * stream);
+int abY2RFast_8_8(const AbY2RJob * jobs, uint32_t count, void * stream);
+int abY2RFast_8_16(const AbY2RJob * jobs, uint32_t count, void * stream);
+int abY2RFast_16_8(const AbY2RJob * jobs, uint32_t count, void * stream);
+int abY2RFast_16_16(const AbY2RJob * jobs, uint32_t count, void * stream);
 
-int abY2RExperiment(const AbY2RJob * job, void * stream, int variant);
+static int y2r_fast_try(const AbY2RJob * jobs, uint32_t count, void * stream)
+{
+    if (jobs[0].yuvBytes == 2) return (jobs[0].rgbBytes == 2) ? abY2RFast_16_16(jobs, count, stream) : abY2RFast_16_8(jobs, count, stream);
+    return (jobs[0].rgbBytes == 2) ? abY2RFast_8_16(jobs, count, stream) : abY2RFast_8_8(jobs, count, stream);
+}
+
+static const char * y2r_fast_name(const AbY2RJob * job)
+{
+    return (job->chroma == AB_CHROMA_BILINEAR) ? "y2r_fast_bilinear" : (job->chroma == AB_CHROMA_NEAREST) ? "y2r_fast_nearest" : "y2r_fast_444";
+}
 
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (forceGeneric >= 8) { /* experiment variants (bits 3-4), fall back to production when not applicable */
-        if (abY2RExperiment(job, stream, forceGeneric >> 3)) {
-            if (kernelName) *kernelName = "y2r_fast_one_tile_per_warp";
-            return finish_launch();
-        }
-        forceGeneric = 0;
-    }
+    forceGeneric &= 3;
     if (forceGeneric == 0) { /* production: compile-time specialised kernels for the hot configurations (y2r_fast.cuh) */
-        int took;
-        if (job->yuvBytes == 2) took = (job->rgbBytes == 2) ? abY2RFast_16_16(job, stream) : abY2RFast_16_8(job, stream);
-        else took = (job->rgbBytes == 2) ? abY2RFast_8_16(job, stream) : abY2RFast_8_8(job, stream);
-        if (took) {
-            if (kernelName) *kernelName = (job->chroma == AB_CHROMA_BILINEAR) ? "y2r_fast_bilinear" : (job->chroma == AB_CHROMA_NEAREST) ? "y2r_fast_nearest" : "y2r_fast_444";
+        if (y2r_fast_try(job, 1, stream)) {
+            if (kernelName) *kernelName = y2r_fast_name(job);
             return finish_launch();
         }
     }
@@ -958,20 +958,67 @@ int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const cha
                               : launch_y2r_typed<uint8_t, uint8_t>(*job, st, forceGeneric, kernelName);
 }
 
-int abR2YFast_8_8(const AbR2YJob * job, void * stream);
-int abR2YFast_8_16(const AbR2YJob * job, void * stream);
-int abR2YFast_16_8(const AbR2YJob * job, void * stream);
-int abR2YFast_16_16(const AbR2YJob * job, void * stream);
+int abLaunchY2RBatch(const AbY2RJob * jobs, uint32_t count, void * stream, int forceGeneric, const char ** kernelName)
+{
+    uint32_t k = 0;
+    while (k < count) {
+        /* longest run of frames with the same sample types, <= AB_MAX_BATCH: one specialised launch if they are compatible */
+        uint32_t n = 1;
+        while (k + n < count && n < AB_MAX_BATCH && jobs[k + n].yuvBytes == jobs[k].yuvBytes && jobs[k + n].rgbBytes == jobs[k].rgbBytes) ++n;
+        if ((forceGeneric & 3) == 0 && n > 1 && y2r_fast_try(jobs + k, n, stream)) {
+            if (kernelName) *kernelName = y2r_fast_name(jobs + k);
+            const int err = finish_launch();
+            if (err) return err;
+        } else {
+            for (uint32_t i = 0; i < n; ++i) {
+                const int err = abLaunchY2R(jobs + k + i, stream, forceGeneric, kernelName);
+                if (err) return err;
+            }
+        }
+        k += n;
+    }
+    return 0;
+}
+
+int abR2YFast_8_8(const AbR2YJob * jobs, uint32_t count, void * stream);
+int abR2YFast_8_16(const AbR2YJob * jobs, uint32_t count, void * stream);
+int abR2YFast_16_8(const AbR2YJob * jobs, uint32_t count, void * stream);
+int abR2YFast_16_16(const AbR2YJob * jobs, uint32_t count, void * stream);
+
+static int r2y_fast_try(const AbR2YJob * jobs, uint32_t count, void * stream)
+{
+    if (jobs[0].rgbBytes == 2) return (jobs[0].yuvBytes == 2) ? abR2YFast_16_16(jobs, count, stream) : abR2YFast_16_8(jobs, count, stream);
+    return (jobs[0].yuvBytes == 2) ? abR2YFast_8_16(jobs, count, stream) : abR2YFast_8_8(jobs, count, stream);
+}
+
+int abLaunchR2YBatch(const AbR2YJob * jobs, uint32_t count, void * stream, int forceGeneric, const char ** kernelName)
+{
+    uint32_t k = 0;
+    while (k < count) {
+        uint32_t n = 1;
+        while (k + n < count && n < AB_MAX_BATCH && jobs[k + n].yuvBytes == jobs[k].yuvBytes && jobs[k + n].rgbBytes == jobs[k].rgbBytes) ++n;
+        if ((forceGeneric & 3) == 0 && n > 1 && r2y_fast_try(jobs + k, n, stream)) {
+            if (kernelName) *kernelName = "r2y_fast";
+            const int err = finish_launch();
+            if (err) return err;
+        } else {
+            for (uint32_t i = 0; i < n; ++i) {
+                const int err = abLaunchR2Y(jobs + k + i, stream, forceGeneric, kernelName);
+                if (err) return err;
+            }
+        }
+        k += n;
+    }
+    return 0;
+}
 
 int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->rowEnd <= job->rowBegin) return 0;
+    forceGeneric &= 3;
     if (forceGeneric == 0) { /* production: compile-time specialised kernels (r2y_fast.cuh) */
-        int took;
-        if (job->rgbBytes == 2) took = (job->yuvBytes == 2) ? abR2YFast_16_16(job, stream) : abR2YFast_16_8(job, stream);
-        else took = (job->yuvBytes == 2) ? abR2YFast_8_16(job, stream) : abR2YFast_8_8(job, stream);
-        if (took) {
+        if (r2y_fast_try(job, 1, stream)) {
             if (kernelName) *kernelName = "r2y_fast";
             return finish_launch();
         }

@@ -102,6 +102,52 @@ typedef struct AbR2YJob {
     uint8_t dstPairAligned; /* every destination plane base and stride is a multiple of 2*yuvBytes */
 } AbR2YJob;
 
+/* ---- batches: one launch converts several frames that share every conversion constant ------------------ */
+/* A kernel launch costs ~4-5 us of ramp-up / drain during which the SMs idle (ncu: sm__cycles_elapsed - active), i.e.
+ * 15 % of a 4K frame and half of a 1080p one.  The specialised kernels therefore take a small table of frames: work
+ * is cut into GROUPS of 8 consecutive 256-pixel tiles of one frame (one tile per warp of a block), so the frame --
+ * pointers, strides, extents -- is block-uniform and lives in uniform registers. */
+#define AB_MAX_BATCH 24
+
+typedef struct AbY2RFrame {
+    const uint8_t * y;
+    const uint8_t * u;
+    const uint8_t * v;
+    const uint8_t * a;
+    uint8_t * rgb;
+    int64_t yRB, uRB, vRB, aRB, rgbRB;
+    uint32_t width, height;
+    uint32_t rowBegin, rowEnd;
+    uint32_t tilesX;     /* 256-pixel tiles per row */
+    uint32_t tiles;      /* tilesX * row units */
+    uint32_t groupStart; /* first group of this frame in the launch */
+    uint32_t pad;
+} AbY2RFrame;
+
+typedef struct AbY2RBatch {
+    AbY2RJob common; /* constants (per-frame members unused) */
+    uint32_t nFrames, totalGroups;
+    AbY2RFrame frame[AB_MAX_BATCH];
+} AbY2RBatch;
+
+typedef struct AbR2YFrame {
+    const uint8_t * rgb;
+    uint8_t * y;
+    uint8_t * u;
+    uint8_t * v;
+    uint8_t * a;
+    int64_t rgbRB, yRB, uRB, vRB, aRB;
+    uint32_t width, height;
+    uint32_t rowBegin, rowEnd;
+    uint32_t tilesX, tiles, groupStart, pad;
+} AbR2YFrame;
+
+typedef struct AbR2YBatch {
+    AbR2YJob common;
+    uint32_t nFrames, totalGroups;
+    AbR2YFrame frame[AB_MAX_BATCH];
+} AbR2YBatch;
+
 /* avifAlphaParams with device pointers (alpha.c:9-149) */
 typedef struct AbAlphaJob {
     const uint8_t * src; /* NULL: fill opaque */
@@ -129,6 +175,9 @@ typedef struct AbRgbPassJob {
  * `forceGeneric` selects the byte-addressed reference kernel instead of the tiled/vectorised one. */
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName);
 int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const char ** kernelName);
+/* `count` jobs in as few launches as possible (one per <= AB_MAX_BATCH compatible frames when the specialised kernels apply) */
+int abLaunchY2RBatch(const AbY2RJob * jobs, uint32_t count, void * stream, int forceGeneric, const char ** kernelName);
+int abLaunchR2YBatch(const AbR2YJob * jobs, uint32_t count, void * stream, int forceGeneric, const char ** kernelName);
 int abLaunchAlpha(const AbAlphaJob * job, void * stream);
 int abLaunchPremultiply(const AbRgbPassJob * job, void * stream);
 int abLaunchToF16(const AbRgbPassJob * job, void * stream);

@@ -10,7 +10,9 @@
  */
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "pixel_math.cuh"
 #include "plan.h"
@@ -108,7 +110,7 @@ struct RTileIn {
 
 /* tile = 256 pixels x ROWS rows starting at luma row j0 */
 template <class C, bool FULL>
-__device__ __forceinline__ void load_rtile(const AbR2YJob & J, uint32_t x0, uint32_t j0, uint32_t lane, RTileIn<C> & in)
+__device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, RTileIn<C> & in)
 {
     using RT = typename C::RT;
     constexpr int ROWS = RTileIn<C>::ROWS;
@@ -116,15 +118,15 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, uint32_t x0, uint
     constexpr int NW = RTileIn<C>::NW;
     constexpr bool fullTile = FULL;
     const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
-    const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
+    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
     /* ---- loads: 8 pixels x ROWS rows, issued before any arithmetic ---- */
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
         for (int k = 0; k < NW; ++k) in.w[r][k] = 0;
         if ((uint32_t)r < nRows) {
-            const uint8_t * p = J.rgb + (int64_t)(j0 + r) * J.rgbRB + (int64_t)px0 * PIXB;
+            const uint8_t * p = F.rgb + (int64_t)(j0 + r) * F.rgbRB + (int64_t)px0 * PIXB;
             if (fullTile || nValid >= 8) {
                 if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
@@ -155,16 +157,16 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, uint32_t x0, uint
 }
 
 template <class C, bool FULL>
-__device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
+__device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
 {
     using RT = typename C::RT;
     using YT = typename C::YT;
     constexpr int ROWS = RTileIn<C>::ROWS;
     constexpr bool fullTile = FULL;
     const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
     if (nValid == 0) return; /* no cross-lane traffic in this kernel */
-    const uint32_t nRows = min((uint32_t)ROWS, J.height - j0);
+    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
 
     /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
     const uint32_t K = J.magicK;
@@ -220,12 +222,12 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, uint32_t
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
-        store_samples8<YT>(J.y + (int64_t)j * J.yRB, px0, ns, yq);
+        store_samples8<YT>(F.y + (int64_t)j * F.yRB, px0, ns, yq);
         if (C::SUB == SUB_444) {
-            store_samples8<YT>(J.u + (int64_t)j * J.uRB, px0, ns, uq);
-            store_samples8<YT>(J.v + (int64_t)j * J.vRB, px0, ns, vq);
+            store_samples8<YT>(F.u + (int64_t)j * F.uRB, px0, ns, uq);
+            store_samples8<YT>(F.v + (int64_t)j * F.vRB, px0, ns, vq);
         }
-        if (writeAlpha) store_samples8<YT>(J.a + (int64_t)j * J.aRB, px0, ns, aq);
+        if (writeAlpha) store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
     }
 
     /* ---- subsampled chroma: ordered box sums over the samples that exist (ref: :413-467) ---- */
@@ -255,8 +257,8 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, uint32_t
                 vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
             }
             const uint32_t uj = j0 >> 1;
-            store_samples4<YT>(J.u + (int64_t)uj * J.uRB, px0 >> 1, nc, uq);
-            store_samples4<YT>(J.v + (int64_t)uj * J.vRB, px0 >> 1, nc, vq);
+            store_samples4<YT>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq);
+            store_samples4<YT>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq);
         } else {
             float uq[4], vq[4];
 #pragma unroll
@@ -271,45 +273,71 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, uint32_t
                 uq[k] = quant_yuv_magic(__fmul_rn(su, inv), J.rangeUV, J.biasUV, hiLimit);
                 vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
             }
-            store_samples4<YT>(J.u + (int64_t)j0 * J.uRB, px0 >> 1, nc, uq);
-            store_samples4<YT>(J.v + (int64_t)j0 * J.vRB, px0 >> 1, nc, vq);
+            store_samples4<YT>(F.u + (int64_t)j0 * F.uRB, px0 >> 1, nc, uq);
+            store_samples4<YT>(F.v + (int64_t)j0 * F.vRB, px0 >> 1, nc, vq);
         }
     }
 }
 
-/* Persistent, software-pipelined like y2r_fast_kernel: a warp strides over the 256-pixel tiles and loads tile i+1 into a
- * second register set before converting tile i.  PERSIST = false: one tile per warp (comparison variant). */
-template <class C, bool PERSIST = true>
-__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YJob J, const uint32_t tilesX, const uint32_t totalTiles)
+/* Persistent, software-pipelined and batched like y2r_fast_kernel: a block strides over groups of 8 consecutive tiles of one
+ * frame (one tile per warp); each warp loads its tile of the next group into a second register set before converting the
+ * current one. */
+__device__ __forceinline__ uint32_t rframe_of_group(const AbR2YBatch & B, uint32_t g)
+{
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && g >= B.frame[f + 1].groupStart) ++f; /* block-uniform */
+    return f;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
 {
     constexpr int ROWS = RTileIn<C>::ROWS;
+    const AbR2YJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * kRWarps;
-    uint32_t tile = blockIdx.x * kRWarps + warp;
-    if (tile >= totalTiles) return;
+    uint32_t g = blockIdx.x;
+    if (g >= B.totalGroups) return;
     RTileIn<C> cur, nxt;
-    uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kRTile, j0 = J.rowBegin + unit * ROWS;
-    bool full = (x0 + kRTile <= J.width);
-    if (full) load_rtile<C, true>(J, x0, j0, lane, cur);
-    else load_rtile<C, false>(J, x0, j0, lane, cur);
+    uint32_t f = rframe_of_group(B, g);
+    uint32_t tile = (g - B.frame[f].groupStart) * kRWarps + warp;
+    bool live = tile < B.frame[f].tiles;
+    uint32_t x0 = 0, j0 = 0;
+    bool full = false;
+    if (live) {
+        const uint32_t unit = tile / B.frame[f].tilesX;
+        x0 = (tile - unit * B.frame[f].tilesX) * kRTile;
+        j0 = B.frame[f].rowBegin + unit * ROWS;
+        full = (x0 + kRTile <= B.frame[f].width);
+        if (full) load_rtile<C, true>(J, B.frame[f], x0, j0, lane, cur);
+        else load_rtile<C, false>(J, B.frame[f], x0, j0, lane, cur);
+    }
     while (true) {
-        const uint32_t ntile = tile + stride;
-        const bool more = PERSIST && (ntile < totalTiles); /* warp-uniform */
-        uint32_t nx0 = 0, nj0 = 0;
-        bool nfull = false;
+        const uint32_t ng = g + gridDim.x;
+        const bool more = ng < B.totalGroups; /* block-uniform */
+        uint32_t nf = f, nx0 = 0, nj0 = 0;
+        bool nlive = false, nfull = false;
         if (more) {
-            const uint32_t nunit = ntile / tilesX;
-            nx0 = (ntile - nunit * tilesX) * kRTile;
-            nj0 = J.rowBegin + nunit * ROWS;
-            nfull = (nx0 + kRTile <= J.width);
-            if (nfull) load_rtile<C, true>(J, nx0, nj0, lane, nxt);
-            else load_rtile<C, false>(J, nx0, nj0, lane, nxt);
+            nf = rframe_of_group(B, ng);
+            const uint32_t ntile = (ng - B.frame[nf].groupStart) * kRWarps + warp;
+            nlive = ntile < B.frame[nf].tiles;
+            if (nlive) {
+                const uint32_t nunit = ntile / B.frame[nf].tilesX;
+                nx0 = (ntile - nunit * B.frame[nf].tilesX) * kRTile;
+                nj0 = B.frame[nf].rowBegin + nunit * ROWS;
+                nfull = (nx0 + kRTile <= B.frame[nf].width);
+                if (nfull) load_rtile<C, true>(J, B.frame[nf], nx0, nj0, lane, nxt);
+                else load_rtile<C, false>(J, B.frame[nf], nx0, nj0, lane, nxt);
+            }
         }
-        if (full) convert_store_rtile<C, true>(J, x0, j0, lane, cur);
-        else convert_store_rtile<C, false>(J, x0, j0, lane, cur);
+        if (live) {
+            if (full) convert_store_rtile<C, true>(J, B.frame[f], x0, j0, lane, cur);
+            else convert_store_rtile<C, false>(J, B.frame[f], x0, j0, lane, cur);
+        }
         if (!more) break;
         cur = nxt;
-        tile = ntile;
+        g = ng;
+        f = nf;
+        live = nlive;
         x0 = nx0;
         j0 = nj0;
         full = nfull;
@@ -317,70 +345,107 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
 }
 
 template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>
-static int rlaunch_cfg(const AbR2YJob & J, cudaStream_t st)
+static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
 {
     using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM>;
     constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
-    const uint32_t units = (J.rowEnd - J.rowBegin + ROWS - 1) / ROWS;
-    const uint32_t tilesX = (J.width + kRTile - 1) / kRTile;
-    const uint32_t total = tilesX * units;
+    uint32_t groups = 0;
+    for (uint32_t f = 0; f < B.nFrames; ++f) {
+        AbR2YFrame & F = B.frame[f];
+        const uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
+        F.tilesX = (F.width + kRTile - 1) / kRTile;
+        F.tiles = F.tilesX * units;
+        F.groupStart = groups;
+        groups += (F.tiles + kRWarps - 1) / kRWarps;
+    }
+    B.totalGroups = groups;
     static int resident = 0; /* blocks resident on the whole device (per instantiation) */
     if (!resident) {
         int dev = 0, sms = 0, perSm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C, true>, kRWarps * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
     }
-    uint32_t blocks = (total + kRWarps - 1) / kRWarps;
-    if (blocks > (uint32_t)resident) blocks = (uint32_t)resident;
-    r2y_fast_kernel<C, true><<<blocks, kRWarps * 32, 0, st>>>(J, tilesX, total);
+    uint32_t blocks = groups;
+    if (groups >= 4u * (uint32_t)resident) blocks = (uint32_t)resident;
+    r2y_fast_kernel<C><<<blocks, kRWarps * 32, 0, st>>>(B);
     return 1;
 }
 
 template <typename RT, typename YT, int SUB>
-static int rlaunch_sub(const AbR2YJob & J, cudaStream_t st)
+static int rlaunch_sub(AbR2YBatch & B, cudaStream_t st)
 {
-    if (J.nChan == 3) return (J.alphaMul == AB_MUL_NONE) ? rlaunch_cfg<RT, YT, SUB, 3, false, AB_MUL_NONE>(J, st) : 0;
+    const AbR2YJob & J = B.common;
+    if (J.nChan == 3) return (J.alphaMul == AB_MUL_NONE) ? rlaunch_cfg<RT, YT, SUB, 3, false, AB_MUL_NONE>(B, st) : 0;
     if (J.alphaFirst) {
         switch (J.alphaMul) {
-            case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_NONE>(J, st);
-            case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_MUL>(J, st);
-            default: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_UNMUL>(J, st);
+            case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_NONE>(B, st);
+            case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_MUL>(B, st);
+            default: return rlaunch_cfg<RT, YT, SUB, 4, true, AB_MUL_FLOAT_UNMUL>(B, st);
         }
     }
     switch (J.alphaMul) {
-        case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_NONE>(J, st);
-        case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_MUL>(J, st);
-        default: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_UNMUL>(J, st);
+        case AB_MUL_NONE: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_NONE>(B, st);
+        case AB_MUL_FLOAT_MUL: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_MUL>(B, st);
+        default: return rlaunch_cfg<RT, YT, SUB, 4, false, AB_MUL_FLOAT_UNMUL>(B, st);
     }
 }
 
-/* returns 1 if a specialised kernel was launched, 0 if the job must take the general kernel */
 template <typename RT, typename YT>
-static int launch_r2y_fast_typed(const AbR2YJob & J, cudaStream_t st)
+static bool rfast_eligible(const AbR2YJob & J)
 {
-    if (J.mode != AB_MODE_COEFF || J.isGray) return 0;
-    if (J.nChan != 3 && J.nChan != 4) return 0;
-    if (!J.rgbMaxDiv.exact) return 0;
-    if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return 0;
-    if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return 0;
-    if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return 0;
-    if (J.width == 0 || J.rowEnd <= J.rowBegin) return 0;
+    if (J.mode != AB_MODE_COEFF || J.isGray) return false;
+    if (J.nChan != 3 && J.nChan != 4) return false;
+    if (!J.rgbMaxDiv.exact) return false;
+    if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return false;
+    if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return false;
+    if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return false;
+    if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
     const uint32_t pixb = J.nChan * (uint32_t)sizeof(RT);
     const uintptr_t srcAlign = ((8 * pixb) % 16 == 0) ? 15 : 7;
-    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & srcAlign) return 0;
+    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & srcAlign) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1;
     uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
     if (J.alphaWrite != AB_ALPHA_KEEP) bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
-    if (bits & lumaAlign) return 0;
+    if (bits & lumaAlign) return false;
     if (J.hasChroma) {
         const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
-        if (cbits & (J.shiftX ? (4 * sizeof(YT) - 1) : lumaAlign)) return 0;
+        if (cbits & (J.shiftX ? (4 * sizeof(YT) - 1) : lumaAlign)) return false;
     }
-    if (!J.hasChroma) return rlaunch_sub<RT, YT, SUB_400>(J, st);
-    if (!J.shiftX) return rlaunch_sub<RT, YT, SUB_444>(J, st);
-    return J.shiftY ? rlaunch_sub<RT, YT, SUB_420>(J, st) : rlaunch_sub<RT, YT, SUB_422>(J, st);
+    return true;
+}
+
+static inline bool rsame_constants(const AbR2YJob & a, const AbR2YJob & b)
+{
+    const size_t from = offsetof(AbR2YJob, yuvMax), to = offsetof(AbR2YJob, srcPairAligned);
+    return memcmp(reinterpret_cast<const char *>(&a) + from, reinterpret_cast<const char *>(&b) + from, to - from) == 0;
+}
+
+/* jobs[0..n) (n <= AB_MAX_BATCH) in ONE specialised launch if all are eligible and share their constants; else 0 */
+template <typename RT, typename YT>
+static int launch_r2y_fast_typed(const AbR2YJob * jobs, uint32_t n, cudaStream_t st)
+{
+    if (n == 0 || n > AB_MAX_BATCH) return 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (!rfast_eligible<RT, YT>(jobs[k])) return 0;
+        if (k && !rsame_constants(jobs[0], jobs[k])) return 0;
+    }
+    AbR2YBatch B;
+    B.common = jobs[0];
+    B.nFrames = n;
+    for (uint32_t k = 0; k < n; ++k) {
+        AbR2YFrame & F = B.frame[k];
+        const AbR2YJob & S = jobs[k];
+        F.rgb = S.rgb; F.y = S.y; F.u = S.u; F.v = S.v; F.a = S.a;
+        F.rgbRB = S.rgbRB; F.yRB = S.yRB; F.uRB = S.uRB; F.vRB = S.vRB; F.aRB = S.aRB;
+        F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
+        F.tilesX = F.tiles = F.groupStart = F.pad = 0;
+    }
+    const AbR2YJob & J = B.common;
+    if (!J.hasChroma) return rlaunch_sub<RT, YT, SUB_400>(B, st);
+    if (!J.shiftX) return rlaunch_sub<RT, YT, SUB_444>(B, st);
+    return J.shiftY ? rlaunch_sub<RT, YT, SUB_420>(B, st) : rlaunch_sub<RT, YT, SUB_422>(B, st);
 }
 
 } // namespace abfast

@@ -637,7 +637,13 @@ void avifReformatAlpha(const avifAlphaParams * params) { alphaCommon(params, 0);
 /* ------------------------------------------------------------------------------------------ */
 /* YUV -> RGB                                                                                  */
 
-static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+/* everything the launch needs besides device pointers: validation, constants, variant classification */
+typedef struct AbY2RPlan {
+    AbState s;
+    int hasChroma, rgbHasAlpha, reformatAlpha;
+} AbY2RPlan;
+
+static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb, AbY2RJob * jobOut, AbY2RPlan * plan)
 {
     /* src/reformat.c:1649-1677 */
     if (!image->yuvPlanes[AVIF_CHAN_Y] || rgb->maxThreads < 0) return AVIF_RESULT_REFORMAT_FAILED;
@@ -749,7 +755,24 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
     job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);
 
-    avifResult res = ctxInit();
+    *jobOut = job;
+    plan->s = s;
+    plan->hasChroma = hasChroma;
+    plan->rgbHasAlpha = rgbHasAlpha;
+    plan->reformatAlpha = reformatAlpha;
+    return AVIF_RESULT_OK;
+}
+
+static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+{
+    AbY2RJob job;
+    AbY2RPlan plan;
+    avifResult res = y2rBuildJob(image, rgb, &job, &plan);
+    if (res != AVIF_RESULT_OK) return res;
+    const AbState s = plan.s;
+    const int hasChroma = plan.hasChroma, rgbHasAlpha = plan.rgbHasAlpha, reformatAlpha = plan.reformatAlpha;
+
+    res = ctxInit();
     if (res != AVIF_RESULT_OK) return res;
     cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
 
@@ -946,7 +969,13 @@ static avifResult allocatePlanes(avifImage * image, int withAlpha)
     return AVIF_RESULT_OK;
 }
 
-static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+typedef struct AbR2YPlan {
+    AbState s;
+    int monochrome, isGray, hasAlpha, writeAlphaPlane;
+} AbR2YPlan;
+
+/* validation, plane allocation, constants (src/reformat.c:221-273); no CUDA */
+static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int async, AbR2YJob * jobOut, AbR2YPlan * plan)
 {
     /* src/reformat.c:221-273 */
     if (!rgb->pixels || rgb->format == AVIF_RGB_FORMAT_RGB_565) return AVIF_RESULT_REFORMAT_FAILED;
@@ -1023,6 +1052,24 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     const int writeAlphaPlane = image->alphaPlane && image->alphaRowBytes; /* :545 */
     job.alphaWrite = (uint8_t)(!writeAlphaPlane ? AB_ALPHA_KEEP : (hasAlpha ? AB_ALPHA_COPY : AB_ALPHA_FILL));
     job.alphaRescale = (uint8_t)(image->depth != rgb->depth);
+
+    *jobOut = job;
+    plan->s = s;
+    plan->monochrome = monochrome;
+    plan->isGray = isGray;
+    plan->hasAlpha = hasAlpha;
+    plan->writeAlphaPlane = writeAlphaPlane;
+    return AVIF_RESULT_OK;
+}
+
+static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+{
+    AbR2YJob job;
+    AbR2YPlan plan;
+    avifResult res = r2yBuildJob(image, rgb, async, &job, &plan);
+    if (res != AVIF_RESULT_OK) return res;
+    const AbState s = plan.s;
+    const int monochrome = plan.monochrome, isGray = plan.isGray, writeAlphaPlane = plan.writeAlphaPlane;
 
     res = ctxInit();
     if (res != AVIF_RESULT_OK) return res;
@@ -1225,4 +1272,107 @@ avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, 
     }
     tls.lastKernel = "copy_pad";
     return AVIF_RESULT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batches of device-resident frames: as few launches as possible (see plan.h, AbY2RBatch)     */
+
+avifResult avifB200ImageYUVToRGBBatchAsync(const avifImage * const * images, avifRGBImage * const * rgbs, uint32_t count, void * stream)
+{
+    if (count == 0) return AVIF_RESULT_OK;
+    if (!images || !rgbs) return AVIF_RESULT_INVALID_ARGUMENT;
+    AbY2RJob * jobs = (AbY2RJob *)malloc((size_t)count * sizeof(AbY2RJob));
+    if (!jobs) return AVIF_RESULT_OUT_OF_MEMORY;
+    avifResult res = AVIF_RESULT_OK;
+    int fusable = 1;
+    for (uint32_t k = 0; k < count && res == AVIF_RESULT_OK; ++k) {
+        AbY2RPlan plan;
+        res = y2rBuildJob(images[k], rgbs[k], &jobs[k], &plan);
+        if (res != AVIF_RESULT_OK) break;
+        const avifImage * image = images[k];
+        const avifRGBImage * rgb = rgbs[k];
+        if (rgb->width != image->width || rgb->height != image->height) fusable = 0; /* multi-pass composition: per image */
+        AbY2RJob * job = &jobs[k];
+        const int needSrcAlpha = (job->alphaWrite == AB_ALPHA_COPY) || job->alphaMul == AB_MUL_FLOAT_MUL || job->alphaMul == AB_MUL_FLOAT_UNMUL;
+        job->y = image->yuvPlanes[0];
+        job->yRB = image->yuvRowBytes[0];
+        job->u = plan.hasChroma ? image->yuvPlanes[1] : NULL;
+        job->uRB = image->yuvRowBytes[1];
+        job->v = plan.hasChroma ? image->yuvPlanes[2] : NULL;
+        job->vRB = image->yuvRowBytes[2];
+        job->a = needSrcAlpha ? image->alphaPlane : NULL;
+        job->aRB = job->a ? image->alphaRowBytes : 0;
+        job->rgb = rgb->pixels;
+        job->rgbRB = rgb->rowBytes;
+        job->rowBegin = 0;
+        job->rowEnd = image->height;
+        const uintptr_t m = 2u * plan.s.yuvChanBytes - 1;
+        uintptr_t bits = (uintptr_t)job->y | (uintptr_t)job->yRB;
+        if (job->u) bits |= (uintptr_t)job->u | (uintptr_t)job->uRB | (uintptr_t)job->v | (uintptr_t)job->vRB;
+        if (job->a) bits |= (uintptr_t)job->a | (uintptr_t)job->aRB;
+        job->pairAligned = (uint8_t)((bits & m) == 0);
+    }
+    if (res == AVIF_RESULT_OK) res = ctxInit();
+    if (res == AVIF_RESULT_OK) {
+        if (fusable) {
+            const char * kname = "";
+            res = cudaToResult(abLaunchY2RBatch(jobs, count, stream, tls.policy, &kname));
+            tls.lastKernel = kname;
+        } else {
+            for (uint32_t k = 0; k < count && res == AVIF_RESULT_OK; ++k) res = yuvToRgbCommon(images[k], rgbs[k], stream, 1);
+        }
+    }
+    free(jobs);
+    return res;
+}
+
+avifResult avifB200ImageRGBToYUVBatchAsync(avifImage * const * images, const avifRGBImage * const * rgbs, uint32_t count, void * stream)
+{
+    if (count == 0) return AVIF_RESULT_OK;
+    if (!images || !rgbs) return AVIF_RESULT_INVALID_ARGUMENT;
+    AbR2YJob * jobs = (AbR2YJob *)malloc((size_t)count * sizeof(AbR2YJob));
+    if (!jobs) return AVIF_RESULT_OUT_OF_MEMORY;
+    avifResult res = AVIF_RESULT_OK;
+    int fusable = 1;
+    for (uint32_t k = 0; k < count && res == AVIF_RESULT_OK; ++k) {
+        AbR2YPlan plan;
+        res = r2yBuildJob(images[k], rgbs[k], 1, &jobs[k], &plan);
+        if (res != AVIF_RESULT_OK) break;
+        if (plan.isGray) fusable = 0; /* gray input also fills the chroma planes: per image */
+        avifImage * image = images[k];
+        AbR2YJob * job = &jobs[k];
+        job->rgb = rgbs[k]->pixels;
+        job->rgbRB = rgbs[k]->rowBytes;
+        job->y = image->yuvPlanes[0];
+        job->yRB = image->yuvRowBytes[0];
+        job->u = plan.monochrome ? NULL : image->yuvPlanes[1];
+        job->uRB = image->yuvRowBytes[1];
+        job->v = plan.monochrome ? NULL : image->yuvPlanes[2];
+        job->vRB = image->yuvRowBytes[2];
+        job->a = plan.writeAlphaPlane ? image->alphaPlane : NULL;
+        job->aRB = image->alphaRowBytes;
+        job->rowBegin = 0;
+        job->rowEnd = image->height;
+        const uint32_t pairBytes = 2u * plan.s.rgbPixBytes;
+        const uintptr_t srcAlign = (pairBytes % 16 == 0) ? 16 : (pairBytes % 8 == 0) ? 8 : (pairBytes % 4 == 0) ? 4 : 2;
+        job->srcPairAligned = (uint8_t)((((uintptr_t)job->rgb | (uintptr_t)job->rgbRB) & (srcAlign - 1)) == 0);
+        const uintptr_t m = 2u * plan.s.yuvChanBytes - 1;
+        uintptr_t bits = (uintptr_t)job->y | (uintptr_t)job->yRB;
+        if (job->u) bits |= (uintptr_t)job->u | (uintptr_t)job->uRB;
+        if (job->v) bits |= (uintptr_t)job->v | (uintptr_t)job->vRB;
+        if (job->a) bits |= (uintptr_t)job->a | (uintptr_t)job->aRB;
+        job->dstPairAligned = (uint8_t)((bits & m) == 0);
+    }
+    if (res == AVIF_RESULT_OK) res = ctxInit();
+    if (res == AVIF_RESULT_OK) {
+        if (fusable) {
+            const char * kname = "";
+            res = cudaToResult(abLaunchR2YBatch(jobs, count, stream, tls.policy, &kname));
+            tls.lastKernel = kname;
+        } else {
+            for (uint32_t k = 0; k < count && res == AVIF_RESULT_OK; ++k) res = rgbToYuvCommon(images[k], rgbs[k], stream, 1);
+        }
+    }
+    free(jobs);
+    return res;
 }

@@ -25,7 +25,9 @@
  */
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "pixel_math.cuh"
 #include "plan.h"
@@ -171,53 +173,53 @@ struct TileRows {
 };
 
 template <class C>
-__device__ __forceinline__ TileRows<C> tile_rows(const AbY2RJob & J, uint32_t unit)
+__device__ __forceinline__ TileRows<C> tile_rows(const AbY2RJob & J, const AbY2RFrame & F, uint32_t unit)
 {
     constexpr int ROWS = TileTraits<C>::ROWS;
     TileRows<C> R;
     if (ROWS == 2) {
-        const int ru = (int)(J.rowBegin >> 1) + (int)unit;
+        const int ru = (int)(F.rowBegin >> 1) + (int)unit;
         R.jrow[0] = 2 * ru - 1;
         R.jrow[ROWS - 1] = 2 * ru;
-        const int chromaH = (int)((J.height + 1) >> 1);
+        const int chromaH = (int)((F.height + 1) >> 1);
         R.cA = (ru >= 1) ? ru - 1 : ru;
         R.cB = (ru < chromaH) ? ru : ru - 1;
     } else {
-        R.jrow[0] = (int)(J.rowBegin + unit);
+        R.jrow[0] = (int)(F.rowBegin + unit);
         R.cA = R.cB = R.jrow[0] >> J.shiftY;
     }
     R.any = false;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        R.rowOn[r] = (R.jrow[r] >= (int)J.rowBegin) && (R.jrow[r] < (int)J.rowEnd);
+        R.rowOn[r] = (R.jrow[r] >= (int)F.rowBegin) && (R.jrow[r] < (int)F.rowEnd);
         R.any = R.any || R.rowOn[r];
     }
     return R;
 }
 
 template <class C, bool FULL>
-__device__ __forceinline__ void load_tile(const AbY2RJob & J, const TileRows<C> & R, uint32_t x0, uint32_t lane, TileIn<C> & in)
+__device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, TileIn<C> & in)
 {
     using T = TileTraits<C>;
     using YT = typename T::YT;
     const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
 #pragma unroll
     for (int r = 0; r < T::ROWS; ++r) {
         in.yw[r][0] = in.yw[r][1] = in.yw[r][2] = in.yw[r][3] = 0;
         if (T::NEED_A) in.aw[r][0] = in.aw[r][1] = in.aw[r][2] = in.aw[r][3] = 0;
         if (R.rowOn[r] && (FULL || nValid)) {
-            load8<YT>(J.y + (int64_t)R.jrow[r] * J.yRB, px0, nValid, in.yw[r]);
-            if (T::NEED_A) load8<YT>(J.a + (int64_t)R.jrow[r] * J.aRB, px0, nValid, in.aw[r]);
+            load8<YT>(F.y + (int64_t)R.jrow[r] * F.yRB, px0, nValid, in.yw[r]);
+            if (T::NEED_A) load8<YT>(F.a + (int64_t)R.jrow[r] * F.aRB, px0, nValid, in.aw[r]);
         }
     }
-    const uint32_t cw = T::SUB ? ((J.width + 1) >> 1) : J.width;
+    const uint32_t cw = T::SUB ? ((F.width + 1) >> 1) : F.width;
     const uint32_t m0 = T::SUB ? (px0 >> 1) : px0;
 #pragma unroll
     for (int c = 0; c < T::CROWS; ++c) {
         const int crow = (c == 0) ? R.cA : R.cB;
-        const uint8_t * ur = J.u + (int64_t)crow * J.uRB;
-        const uint8_t * vr = J.v + (int64_t)crow * J.vRB;
+        const uint8_t * ur = F.u + (int64_t)crow * F.uRB;
+        const uint8_t * vr = F.v + (int64_t)crow * F.vRB;
         if (T::SUB) {
             if (FULL) { /* the lane's 4 columns exist: m0 + 3 <= 127 + 128*tile < cw */
                 load4_clamped<YT>(ur, m0, m0 + 4, in.uw[c]);
@@ -251,7 +253,7 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const TileRows<C> 
 }
 
 template <class C, bool FULL>
-__device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in)
+__device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in)
 {
     using T = TileTraits<C>;
     using YT = typename T::YT;
@@ -259,7 +261,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const Til
     constexpr int ROWS = T::ROWS, CROWS = T::CROWS, PIXB = T::PIXB;
     constexpr bool SUB = T::SUB, BIL = T::BIL, HAS_A = T::HAS_A, NEED_A = T::NEED_A;
     const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < J.width) ? min(8u, J.width - px0) : 0u);
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
 
     /* ------------------------------ chroma ------------------------------ */
     const uint32_t K = J.magicK;
@@ -405,7 +407,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const Til
                 words[wi] = __byte_perm(lo, hi, 0x5410u);
             }
         }
-        uint8_t * d = J.rgb + (int64_t)R.jrow[r] * J.rgbRB + (int64_t)px0 * PIXB;
+        uint8_t * d = F.rgb + (int64_t)R.jrow[r] * F.rgbRB + (int64_t)px0 * PIXB;
         if (FULL || nValid == 8) {
             if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
@@ -430,65 +432,76 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const Til
 
 /* ---- the kernel ------------------------------------------------------------------------------------- */
 
-/* VARIANT 3: one tile per warp (grid = tiles).  VARIANT 4 (production): persistent warps stride over the tiles and
- * load tile i+1 into a second register set before converting tile i, so a warp always has 50-150 B of loads in flight
- * while it computes (at 25-50 % occupancy the scheduler alone cannot hide HBM latency: ncu showed 33 % long_scoreboard
- * + 20 % store-drain stalls on the 8K case).  Tile order = row-major, so concurrently running warps touch adjacent
- * 256-pixel spans.  (Shared-memory staged stores were measured slower: profiles/r01_variants.md.) */
-template <class C, int VARIANT = 4>
-__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RJob J, const uint32_t tilesX, const uint32_t totalTiles)
+/* Persistent, software-pipelined, batched.  Work unit = GROUP of 8 consecutive tiles of one frame (one per warp), so
+ * the frame is block-uniform.  A block strides over the groups of all frames of the launch; each warp loads its tile
+ * of group g+stride into a second register set before converting its tile of group g, so it always has 50-150 B of
+ * loads in flight while it computes (at 25-50 % occupancy the scheduler alone cannot hide HBM latency: ncu showed 33 %
+ * long_scoreboard + 20 % store-drain stalls on the 8K case with one tile per warp).  Tiles are row-major, so concurrently
+ * running warps touch adjacent 256-pixel spans.  (Shared-memory staged stores measured slower: profiles/r01_variants.md.) */
+template <class C>
+__device__ __forceinline__ uint32_t frame_of_group(const AbY2RBatch & B, uint32_t g)
 {
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && g >= B.frame[f + 1].groupStart) ++f; /* block-uniform */
+    return f;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
+{
+    const AbY2RJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * kWarps;
-    uint32_t tile = blockIdx.x * kWarps + warp;
-    if (tile >= totalTiles) return;
-    if (VARIANT == 3) { /* one tile per warp */
-        const uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kTile;
-        const TileRows<C> R = tile_rows<C>(J, unit);
-        if (!R.any) return;
-        TileIn<C> in;
-        if (x0 + kTile <= J.width) {
-            load_tile<C, true>(J, R, x0, lane, in);
-            convert_store_tile<C, true>(J, R, x0, lane, in);
-        } else {
-            load_tile<C, false>(J, R, x0, lane, in);
-            convert_store_tile<C, false>(J, R, x0, lane, in);
-        }
-        return;
-    }
-    /* persistent, software-pipelined: cur = tile being converted, nxt = tile whose loads are in flight */
+    uint32_t g = blockIdx.x;
+    if (g >= B.totalGroups) return;
     TileIn<C> cur, nxt;
-    uint32_t unit = tile / tilesX, x0 = (tile - unit * tilesX) * kTile;
-    TileRows<C> R = tile_rows<C>(J, unit);
-    bool full = (x0 + kTile <= J.width);
-    if (R.any) {
-        if (full) load_tile<C, true>(J, R, x0, lane, cur);
-        else load_tile<C, false>(J, R, x0, lane, cur);
+    uint32_t f = frame_of_group<C>(B, g);
+    uint32_t tile = (g - B.frame[f].groupStart) * kWarps + warp;
+    bool live = tile < B.frame[f].tiles; /* the last group of a frame may be partial */
+    uint32_t unit = 0, x0 = 0;
+    TileRows<C> R;
+    R.any = false;
+    bool full = false;
+    if (live) {
+        unit = tile / B.frame[f].tilesX;
+        x0 = (tile - unit * B.frame[f].tilesX) * kTile;
+        R = tile_rows<C>(J, B.frame[f], unit);
+        full = (x0 + kTile <= B.frame[f].width);
+        if (R.any) {
+            if (full) load_tile<C, true>(J, B.frame[f], R, x0, lane, cur);
+            else load_tile<C, false>(J, B.frame[f], R, x0, lane, cur);
+        }
     }
     while (true) {
-        const uint32_t ntile = tile + stride;
-        const bool more = ntile < totalTiles; /* warp-uniform */
-        uint32_t nunit = 0, nx0 = 0;
-        TileRows<C> NR = R;
-        bool nfull = false;
+        const uint32_t ng = g + gridDim.x;
+        const bool more = ng < B.totalGroups; /* block-uniform */
+        uint32_t nf = f, nx0 = 0;
+        bool nlive = false, nfull = false;
+        TileRows<C> NR;
+        NR.any = false;
         if (more) {
-            nunit = ntile / tilesX;
-            nx0 = (ntile - nunit * tilesX) * kTile;
-            NR = tile_rows<C>(J, nunit);
-            nfull = (nx0 + kTile <= J.width);
-            if (NR.any) {
-                if (nfull) load_tile<C, true>(J, NR, nx0, lane, nxt);
-                else load_tile<C, false>(J, NR, nx0, lane, nxt);
+            nf = frame_of_group<C>(B, ng);
+            const uint32_t ntile = (ng - B.frame[nf].groupStart) * kWarps + warp;
+            nlive = ntile < B.frame[nf].tiles;
+            if (nlive) {
+                const uint32_t nunit = ntile / B.frame[nf].tilesX;
+                nx0 = (ntile - nunit * B.frame[nf].tilesX) * kTile;
+                NR = tile_rows<C>(J, B.frame[nf], nunit);
+                nfull = (nx0 + kTile <= B.frame[nf].width);
+                if (NR.any) {
+                    if (nfull) load_tile<C, true>(J, B.frame[nf], NR, nx0, lane, nxt);
+                    else load_tile<C, false>(J, B.frame[nf], NR, nx0, lane, nxt);
+                }
             }
         }
-        if (R.any) {
-            if (full) convert_store_tile<C, true>(J, R, x0, lane, cur);
-            else convert_store_tile<C, false>(J, R, x0, lane, cur);
+        if (live && R.any) {
+            if (full) convert_store_tile<C, true>(J, B.frame[f], R, x0, lane, cur);
+            else convert_store_tile<C, false>(J, B.frame[f], R, x0, lane, cur);
         }
         if (!more) break;
         cur = nxt;
-        tile = ntile;
-        unit = nunit;
+        g = ng;
+        f = nf;
+        live = nlive;
         x0 = nx0;
         R = NR;
         full = nfull;
@@ -497,97 +510,136 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int VARIANT = 4>
-static int launch_cfg(const AbY2RJob & J, cudaStream_t st)
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;
-    const uint32_t rows = J.rowEnd - J.rowBegin;
-    uint32_t units = rows;
-    if (CHROMA == CH_BIL420) units = (J.rowEnd >> 1) - (J.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
-    const uint32_t tilesX = (J.width + kTile - 1) / kTile;
-    const uint32_t total = tilesX * units;
-    uint32_t blocks = (total + kWarps - 1) / kWarps;
-    if (VARIANT == 4) {
-        static int resident = 0; /* blocks that fit on the whole device at once (per instantiation) */
-        if (!resident) {
-            int dev = 0, sms = 0, perSm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C, VARIANT>, kWarps * 32, 0);
-            resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
-        }
-        if (blocks > (uint32_t)resident) blocks = (uint32_t)resident;
+    uint32_t groups = 0;
+    for (uint32_t f = 0; f < B.nFrames; ++f) {
+        AbY2RFrame & F = B.frame[f];
+        const uint32_t rows = F.rowEnd - F.rowBegin;
+        uint32_t units = rows;
+        if (CHROMA == CH_BIL420) units = (F.rowEnd >> 1) - (F.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
+        F.tilesX = (F.width + kTile - 1) / kTile;
+        F.tiles = F.tilesX * units;
+        F.groupStart = groups;
+        groups += (F.tiles + kWarps - 1) / kWarps;
     }
-    y2r_fast_kernel<C, VARIANT><<<blocks, kWarps * 32, 0, st>>>(J, tilesX, total);
+    B.totalGroups = groups;
+    static int resident = 0; /* blocks that fit on the whole device at once (per instantiation) */
+    if (!resident) {
+        int dev = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
+        resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+    }
+    /* few groups per resident block -> one group per block (balance beats prefetch); many -> persistent */
+    uint32_t blocks = groups;
+    if (groups >= 4u * (uint32_t)resident) blocks = (uint32_t)resident;
+    y2r_fast_kernel<C><<<blocks, kWarps * 32, 0, st>>>(B);
     return 1;
 }
 
 template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST>
-static int launch_alpha(const AbY2RJob & J, cudaStream_t st)
+static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
 {
+    const AbY2RJob & J = B.common;
     constexpr bool slow = (CHROMA == CH_BIL420 || CHROMA == CH_BIL422); /* general loop: alpha math in float; fast loops: integer post-pass */
     if (NCH == 3) {
-        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE>(J, st);
-        if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL>(J, st);
+        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE>(B, st);
+        if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL>(B, st);
         return 0;
     }
     if (J.alphaWrite == AB_ALPHA_FILL) {
-        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_FILL, AB_MUL_NONE>(J, st);
+        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_FILL, AB_MUL_NONE>(B, st);
         return 0;
     }
     if (J.alphaWrite != AB_ALPHA_COPY) return 0;
     switch (J.alphaMul) {
-        case AB_MUL_NONE: return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(J, st);
-        case AB_MUL_INT_PREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(J, st);
-        case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(J, st);
-        case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(J, st);
-        case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(J, st);
+        case AB_MUL_NONE: return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(B, st);
+        case AB_MUL_INT_PREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(B, st);
+        case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(B, st);
+        case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(B, st);
+        case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(B, st);
         default: return 0;
     }
 }
 
-/* returns 1 if a specialised kernel was launched, 0 if the job must take the general kernel */
+/* can this job run on a specialised kernel? (constants + alignment of its own planes) */
 template <typename YT, typename RT>
-static int launch_y2r_fast_typed(const AbY2RJob & Jin, cudaStream_t st)
+static bool fast_eligible(const AbY2RJob & J)
 {
-    AbY2RJob J = Jin;
-    if (J.mode != AB_MODE_COEFF || J.isGray || J.is565 || J.toF16 || J.chroma == AB_CHROMA_NONE) return 0;
-    if (J.nChan != 3 && J.nChan != 4) return 0;
-    if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return 0;
-    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return 0;
-    if (!J.rangeY.exact || !J.rangeUV.exact || !J.kg.exact) return 0;
-    if ((J.alphaMul == AB_MUL_INT_PREMUL) && !J.rgbMaxDiv.exact) return 0;
-    if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.exact) return 0;
-    /* alignment of the vector accesses */
+    if (J.mode != AB_MODE_COEFF || J.isGray || J.is565 || J.toF16 || J.chroma == AB_CHROMA_NONE) return false;
+    if (J.nChan != 3 && J.nChan != 4) return false;
+    if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
+    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return false;
+    if (!J.rangeY.exact || !J.rangeUV.exact || !J.kg.exact) return false;
+    if ((J.alphaMul == AB_MUL_INT_PREMUL) && !J.rgbMaxDiv.exact) return false;
+    if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.exact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
     const bool sub = (J.chroma != AB_CHROMA_FULL);
     uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
     const bool needA = (J.alphaWrite == AB_ALPHA_COPY) || (J.alphaMul != AB_MUL_NONE);
     if (needA) {
-        if (!J.a) return 0;
+        if (!J.a) return false;
         bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
     }
-    if (bits & lumaAlign) return 0;
+    if (bits & lumaAlign) return false;
     const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
-    if (cbits & (sub ? subAlign : lumaAlign)) return 0;
-    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & 15) return 0;
-    if (J.width == 0 || J.rowEnd <= J.rowBegin) return 0;
+    if (cbits & (sub ? subAlign : lumaAlign)) return false;
+    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & 15) return false;
+    if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
+    return true;
+}
 
+/* every conversion constant equal (the per-frame members -- pointers, strides, extents -- lead the struct) */
+static inline bool same_constants(const AbY2RJob & a, const AbY2RJob & b)
+{
+    const size_t from = offsetof(AbY2RJob, yuvMax), to = offsetof(AbY2RJob, pairAligned);
+    return memcmp(reinterpret_cast<const char *>(&a) + from, reinterpret_cast<const char *>(&b) + from, to - from) == 0;
+}
+
+/* Launches jobs[0..n) (n <= AB_MAX_BATCH) in ONE specialised kernel if all are eligible and share their constants.
+ * Returns 1 if launched, 0 if the caller must take the general path. */
+template <typename YT, typename RT>
+static int launch_y2r_fast_typed(const AbY2RJob * jobs, uint32_t n, cudaStream_t st)
+{
+    if (n == 0 || n > AB_MAX_BATCH) return 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (!fast_eligible<YT, RT>(jobs[k])) return 0;
+        if (k && !same_constants(jobs[0], jobs[k])) return 0;
+    }
+    AbY2RBatch B;
+    B.common = jobs[0];
+    B.nFrames = n;
+    AbY2RJob & J = B.common;
     /* B-first layouts: the matrix is symmetric in (R,Cr,c1,c3) <-> (B,Cb,c2,c4) and float addition commutes, so BGR order
      * is the RGB kernel with the chroma planes and their constants exchanged. */
-    if (J.swapRB) {
-        const uint8_t * tp = J.u; J.u = J.v; J.v = tp;
-        const int64_t ts = J.uRB; J.uRB = J.vRB; J.vRB = ts;
+    const bool swap = J.swapRB != 0;
+    if (swap) {
         float tf = J.c1; J.c1 = J.c2; J.c2 = tf;
         tf = J.c3; J.c3 = J.c4; J.c4 = tf;
         J.swapRB = 0;
+    }
+    for (uint32_t k = 0; k < n; ++k) {
+        AbY2RFrame & F = B.frame[k];
+        const AbY2RJob & S = jobs[k];
+        F.y = S.y; F.a = S.a; F.rgb = S.rgb;
+        F.u = swap ? S.v : S.u;
+        F.v = swap ? S.u : S.v;
+        F.yRB = S.yRB; F.aRB = S.aRB; F.rgbRB = S.rgbRB;
+        F.uRB = swap ? S.vRB : S.uRB;
+        F.vRB = swap ? S.uRB : S.vRB;
+        F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
+        F.tilesX = F.tiles = F.groupStart = F.pad = 0;
     }
     const bool afirst = J.alphaFirst != 0;
     const int nch = J.nChan;
 #define ABF_DISPATCH(CH)                                                              \
     do {                                                                              \
-        if (nch == 3) return launch_alpha<YT, RT, CH, 3, false>(J, st);               \
-        return afirst ? launch_alpha<YT, RT, CH, 4, true>(J, st) : launch_alpha<YT, RT, CH, 4, false>(J, st); \
+        if (nch == 3) return launch_alpha<YT, RT, CH, 3, false>(B, st);               \
+        return afirst ? launch_alpha<YT, RT, CH, 4, true>(B, st) : launch_alpha<YT, RT, CH, 4, false>(B, st); \
     } while (0)
     if (J.chroma == AB_CHROMA_FULL) ABF_DISPATCH(CH_FULL);
     if (J.chroma == AB_CHROMA_NEAREST) ABF_DISPATCH(CH_NEAREST);

@@ -160,3 +160,12 @@ class RGBImage:
         a = np.ascontiguousarray(arr2d, dtype=np.uint8).reshape(self.c.height, self.c.width * self.pixel_bytes)
         raw[:, :a.shape[1]] = a
         self.buf.set(raw)
+
+
+def pointer_array(items):
+    """ctypes array of pointers to the structs of YUVImage / RGBImage wrappers (argument of the *BatchAsync entry points)."""
+    import ctypes as C
+    if not items:
+        return None
+    t = type(items[0].c)
+    return (C.POINTER(t) * len(items))(*[C.pointer(it.c) for it in items])

@@ -204,3 +204,74 @@ def test_exhaustive_8bit_yuv_cube(gpu_product, oracle):
         assert lib.avifImageYUVToRGB(img.ptr(), rgb.ptr()) == 0
         outs.append(rgb.payload_bytes().copy())
     assert util.first_mismatch(outs[0], outs[1]) is None
+
+
+def _batch_case(gpu_product, oracle, specs, seed0):
+    """Runs the batch entry points on device-resident frames and checks every frame against the oracle."""
+    import ctypes
+    import torch
+    from libavif_b200.images import pointer_array
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    imgs = [util.make_yuv(sp, seed0 + k, device="cuda:0") for k, sp in enumerate(specs)]
+    rgbs = [util.make_rgb_dst(sp, device="cuda:0") for sp in specs]
+    want = [util.yuv_to_rgb(oracle, sp, seed0 + k) for k, sp in enumerate(specs)]
+    codes = {w[0] for w in want}
+    res = gpu_product.avifB200ImageYUVToRGBBatchAsync(pointer_array(imgs), pointer_array(rgbs), len(specs), stream)
+    torch.cuda.synchronize()
+    if codes == {0}:
+        assert res == 0
+        for k, sp in enumerate(specs):
+            mm = util.first_mismatch(want[k][1], rgbs[k].full_bytes())
+            assert mm is None, f"frame {k} {sp.ident()}: {mm}"
+    else:
+        assert res in codes - {0}
+    return gpu_product.avifB200LastKernelName().decode()
+
+
+def test_batch_yuv_to_rgb(gpu_product, oracle):
+    import dataclasses
+    gpu_product.avifB200ResetKernelLaunchCount()
+    base = util.Spec(w=1920, h=64, depth=10, fmt=abi.AVIF_PIXEL_FORMAT_YUV420, rng=0, mc=abi.MC_BT709, rgb_depth=16,
+                     rgb_fmt=abi.AVIF_RGB_FORMAT_RGB, ups=abi.AVIF_CHROMA_UPSAMPLING_BILINEAR)
+    # 30 equal frames: two fused launches (24 + 6)
+    name = _batch_case(gpu_product, oracle, [base] * 30, 100)
+    assert name.startswith("y2r_fast") and gpu_product.avifB200KernelLaunchCount() == 2
+    # same constants, different sizes (incl. ragged and tiny ones) still fuse
+    sizes = [(264, 6), (8, 3), (1000, 5), (257, 7), (2056, 2), (16, 16), (520, 9)]
+    gpu_product.avifB200ResetKernelLaunchCount()
+    _batch_case(gpu_product, oracle, [dataclasses.replace(base, w=w, h=h) for w, h in sizes], 200)
+    assert gpu_product.avifB200KernelLaunchCount() == 1
+    # alpha + premultiply, 4:4:4
+    c2 = util.Spec(w=512, h=33, depth=10, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rng=1, mc=abi.MC_BT709, alpha=True, rgb_depth=10,
+                   rgb_fmt=abi.AVIF_RGB_FORMAT_RGBA, rgb_premult=True)
+    _batch_case(gpu_product, oracle, [c2] * 5, 300)
+    # heterogeneous batch: falls back to compatible runs / per-image launches, still exact
+    mixed = [base, c2, dataclasses.replace(base, mc=abi.MC_BT601), dataclasses.replace(c2, rgb_fmt=abi.AVIF_RGB_FORMAT_BGRA),
+             dataclasses.replace(base, depth=8, rgb_depth=8), dataclasses.replace(base, mc=abi.MC_YCGCO, rng=1),
+             dataclasses.replace(base, rgb_fmt=abi.AVIF_RGB_FORMAT_RGB_565, rgb_depth=8), dataclasses.replace(c2, is_float=True, rgb_depth=16)]
+    _batch_case(gpu_product, oracle, mixed, 400)
+    # one invalid frame: its error code comes back
+    _batch_case(gpu_product, oracle, [base, dataclasses.replace(base, mc=3), base], 500)
+
+
+def test_batch_rgb_to_yuv(gpu_product, oracle):
+    import ctypes
+    import dataclasses
+    import torch
+    from libavif_b200.images import pointer_array
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    base = util.Spec(w=1920, h=36, depth=8, fmt=abi.AVIF_PIXEL_FORMAT_YUV420, rng=1, mc=abi.MC_BT601, rgb_depth=8, rgb_fmt=abi.AVIF_RGB_FORMAT_RGBA)
+    c2 = util.Spec(w=520, h=17, depth=10, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rng=1, mc=abi.MC_BT709, rgb_depth=10, rgb_fmt=abi.AVIF_RGB_FORMAT_RGBA, rgb_premult=True)
+    for specs in ([base] * 26, [dataclasses.replace(base, w=w, h=h) for w, h in [(264, 6), (9, 3), (1001, 5), (2056, 2)]], [c2] * 3,
+                  [base, c2, dataclasses.replace(base, rgb_fmt=abi.AVIF_RGB_FORMAT_GRAY), dataclasses.replace(c2, mc=abi.MC_IDENTITY)]):
+        srcs = [util.make_rgb_src(sp, 700 + k, device="cuda:0") for k, sp in enumerate(specs)]
+        dsts = [util.make_yuv_dst(sp, device="cuda:0", with_alpha=abi.rgb_format_has_alpha(sp.rgb_fmt)) for sp in specs]
+        assert gpu_product.avifB200ImageRGBToYUVBatchAsync(pointer_array(dsts), pointer_array(srcs), len(specs), stream) == 0
+        torch.cuda.synchronize()
+        for k, sp in enumerate(specs):
+            ro, po = util.rgb_to_yuv(oracle, sp, 700 + k)
+            assert ro == 0
+            for p in range(4):
+                if po[p] is not None:
+                    mm = util.first_mismatch(po[p], dsts[k].bufs[p].host().reshape(-1))
+                    assert mm is None, f"frame {k} plane {p} {sp.ident()}: {mm}"

@@ -11,8 +11,6 @@ if [ "$2" != "skiptests" ]; then
   timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1
   tail -25 $OUT/pytest_gpu.log
 fi
-timeout 600 python tools/experiments.py > $OUT/experiments.json 2> $OUT/experiments.err; cat $OUT/experiments.json | head -80; tail -3 $OUT/experiments.err
-for mb in 16 32 64; do AVIF_B200_BAND_MB=$mb timeout 300 python bench.py --no-cpu-baseline --steps 5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('band_mb',$mb,'e2e',d['e2e']['value'])" | tee -a $OUT/band_sweep.txt; done
 timeout 600 python bench.py --extras > $OUT/bench.json 2> $OUT/bench.err
 tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
 # launch list (cold-cache, serialised: compare shares only)
