@@ -965,15 +965,26 @@ int abLaunchY2RBatch(const AbY2RJob * jobs, uint32_t count, void * stream, int f
         /* longest run of frames with the same sample types, <= AB_MAX_BATCH: one specialised launch if they are compatible */
         uint32_t n = 1;
         while (k + n < count && n < AB_MAX_BATCH && jobs[k + n].yuvBytes == jobs[k].yuvBytes && jobs[k + n].rgbBytes == jobs[k].rgbBytes) ++n;
-        if ((forceGeneric & 3) == 0 && n > 1 && y2r_fast_try(jobs + k, n, stream)) {
+        /* longest prefix of the run that one specialised launch can take (frames must be eligible and share constants) */
+        bool fused = false;
+        if ((forceGeneric & 3) == 0) {
+            for (; n > 1; --n) {
+                if (y2r_fast_try(jobs + k, n, stream)) {
+                    fused = true;
+                    break;
+                }
+            }
+        } else {
+            n = 1;
+        }
+        if (fused) {
             if (kernelName) *kernelName = y2r_fast_name(jobs + k);
             const int err = finish_launch();
             if (err) return err;
         } else {
-            for (uint32_t i = 0; i < n; ++i) {
-                const int err = abLaunchY2R(jobs + k + i, stream, forceGeneric, kernelName);
-                if (err) return err;
-            }
+            n = 1;
+            const int err = abLaunchY2R(jobs + k, stream, forceGeneric, kernelName);
+            if (err) return err;
         }
         k += n;
     }
@@ -997,15 +1008,25 @@ int abLaunchR2YBatch(const AbR2YJob * jobs, uint32_t count, void * stream, int f
     while (k < count) {
         uint32_t n = 1;
         while (k + n < count && n < AB_MAX_BATCH && jobs[k + n].yuvBytes == jobs[k].yuvBytes && jobs[k + n].rgbBytes == jobs[k].rgbBytes) ++n;
-        if ((forceGeneric & 3) == 0 && n > 1 && r2y_fast_try(jobs + k, n, stream)) {
+        bool fused = false;
+        if ((forceGeneric & 3) == 0) {
+            for (; n > 1; --n) {
+                if (r2y_fast_try(jobs + k, n, stream)) {
+                    fused = true;
+                    break;
+                }
+            }
+        } else {
+            n = 1;
+        }
+        if (fused) {
             if (kernelName) *kernelName = "r2y_fast";
             const int err = finish_launch();
             if (err) return err;
         } else {
-            for (uint32_t i = 0; i < n; ++i) {
-                const int err = abLaunchR2Y(jobs + k + i, stream, forceGeneric, kernelName);
-                if (err) return err;
-            }
+            n = 1;
+            const int err = abLaunchR2Y(jobs + k, stream, forceGeneric, kernelName);
+            if (err) return err;
         }
         k += n;
     }

@@ -105,8 +105,9 @@ typedef struct AbR2YJob {
 /* ---- batches: one launch converts several frames that share every conversion constant ------------------ */
 /* A kernel launch costs ~4-5 us of ramp-up / drain during which the SMs idle (ncu: sm__cycles_elapsed - active), i.e.
  * 15 % of a 4K frame and half of a 1080p one.  The specialised kernels therefore take a small table of frames: work
- * is cut into GROUPS of 8 consecutive 256-pixel tiles of one frame (one tile per warp of a block), so the frame --
- * pointers, strides, extents -- is block-uniform and lives in uniform registers. */
+ * is cut into GROUPS of 8 consecutive 256-pixel tiles of one frame (one tile per warp of a block) and every block is
+ * bound to ONE frame for its whole life (blocks are shared out in proportion to the frames' group counts), so the
+ * frame -- pointers, strides, extents -- is a loop invariant held in (uniform) registers. */
 #define AB_MAX_BATCH 24
 
 typedef struct AbY2RFrame {
@@ -120,13 +121,15 @@ typedef struct AbY2RFrame {
     uint32_t rowBegin, rowEnd;
     uint32_t tilesX;     /* 256-pixel tiles per row */
     uint32_t tiles;      /* tilesX * row units */
-    uint32_t groupStart; /* first group of this frame in the launch */
+    uint32_t groups;     /* ceil(tiles / 8) */
+    uint32_t blockStart; /* blocks [blockStart, blockStart + blocks) of the launch work on this frame only, */
+    uint32_t blocks;     /* striding over its groups: the frame is invariant for the whole life of a block */
     uint32_t pad;
 } AbY2RFrame;
 
 typedef struct AbY2RBatch {
     AbY2RJob common; /* constants (per-frame members unused) */
-    uint32_t nFrames, totalGroups;
+    uint32_t nFrames, totalBlocks;
     AbY2RFrame frame[AB_MAX_BATCH];
 } AbY2RBatch;
 
@@ -139,12 +142,12 @@ typedef struct AbR2YFrame {
     int64_t rgbRB, yRB, uRB, vRB, aRB;
     uint32_t width, height;
     uint32_t rowBegin, rowEnd;
-    uint32_t tilesX, tiles, groupStart, pad;
+    uint32_t tilesX, tiles, groups, blockStart, blocks, pad;
 } AbR2YFrame;
 
 typedef struct AbR2YBatch {
     AbR2YJob common;
-    uint32_t nFrames, totalGroups;
+    uint32_t nFrames, totalBlocks;
     AbR2YFrame frame[AB_MAX_BATCH];
 } AbR2YBatch;
 

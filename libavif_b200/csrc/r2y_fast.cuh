@@ -282,66 +282,75 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
 /* Persistent, software-pipelined and batched like y2r_fast_kernel: a block strides over groups of 8 consecutive tiles of one
  * frame (one tile per warp); each warp loads its tile of the next group into a second register set before converting the
  * current one. */
-__device__ __forceinline__ uint32_t rframe_of_group(const AbR2YBatch & B, uint32_t g)
-{
-    uint32_t f = 0;
-    while (f + 1 < B.nFrames && g >= B.frame[f + 1].groupStart) ++f; /* block-uniform */
-    return f;
-}
-
 template <class C>
 __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
 {
     constexpr int ROWS = RTileIn<C>::ROWS;
     const AbR2YJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t g = blockIdx.x;
-    if (g >= B.totalGroups) return;
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f; /* block-uniform, once per block */
+    const AbR2YFrame & F = B.frame[f];                                         /* invariant for the life of the block */
+    const uint32_t gStride = F.blocks;
+    uint32_t g = blockIdx.x - F.blockStart;
+    if (g >= F.groups) return;
     RTileIn<C> cur, nxt;
-    uint32_t f = rframe_of_group(B, g);
-    uint32_t tile = (g - B.frame[f].groupStart) * kRWarps + warp;
-    bool live = tile < B.frame[f].tiles;
+    uint32_t tile = g * kRWarps + warp;
+    bool live = tile < F.tiles;
     uint32_t x0 = 0, j0 = 0;
     bool full = false;
     if (live) {
-        const uint32_t unit = tile / B.frame[f].tilesX;
-        x0 = (tile - unit * B.frame[f].tilesX) * kRTile;
-        j0 = B.frame[f].rowBegin + unit * ROWS;
-        full = (x0 + kRTile <= B.frame[f].width);
-        if (full) load_rtile<C, true>(J, B.frame[f], x0, j0, lane, cur);
-        else load_rtile<C, false>(J, B.frame[f], x0, j0, lane, cur);
+        const uint32_t unit = tile / F.tilesX;
+        x0 = (tile - unit * F.tilesX) * kRTile;
+        j0 = F.rowBegin + unit * ROWS;
+        full = (x0 + kRTile <= F.width);
+        if (full) load_rtile<C, true>(J, F, x0, j0, lane, cur);
+        else load_rtile<C, false>(J, F, x0, j0, lane, cur);
     }
     while (true) {
-        const uint32_t ng = g + gridDim.x;
-        const bool more = ng < B.totalGroups; /* block-uniform */
-        uint32_t nf = f, nx0 = 0, nj0 = 0;
+        const uint32_t ng = g + gStride;
+        const bool more = ng < F.groups; /* block-uniform */
+        uint32_t nx0 = 0, nj0 = 0;
         bool nlive = false, nfull = false;
         if (more) {
-            nf = rframe_of_group(B, ng);
-            const uint32_t ntile = (ng - B.frame[nf].groupStart) * kRWarps + warp;
-            nlive = ntile < B.frame[nf].tiles;
+            const uint32_t ntile = ng * kRWarps + warp;
+            nlive = ntile < F.tiles;
             if (nlive) {
-                const uint32_t nunit = ntile / B.frame[nf].tilesX;
-                nx0 = (ntile - nunit * B.frame[nf].tilesX) * kRTile;
-                nj0 = B.frame[nf].rowBegin + nunit * ROWS;
-                nfull = (nx0 + kRTile <= B.frame[nf].width);
-                if (nfull) load_rtile<C, true>(J, B.frame[nf], nx0, nj0, lane, nxt);
-                else load_rtile<C, false>(J, B.frame[nf], nx0, nj0, lane, nxt);
+                const uint32_t nunit = ntile / F.tilesX;
+                nx0 = (ntile - nunit * F.tilesX) * kRTile;
+                nj0 = F.rowBegin + nunit * ROWS;
+                nfull = (nx0 + kRTile <= F.width);
+                if (nfull) load_rtile<C, true>(J, F, nx0, nj0, lane, nxt);
+                else load_rtile<C, false>(J, F, nx0, nj0, lane, nxt);
             }
         }
         if (live) {
-            if (full) convert_store_rtile<C, true>(J, B.frame[f], x0, j0, lane, cur);
-            else convert_store_rtile<C, false>(J, B.frame[f], x0, j0, lane, cur);
+            if (full) convert_store_rtile<C, true>(J, F, x0, j0, lane, cur);
+            else convert_store_rtile<C, false>(J, F, x0, j0, lane, cur);
         }
         if (!more) break;
         cur = nxt;
         g = ng;
-        f = nf;
         live = nlive;
         x0 = nx0;
         j0 = nj0;
         full = nfull;
     }
+}
+
+template <class FrameT>
+static uint32_t rassign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups, uint32_t blocksWanted)
+{
+    uint32_t start = 0;
+    for (uint32_t f = 0; f < n; ++f) {
+        uint64_t share = ((uint64_t)frames[f].groups * blocksWanted + totalGroups - 1) / (totalGroups ? totalGroups : 1);
+        if (share < 1) share = 1;
+        if (share > frames[f].groups) share = frames[f].groups ? frames[f].groups : 1;
+        frames[f].blockStart = start;
+        frames[f].blocks = (uint32_t)share;
+        start += (uint32_t)share;
+    }
+    return start;
 }
 
 template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>
@@ -355,10 +364,9 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
         const uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
         F.tilesX = (F.width + kRTile - 1) / kRTile;
         F.tiles = F.tilesX * units;
-        F.groupStart = groups;
-        groups += (F.tiles + kRWarps - 1) / kRWarps;
+        F.groups = (F.tiles + kRWarps - 1) / kRWarps;
+        groups += F.groups;
     }
-    B.totalGroups = groups;
     static int resident = 0; /* blocks resident on the whole device (per instantiation) */
     if (!resident) {
         int dev = 0, sms = 0, perSm = 0;
@@ -367,9 +375,9 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
     }
-    uint32_t blocks = groups;
-    if (groups >= 4u * (uint32_t)resident) blocks = (uint32_t)resident;
-    r2y_fast_kernel<C><<<blocks, kRWarps * 32, 0, st>>>(B);
+    const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
+    B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);
+    r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
     return 1;
 }
 
@@ -440,7 +448,7 @@ static int launch_r2y_fast_typed(const AbR2YJob * jobs, uint32_t n, cudaStream_t
         F.rgb = S.rgb; F.y = S.y; F.u = S.u; F.v = S.v; F.a = S.a;
         F.rgbRB = S.rgbRB; F.yRB = S.yRB; F.uRB = S.uRB; F.vRB = S.vRB; F.aRB = S.aRB;
         F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
-        F.tilesX = F.tiles = F.groupStart = F.pad = 0;
+        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = F.pad = 0;
     }
     const AbR2YJob & J = B.common;
     if (!J.hasChroma) return rlaunch_sub<RT, YT, SUB_400>(B, st);

@@ -439,73 +439,82 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
  * long_scoreboard + 20 % store-drain stalls on the 8K case with one tile per warp).  Tiles are row-major, so concurrently
  * running warps touch adjacent 256-pixel spans.  (Shared-memory staged stores measured slower: profiles/r01_variants.md.) */
 template <class C>
-__device__ __forceinline__ uint32_t frame_of_group(const AbY2RBatch & B, uint32_t g)
-{
-    uint32_t f = 0;
-    while (f + 1 < B.nFrames && g >= B.frame[f + 1].groupStart) ++f; /* block-uniform */
-    return f;
-}
-
-template <class C>
 __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
 {
     const AbY2RJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t g = blockIdx.x;
-    if (g >= B.totalGroups) return;
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f; /* block-uniform, once per block */
+    const AbY2RFrame & F = B.frame[f];                                         /* invariant for the life of the block */
+    const uint32_t gStride = F.blocks;
+    uint32_t g = blockIdx.x - F.blockStart;
+    if (g >= F.groups) return;
     TileIn<C> cur, nxt;
-    uint32_t f = frame_of_group<C>(B, g);
-    uint32_t tile = (g - B.frame[f].groupStart) * kWarps + warp;
-    bool live = tile < B.frame[f].tiles; /* the last group of a frame may be partial */
-    uint32_t unit = 0, x0 = 0;
+    uint32_t tile = g * kWarps + warp;
+    bool live = tile < F.tiles; /* the last group of a frame may be partial */
+    uint32_t x0 = 0;
     TileRows<C> R;
     R.any = false;
     bool full = false;
     if (live) {
-        unit = tile / B.frame[f].tilesX;
-        x0 = (tile - unit * B.frame[f].tilesX) * kTile;
-        R = tile_rows<C>(J, B.frame[f], unit);
-        full = (x0 + kTile <= B.frame[f].width);
+        const uint32_t unit = tile / F.tilesX;
+        x0 = (tile - unit * F.tilesX) * kTile;
+        R = tile_rows<C>(J, F, unit);
+        full = (x0 + kTile <= F.width);
         if (R.any) {
-            if (full) load_tile<C, true>(J, B.frame[f], R, x0, lane, cur);
-            else load_tile<C, false>(J, B.frame[f], R, x0, lane, cur);
+            if (full) load_tile<C, true>(J, F, R, x0, lane, cur);
+            else load_tile<C, false>(J, F, R, x0, lane, cur);
         }
     }
     while (true) {
-        const uint32_t ng = g + gridDim.x;
-        const bool more = ng < B.totalGroups; /* block-uniform */
-        uint32_t nf = f, nx0 = 0;
+        const uint32_t ng = g + gStride;
+        const bool more = ng < F.groups; /* block-uniform */
+        uint32_t nx0 = 0;
         bool nlive = false, nfull = false;
         TileRows<C> NR;
         NR.any = false;
         if (more) {
-            nf = frame_of_group<C>(B, ng);
-            const uint32_t ntile = (ng - B.frame[nf].groupStart) * kWarps + warp;
-            nlive = ntile < B.frame[nf].tiles;
+            const uint32_t ntile = ng * kWarps + warp;
+            nlive = ntile < F.tiles;
             if (nlive) {
-                const uint32_t nunit = ntile / B.frame[nf].tilesX;
-                nx0 = (ntile - nunit * B.frame[nf].tilesX) * kTile;
-                NR = tile_rows<C>(J, B.frame[nf], nunit);
-                nfull = (nx0 + kTile <= B.frame[nf].width);
+                const uint32_t nunit = ntile / F.tilesX;
+                nx0 = (ntile - nunit * F.tilesX) * kTile;
+                NR = tile_rows<C>(J, F, nunit);
+                nfull = (nx0 + kTile <= F.width);
                 if (NR.any) {
-                    if (nfull) load_tile<C, true>(J, B.frame[nf], NR, nx0, lane, nxt);
-                    else load_tile<C, false>(J, B.frame[nf], NR, nx0, lane, nxt);
+                    if (nfull) load_tile<C, true>(J, F, NR, nx0, lane, nxt);
+                    else load_tile<C, false>(J, F, NR, nx0, lane, nxt);
                 }
             }
         }
         if (live && R.any) {
-            if (full) convert_store_tile<C, true>(J, B.frame[f], R, x0, lane, cur);
-            else convert_store_tile<C, false>(J, B.frame[f], R, x0, lane, cur);
+            if (full) convert_store_tile<C, true>(J, F, R, x0, lane, cur);
+            else convert_store_tile<C, false>(J, F, R, x0, lane, cur);
         }
         if (!more) break;
         cur = nxt;
         g = ng;
-        f = nf;
         live = nlive;
         x0 = nx0;
         R = NR;
         full = nfull;
     }
+}
+
+/* share `blocksWanted` blocks among the frames in proportion to their group counts (every frame gets at least one) */
+template <class FrameT>
+static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups, uint32_t blocksWanted)
+{
+    uint32_t start = 0;
+    for (uint32_t f = 0; f < n; ++f) {
+        uint64_t share = ((uint64_t)frames[f].groups * blocksWanted + totalGroups - 1) / (totalGroups ? totalGroups : 1);
+        if (share < 1) share = 1;
+        if (share > frames[f].groups) share = frames[f].groups ? frames[f].groups : 1;
+        frames[f].blockStart = start;
+        frames[f].blocks = (uint32_t)share;
+        start += (uint32_t)share;
+    }
+    return start;
 }
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
@@ -522,10 +531,9 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
         if (CHROMA == CH_BIL420) units = (F.rowEnd >> 1) - (F.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
         F.tilesX = (F.width + kTile - 1) / kTile;
         F.tiles = F.tilesX * units;
-        F.groupStart = groups;
-        groups += (F.tiles + kWarps - 1) / kWarps;
+        F.groups = (F.tiles + kWarps - 1) / kWarps;
+        groups += F.groups;
     }
-    B.totalGroups = groups;
     static int resident = 0; /* blocks that fit on the whole device at once (per instantiation) */
     if (!resident) {
         int dev = 0, sms = 0, perSm = 0;
@@ -535,9 +543,9 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
     }
     /* few groups per resident block -> one group per block (balance beats prefetch); many -> persistent */
-    uint32_t blocks = groups;
-    if (groups >= 4u * (uint32_t)resident) blocks = (uint32_t)resident;
-    y2r_fast_kernel<C><<<blocks, kWarps * 32, 0, st>>>(B);
+    const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
+    B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, wanted);
+    y2r_fast_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
     return 1;
 }
 
@@ -632,7 +640,7 @@ static int launch_y2r_fast_typed(const AbY2RJob * jobs, uint32_t n, cudaStream_t
         F.uRB = swap ? S.vRB : S.uRB;
         F.vRB = swap ? S.uRB : S.vRB;
         F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
-        F.tilesX = F.tiles = F.groupStart = F.pad = 0;
+        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = F.pad = 0;
     }
     const bool afirst = J.alphaFirst != 0;
     const int nch = J.nChan;
