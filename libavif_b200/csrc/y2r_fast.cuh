@@ -505,14 +505,37 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
 template <class FrameT>
 static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups, uint32_t blocksWanted)
 {
+    /* floor shares (>= 1 block per frame, <= its group count), then hand the remaining blocks to the frames with the most
+     * groups per block; the total never exceeds blocksWanted (as long as n <= blocksWanted), so every block of a persistent
+     * launch is resident from the start */
+    if (totalGroups == 0) totalGroups = 1;
+    uint32_t used = 0;
+    for (uint32_t f = 0; f < n; ++f) {
+        uint64_t share = (uint64_t)frames[f].groups * blocksWanted / totalGroups;
+        if (share < 1) share = 1;
+        if (share > frames[f].groups && frames[f].groups) share = frames[f].groups;
+        frames[f].blocks = (uint32_t)share;
+        used += (uint32_t)share;
+    }
+    while (used < blocksWanted) {
+        uint32_t best = n;
+        uint64_t bestLoad = 0;
+        for (uint32_t f = 0; f < n; ++f) {
+            if (frames[f].blocks >= frames[f].groups) continue;
+            const uint64_t load = ((uint64_t)frames[f].groups << 16) / frames[f].blocks;
+            if (best == n || load > bestLoad) {
+                best = f;
+                bestLoad = load;
+            }
+        }
+        if (best == n) break;
+        ++frames[best].blocks;
+        ++used;
+    }
     uint32_t start = 0;
     for (uint32_t f = 0; f < n; ++f) {
-        uint64_t share = ((uint64_t)frames[f].groups * blocksWanted + totalGroups - 1) / (totalGroups ? totalGroups : 1);
-        if (share < 1) share = 1;
-        if (share > frames[f].groups) share = frames[f].groups ? frames[f].groups : 1;
         frames[f].blockStart = start;
-        frames[f].blocks = (uint32_t)share;
-        start += (uint32_t)share;
+        start += frames[f].blocks;
     }
     return start;
 }
