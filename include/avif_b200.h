@@ -327,6 +327,10 @@ AVIF_B200_API const char * avifB200LastKernelName(void);
 AVIF_B200_API size_t avifB200VerifiedDivisorCount(void);
 AVIF_B200_API uint32_t avifB200VerifiedDivisorBits(size_t index);
 AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches);
+/* Sample and channel codes are normalised with a 2-operation quotient that is exact for integer numerators in
+ * [-65536, 65535] (csrc/pixel_math.cuh: div_int).  The host proves that by exhaustion for every divisor it meets; this
+ * re-runs the proof on the device.  hostVerdict receives the host's result (1 = proven). */
+AVIF_B200_API avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
 /* Alpha unmultiply divides three colour values by the same normalised alpha; the kernels share one reciprocal
  * between the three IEEE divisions (pixel_math.cuh: rcp_refined).  Re-checks that against the hardware's IEEE division:
  * sampledColour == 0: every (colour code, alpha code) pair of the given depth; != 0: random colour values in [0,1]. */

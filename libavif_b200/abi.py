@@ -152,6 +152,7 @@ PROTOTYPES = {
     "avifB200VerifiedDivisorCount": (C.c_size_t, []),
     "avifB200VerifiedDivisorBits": (C.c_uint32, [C.c_size_t]),
     "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
+    "avifB200SelfTestIntDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "avifB200SelfTestAlphaDivision": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "avifB200DeviceAvailable": (C.c_int, []),
     "avifB200Version": (C.c_char_p, []),

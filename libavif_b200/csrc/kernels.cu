@@ -755,8 +755,8 @@ __global__ void __launch_bounds__(256) alpha_kernel(const __grid_constant__ AbAl
         const uint32_t srcMax = (1u << J.srcDepth) - 1, dstMax = (1u << J.dstDepth) - 1;
         AbDiv sd;
         sd.d = (float)srcMax;
-        sd.r = 0.0f;
-        sd.exact = 0;
+        sd.r = sd.rh = sd.rl = 0.0f;
+        sd.exact = sd.intExact = 0;
         st_chan<DT>(d, alpha_rescale(a, sd, (float)dstMax, dstMax));
     }
 }
@@ -834,6 +834,15 @@ __global__ void __launch_bounds__(256) div_selftest_kernel(float d, float r, uns
         if (__float_as_uint(fast) != __float_as_uint(__fdiv_rn(x, d))) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+/* self-test of div_int: every integer numerator in [-65536, 65535] */
+__global__ void __launch_bounds__(256) int_div_selftest_kernel(AbDiv dv, unsigned long long * mismatches)
+{
+    const int x = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 65536;
+    if (x > 65535) return;
+    const float xf = (float)x;
+    if (__float_as_uint(div_int(xf, dv)) != __float_as_uint(__fdiv_rn(xf, dv.d))) atomicAdd(mismatches, 1ull);
 }
 
 /* self-test of the shared-reciprocal division (pixel_math.cuh: rcp_refined / div_by_rcp) against __fdiv_rn:
@@ -1142,6 +1151,23 @@ int abDivSelfTest(float d, unsigned long long * mismatches, void * stream)
     err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
     if (!err) {
         div_selftest_kernel<<<148 * 16, 256, 0, st>>>(d, 1.0f / d, dev);
+        err = finish_launch();
+    }
+    if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);
+    if (!err) err = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return err;
+}
+
+int abIntDivSelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long * dev = nullptr;
+    int err = (int)cudaMalloc((void **)&dev, sizeof(*dev));
+    if (err) return err;
+    err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
+    if (!err) {
+        int_div_selftest_kernel<<<131072 / 256, 256, 0, st>>>(*dv, dev);
         err = finish_launch();
     }
     if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);

@@ -28,10 +28,13 @@ enum { AB_MUL_NONE = 0, AB_MUL_FLOAT_MUL = 1, AB_MUL_FLOAT_UNMUL = 2, AB_MUL_INT
  * `exact` is set by the host only for divisors whose (x,d) domain has been verified exhaustively to give the
  * IEEE-754 correctly rounded quotient (tests/test_division.py); otherwise the kernels use __fdiv_rn. */
 typedef struct AbDiv {
-    float d;   /* divisor */
-    float r;   /* RN(1/d) */
-    int exact; /* 1: the 3-op sequence is proven == x/d on this call's domain */
-    int pad;
+    float d;      /* divisor */
+    float r;      /* RN(1/d) */
+    float rh, rl; /* 1/d in double precision, split into two floats: rh = RN(1/d), rl = RN(1/d - rh) */
+    int exact;    /* 1: q=x*r; e=fma(-q,d,x); q'=fma(e,r,q) is proven == x/d for every float x (verified_divisors.h) */
+    int intExact; /* 1: fma(x, rh, RN(x*rl)) is proven == x/d for every INTEGER x in [-65536, 65535] (checked by exhaustion
+                     on the host when the divisor is first seen: shim.c divisorIntVerified) -- the 2-op form used to
+                     normalise sample codes */
 } AbDiv;
 
 typedef struct AbY2RJob {
@@ -191,6 +194,7 @@ int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t 
                     uint32_t dstH, uint32_t bytesPerSample, void * stream);
 /* exhaustive device check of div_const's fast form for divisor d (counts x whose result differs from x/d) */
 int abDivSelfTest(float d, unsigned long long * mismatches, void * stream);
+int abIntDivSelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream);
 int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, void * stream);
 /* number of kernel launches issued by the calling thread through the functions above */
 uint64_t abLaunchCount(void);

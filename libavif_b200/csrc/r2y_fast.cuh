@@ -183,14 +183,14 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             constexpr int c0 = C::AFIRST ? 1 : 0;
-            const float x0 = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
-            const float gg = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
-            const float x2 = rdivx(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
+            const float x0 = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
+            const float gg = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
+            const float x2 = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
             float R = swap ? x2 : x0, G = gg, B = swap ? x0 : x2;
             float am = 0.0f;
             if (C::NCH == 4) am = chan_magic<RT>(in.w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
             if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
-                const float a = rdivx(__fsub_rn(am, magicOne), J.rgbMaxDiv);
+                const float a = div_int(__fsub_rn(am, magicOne), J.rgbMaxDiv);
                 if (C::AM == AB_MUL_FLOAT_MUL) {
                     const bool scale = (a < 1.0f); /* a == 0: the products are exact zeros as well */
                     R = scale ? __fmul_rn(R, a) : R;
@@ -428,7 +428,7 @@ static bool rfast_eligible(const AbR2YJob & J)
 {
     if (J.mode != AB_MODE_COEFF || J.isGray) return false;
     if (J.nChan != 3 && J.nChan != 4) return false;
-    if (!J.rgbMaxDiv.exact) return false;
+    if (!J.rgbMaxDiv.intExact) return false;
     if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return false;
     if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return false;

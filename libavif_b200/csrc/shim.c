@@ -157,6 +157,7 @@ static avifResult cudaToResult(int err)
     } while (0)
 
 static avifResult ctxInit(void);
+static AbDiv makeIntDiv(float d);
 
 int avifB200DeviceAvailable(void)
 {
@@ -191,6 +192,23 @@ avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches)
     if (res != AVIF_RESULT_OK) return res;
     unsigned long long bad = 0;
     AB_CUDA(abDivSelfTest(d, &bad, tls.stream));
+    *mismatches = bad;
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches)
+{
+    float d;
+    memcpy(&d, &divisorBits, sizeof(d));
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    const int saved = tlsExactDivision;
+    tlsExactDivision = 0;
+    AbDiv dv = makeIntDiv(d);
+    tlsExactDivision = saved;
+    if (hostVerdict) *hostVerdict = dv.intExact;
+    unsigned long long bad = 0;
+    AB_CUDA(abIntDivSelfTest(&dv, &bad, tls.stream));
     *mismatches = bad;
     return AVIF_RESULT_OK;
 }
@@ -519,13 +537,56 @@ static int divisorVerified(float d)
     return 0;
 }
 
+/* Proof by exhaustion, on the host, that fma(x, rh, RN(x*rl)) == x/d for every integer x in [-65536, 65535]: sample codes
+ * minus their bias, and channel codes, are such integers.  131072 fmaf() calls (< 1 ms), cached per thread. */
+static int divisorIntVerified(float d, float rh, float rl)
+{
+    enum { kCache = 16 };
+    static _Thread_local struct { uint32_t bits; int ok; int used; } cache[kCache];
+    uint32_t bits;
+    memcpy(&bits, &d, sizeof(bits));
+    for (int k = 0; k < kCache; ++k) {
+        if (cache[k].used && cache[k].bits == bits) return cache[k].ok;
+    }
+    int ok = isfinite(d) && d != 0.0f;
+    for (int x = -65536; ok && x <= 65535; ++x) {
+        const float xf = (float)x;
+        const float fast = fmaf(xf, rh, xf * rl);
+        const float ref = xf / d;
+        uint32_t a, b;
+        memcpy(&a, &fast, 4);
+        memcpy(&b, &ref, 4);
+        if (a != b) ok = 0;
+    }
+    for (int k = 0; k < kCache; ++k) {
+        if (!cache[k].used) {
+            cache[k].used = 1;
+            cache[k].bits = bits;
+            cache[k].ok = ok;
+            break;
+        }
+    }
+    return ok;
+}
+
 static AbDiv makeDiv(float d)
 {
     AbDiv v;
     v.d = d;
     v.r = 1.0f / d;
+    const double inv = 1.0 / (double)d;
+    v.rh = (float)inv;
+    v.rl = (float)(inv - (double)v.rh);
     v.exact = !tlsExactDivision && divisorVerified(d);
-    v.pad = 0;
+    v.intExact = 0;
+    return v;
+}
+
+/* divisors that only ever see integer numerators (code ranges, 2^depth - 1) */
+static AbDiv makeIntDiv(float d)
+{
+    AbDiv v = makeDiv(d);
+    v.intExact = !tlsExactDivision && divisorIntVerified(d, v.rh, v.rl);
     return v;
 }
 
@@ -700,17 +761,17 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     job.yuvMaxF = (float)s.yuvMax;
     job.rgbMaxF = s.rgbMaxF;
     job.biasY = s.biasY;
-    job.rangeY = makeDiv(s.rangeY);
+    job.rangeY = makeIntDiv(s.rangeY);
     if (s.mode == AB_MODE_IDENTITY) { /* chroma shares the luma table, :587-589 */
         job.biasUV = s.biasY;
-        job.rangeUV = makeDiv(s.rangeY);
+        job.rangeUV = makeIntDiv(s.rangeY);
     } else {
         job.biasUV = s.biasUV;
-        job.rangeUV = makeDiv(s.rangeUV);
+        job.rangeUV = makeIntDiv(s.rangeUV);
     }
     job.kg = makeDiv(s.kg);
-    job.yuvMaxDiv = makeDiv((float)s.yuvMax);
-    job.rgbMaxDiv = makeDiv(s.rgbMaxF);
+    job.yuvMaxDiv = makeIntDiv((float)s.yuvMax);
+    job.rgbMaxDiv = makeIntDiv(s.rgbMaxF);
     job.c1 = 2 * (1 - s.kr);
     job.c2 = 2 * (1 - s.kb);
     job.c3 = s.kr * (1 - s.kr);
@@ -1029,7 +1090,7 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
     job.kb = s.kb;
     job.du = makeDiv(2 * (1 - s.kb));
     job.dv = makeDiv(2 * (1 - s.kr));
-    job.rgbMaxDiv = makeDiv(s.rgbMaxF);
+    job.rgbMaxDiv = makeIntDiv(s.rgbMaxF);
     job.magicK = 0x4B000000u;
     job.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
     job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);

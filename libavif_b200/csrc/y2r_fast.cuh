@@ -129,7 +129,7 @@ template <typename T>
 __device__ __forceinline__ float norm_magic(float mf, float magicMax, float magicBias, const AbDiv & range)
 {
     if (sizeof(T) == 2) mf = fminf(mf, magicMax); /* clamp garbage high bits of 16-bit containers */
-    return divx(__fsub_rn(mf, magicBias), range);
+    return div_int(__fsub_rn(mf, magicBias), range); /* integer numerator: 2-op exact quotient */
 }
 
 /* (T)(0.5f + c*max) as the bit pattern of 2^23 + code (low 16 bits = code) */
@@ -346,7 +346,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
             if (NEED_A) am = magic_sample<YT>(in.aw[r], t, K);
             if (C::AM == AB_MUL_FLOAT_MUL || C::AM == AB_MUL_FLOAT_UNMUL) { /* ref: src/reformat.c:894-947 */
                 const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
-                const float Ac = clamp01f(divx(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
+                const float Ac = clamp01f(div_int(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
                 if (C::AM == AB_MUL_FLOAT_MUL) {
                     const bool scale = (Ac < 1.0f); /* Ac == 0 gives exact zeros through the multiply as well */
                     Rv = scale ? __fmul_rn(Rv, Ac) : Rv;
@@ -439,7 +439,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
  * long_scoreboard + 20 % store-drain stalls on the 8K case with one tile per warp).  Tiles are row-major, so concurrently
  * running warps touch adjacent 256-pixel spans.  (Shared-memory staged stores measured slower: profiles/r01_variants.md.) */
 template <class C>
-__global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
+__global__ void __launch_bounds__(kWarps * 32, 3) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
 {
     const AbY2RJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -449,6 +449,26 @@ __global__ void __launch_bounds__(kWarps * 32, (C::CHROMA == CH_BIL420) ? 2 : 3)
     const uint32_t gStride = F.blocks;
     uint32_t g = blockIdx.x - F.blockStart;
     if (g >= F.groups) return;
+    if (C::CHROMA == CH_BIL420) {
+        /* the two-row bilinear tile already keeps ~100 values live: a second (prefetch) register set would cost a whole
+         * resident block per SM and measured no gain (profiles/r01_variants.md) -- plain persistent loop */
+        for (; g < F.groups; g += gStride) {
+            const uint32_t t = g * kWarps + warp;
+            if (t >= F.tiles) continue; /* warp-uniform */
+            const uint32_t unit = t / F.tilesX, tx0 = (t - unit * F.tilesX) * kTile;
+            const TileRows<C> TR = tile_rows<C>(J, F, unit);
+            if (!TR.any) continue;
+            TileIn<C> in;
+            if (tx0 + kTile <= F.width) {
+                load_tile<C, true>(J, F, TR, tx0, lane, in);
+                convert_store_tile<C, true>(J, F, TR, tx0, lane, in);
+            } else {
+                load_tile<C, false>(J, F, TR, tx0, lane, in);
+                convert_store_tile<C, false>(J, F, TR, tx0, lane, in);
+            }
+        }
+        return;
+    }
     TileIn<C> cur, nxt;
     uint32_t tile = g * kWarps + warp;
     bool live = tile < F.tiles; /* the last group of a frame may be partial */
@@ -605,9 +625,9 @@ static bool fast_eligible(const AbY2RJob & J)
     if (J.nChan != 3 && J.nChan != 4) return false;
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return false;
-    if (!J.rangeY.exact || !J.rangeUV.exact || !J.kg.exact) return false;
+    if (!J.rangeY.intExact || !J.rangeUV.intExact || !J.kg.exact) return false;
     if ((J.alphaMul == AB_MUL_INT_PREMUL) && !J.rgbMaxDiv.exact) return false;
-    if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.exact) return false;
+    if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
     const bool sub = (J.chroma != AB_CHROMA_FULL);
     uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;

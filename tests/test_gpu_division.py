@@ -25,3 +25,21 @@ def test_shared_reciprocal_alpha_division(gpu_product, depth, sampled):
     bad = ctypes.c_uint64(1)
     assert gpu_product.avifB200SelfTestAlphaDivision(depth, sampled, ctypes.byref(bad)) == 0
     assert bad.value == 0
+
+
+def test_integer_numerator_division_on_device(gpu_product):
+    """div_int (2-op quotient for sample / channel codes): host proof and device re-check agree, for every divisor the path
+    uses: code ranges of every depth x range, and 2^depth - 1."""
+    import struct
+    ds = [255, 1023, 4095, 65535] + [219 << k for k in (0, 2, 4, 8)] + [224 << k for k in (0, 2, 4, 8)]
+    for d in ds:
+        bits = struct.unpack("<I", struct.pack("<f", float(d)))[0]
+        verdict, bad = ctypes.c_int(-1), ctypes.c_uint64(99)
+        assert gpu_product.avifB200SelfTestIntDivisor(bits, ctypes.byref(verdict), ctypes.byref(bad)) == 0
+        assert verdict.value == 1 and bad.value == 0, (d, verdict.value, bad.value)
+    # host verdict and device count must agree for arbitrary divisors too (whatever the verdict is)
+    for d in (3.0, 0.7152, 1000.0, 12345.678, 7.0):
+        bits = struct.unpack("<I", struct.pack("<f", d))[0]
+        verdict, bad = ctypes.c_int(-1), ctypes.c_uint64(99)
+        assert gpu_product.avifB200SelfTestIntDivisor(bits, ctypes.byref(verdict), ctypes.byref(bad)) == 0
+        assert (verdict.value == 1) == (bad.value == 0), (d, verdict.value, bad.value)
