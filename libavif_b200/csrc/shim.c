@@ -133,7 +133,7 @@ int avifFullToLimitedUV(uint32_t depth, int v) { return fullToLim(depth, 1, v); 
 typedef struct AbCtx {
     int ready;
     cudaStream_t stream;           /* kernels (and everything, on the unpipelined path) */
-    cudaStream_t up, down;         /* host->device / device->host copy streams of the band pipeline */
+    cudaStream_t up, up2, down;    /* host->device (two, alternating bands) / device->host copy streams of the band pipeline */
     cudaEvent_t evUp[AB_MAX_BANDS], evKernel[AB_MAX_BANDS];
     uint8_t * arena;
     size_t arenaCap;
@@ -244,6 +244,7 @@ static avifResult ctxInit(void)
     if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR; /* no CPU fallback by design */
     AB_CUDA(cudaStreamCreateWithFlags(&tls.stream, cudaStreamNonBlocking));
     AB_CUDA(cudaStreamCreateWithFlags(&tls.up, cudaStreamNonBlocking));
+    AB_CUDA(cudaStreamCreateWithFlags(&tls.up2, cudaStreamNonBlocking));
     AB_CUDA(cudaStreamCreateWithFlags(&tls.down, cudaStreamNonBlocking));
     for (int k = 0; k < AB_MAX_BANDS; ++k) {
         AB_CUDA(cudaEventCreateWithFlags(&tls.evUp[k], cudaEventDisableTiming));
@@ -361,6 +362,18 @@ static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cuda
 /* Band pipeline of the host-pointer path: the frame is cut into row bands; band b's planes go up on `up`, its
  * kernel runs on `stream` once they (and, for vertical chroma blending, the next band's) have landed, its result
  * goes down on `down` -- PCIe is full duplex, so a frame costs max(upload, download) instead of their sum. */
+/* upload stream of band b: alternating between two streams keeps two host->device copies in flight (small uploads are
+ * latency-bound on PCIe reads, profiles/r01_variants.md); AVIF_B200_UP_STREAMS=1 restores the single stream */
+static cudaStream_t upStream(int band)
+{
+    static _Thread_local int nUp = 0;
+    if (!nUp) {
+        const char * e = getenv("AVIF_B200_UP_STREAMS");
+        nUp = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return (nUp == 2 && (band & 1)) ? tls.up2 : tls.up;
+}
+
 static int planBands(uint32_t height, size_t frameBytes, uint32_t bandRows[AB_MAX_BANDS + 1])
 {
     static _Thread_local size_t bandBytes = 0;
@@ -901,11 +914,12 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
         for (int b = 0; b < nb; ++b) {
             const uint32_t r0 = bands[b], r1 = bands[b + 1];
             const uint32_t c0 = r0 >> s.shiftY, c1 = (uint32_t)(((uint64_t)r1 + s.shiftY) >> s.shiftY);
-            AB_CUDA(regionUpload(&ry, r0, r1, tls.up));
-            AB_CUDA(regionUpload(&ru, c0, c1, tls.up));
-            AB_CUDA(regionUpload(&rv, c0, c1, tls.up));
-            AB_CUDA(regionUpload(&ra, r0, r1, tls.up));
-            AB_CUDA(cudaEventRecord(tls.evUp[b], tls.up));
+            cudaStream_t us = upStream(b);
+            AB_CUDA(regionUpload(&ry, r0, r1, us));
+            AB_CUDA(regionUpload(&ru, c0, c1, us));
+            AB_CUDA(regionUpload(&rv, c0, c1, us));
+            AB_CUDA(regionUpload(&ra, r0, r1, us));
+            AB_CUDA(cudaEventRecord(tls.evUp[b], us));
         }
         for (int b = 0; b < nb; ++b) {
             const int need = (b + lookAhead < nb) ? b + lookAhead : nb - 1;
@@ -1197,8 +1211,9 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
         const int nb = planBands(image->height, frameBytes, bands);
         const char * pname = "";
         for (int b = 0; b < nb; ++b) {
-            AB_CUDA(regionUpload(&rrgb, bands[b], bands[b + 1], tls.up));
-            AB_CUDA(cudaEventRecord(tls.evUp[b], tls.up));
+            cudaStream_t us = upStream(b);
+            AB_CUDA(regionUpload(&rrgb, bands[b], bands[b + 1], us));
+            AB_CUDA(cudaEventRecord(tls.evUp[b], us));
         }
         for (int b = 0; b < nb; ++b) {
             const uint32_t r0 = bands[b], r1 = bands[b + 1];
