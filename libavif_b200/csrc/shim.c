@@ -362,14 +362,14 @@ static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cuda
 /* Band pipeline of the host-pointer path: the frame is cut into row bands; band b's planes go up on `up`, its
  * kernel runs on `stream` once they (and, for vertical chroma blending, the next band's) have landed, its result
  * goes down on `down` -- PCIe is full duplex, so a frame costs max(upload, download) instead of their sum. */
-/* upload stream of band b: alternating between two streams keeps two host->device copies in flight (small uploads are
- * latency-bound on PCIe reads, profiles/r01_variants.md); AVIF_B200_UP_STREAMS=1 restores the single stream */
+/* upload stream of band b.  One stream by default: alternating bands between two upload streams (AVIF_B200_UP_STREAMS=2)
+ * measured 10 % slower end to end on this host (profiles/r01_variants.md) */
 static cudaStream_t upStream(int band)
 {
     static _Thread_local int nUp = 0;
     if (!nUp) {
         const char * e = getenv("AVIF_B200_UP_STREAMS");
-        nUp = (e && atoi(e) == 1) ? 1 : 2;
+        nUp = (e && atoi(e) == 2) ? 2 : 1;
     }
     return (nUp == 2 && (band & 1)) ? tls.up2 : tls.up;
 }
