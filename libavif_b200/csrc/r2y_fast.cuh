@@ -57,6 +57,14 @@ __device__ __forceinline__ float quant_yuv_magic(float v, float range, float bia
     return __fadd_rz(fminf(fmaxf(t, 0.0f), hiLimit), 8388608.0f); /* floor+clamp == trunc(clamp(t, 0, max + 0.5)) */
 }
 
+/* luma: every term of Y = kr*R + kg*G + kb*B is >= 0 for the matrices the specialised kernels accept (their divisors are
+ * whitelisted, all with kr, kg, kb >= 0), so t >= bias + 0.5 > 0 and only the upper clamp can act */
+__device__ __forceinline__ float quant_luma_magic(float v, float range, float bias, float hiLimit)
+{
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+    return __fadd_rz(fminf(t, hiLimit), 8388608.0f);
+}
+
 template <typename YT>
 __device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8])
 {
@@ -196,17 +204,23 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
                     R = scale ? __fmul_rn(R, a) : R;
                     G = scale ? __fmul_rn(G, a) : G;
                     B = scale ? __fmul_rn(B, a) : B;
-                } else if (a == 0.0f) {
-                    R = G = B = 0.0f;
-                } else if (a < 1.0f) {
-                    const float r1 = rcp_refined(a);
-                    R = min1(div_by_rcp(R, a, r1));
-                    G = min1(div_by_rcp(G, a, r1));
-                    B = min1(div_by_rcp(B, a, r1));
+                } else {
+                    /* branch-free so that the 8 pixels of the lane interleave freely: a == 0 -> 0, 0 < a < 1 -> min(c/a, 1),
+                     * a >= 1 -> untouched.  The divisor is forced to 1 when no division is wanted (x/1 == x exactly). */
+                    const bool zero = (a == 0.0f), need = (a > 0.0f) && (a < 1.0f);
+                    const float d = need ? a : 1.0f;
+                    const float r1 = rcp_refined(d);
+                    R = zero ? 0.0f : R;
+                    G = zero ? 0.0f : G;
+                    B = zero ? 0.0f : B;
+                    const float qR = min1(div_by_rcp(R, d, r1)), qG = min1(div_by_rcp(G, d, r1)), qB = min1(div_by_rcp(B, d, r1));
+                    R = need ? qR : R;
+                    G = need ? qG : G;
+                    B = need ? qB : B;
                 }
             }
             const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
-            yq[t] = quant_yuv_magic(Y, J.rangeY, J.biasY, hiLimit);
+            yq[t] = quant_luma_magic(Y, J.rangeY, J.biasY, hiLimit);
             if (C::SUB != SUB_400) {
                 const float U = rdivx(__fsub_rn(B, Y), J.du);
                 const float V = rdivx(__fsub_rn(R, Y), J.dv);

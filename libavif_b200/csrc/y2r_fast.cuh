@@ -352,13 +352,18 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                     Rv = scale ? __fmul_rn(Rv, Ac) : Rv;
                     Gv = scale ? __fmul_rn(Gv, Ac) : Gv;
                     Bv = scale ? __fmul_rn(Bv, Ac) : Bv;
-                } else if (Ac == 0.0f) {
-                    Rv = Gv = Bv = 0.0f;
-                } else if (Ac < 1.0f) {
-                    const float r1 = rcp_refined(Ac);
-                    Rv = min1(div_by_rcp(Rv, Ac, r1));
-                    Gv = min1(div_by_rcp(Gv, Ac, r1));
-                    Bv = min1(div_by_rcp(Bv, Ac, r1));
+                } else {
+                    /* branch-free (see r2y_fast.cuh): Ac == 0 -> 0, 0 < Ac < 1 -> min(c/Ac, 1), Ac == 1 -> untouched */
+                    const bool zero = (Ac == 0.0f), need = (Ac > 0.0f) && (Ac < 1.0f);
+                    const float d = need ? Ac : 1.0f;
+                    const float r1 = rcp_refined(d);
+                    Rv = zero ? 0.0f : Rv;
+                    Gv = zero ? 0.0f : Gv;
+                    Bv = zero ? 0.0f : Bv;
+                    const float qR = min1(div_by_rcp(Rv, d, r1)), qG = min1(div_by_rcp(Gv, d, r1)), qB = min1(div_by_rcp(Bv, d, r1));
+                    Rv = need ? qR : Rv;
+                    Gv = need ? qG : Gv;
+                    Bv = need ? qB : Bv;
                 }
             }
             float qr = quant_magic(Rv, J.rgbMaxF), qg = quant_magic(Gv, J.rgbMaxF), qb = quant_magic(Bv, J.rgbMaxF);
