@@ -137,3 +137,22 @@ def test_grid_plane_staging(gpu_product, fmt, depth):
         dw, dh = dst.plane_dims(p)
         exp = np.pad(s, ((0, dh - s.shape[0]), (0, dw - s.shape[1])), mode="edge")
         assert (dst.plane_samples(p) == exp).all(), f"plane {p}"
+
+
+def test_concurrent_host_threads(gpu_product, oracle):
+    """The entry points are re-entrant (the reference is exercised under TSan with concurrent calls on different images):
+    all library state is thread-local.  8 host threads convert different frames at once, host and device pointers mixed."""
+    import concurrent.futures as cf
+    specs = util.random_y2r_specs(64, seed=77, sizes=[(640, 48), (1921, 9), (264, 33), (96, 96)])
+    want = [util.yuv_to_rgb(oracle, sp, 900 + k) for k, sp in enumerate(specs)]
+
+    def work(k):
+        dev = "cuda:0" if k % 3 == 0 else None
+        return util.yuv_to_rgb(gpu_product, specs[k], 900 + k, device=dev)
+
+    with cf.ThreadPoolExecutor(max_workers=8) as pool:
+        got = list(pool.map(work, range(len(specs))))
+    for k, (w, g) in enumerate(zip(want, got)):
+        assert w[0] == g[0], specs[k].ident()
+        if w[0] == 0:
+            assert util.first_mismatch(w[1], g[1]) is None, specs[k].ident()
