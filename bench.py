@@ -479,6 +479,29 @@ def run_extras(lib, dev, sptr, stream, peak_gbs):
                      "alg_bytes_per_px": bpp, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
         del fr
         torch.cuda.empty_cache()
+    # C4: the 16 cells (1920x1080 RGBA8) of the 4x4 grid -> 4:2:0 8-bit BT.601 full + alpha, one batched RGB->YUV launch
+    cells = []
+    for f in range(16):
+        rgb = RGBImage(1920, 1080, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(400 + f)
+        rgb.buf._t[:rgb.buf.nbytes].copy_(torch.randint(0, 256, (rgb.buf.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
+        cells.append((YUVImage(1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 1, 6, alpha=True, device=dev), rgb))
+    from libavif_b200.images import pointer_array
+    pi, pr = pointer_array([c[0] for c in cells]), pointer_array([c[1] for c in cells])
+    assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    gbs = 6.5 * 16 * 1920 * 1080 / (ms * 1e-3) / 1e9
+    out["C4_16_cells_1080p_RGBA8_to_420_8b_alpha"] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": 16, "us_per_frame_per_image_launches": None,
+                                                       "us_per_frame": ms * 1e3 / 16, "us_per_canvas": ms * 1e3, "Mpixels_per_s": 16 * 1920 * 1080 / (ms * 1e-3) / 1e6,
+                                                       "alg_bytes_per_px": 6.5, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
     return out
 
 

@@ -33,6 +33,10 @@ struct RCfg {
     static constexpr int AM = AM_; /* AB_MUL_NONE / FLOAT_MUL / FLOAT_UNMUL */
 };
 
+#ifndef AB_R2Y_NOPREFETCH420
+#define AB_R2Y_NOPREFETCH420 0 /* 1 was tried: the two-row tile then spills at 3 blocks/SM and gains nothing at 2 */
+#endif
+constexpr bool kR2YNoPrefetch420 = (AB_R2Y_NOPREFETCH420 != 0);
 constexpr int kRTile = 256;
 constexpr int kRWarps = 8;
 
@@ -297,7 +301,7 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
  * frame (one tile per warp); each warp loads its tile of the next group into a second register set before converting the
  * current one. */
 template <class C>
-__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
+__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420 && !kR2YNoPrefetch420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
 {
     constexpr int ROWS = RTileIn<C>::ROWS;
     const AbR2YJob & J = B.common;
@@ -308,6 +312,22 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420) ? 2 : 3) r2y
     const uint32_t gStride = F.blocks;
     uint32_t g = blockIdx.x - F.blockStart;
     if (g >= F.groups) return;
+    if (kR2YNoPrefetch420 && C::SUB == SUB_420) { /* two-row tiles: a second register set costs a resident block per SM */
+        for (; g < F.groups; g += gStride) {
+            const uint32_t t = g * kRWarps + warp;
+            if (t >= F.tiles) continue;
+            const uint32_t unit = t / F.tilesX, tx0 = (t - unit * F.tilesX) * kRTile, tj0 = F.rowBegin + unit * ROWS;
+            RTileIn<C> in;
+            if (tx0 + kRTile <= F.width) {
+                load_rtile<C, true>(J, F, tx0, tj0, lane, in);
+                convert_store_rtile<C, true>(J, F, tx0, tj0, lane, in);
+            } else {
+                load_rtile<C, false>(J, F, tx0, tj0, lane, in);
+                convert_store_rtile<C, false>(J, F, tx0, tj0, lane, in);
+            }
+        }
+        return;
+    }
     RTileIn<C> cur, nxt;
     uint32_t tile = g * kRWarps + warp;
     bool live = tile < F.tiles;
