@@ -37,6 +37,13 @@ struct RCfg {
 #define AB_R2Y_NOPREFETCH420 0 /* 1 was tried: the two-row tile then spills at 3 blocks/SM and gains nothing at 2 */
 #endif
 constexpr bool kR2YNoPrefetch420 = (AB_R2Y_NOPREFETCH420 != 0);
+/* 16-bit RGBA in, 4:2:0 out: one two-row tile is already 32 registers of input per lane, and a second (prefetched) set
+ * does not fit the 128-register budget of two resident blocks per SM without spilling -- those run the plain loop. */
+template <class C>
+struct RLoop {
+    static constexpr bool PLAIN = (C::SUB == SUB_420) && (kR2YNoPrefetch420 || (sizeof(typename C::RT) == 2 && C::NCH == 4));
+    static constexpr int MIN_BLOCKS = (C::SUB == SUB_420 && !kR2YNoPrefetch420) ? 2 : 3;
+};
 constexpr int kRTile = 256;
 constexpr int kRWarps = 8;
 
@@ -301,7 +308,7 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
  * frame (one tile per warp); each warp loads its tile of the next group into a second register set before converting the
  * current one. */
 template <class C>
-__global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420 && !kR2YNoPrefetch420) ? 2 : 3) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
+__global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_kernel(const __grid_constant__ AbR2YBatch B)
 {
     constexpr int ROWS = RTileIn<C>::ROWS;
     const AbR2YJob & J = B.common;
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(kRWarps * 32, (C::SUB == SUB_420 && !kR2YNoPre
     const uint32_t gStride = F.blocks;
     uint32_t g = blockIdx.x - F.blockStart;
     if (g >= F.groups) return;
-    if (kR2YNoPrefetch420 && C::SUB == SUB_420) { /* two-row tiles: a second register set costs a resident block per SM */
+    if (RLoop<C>::PLAIN) { /* two-row tiles: a second register set costs a resident block per SM */
         for (; g < F.groups; g += gStride) {
             const uint32_t t = g * kRWarps + warp;
             if (t >= F.tiles) continue;

@@ -18,6 +18,7 @@
 
 #include <cuda_runtime_api.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -178,6 +179,13 @@ void avifB200SetKernelPolicy(int policy)
     tlsExactDivision = (policy >> 1) & 1;
 }
 uint64_t avifB200KernelLaunchCount(void) { return abLaunchCount(); }
+/* AVIF_B200_TRACE_CALLS=1: report at process exit how much work went through the GPU; this is how an interposed
+ * (LD_PRELOAD) deployment shows that it is live (tests/test_gpu_dropin.py). */
+__attribute__((destructor)) static void abReportAtExit(void)
+{
+    const char * e = getenv("AVIF_B200_TRACE_CALLS");
+    if (e && e[0] == '1') fprintf(stderr, "avif_b200: kernel launches %llu\n", (unsigned long long)abLaunchCount());
+}
 void avifB200ResetKernelLaunchCount(void) { abLaunchCountReset(); }
 const char * avifB200LastKernelName(void) { return tls.lastKernel ? tls.lastKernel : ""; }
 

@@ -35,6 +35,21 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "reference_vectors.json")
     json.dump(out, open(path, "w"), indent=0)
     print("wrote", path, len(out["y2r"]), len(out["r2y"]))
+    tool_outputs()
+
+
+def tool_outputs():
+    """stdout of the reference's own stress tool (oracle/_ref/avifyuv = tests/avifyuv.c of the reference, linked
+    against the reference build), run natively on the CPU; tests/test_gpu_dropin.py replays the tool with the
+    B200 library preloaded and requires the same bytes."""
+    import subprocess
+    tool = os.path.join(ROOT, "oracle", "_ref", "avifyuv")
+    for mode, extra in (("rgb", []), ("limited", []), ("premultiply", ["-v"])):
+        text = subprocess.run([tool, "-m", mode, *extra], capture_output=True, check=True).stdout.decode()
+        if extra:  # drop the "[ n/ N]" progress lines, keep the per-depth drift histograms
+            text = "".join(l + "\n" for l in text.replace("\r", "\n").split("\n") if l and not l.startswith("["))
+        open(os.path.join(ROOT, "tests", "golden", f"avifyuv_{mode}.txt"), "w").write(text)
+        print("wrote avifyuv_%s.txt" % mode)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,75 @@
+"""Drop-in proof with the reference's own test program.
+
+`oracle/_ref/avifyuv` is the reference's conversion stress tool (tests/avifyuv.c), compiled from the reference
+tree where it lies and linked against the reference build `oracle/_ref/libavif_ref.so` (recipe: oracle/Makefile).
+Run with `LD_PRELOAD=libavif_b200.so`, every entry point declared in include/avif_b200.h is interposed by the
+B200 library while the rest of the tool (image allocation, printing) still comes from the reference build: that
+is exactly the situation of a libavif whose reformat path was replaced.  The tool's output must stay
+byte-identical to the output of the untouched reference, which is committed under tests/golden/avifyuv_*.txt
+(written by the native run in the build container; tests/golden/make_golden.py documents the commands).
+
+The binary is test infrastructure like the rest of oracle/_ref; the product is only the preloaded library.
+"""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+TOOL = os.path.join(ROOT, "oracle", "_ref", "avifyuv")
+LIB = os.path.join(ROOT, "libavif_b200", "csrc", "libavif_b200.so")
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, preload, extra=()):
+    env = dict(os.environ)
+    if preload:
+        env["LD_PRELOAD"] = LIB
+        env["AVIF_B200_TRACE_CALLS"] = "1"
+    out = subprocess.run([TOOL, "-m", mode, *extra], env=env, capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return out.stdout.decode(), out.stderr.decode()
+
+
+def _golden(name):
+    with open(os.path.join(HERE, "golden", name)) as f:
+        return f.read()
+
+
+def _strip_progress(text):
+    return "".join(line + "\n" for line in text.replace("\r", "\n").split("\n") if line and not line.startswith("["))
+
+
+@pytest.fixture(scope="module")
+def tool():
+    if not os.path.exists(TOOL):
+        pytest.skip("oracle/_ref/avifyuv not built (reference tree absent at build time)")
+    if not os.path.exists(LIB):
+        pytest.fail("libavif_b200.so missing: run __graft_entry__.build()")
+    return TOOL
+
+
+def test_rgb_mode_identical_and_served_by_gpu(tool):
+    native, _ = _run("rgb", preload=False)
+    assert native == _golden("avifyuv_rgb.txt")
+    preloaded, trace = _run("rgb", preload=True)
+    assert preloaded == native
+    # the interposed library reports how many kernels it launched when the process exits
+    assert "avif_b200: kernel launches" in trace
+    launches = int(trace.split("avif_b200: kernel launches")[-1].split()[0])
+    assert launches >= 144 * 4
+
+
+def test_limited_mode_identical(tool):
+    preloaded, _ = _run("limited", preload=True)
+    assert preloaded == _golden("avifyuv_limited.txt")
+
+
+def test_premultiply_mode_identical(tool):
+    # 2^16 + 2^12 + 2^10 + 2^8 images, one un-premultiply and one premultiply call each, every (r <= a) pair
+    preloaded, trace = _run("premultiply", preload=True, extra=("-v",))
+    assert _strip_progress(preloaded) == _golden("avifyuv_premultiply.txt")
+    launches = int(trace.split("avif_b200: kernel launches")[-1].split()[0])
+    assert launches >= 2 * (65536 + 4096 + 1024 + 256)
