@@ -477,6 +477,21 @@ def run_extras(lib, dev, sptr, stream, peak_gbs):
         out[name] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": nf, "us_per_frame_per_image_launches": res["per_image_launch"] * 1e3,
                      "us_per_frame": ms * 1e3, "Mpixels_per_s": w * h / (ms * 1e-3) / 1e6,
                      "alg_bytes_per_px": bpp, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
+        if name.startswith("C3"):
+            # the same frames back: RGBA16 (12-bit) -> 4:2:0 12-bit + alpha, premultiplying (image is premultiplied)
+            assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, nf, sptr) == 0
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, nf, sptr) == 0
+            e1.record(stream)
+            torch.cuda.synchronize()
+            bms = e0.elapsed_time(e1) / (5 * nf)
+            bgbs = bpp * w * h / (bms * 1e-3) / 1e9
+            out["C3_back_RGBA16_to_8K_420_12b_alpha"] = {
+                "kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": nf, "us_per_frame": bms * 1e3,
+                "Mpixels_per_s": w * h / (bms * 1e-3) / 1e6, "alg_bytes_per_px": bpp, "achieved_gbs": bgbs, "frac_of_peak": bgbs / peak_gbs}
         del fr
         torch.cuda.empty_cache()
     # C4: the 16 cells (1920x1080 RGBA8) of the 4x4 grid -> 4:2:0 8-bit BT.601 full + alpha, one batched RGB->YUV launch

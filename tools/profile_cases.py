@@ -21,7 +21,7 @@ CASES = [
     # name, w, h, depth, fmt, range, mc, alpha, img_premult, rgb_depth, rgb_fmt, upsampling, rgb_premult, back?
     ("NS", 7680, 4320, 10, 1, 1, 1, False, False, 10, 1, 0, False, False),
     ("C2", 3840, 2160, 10, 1, 1, 1, True, False, 10, 1, 0, True, True),
-    ("C3", 7680, 4320, 12, 3, 0, 9, True, True, 12, 1, 4, False, False),
+    ("C3", 7680, 4320, 12, 3, 0, 9, True, True, 12, 1, 4, False, True),
     ("C5bil", 3840, 2160, 10, 3, 0, 1, False, False, 16, 0, 0, False, False),
     ("C5near", 3840, 2160, 10, 3, 0, 1, False, False, 16, 0, 3, False, False),
     ("C1bil", 1920, 1080, 8, 3, 0, 6, False, False, 8, 1, 4, False, False),
