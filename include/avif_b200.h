@@ -331,6 +331,12 @@ AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t 
  * [-65536, 65535] (csrc/pixel_math.cuh: div_int).  The host proves that by exhaustion for every divisor it meets; this
  * re-runs the proof on the device.  hostVerdict receives the host's result (1 = proven). */
 AVIF_B200_API avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
+/* The integer premultiply fused behind a conversion, floorf(c * a / maxF + 0.5f) (src/alpha.c:187-189), runs for channel
+ * depths <= 12 as trunc(fma(c * a, r, k)) with the constants of csrc/verified_premul.h.  Both forms are compared on every
+ * code pair (c, a): avifB200VerifyPremulFma on the host (no device needed), avifB200SelfTestPremulFma on the device.
+ * AVIF_RESULT_NOT_IMPLEMENTED: no constants for that depth (the general form is used). */
+AVIF_B200_API avifResult avifB200VerifyPremulFma(uint32_t depth, uint64_t * mismatches);
+AVIF_B200_API avifResult avifB200SelfTestPremulFma(uint32_t depth, uint64_t * mismatches);
 /* Alpha unmultiply divides three colour values by the same normalised alpha; the kernels share one reciprocal
  * between the three IEEE divisions (pixel_math.cuh: rcp_refined).  Re-checks that against the hardware's IEEE division:
  * sampledColour == 0: every (colour code, alpha code) pair of the given depth; != 0: random colour values in [0,1]. */

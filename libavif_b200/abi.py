@@ -154,6 +154,8 @@ PROTOTYPES = {
     "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200SelfTestIntDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "avifB200SelfTestAlphaDivision": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "avifB200VerifyPremulFma": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
+    "avifB200SelfTestPremulFma": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200DeviceAvailable": (C.c_int, []),
     "avifB200Version": (C.c_char_p, []),
 }

@@ -874,6 +874,24 @@ __global__ void __launch_bounds__(256) alpha_div_selftest_kernel(uint32_t max, i
     if (bad) atomicAdd(mismatches, bad);
 }
 
+/* premul_fma_magic against the reference form floorf(c * a / maxF + 0.5f) with the hardware's IEEE division, for every
+ * code pair (c, a) in [0, max]^2. */
+__global__ void __launch_bounds__(256) premul_fma_selftest_kernel(uint32_t max, float r, float k, unsigned long long * mismatches)
+{
+    const uint64_t total = (uint64_t)(max + 1) * (max + 1);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const float maxF = (float)max;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t a = (uint32_t)(i % (max + 1)), c = (uint32_t)(i / (max + 1));
+        const float ref = floorf(__fadd_rn(__fdiv_rn(__fmul_rn((float)c, (float)a), maxF), 0.5f));
+        const float af = (float)a;
+        const float got = premul_fma_magic(__uint_as_float(0x4B000000u | c), af, __fmul_rn(af, -8388608.0f), r, k);
+        if ((__float_as_uint(got) & 0xFFFFu) != (uint32_t)ref || (__float_as_uint(got) >> 16) != 0x4B00u) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* launch helpers                                                                                  */
 
@@ -1185,6 +1203,23 @@ int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, 
     err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
     if (!err) {
         alpha_div_selftest_kernel<<<148 * 16, 256, 0, st>>>(max, mode, dev);
+        err = finish_launch();
+    }
+    if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);
+    if (!err) err = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return err;
+}
+
+int abPremulFmaSelfTest(uint32_t max, float r, float k, unsigned long long * mismatches, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long * dev = nullptr;
+    int err = (int)cudaMalloc((void **)&dev, sizeof(*dev));
+    if (err) return err;
+    err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
+    if (!err) {
+        premul_fma_selftest_kernel<<<148 * 16, 256, 0, st>>>(max, r, k, dev);
         err = finish_launch();
     }
     if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);

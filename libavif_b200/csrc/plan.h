@@ -22,7 +22,8 @@ enum { AB_CHROMA_NONE = 0, AB_CHROMA_FULL = 1, AB_CHROMA_NEAREST = 2, AB_CHROMA_
 enum { AB_ALPHA_KEEP = 0, AB_ALPHA_COPY = 1, AB_ALPHA_FILL = 2 };
 /* alpha (un)multiply flavours: the reference does it either in normalised float inside the general loop
  * (reformat.c:894-947) or as an integer-domain post-pass on the quantised pixels (alpha.c:151-535). */
-enum { AB_MUL_NONE = 0, AB_MUL_FLOAT_MUL = 1, AB_MUL_FLOAT_UNMUL = 2, AB_MUL_INT_PREMUL = 3, AB_MUL_INT_UNPREMUL = 4 };
+enum { AB_MUL_NONE = 0, AB_MUL_FLOAT_MUL = 1, AB_MUL_FLOAT_UNMUL = 2, AB_MUL_INT_PREMUL = 3, AB_MUL_INT_UNPREMUL = 4,
+       AB_MUL_INT_PREMUL_FMA = 5 /* kernel-template value only: INT_PREMUL with the verified 2-fma form (pmR != 0) */ };
 
 /* Exact division by a call-constant divisor d:  q = x*r; e = fma(-q,d,x); q' = fma(e,r,q) with r = RN(1/d).
  * `exact` is set by the host only for divisors whose (x,d) domain has been verified exhaustively to give the
@@ -54,6 +55,7 @@ typedef struct AbY2RJob {
     AbDiv yuvMaxDiv, rgbMaxDiv; /* (2^depth - 1) as divisors: alpha normalisation / rescale / premultiply */
     float c1, c2, c3, c4; /* 2(1-kr), 2(1-kb), kr(1-kr), kb(1-kb) as float constants (reformat.c:1014-1016) */
     float f16mul;         /* 2^-112 * (1/65535)  (reformat.c:1429-1430) */
+    float pmR, pmK;       /* integer premultiply as floor(fma(c*a, pmR, pmK)); 0 when no verified constants exist for rgbDepth */
     uint32_t magicK;               /* 0x4B000000, passed as data so that PRMT takes it from a uniform register and keeps its selector immediate */
     float magicBiasY, magicBiasUV; /* 2^23 + bias: (float)cp - bias == as_float(cp | 0x4B000000) - magicBias, exactly */
     uint8_t yuvBytes, rgbBytes; /* bytes per sample / per channel */
@@ -195,6 +197,7 @@ int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t 
 /* exhaustive device check of div_const's fast form for divisor d (counts x whose result differs from x/d) */
 int abDivSelfTest(float d, unsigned long long * mismatches, void * stream);
 int abIntDivSelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream);
+int abPremulFmaSelfTest(uint32_t max, float r, float k, unsigned long long * mismatches, void * stream);
 int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, void * stream);
 /* number of kernel launches issued by the calling thread through the functions above */
 uint64_t abLaunchCount(void);

@@ -211,23 +211,23 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
             if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
                 const float a = div_int(__fsub_rn(am, magicOne), J.rgbMaxDiv);
                 if (C::AM == AB_MUL_FLOAT_MUL) {
-                    const bool scale = (a < 1.0f); /* a == 0: the products are exact zeros as well */
-                    R = scale ? __fmul_rn(R, a) : R;
-                    G = scale ? __fmul_rn(G, a) : G;
-                    B = scale ? __fmul_rn(B, a) : B;
+                    /* a >= 1 leaves the colour untouched (x*1 == x), a == 0 zeroes it through the multiply */
+                    const float am1 = fminf(a, 1.0f);
+                    R = __fmul_rn(R, am1);
+                    G = __fmul_rn(G, am1);
+                    B = __fmul_rn(B, am1);
                 } else {
                     /* branch-free so that the 8 pixels of the lane interleave freely: a == 0 -> 0, 0 < a < 1 -> min(c/a, 1),
-                     * a >= 1 -> untouched.  The divisor is forced to 1 when no division is wanted (x/1 == x exactly). */
-                    const bool zero = (a == 0.0f), need = (a > 0.0f) && (a < 1.0f);
-                    const float d = need ? a : 1.0f;
-                    const float r1 = rcp_refined(d);
-                    R = zero ? 0.0f : R;
-                    G = zero ? 0.0f : G;
-                    B = zero ? 0.0f : B;
+                     * a >= 1 -> untouched (the channel may hold more than 1 there: codes above max are not clamped).
+                     * a == 0 takes the quotient path with divisor 1 and a zero "reciprocal": div_by_rcp then returns +0
+                     * (q0 = x*0 = 0, remainder x, 0*x + 0 = 0). */
+                    const bool zero = (a == 0.0f), below = (a < 1.0f);
+                    const float d = (below && !zero) ? a : 1.0f;
+                    const float r1 = zero ? 0.0f : rcp_refined(d);
                     const float qR = min1(div_by_rcp(R, d, r1)), qG = min1(div_by_rcp(G, d, r1)), qB = min1(div_by_rcp(B, d, r1));
-                    R = need ? qR : R;
-                    G = need ? qG : G;
-                    B = need ? qB : B;
+                    R = below ? qR : R;
+                    G = below ? qG : G;
+                    B = below ? qB : B;
                 }
             }
             const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */

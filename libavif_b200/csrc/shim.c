@@ -24,6 +24,7 @@
 
 #include "plan.h"
 #include "verified_divisors.h"
+#include "verified_premul.h"
 
 #define AB_VERSION "libavif_b200 0.1 (sm_100a)"
 
@@ -217,6 +218,51 @@ avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, u
     if (hostVerdict) *hostVerdict = dv.intExact;
     unsigned long long bad = 0;
     AB_CUDA(abIntDivSelfTest(&dv, &bad, tls.stream));
+    *mismatches = bad;
+    return AVIF_RESULT_OK;
+}
+
+/* verified_premul.h lookup: constants of the 2-fma integer premultiply for this channel depth (0 = none) */
+static int premulFmaConstants(uint32_t depth, float * r, float * k)
+{
+    for (size_t i = 0; i < sizeof(kAbVerifiedPremul) / sizeof(kAbVerifiedPremul[0]); ++i) {
+        if (kAbVerifiedPremul[i].depth == depth) {
+            memcpy(r, &kAbVerifiedPremul[i].rBits, sizeof(*r));
+            memcpy(k, &kAbVerifiedPremul[i].kBits, sizeof(*k));
+            return 1;
+        }
+    }
+    return 0;
+}
+
+/* Host re-run of tools/verify_premul.c for one depth (no device needed): every code pair, reference form vs fma form. */
+avifResult avifB200VerifyPremulFma(uint32_t depth, uint64_t * mismatches)
+{
+    float r, k;
+    if (!mismatches) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (!premulFmaConstants(depth, &r, &k)) return AVIF_RESULT_NOT_IMPLEMENTED;
+    const uint32_t max = (1u << depth) - 1;
+    const float maxF = (float)max;
+    uint64_t bad = 0;
+    for (uint32_t a = 0; a <= max; ++a) {
+        for (uint32_t c = 0; c <= max; ++c) {
+            const float x = (float)c * (float)a;
+            bad += ((uint32_t)floorf(x / maxF + 0.5f) != (uint32_t)fmaf(x, r, k));
+        }
+    }
+    *mismatches = bad;
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifB200SelfTestPremulFma(uint32_t depth, uint64_t * mismatches)
+{
+    float r, k;
+    if (!mismatches) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (!premulFmaConstants(depth, &r, &k)) return AVIF_RESULT_NOT_IMPLEMENTED;
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    unsigned long long bad = 0;
+    AB_CUDA(abPremulFmaSelfTest((1u << depth) - 1, r, k, &bad, tls.stream));
     *mismatches = bad;
     return AVIF_RESULT_OK;
 }
@@ -833,6 +879,8 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     if (alphaMode == 0) job.alphaMul = AB_MUL_NONE;
     else if (fast) job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_INT_PREMUL : AB_MUL_INT_UNPREMUL);
     else job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL);
+    job.pmR = job.pmK = 0.0f;
+    if (job.alphaMul == AB_MUL_INT_PREMUL && !tlsExactDivision) (void)premulFmaConstants(rgb->depth, &job.pmR, &job.pmK);
     job.toF16 = (uint8_t)(rgb->isFloat ? 1 : 0);
     job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
     job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);

@@ -124,6 +124,15 @@ __device__ __forceinline__ float divx(float x, const AbDiv & dv)
     return __fmaf_rn(__fmaf_rn(-q, dv.d, x), dv.r, q);
 }
 
+/* RN(2x / d) for a verified divisor with the doubling folded into the constants (r2 = 2r, dh = d/2): every intermediate of
+ * divx is scaled by exactly 2 or unchanged (q2 = 2q, the residual x - q2*dh = x - q*d, result 2q'), and RN(2x/d) = 2 RN(x/d)
+ * because doubling commutes with rounding away from the subnormal range -- |x| is 0 or far above 2^-60 here. */
+__device__ __forceinline__ float div2x(float x, float r2, float dh)
+{
+    const float q2 = __fmul_rn(x, r2);
+    return __fmaf_rn(__fmaf_rn(-q2, dh, x), r2, q2);
+}
+
 /* normalised value of a magic-float code: ((float)min(code, yuvMax) - bias) / range  (ref: src/reformat.c:583,:598,:1005) */
 template <typename T>
 __device__ __forceinline__ float norm_magic(float mf, float magicMax, float magicBias, const AbDiv & range)
@@ -327,6 +336,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 
     /* ------------------------------ pixels ------------------------------ */
     const float magicOne = 8388608.0f;
+    const float kgR2 = __fmul_rn(J.kg.r, 2.0f), kgDh = __fmul_rn(J.kg.d, 0.5f); /* exact scalings: see div2x */
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (!R.rowOn[r]) continue; /* warp-uniform */
@@ -338,7 +348,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
             /* ref: src/reformat.c:1014-1016 == :874-876 */
             float Rv = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
             float Bv = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
-            float Gv = __fsub_rn(Y, divx(__fmul_rn(2.0f, __fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb))), J.kg));
+            float Gv = __fsub_rn(Y, div2x(__fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb)), kgR2, kgDh));
             Rv = clamp01f(Rv);
             Gv = clamp01f(Gv);
             Bv = clamp01f(Bv);
@@ -348,22 +358,22 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
                 const float Ac = clamp01f(div_int(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
                 if (C::AM == AB_MUL_FLOAT_MUL) {
-                    const bool scale = (Ac < 1.0f); /* Ac == 0 gives exact zeros through the multiply as well */
-                    Rv = scale ? __fmul_rn(Rv, Ac) : Rv;
-                    Gv = scale ? __fmul_rn(Gv, Ac) : Gv;
-                    Bv = scale ? __fmul_rn(Bv, Ac) : Bv;
+                    /* Ac is clamped to [0,1]: Ac == 1 multiplies exactly (the reference skips it) and Ac == 0 gives exact
+                     * zeros (the reference stores them): no selects */
+                    Rv = __fmul_rn(Rv, Ac);
+                    Gv = __fmul_rn(Gv, Ac);
+                    Bv = __fmul_rn(Bv, Ac);
                 } else {
-                    /* branch-free (see r2y_fast.cuh): Ac == 0 -> 0, 0 < Ac < 1 -> min(c/Ac, 1), Ac == 1 -> untouched */
-                    const bool zero = (Ac == 0.0f), need = (Ac > 0.0f) && (Ac < 1.0f);
-                    const float d = need ? Ac : 1.0f;
-                    const float r1 = rcp_refined(d);
-                    Rv = zero ? 0.0f : Rv;
-                    Gv = zero ? 0.0f : Gv;
-                    Bv = zero ? 0.0f : Bv;
-                    const float qR = min1(div_by_rcp(Rv, d, r1)), qG = min1(div_by_rcp(Gv, d, r1)), qB = min1(div_by_rcp(Bv, d, r1));
-                    Rv = need ? qR : Rv;
-                    Gv = need ? qG : Gv;
-                    Bv = need ? qB : Bv;
+                    /* branch- and select-free per channel: Ac == 0 -> 0, 0 < Ac < 1 -> min(c/Ac, 1), Ac == 1 -> untouched.
+                     * The colour values are already clamped to [0,1], so with the divisor forced to 1 the quotient (x/1 == x,
+                     * exactly) and its min with 1 leave them as they are; a zero "reciprocal" makes div_by_rcp return +0
+                     * (q0 = x*0 = 0, remainder x, 0*x + 0 = 0). */
+                    const bool zero = (Ac == 0.0f);
+                    const float d = zero ? 1.0f : Ac;
+                    const float r1 = zero ? 0.0f : rcp_refined(d);
+                    Rv = min1(div_by_rcp(Rv, d, r1));
+                    Gv = min1(div_by_rcp(Gv, d, r1));
+                    Bv = min1(div_by_rcp(Bv, d, r1));
                 }
             }
             float qr = quant_magic(Rv, J.rgbMaxF), qg = quant_magic(Gv, J.rgbMaxF), qb = quant_magic(Bv, J.rgbMaxF);
@@ -375,6 +385,12 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 qr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
                 qg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
                 qb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
+            } else if (C::AM == AB_MUL_INT_PREMUL_FMA) { /* the same function of (c, a) for depths <= 12: pixel_math.cuh */
+                const float ac = fminf(__fsub_rn(am, magicOne), J.rgbMaxF);
+                const float negA23 = __fmul_rn(ac, -8388608.0f);
+                qr = premul_fma_magic(qr, ac, negA23, J.pmR, J.pmK);
+                qg = premul_fma_magic(qg, ac, negA23, J.pmR, J.pmK);
+                qb = premul_fma_magic(qb, ac, negA23, J.pmR, J.pmK);
             } else if (C::AM == AB_MUL_INT_UNPREMUL) { /* ref: src/alpha.c:366-381 */
                 const float af = __fsub_rn(am, magicOne);
                 const bool opaque = (af >= J.rgbMaxF), zero = (af == 0.0f);
@@ -614,7 +630,11 @@ static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
     if (J.alphaWrite != AB_ALPHA_COPY) return 0;
     switch (J.alphaMul) {
         case AB_MUL_NONE: return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(B, st);
-        case AB_MUL_INT_PREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(B, st);
+        case AB_MUL_INT_PREMUL:
+            if (slow || AFIRST) return 0;
+            if (J.pmR != 0.0f) return launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL_FMA>(B, st);
+            /* 8-bit channels always have verified constants: the general form is only instantiated for 16-bit ones */
+            return (sizeof(RT) == 1) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(B, st);
         case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(B, st);
         case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(B, st);
         case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(B, st);
@@ -631,7 +651,7 @@ static bool fast_eligible(const AbY2RJob & J)
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return false;
     if (!J.rangeY.intExact || !J.rangeUV.intExact || !J.kg.exact) return false;
-    if ((J.alphaMul == AB_MUL_INT_PREMUL) && !J.rgbMaxDiv.exact) return false;
+    if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && !J.rgbMaxDiv.exact) return false;
     if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
     const bool sub = (J.chroma != AB_CHROMA_FULL);

@@ -43,3 +43,12 @@ def test_integer_numerator_division_on_device(gpu_product):
         verdict, bad = ctypes.c_int(-1), ctypes.c_uint64(99)
         assert gpu_product.avifB200SelfTestIntDivisor(bits, ctypes.byref(verdict), ctypes.byref(bad)) == 0
         assert (verdict.value == 1) == (bad.value == 0), (d, verdict.value, bad.value)
+
+
+@pytest.mark.parametrize("depth", [8, 10, 12])
+def test_premultiply_fma_form_on_device(gpu_product, depth):
+    """The 2-fma integer premultiply of the fused YUV->RGB kernels (verified_premul.h) against the reference's
+    multiply / IEEE divide / add / floor sequence, on the device, for every (colour code, alpha code) pair."""
+    bad = ctypes.c_uint64(5)
+    assert gpu_product.avifB200SelfTestPremulFma(depth, ctypes.byref(bad)) == 0
+    assert bad.value == 0

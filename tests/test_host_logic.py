@@ -128,3 +128,15 @@ def test_verified_divisor_table_is_sorted_and_covers_supported_matrices(product)
         assert f(float(np.float32(2) * (np.float32(1) - kr))) in bits
     for d in (255, 1023, 4095, 65535, 219, 876, 3504, 56064, 224, 896, 3584, 57344):
         assert f(float(d)) in bits
+
+
+def test_premultiply_fma_constants_proven_on_host(product):
+    """verified_premul.h: trunc(fma(c*a, r, k)) == floorf(c*a/max + 0.5f) for every code pair of depths 8..12 (host loop in
+    the library, 22 M pairs in all); 16 bits has no constants and keeps the reference's operation sequence."""
+    import ctypes
+    for depth in (8, 9, 10, 11, 12):
+        bad = ctypes.c_uint64(77)
+        assert product.avifB200VerifyPremulFma(depth, ctypes.byref(bad)) == 0
+        assert bad.value == 0, depth
+    bad = ctypes.c_uint64(0)
+    assert product.avifB200VerifyPremulFma(16, ctypes.byref(bad)) == 25  # AVIF_RESULT_NOT_IMPLEMENTED
