@@ -12,7 +12,8 @@ from . import abi
 from .abi import *  # noqa: F401,F403  (enum values, struct classes)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libavif_b200.so")
+# AVIF_B200_LIB: load another build of the same sources (kernel-tuning variants, tools/variant_sweep.sh)
+LIB_PATH = os.environ.get("AVIF_B200_LIB") or os.path.join(_HERE, "csrc", "libavif_b200.so")
 _lib = None
 
 

@@ -33,16 +33,39 @@ struct RCfg {
     static constexpr int AM = AM_; /* AB_MUL_NONE / FLOAT_MUL / FLOAT_UNMUL */
 };
 
+/* Loop shape per tile class, from the sweeps in profiles/r01_variants.md (tools/variant_sweep.sh; -D switches for
+ * `make variant`).  The chroma box sums are accumulated as the pixels are produced, so even the two-row 4:2:0 tiles fit
+ * 80 registers:
+ *   one-row tiles (4:4:4, 4:2:2, 4:0:0)   prefetched second register set, 4 blocks/SM (64 registers) -- 7 % faster than 3;
+ *                                         5 blocks/SM spill (+60 %)
+ *   two-row tiles, 8-bit channels         prefetch, 3 blocks/SM   -- 10 % faster than 2; plain loop at 4 measured equal
+ *   two-row tiles, 16-bit channels        3 blocks/SM (-13 % on 8K RGBA16); RGBA16 runs the plain loop: its tile alone is 32
+ *                                         registers of input per lane and a second set does not fit */
 #ifndef AB_R2Y_NOPREFETCH420
-#define AB_R2Y_NOPREFETCH420 0 /* 1 was tried: the two-row tile then spills at 3 blocks/SM and gains nothing at 2 */
+#define AB_R2Y_NOPREFETCH420 0 /* 1: plain loop for every two-row tile */
 #endif
 constexpr bool kR2YNoPrefetch420 = (AB_R2Y_NOPREFETCH420 != 0);
-/* 16-bit RGBA in, 4:2:0 out: one two-row tile is already 32 registers of input per lane, and a second (prefetched) set
- * does not fit the 128-register budget of two resident blocks per SM without spilling -- those run the plain loop. */
+#ifndef AB_R2Y_PLAIN444
+#define AB_R2Y_PLAIN444 0
+#endif
+#ifndef AB_R2Y_MINB444
+#define AB_R2Y_MINB444 4
+#endif
+#ifndef AB_R2Y_MINB420_8
+#define AB_R2Y_MINB420_8 3
+#endif
+#ifndef AB_R2Y_MINB420_16
+#define AB_R2Y_MINB420_16 3
+#endif
+#ifndef AB_R2Y_PLAIN420_8
+#define AB_R2Y_PLAIN420_8 0
+#endif
 template <class C>
 struct RLoop {
-    static constexpr bool PLAIN = (C::SUB == SUB_420) && (kR2YNoPrefetch420 || (sizeof(typename C::RT) == 2 && C::NCH == 4));
-    static constexpr int MIN_BLOCKS = (C::SUB == SUB_420 && !kR2YNoPrefetch420) ? 2 : 3;
+    static constexpr bool SMALL420 = (C::SUB == SUB_420) && (sizeof(typename C::RT) == 1);
+    static constexpr bool PLAIN = SMALL420 ? (AB_R2Y_PLAIN420_8 != 0)
+                                           : ((C::SUB == SUB_420) ? (kR2YNoPrefetch420 || (sizeof(typename C::RT) == 2 && C::NCH == 4)) : (AB_R2Y_PLAIN444 != 0));
+    static constexpr int MIN_BLOCKS = SMALL420 ? AB_R2Y_MINB420_8 : ((C::SUB == SUB_420) ? AB_R2Y_MINB420_16 : AB_R2Y_MINB444);
 };
 constexpr int kRTile = 256;
 constexpr int kRWarps = 8;
@@ -194,7 +217,7 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
     const float magicOne = 8388608.0f;
     const float hiLimit = __fadd_rn(J.yuvMaxF, 0.5f);
     const bool swap = J.swapRB != 0;
-    float uf[ROWS][8], vf[ROWS][8];
+    float su[4], sv[4]; /* subsampled chroma: running sums of each 2x2 (4:2:0) / 2x1 (4:2:2) box, in the reference's order */
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if ((uint32_t)r >= nRows) continue;
@@ -239,8 +262,15 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
                     uq[t] = quant_yuv_magic(U, J.rangeUV, J.biasUV, hiLimit);
                     vq[t] = quant_yuv_magic(V, J.rangeUV, J.biasUV, hiLimit);
                 } else {
-                    uf[r][t] = U;
-                    vf[r][t] = V;
+                    /* ref: :413-467 sums the samples that exist row by row, left to right, starting from 0 + first */
+                    const int k = t >> 1;
+                    if ((t & 1) == 0) {
+                        su[k] = (r == 0) ? U : __fadd_rn(su[k], U);
+                        sv[k] = (r == 0) ? V : __fadd_rn(sv[k], V);
+                    } else if (fullTile || (uint32_t)t < nValid) {
+                        su[k] = __fadd_rn(su[k], U);
+                        sv[k] = __fadd_rn(sv[k], V);
+                    }
                 }
             }
             aq[t] = copyAlpha ? am : fillAlpha; /* ref: :545-569 */
@@ -255,52 +285,20 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
         if (writeAlpha) store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
     }
 
-    /* ---- subsampled chroma: ordered box sums over the samples that exist (ref: :413-467) ---- */
+    /* ---- subsampled chroma: average of the box (a division by 1, 2 or 4: exact scaling), quantise, store ---- */
     if (C::SUB == SUB_420 || C::SUB == SUB_422) {
         const uint32_t nc = (nValid + 1) >> 1;
-        if (C::SUB == SUB_420) {
-            float uq[4], vq[4];
+        float uq[4], vq[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool two = (uint32_t)(2 * k + 1) < nValid; /* block width 2 */
-                float su = uf[0][2 * k], sv = vf[0][2 * k]; /* 0 + TL */
-                if (two) {
-                    su = __fadd_rn(su, uf[0][2 * k + 1]);
-                    sv = __fadd_rn(sv, vf[0][2 * k + 1]);
-                }
-                if (nRows == 2) {
-                    su = __fadd_rn(su, uf[ROWS - 1][2 * k]);
-                    sv = __fadd_rn(sv, vf[ROWS - 1][2 * k]);
-                    if (two) {
-                        su = __fadd_rn(su, uf[ROWS - 1][2 * k + 1]);
-                        sv = __fadd_rn(sv, vf[ROWS - 1][2 * k + 1]);
-                    }
-                }
-                /* division by the sample count 1, 2 or 4 is an exact scaling */
-                const float inv = (two ? 0.5f : 1.0f) * ((nRows == 2) ? 0.5f : 1.0f);
-                uq[k] = quant_yuv_magic(__fmul_rn(su, inv), J.rangeUV, J.biasUV, hiLimit);
-                vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
-            }
-            const uint32_t uj = j0 >> 1;
-            store_samples4<YT>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq);
-            store_samples4<YT>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq);
-        } else {
-            float uq[4], vq[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool two = (uint32_t)(2 * k + 1) < nValid;
-                float su = uf[0][2 * k], sv = vf[0][2 * k];
-                if (two) {
-                    su = __fadd_rn(su, uf[0][2 * k + 1]);
-                    sv = __fadd_rn(sv, vf[0][2 * k + 1]);
-                }
-                const float inv = two ? 0.5f : 1.0f;
-                uq[k] = quant_yuv_magic(__fmul_rn(su, inv), J.rangeUV, J.biasUV, hiLimit);
-                vq[k] = quant_yuv_magic(__fmul_rn(sv, inv), J.rangeUV, J.biasUV, hiLimit);
-            }
-            store_samples4<YT>(F.u + (int64_t)j0 * F.uRB, px0 >> 1, nc, uq);
-            store_samples4<YT>(F.v + (int64_t)j0 * F.vRB, px0 >> 1, nc, vq);
+        for (int k = 0; k < 4; ++k) {
+            const bool two = fullTile || ((uint32_t)(2 * k + 1) < nValid); /* block width 2 */
+            const float inv = (two ? 0.5f : 1.0f) * ((C::SUB == SUB_420 && nRows == 2) ? 0.5f : 1.0f);
+            uq[k] = quant_yuv_magic(__fmul_rn(su[k], inv), J.rangeUV, J.biasUV, hiLimit);
+            vq[k] = quant_yuv_magic(__fmul_rn(sv[k], inv), J.rangeUV, J.biasUV, hiLimit);
         }
+        const uint32_t uj = (C::SUB == SUB_420) ? (j0 >> 1) : j0;
+        store_samples4<YT>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq);
+        store_samples4<YT>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq);
     }
 }
 

@@ -459,8 +459,33 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
  * loads in flight while it computes (at 25-50 % occupancy the scheduler alone cannot hide HBM latency: ncu showed 33 %
  * long_scoreboard + 20 % store-drain stalls on the 8K case with one tile per warp).  Tiles are row-major, so concurrently
  * running warps touch adjacent 256-pixel spans.  (Shared-memory staged stores measured slower: profiles/r01_variants.md.) */
+/* Loop shape per chroma class, from the sweep in profiles/r01_variants.md (tools/variant_sweep.sh; -D switches for `make variant`):
+ *   4:4:4            prefetched second register set, 3 blocks/SM (80 registers)   -- 4 blocks or no prefetch: 4-20 % slower
+ *   nearest 4:2:x    plain loop, 5 blocks/SM (48 registers)                        -- 6-15 % faster than prefetch at 4 blocks
+ *   bilinear 4:2:0   plain loop, 3 blocks/SM (the two-row tile keeps ~100 values live; 4 blocks spill)
+ *   bilinear 4:2:2   prefetch, 3 blocks/SM */
+#ifndef AB_Y2R_MINB
+#define AB_Y2R_MINB 3
+#endif
+#ifndef AB_Y2R_MINB_BIL420
+#define AB_Y2R_MINB_BIL420 3
+#endif
+#ifndef AB_Y2R_MINB_NEAREST
+#define AB_Y2R_MINB_NEAREST 5
+#endif
+#ifndef AB_Y2R_PLAIN_NEAREST
+#define AB_Y2R_PLAIN_NEAREST 1
+#endif
+#ifndef AB_Y2R_PLAIN /* 1: no prefetched register set in any kernel */
+#define AB_Y2R_PLAIN 0
+#endif
 template <class C>
-__global__ void __launch_bounds__(kWarps * 32, 3) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
+struct YLoop {
+    static constexpr bool PLAIN = (C::CHROMA == CH_BIL420) || (AB_Y2R_PLAIN != 0) || (C::CHROMA == CH_NEAREST && AB_Y2R_PLAIN_NEAREST != 0);
+    static constexpr int MIN_BLOCKS = (C::CHROMA == CH_BIL420) ? AB_Y2R_MINB_BIL420 : ((C::CHROMA == CH_NEAREST) ? AB_Y2R_MINB_NEAREST : AB_Y2R_MINB);
+};
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_kernel(const __grid_constant__ AbY2RBatch B)
 {
     const AbY2RJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) y2r_fast_kernel(const __grid_c
     const uint32_t gStride = F.blocks;
     uint32_t g = blockIdx.x - F.blockStart;
     if (g >= F.groups) return;
-    if (C::CHROMA == CH_BIL420) {
+    if (YLoop<C>::PLAIN) {
         /* the two-row bilinear tile already keeps ~100 values live: a second (prefetch) register set would cost a whole
          * resident block per SM and measured no gain (profiles/r01_variants.md) -- plain persistent loop */
         for (; g < F.groups; g += gStride) {
