@@ -166,8 +166,9 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame 
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
 #pragma unroll
-        for (int k = 0; k < NW; ++k) in.w[r][k] = 0;
-        if ((uint32_t)r < nRows) {
+        for (int k = 0; k < NW; ++k)
+            if (!FULL || r > 0) in.w[r][k] = 0; /* row 0 of a full tile is loaded unconditionally */
+        if (r == 0 || (uint32_t)r < nRows) { /* the tile's first row always exists */
             const uint8_t * p = F.rgb + (int64_t)(j0 + r) * F.rgbRB + (int64_t)px0 * PIXB;
             if (fullTile || nValid >= 8) {
                 if ((8 * PIXB) % 16 == 0) {

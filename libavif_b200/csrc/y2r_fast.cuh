@@ -62,6 +62,19 @@ __device__ __forceinline__ float magic_sample(const uint32_t * w, int k, uint32_
     return __uint_as_float(__byte_perm(w[k >> 2], K, 0x7440u | (uint32_t)(k & 3)));
 }
 
+#ifndef AB_Y2R_PACKED_CLAMP /* tuning switch: 0 = one FMNMX per sample after the conversion to float */
+#define AB_Y2R_PACKED_CLAMP 1
+#endif
+/* the same with the code clamped to yuvMax first (ref: AVIF_MIN(ptr[i], yuvMaxChannel), src/reformat.c:583-598): 16-bit
+ * containers may hold garbage above the depth.  mm = yuvMax in both halves: one VIMNMX.U16x2 per pair of samples (the two
+ * samples of a word share it), instead of one FMNMX per sample. */
+template <typename T>
+__device__ __forceinline__ float magic_sample_c(const uint32_t * w, int k, uint32_t K, uint32_t mm)
+{
+    if (sizeof(T) == 2) return __uint_as_float(__byte_perm(AB_Y2R_PACKED_CLAMP ? __vminu2(w[k >> 1], mm) : w[k >> 1], K, (k & 1) ? 0x7432u : 0x7410u));
+    return __uint_as_float(__byte_perm(w[k >> 2], K, 0x7440u | (uint32_t)(k & 3)));
+}
+
 /* 8 consecutive samples starting at x (x % 8 == 0, row 16/8-byte aligned); n = how many of them exist */
 template <typename T>
 __device__ __forceinline__ void load8(const uint8_t * row, uint32_t x, uint32_t n, uint32_t w[4])
@@ -134,10 +147,10 @@ __device__ __forceinline__ float div2x(float x, float r2, float dh)
 }
 
 /* normalised value of a magic-float code: ((float)min(code, yuvMax) - bias) / range  (ref: src/reformat.c:583,:598,:1005) */
-template <typename T>
+template <typename T, bool CLAMP = true>
 __device__ __forceinline__ float norm_magic(float mf, float magicMax, float magicBias, const AbDiv & range)
 {
-    if (sizeof(T) == 2) mf = fminf(mf, magicMax); /* clamp garbage high bits of 16-bit containers */
+    if (CLAMP && sizeof(T) == 2) mf = fminf(mf, magicMax); /* clamp garbage high bits of 16-bit containers */
     return div_int(__fsub_rn(mf, magicBias), range); /* integer numerator: 2-op exact quotient */
 }
 
@@ -169,7 +182,7 @@ struct TileIn {
     uint32_t yw[T::ROWS][4];
     uint32_t aw[T::NEED_A ? T::ROWS : 1][4];
     uint32_t uw[T::CROWS][T::CW], vw[T::CROWS][T::CW];
-    float hlU[T::BIL ? T::CROWS : 1], hrU[T::BIL ? T::CROWS : 1], hlV[T::BIL ? T::CROWS : 1], hrV[T::BIL ? T::CROWS : 1];
+    float hU[T::BIL ? T::CROWS : 1], hV[T::BIL ? T::CROWS : 1]; /* bilinear: the column left of lane 0's / right of lane 31's (magic floats) */
 };
 
 /* rows of a tile: `unit` counts luma rows, or row pairs (2r-1, 2r) for 4:2:0 bilinear */
@@ -238,16 +251,13 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
                 load4_clamped<YT>(vr, m0, cw, in.vw[c]);
             }
             if (T::BIL) {
-                in.hlU[c] = in.hrU[c] = in.hlV[c] = in.hrV[c] = 0.0f;
-                if (lane == 0) {
-                    const uint32_t col = (m0 > 0) ? m0 - 1 : 0;
-                    in.hlU[c] = magic_scalar<YT>(ur, col);
-                    in.hlV[c] = magic_scalar<YT>(vr, col);
-                }
-                if (lane == 31) {
-                    const uint32_t col = min(m0 + 4, cw - 1);
-                    in.hrU[c] = magic_scalar<YT>(ur, col);
-                    in.hrV[c] = magic_scalar<YT>(vr, col);
+                /* only the two edge lanes need a column outside the warp's span (clamped at the picture edge): one
+                 * divergent region for both, one register per plane */
+                in.hU[c] = in.hV[c] = 0.0f;
+                if (lane == 0 || lane == 31) {
+                    const uint32_t col = (lane == 0) ? ((m0 > 0) ? m0 - 1 : 0) : min(m0 + 4, cw - 1);
+                    in.hU[c] = magic_scalar<YT>(ur, col);
+                    in.hV[c] = magic_scalar<YT>(vr, col);
                 }
             }
         } else {
@@ -275,18 +285,19 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
     /* ------------------------------ chroma ------------------------------ */
     const uint32_t K = J.magicK;
     const float magicMax = __uint_as_float(0x4B000000u | J.yuvMax);
+    const uint32_t mm = J.yuvMax * 0x10001u; /* yuvMax in both 16-bit halves (unused for 8-bit samples) */
     float cb[ROWS][8], cr[ROWS][8];
     if (!SUB) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            cb[0][t] = norm_magic<YT>(magic_sample<YT>(in.uw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
-            cr[0][t] = norm_magic<YT>(magic_sample<YT>(in.vw[0], t, K), magicMax, J.magicBiasUV, J.rangeUV);
+            cb[0][t] = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.uw[0], t, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
+            cr[0][t] = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.vw[0], t, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
         }
     } else if (!BIL) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float nu = norm_magic<YT>(magic_sample<YT>(in.uw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
-            const float nv = norm_magic<YT>(magic_sample<YT>(in.vw[0], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nu = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.uw[0], k, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
+            const float nv = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.vw[0], k, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
             cb[0][2 * k] = cb[0][2 * k + 1] = nu;
             cr[0][2 * k] = cr[0][2 * k + 1] = nv;
         }
@@ -302,12 +313,13 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 float n[6];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    n[k + 1] = norm_magic<YT>(magic_sample<YT>(plane ? in.vw[c] : in.uw[c], k, K), magicMax, J.magicBiasUV, J.rangeUV);
+                    n[k + 1] = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(plane ? in.vw[c] : in.uw[c], k, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
                 }
                 float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
                 float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
-                if (lane == 0) left = norm_magic<YT>(plane ? in.hlV[c] : in.hlU[c], magicMax, J.magicBiasUV, J.rangeUV);
-                if (lane == 31) right = norm_magic<YT>(plane ? in.hrV[c] : in.hrU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                const float halo = norm_magic<YT>(plane ? in.hV[c] : in.hU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                left = (lane == 0) ? halo : left;
+                right = (lane == 31) ? halo : right;
                 n[0] = left;
                 n[5] = right;
 #pragma unroll
@@ -343,7 +355,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
         float ch[8][4];            /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const float Y = norm_magic<YT>(magic_sample<YT>(in.yw[r], t, K), magicMax, J.magicBiasY, J.rangeY);
+            const float Y = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.yw[r], t, K, mm), magicMax, J.magicBiasY, J.rangeY);
             const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
             /* ref: src/reformat.c:1014-1016 == :874-876 */
             float Rv = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
