@@ -331,6 +331,18 @@ AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t 
  * [-65536, 65535] (csrc/pixel_math.cuh: div_int).  The host proves that by exhaustion for every divisor it meets; this
  * re-runs the proof on the device.  hostVerdict receives the host's result (1 = proven). */
 AVIF_B200_API avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
+/* ---- B-2: the reference's internal seam (include/avif/internal.h:350-387) ------------------------------------------
+ * libavif_b200_hooks.so exports the six functions src/reformat.c and src/alpha.c call before their built-in loops
+ * (avifImageYUVToRGBLibYUV, avifImageRGBToYUVLibYUV, avifRGBImage{Pre,Unpre}multiplyAlphaLibYUV, avifRGBImageToF16LibYUV,
+ * avifImageRGBToYUVLibSharpYUV) and forwards them here: an unmodified reformat.c / alpha.c linked with that library instead
+ * of reformat_libyuv.c runs its conversions on the GPU ("B-2").  Host pointers, synchronous.
+ * YUV->RGB does the colour conversion (and the alpha channel when reformatAlpha is set) but never the alpha (un)multiply
+ * or the F16 pass: the caller runs those through the other hooks.  It answers AVIF_RESULT_NOT_IMPLEMENTED for the
+ * combinations where that split would not reproduce the built-in path (alpha multiply inside the general loop). */
+AVIF_B200_API avifResult avifB200HookImageYUVToRGB(const avifImage * image, avifRGBImage * rgb, avifBool reformatAlpha, avifBool * alphaReformatted);
+AVIF_B200_API avifResult avifB200HookImageRGBToYUV(avifImage * image, const avifRGBImage * rgb);
+AVIF_B200_API avifResult avifB200HookRGBImageToF16(avifRGBImage * rgb);
+
 /* The integer premultiply fused behind a conversion, floorf(c * a / maxF + 0.5f) (src/alpha.c:187-189), runs for channel
  * depths <= 12 as trunc(fma(c * a, r, k)) with the constants of csrc/verified_premul.h.  Both forms are compared on every
  * code pair (c, a): avifB200VerifyPremulFma on the host (no device needed), avifB200SelfTestPremulFma on the device.

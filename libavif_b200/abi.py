@@ -154,6 +154,9 @@ PROTOTYPES = {
     "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200SelfTestIntDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "avifB200SelfTestAlphaDivision": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "avifB200HookImageYUVToRGB": (C.c_int, [_PI, _PR, C.c_int, C.POINTER(C.c_int)]),
+    "avifB200HookImageRGBToYUV": (C.c_int, [_PI, _PR]),
+    "avifB200HookRGBImageToF16": (C.c_int, [_PR]),
     "avifB200VerifyPremulFma": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200SelfTestPremulFma": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200DeviceAvailable": (C.c_int, []),

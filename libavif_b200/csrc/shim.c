@@ -145,6 +145,9 @@ typedef struct AbCtx {
 static _Thread_local AbCtx tls;
 static _Thread_local int tlsZeroCopy = 0;      /* experiment: kernels read / write pinned host memory directly over PCIe */
 static _Thread_local int tlsExactDivision = 0; /* 1: always use IEEE division instructions (tests cross-check both forms) */
+/* Set while serving the reference's internal libyuv seam (avifB200HookImageYUVToRGB): colour conversion only -- the caller
+ * (the reference's avifImageYUVToRGBImpl, src/reformat.c:1445-1593) runs the integer (un)premultiply and F16 passes itself. */
+static _Thread_local struct { int active, reformatAlpha; } tlsHook = { 0, 0 };
 
 static avifResult cudaToResult(int err)
 {
@@ -722,6 +725,37 @@ avifResult avifB200RGBImageUnpremultiplyAlphaHost(avifRGBImage * rgb) { return p
 avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 0, stream, 1); }
 avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 1, stream, 1); }
 
+/* src/reformat.c:1419-1443 as a pass of its own (the conversions fuse it; the internal seam needs it separately) */
+static avifResult toF16Common(avifRGBImage * rgb)
+{
+    if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (rgb->depth <= 8 || rgb->depth > 16) return AVIF_RESULT_INVALID_ARGUMENT; /* half floats live in 16-bit channels */
+    avifResult res = ctxInit();
+    if (res != AVIF_RESULT_OK) return res;
+    cudaStream_t st = tls.stream;
+    AbRgbPassJob job;
+    memset(&job, 0, sizeof(job));
+    AbRegion px;
+    regionInit(&px, rgb->pixels, rgb->rowBytes, (size_t)rgb->width * avifRGBImagePixelSize(rgb), rgb->height, 0);
+    res = arenaReserve(regionArenaBytes(&px));
+    if (res != AVIF_RESULT_OK) return res;
+    uint8_t * cursor = tls.arena;
+    regionPlace(&px, &cursor);
+    AB_CUDA(regionUpload(&px, 0, px.rows, st));
+    job.pixels = px.dev;
+    job.rowBytes = px.devRB;
+    job.width = rgb->width;
+    job.height = rgb->height;
+    job.depth = rgb->depth;
+    job.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
+    job.f16mul = f16Multiplier(rgb->depth);
+    AB_CUDA(abLaunchToF16(&job, st));
+    tls.lastKernel = "to_f16";
+    AB_CUDA(regionDownload(&px, 0, px.rows, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* alpha plane <-> channel (src/alpha.c:9-149); void like the reference: failures cannot be reported */
 
@@ -794,7 +828,7 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     /* rgb->maxThreads only splits rows in the reference and never changes results (:1679-1747): a hint here. */
 
     /* src/reformat.c:1449-1450, :1475 */
-    const int reformatAlpha = rgbHasAlpha && (!rgb->ignoreAlpha || alphaMode != 0);
+    int reformatAlpha = rgbHasAlpha && (!rgb->ignoreAlpha || alphaMode != 0);
     const int srcAlphaUsable = image->alphaPlane && image->alphaRowBytes;
 
     /* variant classification, src/reformat.c:1496-1567 */
@@ -810,6 +844,14 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
         } else if (s.mode == AB_MODE_COEFF) {
             fast = 1;
         }
+    }
+    if (tlsHook.active) {
+        /* The caller applies alpha (un)multiply as an integer pass over the quantised pixels after this returns.  That equals
+         * the built-in path only where the built-in path does the same (the "fast" class); the general loop multiplies in
+         * normalised float before quantising, so those combinations are declined (the caller then runs its own loop). */
+        if (alphaMode != 0 && !fast) return AVIF_RESULT_NOT_IMPLEMENTED;
+        alphaMode = 0;
+        reformatAlpha = tlsHook.reformatAlpha;
     }
     int hasChroma;
     if (fast) {
@@ -881,7 +923,7 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     else job.alphaMul = (uint8_t)((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL);
     job.pmR = job.pmK = 0.0f;
     if (job.alphaMul == AB_MUL_INT_PREMUL && !tlsExactDivision) (void)premulFmaConstants(rgb->depth, &job.pmR, &job.pmK);
-    job.toF16 = (uint8_t)(rgb->isFloat ? 1 : 0);
+    job.toF16 = (uint8_t)((rgb->isFloat && !tlsHook.active) ? 1 : 0);
     job.swapRB = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_BGR || rgb->format == AVIF_RGB_FORMAT_BGRA || rgb->format == AVIF_RGB_FORMAT_ABGR);
     job.alphaFirst = (uint8_t)(rgb->format == AVIF_RGB_FORMAT_ARGB || rgb->format == AVIF_RGB_FORMAT_ABGR || rgb->format == AVIF_RGB_FORMAT_AGRAY);
 
@@ -1038,7 +1080,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
             pj.unmultiply = (uint8_t)(intMul == AB_MUL_INT_UNPREMUL);
             AB_CUDA(abLaunchPremultiply(&pj, st));
         }
-        if (rgb->isFloat) {
+        if (job.toF16) {
             pj.nChan = (uint8_t)avifRGBFormatChannelCount(rgb->format);
             pj.f16mul = job.f16mul;
             AB_CUDA(abLaunchToF16(&pj, st));
@@ -1055,6 +1097,20 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
 avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBAsync(const avifImage * image, avifRGBImage * rgb, void * stream) { return yuvToRgbCommon(image, rgb, stream, 1); }
+
+/* The reference's internal seam, include/avif/internal.h:350-387 (its libyuv hooks): colour conversion only, the
+ * caller keeps the surrounding passes.  libavif_b200_hooks.so exports these under the reference's hook names. */
+avifResult avifB200HookImageYUVToRGB(const avifImage * image, avifRGBImage * rgb, avifBool reformatAlpha, avifBool * alphaReformatted)
+{
+    if (alphaReformatted) *alphaReformatted = AVIF_FALSE;
+    tlsHook.active = 1;
+    tlsHook.reformatAlpha = reformatAlpha ? 1 : 0;
+    const avifResult res = yuvToRgbCommon(image, rgb, NULL, 0);
+    tlsHook.active = 0;
+    if (res == AVIF_RESULT_OK && reformatAlpha && alphaReformatted) *alphaReformatted = AVIF_TRUE; /* the kernel wrote the channel */
+    return res;
+}
+avifResult avifB200HookRGBImageToF16(avifRGBImage * rgb) { return toF16Common(rgb); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* RGB -> YUV                                                                                  */
@@ -1115,7 +1171,7 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
     if (rgb->isFloat) return AVIF_RESULT_NOT_IMPLEMENTED;
 
     const int hasAlpha = avifRGBFormatHasAlpha(rgb->format) && !rgb->ignoreAlpha;
-    const int wantAlphaPlane = hasAlpha;
+    const int wantAlphaPlane = hasAlpha && !tlsHook.active; /* seam: the caller owns allocation and the alpha plane */
     const int monochrome = (image->yuvFormat == AVIF_PIXEL_FORMAT_YUV400);
     const int planesMissing = !image->yuvPlanes[0] || (!monochrome && (!image->yuvPlanes[1] || !image->yuvPlanes[2])) || (wantAlphaPlane && !image->alphaPlane);
     if (planesMissing) {
@@ -1131,6 +1187,7 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
         if (!rgb->alphaPremultiplied && image->alphaPremultiplied) alphaMode = 1;
         else if (rgb->alphaPremultiplied && !image->alphaPremultiplied) alphaMode = 2;
     }
+    if (tlsHook.active && alphaMode != 0) return AVIF_RESULT_NOT_IMPLEMENTED; /* the caller only asks for NO_OP (src/reformat.c:265) */
     const int isGray = avifRGBFormatIsGray(rgb->format);
     if (!isGray && rgb->chromaDownsampling == AVIF_CHROMA_DOWNSAMPLING_SHARP_YUV && image->yuvFormat == AVIF_PIXEL_FORMAT_YUV420) {
         return AVIF_RESULT_NOT_IMPLEMENTED; /* no libsharpyuv: src/reformat.c:256-261, src/reformat_libsharpyuv.c:75-83 */
@@ -1180,7 +1237,7 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
     job.offGray = (uint8_t)s.offGray;
     job.isGray = (uint8_t)isGray;
     job.alphaMul = (uint8_t)((alphaMode == 0) ? AB_MUL_NONE : ((alphaMode == 1) ? AB_MUL_FLOAT_MUL : AB_MUL_FLOAT_UNMUL));
-    const int writeAlphaPlane = image->alphaPlane && image->alphaRowBytes; /* :545 */
+    const int writeAlphaPlane = !tlsHook.active && image->alphaPlane && image->alphaRowBytes; /* :545 */
     job.alphaWrite = (uint8_t)(!writeAlphaPlane ? AB_ALPHA_KEEP : (hasAlpha ? AB_ALPHA_COPY : AB_ALPHA_FILL));
     job.alphaRescale = (uint8_t)(image->depth != rgb->depth);
 
@@ -1314,6 +1371,15 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     return AVIF_RESULT_OK;
 }
 
+avifResult avifB200HookImageRGBToYUV(avifImage * image, const avifRGBImage * rgb)
+{
+    /* src/reformat.c:265-273: planes are allocated by the caller, alpha mode is NO_OP, the alpha plane is written by the
+     * caller afterwards (:545-569) */
+    tlsHook.active = 1;
+    const avifResult res = rgbToYuvCommon(image, rgb, NULL, 0);
+    tlsHook.active = 0;
+    return res;
+}
 avifResult avifImageRGBToYUV(avifImage * image, const avifRGBImage * rgb) { return rgbToYuvCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageRGBToYUVHost(avifImage * image, const avifRGBImage * rgb) { return rgbToYuvCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avifRGBImage * rgb, void * stream) { return rgbToYuvCommon(image, rgb, stream, 1); }

@@ -58,3 +58,14 @@ def load_reference():
     raw.avifCalcYUVCoefficients.restype = None
     raw.avifCalcYUVCoefficients.argtypes = [ctypes.POINTER(abi.avifImage)] + [ctypes.POINTER(ctypes.c_float)] * 3
     return lib
+
+
+REF_B2_SO = os.path.join(_HERE, "_ref", "libavif_ref_b2.so")
+
+
+def load_reference_b2():
+    """The same reference sources minus reformat_libyuv.c / reformat_libsharpyuv.c, linked against libavif_b200_hooks.so: the
+    reference's own reformat.c / alpha.c driving the GPU through its internal seam (None when it was never built here)."""
+    if not os.path.exists(REF_B2_SO):
+        return None
+    return _Facade(ctypes.CDLL(REF_B2_SO), lambda n: n)

@@ -117,3 +117,24 @@ def test_no_gpu_means_loud_failure_not_fallback(product):
     spec = util.Spec(w=16, h=8)
     assert util.yuv_to_rgb(product, spec, 1)[0] == abi.AVIF_RESULT_UNKNOWN_ERROR
     assert util.rgb_to_yuv(product, spec, 1)[0] == abi.AVIF_RESULT_UNKNOWN_ERROR
+
+
+def test_internal_seam_library_exports_the_reference_hook_names():
+    """libavif_b200_hooks.so (B-2): the six functions src/reformat.c / src/alpha.c call before their built-in loops
+    (include/avif/internal.h:350-387) plus avifLibYUVVersion, and nothing that would interpose the public API."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(here, "libavif_b200", "csrc", "libavif_b200_hooks.so")
+    assert os.path.exists(path), "run __graft_entry__.build()"
+    lib = ctypes.CDLL(path)
+    hooks = ["avifImageRGBToYUVLibYUV", "avifImageYUVToRGBLibYUV", "avifImageRGBToYUVLibSharpYUV", "avifRGBImageToF16LibYUV",
+             "avifRGBImagePremultiplyAlphaLibYUV", "avifRGBImageUnpremultiplyAlphaLibYUV", "avifLibYUVVersion"]
+    for name in hooks:
+        assert hasattr(lib, name), name
+    lib.avifLibYUVVersion.restype = ctypes.c_uint
+    assert lib.avifLibYUVVersion() == 0
+    exported = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    names = {line.split()[-1] for line in exported.splitlines() if " T " in line}
+    assert names == set(hooks), names ^ set(hooks)

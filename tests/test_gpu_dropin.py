@@ -73,3 +73,65 @@ def test_premultiply_mode_identical(tool):
     assert _strip_progress(preloaded) == _golden("avifyuv_premultiply.txt")
     launches = int(trace.split("avif_b200: kernel launches")[-1].split()[0])
     assert launches >= 2 * (65536 + 4096 + 1024 + 256)
+
+
+# ---- B-2: the reference's internal seam -----------------------------------------------------------------------------------
+# oracle/_ref/libavif_ref_b2.so = the reference's own reformat.c / alpha.c / ... compiled WITHOUT reformat_libyuv.c and
+# reformat_libsharpyuv.c and linked against libavif_b200_hooks.so, which provides those files' six hook functions on the GPU
+# (libavif_b200/csrc/hooks.c).  avifyuv_b2 is the reference's stress tool linked against that build.
+TOOL_B2 = os.path.join(ROOT, "oracle", "_ref", "avifyuv_b2")
+LIB_B2 = os.path.join(ROOT, "oracle", "_ref", "libavif_ref_b2.so")
+
+
+@pytest.fixture(scope="module")
+def b2():
+    if not os.path.exists(TOOL_B2) or not os.path.exists(LIB_B2):
+        pytest.skip("oracle/_ref B-2 build absent (reference tree absent at build time)")
+    return TOOL_B2
+
+
+def _run_b2(mode, extra=()):
+    env = dict(os.environ, AVIF_B200_TRACE_CALLS="1")
+    out = subprocess.run([TOOL_B2, "-m", mode, *extra], env=env, capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    return out.stdout.decode(), out.stderr.decode()
+
+
+def test_b2_reference_tool_on_hooks(b2):
+    out, trace = _run_b2("rgb")
+    assert out == _golden("avifyuv_rgb.txt")
+    launches = int(trace.split("avif_b200: kernel launches")[-1].split()[0])
+    assert launches >= 144 * 4  # every conversion of the tool went through a hook
+    out, _ = _run_b2("premultiply", extra=("-v",))
+    assert _strip_progress(out) == _golden("avifyuv_premultiply.txt")
+
+
+def test_b2_reference_library_equals_plain_reference(b2, reference):
+    """Random specs through the hooked reference build and through the plain reference build: same bytes and result
+    codes, and the hooked build actually launched kernels (it declines only alpha-multiply-in-the-general-loop cases)."""
+    import libavif_b200 as L
+    from oracle import loader
+    from tests import util
+    hooked = loader.load_reference_b2()
+    gpu = L.lib()
+    gpu.avifB200ResetKernelLaunchCount()
+    n_y2r = n_r2y = 0
+    for k, spec in enumerate(util.random_y2r_specs(120, seed=777, max_dim=64)):
+        ca, a = util.yuv_to_rgb(reference, spec, seed=9000 + k)
+        cb, b = util.yuv_to_rgb(hooked, spec, seed=9000 + k)
+        assert ca == cb, (spec, ca, cb)
+        if ca == 0:
+            assert bytes(a) == bytes(b), spec
+            n_y2r += 1
+    for k, spec in enumerate(util.random_r2y_specs(120, seed=778, max_dim=64)):
+        ca, pa = util.rgb_to_yuv(reference, spec, seed=9500 + k)
+        cb, pb = util.rgb_to_yuv(hooked, spec, seed=9500 + k)
+        assert ca == cb, (spec, ca, cb)
+        if ca == 0:
+            for x, y in zip(pa, pb):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert bytes(x) == bytes(y), spec
+            n_r2y += 1
+    assert n_y2r > 60 and n_r2y > 60
+    assert gpu.avifB200KernelLaunchCount() >= (n_y2r + n_r2y) // 2
