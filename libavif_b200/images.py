@@ -129,6 +129,10 @@ class YUVImage:
 class RGBImage:
     """avifRGBImage + the storage behind rgb.pixels; defaults follow avifRGBImageSetDefaults (src/avif.c:700-717)."""
 
+    # rgb->avoidLibYUV: irrelevant to this library (always built-in-path results); a reference build only consults its
+    # internal libyuv seam when it is 0 (tests of libavif_b200_hooks.so clear it)
+    AVOID_LIBYUV = 1
+
     def __init__(self, width, height, depth, fmt=abi.AVIF_RGB_FORMAT_RGBA, upsampling=abi.AVIF_CHROMA_UPSAMPLING_AUTOMATIC,
                  downsampling=abi.AVIF_CHROMA_DOWNSAMPLING_AUTOMATIC, ignore_alpha=False, alpha_premultiplied=False,
                  is_float=False, max_threads=1, device=None, pinned=False, row_pad=0, offset=0, allocate=True):
@@ -136,7 +140,7 @@ class RGBImage:
         c = self.c
         c.width, c.height, c.depth, c.format = width, height, depth, fmt
         c.chromaUpsampling, c.chromaDownsampling = upsampling, downsampling
-        c.avoidLibYUV, c.ignoreAlpha, c.alphaPremultiplied, c.isFloat = 1, int(ignore_alpha), int(alpha_premultiplied), int(is_float)
+        c.avoidLibYUV, c.ignoreAlpha, c.alphaPremultiplied, c.isFloat = self.AVOID_LIBYUV, int(ignore_alpha), int(alpha_premultiplied), int(is_float)
         c.maxThreads = max_threads
         self.device = device
         self.pixel_bytes = abi.rgb_pixel_size(fmt, depth) if 0 <= fmt < abi.AVIF_RGB_FORMAT_COUNT else 4
