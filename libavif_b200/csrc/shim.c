@@ -431,15 +431,24 @@ static cudaStream_t upStream(int band)
     return (nUp == 2 && (band & 1)) ? tls.up2 : tls.up;
 }
 
+/* synchronous host-pointer conversions currently inside the library, over all threads */
+static int gHostCallsInFlight = 0;
+
 static int planBands(uint32_t height, size_t frameBytes, uint32_t bandRows[AB_MAX_BANDS + 1])
 {
     static _Thread_local size_t bandBytes = 0;
+    static _Thread_local int bandFixed = 0;
     if (!bandBytes) {
-        const char * e = getenv("AVIF_B200_BAND_MB"); /* tuning knob; default from profiles/r01_pcie.md */
+        const char * e = getenv("AVIF_B200_BAND_MB"); /* tuning knob; default from profiles/r01_variants.md */
         const long mb = e ? atol(e) : 0;
+        bandFixed = (mb > 0);
         bandBytes = (size_t)((mb > 0) ? mb : 24) << 20;
     }
     int n = (int)(frameBytes / bandBytes);
+    /* A lone caller overlaps its own upload, kernel and download band by band.  When several host threads convert at once
+     * their calls already overlap each other, and whole-plane copies use PCIe better than 5 MB pieces (uploads below 16 MB run
+     * at half rate on this host): one band then (measured: 4.7 -> 5.2-5.4 Gpixel/s with 4-8 threads, profiles/r01_variants.md). */
+    if (!bandFixed && __atomic_load_n(&gHostCallsInFlight, __ATOMIC_RELAXED) > 1) n = 1;
     if (n < 1) n = 1;
     if (n > AB_MAX_BANDS) n = AB_MAX_BANDS;
     uint32_t per = (height + (uint32_t)n - 1) / (uint32_t)n;
@@ -935,7 +944,7 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     return AVIF_RESULT_OK;
 }
 
-static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
 {
     AbY2RJob job;
     AbY2RPlan plan;
@@ -1094,6 +1103,14 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     return AVIF_RESULT_OK;
 }
 
+static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+{
+    if (async) return yuvToRgbImpl(image, rgb, userStream, 1);
+    __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    const avifResult res = yuvToRgbImpl(image, rgb, NULL, 0);
+    __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    return res;
+}
 avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBAsync(const avifImage * image, avifRGBImage * rgb, void * stream) { return yuvToRgbCommon(image, rgb, stream, 1); }
@@ -1250,7 +1267,7 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
     return AVIF_RESULT_OK;
 }
 
-static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
 {
     AbR2YJob job;
     AbR2YPlan plan;
@@ -1371,6 +1388,14 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     return AVIF_RESULT_OK;
 }
 
+static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+{
+    if (async) return rgbToYuvImpl(image, rgb, userStream, 1);
+    __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    const avifResult res = rgbToYuvImpl(image, rgb, NULL, 0);
+    __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    return res;
+}
 avifResult avifB200HookImageRGBToYUV(avifImage * image, const avifRGBImage * rgb)
 {
     /* src/reformat.c:265-273: planes are allocated by the caller, alpha mode is NO_OP, the alpha plane is written by the
