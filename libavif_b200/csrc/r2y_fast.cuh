@@ -99,8 +99,41 @@ __device__ __forceinline__ float quant_luma_magic(float v, float range, float bi
     return __fadd_rz(fminf(t, hiLimit), 8388608.0f);
 }
 
+#ifndef AB_R2Y_SATCVT /* tuning switch: 0 = clamp in float (2 FMNMX) and take the code from FADD.RZ's mantissa */
+#define AB_R2Y_SATCVT 1
+#endif
+/* The same quantisation through the saturating float -> integer conversion: cvt.rzi truncates (== floor for t >= 0), maps
+ * negatives and NaN to 0 and saturates at the container maximum -- the reference's clamp(floor(t), 0, max) for 8-bit samples;
+ * 16-bit samples of depth 10/12 still need min(code, yuvMax), which the store does on packed pairs (CLAMP below).
+ * Returned as a bit container (code in the low half, upper half zero) so that both forms pack alike. */
 template <typename YT>
-__device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8])
+__device__ __forceinline__ float quant_code_sat(float v, float range, float bias)
+{
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+    uint32_t c;
+    if (sizeof(YT) == 1) {
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(c) : "f"(t));
+    } else {
+        unsigned short h;
+        asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(h) : "f"(t));
+        c = h;
+    }
+    return __uint_as_float(c);
+}
+template <typename YT>
+__device__ __forceinline__ float quant_yuv(float v, float range, float bias, float hiLimit)
+{
+    return AB_R2Y_SATCVT ? quant_code_sat<YT>(v, range, bias) : quant_yuv_magic(v, range, bias, hiLimit);
+}
+template <typename YT>
+__device__ __forceinline__ float quant_luma(float v, float range, float bias, float hiLimit)
+{
+    return AB_R2Y_SATCVT ? quant_code_sat<YT>(v, range, bias) : quant_luma_magic(v, range, bias, hiLimit);
+}
+
+/* CLAMP: the containers hold saturated 16-bit codes that still have to be limited to yuvMax (mm = yuvMax in both halves) */
+template <typename YT, bool CLAMP = false>
+__device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8], uint32_t mm = 0)
 {
     if (n >= 8) {
         if (sizeof(YT) == 2) {
@@ -109,6 +142,9 @@ __device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32
             v.y = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x5410u);
             v.z = __byte_perm(__float_as_uint(q[4]), __float_as_uint(q[5]), 0x5410u);
             v.w = __byte_perm(__float_as_uint(q[6]), __float_as_uint(q[7]), 0x5410u);
+            if (CLAMP) {
+                v.x = __vminu2(v.x, mm); v.y = __vminu2(v.y, mm); v.z = __vminu2(v.z, mm); v.w = __vminu2(v.w, mm);
+            }
             *reinterpret_cast<uint4 *>(row + (size_t)x * 2) = v;
         } else {
             uint2 v;
@@ -118,19 +154,25 @@ __device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)(__float_as_uint(q[k]) & 0xFFFFu);
+        for (int k = 0; k < 8; ++k) {
+            uint32_t c = __float_as_uint(q[k]) & 0xFFFFu;
+            if (CLAMP) c = min(c, mm & 0xFFFFu);
+            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)c;
+        }
     }
 }
 
-template <typename YT>
-__device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32_t n, const float q[4])
+template <typename YT, bool CLAMP = false>
+__device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32_t n, const float q[4], uint32_t mm = 0)
 {
     if (n >= 4) {
         if (sizeof(YT) == 2) {
             uint2 v;
             v.x = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x5410u);
             v.y = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x5410u);
+            if (CLAMP) {
+                v.x = __vminu2(v.x, mm); v.y = __vminu2(v.y, mm);
+            }
             *reinterpret_cast<uint2 *>(row + (size_t)x * 2) = v;
         } else {
             *reinterpret_cast<uint32_t *>(row + x) =
@@ -138,8 +180,11 @@ __device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)(__float_as_uint(q[k]) & 0xFFFFu);
+        for (int k = 0; k < 4; ++k) {
+            uint32_t c = __float_as_uint(q[k]) & 0xFFFFu;
+            if (CLAMP) c = min(c, mm & 0xFFFFu);
+            if ((uint32_t)k < n) reinterpret_cast<YT *>(row)[x + k] = (YT)c;
+        }
     }
 }
 
@@ -217,6 +262,8 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
     const float fillAlpha = __uint_as_float(0x4B000000u | J.yuvMax);
     const float magicOne = 8388608.0f;
     const float hiLimit = __fadd_rn(J.yuvMaxF, 0.5f);
+    constexpr bool QC = (AB_R2Y_SATCVT != 0) && (sizeof(YT) == 2); /* saturated 16-bit codes: min with yuvMax at the store */
+    const uint32_t mm = J.yuvMax * 0x10001u;
     const bool swap = J.swapRB != 0;
     float su[4], sv[4]; /* subsampled chroma: running sums of each 2x2 (4:2:0) / 2x1 (4:2:2) box, in the reference's order */
 #pragma unroll
@@ -255,13 +302,13 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
                 }
             }
             const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
-            yq[t] = quant_luma_magic(Y, J.rangeY, J.biasY, hiLimit);
+            yq[t] = quant_luma<YT>(Y, J.rangeY, J.biasY, hiLimit);
             if (C::SUB != SUB_400) {
                 const float U = rdivx(__fsub_rn(B, Y), J.du);
                 const float V = rdivx(__fsub_rn(R, Y), J.dv);
                 if (C::SUB == SUB_444) {
-                    uq[t] = quant_yuv_magic(U, J.rangeUV, J.biasUV, hiLimit);
-                    vq[t] = quant_yuv_magic(V, J.rangeUV, J.biasUV, hiLimit);
+                    uq[t] = quant_yuv<YT>(U, J.rangeUV, J.biasUV, hiLimit);
+                    vq[t] = quant_yuv<YT>(V, J.rangeUV, J.biasUV, hiLimit);
                 } else {
                     /* ref: :413-467 sums the samples that exist row by row, left to right, starting from 0 + first */
                     const int k = t >> 1;
@@ -278,10 +325,10 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
-        store_samples8<YT>(F.y + (int64_t)j * F.yRB, px0, ns, yq);
+        store_samples8<YT, QC>(F.y + (int64_t)j * F.yRB, px0, ns, yq, mm);
         if (C::SUB == SUB_444) {
-            store_samples8<YT>(F.u + (int64_t)j * F.uRB, px0, ns, uq);
-            store_samples8<YT>(F.v + (int64_t)j * F.vRB, px0, ns, vq);
+            store_samples8<YT, QC>(F.u + (int64_t)j * F.uRB, px0, ns, uq, mm);
+            store_samples8<YT, QC>(F.v + (int64_t)j * F.vRB, px0, ns, vq, mm);
         }
         if (writeAlpha) store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
     }
@@ -294,12 +341,12 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
         for (int k = 0; k < 4; ++k) {
             const bool two = fullTile || ((uint32_t)(2 * k + 1) < nValid); /* block width 2 */
             const float inv = (two ? 0.5f : 1.0f) * ((C::SUB == SUB_420 && nRows == 2) ? 0.5f : 1.0f);
-            uq[k] = quant_yuv_magic(__fmul_rn(su[k], inv), J.rangeUV, J.biasUV, hiLimit);
-            vq[k] = quant_yuv_magic(__fmul_rn(sv[k], inv), J.rangeUV, J.biasUV, hiLimit);
+            uq[k] = quant_yuv<YT>(__fmul_rn(su[k], inv), J.rangeUV, J.biasUV, hiLimit);
+            vq[k] = quant_yuv<YT>(__fmul_rn(sv[k], inv), J.rangeUV, J.biasUV, hiLimit);
         }
         const uint32_t uj = (C::SUB == SUB_420) ? (j0 >> 1) : j0;
-        store_samples4<YT>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq);
-        store_samples4<YT>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq);
+        store_samples4<YT, QC>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq, mm);
+        store_samples4<YT, QC>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq, mm);
     }
 }
 
