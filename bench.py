@@ -339,7 +339,7 @@ def run_b200(args):
         hframes.append((src, rgb, back))
 
     from concurrent.futures import ThreadPoolExecutor
-    nthr = max(1, min(args.e2e_threads, Be))
+    nthr = max(1, min(args.e2e_threads, Be, max(1, usable_cpus() // world)))  # ranks share the host's cores
     pool = ThreadPoolExecutor(max_workers=nthr)
 
     def e2e_frames(chunk):  # one host thread: its frames, one synchronous round trip after the other
