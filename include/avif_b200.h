@@ -63,7 +63,8 @@ typedef enum avifResult {
     AVIF_RESULT_INVALID_ARGUMENT = 24,
     AVIF_RESULT_NOT_IMPLEMENTED = 25,
     AVIF_RESULT_OUT_OF_MEMORY = 26,
-    AVIF_RESULT_INTERNAL_ERROR = 29
+    AVIF_RESULT_INTERNAL_ERROR = 29,
+    AVIF_RESULT_INVALID_TONE_MAPPED_IMAGE = 32
 } avifResult;
 
 typedef enum avifPixelFormat {
@@ -247,6 +248,66 @@ AVIF_B200_API void avifRGBImageFreePixels(avifRGBImage * rgb);
 AVIF_B200_API void avifGetPixelFormatInfo(avifPixelFormat format, avifPixelFormatInfo * info);
 AVIF_B200_API unsigned int avifLibYUVVersion(void);
 
+/* ---- gain-map tone mapping: ABI-identical subset of avif.h:366-387, :419-453, :630-712, :1727-1745 ---- */
+enum {
+    AVIF_TRANSFER_CHARACTERISTICS_UNKNOWN = 0,
+    AVIF_TRANSFER_CHARACTERISTICS_BT709 = 1,
+    AVIF_TRANSFER_CHARACTERISTICS_UNSPECIFIED = 2,
+    AVIF_TRANSFER_CHARACTERISTICS_BT470M = 4,
+    AVIF_TRANSFER_CHARACTERISTICS_BT470BG = 5,
+    AVIF_TRANSFER_CHARACTERISTICS_BT601 = 6,
+    AVIF_TRANSFER_CHARACTERISTICS_SMPTE240 = 7,
+    AVIF_TRANSFER_CHARACTERISTICS_LINEAR = 8,
+    AVIF_TRANSFER_CHARACTERISTICS_LOG100 = 9,
+    AVIF_TRANSFER_CHARACTERISTICS_LOG100_SQRT10 = 10,
+    AVIF_TRANSFER_CHARACTERISTICS_IEC61966 = 11,
+    AVIF_TRANSFER_CHARACTERISTICS_BT1361 = 12,
+    AVIF_TRANSFER_CHARACTERISTICS_SRGB = 13,
+    AVIF_TRANSFER_CHARACTERISTICS_BT2020_10BIT = 14,
+    AVIF_TRANSFER_CHARACTERISTICS_BT2020_12BIT = 15,
+    AVIF_TRANSFER_CHARACTERISTICS_PQ = 16,
+    AVIF_TRANSFER_CHARACTERISTICS_SMPTE2084 = 16,
+    AVIF_TRANSFER_CHARACTERISTICS_SMPTE428 = 17,
+    AVIF_TRANSFER_CHARACTERISTICS_HLG = 18
+};
+#define AVIF_DIAGNOSTICS_ERROR_BUFFER_SIZE 256
+typedef struct avifDiagnostics { char error[AVIF_DIAGNOSTICS_ERROR_BUFFER_SIZE]; } avifDiagnostics;
+typedef struct avifSignedFraction { int32_t n; uint32_t d; } avifSignedFraction;
+typedef struct avifUnsignedFraction { uint32_t n; uint32_t d; } avifUnsignedFraction;
+typedef struct avifGainMap {
+    struct avifImage * image; /* gain-map pixels (YUV); metadata below interprets them */
+    avifSignedFraction gainMapMin[3];
+    avifSignedFraction gainMapMax[3];
+    avifUnsignedFraction gainMapGamma[3];
+    avifSignedFraction baseOffset[3];
+    avifSignedFraction alternateOffset[3];
+    avifUnsignedFraction baseHdrHeadroom;
+    avifUnsignedFraction alternateHdrHeadroom;
+    avifBool useBaseColorSpace;
+    avifRWData altICC;
+    avifColorPrimaries altColorPrimaries;
+    avifTransferCharacteristics altTransferCharacteristics;
+    avifMatrixCoefficients altMatrixCoefficients;
+    avifRange altYUVRange;
+    uint32_t altDepth;
+    uint32_t altPlaneCount;
+    avifContentLightLevelInformationBox altCLLI;
+} avifGainMap;
+
+/* src/gainmap.c:73-315 and :317-360: tone-maps baseImage with gainMap for a display of the given log2 HDR headroom.
+ * Allocates toneMappedImage->pixels (width/height/rowBytes set here; format, depth, isFloat are the caller's request).
+ * Arithmetic is binary32 with libm's powf/exp2f/logf in the reference and CUDA's on the device: results agree to +-1 output
+ * code, not bit for bit.  A gain map of another size than the base image needs avifImageScale (libyuv
+ * scaling, SURVEY 8f-4, not built): AVIF_RESULT_NOT_IMPLEMENTED with a diagnostic. */
+AVIF_B200_API avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                                                  avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap,
+                                                  float hdrHeadroom, avifColorPrimaries outputColorPrimaries,
+                                                  avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
+                                                  avifContentLightLevelInformationBox * clli, avifDiagnostics * diag);
+AVIF_B200_API avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap * gainMap, float hdrHeadroom,
+                                               avifColorPrimaries outputColorPrimaries,
+                                               avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
+                                               avifContentLightLevelInformationBox * clli, avifDiagnostics * diag);
 #endif /* AVIF_AVIF_H */
 
 /* ---- internal seam of the reference (include/avif/internal.h:259-278), exported for drop-in at B-2 ---- */

@@ -101,6 +101,36 @@ class avifAlphaParams(C.Structure):
     ]
 
 
+class avifSignedFraction(C.Structure):
+    _fields_ = [("n", C.c_int32), ("d", C.c_uint32)]
+
+
+class avifUnsignedFraction(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("d", C.c_uint32)]
+
+
+class avifDiagnostics(C.Structure):
+    _fields_ = [("error", C.c_char * 256)]
+
+
+class avifContentLightLevelInformationBox(C.Structure):
+    _fields_ = [("maxCLL", C.c_uint16), ("maxPALL", C.c_uint16)]
+
+
+class avifGainMap(C.Structure):  # avif.h:630-712
+    _fields_ = [
+        ("image", C.POINTER(avifImage)),
+        ("gainMapMin", avifSignedFraction * 3), ("gainMapMax", avifSignedFraction * 3), ("gainMapGamma", avifUnsignedFraction * 3),
+        ("baseOffset", avifSignedFraction * 3), ("alternateOffset", avifSignedFraction * 3),
+        ("baseHdrHeadroom", avifUnsignedFraction), ("alternateHdrHeadroom", avifUnsignedFraction),
+        ("useBaseColorSpace", C.c_int),
+        ("altICC", avifRWData),
+        ("altColorPrimaries", C.c_uint16), ("altTransferCharacteristics", C.c_uint16), ("altMatrixCoefficients", C.c_uint16),
+        ("altYUVRange", C.c_int), ("altDepth", C.c_uint32), ("altPlaneCount", C.c_uint32),
+        ("altCLLI", avifContentLightLevelInformationBox),
+    ]
+
+
 class avifPixelFormatInfo(C.Structure):
     _fields_ = [("monochrome", C.c_int), ("chromaShiftX", C.c_int), ("chromaShiftY", C.c_int)]
 
@@ -154,6 +184,10 @@ PROTOTYPES = {
     "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200SelfTestIntDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "avifB200SelfTestAlphaDivision": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "avifRGBImageApplyGainMap": (C.c_int, [_PR, C.c_uint16, C.c_uint16, C.POINTER(avifGainMap), C.c_float, C.c_uint16, C.c_uint16, _PR,
+                                           C.POINTER(avifContentLightLevelInformationBox), C.POINTER(avifDiagnostics)]),
+    "avifImageApplyGainMap": (C.c_int, [_PI, C.POINTER(avifGainMap), C.c_float, C.c_uint16, C.c_uint16, _PR,
+                                        C.POINTER(avifContentLightLevelInformationBox), C.POINTER(avifDiagnostics)]),
     "avifB200HookImageYUVToRGB": (C.c_int, [_PI, _PR, C.c_int, C.POINTER(C.c_int)]),
     "avifB200HookImageRGBToYUV": (C.c_int, [_PI, _PR]),
     "avifB200HookRGBImageToF16": (C.c_int, [_PR]),

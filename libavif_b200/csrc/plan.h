@@ -179,6 +179,35 @@ typedef struct AbRgbPassJob {
     float f16mul;
 } AbRgbPassJob;
 
+/* ---- gain-map tone mapping (tonemap.cu; src/gainmap.c:73-315) ---- */
+typedef struct AbPixFmt { /* what avifGetRGBAPixel / avifSetRGBAPixel need (src/reformat.c:32-117, :1856-1939) */
+    uint32_t pixBytes, chanBytes;
+    uint32_t offR, offG, offB, offA; /* byte offsets exactly as avifGetRGBColorSpaceInfo leaves them (0 for the gray formats) */
+    uint8_t hasAlpha, isFloat, is565;
+    float maxF;
+} AbPixFmt;
+typedef struct AbToneMapJob {
+    const uint8_t * base; /* base rendition, RGB */
+    const uint8_t * gain; /* gain map converted to RGB(A) (src/gainmap.c:203-212); unused when !applyGain */
+    uint8_t * out;
+    int64_t baseRB, gainRB, outRB;
+    uint32_t width, height;
+    AbPixFmt baseFmt, gainFmt, outFmt;
+    uint8_t tfIn, tfOut;    /* avifTransferCharacteristics of the base / of the output (table: src/colr.c:470-491) */
+    uint8_t applyGain;      /* weight != 0 */
+    uint8_t transcode;      /* weight == 0: run gamma -> linear (-> primaries) -> gamma at all (src/gainmap.c:156) */
+    uint8_t inConv, outConv; /* primaries conversions (3x3 in double, src/colrconvert.c:178-186) */
+    double inM[9], outM[9];
+    float gammaInv[3], gmMin[3], gmMax[3], baseOff[3], altOff[3];
+    float weight;
+    /* results: [0] = max over every tone-mapped linear channel value (as float bits; values <= 0 never raise it),
+     * nanIndex = smallest y*width+x whose output is NaN (0xFFFFFFFF if none), sum = sum over pixels of max(r,g,b,0) */
+    uint32_t * maxBits;
+    uint32_t * nanIndex;
+    double * sum;
+} AbToneMapJob;
+int abLaunchToneMap(const AbToneMapJob * job, void * stream);
+
 /* Launchers (kernels.cu).  `stream` is a cudaStream_t.  Return 0 on success, else a cudaError_t value.
  * `forceGeneric` selects the byte-addressed reference kernel instead of the tiled/vectorised one. */
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName);

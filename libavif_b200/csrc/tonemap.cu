@@ -1,0 +1,296 @@
+/*
+ * tonemap.cu -- gain-map tone mapping of an RGB image, one thread per pixel.
+ *
+ * Mirrors the per-pixel body of avifRGBImageApplyGainMap (src/gainmap.c:140-168 without a gain, :229-296 with one):
+ *   read RGBA (src/reformat.c:1856-1897) -> gamma-to-linear (src/colr.c:216-467) -> optional primaries change in double
+ *   (src/colrconvert.c:178-186) -> per channel  (base + baseOffset) * exp2f(lerp(min, max, powf(g, 1/gamma)) * weight) - altOffset
+ *   -> optional primaries change -> linear-to-gamma -> clamp [0,1] -> write (src/reformat.c:1899-1939),
+ *   plus the two reductions behind the content light level (src/gainmap.c:265-270, :293, :297-306).
+ * Every C operator of the reference is one explicitly rounded operation here (-fmad=false); the transcendental calls are
+ * CUDA's powf / exp2f / expf / logf / log10f / sqrtf where the reference calls libm's -- equal to about an ulp, which is why this
+ * row is compared to +-1 output code instead of bit for bit.
+ * Compute-bound by design (up to 9 powf + 3 exp2f per pixel): the bound that matters is the SFU/FMA issue rate, not HBM.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.h"
+
+namespace {
+
+__device__ __forceinline__ float clamp01(float v) { return (v < 0.0f) ? 0.0f : ((1.0f < v) ? 1.0f : v); } /* AVIF_CLAMP */
+
+/* src/colr.c:216-467; id = avifTransferCharacteristics; unknown ids take BT.709 (:497, :508) */
+__device__ float to_linear(int id, float g)
+{
+    switch (id) {
+        case 4: return powf(clamp01(g), 2.2f);
+        case 5: return powf(clamp01(g), 2.8f);
+        case 7:
+            if (g < 0.0f) return 0.0f;
+            if (g < __fmul_rn(4.0f, 0.022821585529445f)) return __fdiv_rn(g, 4.0f);
+            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.111572195921731f), 1.111572195921731f), __fdiv_rn(1.0f, 0.45f));
+            return 1.0f;
+        case 8: return clamp01(g);
+        case 9: return (g <= 0.0f) ? __fdiv_rn(0.01f, 2.0f) : powf(10.0f, __fmul_rn(2.0f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
+        case 10: return (g <= 0.0f) ? __fdiv_rn(0.00316227766f, 2.0f) : powf(10.0f, __fmul_rn(2.5f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
+        case 11:
+            if (g < __fmul_rn(-4.5f, 0.018053968510807f)) return -powf(__fdiv_rn(__fsub_rn(g, 0.09929682680944f), -1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
+            return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+        case 12:
+            if (g < -0.25f) return -0.25f;
+            if (g < 0.0f) return __fdiv_rn(powf(__fdiv_rn(__fsub_rn(g, 0.02482420670236f), -0.27482420670236f), __fdiv_rn(1.0f, 0.45f)), -4.0f);
+            if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
+            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            return 1.0f;
+        case 13:
+            if (g < 0.0f) return 0.0f;
+            if (g < __fmul_rn(12.92f, 0.0030412825601275209f)) return __fdiv_rn(g, 12.92f);
+            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.0550107189475866f), 1.0550107189475866f), 2.4f);
+            return 1.0f;
+        case 16: {
+            if (!(g > 0.0f)) return 0.0f;
+            const float pg = powf(g, __fdiv_rn(1.0f, 78.84375f));
+            const float num = fmaxf(__fsub_rn(pg, 0.8359375f), 0.0f);
+            const float den = fmaxf(__fsub_rn(18.8515625f, __fmul_rn(18.6875f, pg)), 1.17549435e-38f);
+            const float lin = powf(__fdiv_rn(num, den), __fdiv_rn(1.0f, 0.1593017578125f));
+            return __fdiv_rn(__fmul_rn(lin, 10000.0f), 203.0f);
+        }
+        case 17: return __fdiv_rn(powf(fmaxf(g, 0.0f), 2.6f), 0.91655527974030934f);
+        case 18: {
+            if (g < 0.0f) return 0.0f;
+            float lin;
+            if (g <= 0.5f) lin = powf(__fmul_rn(__fmul_rn(g, g), __fdiv_rn(1.0f, 3.0f)), 1.2f);
+            else lin = powf(__fdiv_rn(__fadd_rn(expf(__fdiv_rn(__fsub_rn(g, 0.55991073f), 0.17883277f)), 0.28466892f), 12.0f), 1.2f);
+            return __fdiv_rn(__fmul_rn(lin, 1000.0f), 203.0f);
+        }
+        default: /* 1, 6, 14, 15 and everything unknown: BT.709 */
+            if (g < 0.0f) return 0.0f;
+            if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
+            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            return 1.0f;
+    }
+}
+
+__device__ float to_gamma(int id, float l)
+{
+    switch (id) {
+        case 4: return powf(clamp01(l), __fdiv_rn(1.0f, 2.2f));
+        case 5: return powf(clamp01(l), __fdiv_rn(1.0f, 2.8f));
+        case 7:
+            if (l < 0.0f) return 0.0f;
+            if (l < 0.022821585529445f) return __fmul_rn(l, 4.0f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.111572195921731f, powf(l, 0.45f)), 0.111572195921731f);
+            return 1.0f;
+        case 8: return clamp01(l);
+        case 9: return (l <= 0.01f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(log10f(fminf(l, 1.0f)), 2.0f));
+        case 10: return (l <= 0.00316227766f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(log10f(fminf(l, 1.0f)), 2.5f));
+        case 11:
+            if (l < -0.018053968510807f) return __fadd_rn(__fmul_rn(-1.09929682680944f, powf(-l, 0.45f)), 0.09929682680944f);
+            if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
+            return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+        case 12:
+            if (l < -0.25f) return -0.25f;
+            if (l < 0.0f) return __fadd_rn(__fmul_rn(-0.27482420670236f, powf(__fmul_rn(-4.0f, l), 0.45f)), 0.02482420670236f);
+            if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+            return 1.0f;
+        case 13:
+            if (l < 0.0f) return 0.0f;
+            if (l < 0.0030412825601275209f) return __fmul_rn(l, 12.92f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.0550107189475866f, powf(l, __fdiv_rn(1.0f, 2.4f))), 0.0550107189475866f);
+            return 1.0f;
+        case 16: {
+            if (!(l > 0.0f)) return 0.0f;
+            const float s = clamp01(__fdiv_rn(__fmul_rn(l, 203.0f), 10000.0f));
+            const float pl = powf(s, 0.1593017578125f);
+            const float num = __fsub_rn(__fmul_rn(0.1640625f, pl), 0.1640625f);
+            const float den = __fadd_rn(1.0f, __fmul_rn(18.6875f, pl));
+            return powf(__fadd_rn(1.0f, __fdiv_rn(num, den)), 78.84375f);
+        }
+        case 17: return powf(__fmul_rn(0.91655527974030934f, fmaxf(l, 0.0f)), __fdiv_rn(1.0f, 2.6f));
+        case 18: {
+            float s = clamp01(__fdiv_rn(__fmul_rn(l, 203.0f), 1000.0f));
+            s = powf(s, __fdiv_rn(1.0f, 1.2f));
+            if (s < 0.0f) return 0.0f;
+            if (s <= __fdiv_rn(1.0f, 12.0f)) return sqrtf(__fmul_rn(3.0f, s));
+            return __fadd_rn(__fmul_rn(0.17883277f, logf(__fsub_rn(__fmul_rn(12.0f, s), 0.28466892f))), 0.55991073f);
+        }
+        default:
+            if (l < 0.0f) return 0.0f;
+            if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+            return 1.0f;
+    }
+}
+
+#define AB_F16_MULTIPLIER 1.9259299444e-34f /* src/reformat.c:1411 */
+
+/* src/reformat.c:1856-1897 */
+__device__ __forceinline__ void get_rgba(const uint8_t * row, uint32_t x, const AbPixFmt & f, float px[4])
+{
+    const uint8_t * p = row + (size_t)x * f.pixBytes;
+    if (f.chanBytes > 1) {
+        const uint32_t r = *reinterpret_cast<const uint16_t *>(p + f.offR), g = *reinterpret_cast<const uint16_t *>(p + f.offG);
+        const uint32_t b = *reinterpret_cast<const uint16_t *>(p + f.offB);
+        if (f.isFloat) {
+            px[0] = __fdiv_rn(__uint_as_float(r << 13), AB_F16_MULTIPLIER);
+            px[1] = __fdiv_rn(__uint_as_float(g << 13), AB_F16_MULTIPLIER);
+            px[2] = __fdiv_rn(__uint_as_float(b << 13), AB_F16_MULTIPLIER);
+            px[3] = f.hasAlpha ? __fdiv_rn(__uint_as_float((uint32_t)*reinterpret_cast<const uint16_t *>(p + f.offA) << 13), AB_F16_MULTIPLIER) : 1.0f;
+        } else {
+            px[0] = __fdiv_rn((float)r, f.maxF);
+            px[1] = __fdiv_rn((float)g, f.maxF);
+            px[2] = __fdiv_rn((float)b, f.maxF);
+            px[3] = f.hasAlpha ? __fdiv_rn((float)*reinterpret_cast<const uint16_t *>(p + f.offA), f.maxF) : __fdiv_rn(f.maxF, f.maxF);
+        }
+    } else if (f.is565) {
+        const uint32_t v = *reinterpret_cast<const uint16_t *>(p + f.offR); /* :637-648 */
+        const uint32_t r5 = (v & 0xF800u) >> 11, g6 = (v & 0x07E0u) >> 5, b5 = v & 0x001Fu;
+        px[0] = __fdiv_rn((float)(((r5 << 3) | (r5 >> 2)) & 0xFFu), f.maxF);
+        px[1] = __fdiv_rn((float)(((g6 << 2) | (g6 >> 4)) & 0xFFu), f.maxF);
+        px[2] = __fdiv_rn((float)(((b5 << 3) | (b5 >> 2)) & 0xFFu), f.maxF);
+        px[3] = 1.0f;
+    } else {
+        px[0] = __fdiv_rn((float)p[f.offR], f.maxF);
+        px[1] = __fdiv_rn((float)p[f.offG], f.maxF);
+        px[2] = __fdiv_rn((float)p[f.offB], f.maxF);
+        px[3] = f.hasAlpha ? __fdiv_rn((float)p[f.offA], f.maxF) : 1.0f;
+    }
+}
+
+/* src/reformat.c:1899-1939; the float -> integer casts truncate */
+__device__ __forceinline__ void set_rgba(uint8_t * row, uint32_t x, const AbPixFmt & f, const float px[4])
+{
+    uint8_t * p = row + (size_t)x * f.pixBytes;
+    if (f.chanBytes > 1) {
+        if (f.isFloat) {
+            *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)(__float_as_uint(__fmul_rn(px[0], AB_F16_MULTIPLIER)) >> 13);
+            *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)(__float_as_uint(__fmul_rn(px[1], AB_F16_MULTIPLIER)) >> 13);
+            *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)(__float_as_uint(__fmul_rn(px[2], AB_F16_MULTIPLIER)) >> 13);
+            if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)(__float_as_uint(__fmul_rn(px[3], AB_F16_MULTIPLIER)) >> 13);
+        } else {
+            *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[0], f.maxF)));
+            *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[1], f.maxF)));
+            *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[2], f.maxF)));
+            if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[3], f.maxF)));
+        }
+    } else {
+        const uint32_t R = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[0], f.maxF))) & 0xFFu;
+        const uint32_t G = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[1], f.maxF))) & 0xFFu;
+        const uint32_t B = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[2], f.maxF))) & 0xFFu;
+        if (f.is565) {
+            *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)((B >> 3) | ((G >> 2) << 5) | ((R >> 3) << 11)); /* :619 */
+            return; /* 565 has no alpha */
+        }
+        p[f.offR] = (uint8_t)R;
+        p[f.offG] = (uint8_t)G;
+        p[f.offB] = (uint8_t)B;
+        if (f.hasAlpha) p[f.offA] = (uint8_t)(__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[3], f.maxF))) & 0xFFu);
+    }
+}
+
+/* src/colrconvert.c:70-75, :178-186: y = M.x in double, left-to-right sums, back to float */
+__device__ __forceinline__ void convert_primaries(float px[4], const double * M)
+{
+    const double x0 = (double)px[0], x1 = (double)px[1], x2 = (double)px[2];
+    px[0] = (float)__dadd_rn(__dadd_rn(__dmul_rn(M[0], x0), __dmul_rn(M[1], x1)), __dmul_rn(M[2], x2));
+    px[1] = (float)__dadd_rn(__dadd_rn(__dmul_rn(M[3], x0), __dmul_rn(M[4], x1)), __dmul_rn(M[5], x2));
+    px[2] = (float)__dadd_rn(__dadd_rn(__dmul_rn(M[6], x0), __dmul_rn(M[7], x1)), __dmul_rn(M[8], x2));
+}
+
+__global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ AbToneMapJob J)
+{
+    const uint64_t total = (uint64_t)J.width * J.height;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    float localMax = 0.0f;  /* src/gainmap.c:213: starts at 0, only larger values replace it */
+    double localSum = 0.0;
+    uint32_t localNan = 0xFFFFFFFFu;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t y = (uint32_t)(i / J.width), x = (uint32_t)(i - (uint64_t)y * J.width);
+        float base[4];
+        get_rgba(J.base + (int64_t)y * J.baseRB, x, J.baseFmt, base);
+        float out[4];
+        if (!J.applyGain) { /* src/gainmap.c:152-167 */
+            if (J.transcode) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) base[c] = to_linear(J.tfIn, base[c]);
+                if (J.inConv) convert_primaries(base, J.inM);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) base[c] = fminf(1.0f, fmaxf(0.0f, to_gamma(J.tfOut, base[c])));
+            }
+            out[0] = base[0]; out[1] = base[1]; out[2] = base[2]; out[3] = base[3];
+        } else { /* src/gainmap.c:231-294 */
+            float gm[4];
+            get_rgba(J.gain + (int64_t)y * J.gainRB, x, J.gainFmt, gm);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) base[c] = to_linear(J.tfIn, base[c]);
+            if (J.inConv) convert_primaries(base, J.inM);
+            float pixelMax = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float w = powf(gm[c], J.gammaInv[c]);
+                const float log2g = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, w), J.gmMin[c]), __fmul_rn(w, J.gmMax[c])); /* lerp, :66-69 */
+                const float t = __fsub_rn(__fmul_rn(__fadd_rn(base[c], J.baseOff[c]), exp2f(__fmul_rn(log2g, J.weight))), J.altOff[c]);
+                if (t > localMax) localMax = t;
+                if (t > pixelMax) pixelMax = t;
+                out[c] = t;
+            }
+            if (J.outConv) convert_primaries(out, J.outM);
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                bad = bad || isnan(out[c]);
+                out[c] = fminf(1.0f, fmaxf(0.0f, to_gamma(J.tfOut, out[c])));
+            }
+            if (bad && (uint32_t)i < localNan) localNan = (uint32_t)i;
+            out[3] = base[3];
+            localSum += (double)pixelMax;
+        }
+        set_rgba(J.out + (int64_t)y * J.outRB, x, J.outFmt, out);
+    }
+    if (!J.applyGain) return;
+    /* block reduction, then one atomic each */
+    __shared__ float sMax[8];
+    __shared__ double sSum[8];
+    __shared__ uint32_t sNan[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        localMax = fmaxf(localMax, __shfl_xor_sync(0xFFFFFFFFu, localMax, o));
+        localSum += __shfl_xor_sync(0xFFFFFFFFu, localSum, o);
+        localNan = min(localNan, __shfl_xor_sync(0xFFFFFFFFu, localNan, o));
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sMax[warp] = localMax;
+        sSum[warp] = localSum;
+        sNan[warp] = localNan;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.0f;
+        double s = 0.0;
+        uint32_t n = 0xFFFFFFFFu;
+        for (uint32_t k = 0; k < (blockDim.x >> 5); ++k) {
+            m = fmaxf(m, sMax[k]);
+            s += sSum[k];
+            n = min(n, sNan[k]);
+        }
+        atomicMax(J.maxBits, __float_as_uint(m)); /* m >= 0: unsigned order of the bits == float order */
+        atomicAdd(J.sum, s);
+        atomicMin(J.nanIndex, n);
+    }
+}
+
+} // namespace
+
+extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
+{
+    const uint64_t total = (uint64_t)job->width * job->height;
+    if (total == 0) return 0;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148u * 16u) blocks = 148u * 16u; /* grid-stride: 8 resident blocks per SM, two waves */
+    tone_map_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
+    return (int)cudaGetLastError();
+}
