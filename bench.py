@@ -529,7 +529,82 @@ def run_extras(lib, dev, sptr, stream, peak_gbs):
     out["C4_16_cells_1080p_RGBA8_to_420_8b_alpha"] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": 16, "us_per_frame_per_image_launches": None,
                                                        "us_per_frame": ms * 1e3 / 16, "us_per_canvas": ms * 1e3, "Mpixels_per_s": 16 * 1920 * 1080 / (ms * 1e-3) / 1e6,
                                                        "alg_bytes_per_px": 6.5, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
+    out["TM_4K_gainmap_sRGB8_to_PQ_RGBA10"] = run_tone_map(lib, dev, stream, peak_gbs)
     return out
+
+
+def run_tone_map(lib, dev, stream, peak_gbs):
+    """gain-map tone mapping of a 4K sRGB RGBA8 base with an 8-bit 4:4:4 gain map into PQ RGBA10, everything
+    device-resident (avifB200RGBImageApplyGainMapDevice), and the reference's src/gainmap.c on one host core on a 1080p
+    crop of the same data (its loop is single-threaded)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from libavif_b200 import abi as A
+    from libavif_b200.images import RGBImage, YUVImage
+
+    def build(w, h, device):
+        g = np.random.RandomState(77)
+        base = RGBImage(w, h, 8, A.AVIF_RGB_FORMAT_RGBA, device=device)
+        base.buf.set(g.randint(0, 256, size=(base.buf.rows, base.buf.row_bytes)).astype(np.uint8))
+        gimg = YUVImage(w, h, 8, A.AVIF_PIXEL_FORMAT_YUV444, A.AVIF_RANGE_FULL, 6, alpha=False, device=device)
+        for p in gimg.present_planes():
+            b = gimg.bufs[p]
+            b.set(g.randint(0, 256, size=(b.rows, b.row_bytes)).astype(np.uint8))
+        gm = A.avifGainMap()
+        gm.image = ctypes.pointer(gimg.c)
+        for c in range(3):
+            gm.gainMapMin[c].n, gm.gainMapMin[c].d = 0, 1
+            gm.gainMapMax[c].n, gm.gainMapMax[c].d = 3, 1
+            gm.gainMapGamma[c].n, gm.gainMapGamma[c].d = 1, 1
+            gm.baseOffset[c].n, gm.baseOffset[c].d = 1, 64
+            gm.alternateOffset[c].n, gm.alternateOffset[c].d = 1, 64
+        gm.baseHdrHeadroom.n, gm.baseHdrHeadroom.d = 0, 1
+        gm.alternateHdrHeadroom.n, gm.alternateHdrHeadroom.d = 3, 1
+        gm.useBaseColorSpace, gm.altColorPrimaries = 1, 2
+        return base, gimg, gm
+
+    W, H = 3840, 2160
+    base, gimg, gm = build(W, H, dev)
+    dst = RGBImage(W, H, 10, A.AVIF_RGB_FORMAT_RGBA, device=dev)
+    clli, diag = A.avifContentLightLevelInformationBox(), A.avifDiagnostics()
+
+    def go():
+        r = lib.avifB200RGBImageApplyGainMapDevice(base.ptr(), 1, 13, ctypes.byref(gm), ctypes.c_float(2.0), 9, 16, dst.ptr(),
+                                                   ctypes.byref(clli), ctypes.byref(diag))
+        assert r == 0, diag.error
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        go()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res = {"api": "avifB200RGBImageApplyGainMapDevice (gain map YUV->RGB + tone-map kernel + statistics read-back per call)",
+           "us_per_frame": ms * 1e3, "Mpixels_per_s": W * H / (ms * 1e-3) / 1e6, "alg_bytes_per_px": 15,
+           "achieved_gbs": 15 * W * H / (ms * 1e-3) / 1e9, "frac_of_peak": 15 * W * H / (ms * 1e-3) / 1e9 / peak_gbs,
+           "bound": "SFU/FMA issue (9 powf + 3 exp2f per pixel), not HBM", "maxCLL": clli.maxCLL, "maxPALL": clli.maxPALL}
+    try:
+        from oracle import loader
+        ref = loader.load_reference()
+        if ref is not None and hasattr(ref, "avifRGBImageApplyGainMap"):
+            cw, ch = 1920, 1080
+            hb, hg, hgm = build(cw, ch, None)
+            out = A.avifRGBImage()
+            out.depth, out.format = 10, A.AVIF_RGB_FORMAT_RGBA
+            t0 = time.perf_counter()
+            r = ref.avifRGBImageApplyGainMap(hb.ptr(), 1, 13, ctypes.byref(hgm), ctypes.c_float(2.0), 9, 16, ctypes.byref(out), None, ctypes.byref(diag))
+            dt = time.perf_counter() - t0
+            ref.avifRGBImageFreePixels(ctypes.byref(out))
+            if r == 0:
+                res["cpu_reference"] = {"Mpixels_per_s": cw * ch / dt / 1e6, "cores": 1, "sample": "one 1920x1080 call of src/gainmap.c (oracle/_ref), single-threaded as in the reference"}
+    except Exception as e:  # the checker is optional here
+        res["cpu_reference"] = {"unavailable": str(e)[:100]}
+    return res
 
 
 def main():

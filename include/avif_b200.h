@@ -392,6 +392,14 @@ AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t 
  * [-65536, 65535] (csrc/pixel_math.cuh: div_int).  The host proves that by exhaustion for every divisor it meets; this
  * re-runs the proof on the device.  hostVerdict receives the host's result (1 = proven). */
 AVIF_B200_API avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
+/* Gain-map tone mapping with everything resident: base pixels, the gain map's planes and toneMappedImage->pixels (allocated by
+ * the caller: width, height, rowBytes set) are device pointers; nothing crosses PCIe except the 16 bytes of statistics. */
+AVIF_B200_API avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                                                            avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap,
+                                                            float hdrHeadroom, avifColorPrimaries outputColorPrimaries,
+                                                            avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
+                                                            avifContentLightLevelInformationBox * clli, avifDiagnostics * diag);
+
 /* ---- B-2: the reference's internal seam (include/avif/internal.h:350-387) ------------------------------------------
  * libavif_b200_hooks.so exports the six functions src/reformat.c and src/alpha.c call before their built-in loops
  * (avifImageYUVToRGBLibYUV, avifImageRGBToYUVLibYUV, avifRGBImage{Pre,Unpre}multiplyAlphaLibYUV, avifRGBImageToF16LibYUV,

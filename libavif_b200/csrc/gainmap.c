@@ -229,10 +229,11 @@ static int onDevice(const void * p)
         }                                                                    \
     } while (0)
 
-avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
-                                    avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap, float hdrHeadroom,
-                                    avifColorPrimaries outputColorPrimaries, avifTransferCharacteristics outputTransferCharacteristics,
-                                    avifRGBImage * toneMappedImage, avifContentLightLevelInformationBox * clli, avifDiagnostics * diag)
+/* deviceOut: toneMappedImage->pixels / rowBytes are the caller's DEVICE buffer (nothing is allocated or copied back) */
+static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                              avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap, float hdrHeadroom,
+                              avifColorPrimaries outputColorPrimaries, avifTransferCharacteristics outputTransferCharacteristics,
+                              avifRGBImage * toneMappedImage, avifContentLightLevelInformationBox * clli, avifDiagnostics * diag, int deviceOut)
 {
     diagClear(diag);
     if (hdrHeadroom < 0.0f) {
@@ -251,10 +252,18 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
         (gainMap->useBaseColorSpace || gainMap->altColorPrimaries == AVIF_COLOR_PRIMARIES_UNSPECIFIED) ? baseColorPrimaries : gainMap->altColorPrimaries;
     const int needIn = (baseColorPrimaries != mathPrimaries), needOut = (mathPrimaries != outputColorPrimaries);
 
-    toneMappedImage->width = width;
-    toneMappedImage->height = height;
-    res = avifRGBImageAllocatePixels(toneMappedImage);
-    if (res != AVIF_RESULT_OK) return res;
+    if (deviceOut) {
+        if (!toneMappedImage->pixels || toneMappedImage->width != width || toneMappedImage->height != height ||
+            (size_t)toneMappedImage->rowBytes < (size_t)width * avifRGBImagePixelSize(toneMappedImage)) {
+            diagSet(diag, "device output must be allocated by the caller with the base image's dimensions");
+            return AVIF_RESULT_INVALID_ARGUMENT;
+        }
+    } else {
+        toneMappedImage->width = width;
+        toneMappedImage->height = height;
+        res = avifRGBImageAllocatePixels(toneMappedImage);
+        if (res != AVIF_RESULT_OK) return res;
+    }
 
     uint8_t *dBase = NULL, *dGain = NULL, *dOut = NULL, *dStats = NULL;
     const float weight = gainMapWeight(hdrHeadroom, gainMap);
@@ -264,7 +273,7 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
         baseImage->format == toneMappedImage->format && baseImage->depth == toneMappedImage->depth && baseImage->isFloat == toneMappedImage->isFloat &&
         baseImage->rowBytes == toneMappedImage->rowBytes) {
         const size_t n = (size_t)baseImage->rowBytes * baseImage->height;
-        GM_CUDA(cudaMemcpy(toneMappedImage->pixels, baseImage->pixels, n, cudaMemcpyDefault)); /* base may live on the device */
+        GM_CUDA(cudaMemcpy(toneMappedImage->pixels, baseImage->pixels, n, cudaMemcpyDefault)); /* either side may live on the device */
         return AVIF_RESULT_OK;
     }
 
@@ -330,7 +339,8 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
             goto cleanup;
         }
         rgbGain.rowBytes = (uint32_t)(((size_t)width * job.gainFmt.pixBytes + 255) & ~(size_t)255);
-        GM_CUDA(cudaMalloc((void **)&dGain, (size_t)rgbGain.rowBytes * height));
+        GM_CUDA(cudaMallocAsync((void **)&dGain, (size_t)rgbGain.rowBytes * height, NULL));
+        GM_CUDA(cudaStreamSynchronize(NULL)); /* the conversion below runs on the library's own streams */
         rgbGain.pixels = dGain;
         res = avifImageYUVToRGB(gmImage, &rgbGain);
         if (res != AVIF_RESULT_OK) goto cleanup;
@@ -352,7 +362,7 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
     } else {
         const size_t rowUsed = (size_t)width * job.baseFmt.pixBytes;
         const size_t pitch = (rowUsed + 255) & ~(size_t)255;
-        GM_CUDA(cudaMalloc((void **)&dBase, pitch * height));
+        GM_CUDA(cudaMallocAsync((void **)&dBase, pitch * height, NULL));
         GM_CUDA(cudaMemcpy2D(dBase, pitch, baseImage->pixels, baseImage->rowBytes, rowUsed, height, cudaMemcpyHostToDevice));
         job.base = dBase;
         job.baseRB = (int64_t)pitch;
@@ -360,11 +370,16 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
     {
         const size_t rowUsed = (size_t)width * job.outFmt.pixBytes;
         const size_t pitch = (rowUsed + 255) & ~(size_t)255;
-        GM_CUDA(cudaMalloc((void **)&dOut, pitch * height));
-        job.out = dOut;
-        job.outRB = (int64_t)pitch;
+        if (deviceOut) {
+            job.out = toneMappedImage->pixels;
+            job.outRB = toneMappedImage->rowBytes;
+        } else {
+            GM_CUDA(cudaMallocAsync((void **)&dOut, pitch * height, NULL));
+            job.out = dOut;
+            job.outRB = (int64_t)pitch;
+        }
         struct { double sum; uint32_t maxBits, nanIndex; } stats = { 0.0, 0u, 0xFFFFFFFFu };
-        GM_CUDA(cudaMalloc((void **)&dStats, sizeof(stats)));
+        GM_CUDA(cudaMallocAsync((void **)&dStats, sizeof(stats), NULL));
         GM_CUDA(cudaMemcpy(dStats, &stats, sizeof(stats), cudaMemcpyHostToDevice));
         job.sum = (double *)dStats;
         job.maxBits = (uint32_t *)(dStats + offsetof(__typeof__(stats), maxBits));
@@ -376,7 +391,7 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
             res = AVIF_RESULT_INVALID_TONE_MAPPED_IMAGE;
             goto cleanup;
         }
-        GM_CUDA(cudaMemcpy2D(toneMappedImage->pixels, toneMappedImage->rowBytes, dOut, pitch, rowUsed, height, cudaMemcpyDeviceToHost));
+        if (!deviceOut) GM_CUDA(cudaMemcpy2D(toneMappedImage->pixels, toneMappedImage->rowBytes, dOut, pitch, rowUsed, height, cudaMemcpyDeviceToHost));
         if (clli && job.applyGain) { /* src/gainmap.c:297-306 */
             float rgbMaxLinear;
             memcpy(&rgbMaxLinear, &stats.maxBits, sizeof(rgbMaxLinear));
@@ -394,11 +409,30 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
     res = AVIF_RESULT_OK;
 
 cleanup:
-    if (dBase) (void)cudaFree(dBase);
-    if (dGain) (void)cudaFree(dGain);
-    if (dOut) (void)cudaFree(dOut);
-    if (dStats) (void)cudaFree(dStats);
+    if (dBase) (void)cudaFreeAsync(dBase, NULL);
+    if (dGain) (void)cudaFreeAsync(dGain, NULL);
+    if (dOut) (void)cudaFreeAsync(dOut, NULL);
+    if (dStats) (void)cudaFreeAsync(dStats, NULL);
     return res;
+}
+
+avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                                    avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap, float hdrHeadroom,
+                                    avifColorPrimaries outputColorPrimaries, avifTransferCharacteristics outputTransferCharacteristics,
+                                    avifRGBImage * toneMappedImage, avifContentLightLevelInformationBox * clli, avifDiagnostics * diag)
+{
+    return applyCommon(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
+                       outputTransferCharacteristics, toneMappedImage, clli, diag, 0);
+}
+/* extension: everything stays on the device -- base pixels, the gain map's planes and the caller-allocated output */
+avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                                              avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap,
+                                              float hdrHeadroom, avifColorPrimaries outputColorPrimaries,
+                                              avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
+                                              avifContentLightLevelInformationBox * clli, avifDiagnostics * diag)
+{
+    return applyCommon(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
+                       outputTransferCharacteristics, toneMappedImage, clli, diag, 1);
 }
 
 /* src/gainmap.c:317-360 */
@@ -419,7 +453,7 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
     if (!baseImage->width || !baseImage->height) return AVIF_RESULT_INVALID_ARGUMENT;
     baseRgb.rowBytes = baseImage->width * pixBytes;
     uint8_t * dev = NULL;
-    if (cudaMalloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess) {
+    if (cudaMallocAsync((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height, NULL) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
         (void)cudaGetLastError();
         return AVIF_RESULT_OUT_OF_MEMORY;
     }
@@ -429,6 +463,6 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
         res = avifRGBImageApplyGainMap(&baseRgb, baseImage->colorPrimaries, baseImage->transferCharacteristics, gainMap, hdrHeadroom,
                                        outputColorPrimaries, outputTransferCharacteristics, toneMappedImage, clli, diag);
     }
-    (void)cudaFree(dev);
+    (void)cudaFreeAsync(dev, NULL);
     return res;
 }

@@ -47,3 +47,33 @@ for name, w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, back in CASES:
             assert lib.avifB200ImageRGBToYUVAsync(dst.ptr(), rgb.ptr(), sptr) == 0
         torch.cuda.synchronize()
         print(name, "back", lib.avifB200LastKernelName().decode())
+
+# gain-map tone mapping: 4K sRGB RGBA8 base + 8-bit 4:4:4 gain map -> PQ RGBA10, device resident
+import numpy as np  # noqa: E402
+
+g = np.random.RandomState(77)
+W, H = 3840, 2160
+base = RGBImage(W, H, 8, 1, device=dev)
+base.buf.set(g.randint(0, 256, size=(base.buf.rows, base.buf.row_bytes)).astype(np.uint8))
+gimg = YUVImage(W, H, 8, 1, 1, 6, alpha=False, device=dev)
+for p in gimg.present_planes():
+    b = gimg.bufs[p]
+    b.set(g.randint(0, 256, size=(b.rows, b.row_bytes)).astype(np.uint8))
+gm = A.avifGainMap()
+gm.image = ctypes.pointer(gimg.c)
+for c in range(3):
+    gm.gainMapMin[c].n, gm.gainMapMin[c].d = 0, 1
+    gm.gainMapMax[c].n, gm.gainMapMax[c].d = 3, 1
+    gm.gainMapGamma[c].n, gm.gainMapGamma[c].d = 1, 1
+    gm.baseOffset[c].n, gm.baseOffset[c].d = 1, 64
+    gm.alternateOffset[c].n, gm.alternateOffset[c].d = 1, 64
+gm.baseHdrHeadroom.n, gm.baseHdrHeadroom.d = 0, 1
+gm.alternateHdrHeadroom.n, gm.alternateHdrHeadroom.d = 3, 1
+gm.useBaseColorSpace, gm.altColorPrimaries = 1, 2
+dst = RGBImage(W, H, 10, 1, device=dev)
+clli, diag = A.avifContentLightLevelInformationBox(), A.avifDiagnostics()
+for _ in range(2):
+    assert lib.avifB200RGBImageApplyGainMapDevice(base.ptr(), 1, 13, ctypes.byref(gm), ctypes.c_float(2.0), 9, 16, dst.ptr(),
+                                                  ctypes.byref(clli), ctypes.byref(diag)) == 0, diag.error
+torch.cuda.synchronize()
+print("TM tone_map_kernel", clli.maxCLL, clli.maxPALL)
