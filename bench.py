@@ -587,7 +587,7 @@ def run_tone_map(lib, dev, stream, peak_gbs):
     res = {"api": "avifB200RGBImageApplyGainMapDevice (gain map YUV->RGB + tone-map kernel + statistics read-back per call)",
            "us_per_frame": ms * 1e3, "Mpixels_per_s": W * H / (ms * 1e-3) / 1e6, "alg_bytes_per_px": 15,
            "achieved_gbs": 15 * W * H / (ms * 1e-3) / 1e9, "frac_of_peak": 15 * W * H / (ms * 1e-3) / 1e9 / peak_gbs,
-           "bound": "SFU/FMA issue (9 powf + 3 exp2f per pixel), not HBM", "maxCLL": clli.maxCLL, "maxPALL": clli.maxPALL}
+           "bound": "SFU/FMA issue (the output transfer function, 3-6 powf per pixel, after every per-code function is tabulated), not HBM", "maxCLL": clli.maxCLL, "maxPALL": clli.maxPALL}
     try:
         from oracle import loader
         ref = loader.load_reference()

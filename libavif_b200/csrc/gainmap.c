@@ -219,6 +219,42 @@ static int onDevice(const void * p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+/* Scratch (converted gain map, staged base, output, tables) comes from a stream-ordered pool that keeps what it has been
+ * given: the default pool hands freed memory back to the driver at every synchronisation (release threshold 0), which
+ * turns each call into milliseconds of mapping work. */
+static cudaError_t scratchAlloc(void ** p, size_t bytes)
+{
+    enum { kMaxDevices = 64 };
+    static cudaMemPool_t pools[kMaxDevices];
+    static int made[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaMallocAsync(p, bytes, NULL);
+    if (!__atomic_load_n(&made[dev], __ATOMIC_ACQUIRE)) {
+        static int lock = 0;
+        while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {
+        }
+        if (!made[dev]) {
+            struct cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&pools[dev], &props);
+            if (e == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                e = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            if (e == cudaSuccess) __atomic_store_n(&made[dev], 1, __ATOMIC_RELEASE);
+        }
+        __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pools[dev], NULL);
+}
+
 #define GM_CUDA(call)                                                        \
     do {                                                                     \
         if ((call) != cudaSuccess) {                                         \
@@ -265,7 +301,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         if (res != AVIF_RESULT_OK) return res;
     }
 
-    uint8_t *dBase = NULL, *dGain = NULL, *dOut = NULL, *dStats = NULL;
+    uint8_t *dBase = NULL, *dGain = NULL, *dOut = NULL, *dStats = NULL, *dLut = NULL;
     const float weight = gainMapWeight(hdrHeadroom, gainMap);
 
     /* src/gainmap.c:120-128: nothing to apply and nothing to convert -> the base image, byte for byte */
@@ -339,7 +375,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
             goto cleanup;
         }
         rgbGain.rowBytes = (uint32_t)(((size_t)width * job.gainFmt.pixBytes + 255) & ~(size_t)255);
-        GM_CUDA(cudaMallocAsync((void **)&dGain, (size_t)rgbGain.rowBytes * height, NULL));
+        GM_CUDA(scratchAlloc((void **)&dGain, (size_t)rgbGain.rowBytes * height));
         GM_CUDA(cudaStreamSynchronize(NULL)); /* the conversion below runs on the library's own streams */
         rgbGain.pixels = dGain;
         res = avifImageYUVToRGB(gmImage, &rgbGain);
@@ -355,6 +391,16 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         }
     }
 
+    /* per-code tables (tone_lut_kernel): one float per possible stored code of the base (unless half float) and three per
+     * possible code of the gain map */
+    job.baseLutN = (job.baseFmt.isFloat || !(job.applyGain || job.transcode)) ? 0u : ((job.baseFmt.chanBytes == 1) ? 256u : 65536u);
+    job.gainLutN = job.applyGain ? ((job.gainFmt.chanBytes == 1) ? 256u : 65536u) : 0u;
+    if (job.baseLutN + job.gainLutN) {
+        GM_CUDA(scratchAlloc((void **)&dLut, ((size_t)job.baseLutN + 3u * (size_t)job.gainLutN) * sizeof(float)));
+        job.baseLut = (float *)dLut;
+        job.gainLut = (float *)dLut + job.baseLutN;
+    }
+
     /* base pixels: used in place when already on the device */
     if (onDevice(baseImage->pixels)) {
         job.base = baseImage->pixels;
@@ -362,7 +408,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
     } else {
         const size_t rowUsed = (size_t)width * job.baseFmt.pixBytes;
         const size_t pitch = (rowUsed + 255) & ~(size_t)255;
-        GM_CUDA(cudaMallocAsync((void **)&dBase, pitch * height, NULL));
+        GM_CUDA(scratchAlloc((void **)&dBase, pitch * height));
         GM_CUDA(cudaMemcpy2D(dBase, pitch, baseImage->pixels, baseImage->rowBytes, rowUsed, height, cudaMemcpyHostToDevice));
         job.base = dBase;
         job.baseRB = (int64_t)pitch;
@@ -374,12 +420,12 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
             job.out = toneMappedImage->pixels;
             job.outRB = toneMappedImage->rowBytes;
         } else {
-            GM_CUDA(cudaMallocAsync((void **)&dOut, pitch * height, NULL));
+            GM_CUDA(scratchAlloc((void **)&dOut, pitch * height));
             job.out = dOut;
             job.outRB = (int64_t)pitch;
         }
         struct { double sum; uint32_t maxBits, nanIndex; } stats = { 0.0, 0u, 0xFFFFFFFFu };
-        GM_CUDA(cudaMallocAsync((void **)&dStats, sizeof(stats), NULL));
+        GM_CUDA(scratchAlloc((void **)&dStats, sizeof(stats)));
         GM_CUDA(cudaMemcpy(dStats, &stats, sizeof(stats), cudaMemcpyHostToDevice));
         job.sum = (double *)dStats;
         job.maxBits = (uint32_t *)(dStats + offsetof(__typeof__(stats), maxBits));
@@ -413,6 +459,7 @@ cleanup:
     if (dGain) (void)cudaFreeAsync(dGain, NULL);
     if (dOut) (void)cudaFreeAsync(dOut, NULL);
     if (dStats) (void)cudaFreeAsync(dStats, NULL);
+    if (dLut) (void)cudaFreeAsync(dLut, NULL);
     return res;
 }
 
@@ -453,7 +500,7 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
     if (!baseImage->width || !baseImage->height) return AVIF_RESULT_INVALID_ARGUMENT;
     baseRgb.rowBytes = baseImage->width * pixBytes;
     uint8_t * dev = NULL;
-    if (cudaMallocAsync((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height, NULL) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
+    if (scratchAlloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
         (void)cudaGetLastError();
         return AVIF_RESULT_OUT_OF_MEMORY;
     }

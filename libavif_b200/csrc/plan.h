@@ -200,6 +200,11 @@ typedef struct AbToneMapJob {
     double inM[9], outM[9];
     float gammaInv[3], gmMin[3], gmMax[3], baseOff[3], altOff[3];
     float weight;
+    /* per-call tables indexed by a stored code (tonemap.cu: tone_lut_kernel); N = 256 or 65536 by container, 0 = not tabulated.
+     * gainLut must be present whenever applyGain is set. */
+    float * baseLut; /* [baseLutN]      to_linear(code / max) */
+    float * gainLut; /* [3][gainLutN]   exp2f(lerp(min, max, powf(code / max, 1/gamma)) * weight) per channel */
+    uint32_t baseLutN, gainLutN;
     /* results: [0] = max over every tone-mapped linear channel value (as float bits; values <= 0 never raise it),
      * nanIndex = smallest y*width+x whose output is NaN (0xFFFFFFFF if none), sum = sum over pixels of max(r,g,b,0) */
     uint32_t * maxBits;
