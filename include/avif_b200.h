@@ -308,6 +308,9 @@ AVIF_B200_API avifResult avifImageApplyGainMap(const avifImage * baseImage, cons
                                                avifColorPrimaries outputColorPrimaries,
                                                avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
                                                avifContentLightLevelInformationBox * clli, avifDiagnostics * diag);
+/* src/scale.c:203-207: scales the YUV / alpha planes in place (new planes, owned by the image) with the vendored libyuv's
+ * kFilterBox arithmetic (third_party/libyuv/source/scale*.c), bit for bit.  Host planes. */
+AVIF_B200_API avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeight, avifDiagnostics * diag);
 #endif /* AVIF_AVIF_H */
 
 /* ---- internal seam of the reference (include/avif/internal.h:259-278), exported for drop-in at B-2 ---- */
@@ -399,6 +402,10 @@ AVIF_B200_API avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage *
                                                             float hdrHeadroom, avifColorPrimaries outputColorPrimaries,
                                                             avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
                                                             avifContentLightLevelInformationBox * clli, avifDiagnostics * diag);
+
+/* The same scaler between resident planes: src planes may be host or device pointers, dst's planes are DEVICE buffers the
+ * caller allocated (width, height, row strides set; planes that are NULL on either side are skipped). */
+AVIF_B200_API avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst);
 
 /* ---- B-2: the reference's internal seam (include/avif/internal.h:350-387) ------------------------------------------
  * libavif_b200_hooks.so exports the six functions src/reformat.c and src/alpha.c call before their built-in loops

@@ -301,7 +301,8 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         if (res != AVIF_RESULT_OK) return res;
     }
 
-    uint8_t *dBase = NULL, *dGain = NULL, *dOut = NULL, *dStats = NULL, *dLut = NULL;
+    uint8_t *dBase = NULL, *dGain = NULL, *dOut = NULL, *dStats = NULL, *dLut = NULL, *dScaled[3] = { NULL, NULL, NULL };
+    avifImage scaled;
     const float weight = gainMapWeight(hdrHeadroom, gainMap);
 
     /* src/gainmap.c:120-128: nothing to apply and nothing to convert -> the base image, byte for byte */
@@ -360,11 +361,35 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
             goto cleanup;
         }
         if (gmImage->width != width || gmImage->height != height) {
-            /* the reference rescales with avifImageScale (libyuv box/bilinear, src/gainmap.c:186-201; SURVEY 8f-4: not built) */
-            diagSet(diag, "gain map is %ux%u, base image %ux%u: rescaling (avifImageScale) is not implemented on this path", gmImage->width,
-                    gmImage->height, width, height);
-            res = AVIF_RESULT_NOT_IMPLEMENTED;
-            goto cleanup;
+            /* src/gainmap.c:186-201: the gain map is brought to the base image's size with avifImageScale (libyuv's box /
+             * bilinear integer scaler, csrc/scale.c + scale_kernels.cu) -- here straight into device planes */
+            scaled = *gmImage;
+            scaled.width = width;
+            scaled.height = height;
+            scaled.alphaPlane = NULL; /* a gain map's alpha never reaches the tone mapper */
+            scaled.alphaRowBytes = 0;
+            scaled.imageOwnsYUVPlanes = AVIF_FALSE;
+            scaled.imageOwnsAlphaPlane = AVIF_FALSE;
+            avifPixelFormatInfo fi;
+            avifGetPixelFormatInfo(gmImage->yuvFormat, &fi);
+            const uint32_t cs = (gmImage->depth > 8) ? 2 : 1;
+            for (int c = 0; c < 3; ++c) {
+                scaled.yuvPlanes[c] = NULL;
+                scaled.yuvRowBytes[c] = 0;
+                if (!gmImage->yuvPlanes[c] || (c > 0 && fi.monochrome)) continue;
+                const uint32_t pw = c ? (uint32_t)(((uint64_t)width + fi.chromaShiftX) >> fi.chromaShiftX) : width;
+                const uint32_t ph = c ? (uint32_t)(((uint64_t)height + fi.chromaShiftY) >> fi.chromaShiftY) : height;
+                const size_t pitch = ((size_t)pw * cs + 255) & ~(size_t)255;
+                GM_CUDA(scratchAlloc((void **)&dScaled[c], pitch * ph));
+                scaled.yuvPlanes[c] = dScaled[c];
+                scaled.yuvRowBytes[c] = (uint32_t)pitch;
+            }
+            res = avifB200ImageScaleToDevice(gmImage, &scaled);
+            if (res != AVIF_RESULT_OK) {
+                diagSet(diag, "scaling the gain map from %ux%u to %ux%u failed", gmImage->width, gmImage->height, width, height);
+                goto cleanup;
+            }
+            gmImage = &scaled;
         }
         /* src/gainmap.c:203-212: the gain map as RGBA of its own depth, through the product's YUV -> RGB (device destination) */
         avifRGBImage rgbGain;
@@ -460,6 +485,9 @@ cleanup:
     if (dOut) (void)cudaFreeAsync(dOut, NULL);
     if (dStats) (void)cudaFreeAsync(dStats, NULL);
     if (dLut) (void)cudaFreeAsync(dLut, NULL);
+    for (int c = 0; c < 3; ++c) {
+        if (dScaled[c]) (void)cudaFreeAsync(dScaled[c], NULL);
+    }
     return res;
 }
 

@@ -213,6 +213,25 @@ typedef struct AbToneMapJob {
 } AbToneMapJob;
 int abLaunchToneMap(const AbToneMapJob * job, void * stream);
 
+/* ---- plane scaling (scale_kernels.cu; src/scale.c over third_party/libyuv/source/scale*.c) ----
+ * The host walks libyuv's 16.16 stepping state machines once per plane (scale.c here: O(width + height) integer work, no
+ * pixels) and hands the kernel two tables; every sample operation happens on the device. */
+enum { AB_SCALE_VERTICAL = 1, AB_SCALE_SIMPLE, AB_SCALE_BILINEAR_DOWN, AB_SCALE_BILINEAR_UP, AB_SCALE_UP2_LINEAR, AB_SCALE_UP2_BILINEAR, AB_SCALE_BOX };
+typedef struct AbScaleJob {
+    const uint8_t * src;
+    uint8_t * dst;
+    int64_t srcRB, dstRB; /* bytes */
+    int32_t srcW, srcH, dstW, dstH;
+    uint8_t bps;        /* bytes per sample: 1 or 2 */
+    uint8_t mode;       /* AB_SCALE_* */
+    uint8_t linearOnly; /* kFilterLinear: horizontal filter only */
+    uint8_t pad;
+    int32_t minBoxWidth; /* box: dx >> 16 (or the constant box width) */
+    const int32_t * rows; /* 4 ints per destination row, meaning depends on mode (scale_kernels.cu) */
+    const int32_t * cols; /* 4 ints per destination column */
+} AbScaleJob;
+int abLaunchScale(const AbScaleJob * job, void * stream);
+
 /* Launchers (kernels.cu).  `stream` is a cudaStream_t.  Return 0 on success, else a cudaError_t value.
  * `forceGeneric` selects the byte-addressed reference kernel instead of the tiled/vectorised one. */
 int abLaunchY2R(const AbY2RJob * job, void * stream, int forceGeneric, const char ** kernelName);

@@ -1,0 +1,486 @@
+/*
+ * scale.c -- host side of avifImageScale: the reference's checks and plane bookkeeping (src/scale.c:24-201)
+ * and libyuv's stepping state machines (third_party/libyuv/source/scale.c, scale_common.c in the reference tree), walked once
+ * per plane to tabulate, for every destination row and column, the source positions the reference's loops would visit.
+ * Only integers about POSITIONS are computed here (O(width + height)); every sample is read, filtered and written by
+ * scale_kernels.cu on the device.  No CPU pixel arithmetic, no fallback.
+ */
+#define AVIF_B200_BUILDING
+#include "avif_b200.h"
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "plan.h"
+
+enum { F_NONE = 0, F_LINEAR = 1, F_BILINEAR = 2, F_BOX = 3 }; /* libyuv FilterMode, include/libyuv/scale.h:17-22 */
+
+/* scale_common.c:428-469 */
+static int filterReduce(int sw, int sh, int dw, int dh, int f)
+{
+    if (f == F_BOX && (dw * 2 >= sw || dh * 2 >= sh)) f = F_BILINEAR;
+    if (f == F_BILINEAR) {
+        if (sh == 1) f = F_LINEAR;
+        if (dh == sh || dh * 3 == sh) f = F_LINEAR;
+        if (sw == 1) f = F_NONE;
+    }
+    if (f == F_LINEAR) {
+        if (sw == 1) f = F_NONE;
+        if (dw == sw || dw * 3 == sw) f = F_NONE;
+    }
+    return f;
+}
+static int fixedDiv(int num, int div) { return (int)(((int64_t)num << 16) / div); }                        /* :472-474 */
+static int fixedDiv1(int num, int div) { return (int)((((int64_t)num << 16) - 0x00010001) / (div - 1)); } /* :477-479 */
+static int centerStart(int d, int s) { return (d < 0) ? -((-d >> 1) + s) : ((d >> 1) + s); }              /* CENTERSTART */
+static int min1(int v) { return v < 1 ? 1 : v; }
+
+/* scale_common.c:484-553 for positive widths; outputs keep their previous value where the reference leaves them untouched */
+static void slope(int sw, int sh, int dw, int dh, int f, int * x, int * y, int * dx, int * dy)
+{
+    if (dw == 1 && sw >= 32768) dw = sw;
+    if (dh == 1 && sh >= 32768) dh = sh;
+    if (f == F_BOX) {
+        *dx = fixedDiv(sw, dw);
+        *dy = fixedDiv(sh, dh);
+        *x = 0;
+        *y = 0;
+    } else if (f == F_BILINEAR) {
+        if (dw <= sw) {
+            *dx = fixedDiv(sw, dw);
+            *x = centerStart(*dx, -32768);
+        } else if (sw > 1 && dw > 1) {
+            *dx = fixedDiv1(sw, dw);
+            *x = 0;
+        }
+        if (dh <= sh) {
+            *dy = fixedDiv(sh, dh);
+            *y = centerStart(*dy, -32768);
+        } else if (sh > 1 && dh > 1) {
+            *dy = fixedDiv1(sh, dh);
+            *y = 0;
+        }
+    } else if (f == F_LINEAR) {
+        if (dw <= sw) {
+            *dx = fixedDiv(sw, dw);
+            *x = centerStart(*dx, -32768);
+        } else if (sw > 1 && dw > 1) {
+            *dx = fixedDiv1(sw, dw);
+            *x = 0;
+        }
+        *dy = fixedDiv(sh, dh);
+        *y = *dy >> 1;
+    } else {
+        *dx = fixedDiv(sw, dw);
+        *dy = fixedDiv(sh, dh);
+        *x = centerStart(*dx, 0);
+        *y = centerStart(*dy, 0);
+    }
+}
+
+typedef struct ScalePlan {
+    int mode; /* 0 = straight copy */
+    int linearOnly;
+    int minBoxWidth;
+    int32_t * rows; /* 4 per destination row */
+    int32_t * cols; /* 4 per destination column */
+} ScalePlan;
+
+static void planFree(ScalePlan * p)
+{
+    free(p->rows);
+    free(p->cols);
+    p->rows = p->cols = NULL;
+}
+
+/* positions of ScaleFilterCols / ScaleCols: x, x+dx, ... (scale_common.c:114-130, :197-222) */
+static void colsStepped(ScalePlan * p, int dw, int x, int dx)
+{
+    for (int i = 0; i < dw; ++i) {
+        p->cols[4 * i + 0] = x >> 16;
+        p->cols[4 * i + 1] = x & 0xffff;
+        x += dx;
+    }
+}
+
+/* The dispatch of ScalePlane (scale.c:829-897), ScalePlane_16 (:899-971) and ScalePlane_12 (:973-1007) for kFilterBox, and
+ * the row / column walk of the loop it lands in. */
+static int planScale(int sw, int sh, int dw, int dh, int sixteen, ScalePlan * p)
+{
+    memset(p, 0, sizeof(*p));
+    const int f = filterReduce(sw, sh, dw, dh, F_BOX);
+    int mode = -1;
+    if (sixteen) { /* ScalePlane_12 tries its own 2x paths first */
+        if ((dw + 1) / 2 == sw && f == F_LINEAR) mode = AB_SCALE_UP2_LINEAR;
+        else if ((dh + 1) / 2 == sh && (dw + 1) / 2 == sw && (f == F_BILINEAR || f == F_BOX)) mode = AB_SCALE_UP2_BILINEAR;
+    }
+    if (mode < 0) {
+        if (dw == sw && dh == sh) mode = 0;
+        else if (dw == sw && f != F_BOX) mode = AB_SCALE_VERTICAL;
+        else if (f == F_BOX && dh * 2 < sh) mode = AB_SCALE_BOX;
+        else if ((dw + 1) / 2 == sw && f == F_LINEAR) mode = AB_SCALE_UP2_LINEAR;
+        else if ((dh + 1) / 2 == sh && (dw + 1) / 2 == sw && (f == F_BILINEAR || f == F_BOX)) mode = AB_SCALE_UP2_BILINEAR;
+        else if (f && dh > sh) mode = AB_SCALE_BILINEAR_UP;
+        else if (f) mode = AB_SCALE_BILINEAR_DOWN;
+        else mode = AB_SCALE_SIMPLE;
+    }
+    p->mode = mode;
+    if (mode == 0) return 1;
+    p->rows = (int32_t *)calloc((size_t)dh * 4, sizeof(int32_t));
+    p->cols = (int32_t *)calloc((size_t)dw * 4, sizeof(int32_t));
+    if (!p->rows || !p->cols) {
+        planFree(p);
+        return 0;
+    }
+    int x = 0, y = 0, dx = 0, dy = 0;
+    switch (mode) {
+        case AB_SCALE_VERTICAL: { /* scale.c:855-871 + scale_common.c:348-386 */
+            if (dh <= sh) {
+                dy = fixedDiv(sh, dh);
+                y = centerStart(dy, -32768);
+            } else if (sh > 1 && dh > 1) {
+                dy = fixedDiv1(sh, dh);
+            }
+            const int maxY = (sh > 1) ? ((sh - 1) << 16) - 1 : 0;
+            for (int j = 0; j < dh; ++j) {
+                if (y > maxY) y = maxY;
+                p->rows[4 * j + 0] = y >> 16;
+                p->rows[4 * j + 1] = f ? ((y >> 8) & 255) : 0;
+                y += dy;
+            }
+            break;
+        }
+        case AB_SCALE_BOX: { /* scale.c:148-198 / :200-256 */
+            slope(sw, sh, dw, dh, F_BOX, &x, &y, &dx, &dy);
+            const int maxY = sh << 16;
+            for (int j = 0; j < dh; ++j) {
+                const int iy = y >> 16;
+                y += dy;
+                if (y > maxY) y = maxY;
+                p->rows[4 * j + 0] = iy;
+                p->rows[4 * j + 1] = min1((y >> 16) - iy);
+            }
+            if (dx & 0xffff) { /* ScaleAddCols2: two box widths */
+                p->minBoxWidth = dx >> 16;
+                for (int i = 0; i < dw; ++i) {
+                    const int ix = x >> 16;
+                    x += dx;
+                    const int bw = min1((x >> 16) - ix);
+                    p->cols[4 * i + 0] = ix;
+                    p->cols[4 * i + 1] = bw;
+                    p->cols[4 * i + 2] = bw - p->minBoxWidth;
+                }
+            } else { /* ScaleAddCols1 (and ScaleAddCols0 when dx == 1.0): one box width */
+                const int bw = min1(dx >> 16);
+                p->minBoxWidth = bw;
+                int xs = x >> 16;
+                for (int i = 0; i < dw; ++i) {
+                    p->cols[4 * i + 0] = xs;
+                    p->cols[4 * i + 1] = bw;
+                    xs += bw;
+                }
+            }
+            break;
+        }
+        case AB_SCALE_UP2_LINEAR: { /* scale.c:467-501 */
+            if (dh == 1) {
+                p->rows[0] = (sh - 1) / 2;
+            } else {
+                dy = fixedDiv(sh - 1, dh - 1);
+                y = (1 << 15) - 1;
+                for (int j = 0; j < dh; ++j) {
+                    p->rows[4 * j + 0] = y >> 16;
+                    y += dy;
+                }
+            }
+            break;
+        }
+        case AB_SCALE_UP2_BILINEAR: break; /* positions follow from (i, j) alone */
+        case AB_SCALE_BILINEAR_UP: { /* scale.c:371-466: two cached filtered rows; which source rows they hold is state */
+            slope(sw, sh, dw, dh, f, &x, &y, &dx, &dy);
+            const int maxY = (sh - 1) << 16;
+            if (y > maxY) y = maxY;
+            int yi = y >> 16;
+            int src = yi;          /* row the reference's `src` pointer is at */
+            int bufA = src;        /* row held at rowptr */
+            if (sh > 1) ++src;
+            int bufB = src;        /* row held at rowptr + rowstride */
+            if (sh > 2) ++src;
+            int lasty = yi;
+            for (int j = 0; j < dh; ++j) {
+                yi = y >> 16;
+                if (yi != lasty) {
+                    if (y > maxY) {
+                        y = maxY;
+                        yi = y >> 16;
+                        src = yi;
+                    }
+                    if (yi != lasty) {
+                        bufA = src; /* filtered into rowptr ... */
+                        const int t = bufA;
+                        bufA = bufB; /* ... then the buffers swap roles */
+                        bufB = t;
+                        lasty = yi;
+                        if ((y + 65536) < maxY) ++src;
+                    }
+                }
+                p->rows[4 * j + 0] = bufA;
+                p->rows[4 * j + 1] = bufB;
+                p->rows[4 * j + 2] = (y >> 8) & 255;
+                y += dy;
+            }
+            p->linearOnly = (f == F_LINEAR);
+            colsStepped(p, dw, x, dx);
+            break;
+        }
+        case AB_SCALE_BILINEAR_DOWN: { /* scale.c:258-312 */
+            slope(sw, sh, dw, dh, f, &x, &y, &dx, &dy);
+            const int maxY = (sh - 1) << 16;
+            if (y > maxY) y = maxY;
+            for (int j = 0; j < dh; ++j) {
+                p->rows[4 * j + 0] = y >> 16;
+                p->rows[4 * j + 1] = (y >> 8) & 255;
+                y += dy;
+                if (y > maxY) y = maxY;
+            }
+            p->linearOnly = (f == F_LINEAR);
+            colsStepped(p, dw, x, dx);
+            break;
+        }
+        default: { /* AB_SCALE_SIMPLE, scale.c:763-793 */
+            slope(sw, sh, dw, dh, F_NONE, &x, &y, &dx, &dy);
+            for (int j = 0; j < dh; ++j) {
+                p->rows[4 * j + 0] = y >> 16;
+                y += dy;
+            }
+            if (sw * 2 == dw && x < 0x8000) { /* ScaleColsUp2 */
+                for (int i = 0; i < dw; ++i) p->cols[4 * i + 0] = i >> 1;
+            } else {
+                colsStepped(p, dw, x, dx);
+            }
+            break;
+        }
+    }
+    return 1;
+}
+
+/* One plane, both ends on the device.  srcRB / dstRB in bytes. */
+static cudaError_t scalePlaneOnDevice(const uint8_t * dSrc, int64_t srcRB, int sw, int sh, uint8_t * dDst, int64_t dstRB, int dw, int dh, int bps,
+                                      int * oom)
+{
+    ScalePlan plan;
+    if (!planScale(sw, sh, dw, dh, bps == 2, &plan)) {
+        *oom = 1;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaSuccess;
+    if (plan.mode == 0) {
+        e = cudaMemcpy2DAsync(dDst, (size_t)dstRB, dSrc, (size_t)srcRB, (size_t)dw * bps, (size_t)dh, cudaMemcpyDeviceToDevice, NULL);
+    } else {
+        int32_t * dTab = NULL;
+        const size_t nr = (size_t)dh * 4, nc = (size_t)dw * 4;
+        e = cudaMallocAsync((void **)&dTab, (nr + nc) * sizeof(int32_t), NULL);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dTab, plan.rows, nr * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dTab + nr, plan.cols, nc * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
+        if (e == cudaSuccess) {
+            AbScaleJob job;
+            memset(&job, 0, sizeof(job));
+            job.src = dSrc;
+            job.dst = dDst;
+            job.srcRB = srcRB;
+            job.dstRB = dstRB;
+            job.srcW = sw;
+            job.srcH = sh;
+            job.dstW = dw;
+            job.dstH = dh;
+            job.bps = (uint8_t)bps;
+            job.mode = (uint8_t)plan.mode;
+            job.linearOnly = (uint8_t)plan.linearOnly;
+            job.minBoxWidth = plan.minBoxWidth;
+            job.rows = dTab;
+            job.cols = dTab + nr;
+            e = (cudaError_t)abLaunchScale(&job, NULL);
+        }
+        /* the tables are pageable host memory: the copies above have been staged before this returns, and the stream-ordered
+         * free runs after the kernel */
+        if (e == cudaSuccess) e = cudaStreamSynchronize(NULL);
+        if (dTab) (void)cudaFreeAsync(dTab, NULL);
+    }
+    planFree(&plan);
+    return e;
+}
+
+static int onDevice(const void * p)
+{
+    struct cudaPointerAttributes at;
+    if (!p) return 0;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static void diagf(avifDiagnostics * diag, const char * msg, unsigned a, unsigned b)
+{
+    if (diag && !diag->error[0]) snprintf(diag->error, sizeof(diag->error), msg, a, b);
+}
+
+/* Extension used by the tone mapper: scale the planes of `src` (host or device pointers) into DEVICE planes described by
+ * `dst` (planes allocated by the caller with cudaMalloc-family calls, dimensions and row strides set). */
+avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
+{
+    if (!src || !dst || !dst->width || !dst->height) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (src->width > 16384 || src->height > 16384) return AVIF_RESULT_NOT_IMPLEMENTED; /* src/scale.c:65-76 */
+    const int bps = (src->depth > 8) ? 2 : 1;
+    avifPixelFormatInfo info;
+    avifGetPixelFormatInfo(src->yuvFormat, &info);
+    avifResult res = AVIF_RESULT_OK;
+    for (int c = 0; c < 4 && res == AVIF_RESULT_OK; ++c) {
+        const uint8_t * sp = (c < 3) ? src->yuvPlanes[c] : src->alphaPlane;
+        uint8_t * dp = (c < 3) ? dst->yuvPlanes[c] : dst->alphaPlane;
+        if (!sp || !dp) continue;
+        const uint32_t srb = (c < 3) ? src->yuvRowBytes[c] : src->alphaRowBytes, drb = (c < 3) ? dst->yuvRowBytes[c] : dst->alphaRowBytes;
+        const int chroma = (c == 1 || c == 2);
+        if (chroma && info.monochrome) continue;
+        const int sw = chroma ? (int)((src->width + info.chromaShiftX) >> info.chromaShiftX) : (int)src->width;
+        const int sh = chroma ? (int)((src->height + info.chromaShiftY) >> info.chromaShiftY) : (int)src->height;
+        const int dw = chroma ? (int)((dst->width + info.chromaShiftX) >> info.chromaShiftX) : (int)dst->width;
+        const int dh = chroma ? (int)((dst->height + info.chromaShiftY) >> info.chromaShiftY) : (int)dst->height;
+        uint8_t * staged = NULL;
+        const uint8_t * dSrc = sp;
+        int64_t dSrcRB = srb;
+        cudaError_t e = cudaSuccess;
+        if (!onDevice(sp)) {
+            const size_t pitch = ((size_t)sw * bps + 255) & ~(size_t)255;
+            e = cudaMallocAsync((void **)&staged, pitch * (size_t)sh, NULL);
+            if (e == cudaSuccess) e = cudaMemcpy2D(staged, pitch, sp, srb, (size_t)sw * bps, (size_t)sh, cudaMemcpyHostToDevice);
+            dSrc = staged;
+            dSrcRB = (int64_t)pitch;
+        }
+        int oom = 0;
+        if (e == cudaSuccess) e = scalePlaneOnDevice(dSrc, dSrcRB, sw, sh, dp, drb, dw, dh, bps, &oom);
+        if (staged) (void)cudaFreeAsync(staged, NULL);
+        if (oom) res = AVIF_RESULT_OUT_OF_MEMORY;
+        else if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            res = (e == cudaErrorMemoryAllocation) ? AVIF_RESULT_OUT_OF_MEMORY : AVIF_RESULT_UNKNOWN_ERROR;
+        }
+    }
+    return res;
+}
+
+/* src/scale.c:24-201 with the default limits of :203-207 */
+avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeight, avifDiagnostics * diag)
+{
+    if (diag) diag->error[0] = '\0';
+    if (image->width == dstWidth && image->height == dstHeight) return AVIF_RESULT_OK;
+    if (!dstWidth || !dstHeight) {
+        diagf(diag, "avifImageScale requested invalid dst dimensions [%ux%u]", dstWidth, dstHeight);
+        return AVIF_RESULT_INVALID_ARGUMENT;
+    }
+    if (dstWidth > (16384u * 16384u) / dstHeight || dstWidth > 32768u || dstHeight > 32768u) { /* avifDimensionsTooLarge, src/avif.c:646-655 */
+        diagf(diag, "avifImageScale requested dst dimensions that are too large [%ux%u]", dstWidth, dstHeight);
+        return AVIF_RESULT_NOT_IMPLEMENTED;
+    }
+    /* the source planes step aside, the image takes the new size (src/scale.c:40-63) */
+    avifImage old = *image;
+    for (int c = 0; c < 3; ++c) {
+        image->yuvPlanes[c] = NULL;
+        image->yuvRowBytes[c] = 0;
+    }
+    image->imageOwnsYUVPlanes = AVIF_FALSE;
+    image->alphaPlane = NULL;
+    image->alphaRowBytes = 0;
+    image->imageOwnsAlphaPlane = AVIF_FALSE;
+    image->width = dstWidth;
+    image->height = dstHeight;
+
+    avifResult res = AVIF_RESULT_OK;
+    uint8_t * dPlanes[4] = { NULL, NULL, NULL, NULL };
+    if ((old.yuvPlanes[0] || old.alphaPlane) && (old.width > 16384 || old.height > 16384)) {
+        diagf(diag, "avifImageScale requested invalid scale for libyuv [%u -> %u]", old.width > 16384 ? old.width : old.height,
+              old.width > 16384 ? dstWidth : dstHeight);
+        res = AVIF_RESULT_NOT_IMPLEMENTED;
+        goto cleanup;
+    }
+    {
+        const uint32_t cs = (image->depth > 8) ? 2 : 1;
+        avifPixelFormatInfo info;
+        avifGetPixelFormatInfo(image->yuvFormat, &info);
+        /* new host planes, like avifImageAllocatePlanes (src/avif.c:431-489): tightly packed rows, owned by the image */
+        avifImage dev = *image; /* the same geometry with device planes: where the kernels write */
+        for (int c = 0; c < 4; ++c) {
+            const int chroma = (c == 1 || c == 2);
+            const uint8_t * sp = (c < 3) ? old.yuvPlanes[c] : old.alphaPlane;
+            const int wanted = (c < 3) ? (old.yuvPlanes[0] != NULL && image->yuvFormat != AVIF_PIXEL_FORMAT_NONE && !(chroma && info.monochrome))
+                                       : (old.alphaPlane != NULL);
+            if (!wanted) continue;
+            const uint32_t w = chroma ? (uint32_t)(((uint64_t)dstWidth + info.chromaShiftX) >> info.chromaShiftX) : dstWidth;
+            const uint32_t h = chroma ? (uint32_t)(((uint64_t)dstHeight + info.chromaShiftY) >> info.chromaShiftY) : dstHeight;
+            uint8_t * host = (uint8_t *)malloc((size_t)cs * w * h);
+            if (!host) {
+                res = AVIF_RESULT_OUT_OF_MEMORY;
+                goto cleanup;
+            }
+            if (c < 3) {
+                image->yuvPlanes[c] = host;
+                image->yuvRowBytes[c] = cs * w;
+                image->imageOwnsYUVPlanes = AVIF_TRUE;
+            } else {
+                image->alphaPlane = host;
+                image->alphaRowBytes = cs * w;
+                image->imageOwnsAlphaPlane = AVIF_TRUE;
+            }
+            if (!sp) continue; /* allocated but not scaled, like src/scale.c:88-91 */
+            const size_t pitch = ((size_t)cs * w + 255) & ~(size_t)255;
+            if (cudaMallocAsync((void **)&dPlanes[c], pitch * h, NULL) != cudaSuccess) {
+                (void)cudaGetLastError();
+                res = AVIF_RESULT_OUT_OF_MEMORY;
+                goto cleanup;
+            }
+            if (c < 3) {
+                dev.yuvPlanes[c] = dPlanes[c];
+                dev.yuvRowBytes[c] = (uint32_t)pitch;
+            } else {
+                dev.alphaPlane = dPlanes[c];
+                dev.alphaRowBytes = (uint32_t)pitch;
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            if (!dPlanes[c]) dev.yuvPlanes[c] = NULL;
+        }
+        if (!dPlanes[3]) dev.alphaPlane = NULL;
+        res = avifB200ImageScaleToDevice(&old, &dev);
+        if (res != AVIF_RESULT_OK) goto cleanup;
+        for (int c = 0; c < 4; ++c) {
+            if (!dPlanes[c]) continue;
+            const int chroma = (c == 1 || c == 2);
+            const uint32_t w = chroma ? (uint32_t)(((uint64_t)dstWidth + info.chromaShiftX) >> info.chromaShiftX) : dstWidth;
+            const uint32_t h = chroma ? (uint32_t)(((uint64_t)dstHeight + info.chromaShiftY) >> info.chromaShiftY) : dstHeight;
+            uint8_t * host = (c < 3) ? image->yuvPlanes[c] : image->alphaPlane;
+            const uint32_t hostRB = (c < 3) ? image->yuvRowBytes[c] : image->alphaRowBytes;
+            const uint32_t devRB = (c < 3) ? dev.yuvRowBytes[c] : dev.alphaRowBytes;
+            if (cudaMemcpy2D(host, hostRB, dPlanes[c], devRB, (size_t)cs * w, h, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                (void)cudaGetLastError();
+                res = AVIF_RESULT_UNKNOWN_ERROR;
+                goto cleanup;
+            }
+        }
+    }
+
+cleanup:
+    for (int c = 0; c < 4; ++c) {
+        if (dPlanes[c]) (void)cudaFreeAsync(dPlanes[c], NULL);
+    }
+    /* the old planes are released if the image owned them (src/scale.c:189-198); on a device box that may be cudaFree'd memory
+     * only if the caller allocated it that way AND handed ownership over, which the reference's avifFree == free forbids too */
+    if (old.yuvPlanes[0] && old.imageOwnsYUVPlanes) {
+        for (int c = 0; c < 3; ++c) free(old.yuvPlanes[c]);
+    }
+    if (old.alphaPlane && old.imageOwnsAlphaPlane) free(old.alphaPlane);
+    return res;
+}

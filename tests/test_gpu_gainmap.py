@@ -191,10 +191,22 @@ def test_nan_and_unsupported_cases_report_like_the_reference(gpu_product, refere
     ra, _, _, _ = apply(reference, base, 1, 13, gm, 3.0, 9, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
     rb, _, _, err = apply(gpu_product, base, 1, 13, gm, 3.0, 9, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
     assert ra == rb, (ra, rb, err)
-    # a gain map of another size needs avifImageScale: declined loudly, never approximated
-    gm2, keep2 = make_gain_map(w // 2, h // 2, seed=12)
-    rb, _, _, err = apply(gpu_product, base, 1, 13, gm2, 3.0, 1, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
-    assert rb == 25 and "avifImageScale" in err
+
+
+@pytest.mark.gpu
+def test_gain_map_of_another_size_is_rescaled_like_the_reference(gpu_product, reference):
+    """src/gainmap.c:186-201: avifImageScale (libyuv box / bilinear) brings the gain map to the base image's size first."""
+    w, h = 96, 64
+    base = make_base(w, h, 8, A.AVIF_RGB_FORMAT_RGBA, seed=31)
+    for gw, gh, fmt in ((48, 32, A.AVIF_PIXEL_FORMAT_YUV444), (24, 16, A.AVIF_PIXEL_FORMAT_YUV420), (200, 150, A.AVIF_PIXEL_FORMAT_YUV400),
+                        (96, 20, A.AVIF_PIXEL_FORMAT_YUV444), (37, 64, A.AVIF_PIXEL_FORMAT_YUV422)):
+        gm, keep = make_gain_map(gw, gh, fmt=fmt, seed=gw * 7 + gh)
+        ra, a, ca, _ = apply(reference, base, 1, 13, gm, 2.0, 1, 13, 10, A.AVIF_RGB_FORMAT_RGBA)
+        rb, b, cb, err = apply(gpu_product, base, 1, 13, gm, 2.0, 1, 13, 10, A.AVIF_RGB_FORMAT_RGBA)
+        assert ra == rb == 0, (gw, gh, ra, rb, err)
+        worst, frac = compare(a, b, 10, False)
+        assert worst <= 1 and frac < 0.02, (gw, gh, fmt, worst, frac)
+        assert abs(ca[0] - cb[0]) <= 1 and abs(ca[1] - cb[1]) <= 1
 
 
 @pytest.mark.gpu
