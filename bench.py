@@ -530,7 +530,65 @@ def run_extras(lib, dev, sptr, stream, peak_gbs):
                                                        "us_per_frame": ms * 1e3 / 16, "us_per_canvas": ms * 1e3, "Mpixels_per_s": 16 * 1920 * 1080 / (ms * 1e-3) / 1e6,
                                                        "alg_bytes_per_px": 6.5, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
     out["TM_4K_gainmap_sRGB8_to_PQ_RGBA10"] = run_tone_map(lib, dev, stream, peak_gbs)
+    out.update(run_scale(lib, dev, stream, peak_gbs))
     return out
+
+
+def run_scale(lib, dev, stream, peak_gbs):
+    """avifImageScale's device scaler (avifB200ImageScaleToDevice, planes resident) for a box downscale and a 2x
+    upscale of 4:2:0 8-bit + alpha, and the reference's src/scale.c + libyuv on one host core for the same sizes."""
+    import ctypes
+    import numpy as np
+    import torch
+    from libavif_b200 import abi as A
+    from libavif_b200.images import YUVImage
+    res = {}
+    for name, (sw, sh, dw, dh) in {"SC_4K_to_1080p_box_420_8b_alpha": (3840, 2160, 1280, 720),
+                                   "SC_1080p_to_4K_up2_420_8b_alpha": (1920, 1080, 3840, 2160)}.items():
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        src = YUVImage(sw, sh, 8, A.AVIF_PIXEL_FORMAT_YUV420, 1, 1, alpha=True, device=dev)
+        for p in src.present_planes():
+            b = src.bufs[p]
+            b._t[:b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
+        dst = YUVImage(dw, dh, 8, A.AVIF_PIXEL_FORMAT_YUV420, 1, 1, alpha=True, device=dev)
+
+        def go():
+            assert lib.avifB200ImageScaleToDevice(src.ptr(), dst.ptr()) == 0
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            go()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = 2.5 * (sw * sh + dw * dh)  # Y + U + V (4:2:0) + alpha, read once and written once
+        entry = {"api": "avifB200ImageScaleToDevice (4 planes: position tables + one kernel each, synchronous)", "us_per_image": ms * 1e3,
+                 "Mpixels_per_s_out": dw * dh / (ms * 1e-3) / 1e6, "alg_bytes": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9,
+                 "frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak_gbs}
+        try:
+            from oracle import loader
+            ref = loader.load_reference()
+            if ref is not None and hasattr(ref, "avifImageScale"):
+                himg = YUVImage(sw, sh, 8, A.AVIF_PIXEL_FORMAT_YUV420, 1, 1, alpha=True)
+                rs = np.random.RandomState(5)
+                for p in himg.present_planes():
+                    b = himg.bufs[p]
+                    b.set(rs.randint(0, 256, size=(b.rows, b.row_bytes)).astype(np.uint8))
+                diag = A.avifDiagnostics()
+                t0 = time.perf_counter()
+                r = ref.avifImageScale(himg.ptr(), dw, dh, ctypes.byref(diag))
+                dt = time.perf_counter() - t0
+                if r == 0:
+                    entry["cpu_reference"] = {"Mpixels_per_s_out": dw * dh / dt / 1e6, "cores": 1, "sample": "one call of src/scale.c + vendored libyuv (oracle/_ref)"}
+        except Exception as e:
+            entry["cpu_reference"] = {"unavailable": str(e)[:100]}
+        res[name] = entry
+    return res
 
 
 def run_tone_map(lib, dev, stream, peak_gbs):

@@ -17,7 +17,7 @@ tail -c 3000 $OUT/bench.json; tail -5 $OUT/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --batch 4 --e2e-batch 1 > $OUT/ncu_launches.log 2>&1
 # full capture of every configuration's kernel (2 launches each; the 2nd of each pair is the warm one)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"y2r_|r2y_|tone_map" -c 48 -o $OUT/prof_cases \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"y2r_|r2y_|tone_map|scale_kernel" -c 80 -o $OUT/prof_cases \
     python tools/profile_cases.py > $OUT/ncu_cases.log 2>&1
 tail -12 $OUT/ncu_cases.log
 ls -la $OUT

@@ -77,3 +77,15 @@ for _ in range(2):
                                                   ctypes.byref(clli), ctypes.byref(diag)) == 0, diag.error
 torch.cuda.synchronize()
 print("TM tone_map_kernel", clli.maxCLL, clli.maxPALL)
+
+# avifImageScale's device scaler: 4K 4:2:0 8-bit + alpha -> 720p (box) and 1080p -> 4K (2x bilinear)
+for (sw, sh, dw, dh) in ((3840, 2160, 1280, 720), (1920, 1080, 3840, 2160)):
+    s_img = YUVImage(sw, sh, 8, 3, 1, 1, alpha=True, device=dev)
+    for p in s_img.present_planes():
+        b = s_img.bufs[p]
+        b._t[:b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), device=dev, dtype=torch.int32).to(torch.uint8))
+    d_img = YUVImage(dw, dh, 8, 3, 1, 1, alpha=True, device=dev)
+    for _ in range(2):
+        assert lib.avifB200ImageScaleToDevice(s_img.ptr(), d_img.ptr()) == 0
+    torch.cuda.synchronize()
+    print("SC", sw, sh, "->", dw, dh)
