@@ -230,7 +230,13 @@ typedef struct AbScaleJob {
     const int32_t * rows; /* 4 ints per destination row, meaning depends on mode (scale_kernels.cu) */
     const int32_t * cols; /* 4 ints per destination column */
 } AbScaleJob;
-int abLaunchScale(const AbScaleJob * job, void * stream);
+enum { AB_SCALE_MAX_PLANES = 4 };
+typedef struct AbScaleBatch { /* the planes of one image (same sample size), one launch */
+    AbScaleJob job[AB_SCALE_MAX_PLANES];
+    uint32_t count;
+    uint32_t blockStart[AB_SCALE_MAX_PLANES + 1]; /* filled by the launcher */
+} AbScaleBatch;
+int abLaunchScaleBatch(AbScaleBatch * batch, void * stream);
 
 /* Launchers (kernels.cu).  `stream` is a cudaStream_t.  Return 0 on success, else a cudaError_t value.
  * `forceGeneric` selects the byte-addressed reference kernel instead of the tiled/vectorised one. */

@@ -267,49 +267,79 @@ static int planScale(int sw, int sh, int dw, int dh, int sixteen, ScalePlan * p)
     return 1;
 }
 
-/* One plane, both ends on the device.  srcRB / dstRB in bytes. */
-static cudaError_t scalePlaneOnDevice(const uint8_t * dSrc, int64_t srcRB, int sw, int sh, uint8_t * dDst, int64_t dstRB, int dw, int dh, int bps,
-                                      int * oom)
+typedef struct PlaneIO { /* one plane, both ends on the device; strides in bytes */
+    const uint8_t * src;
+    uint8_t * dst;
+    int64_t srcRB, dstRB;
+    int sw, sh, dw, dh;
+} PlaneIO;
+
+/* Up to four planes of one image: their position tables go up in ONE copy, the samples are produced by ONE launch. */
+static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, int * oom)
 {
-    ScalePlan plan;
-    if (!planScale(sw, sh, dw, dh, bps == 2, &plan)) {
-        *oom = 1;
-        return cudaSuccess;
-    }
+    ScalePlan plans[AB_SCALE_MAX_PLANES];
+    memset(plans, 0, sizeof(plans));
+    size_t tableInts = 0;
     cudaError_t e = cudaSuccess;
-    if (plan.mode == 0) {
-        e = cudaMemcpy2DAsync(dDst, (size_t)dstRB, dSrc, (size_t)srcRB, (size_t)dw * bps, (size_t)dh, cudaMemcpyDeviceToDevice, NULL);
-    } else {
-        int32_t * dTab = NULL;
-        const size_t nr = (size_t)dh * 4, nc = (size_t)dw * 4;
-        e = cudaMallocAsync((void **)&dTab, (nr + nc) * sizeof(int32_t), NULL);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dTab, plan.rows, nr * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dTab + nr, plan.cols, nc * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
-        if (e == cudaSuccess) {
-            AbScaleJob job;
-            memset(&job, 0, sizeof(job));
-            job.src = dSrc;
-            job.dst = dDst;
-            job.srcRB = srcRB;
-            job.dstRB = dstRB;
-            job.srcW = sw;
-            job.srcH = sh;
-            job.dstW = dw;
-            job.dstH = dh;
-            job.bps = (uint8_t)bps;
-            job.mode = (uint8_t)plan.mode;
-            job.linearOnly = (uint8_t)plan.linearOnly;
-            job.minBoxWidth = plan.minBoxWidth;
-            job.rows = dTab;
-            job.cols = dTab + nr;
-            e = (cudaError_t)abLaunchScale(&job, NULL);
+    int32_t *hTab = NULL, *dTab = NULL;
+    for (int k = 0; k < count; ++k) {
+        if (!planScale(io[k].sw, io[k].sh, io[k].dw, io[k].dh, bps == 2, &plans[k])) {
+            *oom = 1;
+            goto done;
         }
-        /* the tables are pageable host memory: the copies above have been staged before this returns, and the stream-ordered
-         * free runs after the kernel */
-        if (e == cudaSuccess) e = cudaStreamSynchronize(NULL);
-        if (dTab) (void)cudaFreeAsync(dTab, NULL);
+        if (plans[k].mode) tableInts += 4 * ((size_t)io[k].dw + (size_t)io[k].dh);
     }
-    planFree(&plan);
+    AbScaleBatch batch;
+    memset(&batch, 0, sizeof(batch));
+    if (tableInts) {
+        hTab = (int32_t *)malloc(tableInts * sizeof(int32_t));
+        if (!hTab) {
+            *oom = 1;
+            goto done;
+        }
+        e = cudaMallocAsync((void **)&dTab, tableInts * sizeof(int32_t), NULL);
+        if (e != cudaSuccess) goto done;
+    }
+    size_t at = 0;
+    for (int k = 0; k < count; ++k) {
+        if (plans[k].mode == 0) { /* same size: CopyPlane (scale.c:849-853) */
+            e = cudaMemcpy2DAsync(io[k].dst, (size_t)io[k].dstRB, io[k].src, (size_t)io[k].srcRB, (size_t)io[k].dw * bps, (size_t)io[k].dh,
+                                  cudaMemcpyDeviceToDevice, NULL);
+            if (e != cudaSuccess) goto done;
+            continue;
+        }
+        AbScaleJob * job = &batch.job[batch.count++];
+        job->src = io[k].src;
+        job->dst = io[k].dst;
+        job->srcRB = io[k].srcRB;
+        job->dstRB = io[k].dstRB;
+        job->srcW = io[k].sw;
+        job->srcH = io[k].sh;
+        job->dstW = io[k].dw;
+        job->dstH = io[k].dh;
+        job->bps = (uint8_t)bps;
+        job->mode = (uint8_t)plans[k].mode;
+        job->linearOnly = (uint8_t)plans[k].linearOnly;
+        job->minBoxWidth = plans[k].minBoxWidth;
+        memcpy(hTab + at, plans[k].rows, (size_t)io[k].dh * 4 * sizeof(int32_t));
+        job->rows = dTab + at;
+        at += (size_t)io[k].dh * 4;
+        memcpy(hTab + at, plans[k].cols, (size_t)io[k].dw * 4 * sizeof(int32_t));
+        job->cols = dTab + at;
+        at += (size_t)io[k].dw * 4;
+    }
+    if (batch.count) {
+        e = cudaMemcpyAsync(dTab, hTab, tableInts * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
+        if (e == cudaSuccess) e = (cudaError_t)abLaunchScaleBatch(&batch, NULL);
+    }
+    /* hTab is pageable: the copy has been staged when cudaMemcpyAsync returns, but one synchronisation per image keeps the
+     * lifetime rules simple (and callers of the synchronous API expect finished planes) */
+    if (e == cudaSuccess) e = cudaStreamSynchronize(NULL);
+
+done:
+    if (dTab) (void)cudaFreeAsync(dTab, NULL);
+    free(hTab);
+    for (int k = 0; k < count; ++k) planFree(&plans[k]);
     return e;
 }
 
@@ -338,39 +368,45 @@ avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
     const int bps = (src->depth > 8) ? 2 : 1;
     avifPixelFormatInfo info;
     avifGetPixelFormatInfo(src->yuvFormat, &info);
-    avifResult res = AVIF_RESULT_OK;
-    for (int c = 0; c < 4 && res == AVIF_RESULT_OK; ++c) {
+    PlaneIO io[AB_SCALE_MAX_PLANES];
+    uint8_t * staged[AB_SCALE_MAX_PLANES] = { NULL, NULL, NULL, NULL };
+    int count = 0, oom = 0;
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < 4 && e == cudaSuccess; ++c) {
         const uint8_t * sp = (c < 3) ? src->yuvPlanes[c] : src->alphaPlane;
         uint8_t * dp = (c < 3) ? dst->yuvPlanes[c] : dst->alphaPlane;
         if (!sp || !dp) continue;
         const uint32_t srb = (c < 3) ? src->yuvRowBytes[c] : src->alphaRowBytes, drb = (c < 3) ? dst->yuvRowBytes[c] : dst->alphaRowBytes;
         const int chroma = (c == 1 || c == 2);
         if (chroma && info.monochrome) continue;
-        const int sw = chroma ? (int)((src->width + info.chromaShiftX) >> info.chromaShiftX) : (int)src->width;
-        const int sh = chroma ? (int)((src->height + info.chromaShiftY) >> info.chromaShiftY) : (int)src->height;
-        const int dw = chroma ? (int)((dst->width + info.chromaShiftX) >> info.chromaShiftX) : (int)dst->width;
-        const int dh = chroma ? (int)((dst->height + info.chromaShiftY) >> info.chromaShiftY) : (int)dst->height;
-        uint8_t * staged = NULL;
-        const uint8_t * dSrc = sp;
-        int64_t dSrcRB = srb;
-        cudaError_t e = cudaSuccess;
+        PlaneIO * p = &io[count];
+        p->sw = chroma ? (int)((src->width + info.chromaShiftX) >> info.chromaShiftX) : (int)src->width;
+        p->sh = chroma ? (int)((src->height + info.chromaShiftY) >> info.chromaShiftY) : (int)src->height;
+        p->dw = chroma ? (int)((dst->width + info.chromaShiftX) >> info.chromaShiftX) : (int)dst->width;
+        p->dh = chroma ? (int)((dst->height + info.chromaShiftY) >> info.chromaShiftY) : (int)dst->height;
+        p->src = sp;
+        p->srcRB = srb;
+        p->dst = dp;
+        p->dstRB = drb;
         if (!onDevice(sp)) {
-            const size_t pitch = ((size_t)sw * bps + 255) & ~(size_t)255;
-            e = cudaMallocAsync((void **)&staged, pitch * (size_t)sh, NULL);
-            if (e == cudaSuccess) e = cudaMemcpy2D(staged, pitch, sp, srb, (size_t)sw * bps, (size_t)sh, cudaMemcpyHostToDevice);
-            dSrc = staged;
-            dSrcRB = (int64_t)pitch;
+            const size_t pitch = ((size_t)p->sw * bps + 255) & ~(size_t)255;
+            e = cudaMallocAsync((void **)&staged[count], pitch * (size_t)p->sh, NULL);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(staged[count], pitch, sp, srb, (size_t)p->sw * bps, (size_t)p->sh, cudaMemcpyHostToDevice, NULL);
+            p->src = staged[count];
+            p->srcRB = (int64_t)pitch;
         }
-        int oom = 0;
-        if (e == cudaSuccess) e = scalePlaneOnDevice(dSrc, dSrcRB, sw, sh, dp, drb, dw, dh, bps, &oom);
-        if (staged) (void)cudaFreeAsync(staged, NULL);
-        if (oom) res = AVIF_RESULT_OUT_OF_MEMORY;
-        else if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            res = (e == cudaErrorMemoryAllocation) ? AVIF_RESULT_OUT_OF_MEMORY : AVIF_RESULT_UNKNOWN_ERROR;
-        }
+        ++count;
     }
-    return res;
+    if (e == cudaSuccess && count) e = scalePlanesOnDevice(io, count, bps, &oom);
+    for (int k = 0; k < AB_SCALE_MAX_PLANES; ++k) {
+        if (staged[k]) (void)cudaFreeAsync(staged[k], NULL);
+    }
+    if (oom) return AVIF_RESULT_OUT_OF_MEMORY;
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return (e == cudaErrorMemoryAllocation) ? AVIF_RESULT_OUT_OF_MEMORY : AVIF_RESULT_UNKNOWN_ERROR;
+    }
+    return AVIF_RESULT_OK;
 }
 
 /* src/scale.c:24-201 with the default limits of :203-207 */

@@ -46,98 +46,138 @@ __device__ __forceinline__ int blend(int a, int b, int f)
     return (int)(uint16_t)(a + (int)((((int64_t)f * ((int64_t)b - a)) + 0x8000) >> 16));
 }
 
+/* one destination sample (i, j) of plane job J */
 template <typename T>
-__global__ void __launch_bounds__(256) scale_kernel(const __grid_constant__ AbScaleJob J)
+__device__ __forceinline__ int scale_sample(const AbScaleJob & J, const int32_t * R, int i, int j)
 {
-    const int64_t total = (int64_t)J.dstW * J.dstH;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int j = (int)(idx / J.dstW), i = (int)(idx - (int64_t)j * J.dstW);
-        const int32_t * R = J.rows + 4 * j;
-        const int32_t * C = J.cols + 4 * i;
-        int v = 0;
-        switch (J.mode) {
-            case AB_SCALE_VERTICAL: { /* rows: yi, yf */
-                const int yi = R[0], yf = R[1];
-                v = interp(ld<T>(J, yi, i), (yf == 0) ? 0 : ld<T>(J, yi + 1, i), yf);
-                break;
-            }
-            case AB_SCALE_SIMPLE: /* rows: yi ; cols: xi */
-                v = ld<T>(J, R[0], C[0]);
-                break;
-            case AB_SCALE_BILINEAR_DOWN: { /* rows: yi, yf ; cols: xi, xf */
-                const int yi = R[0], yf = J.linearOnly ? 0 : R[1], xi = C[0], xf = C[1];
-                const int a = interp(ld<T>(J, yi, xi), yf ? ld<T>(J, yi + 1, xi) : 0, yf);
-                const int b = interp(ld<T>(J, yi, xi + 1), yf ? ld<T>(J, yi + 1, xi + 1) : 0, yf);
-                v = blend<T>(a, b, xf);
-                break;
-            }
-            case AB_SCALE_BILINEAR_UP: { /* rows: ra, rb, yf ; cols: xi, xf */
-                const int ra = R[0], rb = R[1], yf = J.linearOnly ? 0 : R[2], xi = C[0], xf = C[1];
-                const int hA = blend<T>(ld<T>(J, ra, xi), ld<T>(J, ra, xi + 1), xf);
-                const int hB = yf ? blend<T>(ld<T>(J, rb, xi), ld<T>(J, rb, xi + 1), xf) : 0;
-                v = interp(hA, hB, yf);
-                break;
-            }
-            case AB_SCALE_UP2_LINEAR: { /* rows: yi */
-                const int yi = R[0];
-                if (i == 0) v = ld<T>(J, yi, 0);
-                else if (i == J.dstW - 1) v = ld<T>(J, yi, (J.dstW - 1) / 2);
-                else {
-                    const int k = (i - 1) >> 1, a = ld<T>(J, yi, k), b = ld<T>(J, yi, k + 1);
-                    v = ((i - 1) & 1) ? ((a + 3 * b + 2) >> 2) : ((3 * a + b + 2) >> 2);
-                }
-                break;
-            }
-            case AB_SCALE_UP2_BILINEAR: { /* scale.c:503-538: row 0 and the last row of an even height come from one source row */
-                int rs, rt; /* near row gets weights (9,3), far row (3,1) */
-                if (j == 0) rs = rt = 0;
-                else {
-                    const int r = (j - 1) >> 1;
-                    if (r >= J.srcH - 1) rs = rt = J.srcH - 1;
-                    else if ((j - 1) & 1) { rs = r + 1; rt = r; }
-                    else { rs = r; rt = r + 1; }
-                }
-                if (i == 0 || i == J.dstW - 1) {
-                    const int k = (i == 0) ? 0 : (J.dstW - 1) / 2;
-                    v = (3 * ld<T>(J, rs, k) + ld<T>(J, rt, k) + 2) >> 2;
-                } else {
-                    const int k = (i - 1) >> 1;
-                    const int kn = ((i - 1) & 1) ? k + 1 : k, kf = ((i - 1) & 1) ? k : k + 1; /* near / far column */
-                    v = (ld<T>(J, rs, kn) * 9 + ld<T>(J, rs, kf) * 3 + ld<T>(J, rt, kn) * 3 + ld<T>(J, rt, kf) * 1 + 8) >> 4;
-                }
-                break;
-            }
-            case AB_SCALE_BOX: { /* rows: iy, boxheight ; cols: ix, boxwidth, table index */
-                const int iy = R[0], bh = R[1], ix = C[0], bw = C[1];
-                uint32_t sum = 0;
-                for (int c = 0; c < bw; ++c) {
-                    uint32_t col = 0; /* ScaleAddRow: one accumulator per source column */
-                    for (int r = 0; r < bh; ++r) col += (uint32_t)ld<T>(J, iy + r, ix + c);
-                    if (sizeof(T) == 1) col &= 0xFFFFu; /* uint16_t accumulators wrap (scale_common.c:316-328) */
-                    sum += col;
-                }
-                int wdiv = J.minBoxWidth + C[2];
-                if (wdiv < 1) wdiv = 1;
-                const int scale = 65536 / (wdiv * bh); /* scaletbl[], scale.c:58-59 */
-                v = (int)((sum * (uint32_t)scale) >> 16);
-                break;
-            }
-            default: break;
+    const int32_t * C = J.cols + 4 * i;
+    switch (J.mode) {
+        case AB_SCALE_VERTICAL: { /* rows: yi, yf */
+            const int yi = R[0], yf = R[1];
+            return interp(ld<T>(J, yi, i), (yf == 0) ? 0 : ld<T>(J, yi + 1, i), yf);
         }
-        *reinterpret_cast<T *>(J.dst + (int64_t)j * J.dstRB + (int64_t)i * sizeof(T)) = (T)v;
+        case AB_SCALE_SIMPLE: /* rows: yi ; cols: xi */
+            return ld<T>(J, R[0], C[0]);
+        case AB_SCALE_BILINEAR_DOWN: { /* rows: yi, yf ; cols: xi, xf */
+            const int yi = R[0], yf = J.linearOnly ? 0 : R[1], xi = C[0], xf = C[1];
+            const int a = interp(ld<T>(J, yi, xi), yf ? ld<T>(J, yi + 1, xi) : 0, yf);
+            const int b = interp(ld<T>(J, yi, xi + 1), yf ? ld<T>(J, yi + 1, xi + 1) : 0, yf);
+            return blend<T>(a, b, xf);
+        }
+        case AB_SCALE_BILINEAR_UP: { /* rows: ra, rb, yf ; cols: xi, xf */
+            const int ra = R[0], rb = R[1], yf = J.linearOnly ? 0 : R[2], xi = C[0], xf = C[1];
+            const int hA = blend<T>(ld<T>(J, ra, xi), ld<T>(J, ra, xi + 1), xf);
+            const int hB = yf ? blend<T>(ld<T>(J, rb, xi), ld<T>(J, rb, xi + 1), xf) : 0;
+            return interp(hA, hB, yf);
+        }
+        case AB_SCALE_UP2_LINEAR: { /* rows: yi */
+            const int yi = R[0];
+            if (i == 0) return ld<T>(J, yi, 0);
+            if (i == J.dstW - 1) return ld<T>(J, yi, (J.dstW - 1) / 2);
+            const int k = (i - 1) >> 1, a = ld<T>(J, yi, k), b = ld<T>(J, yi, k + 1);
+            return ((i - 1) & 1) ? ((a + 3 * b + 2) >> 2) : ((3 * a + b + 2) >> 2);
+        }
+        case AB_SCALE_UP2_BILINEAR: { /* scale.c:503-538: row 0 and the last row of an even height come from one source row */
+            int rs, rt; /* near row gets weights (9,3), far row (3,1) */
+            if (j == 0) rs = rt = 0;
+            else {
+                const int r = (j - 1) >> 1;
+                if (r >= J.srcH - 1) rs = rt = J.srcH - 1;
+                else if ((j - 1) & 1) { rs = r + 1; rt = r; }
+                else { rs = r; rt = r + 1; }
+            }
+            if (i == 0 || i == J.dstW - 1) {
+                const int k = (i == 0) ? 0 : (J.dstW - 1) / 2;
+                return (3 * ld<T>(J, rs, k) + ld<T>(J, rt, k) + 2) >> 2;
+            }
+            const int k = (i - 1) >> 1;
+            const int kn = ((i - 1) & 1) ? k + 1 : k, kf = ((i - 1) & 1) ? k : k + 1; /* near / far column */
+            return (ld<T>(J, rs, kn) * 9 + ld<T>(J, rs, kf) * 3 + ld<T>(J, rt, kn) * 3 + ld<T>(J, rt, kf) * 1 + 8) >> 4;
+        }
+        case AB_SCALE_BOX: { /* rows: iy, boxheight ; cols: ix, boxwidth, table index */
+            const int iy = R[0], bh = R[1], ix = C[0], bw = C[1];
+            uint32_t sum = 0;
+            for (int c = 0; c < bw; ++c) {
+                uint32_t col = 0; /* ScaleAddRow: one accumulator per source column */
+                for (int r = 0; r < bh; ++r) col += (uint32_t)ld<T>(J, iy + r, ix + c);
+                if (sizeof(T) == 1) col &= 0xFFFFu; /* uint16_t accumulators wrap (scale_common.c:316-328) */
+                sum += col;
+            }
+            int wdiv = J.minBoxWidth + C[2];
+            if (wdiv < 1) wdiv = 1;
+            const int scale = 65536 / (wdiv * bh); /* scaletbl[], scale.c:58-59 */
+            return (int)((sum * (uint32_t)scale) >> 16);
+        }
+        default: return 0;
+    }
+}
+
+/* All planes of one image in one launch.  A thread produces 8 bytes of one destination row (8 u8 or 4 u16 samples) and stores
+ * them as one vector when the row is 8-byte aligned; consecutive threads take consecutive groups, so a warp writes 256
+ * contiguous bytes.  Blocks are shared out over the planes by blockStart[]. */
+template <typename T>
+__global__ void __launch_bounds__(256) scale_batch_kernel(const __grid_constant__ AbScaleBatch B)
+{
+    constexpr int VEC = 8 / (int)sizeof(T);
+    uint32_t p = 0;
+    while (p + 1 < B.count && blockIdx.x >= B.blockStart[p + 1]) ++p;
+    const AbScaleJob & J = B.job[p];
+    const int64_t groupsPerRow = (J.dstW + VEC - 1) / VEC;
+    const int64_t total = groupsPerRow * J.dstH;
+    const int64_t stride = (int64_t)(B.blockStart[p + 1] - B.blockStart[p]) * blockDim.x;
+    const bool aligned = ((((uintptr_t)J.dst) | (uintptr_t)J.dstRB) & 7u) == 0;
+    for (int64_t u = (int64_t)(blockIdx.x - B.blockStart[p]) * blockDim.x + threadIdx.x; u < total; u += stride) {
+        const int j = (int)(u / groupsPerRow), i0 = (int)(u - (int64_t)j * groupsPerRow) * VEC;
+        const int32_t * R = J.rows + 4 * j;
+        int v[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = (i0 + k < J.dstW) ? scale_sample<T>(J, R, i0 + k, j) : 0;
+        T * out = reinterpret_cast<T *>(J.dst + (int64_t)j * J.dstRB) + i0;
+        if (aligned && i0 + VEC <= J.dstW) {
+            uint2 w;
+            if (sizeof(T) == 1) {
+                w.x = (uint32_t)(v[0] & 0xFF) | ((uint32_t)(v[1] & 0xFF) << 8) | ((uint32_t)(v[2] & 0xFF) << 16) | ((uint32_t)(v[3] & 0xFF) << 24);
+                w.y = (uint32_t)(v[4 % VEC] & 0xFF) | ((uint32_t)(v[5 % VEC] & 0xFF) << 8) | ((uint32_t)(v[6 % VEC] & 0xFF) << 16) |
+                      ((uint32_t)(v[7 % VEC] & 0xFF) << 24);
+            } else {
+                w.x = (uint32_t)(v[0] & 0xFFFF) | ((uint32_t)(v[1] & 0xFFFF) << 16);
+                w.y = (uint32_t)(v[2] & 0xFFFF) | ((uint32_t)(v[3] & 0xFFFF) << 16);
+            }
+            *reinterpret_cast<uint2 *>(out) = w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (i0 + k < J.dstW) out[k] = (T)v[k];
+        }
     }
 }
 
 } // namespace
 
-extern "C" int abLaunchScale(const AbScaleJob * job, void * stream)
+extern "C" int abLaunchScaleBatch(AbScaleBatch * batch, void * stream)
 {
-    const int64_t total = (int64_t)job->dstW * job->dstH;
-    if (total <= 0) return 0;
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (job->bps == 1) scale_kernel<uint8_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
-    else scale_kernel<uint16_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
+    if (batch->count == 0) return 0;
+    /* blocks in proportion to the work of each plane, 16 resident waves' worth in all */
+    int64_t units[AB_SCALE_MAX_PLANES], all = 0;
+    const int vec = 8 / batch->job[0].bps;
+    for (uint32_t p = 0; p < batch->count; ++p) {
+        units[p] = (int64_t)((batch->job[p].dstW + vec - 1) / vec) * batch->job[p].dstH;
+        all += units[p];
+    }
+    if (all <= 0) return 0;
+    const int64_t budget = 148 * 16;
+    uint32_t start = 0;
+    for (uint32_t p = 0; p < batch->count; ++p) {
+        int64_t need = (units[p] + 255) / 256;
+        int64_t share = (units[p] * budget + all - 1) / all;
+        if (share < 1) share = 1;
+        if (share > need) share = need;
+        if (share < 1) share = 1;
+        batch->blockStart[p] = start;
+        start += (uint32_t)share;
+    }
+    batch->blockStart[batch->count] = start;
+    if (batch->job[0].bps == 1) scale_batch_kernel<uint8_t><<<start, 256, 0, (cudaStream_t)stream>>>(*batch);
+    else scale_batch_kernel<uint16_t><<<start, 256, 0, (cudaStream_t)stream>>>(*batch);
     return (int)cudaGetLastError();
 }
