@@ -31,6 +31,18 @@ int main(void) {
     F(avifRGBImage, width); F(avifRGBImage, height); F(avifRGBImage, depth); F(avifRGBImage, format); F(avifRGBImage, chromaUpsampling);
     F(avifRGBImage, chromaDownsampling); F(avifRGBImage, avoidLibYUV); F(avifRGBImage, ignoreAlpha); F(avifRGBImage, alphaPremultiplied);
     F(avifRGBImage, isFloat); F(avifRGBImage, maxThreads); F(avifRGBImage, pixels); F(avifRGBImage, rowBytes);
+    printf("sizeof.avifGainMap %%zu\n", sizeof(avifGainMap));
+    printf("sizeof.avifDiagnostics %%zu\n", sizeof(avifDiagnostics));
+    printf("sizeof.avifContentLightLevelInformationBox %%zu\n", sizeof(avifContentLightLevelInformationBox));
+    F(avifGainMap, image); F(avifGainMap, gainMapMin); F(avifGainMap, gainMapMax); F(avifGainMap, gainMapGamma); F(avifGainMap, baseOffset);
+    F(avifGainMap, alternateOffset); F(avifGainMap, baseHdrHeadroom); F(avifGainMap, alternateHdrHeadroom); F(avifGainMap, useBaseColorSpace);
+    F(avifGainMap, altICC); F(avifGainMap, altColorPrimaries); F(avifGainMap, altTransferCharacteristics); F(avifGainMap, altMatrixCoefficients);
+    F(avifGainMap, altYUVRange); F(avifGainMap, altDepth); F(avifGainMap, altPlaneCount); F(avifGainMap, altCLLI);
+    printf("enum.AVIF_RESULT_INVALID_TONE_MAPPED_IMAGE %%d\n", (int)AVIF_RESULT_INVALID_TONE_MAPPED_IMAGE);
+    printf("enum.AVIF_TRANSFER_CHARACTERISTICS_HLG %%d\n", (int)AVIF_TRANSFER_CHARACTERISTICS_HLG);
+    printf("enum.AVIF_TRANSFER_CHARACTERISTICS_PQ %%d\n", (int)AVIF_TRANSFER_CHARACTERISTICS_PQ);
+    printf("enum.AVIF_TRANSFER_CHARACTERISTICS_SRGB %%d\n", (int)AVIF_TRANSFER_CHARACTERISTICS_SRGB);
+    printf("enum.AVIF_COLOR_PRIMARIES_SMPTE432 %%d\n", (int)AVIF_COLOR_PRIMARIES_SMPTE432);
     printf("enum.AVIF_RESULT_REFORMAT_FAILED %%d\n", (int)AVIF_RESULT_REFORMAT_FAILED);
     printf("enum.AVIF_RESULT_INVALID_ARGUMENT %%d\n", (int)AVIF_RESULT_INVALID_ARGUMENT);
     printf("enum.AVIF_RESULT_NOT_IMPLEMENTED %%d\n", (int)AVIF_RESULT_NOT_IMPLEMENTED);
@@ -75,6 +87,12 @@ def test_ctypes_mirror_matches_header():
     mine = _probe('#include "avif_b200.h"', [os.path.join(ROOT, "include")])
     assert ctypes.sizeof(abi.avifImage) == int(mine["sizeof.avifImage"])
     assert ctypes.sizeof(abi.avifRGBImage) == int(mine["sizeof.avifRGBImage"])
+    assert ctypes.sizeof(abi.avifGainMap) == int(mine["sizeof.avifGainMap"])
+    assert ctypes.sizeof(abi.avifDiagnostics) == int(mine["sizeof.avifDiagnostics"])
+    for key, off in mine.items():
+        t, _, m = key.partition(".")
+        if t == "avifGainMap":
+            assert getattr(abi.avifGainMap, m).offset == int(off), key
     for key, off in mine.items():
         t, _, m = key.partition(".")
         if t in ("avifImage", "avifRGBImage"):
