@@ -407,6 +407,13 @@ AVIF_B200_API avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage *
  * caller allocated (width, height, row strides set; planes that are NULL on either side are skipped). */
 AVIF_B200_API avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst);
 
+/* Host-logic test hooks (no device needed; tests/test_host_logic.py): the scaler's loop choice and position tables for one plane
+ * (mode = AB_SCALE_* of csrc/plan.h, 0 = copy; rows / cols: 4 ints per destination row / column, may be NULL), and the tone
+ * mapper's primaries matrix (row-major doubles; returns 0 where the reference's derivation fails). */
+AVIF_B200_API avifResult avifB200DebugScalePlan(int srcWidth, int srcHeight, int dstWidth, int dstHeight, int sixteenBit, int * mode,
+                                                int * linearOnly, int * minBoxWidth, int32_t * rows, int32_t * cols);
+AVIF_B200_API int avifB200DebugPrimariesMatrix(avifColorPrimaries src, avifColorPrimaries dst, double out[9]);
+
 /* ---- B-2: the reference's internal seam (include/avif/internal.h:350-387) ------------------------------------------
  * libavif_b200_hooks.so exports the six functions src/reformat.c and src/alpha.c call before their built-in loops
  * (avifImageYUVToRGBLibYUV, avifImageRGBToYUVLibYUV, avifRGBImage{Pre,Unpre}multiplyAlphaLibYUV, avifRGBImageToF16LibYUV,

@@ -180,6 +180,10 @@ static int rgbToRgb(avifColorPrimaries src, avifColorPrimaries dst, double * out
     return 1;
 }
 
+/* Test hook (no device involved): the primaries conversion matrix the tone mapper would use, row-major.  Returns 0 when the
+ * reference's avifColorPrimariesComputeRGBToRGBMatrix would fail. */
+int avifB200DebugPrimariesMatrix(avifColorPrimaries src, avifColorPrimaries dst, double out[9]) { return rgbToRgb(src, dst, out); }
+
 /* src/reformat.c:32-117 */
 static int pixFmt(const avifRGBImage * rgb, AbPixFmt * f)
 {

@@ -267,6 +267,25 @@ static int planScale(int sw, int sh, int dw, int dh, int sixteen, ScalePlan * p)
     return 1;
 }
 
+/* Test hook (no device involved): the loop libyuv's dispatcher picks for one plane and the position tables this file would
+ * hand to the kernel.  rows / cols receive 4 ints per destination row / column when non-NULL (caller-allocated). */
+avifResult avifB200DebugScalePlan(int srcWidth, int srcHeight, int dstWidth, int dstHeight, int sixteenBit, int * mode, int * linearOnly,
+                                  int * minBoxWidth, int32_t * rows, int32_t * cols)
+{
+    if (srcWidth <= 0 || srcHeight <= 0 || dstWidth <= 0 || dstHeight <= 0) return AVIF_RESULT_INVALID_ARGUMENT;
+    ScalePlan plan;
+    if (!planScale(srcWidth, srcHeight, dstWidth, dstHeight, sixteenBit, &plan)) return AVIF_RESULT_OUT_OF_MEMORY;
+    if (mode) *mode = plan.mode;
+    if (linearOnly) *linearOnly = plan.linearOnly;
+    if (minBoxWidth) *minBoxWidth = plan.minBoxWidth;
+    if (plan.mode) {
+        if (rows) memcpy(rows, plan.rows, (size_t)dstHeight * 4 * sizeof(int32_t));
+        if (cols) memcpy(cols, plan.cols, (size_t)dstWidth * 4 * sizeof(int32_t));
+    }
+    planFree(&plan);
+    return AVIF_RESULT_OK;
+}
+
 typedef struct PlaneIO { /* one plane, both ends on the device; strides in bytes */
     const uint8_t * src;
     uint8_t * dst;
