@@ -226,15 +226,15 @@ static int onDevice(const void * p)
 /* Scratch (converted gain map, staged base, output, tables) comes from a stream-ordered pool that keeps what it has been
  * given: the default pool hands freed memory back to the driver at every synchronisation (release threshold 0), which
  * turns each call into milliseconds of mapping work. */
-static cudaError_t scratchAlloc(void ** p, size_t bytes)
+int abScratchAlloc(void ** p, size_t bytes)
 {
     enum { kMaxDevices = 64 };
     static cudaMemPool_t pools[kMaxDevices];
     static int made[kMaxDevices];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= kMaxDevices) return cudaMallocAsync(p, bytes, NULL);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= kMaxDevices) return (int)cudaMallocAsync(p, bytes, NULL);
     if (!__atomic_load_n(&made[dev], __ATOMIC_ACQUIRE)) {
         static int lock = 0;
         while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {
@@ -254,9 +254,9 @@ static cudaError_t scratchAlloc(void ** p, size_t bytes)
             if (e == cudaSuccess) __atomic_store_n(&made[dev], 1, __ATOMIC_RELEASE);
         }
         __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) return (int)e;
     }
-    return cudaMallocFromPoolAsync(p, bytes, pools[dev], NULL);
+    return (int)cudaMallocFromPoolAsync(p, bytes, pools[dev], NULL);
 }
 
 #define GM_CUDA(call)                                                        \
@@ -384,7 +384,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
                 const uint32_t pw = c ? (uint32_t)(((uint64_t)width + fi.chromaShiftX) >> fi.chromaShiftX) : width;
                 const uint32_t ph = c ? (uint32_t)(((uint64_t)height + fi.chromaShiftY) >> fi.chromaShiftY) : height;
                 const size_t pitch = ((size_t)pw * cs + 255) & ~(size_t)255;
-                GM_CUDA(scratchAlloc((void **)&dScaled[c], pitch * ph));
+                GM_CUDA((cudaError_t)abScratchAlloc((void **)&dScaled[c], pitch * ph));
                 scaled.yuvPlanes[c] = dScaled[c];
                 scaled.yuvRowBytes[c] = (uint32_t)pitch;
             }
@@ -404,7 +404,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
             goto cleanup;
         }
         rgbGain.rowBytes = (uint32_t)(((size_t)width * job.gainFmt.pixBytes + 255) & ~(size_t)255);
-        GM_CUDA(scratchAlloc((void **)&dGain, (size_t)rgbGain.rowBytes * height));
+        GM_CUDA((cudaError_t)abScratchAlloc((void **)&dGain, (size_t)rgbGain.rowBytes * height));
         GM_CUDA(cudaStreamSynchronize(NULL)); /* the conversion below runs on the library's own streams */
         rgbGain.pixels = dGain;
         res = avifImageYUVToRGB(gmImage, &rgbGain);
@@ -425,7 +425,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
     job.baseLutN = (job.baseFmt.isFloat || !(job.applyGain || job.transcode)) ? 0u : ((job.baseFmt.chanBytes == 1) ? 256u : 65536u);
     job.gainLutN = job.applyGain ? ((job.gainFmt.chanBytes == 1) ? 256u : 65536u) : 0u;
     if (job.baseLutN + job.gainLutN) {
-        GM_CUDA(scratchAlloc((void **)&dLut, ((size_t)job.baseLutN + 3u * (size_t)job.gainLutN) * sizeof(float)));
+        GM_CUDA((cudaError_t)abScratchAlloc((void **)&dLut, ((size_t)job.baseLutN + 3u * (size_t)job.gainLutN) * sizeof(float)));
         job.baseLut = (float *)dLut;
         job.gainLut = (float *)dLut + job.baseLutN;
     }
@@ -437,7 +437,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
     } else {
         const size_t rowUsed = (size_t)width * job.baseFmt.pixBytes;
         const size_t pitch = (rowUsed + 255) & ~(size_t)255;
-        GM_CUDA(scratchAlloc((void **)&dBase, pitch * height));
+        GM_CUDA((cudaError_t)abScratchAlloc((void **)&dBase, pitch * height));
         GM_CUDA(cudaMemcpy2D(dBase, pitch, baseImage->pixels, baseImage->rowBytes, rowUsed, height, cudaMemcpyHostToDevice));
         job.base = dBase;
         job.baseRB = (int64_t)pitch;
@@ -449,12 +449,12 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
             job.out = toneMappedImage->pixels;
             job.outRB = toneMappedImage->rowBytes;
         } else {
-            GM_CUDA(scratchAlloc((void **)&dOut, pitch * height));
+            GM_CUDA((cudaError_t)abScratchAlloc((void **)&dOut, pitch * height));
             job.out = dOut;
             job.outRB = (int64_t)pitch;
         }
         struct { double sum; uint32_t maxBits, nanIndex; } stats = { 0.0, 0u, 0xFFFFFFFFu };
-        GM_CUDA(scratchAlloc((void **)&dStats, sizeof(stats)));
+        GM_CUDA((cudaError_t)abScratchAlloc((void **)&dStats, sizeof(stats)));
         GM_CUDA(cudaMemcpy(dStats, &stats, sizeof(stats), cudaMemcpyHostToDevice));
         job.sum = (double *)dStats;
         job.maxBits = (uint32_t *)(dStats + offsetof(__typeof__(stats), maxBits));
@@ -532,7 +532,7 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
     if (!baseImage->width || !baseImage->height) return AVIF_RESULT_INVALID_ARGUMENT;
     baseRgb.rowBytes = baseImage->width * pixBytes;
     uint8_t * dev = NULL;
-    if (scratchAlloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
+    if ((cudaError_t)abScratchAlloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
         (void)cudaGetLastError();
         return AVIF_RESULT_OUT_OF_MEMORY;
     }

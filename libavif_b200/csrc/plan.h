@@ -212,6 +212,9 @@ typedef struct AbToneMapJob {
     double * sum;
 } AbToneMapJob;
 int abLaunchToneMap(const AbToneMapJob * job, void * stream);
+/* Stream-ordered (legacy default stream) device scratch from a per-device pool that keeps freed memory instead of returning it
+ * to the driver at every synchronisation (gainmap.c); release with cudaFreeAsync(p, NULL).  Returns a cudaError_t value. */
+int abScratchAlloc(void ** p, size_t bytes);
 
 /* ---- plane scaling (scale_kernels.cu; src/scale.c over third_party/libyuv/source/scale*.c) ----
  * The host walks libyuv's 16.16 stepping state machines once per plane (scale.c here: O(width + height) integer work, no

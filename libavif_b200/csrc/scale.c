@@ -316,7 +316,7 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
             *oom = 1;
             goto done;
         }
-        e = cudaMallocAsync((void **)&dTab, tableInts * sizeof(int32_t), NULL);
+        e = (cudaError_t)abScratchAlloc((void **)&dTab, tableInts * sizeof(int32_t));
         if (e != cudaSuccess) goto done;
     }
     size_t at = 0;
@@ -409,7 +409,7 @@ avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
         p->dstRB = drb;
         if (!onDevice(sp)) {
             const size_t pitch = ((size_t)p->sw * bps + 255) & ~(size_t)255;
-            e = cudaMallocAsync((void **)&staged[count], pitch * (size_t)p->sh, NULL);
+            e = (cudaError_t)abScratchAlloc((void **)&staged[count], pitch * (size_t)p->sh);
             if (e == cudaSuccess) e = cudaMemcpy2DAsync(staged[count], pitch, sp, srb, (size_t)p->sw * bps, (size_t)p->sh, cudaMemcpyHostToDevice, NULL);
             p->src = staged[count];
             p->srcRB = (int64_t)pitch;
@@ -492,7 +492,7 @@ avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeig
             }
             if (!sp) continue; /* allocated but not scaled, like src/scale.c:88-91 */
             const size_t pitch = ((size_t)cs * w + 255) & ~(size_t)255;
-            if (cudaMallocAsync((void **)&dPlanes[c], pitch * h, NULL) != cudaSuccess) {
+            if ((cudaError_t)abScratchAlloc((void **)&dPlanes[c], pitch * h) != cudaSuccess) {
                 (void)cudaGetLastError();
                 res = AVIF_RESULT_OUT_OF_MEMORY;
                 goto cleanup;
