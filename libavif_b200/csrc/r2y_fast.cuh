@@ -41,6 +41,9 @@ struct RCfg {
  *   two-row tiles, 8-bit channels         prefetch, 3 blocks/SM   -- 10 % faster than 2; plain loop at 4 measured equal
  *   two-row tiles, 16-bit channels        3 blocks/SM (-13 % on 8K RGBA16); RGBA16 runs the plain loop: its tile alone is 32
  *                                         registers of input per lane and a second set does not fit */
+#ifndef AB_R2Y_UNROLL2 /* 1: the prefetching loop written out twice (ping-pong register sets, no copies) */
+#define AB_R2Y_UNROLL2 0
+#endif
 #ifndef AB_R2Y_NOPREFETCH420
 #define AB_R2Y_NOPREFETCH420 0 /* 1: plain loop for every two-row tile */
 #endif
@@ -381,6 +384,50 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
         }
         return;
     }
+#if AB_R2Y_UNROLL2
+    /* ping-pong register sets: see y2r_fast_kernel */
+    struct Slot {
+        RTileIn<C> in;
+        uint32_t x0, j0;
+        bool live, full;
+    };
+    auto fetch = [&](Slot & s, uint32_t grp) {
+        const uint32_t t = grp * kRWarps + warp;
+        s.live = t < F.tiles;
+        s.x0 = s.j0 = 0;
+        s.full = false;
+        if (s.live) {
+            const uint32_t unit = t / F.tilesX;
+            s.x0 = (t - unit * F.tilesX) * kRTile;
+            s.j0 = F.rowBegin + unit * ROWS;
+            s.full = (s.x0 + kRTile <= F.width);
+            if (s.full) load_rtile<C, true>(J, F, s.x0, s.j0, lane, s.in);
+            else load_rtile<C, false>(J, F, s.x0, s.j0, lane, s.in);
+        }
+    };
+    auto run = [&](const Slot & s) {
+        if (s.live) {
+            if (s.full) convert_store_rtile<C, true>(J, F, s.x0, s.j0, lane, s.in);
+            else convert_store_rtile<C, false>(J, F, s.x0, s.j0, lane, s.in);
+        }
+    };
+    Slot a, b;
+    fetch(a, g);
+    while (true) {
+        uint32_t ng = g + gStride;
+        bool more = ng < F.groups; /* block-uniform */
+        if (more) fetch(b, ng);
+        run(a);
+        if (!more) break;
+        g = ng;
+        ng = g + gStride;
+        more = ng < F.groups;
+        if (more) fetch(a, ng);
+        run(b);
+        if (!more) break;
+        g = ng;
+    }
+#else
     RTileIn<C> cur, nxt;
     uint32_t tile = g * kRWarps + warp;
     bool live = tile < F.tiles;
@@ -423,6 +470,7 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
         j0 = nj0;
         full = nfull;
     }
+#endif
 }
 
 template <class FrameT>

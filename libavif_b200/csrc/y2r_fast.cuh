@@ -488,6 +488,9 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #ifndef AB_Y2R_PLAIN_NEAREST
 #define AB_Y2R_PLAIN_NEAREST 1
 #endif
+#ifndef AB_Y2R_UNROLL2 /* 1: the prefetching loop written out twice (ping-pong register sets, no copies) */
+#define AB_Y2R_UNROLL2 0
+#endif
 #ifndef AB_Y2R_PLAIN /* 1: no prefetched register set in any kernel */
 #define AB_Y2R_PLAIN 0
 #endif
@@ -527,6 +530,55 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
         }
         return;
     }
+#if AB_Y2R_UNROLL2
+    /* Two register sets that swap roles: the loop body is written out twice so that "the prefetched tile becomes the current
+     * one" is a change of names, not ~20 register moves per tile. */
+    struct Slot {
+        TileIn<C> in;
+        TileRows<C> R;
+        uint32_t x0;
+        bool live, full;
+    };
+    auto fetch = [&](Slot & s, uint32_t grp) {
+        const uint32_t t = grp * kWarps + warp;
+        s.live = t < F.tiles;
+        s.x0 = 0;
+        s.full = false;
+        s.R.any = false;
+        if (s.live) {
+            const uint32_t unit = t / F.tilesX;
+            s.x0 = (t - unit * F.tilesX) * kTile;
+            s.R = tile_rows<C>(J, F, unit);
+            s.full = (s.x0 + kTile <= F.width);
+            if (s.R.any) {
+                if (s.full) load_tile<C, true>(J, F, s.R, s.x0, lane, s.in);
+                else load_tile<C, false>(J, F, s.R, s.x0, lane, s.in);
+            }
+        }
+    };
+    auto run = [&](const Slot & s) {
+        if (s.live && s.R.any) {
+            if (s.full) convert_store_tile<C, true>(J, F, s.R, s.x0, lane, s.in);
+            else convert_store_tile<C, false>(J, F, s.R, s.x0, lane, s.in);
+        }
+    };
+    Slot a, b;
+    fetch(a, g);
+    while (true) {
+        uint32_t ng = g + gStride;
+        bool more = ng < F.groups; /* block-uniform */
+        if (more) fetch(b, ng);
+        run(a);
+        if (!more) break;
+        g = ng;
+        ng = g + gStride;
+        more = ng < F.groups;
+        if (more) fetch(a, ng);
+        run(b);
+        if (!more) break;
+        g = ng;
+    }
+#else
     TileIn<C> cur, nxt;
     uint32_t tile = g * kWarps + warp;
     bool live = tile < F.tiles; /* the last group of a frame may be partial */
@@ -577,6 +629,7 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
         R = NR;
         full = nfull;
     }
+#endif
 }
 
 /* share `blocksWanted` blocks among the frames in proportion to their group counts (every frame gets at least one) */
