@@ -14,6 +14,8 @@ d = json.load(open(sys.argv[1]))
 k = d["roofline"]["kernels"]
 row = {"C2fwd": k["y2r_fast_444"]["ms_per_launch"] * 1e3 / d["roofline"]["frames_per_launch"], "C2back": k["r2y_fast"]["ms_per_launch"] * 1e3 / d["roofline"]["frames_per_launch"]}
 for n, e in d["extras"].items():
+    if not isinstance(e, dict) or "us_per_frame" not in e:
+        continue
     row[n.split("_")[0] + ("_" + n.split("_")[-1] if n.startswith(("C1", "C5")) else "") + ("_back" if "back" in n else "")] = e["us_per_frame"]
 print(sys.argv[2].ljust(10), " ".join(f"{a}={b:.1f}" for a, b in row.items()))
 PY
