@@ -36,6 +36,46 @@ def main():
     json.dump(out, open(path, "w"), indent=0)
     print("wrote", path, len(out["y2r"]), len(out["r2y"]))
     tool_outputs()
+    next_rows()
+
+
+def next_rows():
+    """Fixtures of the rows beyond the reformat path, from the compiled reference: FNV-1a-64 of every plane avifImageScale
+    produces for the size pairs of tests/test_gpu_scale.py (bit-exact row), and the tone-mapped pixels of three small gain-map
+    cases (the +-1-code row keeps the pixels themselves)."""
+    import numpy as np
+    from tests import test_gpu_scale as ts
+    from tests import test_gpu_gainmap as tg
+    ref = loader.load_reference()
+    orc = loader.load_oracle()
+    out = {"scale": []}
+    A = ts.A
+    for depth in (8, 10, 12):
+        for k, ((w, h), (dw, dh)) in enumerate(ts.CASES):
+            for fmt, alpha in ((A.AVIF_PIXEL_FORMAT_YUV444, True), (A.AVIF_PIXEL_FORMAT_YUV420, False), (A.AVIF_PIXEL_FORMAT_YUV400, True)):
+                res, planes, dims, _ = ts.scaled_planes(ref, w, h, depth, fmt, alpha, 1000 + k, dw, dh)
+                hs = []
+                for p_i, pl in enumerate(planes):
+                    if pl is None or (fmt == A.AVIF_PIXEL_FORMAT_YUV400 and p_i in (1, 2)):
+                        hs.append(None)
+                    else:
+                        hs.append(f"{util.fnv1a64(orc, np.ascontiguousarray(pl).reshape(-1)):016x}")
+                out["scale"].append({"src": [w, h], "dst": [dw, dh], "depth": depth, "fmt": int(fmt), "alpha": alpha, "seed": 1000 + k,
+                                     "result": res, "planes": hs})
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "scale_vectors.json"), "w"), indent=0)
+    tm = {}
+    cases = {"srgb8_to_pq10": dict(tc_in=13, tc_out=16, depth=10, headroom=1.5, cp_out=9),
+             "bt709_8_to_srgb8": dict(tc_in=1, tc_out=13, depth=8, headroom=3.0, cp_out=1),
+             "hlg10_to_hlg12": dict(tc_in=18, tc_out=18, depth=12, headroom=0.7, cp_out=12)}
+    for name, c in cases.items():
+        gm, keep = tg.make_gain_map(48, 32, seed=77)
+        base = tg.make_base(48, 32, 8, A.AVIF_RGB_FORMAT_RGBA, seed=78)
+        res, data, clli, _ = tg.apply(ref, base, 1, c["tc_in"], gm, c["headroom"], c["cp_out"], c["tc_out"], c["depth"], A.AVIF_RGB_FORMAT_RGBA)
+        assert res == 0
+        tm[name + "_pixels"] = data
+        tm[name + "_clli"] = np.array(clli, dtype=np.int64)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tonemap_vectors.npz"), **tm)
+    print("wrote scale_vectors.json", len(out["scale"]), "and tonemap_vectors.npz", len(tm))
 
 
 def tool_outputs():

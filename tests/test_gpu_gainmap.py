@@ -255,3 +255,23 @@ def test_argument_checks_need_no_device(product, reference):
         rb, _, _, eb = apply(product, base, 1, 13, g, headroom, 1, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
         assert ra == rb == 24, (ra, rb, ea, eb)
         assert ea and eb  # both explain themselves in diag
+
+
+@pytest.mark.gpu
+def test_committed_vectors(gpu_product):
+    """tests/golden/tonemap_vectors.npz: the reference's tone-mapped pixels for three small cases (tests/golden/make_golden.py).
+    Runs where neither /root/reference nor oracle/_ref exists."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tonemap_vectors.npz"))
+    cases = {"srgb8_to_pq10": dict(tc_in=13, tc_out=16, depth=10, headroom=1.5, cp_out=9),
+             "bt709_8_to_srgb8": dict(tc_in=1, tc_out=13, depth=8, headroom=3.0, cp_out=1),
+             "hlg10_to_hlg12": dict(tc_in=18, tc_out=18, depth=12, headroom=0.7, cp_out=12)}
+    for name, c in cases.items():
+        gm, keep = make_gain_map(48, 32, seed=77)
+        base = make_base(48, 32, 8, A.AVIF_RGB_FORMAT_RGBA, seed=78)
+        res, data, clli, err = apply(gpu_product, base, 1, c["tc_in"], gm, c["headroom"], c["cp_out"], c["tc_out"], c["depth"], A.AVIF_RGB_FORMAT_RGBA)
+        assert res == 0, err
+        worst, frac = compare(g[name + "_pixels"], data, c["depth"], False)
+        assert worst <= 1 and frac < 0.02, (name, worst, frac)
+        want = g[name + "_clli"]
+        assert abs(int(want[0]) - clli[0]) <= 1 and abs(int(want[1]) - clli[1]) <= 1

@@ -121,3 +121,24 @@ def test_argument_checks_need_no_device(product, reference):
     ra, _, _, _ = scaled_planes(reference, 16, 16, 8, A.AVIF_PIXEL_FORMAT_YUV444, False, 1, 16, 16)
     rb, _, _, _ = scaled_planes(product, 16, 16, 8, A.AVIF_PIXEL_FORMAT_YUV444, False, 1, 16, 16)
     assert ra == rb == 0
+
+
+@pytest.mark.gpu
+def test_committed_vectors(gpu_product, oracle):
+    """tests/golden/scale_vectors.json: hashes of the planes the compiled reference produced (tests/golden/make_golden.py).
+    Runs where neither /root/reference nor oracle/_ref exists."""
+    import json
+    import os
+    from tests import util
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scale_vectors.json")))["scale"]
+    for v in vec:
+        (w, h), (dw, dh) = v["src"], v["dst"]
+        res, planes, _, err = scaled_planes(gpu_product, w, h, v["depth"], v["fmt"], v["alpha"], v["seed"], dw, dh)
+        assert res == v["result"], (v, err)
+        if res != 0 or (w, h) == (dw, dh):
+            continue
+        for p, want in enumerate(v["planes"]):
+            if want is None:
+                continue
+            assert planes[p] is not None
+            assert f"{util.fnv1a64(oracle, np.ascontiguousarray(planes[p]).reshape(-1)):016x}" == want, (v["src"], v["dst"], v["depth"], v["fmt"], p)

@@ -158,3 +158,35 @@ def test_primaries_matrices_equal_the_reference(product, reference):
             assert bool(ra) == bool(rb), (a, b)
             if ra:
                 assert bytes(ma) == bytes(mb), (a, b, list(ma), list(mb))
+
+
+def test_position_tables_reproduce_the_committed_vectors(product, oracle):
+    """The same check against tests/golden/scale_vectors.json (plane hashes recorded from the compiled reference by
+    tests/golden/make_golden.py): needs neither /root/reference nor oracle/_ref nor a GPU."""
+    import json
+    import os
+    from tests import test_gpu_scale as ts
+    from tests import util
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "scale_vectors.json")))["scale"]
+    shifts = {A.AVIF_PIXEL_FORMAT_YUV444: (0, 0), A.AVIF_PIXEL_FORMAT_YUV422: (1, 0), A.AVIF_PIXEL_FORMAT_YUV420: (1, 1), A.AVIF_PIXEL_FORMAT_YUV400: (0, 0)}
+    checked = 0
+    for v in vec[::3]:  # every third vector keeps this under a few seconds; the GPU test walks all of them
+        (w, h), (dw, dh), depth, fmt = v["src"], v["dst"], v["depth"], v["fmt"]
+        if v["result"] != 0 or (w, h) == (dw, dh):
+            continue
+        img = ts.make_image(w, h, depth, fmt, v["alpha"], v["seed"])
+        sx, sy = shifts[fmt]
+        for p in range(4):
+            if v["planes"][p] is None:
+                continue
+            chroma = p in (1, 2)
+            sw, sh = ((w + sx) >> sx, (h + sy) >> sy) if chroma else (w, h)
+            pw, ph = ((dw + sx) >> sx, (dh + sy) >> sy) if chroma else (dw, dh)
+            raw = img.bufs[p].host()
+            src = raw[:, :sw * 2].copy().view(np.uint16).astype(np.int64) if depth > 8 else raw[:, :sw].astype(np.int64)
+            pl = plan(product, sw, sh, pw, ph, depth > 8)
+            got = src if pl[0] == 0 else emulate(src, pw, ph, depth > 8, pl) & (0xFFFF if depth > 8 else 0xFF)
+            data = got.astype(np.uint16).view(np.uint8) if depth > 8 else got.astype(np.uint8)
+            assert f"{util.fnv1a64(oracle, np.ascontiguousarray(data).reshape(-1)):016x}" == v["planes"][p], (v["src"], v["dst"], depth, fmt, p)
+            checked += 1
+    assert checked > 100
