@@ -156,3 +156,18 @@ def test_internal_seam_library_exports_the_reference_hook_names():
     exported = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     names = {line.split()[-1] for line in exported.splitlines() if " T " in line}
     assert names == set(hooks), names ^ set(hooks)
+
+
+def test_header_coexists_with_the_reference_headers_and_cxx():
+    """INTEGRATION.md's seams include avif_b200.h AFTER the reference's own headers (only the avifB200* extensions are then
+    declared), and C++ callers include it alone: both must compile."""
+    inc = os.path.join(ROOT, "include")
+    with tempfile.TemporaryDirectory() as td:
+        cxx = os.path.join(td, "a.cpp")
+        open(cxx, "w").write('#include "avif_b200.h"\nint main() { avifRGBImage r; avifGainMap g; (void)r; (void)g; return 0; }\n')
+        subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{inc}", cxx], check=True)
+        if os.path.isdir(REF_INCLUDE):
+            c = os.path.join(td, "b.c")
+            open(c, "w").write('#include "avif/avif.h"\n#include "avif/internal.h"\n#include "avif_b200.h"\n'
+                               'int main(void) { return avifB200DeviceAvailable() & 0; }\n')
+            subprocess.run(["gcc", "-std=gnu11", "-fsyntax-only", f"-I{REF_INCLUDE}", f"-I{inc}", c], check=True)
