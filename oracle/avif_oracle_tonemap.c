@@ -1,6 +1,6 @@
 /*
  * avif_oracle_tonemap.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement of gain-map tone mapping
- * (avifRGBImageApplyGainMap, ref: src/gainmap.c:73-315) for gain maps that already have the base image's size, with the
+ * (avifRGBImageApplyGainMap, ref: src/gainmap.c:73-315; gain maps of another size go through avif_oracle_scale.c first), with the
  * host libm like the reference: against the reference compiled from its own sources (oracle/_ref) it is BIT-EXACT
  * (tests/test_oracle_tonemap.py) -- parity status PINNED.  The CUDA kernel (libavif_b200/csrc/tonemap.cu) is compared with the
  * reference / this restatement to +-1 output code because CUDA's powf / exp2f are not glibc's.
@@ -19,6 +19,7 @@
 #define ORACLE_API __attribute__((visibility("default")))
 
 avifResult oracleImageYUVToRGB(const avifImage * image, avifRGBImage * rgb); /* avif_oracle.c */
+avifResult oracleImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeight, avifDiagnostics * diag); /* avif_oracle_scale.c */
 
 /* the few host helpers of src/avif.c this file needs, restated locally so that liboracle.so stays self-contained
  * (ref: src/avif.c:670-741); the output pixels are malloc'ed like avifAlloc does */
@@ -377,8 +378,7 @@ static float ufrac(avifUnsignedFraction f) { return f.d ? ((float)f.n / f.d) : 0
 static float clampf_u16(float v) { return (v < 0.0f) ? 0.0f : ((65535.0f < v) ? 65535.0f : v); }
 static float nanSafeClamp(float v) { return fminf(1.0f, fmaxf(0.0f, v)); }             /* ref: :13-16 */
 
-/* ref: src/gainmap.c:73-315.  Gain maps of another size than the base image (the reference rescales them with avifImageScale,
- * :186-201) are outside this restatement: AVIF_RESULT_NOT_IMPLEMENTED. */
+/* ref: src/gainmap.c:73-315 */
 ORACLE_API avifResult oracleRGBImageApplyGainMap(const avifRGBImage * base, avifColorPrimaries baseCP, avifTransferCharacteristics baseTC,
                                                  const avifGainMap * gm, float hdrHeadroom, avifColorPrimaries outCP,
                                                  avifTransferCharacteristics outTC, avifRGBImage * out,
@@ -441,13 +441,28 @@ ORACLE_API avifResult oracleRGBImageApplyGainMap(const avifRGBImage * base, avif
     Mat inM, outM;
     if (needIn && !rgbToRgb(baseCP, mathCP, inM)) return AVIF_RESULT_NOT_IMPLEMENTED;
     if (needOut && !rgbToRgb(mathCP, outCP, outM)) return AVIF_RESULT_NOT_IMPLEMENTED;
-    if (!gm->image || gm->image->width != W || gm->image->height != H) return AVIF_RESULT_NOT_IMPLEMENTED;
+    if (!gm->image) return AVIF_RESULT_INVALID_ARGUMENT;
+    const avifImage * gmImage = gm->image;
+    avifImage scaled;
+    int haveScaled = 0;
+    if (gmImage->width != W || gmImage->height != H) { /* ref: :186-201, through avif_oracle_scale.c */
+        scaled = *gmImage; /* a view: the scaler replaces the planes with its own and owns those */
+        scaled.imageOwnsYUVPlanes = AVIF_FALSE;
+        scaled.imageOwnsAlphaPlane = AVIF_FALSE;
+        res = oracleImageScale(&scaled, W, H, NULL);
+        if (res != AVIF_RESULT_OK) return res;
+        haveScaled = 1;
+        gmImage = &scaled;
+    }
 
     avifRGBImage g; /* ref: :203-212 */
-    setDefaults(&g, gm->image);
+    setDefaults(&g, gmImage);
     res = allocPixels(&g);
-    if (res != AVIF_RESULT_OK) return res;
-    res = oracleImageYUVToRGB(gm->image, &g);
+    if (res == AVIF_RESULT_OK) res = oracleImageYUVToRGB(gmImage, &g);
+    if (haveScaled) {
+        for (int c = 0; c < 3; ++c) free(scaled.yuvPlanes[c]);
+        free(scaled.alphaPlane);
+    }
     if (res != AVIF_RESULT_OK || !layoutOf(&g, &LG)) {
         free(g.pixels);
         return (res != AVIF_RESULT_OK) ? res : AVIF_RESULT_NOT_IMPLEMENTED;

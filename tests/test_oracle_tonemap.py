@@ -90,3 +90,16 @@ def test_rgb565_zero_weight_and_errors_bit_exact(oracle, reference):
     ra, _, _ = apply_any(reference, b8, 1, 13, bad, 3.0, 9, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
     rb, _, _ = apply_any(oracle, b8, 1, 13, bad, 3.0, 9, 13, 8, A.AVIF_RGB_FORMAT_RGBA)
     assert ra == rb
+
+
+def test_rescaled_gain_maps_bit_exact(oracle, reference):
+    """src/gainmap.c:186-201: gain maps of another size are brought to the base image's size by avifImageScale first."""
+    w, h = 64, 40
+    base = tg.make_base(w, h, 8, A.AVIF_RGB_FORMAT_RGBA, seed=21)
+    for gw, gh, fmt, depth in ((32, 20, A.AVIF_PIXEL_FORMAT_YUV444, 8), (16, 10, A.AVIF_PIXEL_FORMAT_YUV420, 10), (150, 99, A.AVIF_PIXEL_FORMAT_YUV400, 8),
+                               (64, 13, A.AVIF_PIXEL_FORMAT_YUV444, 12), (21, 40, A.AVIF_PIXEL_FORMAT_YUV422, 8)):
+        gm, keep = tg.make_gain_map(gw, gh, depth=depth, fmt=fmt, seed=gw * 5 + gh)
+        ra, a, ca = apply_any(reference, base, 1, 13, gm, 2.0, 9, 16, 10, A.AVIF_RGB_FORMAT_RGBA)
+        rb, b, cb = apply_any(oracle, base, 1, 13, gm, 2.0, 9, 16, 10, A.AVIF_RGB_FORMAT_RGBA)
+        assert ra == rb == 0, (gw, gh, ra, rb)
+        assert np.array_equal(a, b) and ca == cb, (gw, gh, fmt)
