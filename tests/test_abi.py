@@ -171,3 +171,20 @@ def test_header_coexists_with_the_reference_headers_and_cxx():
             open(c, "w").write('#include "avif/avif.h"\n#include "avif/internal.h"\n#include "avif_b200.h"\n'
                                'int main(void) { return avifB200DeviceAvailable() & 0; }\n')
             subprocess.run(["gcc", "-std=gnu11", "-fsyntax-only", f"-I{REF_INCLUDE}", f"-I{inc}", c], check=True)
+
+
+def test_c_client_example_builds_and_fails_loudly_without_a_device(tmp_path):
+    """examples/convert_frame.c is a plain C caller of the public ABI.  It must link against the library as is; on a machine
+    without a CUDA device the conversion must FAIL (exit code 3, no CPU fallback), with one it must succeed."""
+    csrc = os.path.join(ROOT, "libavif_b200", "csrc")
+    exe = str(tmp_path / "convert_frame")
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Wextra", "-Werror", f"-I{os.path.join(ROOT, 'include')}", os.path.join(ROOT, "examples", "convert_frame.c"),
+                    f"-L{csrc}", "-lavif_b200", f"-Wl,-rpath,{csrc}", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    import libavif_b200
+    if libavif_b200.device_available():
+        assert out.returncode == 0, out.stderr
+        assert "kernel: y2r_" in out.stdout
+    else:
+        assert out.returncode == 3
+        assert "no CPU fallback" in out.stderr
