@@ -371,7 +371,23 @@ AVIF_B200_API avifResult avifB200ImageLimitedToFullAlpha(avifImage * image);
 AVIF_B200_API avifResult avifB200ImageCopySamplesAsync(avifImage * dst, const avifImage * src, avifPlanesFlags planes, void * stream);
 AVIF_B200_API avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, void * stream);
 
-/* Pinned host memory helpers for callers that want full PCIe rate on the host-pointer path. */
+/* ---- which GPU serves a synchronous (host-pointer) call ----------------------------------------------------------------
+ * The reference has no notion of a device; its own parallel unit is the per-call thread fan-out of
+ * src/reformat.c:1679-1747.  Here several host threads may convert at once (avif.h:1012-1014), each on a GPU chosen as follows:
+ *   1. a plane / pixel pointer that is device memory pins the call to that memory's device;
+ *   2. else the device the calling thread selected with avifB200SetDevice(d)  (d < 0: back to the policy);
+ *   3. else the device the process policy dealt to this thread the first time it entered the library: the list given to
+ *      avifB200SetDevices(), else the environment variable AVIF_B200_DEVICES ("all" or a list like "0,2,5"), dealt round-robin
+ *      in first-touch order; with neither, every visible device round-robin starting at the thread's current CUDA device.
+ * The thread's current CUDA device is restored before the call returns.  Each (thread, device) pair owns its streams, its
+ * device arena and its pinned ring; they are released when the thread exits.  The stream-ordered (*Async) entry points
+ * never select a device: the caller's stream defines it.  avifB200GetDevice() = what rule 2/3 gives the calling thread. */
+AVIF_B200_API avifResult avifB200SetDevice(int device);
+AVIF_B200_API avifResult avifB200SetDevices(const int * devices, int count);
+AVIF_B200_API int avifB200GetDevice(void);
+
+/* Pinned host memory helpers for callers that want full PCIe rate on the host-pointer path.  Pageable (malloc) buffers work
+ * as well: the calling thread stages them through a pinned ring while the copy engines run (shim.c: stagedUpload). */
 AVIF_B200_API void * avifB200AllocPinned(size_t size);
 AVIF_B200_API void avifB200FreePinned(void * p);
 

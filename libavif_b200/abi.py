@@ -147,6 +147,9 @@ PROTOTYPES = {
     "avifFullToLimitedUV": (C.c_int, [C.c_uint32, C.c_int]),
     "avifLimitedToFullY": (C.c_int, [C.c_uint32, C.c_int]),
     "avifLimitedToFullUV": (C.c_int, [C.c_uint32, C.c_int]),
+    "avifB200SetDevice": (C.c_int, [C.c_int]),
+    "avifB200SetDevices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "avifB200GetDevice": (C.c_int, []),
     "avifRGBFormatChannelCount": (C.c_uint32, [C.c_int]),
     "avifRGBFormatHasAlpha": (C.c_int, [C.c_int]),
     "avifRGBFormatIsGray": (C.c_int, [C.c_int]),

@@ -234,7 +234,7 @@ int abScratchAlloc(void ** p, size_t bytes)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    if (dev < 0 || dev >= kMaxDevices) return (int)cudaMallocAsync(p, bytes, NULL);
+    if (dev < 0 || dev >= kMaxDevices) return (int)cudaMallocAsync(p, bytes, AB_STREAM);
     if (!__atomic_load_n(&made[dev], __ATOMIC_ACQUIRE)) {
         static int lock = 0;
         while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {
@@ -256,7 +256,7 @@ int abScratchAlloc(void ** p, size_t bytes)
         __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
         if (e != cudaSuccess) return (int)e;
     }
-    return (int)cudaMallocFromPoolAsync(p, bytes, pools[dev], NULL);
+    return (int)cudaMallocFromPoolAsync(p, bytes, pools[dev], AB_STREAM);
 }
 
 #define GM_CUDA(call)                                                        \
@@ -314,7 +314,8 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         baseImage->format == toneMappedImage->format && baseImage->depth == toneMappedImage->depth && baseImage->isFloat == toneMappedImage->isFloat &&
         baseImage->rowBytes == toneMappedImage->rowBytes) {
         const size_t n = (size_t)baseImage->rowBytes * baseImage->height;
-        GM_CUDA(cudaMemcpy(toneMappedImage->pixels, baseImage->pixels, n, cudaMemcpyDefault)); /* either side may live on the device */
+        GM_CUDA(cudaMemcpyAsync(toneMappedImage->pixels, baseImage->pixels, n, cudaMemcpyDefault, AB_STREAM)); /* either side may live on the device */
+        GM_CUDA(cudaStreamSynchronize(AB_STREAM));
         return AVIF_RESULT_OK;
     }
 
@@ -405,7 +406,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         }
         rgbGain.rowBytes = (uint32_t)(((size_t)width * job.gainFmt.pixBytes + 255) & ~(size_t)255);
         GM_CUDA((cudaError_t)abScratchAlloc((void **)&dGain, (size_t)rgbGain.rowBytes * height));
-        GM_CUDA(cudaStreamSynchronize(NULL)); /* the conversion below runs on the library's own streams */
+        GM_CUDA(cudaStreamSynchronize(AB_STREAM)); /* the conversion below runs on the library's own streams */
         rgbGain.pixels = dGain;
         res = avifImageYUVToRGB(gmImage, &rgbGain);
         if (res != AVIF_RESULT_OK) goto cleanup;
@@ -438,7 +439,7 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         const size_t rowUsed = (size_t)width * job.baseFmt.pixBytes;
         const size_t pitch = (rowUsed + 255) & ~(size_t)255;
         GM_CUDA((cudaError_t)abScratchAlloc((void **)&dBase, pitch * height));
-        GM_CUDA(cudaMemcpy2D(dBase, pitch, baseImage->pixels, baseImage->rowBytes, rowUsed, height, cudaMemcpyHostToDevice));
+        GM_CUDA(cudaMemcpy2DAsync(dBase, pitch, baseImage->pixels, baseImage->rowBytes, rowUsed, height, cudaMemcpyHostToDevice, AB_STREAM));
         job.base = dBase;
         job.baseRB = (int64_t)pitch;
     }
@@ -455,18 +456,22 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
         }
         struct { double sum; uint32_t maxBits, nanIndex; } stats = { 0.0, 0u, 0xFFFFFFFFu };
         GM_CUDA((cudaError_t)abScratchAlloc((void **)&dStats, sizeof(stats)));
-        GM_CUDA(cudaMemcpy(dStats, &stats, sizeof(stats), cudaMemcpyHostToDevice));
+        GM_CUDA(cudaMemcpyAsync(dStats, &stats, sizeof(stats), cudaMemcpyHostToDevice, AB_STREAM));
         job.sum = (double *)dStats;
         job.maxBits = (uint32_t *)(dStats + offsetof(__typeof__(stats), maxBits));
         job.nanIndex = (uint32_t *)(dStats + offsetof(__typeof__(stats), nanIndex));
-        GM_CUDA((cudaError_t)abLaunchToneMap(&job, NULL));
-        GM_CUDA(cudaMemcpy(&stats, dStats, sizeof(stats), cudaMemcpyDeviceToHost)); /* synchronises the launch */
+        GM_CUDA((cudaError_t)abLaunchToneMap(&job, AB_STREAM));
+        GM_CUDA(cudaMemcpyAsync(&stats, dStats, sizeof(stats), cudaMemcpyDeviceToHost, AB_STREAM));
+        GM_CUDA(cudaStreamSynchronize(AB_STREAM)); /* the launch and the read-back */
         if (job.applyGain && stats.nanIndex != 0xFFFFFFFFu) { /* src/gainmap.c:283-288 */
             diagSet(diag, "Degenerate gain map parameters produce NaN at pixel (%u, %u)", stats.nanIndex % width, stats.nanIndex / width);
             res = AVIF_RESULT_INVALID_TONE_MAPPED_IMAGE;
             goto cleanup;
         }
-        if (!deviceOut) GM_CUDA(cudaMemcpy2D(toneMappedImage->pixels, toneMappedImage->rowBytes, dOut, pitch, rowUsed, height, cudaMemcpyDeviceToHost));
+        if (!deviceOut) {
+            GM_CUDA(cudaMemcpy2DAsync(toneMappedImage->pixels, toneMappedImage->rowBytes, dOut, pitch, rowUsed, height, cudaMemcpyDeviceToHost, AB_STREAM));
+            GM_CUDA(cudaStreamSynchronize(AB_STREAM));
+        }
         if (clli && job.applyGain) { /* src/gainmap.c:297-306 */
             float rgbMaxLinear;
             memcpy(&rgbMaxLinear, &stats.maxBits, sizeof(rgbMaxLinear));
@@ -484,14 +489,31 @@ static avifResult applyCommon(const avifRGBImage * baseImage, avifColorPrimaries
     res = AVIF_RESULT_OK;
 
 cleanup:
-    if (dBase) (void)cudaFreeAsync(dBase, NULL);
-    if (dGain) (void)cudaFreeAsync(dGain, NULL);
-    if (dOut) (void)cudaFreeAsync(dOut, NULL);
-    if (dStats) (void)cudaFreeAsync(dStats, NULL);
-    if (dLut) (void)cudaFreeAsync(dLut, NULL);
+    if (dBase) (void)cudaFreeAsync(dBase, AB_STREAM);
+    if (dGain) (void)cudaFreeAsync(dGain, AB_STREAM);
+    if (dOut) (void)cudaFreeAsync(dOut, AB_STREAM);
+    if (dStats) (void)cudaFreeAsync(dStats, AB_STREAM);
+    if (dLut) (void)cudaFreeAsync(dLut, AB_STREAM);
     for (int c = 0; c < 3; ++c) {
-        if (dScaled[c]) (void)cudaFreeAsync(dScaled[c], NULL);
+        if (dScaled[c]) (void)cudaFreeAsync(dScaled[c], AB_STREAM);
     }
+    return res;
+}
+
+/* applyCommon on the device the call belongs to (shim.c: device policy; resident buffers pin it) */
+static avifResult applyScoped(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
+                              avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap, float hdrHeadroom,
+                              avifColorPrimaries outputColorPrimaries, avifTransferCharacteristics outputTransferCharacteristics,
+                              avifRGBImage * toneMappedImage, avifContentLightLevelInformationBox * clli, avifDiagnostics * diag, int deviceOut)
+{
+    const void * ptrs[3] = { (deviceOut && toneMappedImage) ? toneMappedImage->pixels : NULL, baseImage ? baseImage->pixels : NULL,
+                             (gainMap && gainMap->image) ? gainMap->image->yuvPlanes[0] : NULL };
+    int prev = -1;
+    avifResult res = (avifResult)abDeviceEnter(ptrs, 3, &prev);
+    if (res != AVIF_RESULT_OK) return res;
+    res = applyCommon(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
+                      outputTransferCharacteristics, toneMappedImage, clli, diag, deviceOut);
+    abDeviceLeave(prev);
     return res;
 }
 
@@ -500,7 +522,7 @@ avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPri
                                     avifColorPrimaries outputColorPrimaries, avifTransferCharacteristics outputTransferCharacteristics,
                                     avifRGBImage * toneMappedImage, avifContentLightLevelInformationBox * clli, avifDiagnostics * diag)
 {
-    return applyCommon(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
+    return applyScoped(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
                        outputTransferCharacteristics, toneMappedImage, clli, diag, 0);
 }
 /* extension: everything stays on the device -- base pixels, the gain map's planes and the caller-allocated output */
@@ -510,7 +532,7 @@ avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage * baseImage, av
                                               avifTransferCharacteristics outputTransferCharacteristics, avifRGBImage * toneMappedImage,
                                               avifContentLightLevelInformationBox * clli, avifDiagnostics * diag)
 {
-    return applyCommon(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
+    return applyScoped(baseImage, baseColorPrimaries, baseTransferCharacteristics, gainMap, hdrHeadroom, outputColorPrimaries,
                        outputTransferCharacteristics, toneMappedImage, clli, diag, 1);
 }
 
@@ -532,8 +554,15 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
     if (!baseImage->width || !baseImage->height) return AVIF_RESULT_INVALID_ARGUMENT;
     baseRgb.rowBytes = baseImage->width * pixBytes;
     uint8_t * dev = NULL;
-    if ((cudaError_t)abScratchAlloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess || cudaStreamSynchronize(NULL) != cudaSuccess) {
+    const void * ptrs[2] = { baseImage->yuvPlanes[0], (gainMap && gainMap->image) ? gainMap->image->yuvPlanes[0] : NULL };
+    int prevDevice = -1;
+    {
+        const avifResult er = (avifResult)abDeviceEnter(ptrs, 2, &prevDevice);
+        if (er != AVIF_RESULT_OK) return er;
+    }
+    if ((cudaError_t)abScratchAlloc((void **)&dev, (size_t)baseRgb.rowBytes * baseImage->height) != cudaSuccess || cudaStreamSynchronize(AB_STREAM) != cudaSuccess) {
         (void)cudaGetLastError();
+        abDeviceLeave(prevDevice);
         return AVIF_RESULT_OUT_OF_MEMORY;
     }
     baseRgb.pixels = dev;
@@ -542,6 +571,7 @@ avifResult avifImageApplyGainMap(const avifImage * baseImage, const avifGainMap 
         res = avifRGBImageApplyGainMap(&baseRgb, baseImage->colorPrimaries, baseImage->transferCharacteristics, gainMap, hdrHeadroom,
                                        outputColorPrimaries, outputTransferCharacteristics, toneMappedImage, clli, diag);
     }
-    (void)cudaFreeAsync(dev, NULL);
+    (void)cudaFreeAsync(dev, AB_STREAM);
+    abDeviceLeave(prevDevice);
     return res;
 }

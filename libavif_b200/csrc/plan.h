@@ -212,8 +212,16 @@ typedef struct AbToneMapJob {
     double * sum;
 } AbToneMapJob;
 int abLaunchToneMap(const AbToneMapJob * job, void * stream);
-/* Stream-ordered (legacy default stream) device scratch from a per-device pool that keeps freed memory instead of returning it
- * to the driver at every synchronisation (gainmap.c); release with cudaFreeAsync(p, NULL).  Returns a cudaError_t value. */
+/* Every host-synchronous helper outside shim.c (tone mapping, scaling) works on the calling thread's own default stream:
+ * unlike the legacy NULL stream it does not serialise with the streams of other threads or of the host application. */
+#define AB_STREAM ((cudaStream_t)0x2) /* == cudaStreamPerThread */
+/* Device selection of a synchronous call (shim.c: policy of avifB200SetDevice / avifB200SetDevices; a pointer that is device
+ * memory pins the call to its device): makes that device current and returns the previous one in *prevDevice (-1: unchanged).
+ * Returns an avifResult value; succeeds without doing anything when no CUDA device exists (the CUDA calls that follow report it). */
+int abDeviceEnter(const void * const * ptrs, int n, int * prevDevice);
+void abDeviceLeave(int prevDevice);
+/* Stream-ordered (AB_STREAM) device scratch from a per-device pool that keeps freed memory instead of returning it
+ * to the driver at every synchronisation (gainmap.c); release with cudaFreeAsync(p, AB_STREAM).  Returns a cudaError_t value. */
 int abScratchAlloc(void ** p, size_t bytes);
 
 /* ---- plane scaling (scale_kernels.cu; src/scale.c over third_party/libyuv/source/scale*.c) ----

@@ -525,13 +525,17 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
         F.groups = (F.tiles + kRWarps - 1) / kRWarps;
         groups += F.groups;
     }
-    static int resident = 0; /* blocks resident on the whole device (per instantiation) */
+    /* blocks that fit on the whole device at once: per instantiation and per device (a process may drive several GPUs) */
+    static int residentOf[16] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int resident = (dev >= 0 && dev < 16) ? residentOf[dev] : 0;
     if (!resident) {
-        int dev = 0, sms = 0, perSm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+        if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);

@@ -323,7 +323,7 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
     for (int k = 0; k < count; ++k) {
         if (plans[k].mode == 0) { /* same size: CopyPlane (scale.c:849-853) */
             e = cudaMemcpy2DAsync(io[k].dst, (size_t)io[k].dstRB, io[k].src, (size_t)io[k].srcRB, (size_t)io[k].dw * bps, (size_t)io[k].dh,
-                                  cudaMemcpyDeviceToDevice, NULL);
+                                  cudaMemcpyDeviceToDevice, AB_STREAM);
             if (e != cudaSuccess) goto done;
             continue;
         }
@@ -348,15 +348,15 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
         at += (size_t)io[k].dw * 4;
     }
     if (batch.count) {
-        e = cudaMemcpyAsync(dTab, hTab, tableInts * sizeof(int32_t), cudaMemcpyHostToDevice, NULL);
-        if (e == cudaSuccess) e = (cudaError_t)abLaunchScaleBatch(&batch, NULL);
+        e = cudaMemcpyAsync(dTab, hTab, tableInts * sizeof(int32_t), cudaMemcpyHostToDevice, AB_STREAM);
+        if (e == cudaSuccess) e = (cudaError_t)abLaunchScaleBatch(&batch, AB_STREAM);
     }
     /* hTab is pageable: the copy has been staged when cudaMemcpyAsync returns, but one synchronisation per image keeps the
      * lifetime rules simple (and callers of the synchronous API expect finished planes) */
-    if (e == cudaSuccess) e = cudaStreamSynchronize(NULL);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(AB_STREAM);
 
 done:
-    if (dTab) (void)cudaFreeAsync(dTab, NULL);
+    if (dTab) (void)cudaFreeAsync(dTab, AB_STREAM);
     free(hTab);
     for (int k = 0; k < count; ++k) planFree(&plans[k]);
     return e;
@@ -380,9 +380,21 @@ static void diagf(avifDiagnostics * diag, const char * msg, unsigned a, unsigned
 
 /* Extension used by the tone mapper: scale the planes of `src` (host or device pointers) into DEVICE planes described by
  * `dst` (planes allocated by the caller with cudaMalloc-family calls, dimensions and row strides set). */
+static avifResult scaleToDeviceBody(const avifImage * src, avifImage * dst);
 avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
 {
     if (!src || !dst || !dst->width || !dst->height) return AVIF_RESULT_INVALID_ARGUMENT;
+    const void * ptrs[8] = { dst->yuvPlanes[0], dst->yuvPlanes[1], dst->yuvPlanes[2], dst->alphaPlane,
+                             src->yuvPlanes[0], src->yuvPlanes[1], src->yuvPlanes[2], src->alphaPlane };
+    int prev = -1;
+    avifResult res = (avifResult)abDeviceEnter(ptrs, 8, &prev);
+    if (res != AVIF_RESULT_OK) return res;
+    res = scaleToDeviceBody(src, dst);
+    abDeviceLeave(prev);
+    return res;
+}
+static avifResult scaleToDeviceBody(const avifImage * src, avifImage * dst)
+{
     if (src->width > 16384 || src->height > 16384) return AVIF_RESULT_NOT_IMPLEMENTED; /* src/scale.c:65-76 */
     const int bps = (src->depth > 8) ? 2 : 1;
     avifPixelFormatInfo info;
@@ -410,7 +422,7 @@ avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
         if (!onDevice(sp)) {
             const size_t pitch = ((size_t)p->sw * bps + 255) & ~(size_t)255;
             e = (cudaError_t)abScratchAlloc((void **)&staged[count], pitch * (size_t)p->sh);
-            if (e == cudaSuccess) e = cudaMemcpy2DAsync(staged[count], pitch, sp, srb, (size_t)p->sw * bps, (size_t)p->sh, cudaMemcpyHostToDevice, NULL);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(staged[count], pitch, sp, srb, (size_t)p->sw * bps, (size_t)p->sh, cudaMemcpyHostToDevice, AB_STREAM);
             p->src = staged[count];
             p->srcRB = (int64_t)pitch;
         }
@@ -418,7 +430,7 @@ avifResult avifB200ImageScaleToDevice(const avifImage * src, avifImage * dst)
     }
     if (e == cudaSuccess && count) e = scalePlanesOnDevice(io, count, bps, &oom);
     for (int k = 0; k < AB_SCALE_MAX_PLANES; ++k) {
-        if (staged[k]) (void)cudaFreeAsync(staged[k], NULL);
+        if (staged[k]) (void)cudaFreeAsync(staged[k], AB_STREAM);
     }
     if (oom) return AVIF_RESULT_OUT_OF_MEMORY;
     if (e != cudaSuccess) {
@@ -440,6 +452,12 @@ avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeig
     if (dstWidth > (16384u * 16384u) / dstHeight || dstWidth > 32768u || dstHeight > 32768u) { /* avifDimensionsTooLarge, src/avif.c:646-655 */
         diagf(diag, "avifImageScale requested dst dimensions that are too large [%ux%u]", dstWidth, dstHeight);
         return AVIF_RESULT_NOT_IMPLEMENTED;
+    }
+    const void * devPtrs[4] = { image->yuvPlanes[0], image->yuvPlanes[1], image->yuvPlanes[2], image->alphaPlane };
+    int prevDevice = -1;
+    {
+        const avifResult er = (avifResult)abDeviceEnter(devPtrs, 4, &prevDevice);
+        if (er != AVIF_RESULT_OK) return er;
     }
     /* the source planes step aside, the image takes the new size (src/scale.c:40-63) */
     avifImage old = *image;
@@ -519,7 +537,8 @@ avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeig
             uint8_t * host = (c < 3) ? image->yuvPlanes[c] : image->alphaPlane;
             const uint32_t hostRB = (c < 3) ? image->yuvRowBytes[c] : image->alphaRowBytes;
             const uint32_t devRB = (c < 3) ? dev.yuvRowBytes[c] : dev.alphaRowBytes;
-            if (cudaMemcpy2D(host, hostRB, dPlanes[c], devRB, (size_t)cs * w, h, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            if (cudaMemcpy2DAsync(host, hostRB, dPlanes[c], devRB, (size_t)cs * w, h, cudaMemcpyDeviceToHost, AB_STREAM) != cudaSuccess ||
+                cudaStreamSynchronize(AB_STREAM) != cudaSuccess) {
                 (void)cudaGetLastError();
                 res = AVIF_RESULT_UNKNOWN_ERROR;
                 goto cleanup;
@@ -529,7 +548,7 @@ avifResult avifImageScale(avifImage * image, uint32_t dstWidth, uint32_t dstHeig
 
 cleanup:
     for (int c = 0; c < 4; ++c) {
-        if (dPlanes[c]) (void)cudaFreeAsync(dPlanes[c], NULL);
+        if (dPlanes[c]) (void)cudaFreeAsync(dPlanes[c], AB_STREAM);
     }
     /* the old planes are released if the image owned them (src/scale.c:189-198); on a device box that may be cudaFree'd memory
      * only if the caller allocated it that way AND handed ownership over, which the reference's avifFree == free forbids too */
@@ -537,5 +556,6 @@ cleanup:
         for (int c = 0; c < 3; ++c) free(old.yuvPlanes[c]);
     }
     if (old.alphaPlane && old.imageOwnsAlphaPlane) free(old.alphaPlane);
+    abDeviceLeave(prevDevice);
     return res;
 }

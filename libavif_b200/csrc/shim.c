@@ -18,6 +18,7 @@
 
 #include <cuda_runtime_api.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -128,21 +129,47 @@ int avifFullToLimitedY(uint32_t depth, int v) { return fullToLim(depth, 0, v); }
 int avifFullToLimitedUV(uint32_t depth, int v) { return fullToLim(depth, 1, v); }
 
 /* ------------------------------------------------------------------------------------------ */
-/* per-thread CUDA context: stream + staging arena                                             */
+/* per-thread, per-device CUDA contexts: streams + staging arena + pinned ring                 */
 
 #define AB_MAX_BANDS 16
+#define AB_MAX_DEVICES 16
+#define AB_RING_SLOTS 4
 
+/* One context = everything a synchronous host-pointer call needs on ONE device.  A host thread owns up to one context
+ * per device (created lazily); which one a call uses is decided per call (ctxEnter).  Contexts are destroyed when the
+ * thread exits (pthread key destructor). */
 typedef struct AbCtx {
     int ready;
+    int device;
     cudaStream_t stream;           /* kernels (and everything, on the unpipelined path) */
     cudaStream_t up, up2, down;    /* host->device (two, alternating bands) / device->host copy streams of the band pipeline */
     cudaEvent_t evUp[AB_MAX_BANDS], evKernel[AB_MAX_BANDS];
     uint8_t * arena;
     size_t arenaCap;
+    /* pinned staging ring for pageable host memory (stagedUpload / stagedDownload): AB_RING_SLOTS chunks that the host
+     * thread fills / drains with memcpy while the copy engines move the previous ones */
+    uint8_t * ring;
+    size_t ringSlotBytes;
+    cudaEvent_t evRing[AB_RING_SLOTS];
+} AbCtx;
+
+typedef struct AbThread {
+    AbCtx ctx[AB_MAX_DEVICES];
+    int assigned;    /* device handed to this thread by the process policy at first touch (-1: none yet) */
+    int explicitDev; /* avifB200SetDevice (-1: follow the policy) */
+} AbThread;
+
+typedef struct AbScope { /* one synchronous call: device selection + context binding (ctxEnter / ctxLeave) */
+    int prevDevice;
+    AbCtx * prevCx;
+} AbScope;
+
+static _Thread_local AbThread * tlsThread = NULL;
+static _Thread_local AbCtx * cx = NULL; /* context of the synchronous call in progress */
+static _Thread_local struct {
     int policy; /* 0 auto, 1 force generic kernels */
     const char * lastKernel;
-} AbCtx;
-static _Thread_local AbCtx tls;
+} tls;
 static _Thread_local int tlsZeroCopy = 0;      /* experiment: kernels read / write pinned host memory directly over PCIe */
 static _Thread_local int tlsExactDivision = 0; /* 1: always use IEEE division instructions (tests cross-check both forms) */
 /* Set while serving the reference's internal libyuv seam (avifB200HookImageYUVToRGB): colour conversion only -- the caller
@@ -161,8 +188,9 @@ static avifResult cudaToResult(int err)
         if (abErr_ != cudaSuccess) return cudaToResult(abErr_); \
     } while (0)
 
-static avifResult ctxInit(void);
 static AbDiv makeIntDiv(float d);
+static avifResult ctxEnter(AbScope * sc, int pointerDevice);
+static avifResult ctxLeave(AbScope * sc, avifResult res);
 
 int avifB200DeviceAvailable(void)
 {
@@ -200,19 +228,21 @@ avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches)
 {
     float d;
     memcpy(&d, &divisorBits, sizeof(d));
-    avifResult res = ctxInit();
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, -1);
     if (res != AVIF_RESULT_OK) return res;
     unsigned long long bad = 0;
-    AB_CUDA(abDivSelfTest(d, &bad, tls.stream));
+    res = cudaToResult(abDivSelfTest(d, &bad, cx->stream));
     *mismatches = bad;
-    return AVIF_RESULT_OK;
+    return ctxLeave(&sc, res);
 }
 
 avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches)
 {
     float d;
     memcpy(&d, &divisorBits, sizeof(d));
-    avifResult res = ctxInit();
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, -1);
     if (res != AVIF_RESULT_OK) return res;
     const int saved = tlsExactDivision;
     tlsExactDivision = 0;
@@ -220,9 +250,9 @@ avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, u
     tlsExactDivision = saved;
     if (hostVerdict) *hostVerdict = dv.intExact;
     unsigned long long bad = 0;
-    AB_CUDA(abIntDivSelfTest(&dv, &bad, tls.stream));
+    res = cudaToResult(abIntDivSelfTest(&dv, &bad, cx->stream));
     *mismatches = bad;
-    return AVIF_RESULT_OK;
+    return ctxLeave(&sc, res);
 }
 
 /* verified_premul.h lookup: constants of the 2-fma integer premultiply for this channel depth (0 = none) */
@@ -262,23 +292,25 @@ avifResult avifB200SelfTestPremulFma(uint32_t depth, uint64_t * mismatches)
     float r, k;
     if (!mismatches) return AVIF_RESULT_INVALID_ARGUMENT;
     if (!premulFmaConstants(depth, &r, &k)) return AVIF_RESULT_NOT_IMPLEMENTED;
-    avifResult res = ctxInit();
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, -1);
     if (res != AVIF_RESULT_OK) return res;
     unsigned long long bad = 0;
-    AB_CUDA(abPremulFmaSelfTest((1u << depth) - 1, r, k, &bad, tls.stream));
+    res = cudaToResult(abPremulFmaSelfTest((1u << depth) - 1, r, k, &bad, cx->stream));
     *mismatches = bad;
-    return AVIF_RESULT_OK;
+    return ctxLeave(&sc, res);
 }
 
 avifResult avifB200SelfTestAlphaDivision(uint32_t depth, int sampledColour, uint64_t * mismatches)
 {
     if (depth < 2 || depth > 16) return AVIF_RESULT_INVALID_ARGUMENT;
-    avifResult res = ctxInit();
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, -1);
     if (res != AVIF_RESULT_OK) return res;
     unsigned long long bad = 0;
-    AB_CUDA(abAlphaDivSelfTest((1u << depth) - 1, sampledColour ? 1 : 0, &bad, tls.stream));
+    res = cudaToResult(abAlphaDivSelfTest((1u << depth) - 1, sampledColour ? 1 : 0, &bad, cx->stream));
     *mismatches = bad;
-    return AVIF_RESULT_OK;
+    return ctxLeave(&sc, res);
 }
 
 void * avifB200AllocPinned(size_t size)
@@ -295,48 +327,321 @@ void avifB200FreePinned(void * p)
     if (p) (void)cudaFreeHost(p);
 }
 
-static avifResult ctxInit(void)
+/* ---- device policy ---------------------------------------------------------------------------
+ * Which GPU serves a synchronous host-pointer call (the reference has no notion of a device; its own parallel unit is the
+ * per-call thread fan-out of src/reformat.c:1679-1747, here: host threads x GPUs):
+ *   1. a plane / pixel pointer that is device memory pins the call to that memory's device;
+ *   2. else the device the calling thread chose with avifB200SetDevice();
+ *   3. else the device the process policy handed this thread when it first entered the library: the list given to
+ *      avifB200SetDevices() / the environment variable AVIF_B200_DEVICES ("all" or "0,2,5"), dealt round-robin in
+ *      first-touch order; without either, all visible devices round-robin STARTING AT the thread's current CUDA device
+ *      (so a single-threaded CUDA application stays on the device it selected, and a pool of N worker threads of a
+ *      CUDA-unaware application is spread over the GPUs instead of piling up on device 0).
+ * The caller's current device is restored when the call returns.  Stream-ordered (Async) entry points never touch the
+ * current device: the caller's stream defines it. */
+static struct {
+    int count;                /* 0: not initialised */
+    int list[AB_MAX_DEVICES];
+    int fromUser;             /* list came from avifB200SetDevices / AVIF_B200_DEVICES */
+    unsigned next;            /* round-robin cursor */
+} gPolicy;
+static pthread_mutex_t gPolicyLock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_key_t gThreadKey;
+static pthread_once_t gThreadKeyOnce = PTHREAD_ONCE_INIT;
+
+static void ctxDestroy(AbCtx * c)
 {
-    if (tls.ready) return AVIF_RESULT_OK;
-    if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR; /* no CPU fallback by design */
-    AB_CUDA(cudaStreamCreateWithFlags(&tls.stream, cudaStreamNonBlocking));
-    AB_CUDA(cudaStreamCreateWithFlags(&tls.up, cudaStreamNonBlocking));
-    AB_CUDA(cudaStreamCreateWithFlags(&tls.up2, cudaStreamNonBlocking));
-    AB_CUDA(cudaStreamCreateWithFlags(&tls.down, cudaStreamNonBlocking));
-    for (int k = 0; k < AB_MAX_BANDS; ++k) {
-        AB_CUDA(cudaEventCreateWithFlags(&tls.evUp[k], cudaEventDisableTiming));
-        AB_CUDA(cudaEventCreateWithFlags(&tls.evKernel[k], cudaEventDisableTiming));
+    if (!c->ready) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (cudaSetDevice(c->device) == cudaSuccess) {
+        (void)cudaStreamSynchronize(c->stream);
+        (void)cudaStreamSynchronize(c->up);
+        (void)cudaStreamSynchronize(c->up2);
+        (void)cudaStreamSynchronize(c->down);
+        for (int k = 0; k < AB_MAX_BANDS; ++k) {
+            if (c->evUp[k]) (void)cudaEventDestroy(c->evUp[k]);
+            if (c->evKernel[k]) (void)cudaEventDestroy(c->evKernel[k]);
+        }
+        for (int k = 0; k < AB_RING_SLOTS; ++k)
+            if (c->evRing[k]) (void)cudaEventDestroy(c->evRing[k]);
+        if (c->stream) (void)cudaStreamDestroy(c->stream);
+        if (c->up) (void)cudaStreamDestroy(c->up);
+        if (c->up2) (void)cudaStreamDestroy(c->up2);
+        if (c->down) (void)cudaStreamDestroy(c->down);
+        if (c->arena) (void)cudaFree(c->arena);
+        if (c->ring) (void)cudaFreeHost(c->ring);
     }
-    tls.ready = 1;
-    return AVIF_RESULT_OK;
+    (void)cudaGetLastError(); /* e.g. cudaErrorCudartUnloading while the process is going down */
+    memset(c, 0, sizeof(*c));
+    if (prev >= 0) (void)cudaSetDevice(prev);
 }
 
-/* grow-only device arena; contents are dead between calls */
-static avifResult arenaReserve(size_t bytes)
+/* thread exit: streams, events, device arena and pinned ring of every context of the thread */
+static void threadDestroy(void * p)
 {
-    if (bytes <= tls.arenaCap) return AVIF_RESULT_OK;
-    if (tls.arena) {
-        AB_CUDA(cudaStreamSynchronize(tls.stream));
-        AB_CUDA(cudaStreamSynchronize(tls.down));
-        AB_CUDA(cudaFree(tls.arena));
-        tls.arena = NULL;
-        tls.arenaCap = 0;
-    }
-    const size_t cap = bytes + (bytes >> 3) + (1u << 20);
-    AB_CUDA(cudaMalloc((void **)&tls.arena, cap));
-    tls.arenaCap = cap;
-    return AVIF_RESULT_OK;
+    AbThread * t = (AbThread *)p;
+    if (!t) return;
+    for (int d = 0; d < AB_MAX_DEVICES; ++d) ctxDestroy(&t->ctx[d]);
+    free(t);
+}
+static void makeThreadKey(void) { (void)pthread_key_create(&gThreadKey, threadDestroy); }
+
+static AbThread * threadState(void)
+{
+    if (tlsThread) return tlsThread;
+    AbThread * t = (AbThread *)calloc(1, sizeof(AbThread));
+    if (!t) return NULL;
+    t->assigned = -1;
+    t->explicitDev = -1;
+    (void)pthread_once(&gThreadKeyOnce, makeThreadKey);
+    (void)pthread_setspecific(gThreadKey, t);
+    tlsThread = t;
+    return t;
 }
 
-static int ptrOnDevice(const void * p)
+static int visibleDevices(void)
 {
-    struct cudaPointerAttributes at;
-    if (!p) return 0;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    return n > AB_MAX_DEVICES ? AB_MAX_DEVICES : n;
+}
+
+/* gPolicyLock held */
+static void policyInitLocked(int startAt)
+{
+    if (gPolicy.count) return;
+    const int n = visibleDevices();
+    if (n <= 0) return;
+    const char * e = getenv("AVIF_B200_DEVICES");
+    if (e && *e && strcmp(e, "all") != 0) {
+        int count = 0;
+        const char * q = e;
+        while (*q && count < AB_MAX_DEVICES) {
+            char * end = NULL;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            if (v >= 0 && v < n) gPolicy.list[count++] = (int)v;
+            q = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') break;
+        }
+        if (count) {
+            gPolicy.count = count;
+            gPolicy.fromUser = 1;
+            return;
+        }
+    }
+    for (int k = 0; k < n; ++k) gPolicy.list[k] = (startAt + k) % n;
+    gPolicy.count = n;
+    gPolicy.fromUser = (e && strcmp(e, "all") == 0);
+}
+
+avifResult avifB200SetDevices(const int * devices, int count)
+{
+    const int n = visibleDevices();
+    if (count < 0 || count > AB_MAX_DEVICES || (count > 0 && !devices)) return AVIF_RESULT_INVALID_ARGUMENT;
+    for (int k = 0; k < count; ++k)
+        if (devices[k] < 0 || devices[k] >= n) return AVIF_RESULT_INVALID_ARGUMENT;
+    pthread_mutex_lock(&gPolicyLock);
+    gPolicy.count = 0; /* count == 0: back to the default policy (re-read lazily) */
+    gPolicy.fromUser = 0;
+    gPolicy.next = 0;
+    if (count) {
+        memcpy(gPolicy.list, devices, (size_t)count * sizeof(int));
+        gPolicy.count = count;
+        gPolicy.fromUser = 1;
+    }
+    pthread_mutex_unlock(&gPolicyLock);
+    return AVIF_RESULT_OK;
+}
+
+avifResult avifB200SetDevice(int device)
+{
+    AbThread * t = threadState();
+    if (!t) return AVIF_RESULT_OUT_OF_MEMORY;
+    if (device < 0) {
+        t->explicitDev = -1;
+        return AVIF_RESULT_OK;
+    }
+    if (device >= visibleDevices()) return AVIF_RESULT_INVALID_ARGUMENT;
+    t->explicitDev = device;
+    return AVIF_RESULT_OK;
+}
+
+/* device that the next synchronous host-pointer call of this thread would use (-1: no device / error) */
+int avifB200GetDevice(void)
+{
+    AbThread * t = threadState();
+    if (!t) return -1;
+    if (t->explicitDev >= 0) return t->explicitDev;
+    if (t->assigned < 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return -1;
+        }
+        pthread_mutex_lock(&gPolicyLock);
+        policyInitLocked(cur);
+        if (gPolicy.count) t->assigned = gPolicy.list[gPolicy.next++ % (unsigned)gPolicy.count];
+        pthread_mutex_unlock(&gPolicyLock);
+    }
+    return t->assigned;
+}
+
+static avifResult ctxCreate(AbCtx * c, int device)
+{
+    /* the device is current */
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    int err = (int)cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (!err) err = (int)cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking);
+    if (!err) err = (int)cudaStreamCreateWithFlags(&c->up2, cudaStreamNonBlocking);
+    if (!err) err = (int)cudaStreamCreateWithFlags(&c->down, cudaStreamNonBlocking);
+    for (int k = 0; k < AB_MAX_BANDS && !err; ++k) {
+        err = (int)cudaEventCreateWithFlags(&c->evUp[k], cudaEventDisableTiming);
+        if (!err) err = (int)cudaEventCreateWithFlags(&c->evKernel[k], cudaEventDisableTiming);
+    }
+    for (int k = 0; k < AB_RING_SLOTS && !err; ++k) err = (int)cudaEventCreateWithFlags(&c->evRing[k], cudaEventDisableTiming);
+    if (err) { /* unwind what exists */
+        c->ready = 1;
+        ctxDestroy(c);
+        return cudaToResult(err);
+    }
+    c->ready = 1;
+    return AVIF_RESULT_OK;
+}
+
+/* Scope of one synchronous call: selects the device (see the policy above), makes it current, binds `cx`. */
+static avifResult ctxEnter(AbScope * sc, int pointerDevice)
+{
+    sc->prevDevice = -1;
+    sc->prevCx = cx;
+    if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR; /* no CPU fallback by design */
+    AbThread * t = threadState();
+    if (!t) return AVIF_RESULT_OUT_OF_MEMORY;
+    int device = pointerDevice;
+    if (device < 0) device = avifB200GetDevice();
+    if (device < 0 || device >= AB_MAX_DEVICES) return AVIF_RESULT_UNKNOWN_ERROR;
+    int cur = -1;
+    AB_CUDA(cudaGetDevice(&cur));
+    if (cur != device) {
+        AB_CUDA(cudaSetDevice(device));
+        sc->prevDevice = cur;
+    }
+    AbCtx * c = &t->ctx[device];
+    if (!c->ready) {
+        const avifResult res = ctxCreate(c, device);
+        if (res != AVIF_RESULT_OK) {
+            if (sc->prevDevice >= 0) (void)cudaSetDevice(sc->prevDevice);
+            sc->prevDevice = -1;
+            return res;
+        }
+    }
+    cx = c;
+    return AVIF_RESULT_OK;
+}
+
+/* Leaves the scope.  A failed call first waits for everything it enqueued: copies must not keep running on the caller's
+ * host buffers (or on the arena the thread's next call reuses) after the error has been reported. */
+static avifResult ctxLeave(AbScope * sc, avifResult res)
+{
+    if (cx && res != AVIF_RESULT_OK) {
+        (void)cudaStreamSynchronize(cx->up);
+        (void)cudaStreamSynchronize(cx->up2);
+        (void)cudaStreamSynchronize(cx->stream);
+        (void)cudaStreamSynchronize(cx->down);
+        (void)cudaGetLastError();
+    }
+    cx = sc->prevCx;
+    if (sc->prevDevice >= 0) (void)cudaSetDevice(sc->prevDevice);
+    return res;
+}
+
+/* device ordinal of the first pointer that is device memory, -1 if all are host (or NULL) */
+static int deviceOfPointers(const void * const * ptrs, int n)
+{
+    for (int k = 0; k < n; ++k) {
+        struct cudaPointerAttributes at;
+        if (!ptrs[k]) continue;
+        if (cudaPointerGetAttributes(&at, ptrs[k]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            continue;
+        }
+        if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return at.device;
+    }
+    return -1;
+}
+static int deviceOfImages(const avifImage * image, const avifRGBImage * rgb)
+{
+    const void * p[5] = { NULL, NULL, NULL, NULL, NULL };
+    if (image) {
+        p[0] = image->yuvPlanes[0];
+        p[1] = image->yuvPlanes[1];
+        p[2] = image->yuvPlanes[2];
+        p[3] = image->alphaPlane;
+    }
+    if (rgb) p[4] = rgb->pixels;
+    return deviceOfPointers(p, 5);
+}
+
+/* device selection for the host-synchronous helpers outside this file (plan.h) */
+int abDeviceEnter(const void * const * ptrs, int n, int * prevDevice)
+{
+    *prevDevice = -1;
+    if (!avifB200DeviceAvailable()) return AVIF_RESULT_OK; /* the caller's first CUDA call reports the missing device */
+    int device = deviceOfPointers(ptrs, n);
+    if (device < 0) device = avifB200GetDevice();
+    if (device < 0) return AVIF_RESULT_UNKNOWN_ERROR;
+    int cur = -1;
+    AB_CUDA(cudaGetDevice(&cur));
+    if (cur != device) {
+        AB_CUDA(cudaSetDevice(device));
+        *prevDevice = cur;
+    }
+    return AVIF_RESULT_OK;
+}
+void abDeviceLeave(int prevDevice)
+{
+    if (prevDevice >= 0) (void)cudaSetDevice(prevDevice);
+}
+
+/* grow-only device arena of the current context; contents are dead between calls */
+static avifResult arenaReserve(size_t bytes)
+{
+    if (bytes <= cx->arenaCap) return AVIF_RESULT_OK;
+    if (cx->arena) {
+        AB_CUDA(cudaStreamSynchronize(cx->stream));
+        AB_CUDA(cudaStreamSynchronize(cx->down));
+        AB_CUDA(cudaFree(cx->arena));
+        cx->arena = NULL;
+        cx->arenaCap = 0;
+    }
+    const size_t cap = bytes + (bytes >> 3) + (1u << 20);
+    AB_CUDA(cudaMalloc((void **)&cx->arena, cap));
+    cx->arenaCap = cap;
+    return AVIF_RESULT_OK;
+}
+
+/* cudaMemoryType of a pointer: Unregistered = pageable host memory, Host = pinned / registered, Device, Managed */
+static int ptrMemoryType(const void * p, struct cudaPointerAttributes * out)
+{
+    struct cudaPointerAttributes at;
+    memset(&at, 0, sizeof(at));
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        at.type = cudaMemoryTypeUnregistered;
+    }
+    if (out) *out = at;
+    return (int)at.type;
+}
+static int ptrOnDevice(const void * p)
+{
+    if (!p) return 0;
+    const int t = ptrMemoryType(p, NULL);
+    return t == cudaMemoryTypeDevice || t == cudaMemoryTypeManaged;
 }
 
 static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -348,6 +653,7 @@ typedef struct AbRegion {
     size_t rowUsed;     /* bytes per row the path touches */
     uint32_t rows;
     int onDevice;
+    int pageable;       /* host memory the copy engines cannot reach directly: staged through the context's pinned ring */
     uint8_t * dev;      /* pointer the kernel uses */
     int64_t devRB;
     int present;
@@ -363,23 +669,29 @@ static void regionInit(AbRegion * r, const void * user, int64_t rb, size_t rowUs
     r->userRB = rb;
     r->rowUsed = rowUsed;
     r->rows = rows;
-    r->onDevice = assumeDevice ? 1 : ptrOnDevice(user);
-    if (!r->onDevice && tlsZeroCopy) {
-        struct cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, user) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-            r->user = (uint8_t *)at.devicePointer; /* mapped pinned memory: usable by kernels as is */
-            r->onDevice = 1;
-        } else {
-            (void)cudaGetLastError();
-        }
+    if (assumeDevice) {
+        r->onDevice = 1;
+        return;
+    }
+    struct cudaPointerAttributes at;
+    const int type = ptrMemoryType(user, &at);
+    r->onDevice = (type == cudaMemoryTypeDevice || type == cudaMemoryTypeManaged);
+    r->pageable = (type == cudaMemoryTypeUnregistered);
+    if (!r->onDevice && tlsZeroCopy && type == cudaMemoryTypeHost && at.devicePointer) {
+        r->user = (uint8_t *)at.devicePointer; /* mapped pinned memory: usable by kernels as is */
+        r->onDevice = 1;
     }
 }
+
+/* rows the arena holds: a stride-0 plane (every row aliases row 0, like in the reference's pointer arithmetic) is one row
+ * that the kernels re-read with a zero device stride */
+static uint32_t regionArenaRows(const AbRegion * r) { return (r->userRB == 0 && !r->exactPitch) ? 1u : r->rows; }
 
 static size_t regionArenaBytes(const AbRegion * r)
 {
     if (!r->present || r->onDevice) return 0;
     if (r->exactPitch) return alignUp((size_t)r->userRB * r->rows, 256);
-    return alignUp(r->rowUsed, 256) * r->rows;
+    return alignUp(r->rowUsed, 256) * regionArenaRows(r);
 }
 
 static void regionPlace(AbRegion * r, uint8_t ** cursor)
@@ -391,8 +703,117 @@ static void regionPlace(AbRegion * r, uint8_t ** cursor)
         return;
     }
     r->dev = *cursor;
-    r->devRB = r->exactPitch ? r->userRB : (int64_t)alignUp(r->rowUsed, 256);
+    r->devRB = r->exactPitch ? r->userRB : ((r->userRB == 0) ? 0 : (int64_t)alignUp(r->rowUsed, 256));
     *cursor += regionArenaBytes(r);
+}
+
+/* ---- pageable host memory: pinned ring ---------------------------------------------------------
+ * cudaMemcpy*Async on pageable memory makes the driver stage every byte through its own bounce buffer, one blocking piece
+ * after the other.  Here the calling thread moves rows between the caller's buffer and AB_RING_SLOTS pinned chunks with
+ * memcpy while the copy engine transfers the chunks filled before (uploads) / fills the next ones (downloads), so the host
+ * copy and the DMA overlap and a call costs about one memcpy of its bytes.  AVIF_B200_STAGING=0 disables it (driver path),
+ * AVIF_B200_RING_MB sets the chunk size. */
+#define AB_STAGE_MIN_BYTES ((size_t)256 << 10)
+static int stagingEnabled(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char * e = getenv("AVIF_B200_STAGING");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+static avifResult ringReserve(size_t rowBytes)
+{
+    size_t want = (size_t)2 << 20;
+    const char * e = getenv("AVIF_B200_RING_MB");
+    if (e && atol(e) > 0) want = (size_t)atol(e) << 20;
+    if (want < rowBytes) want = alignUp(rowBytes, 4096); /* a chunk holds whole rows */
+    if (cx->ring && cx->ringSlotBytes >= want) return AVIF_RESULT_OK;
+    if (cx->ring) {
+        for (int k = 0; k < AB_RING_SLOTS; ++k) AB_CUDA(cudaEventSynchronize(cx->evRing[k]));
+        AB_CUDA(cudaFreeHost(cx->ring));
+        cx->ring = NULL;
+        cx->ringSlotBytes = 0;
+    }
+    AB_CUDA(cudaHostAlloc((void **)&cx->ring, want * AB_RING_SLOTS, cudaHostAllocDefault));
+    cx->ringSlotBytes = want;
+    return AVIF_RESULT_OK;
+}
+static int regionStaged(const AbRegion * r, uint32_t rows)
+{
+    return r->pageable && stagingEnabled() && !r->exactPitch && r->userRB != 0 && (size_t)r->rowUsed * rows >= AB_STAGE_MIN_BYTES;
+}
+static unsigned gRingCursor(void)
+{
+    static _Thread_local unsigned cursor = 0;
+    return cursor++;
+}
+
+static avifResult stagedUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
+{
+    const size_t pitch = (size_t)r->devRB; /* the chunk mirrors the arena layout: one 1-D DMA per chunk */
+    avifResult res = ringReserve(pitch);
+    if (res != AVIF_RESULT_OK) return res;
+    const uint32_t perChunk = (uint32_t)(cx->ringSlotBytes / pitch);
+    for (uint32_t row = row0; row < row1; row += perChunk) {
+        const uint32_t n = (row1 - row < perChunk) ? row1 - row : perChunk;
+        const unsigned slot = gRingCursor() % AB_RING_SLOTS;
+        uint8_t * chunk = cx->ring + (size_t)slot * cx->ringSlotBytes;
+        AB_CUDA(cudaEventSynchronize(cx->evRing[slot])); /* the DMA that last used this chunk */
+        const uint8_t * src = r->user + (int64_t)row * r->userRB;
+        if ((size_t)r->userRB == pitch) {
+            memcpy(chunk, src, pitch * (n - 1) + r->rowUsed);
+        } else {
+            for (uint32_t k = 0; k < n; ++k) memcpy(chunk + (size_t)k * pitch, src + (int64_t)k * r->userRB, r->rowUsed);
+        }
+        AB_CUDA(cudaMemcpyAsync(r->dev + (size_t)row * pitch, chunk, pitch * (n - 1) + r->rowUsed, cudaMemcpyHostToDevice, st));
+        AB_CUDA(cudaEventRecord(cx->evRing[slot], st));
+    }
+    return AVIF_RESULT_OK;
+}
+
+/* returns when the rows are in the caller's buffer */
+static avifResult stagedDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
+{
+    const size_t pitch = (size_t)r->devRB;
+    avifResult res = ringReserve(pitch);
+    if (res != AVIF_RESULT_OK) return res;
+    const uint32_t perChunk = (uint32_t)(cx->ringSlotBytes / pitch);
+    struct { uint32_t row, n; unsigned slot; } pending[AB_RING_SLOTS];
+    int head = 0, count = 0;
+    uint32_t row = row0;
+    while (row < row1 || count) {
+        if (row < row1 && count < AB_RING_SLOTS) { /* keep the copy engine AB_RING_SLOTS chunks ahead of the host copy */
+            const uint32_t n = (row1 - row < perChunk) ? row1 - row : perChunk;
+            const unsigned slot = gRingCursor() % AB_RING_SLOTS;
+            /* slots are handed out round-robin and drained in order: `slot` is free unless an upload of this call still uses it */
+            AB_CUDA(cudaEventSynchronize(cx->evRing[slot]));
+            AB_CUDA(cudaMemcpyAsync(cx->ring + (size_t)slot * cx->ringSlotBytes, r->dev + (size_t)row * pitch, pitch * (n - 1) + r->rowUsed,
+                                    cudaMemcpyDeviceToHost, st));
+            AB_CUDA(cudaEventRecord(cx->evRing[slot], st));
+            const int tail = (head + count) % AB_RING_SLOTS;
+            pending[tail].row = row;
+            pending[tail].n = n;
+            pending[tail].slot = slot;
+            ++count;
+            row += n;
+            continue;
+        }
+        const uint32_t prow = pending[head].row, pn = pending[head].n;
+        const unsigned slot = pending[head].slot;
+        head = (head + 1) % AB_RING_SLOTS;
+        --count;
+        AB_CUDA(cudaEventSynchronize(cx->evRing[slot]));
+        const uint8_t * chunk = cx->ring + (size_t)slot * cx->ringSlotBytes;
+        uint8_t * dst = r->user + (int64_t)prow * r->userRB;
+        if ((size_t)r->userRB == pitch) {
+            memcpy(dst, chunk, pitch * (pn - 1) + r->rowUsed);
+        } else {
+            for (uint32_t k = 0; k < pn; ++k) memcpy(dst + (int64_t)k * r->userRB, chunk + (size_t)k * pitch, r->rowUsed);
+        }
+    }
+    return AVIF_RESULT_OK;
 }
 
 static int regionUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
@@ -401,6 +822,7 @@ static int regionUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaSt
     if (r->userRB == 0 || r->rowUsed == 0) { /* stride-0 plane (every row aliases row 0): upload the single row */
         return (int)cudaMemcpyAsync(r->dev, r->user, r->rowUsed, cudaMemcpyHostToDevice, st);
     }
+    if (regionStaged(r, row1 - row0)) return (stagedUpload(r, row0, row1, st) == AVIF_RESULT_OK) ? cudaSuccess : cudaErrorUnknown;
     return (int)cudaMemcpy2DAsync(r->dev + (int64_t)row0 * r->devRB, (size_t)r->devRB, r->user + (int64_t)row0 * r->userRB, (size_t)r->userRB,
                                   r->rowUsed, row1 - row0, cudaMemcpyHostToDevice, st);
 }
@@ -412,6 +834,7 @@ static int regionDownload(const AbRegion * r, uint32_t row0, uint32_t row1, cuda
         return (int)cudaMemcpyAsync(r->user + (int64_t)row0 * r->userRB, r->dev + (int64_t)row0 * r->devRB, (size_t)r->userRB * (row1 - row0),
                                     cudaMemcpyDeviceToHost, st);
     }
+    if (regionStaged(r, row1 - row0)) return (stagedDownload(r, row0, row1, st) == AVIF_RESULT_OK) ? cudaSuccess : cudaErrorUnknown;
     return (int)cudaMemcpy2DAsync(r->user + (int64_t)row0 * r->userRB, (size_t)r->userRB, r->dev + (int64_t)row0 * r->devRB, (size_t)r->devRB,
                                   r->rowUsed, row1 - row0, cudaMemcpyDeviceToHost, st);
 }
@@ -428,7 +851,7 @@ static cudaStream_t upStream(int band)
         const char * e = getenv("AVIF_B200_UP_STREAMS");
         nUp = (e && atoi(e) == 2) ? 2 : 1;
     }
-    return (nUp == 2 && (band & 1)) ? tls.up2 : tls.up;
+    return (nUp == 2 && (band & 1)) ? cx->up2 : cx->up;
 }
 
 /* synchronous host-pointer conversions currently inside the library, over all threads */
@@ -692,7 +1115,7 @@ static float f16Multiplier(uint32_t depth)
 }
 
 /* src/alpha.c:151-336 / :338-535 */
-static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * userStream, int async)
+static avifResult premultiplyBody(avifRGBImage * rgb, int unmultiply, void * userStream, int async)
 {
     if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_REFORMAT_FAILED;
     if (!avifRGBFormatHasAlpha(rgb->format)) return unmultiply ? AVIF_RESULT_REFORMAT_FAILED : AVIF_RESULT_INVALID_ARGUMENT;
@@ -700,9 +1123,8 @@ static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * u
     memset(&job, 0, sizeof(job));
     if (!premulLayout(rgb->format, &job)) return AVIF_RESULT_NOT_IMPLEMENTED;
     if (rgb->depth < 8 || rgb->depth > 16) return AVIF_RESULT_REFORMAT_FAILED; /* the reference asserts */
-    avifResult res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
-    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+    avifResult res;
+    cudaStream_t st = async ? (cudaStream_t)userStream : cx->stream;
 
     AbRegion px;
     regionInit(&px, rgb->pixels, rgb->rowBytes, (size_t)rgb->width * avifRGBImagePixelSize(rgb), rgb->height, async);
@@ -710,7 +1132,7 @@ static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * u
         res = arenaReserve(regionArenaBytes(&px));
         if (res != AVIF_RESULT_OK) return res;
     }
-    uint8_t * cursor = tls.arena;
+    uint8_t * cursor = async ? NULL : cx->arena;
     regionPlace(&px, &cursor);
     AB_CUDA(regionUpload(&px, 0, px.rows, st));
     job.pixels = px.dev;
@@ -727,6 +1149,17 @@ static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * u
     return AVIF_RESULT_OK;
 }
 
+static avifResult premultiplyCommon(avifRGBImage * rgb, int unmultiply, void * userStream, int async)
+{
+    if (async) return premultiplyBody(rgb, unmultiply, userStream, 1);
+    /* argument errors are reported without needing a device, like the reference */
+    if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_REFORMAT_FAILED;
+    if (!avifRGBFormatHasAlpha(rgb->format)) return unmultiply ? AVIF_RESULT_REFORMAT_FAILED : AVIF_RESULT_INVALID_ARGUMENT;
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, deviceOfImages(NULL, rgb));
+    if (res != AVIF_RESULT_OK) return res;
+    return ctxLeave(&sc, premultiplyBody(rgb, unmultiply, NULL, 0));
+}
 avifResult avifRGBImagePremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 0, NULL, 0); }
 avifResult avifRGBImageUnpremultiplyAlpha(avifRGBImage * rgb) { return premultiplyCommon(rgb, 1, NULL, 0); }
 avifResult avifB200RGBImagePremultiplyAlphaHost(avifRGBImage * rgb) { return premultiplyCommon(rgb, 0, NULL, 0); }
@@ -735,20 +1168,19 @@ avifResult avifB200RGBImagePremultiplyAlphaAsync(avifRGBImage * rgb, void * stre
 avifResult avifB200RGBImageUnpremultiplyAlphaAsync(avifRGBImage * rgb, void * stream) { return premultiplyCommon(rgb, 1, stream, 1); }
 
 /* src/reformat.c:1419-1443 as a pass of its own (the conversions fuse it; the internal seam needs it separately) */
-static avifResult toF16Common(avifRGBImage * rgb)
+static avifResult toF16Body(avifRGBImage * rgb)
 {
     if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
     if (rgb->depth <= 8 || rgb->depth > 16) return AVIF_RESULT_INVALID_ARGUMENT; /* half floats live in 16-bit channels */
-    avifResult res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
-    cudaStream_t st = tls.stream;
+    avifResult res;
+    cudaStream_t st = cx->stream;
     AbRgbPassJob job;
     memset(&job, 0, sizeof(job));
     AbRegion px;
     regionInit(&px, rgb->pixels, rgb->rowBytes, (size_t)rgb->width * avifRGBImagePixelSize(rgb), rgb->height, 0);
     res = arenaReserve(regionArenaBytes(&px));
     if (res != AVIF_RESULT_OK) return res;
-    uint8_t * cursor = tls.arena;
+    uint8_t * cursor = cx->arena;
     regionPlace(&px, &cursor);
     AB_CUDA(regionUpload(&px, 0, px.rows, st));
     job.pixels = px.dev;
@@ -765,23 +1197,31 @@ static avifResult toF16Common(avifRGBImage * rgb)
     return AVIF_RESULT_OK;
 }
 
+static avifResult toF16Common(avifRGBImage * rgb)
+{
+    if (!rgb->pixels || !rgb->rowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, deviceOfImages(NULL, rgb));
+    if (res != AVIF_RESULT_OK) return res;
+    return ctxLeave(&sc, toF16Body(rgb));
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* alpha plane <-> channel (src/alpha.c:9-149); void like the reference: failures cannot be reported */
 
-static void alphaCommon(const avifAlphaParams * p, int fill)
+static avifResult alphaBody(const avifAlphaParams * p, int fill)
 {
-    if (ctxInit() != AVIF_RESULT_OK || p->width == 0 || p->height == 0) return;
-    cudaStream_t st = tls.stream;
+    cudaStream_t st = cx->stream;
     const uint32_t dcb = (p->dstDepth > 8) ? 2 : 1, scb = (p->srcDepth > 8) ? 2 : 1;
     AbRegion src, dst;
     regionInit(&dst, p->dstPlane, p->dstRowBytes, (size_t)p->dstOffsetBytes + (size_t)(p->width - 1) * p->dstPixelBytes + dcb, p->height, 0);
     regionInit(&src, fill ? NULL : p->srcPlane, p->srcRowBytes, (size_t)p->srcOffsetBytes + (size_t)(p->width - 1) * p->srcPixelBytes + scb, p->height, 0);
-    if (arenaReserve(regionArenaBytes(&src) + regionArenaBytes(&dst)) != AVIF_RESULT_OK) return;
-    uint8_t * cursor = tls.arena;
+    if (arenaReserve(regionArenaBytes(&src) + regionArenaBytes(&dst)) != AVIF_RESULT_OK) return AVIF_RESULT_OUT_OF_MEMORY;
+    uint8_t * cursor = cx->arena;
     regionPlace(&src, &cursor);
     regionPlace(&dst, &cursor);
-    if (regionUpload(&src, 0, src.rows, st) != cudaSuccess) return;
-    if (regionUpload(&dst, 0, dst.rows, st) != cudaSuccess) return; /* untouched channels must survive the round trip */
+    AB_CUDA(regionUpload(&src, 0, src.rows, st));
+    AB_CUDA(regionUpload(&dst, 0, dst.rows, st)); /* untouched channels must survive the round trip */
     AbAlphaJob job;
     memset(&job, 0, sizeof(job));
     job.src = fill ? NULL : src.dev;
@@ -796,11 +1236,22 @@ static void alphaCommon(const avifAlphaParams * p, int fill)
     job.srcPix = p->srcPixelBytes;
     job.dstOff = p->dstOffsetBytes;
     job.dstPix = p->dstPixelBytes;
-    if (abLaunchAlpha(&job, st) != cudaSuccess) return;
+    AB_CUDA(abLaunchAlpha(&job, st));
     tls.lastKernel = fill ? "alpha_fill" : "alpha_reformat";
-    if (regionDownload(&dst, 0, dst.rows, st) != cudaSuccess) return;
-    (void)cudaStreamSynchronize(st);
+    AB_CUDA(regionDownload(&dst, 0, dst.rows, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    return AVIF_RESULT_OK;
 }
+
+static void alphaCommon(const avifAlphaParams * p, int fill)
+{
+    if (p->width == 0 || p->height == 0) return;
+    const void * ptrs[2] = { p->dstPlane, fill ? NULL : p->srcPlane };
+    AbScope sc;
+    if (ctxEnter(&sc, deviceOfPointers(ptrs, 2)) != AVIF_RESULT_OK) return;
+    (void)ctxLeave(&sc, alphaBody(p, fill));
+}
+
 
 void avifFillAlpha(const avifAlphaParams * params) { alphaCommon(params, 1); }
 void avifReformatAlpha(const avifAlphaParams * params) { alphaCommon(params, 0); }
@@ -944,18 +1395,13 @@ static avifResult y2rBuildJob(const avifImage * image, const avifRGBImage * rgb,
     return AVIF_RESULT_OK;
 }
 
-static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
+static avifResult yuvToRgbBody(const avifImage * image, avifRGBImage * rgb, void * userStream, int async, AbY2RJob job, const AbY2RPlan * planIn)
 {
-    AbY2RJob job;
-    AbY2RPlan plan;
-    avifResult res = y2rBuildJob(image, rgb, &job, &plan);
-    if (res != AVIF_RESULT_OK) return res;
+    const AbY2RPlan plan = *planIn;
+    avifResult res;
     const AbState s = plan.s;
     const int hasChroma = plan.hasChroma, rgbHasAlpha = plan.rgbHasAlpha, reformatAlpha = plan.reformatAlpha;
-
-    res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
-    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+    cudaStream_t st = async ? (cudaStream_t)userStream : cx->stream;
 
     /* the alpha channel / post-passes iterate over rgb->width x rgb->height, the colour loop over the image's
      * (src/reformat.c:1467-1468 vs :686,:703).  When they agree (always, for sane callers) everything is one kernel. */
@@ -979,7 +1425,7 @@ static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void
         res = arenaReserve(regionArenaBytes(&ry) + regionArenaBytes(&ru) + regionArenaBytes(&rv) + regionArenaBytes(&ra) + regionArenaBytes(&rrgb));
         if (res != AVIF_RESULT_OK) return res;
     }
-    uint8_t * cursor = tls.arena;
+    uint8_t * cursor = async ? NULL : cx->arena;
     regionPlace(&ry, &cursor);
     regionPlace(&ru, &cursor);
     regionPlace(&rv, &cursor);
@@ -990,8 +1436,11 @@ static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void
     const int anyHost = !ry.onDevice || (ru.present && !ru.onDevice) || (rv.present && !rv.onDevice) || (ra.present && !ra.onDevice) || !rrgb.onDevice;
     const size_t frameBytes = (size_t)ry.rowUsed * ry.rows + (ru.present ? 2 * (size_t)ru.rowUsed * ru.rows : 0) +
                               (ra.present ? (size_t)ra.rowUsed * ra.rows : 0) + (size_t)rrgb.rowUsed * rrgb.rows;
-    const int pipelined = !async && anyHost && sameDims && !keepsDstBytes && frameBytes >= ((size_t)8 << 20) &&
-                          (!ra.present || image->alphaRowBytes != 0);
+    /* pageable buffers are staged chunk by chunk by this thread (stagedUpload / stagedDownload): the host copy is the
+     * critical path there and already overlaps the DMA, so bands would only add launches */
+    const int anyStaged = regionStaged(&ry, ry.rows) || regionStaged(&ra, ra.rows) || regionStaged(&rrgb, rrgb.rows);
+    const int pipelined = !async && anyHost && !anyStaged && sameDims && !keepsDstBytes && frameBytes >= ((size_t)8 << 20) &&
+                          (!ra.present || image->alphaRowBytes != 0) && image->yuvRowBytes[0] != 0;
 
     job.y = ry.dev;
     job.yRB = ry.devRB;
@@ -1026,20 +1475,20 @@ static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void
             AB_CUDA(regionUpload(&ru, c0, c1, us));
             AB_CUDA(regionUpload(&rv, c0, c1, us));
             AB_CUDA(regionUpload(&ra, r0, r1, us));
-            AB_CUDA(cudaEventRecord(tls.evUp[b], us));
+            AB_CUDA(cudaEventRecord(cx->evUp[b], us));
         }
         for (int b = 0; b < nb; ++b) {
             const int need = (b + lookAhead < nb) ? b + lookAhead : nb - 1;
-            AB_CUDA(cudaStreamWaitEvent(st, tls.evUp[need], 0));
+            AB_CUDA(cudaStreamWaitEvent(st, cx->evUp[need], 0));
             job.rowBegin = bands[b];
             job.rowEnd = bands[b + 1];
             AB_CUDA(abLaunchY2R(&job, st, tls.policy, &kname));
-            AB_CUDA(cudaEventRecord(tls.evKernel[b], st));
-            AB_CUDA(cudaStreamWaitEvent(tls.down, tls.evKernel[b], 0));
-            AB_CUDA(regionDownload(&rrgb, bands[b], bands[b + 1], tls.down));
+            AB_CUDA(cudaEventRecord(cx->evKernel[b], st));
+            AB_CUDA(cudaStreamWaitEvent(cx->down, cx->evKernel[b], 0));
+            AB_CUDA(regionDownload(&rrgb, bands[b], bands[b + 1], cx->down));
         }
         tls.lastKernel = kname;
-        AB_CUDA(cudaStreamSynchronize(tls.down));
+        AB_CUDA(cudaStreamSynchronize(cx->down));
         return AVIF_RESULT_OK;
     }
 
@@ -1105,11 +1554,18 @@ static avifResult yuvToRgbImpl(const avifImage * image, avifRGBImage * rgb, void
 
 static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, void * userStream, int async)
 {
-    if (async) return yuvToRgbImpl(image, rgb, userStream, 1);
+    AbY2RJob job;
+    AbY2RPlan plan;
+    avifResult res = y2rBuildJob(image, rgb, &job, &plan); /* validation and constants: no device involved */
+    if (res != AVIF_RESULT_OK) return res;
+    if (async) return yuvToRgbBody(image, rgb, userStream, 1, job, &plan);
+    AbScope sc;
+    res = ctxEnter(&sc, deviceOfImages(image, rgb));
+    if (res != AVIF_RESULT_OK) return res;
     __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
-    const avifResult res = yuvToRgbImpl(image, rgb, NULL, 0);
+    res = yuvToRgbBody(image, rgb, NULL, 0, job, &plan);
     __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
-    return res;
+    return ctxLeave(&sc, res);
 }
 avifResult avifImageYUVToRGB(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
 avifResult avifB200ImageYUVToRGBHost(const avifImage * image, avifRGBImage * rgb) { return yuvToRgbCommon(image, rgb, NULL, 0); }
@@ -1133,7 +1589,7 @@ avifResult avifB200HookRGBImageToF16(avifRGBImage * rgb) { return toF16Common(rg
 /* RGB -> YUV                                                                                  */
 
 /* src/avif.c:431-489: missing planes are malloc'ed and owned by the image; existing ones are kept */
-static avifResult allocatePlanes(avifImage * image, int withAlpha)
+static avifResult allocatePlanes(avifImage * image, int withAlpha, int validateOnly)
 {
     if (image->width == 0 || image->height == 0 || image->depth == 0 || image->depth > 16) return AVIF_RESULT_INVALID_ARGUMENT;
     const uint32_t cs = (image->depth > 8) ? 2 : 1;
@@ -1141,6 +1597,7 @@ static avifResult allocatePlanes(avifImage * image, int withAlpha)
     const uint32_t fullRowBytes = cs * image->width;
     if (image->height > PTRDIFF_MAX / fullRowBytes) return AVIF_RESULT_INVALID_ARGUMENT;
     const size_t fullSize = (size_t)fullRowBytes * image->height;
+    if (validateOnly) return AVIF_RESULT_OK; /* device-resident planes stay the caller's: no allocation, ownership flags untouched */
     if (image->yuvFormat != AVIF_PIXEL_FORMAT_NONE) {
         avifPixelFormatInfo fi;
         avifGetPixelFormatInfo(image->yuvFormat, &fi);
@@ -1196,7 +1653,11 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
          * meaningful when the call may stage through the host. */
         if (async || ptrOnDevice(rgb->pixels)) return AVIF_RESULT_INVALID_ARGUMENT;
     }
-    avifResult res = allocatePlanes(image, wantAlphaPlane);
+    /* The reference (src/avif.c:431-489) marks the image as owner of its planes whenever it passes through here, which is
+     * only ever true of host memory it can free().  Planes that live in device memory (stream-ordered entry points, or the
+     * synchronous ones called with resident planes) belong to the caller: imageOwns* stay as they are. */
+    const int residentPlanes = async || (!planesMissing && ptrOnDevice(image->yuvPlanes[0]));
+    avifResult res = allocatePlanes(image, wantAlphaPlane, residentPlanes);
     if (res != AVIF_RESULT_OK) return res;
 
     int alphaMode = 0;
@@ -1267,18 +1728,13 @@ static avifResult r2yBuildJob(avifImage * image, const avifRGBImage * rgb, int a
     return AVIF_RESULT_OK;
 }
 
-static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
+static avifResult rgbToYuvBody(avifImage * image, const avifRGBImage * rgb, void * userStream, int async, AbR2YJob job, const AbR2YPlan * planIn)
 {
-    AbR2YJob job;
-    AbR2YPlan plan;
-    avifResult res = r2yBuildJob(image, rgb, async, &job, &plan);
-    if (res != AVIF_RESULT_OK) return res;
+    const AbR2YPlan plan = *planIn;
+    avifResult res;
     const AbState s = plan.s;
     const int monochrome = plan.monochrome, isGray = plan.isGray, writeAlphaPlane = plan.writeAlphaPlane;
-
-    res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
-    cudaStream_t st = async ? (cudaStream_t)userStream : tls.stream;
+    cudaStream_t st = async ? (cudaStream_t)userStream : cx->stream;
 
     const uint32_t cw = (uint32_t)(((uint64_t)image->width + s.shiftX) >> s.shiftX);
     const uint32_t ch = (uint32_t)(((uint64_t)image->height + s.shiftY) >> s.shiftY);
@@ -1301,7 +1757,7 @@ static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void
         res = arenaReserve(regionArenaBytes(&rrgb) + regionArenaBytes(&ry) + regionArenaBytes(&ru) + regionArenaBytes(&rv) + regionArenaBytes(&ra));
         if (res != AVIF_RESULT_OK) return res;
     }
-    uint8_t * cursor = tls.arena;
+    uint8_t * cursor = async ? NULL : cx->arena;
     regionPlace(&rrgb, &cursor);
     regionPlace(&ry, &cursor);
     regionPlace(&ru, &cursor);
@@ -1335,7 +1791,8 @@ static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void
     const int anyHost = !rrgb.onDevice || !ry.onDevice || (ru.present && !ru.onDevice) || (rv.present && !rv.onDevice) || (ra.present && !ra.onDevice);
     const size_t frameBytes = (size_t)rrgb.rowUsed * rrgb.rows + (size_t)ry.rowUsed * ry.rows + (ru.present ? 2 * (size_t)ru.rowUsed * ru.rows : 0) +
                               (ra.present ? (size_t)ra.rowUsed * ra.rows : 0);
-    if (!async && anyHost && !grayChromaFill && frameBytes >= ((size_t)8 << 20)) {
+    const int anyStaged = regionStaged(&rrgb, rrgb.rows) || regionStaged(&ry, ry.rows) || regionStaged(&ra, ra.rows);
+    if (!async && anyHost && !anyStaged && !grayChromaFill && frameBytes >= ((size_t)8 << 20) && rgb->rowBytes != 0) {
         /* band pipeline (see planBands): pixels up, kernel, planes down, on three streams */
         uint32_t bands[AB_MAX_BANDS + 1];
         const int nb = planBands(image->height, frameBytes, bands);
@@ -1343,24 +1800,24 @@ static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void
         for (int b = 0; b < nb; ++b) {
             cudaStream_t us = upStream(b);
             AB_CUDA(regionUpload(&rrgb, bands[b], bands[b + 1], us));
-            AB_CUDA(cudaEventRecord(tls.evUp[b], us));
+            AB_CUDA(cudaEventRecord(cx->evUp[b], us));
         }
         for (int b = 0; b < nb; ++b) {
             const uint32_t r0 = bands[b], r1 = bands[b + 1];
             const uint32_t c0 = r0 >> job.shiftY, c1 = (uint32_t)(((uint64_t)r1 + job.shiftY) >> job.shiftY);
-            AB_CUDA(cudaStreamWaitEvent(st, tls.evUp[b], 0));
+            AB_CUDA(cudaStreamWaitEvent(st, cx->evUp[b], 0));
             job.rowBegin = r0;
             job.rowEnd = r1;
             AB_CUDA(abLaunchR2Y(&job, st, tls.policy, &pname));
-            AB_CUDA(cudaEventRecord(tls.evKernel[b], st));
-            AB_CUDA(cudaStreamWaitEvent(tls.down, tls.evKernel[b], 0));
-            AB_CUDA(regionDownload(&ry, r0, r1, tls.down));
-            AB_CUDA(regionDownload(&ru, c0, c1, tls.down));
-            AB_CUDA(regionDownload(&rv, c0, c1, tls.down));
-            AB_CUDA(regionDownload(&ra, r0, r1, tls.down));
+            AB_CUDA(cudaEventRecord(cx->evKernel[b], st));
+            AB_CUDA(cudaStreamWaitEvent(cx->down, cx->evKernel[b], 0));
+            AB_CUDA(regionDownload(&ry, r0, r1, cx->down));
+            AB_CUDA(regionDownload(&ru, c0, c1, cx->down));
+            AB_CUDA(regionDownload(&rv, c0, c1, cx->down));
+            AB_CUDA(regionDownload(&ra, r0, r1, cx->down));
         }
         tls.lastKernel = pname;
-        AB_CUDA(cudaStreamSynchronize(tls.down));
+        AB_CUDA(cudaStreamSynchronize(cx->down));
         return AVIF_RESULT_OK;
     }
 
@@ -1390,11 +1847,18 @@ static avifResult rgbToYuvImpl(avifImage * image, const avifRGBImage * rgb, void
 
 static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, void * userStream, int async)
 {
-    if (async) return rgbToYuvImpl(image, rgb, userStream, 1);
+    AbR2YJob job;
+    AbR2YPlan plan;
+    avifResult res = r2yBuildJob(image, rgb, async, &job, &plan); /* validation, plane allocation, constants: no device involved */
+    if (res != AVIF_RESULT_OK) return res;
+    if (async) return rgbToYuvBody(image, rgb, userStream, 1, job, &plan);
+    AbScope sc;
+    res = ctxEnter(&sc, deviceOfImages(image, rgb));
+    if (res != AVIF_RESULT_OK) return res;
     __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
-    const avifResult res = rgbToYuvImpl(image, rgb, NULL, 0);
+    res = rgbToYuvBody(image, rgb, NULL, 0, job, &plan);
     __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
-    return res;
+    return ctxLeave(&sc, res);
 }
 avifResult avifB200HookImageRGBToYUV(avifImage * image, const avifRGBImage * rgb)
 {
@@ -1413,18 +1877,16 @@ avifResult avifB200ImageRGBToYUVAsync(avifImage * image, const avifRGBImage * rg
 /* "next" rows: alpha range expansion and grid plane staging                    */
 
 /* src/read.c:6724-6764 */
-avifResult avifB200ImageLimitedToFullAlpha(avifImage * image)
+static avifResult limitedToFullAlphaBody(avifImage * image)
 {
-    if (!image->alphaPlane) return AVIF_RESULT_OK;
-    avifResult res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
-    cudaStream_t st = tls.stream;
+    avifResult res;
+    cudaStream_t st = cx->stream;
     const uint32_t cb = (image->depth > 8) ? 2 : 1;
     AbRegion ra;
     regionInit(&ra, image->alphaPlane, image->alphaRowBytes, (size_t)image->width * cb, image->height, 0);
     res = arenaReserve(regionArenaBytes(&ra));
     if (res != AVIF_RESULT_OK) return res;
-    uint8_t * cursor = tls.arena;
+    uint8_t * cursor = cx->arena;
     regionPlace(&ra, &cursor);
     AB_CUDA(regionUpload(&ra, 0, ra.rows, st));
     AB_CUDA(abLaunchLimitedToFull(ra.dev, ra.devRB, image->width, image->height, image->depth, st));
@@ -1432,6 +1894,16 @@ avifResult avifB200ImageLimitedToFullAlpha(avifImage * image)
     AB_CUDA(regionDownload(&ra, 0, ra.rows, st));
     AB_CUDA(cudaStreamSynchronize(st));
     return AVIF_RESULT_OK;
+}
+
+avifResult avifB200ImageLimitedToFullAlpha(avifImage * image)
+{
+    if (!image->alphaPlane) return AVIF_RESULT_OK;
+    const void * ptrs[1] = { image->alphaPlane };
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, deviceOfPointers(ptrs, 1));
+    if (res != AVIF_RESULT_OK) return res;
+    return ctxLeave(&sc, limitedToFullAlphaBody(image));
 }
 
 static void planeGeometry(const avifImage * im, int plane, uint32_t * w, uint32_t * h)
@@ -1453,8 +1925,6 @@ static void planeGeometry(const avifImage * im, int plane, uint32_t * w, uint32_
 avifResult avifB200ImageCopySamplesAsync(avifImage * dst, const avifImage * src, avifPlanesFlags planes, void * stream)
 {
     if (dst->depth != src->depth || dst->yuvFormat != src->yuvFormat) return AVIF_RESULT_INVALID_ARGUMENT;
-    avifResult res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
     const size_t bps = (src->depth > 8) ? 2 : 1;
     for (int c = AVIF_CHAN_Y; c <= AVIF_CHAN_A; ++c) {
         const int isAlpha = (c == AVIF_CHAN_A);
@@ -1478,8 +1948,6 @@ avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, 
     if (dst->depth != src->depth || dst->yuvFormat != src->yuvFormat || dst->width < src->width || dst->height < src->height) {
         return AVIF_RESULT_INVALID_ARGUMENT;
     }
-    avifResult res = ctxInit();
-    if (res != AVIF_RESULT_OK) return res;
     const uint32_t bps = (src->depth > 8) ? 2 : 1;
     for (int c = AVIF_CHAN_Y; c <= AVIF_CHAN_A; ++c) {
         const int isAlpha = (c == AVIF_CHAN_A);
@@ -1535,7 +2003,7 @@ avifResult avifB200ImageYUVToRGBBatchAsync(const avifImage * const * images, avi
         if (job->a) bits |= (uintptr_t)job->a | (uintptr_t)job->aRB;
         job->pairAligned = (uint8_t)((bits & m) == 0);
     }
-    if (res == AVIF_RESULT_OK) res = ctxInit();
+    if (res == AVIF_RESULT_OK && !avifB200DeviceAvailable()) res = AVIF_RESULT_UNKNOWN_ERROR;
     if (res == AVIF_RESULT_OK) {
         if (fusable) {
             const char * kname = "";
@@ -1586,7 +2054,7 @@ avifResult avifB200ImageRGBToYUVBatchAsync(avifImage * const * images, const avi
         if (job->a) bits |= (uintptr_t)job->a | (uintptr_t)job->aRB;
         job->dstPairAligned = (uint8_t)((bits & m) == 0);
     }
-    if (res == AVIF_RESULT_OK) res = ctxInit();
+    if (res == AVIF_RESULT_OK && !avifB200DeviceAvailable()) res = AVIF_RESULT_UNKNOWN_ERROR;
     if (res == AVIF_RESULT_OK) {
         if (fusable) {
             const char * kname = "";

@@ -688,15 +688,18 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
         F.groups = (F.tiles + kWarps - 1) / kWarps;
         groups += F.groups;
     }
-    static int resident = 0; /* blocks that fit on the whole device at once (per instantiation) */
+    /* blocks that fit on the whole device at once: per instantiation and per device (a process may drive several GPUs) */
+    static int residentOf[16] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int resident = (dev >= 0 && dev < 16) ? residentOf[dev] : 0;
     if (!resident) {
-        int dev = 0, sms = 0, perSm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+        if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
-    /* few groups per resident block -> one group per block (balance beats prefetch); many -> persistent */
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, wanted);
     y2r_fast_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
