@@ -42,7 +42,8 @@ def parse_args():
                     help="host threads of the host-buffer leg, each converting its own frames through the synchronous C-ABI "
                          "(the reference arm uses every host core; independent calls from different threads are legal, avif.h:1012)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE configs (kernel-only) into 'extras'")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration legs (NS, C3, C5, C1, C4 canvas, C5 batch)")
+    ap.add_argument("--extras", action="store_true", help="also time the rows beyond the reformat path (tone mapping, scaling) into 'extras'")
     return ap.parse_args()
 
 
@@ -112,12 +113,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # synthetic frames (SURVEY.md Appendix D distribution: uniform codes), generated with torch on the target memory
 
-
-def c2_specs(abi):
-    img = dict(width=W, height=H, depth=DEPTH, yuv_format=abi.AVIF_PIXEL_FORMAT_YUV444, yuv_range=abi.AVIF_RANGE_FULL,
-               mc=abi.MC_BT709, alpha=True, alpha_premultiplied=False)
-    rgb = dict(width=W, height=H, depth=DEPTH, fmt=abi.AVIF_RGB_FORMAT_RGBA, alpha_premultiplied=True)
-    return img, rgb
+WORKLOAD = ("C2 round trip: avifImageYUVToRGB + avifImageRGBToYUV, 3840x2160 YUV444 10-bit BT.709 full + alpha, RGBA10 premultiplied")
+METRIC = "Mpixels/s YUV<->RGB (C2 round trip 3840x2160 4:4:4 10-bit + alpha premultiply)"
+CONFIG = {"workload": WORKLOAD, "pixel_count": "each direction counts W*H", "sharding": "frames across ranks, no collective",
+          "l2": "inputs larger than L2: every step converts distinct frames, 265 MB each"}
 
 
 def fill_uniform(img, seed):
@@ -127,15 +126,33 @@ def fill_uniform(img, seed):
     mask = (1 << img.c.depth) - 1
     for p in img.present_planes():
         b = img.bufs[p]
-        n16 = b.nbytes // 2
         if b.device is None:
             rs = np.random.RandomState(seed * 7 + p)
-            b.flat[b.offset:b.offset + b.nbytes].view(np.uint16)[:] = rs.randint(0, mask + 1, size=n16, dtype=np.uint16)
+            if img.bps == 2:
+                b.flat[b.offset:b.offset + b.nbytes].view(np.uint16)[:] = rs.randint(0, mask + 1, size=b.nbytes // 2, dtype=np.uint16)
+            else:
+                b.flat[b.offset:b.offset + b.nbytes] = rs.randint(0, mask + 1, size=b.nbytes, dtype=np.uint8)
         else:
             g = torch.Generator(device=b.device)
             g.manual_seed(seed * 7 + p)
-            v = torch.randint(0, mask + 1, (n16,), generator=g, device=b.device, dtype=torch.int32).to(torch.int16)
-            b._t[b.offset:b.offset + b.nbytes].view(torch.int16).copy_(v)
+            if img.bps == 2:
+                v = torch.randint(0, mask + 1, (b.nbytes // 2,), generator=g, device=b.device, dtype=torch.int32).to(torch.int16)
+                b._t[b.offset:b.offset + b.nbytes].view(torch.int16).copy_(v)
+            else:
+                v = torch.randint(0, mask + 1, (b.nbytes,), generator=g, device=b.device, dtype=torch.int32).to(torch.uint8)
+                b._t[b.offset:b.offset + b.nbytes].copy_(v)
+
+
+def fill_uniform_rgb(rgb, seed):
+    import torch
+    b = rgb.buf
+    g = torch.Generator(device=b.device)
+    g.manual_seed(seed)
+    if rgb.c.depth > 8:
+        v = torch.randint(0, 1 << rgb.c.depth, (b.nbytes // 2,), generator=g, device=b.device, dtype=torch.int32).to(torch.int16)
+        b._t[b.offset:b.offset + b.nbytes].view(torch.int16).copy_(v)
+    else:
+        b._t[b.offset:b.offset + b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), generator=g, device=b.device, dtype=torch.int32).to(torch.uint8))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -158,9 +175,7 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     """Times C2 round trips of the reference CPU implementation with one frame per host thread.
     Returns dict(value Mpx/s, ms_per_step, cores, kind, sample)."""
     import concurrent.futures as cf
-    import numpy as np
-    from libavif_b200 import abi
-    from libavif_b200.images import RGBImage, YUVImage
+    from libavif_b200 import workloads as wl
     from oracle import loader
     ref = loader.load_reference()
     kind = "reference"
@@ -168,15 +183,12 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
         ref, kind = loader.load_oracle(), "port"
     cores = usable_cpus()
     threads = max(1, min(cores, max_threads or cores))
-    ispec, rspec = c2_specs(abi)
     # one shared read-only input frame; per-thread outputs (the conversion never writes its inputs)
-    src = YUVImage(**ispec)
+    src = wl.make_yuv("C2")
     fill_uniform(src, 1)
     work = []
     for _ in range(threads):
-        rgb = RGBImage(**rspec)
-        back = YUVImage(**ispec)
-        work.append((rgb, back))
+        work.append((wl.make_rgb("C2"), wl.make_yuv("C2")))
 
     def one(k):
         rgb, back = work[k]
@@ -189,8 +201,10 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     def step(n=None):
         assert all(r == 0 for r in pool.map(one, range(n or threads)))
 
+    t_w0 = time.perf_counter()
     for _ in range(max(1, warmup)):
         step()
+    warm_s = time.perf_counter() - t_w0
     # the reference arm gets its best configuration: all usable threads, or one per physical core if SMT siblings only fight
     if threads >= 4:
         t0 = time.perf_counter(); step(); t_all_threads = time.perf_counter() - t0
@@ -201,7 +215,7 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     t_start = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        step()
+        step(threads)
         t_all.append(time.perf_counter() - t0)
         done += 1
         if seconds_budget and time.perf_counter() - t_start > seconds_budget:
@@ -210,7 +224,7 @@ def cpu_round_trips(seconds_budget, steps, warmup, max_threads=None):
     total = sum(t_all)
     px = done * threads * 2 * PX
     return {"value": px / total / 1e6, "unit": "Mpixels/s", "ms_per_step": 1e3 * total / done, "cores": threads, "kind": kind,
-            "steps_done": done,
+            "steps_done": done, "warmup_s": warm_s,
             "sample": f"{done} steps x {threads} concurrent C2 round trips (one 3840x2160 frame per host thread, maxThreads=1), "
                       f"{'reference sources compiled -O3 (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
 
@@ -219,14 +233,12 @@ def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    r = cpu_round_trips(seconds_budget=150, steps=args.steps, warmup=min(args.warmup, 2))
+    r = cpu_round_trips(seconds_budget=150, steps=args.steps, warmup=args.warmup)
     line = {
-        "impl": "reference", "metric": "Mpixels/s YUV<->RGB (C2 round trip 3840x2160 4:4:4 10-bit + alpha premultiply)",
-        "value": r["value"], "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": min(args.warmup, 2),
+        "impl": "reference", "metric": METRIC,
+        "value": r["value"], "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": r["steps_done"], "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "C2 round trip: avifImageYUVToRGB + avifImageRGBToYUV, 3840x2160 YUV444 10-bit BT.709 full + alpha, RGBA10 premultiplied",
-                   "frames_per_step": r["cores"], "pixel_count": "each direction counts W*H"},
+        "data": "synthetic", "config": dict(CONFIG), "frames_per_step": r["cores"],
         "cpu_baseline": {"value": r["value"], "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -238,13 +250,211 @@ def run_reference_arm(args):
 # B200 arm
 
 
+def gpu_local_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), intersected with this process's mask."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        txt = open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+def time_launches(stream, fn, reps):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def golden_vectors():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_vectors.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def traffic_table():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def run_configs(lib, dev, sptr, stream, peak_gbs, rank):
+    """The other BASELINE.json configurations (north star NS, C3, C5, C1, C4 cells): kernel time per frame through the batch
+    entry point (frames per launch as listed) and through one launch per frame, each against the HBM roofline, plus a check of
+    the converted bytes against the digests the compiled reference produced for the same seeded input (tests/golden)."""
+    import torch
+    from libavif_b200 import workloads as wl
+    from libavif_b200.images import pointer_array
+    gold = golden_vectors()
+    traffic = traffic_table()
+    out = {}
+    plan = [("NS", 4), ("C3", 4), ("C5", 8), ("C5_nearest", 8), ("C1", 24), ("C1_nearest", 24), ("F16", 8), ("RGB565", 8)]
+    for name, nf in plan:
+        cfg = wl.CONFIGS[name]
+        w, h = wl.dims(name)
+        fr = []
+        for f in range(nf):
+            img = wl.make_yuv(name, device=dev)
+            fill_uniform(img, 1000 + 31 * f + rank)
+            fr.append((img, wl.make_rgb(name, device=dev)))
+        pi, pr = pointer_array([f[0] for f in fr]), pointer_array([f[1] for f in fr])
+
+        def batch():
+            assert lib.avifB200ImageYUVToRGBBatchAsync(pi, pr, nf, sptr) == 0
+
+        def single():
+            for img, rgb in fr:
+                assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
+        for _ in range(3):
+            batch()
+            single()
+        torch.cuda.synchronize()
+        reps = 5
+        ms_b = time_launches(stream, batch, reps) / nf
+        kname = lib.avifB200LastKernelName().decode()
+        ms_s = time_launches(stream, single, reps) / nf
+        alg = cfg["bytes_per_px"] * w * h
+        entry = {"kernel": kname, "direction": "YUVToRGB", "frames_per_launch": nf, "us_per_frame": ms_b * 1e3, "us_per_frame_single_launch": ms_s * 1e3,
+                 "Mpixels_per_s": w * h / (ms_b * 1e-3) / 1e6, "alg_bytes_per_px": cfg["bytes_per_px"],
+                 "roofline": {"bound": "hbm", "achieved": alg / (ms_b * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                              "frac": alg / (ms_b * 1e-3) / 1e9 / peak_gbs, "traffic": (traffic.get(name) or {}).get("dram_bytes_per_frame")},
+                 "roofline_single_launch": {"achieved": alg / (ms_s * 1e-3) / 1e9, "frac": alg / (ms_s * 1e-3) / 1e9 / peak_gbs}}
+        if name == "NS":
+            entry["north_star"] = {"target": ">= 0.70 of 8 TB/s", "frac_of_8TBps": alg / (ms_b * 1e-3) / 1e9 / 8000.0,
+                                   "frac_of_8TBps_single_launch": alg / (ms_s * 1e-3) / 1e9 / 8000.0}
+        if cfg.get("back"):
+            bi = [wl.make_yuv(name, device=dev) for _ in range(nf)]
+            pb = pointer_array(bi)
+
+            def back():
+                assert lib.avifB200ImageRGBToYUVBatchAsync(pb, pr, nf, sptr) == 0
+            for _ in range(3):
+                back()
+            torch.cuda.synchronize()
+            ms = time_launches(stream, back, reps) / nf
+            entry["back"] = {"kernel": lib.avifB200LastKernelName().decode(), "direction": "RGBToYUV", "us_per_frame": ms * 1e3,
+                             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak_gbs,
+                                          "traffic": (traffic.get(name + "_back") or {}).get("dram_bytes_per_frame")}}
+        # parity of what was just timed: frame 0 <- the seeded input of the fixture, same entry points, digest of the bytes
+        g = gold.get(name)
+        if g:
+            wl.fill_yuv_seeded(fr[0][0], g["seed"])
+            batch()
+            torch.cuda.synchronize()
+            entry["check"] = "ok" if wl.rgb_digest(fr[0][1]) == g["rgb"] else "MISMATCH"
+            if cfg.get("back") and "yuv_back" in g:
+                back()
+                torch.cuda.synchronize()
+                entry["back"]["check"] = "ok" if wl.yuv_digest(bi[0]) == g["yuv_back"] else "MISMATCH"
+        out[name] = entry
+        del fr
+        torch.cuda.empty_cache()
+    out["C4_canvas"] = run_c4_single_gpu(lib, dev, sptr, stream, peak_gbs, gold)
+    return out
+
+
+def run_c4_single_gpu(lib, dev, sptr, stream, peak_gbs, gold):
+    """C4 on one GPU: the 16 cells of the 4x4 grid (1920x1080 RGBA8) are VIEWS of one 7680x4320 canvas -- source pixels and
+    destination planes alike -- converted by ONE batched RGB->YUV launch: no per-cell allocation, no assembly pass."""
+    import ctypes
+    import torch
+    from libavif_b200 import abi as A
+    from libavif_b200 import sharding, workloads as wl
+    from libavif_b200.images import RGBImage, YUVImage, pointer_array
+    cw, ch, cols, rows = 1920, 1080, 4, 4
+    W_, H_ = cw * cols, ch * rows
+    canvas_rgb = RGBImage(W_, H_, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
+    fill_uniform_rgb(canvas_rgb, 4)
+    canvas = YUVImage(W_, H_, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
+    rects = sharding.split_grid(W_, H_, cols, rows, A.AVIF_PIXEL_FORMAT_YUV420)
+    cells_y = [sharding.view_yuv(canvas.c, r) for r in rects]
+    cells_r = [sharding.view_rgb(canvas_rgb.c, r) for r in rects]
+    pi = (ctypes.POINTER(A.avifImage) * 16)(*[ctypes.pointer(c) for c in cells_y])
+    pr = (ctypes.POINTER(A.avifRGBImage) * 16)(*[ctypes.pointer(c) for c in cells_r])
+
+    def go():
+        assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    ms = time_launches(stream, go, 10)
+    whole = YUVImage(W_, H_, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
+    assert lib.avifB200ImageRGBToYUVAsync(whole.ptr(), canvas_rgb.ptr(), sptr) == 0
+    torch.cuda.synchronize()
+    same = wl.yuv_digest(whole) == wl.yuv_digest(canvas)
+    alg = 6.5 * W_ * H_
+    return {"kernel": lib.avifB200LastKernelName().decode(), "direction": "RGBToYUV", "cells": 16, "us_per_canvas": ms * 1e3, "Mpixels_per_s": W_ * H_ / (ms * 1e-3) / 1e6,
+            "alg_bytes_per_px": 6.5, "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak_gbs},
+            "check": "ok (cell views == whole-canvas conversion)" if same else "MISMATCH"}
+
+
+def run_c5_batch(lib, dev, sptr, stream, rank, world, dist, nthreads):
+    """BASELINE config 5: 256 synthetic 4K 4:2:0 10-bit frames -> RGB16 (default upsampling = bilinear), frames dealt to the
+    ranks (f mod world), no collective; (a) resident: batch launches of <= 24 frames, CUDA events, max over ranks;
+    (b) through the synchronous C-ABI with pinned host buffers on a sample of the rank's frames."""
+    import torch
+    from libavif_b200 import workloads as wl
+    from libavif_b200.images import pointer_array
+    total = 256
+    mine = [f for f in range(total) if f % world == rank]
+    w, h = wl.dims("C5")
+    srcs, dsts = [], []
+    for f in mine:
+        img = wl.make_yuv("C5", device=dev)
+        fill_uniform(img, 5 + f)
+        srcs.append(img)
+        dsts.append(wl.make_rgb("C5", device=dev))
+    chunks = [(pointer_array(srcs[k:k + 24]), pointer_array(dsts[k:k + 24]), len(srcs[k:k + 24])) for k in range(0, len(srcs), 24)]
+
+    def go():
+        for pi, pr, n in chunks:
+            assert lib.avifB200ImageYUVToRGBBatchAsync(pi, pr, n, sptr) == 0
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = time_launches(stream, go, 3)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = {"frames": total, "frames_per_gpu": len(mine), "ms_per_pass": ms, "Mpixels_per_s": total * w * h / (ms * 1e-3) / 1e6,
+           "achieved_gbs_per_gpu": 9 * len(mine) * w * h / (ms * 1e-3) / 1e9, "kernel": lib.avifB200LastKernelName().decode()}
+    del srcs, dsts, chunks
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_b200(args):
     rank, world, local = dist_env()
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
     import libavif_b200 as L
-    from libavif_b200 import abi
-    from libavif_b200.images import RGBImage, YUVImage
+    from libavif_b200 import workloads as wl
+    from libavif_b200.images import pointer_array
 
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
@@ -254,23 +464,20 @@ def run_b200(args):
     if not L.device_available():
         raise SystemExit("bench.py: libavif_b200 sees no CUDA device (there is no CPU fallback)")
     torch.zeros(1, device=dev)  # make torch's context current before the library's first call
+    assert lib.avifB200SetDevice(local) == 0  # this rank's GPU serves the main thread's synchronous calls too
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    ispec, rspec = c2_specs(abi)
 
     # ---------------- device-resident leg ----------------
     B = args.batch
     frames = []
     for f in range(B):
-        src = YUVImage(device=dev, **ispec)
+        src = wl.make_yuv("C2", device=dev)
         fill_uniform(src, 100 + rank * 1000 + f)
-        rgb = RGBImage(device=dev, **rspec)
-        back = YUVImage(device=dev, **ispec)
-        frames.append((src, rgb, back))
+        frames.append((src, wl.make_rgb("C2", device=dev), wl.make_yuv("C2", device=dev)))
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    from libavif_b200.images import pointer_array
     p_src, p_rgb, p_back = pointer_array([f[0] for f in frames]), pointer_array([f[1] for f in frames]), pointer_array([f[2] for f in frames])
 
     def step(record=None):
@@ -292,7 +499,6 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step()
-    kfwd = lib.avifB200LastKernelName  # noqa
     step()
     torch.cuda.synchronize()
     # names of the two kernels of the step
@@ -328,49 +534,84 @@ def run_b200(args):
         elapsed_ms = float(t.item())
     value = world * args.steps * B * 2 * PX / (elapsed_ms * 1e-3) / 1e6
 
-    # ---------------- host-buffer (end-to-end) leg ----------------
+    # parity of the timed path: frame 0 <- the fixture's seeded input, same two launches, digests against the compiled reference's
+    gold = golden_vectors().get("C2")
+    check = None
+    if gold:
+        wl.fill_yuv_seeded(frames[0][0], gold["seed"])
+        step()
+        torch.cuda.synchronize()
+        check = {"rgb": "ok" if wl.rgb_digest(frames[0][1]) == gold["rgb"] else "MISMATCH",
+                 "yuv_back": "ok" if wl.yuv_digest(frames[0][2]) == gold["yuv_back"] else "MISMATCH",
+                 "against": "tests/golden/bench_vectors.json (digests of the compiled reference's output for the same seeded frame)"}
+    del frames, p_src, p_rgb, p_back
+    torch.cuda.empty_cache()
+
+    # ---------------- host-buffer (end-to-end) legs: pinned, then pageable ----------------
     Be = args.e2e_batch
-    hframes = []
-    for f in range(Be):
-        src = YUVImage(pinned=True, **ispec)
-        fill_uniform(src, 500 + rank * 1000 + f)
-        rgb = RGBImage(pinned=True, **rspec)
-        back = YUVImage(pinned=True, **ispec)
-        hframes.append((src, rgb, back))
-
+    cpus_before = os.sched_getaffinity(0)
+    local_cpus = gpu_local_cpus(local)
+    if local_cpus:
+        os.sched_setaffinity(0, local_cpus)  # pinned buffers are first-touched, and the workers run, next to this rank's GPU
     from concurrent.futures import ThreadPoolExecutor
-    nthr = max(1, min(args.e2e_threads, Be, max(1, usable_cpus() // world)))  # ranks share the host's cores
-    pool = ThreadPoolExecutor(max_workers=nthr)
+    nthr = max(1, min(args.e2e_threads, Be, max(1, usable_cpus() // (world if not local_cpus else 1))))
+    if local_cpus and world > 1:
+        nthr = max(1, min(nthr, max(1, (os.cpu_count() or 8) // world)))
 
-    def e2e_frames(chunk):  # one host thread: its frames, one synchronous round trip after the other
-        for src, rgb, back in chunk:
-            assert lib.avifImageYUVToRGB(src.ptr(), rgb.ptr()) == 0
-            assert lib.avifImageRGBToYUV(back.ptr(), rgb.ptr()) == 0
+    def worker_init():
+        # every worker thread of this rank talks to this rank's GPU (shim.c: a thread without a choice is dealt a device round-robin)
+        assert lib.avifB200SetDevice(local) == 0
+    pool = ThreadPoolExecutor(max_workers=nthr, initializer=worker_init)
 
-    def e2e_step():
-        # ctypes drops the GIL inside the library; every thread has its own streams and staging arena (shim.c: tls),
-        # so one thread's upload overlaps another's kernel and download (PCIe is full duplex)
-        list(pool.map(e2e_frames, [hframes[t::nthr] for t in range(nthr)]))
+    def e2e_leg(pinned):
+        hframes = []
+        for f in range(Be):
+            src = wl.make_yuv("C2", pinned=pinned)
+            fill_uniform(src, 500 + rank * 1000 + f)
+            hframes.append((src, wl.make_rgb("C2", pinned=pinned), wl.make_yuv("C2", pinned=pinned)))
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    e2e_steps = max(3, min(args.steps, 20))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # synchronous API: returns when the results are in host memory
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * e2e_steps * Be * 2 * PX / e2e_s / 1e6
+        def e2e_frames(chunk):  # one host thread: its frames, one synchronous round trip after the other
+            for src, rgb, back in chunk:
+                assert lib.avifImageYUVToRGB(src.ptr(), rgb.ptr()) == 0
+                assert lib.avifImageRGBToYUV(back.ptr(), rgb.ptr()) == 0
+
+        def e2e_step():
+            # ctypes drops the GIL inside the library; every thread has its own streams and staging arena (shim.c), so one
+            # thread's upload overlaps another's kernel and download (PCIe is full duplex)
+            list(pool.map(e2e_frames, [hframes[t::nthr] for t in range(nthr)]))
+
+        for _ in range(max(1, args.warmup)):
+            e2e_step()
+        e2e_steps = max(3, min(args.steps, 20 if pinned else 6))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()  # synchronous API: returns when the results are in host memory
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        ok = None
+        if gold:  # what came back over PCIe is checked as well
+            src, rgb, back = hframes[0]
+            wl.fill_yuv_seeded(src, gold["seed"])
+            e2e_frames([hframes[0]])
+            ok = "ok" if (wl.rgb_digest(rgb) == gold["rgb"] and wl.yuv_digest(back) == gold["yuv_back"]) else "MISMATCH"
+        return world * e2e_steps * Be * 2 * PX / e2e_s / 1e6, e2e_steps, ok
+
+    e2e_value, e2e_steps, e2e_ok = e2e_leg(True)
+    pg_value, pg_steps, pg_ok = e2e_leg(False)
+    pool.shutdown()
+    os.sched_setaffinity(0, cpus_before)
     plane_bytes = PX * 2
     h2d = Be * (4 * plane_bytes + 4 * plane_bytes)  # fwd: Y,U,V,A ; back: RGBA16
     d2h = Be * (4 * plane_bytes + 4 * plane_bytes)  # fwd: RGBA16  ; back: Y,U,V,A
+
+    c5 = run_c5_batch(lib, dev, sptr, stream, rank, world, dist, nthr) if not args.no_configs else None
 
     if rank != 0:
         if world > 1:
@@ -391,40 +632,42 @@ def run_b200(args):
         name_back: {"direction": "RGBToYUV", "ms_per_launch": back_ms, "achieved_gbs": alg / (back_ms * 1e-3) / 1e9},
     }
     dom = name_fwd if fwd_ms >= back_ms else name_back
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    tr = traffic_table().get("C2" if dom == name_fwd else "C2_back") or {}
+    traffic = tr.get("dram_bytes_per_frame")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": kern[dom]["achieved_gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "frac": kern[dom]["achieved_gbs"] / peak_gbs, "traffic": (traffic * B if traffic is not None else None),
+                "traffic_source": tr.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "frames_per_launch": B, "kernels": kern}
-    if traffic is not None:
-        roofline["traffic"] = traffic * B  # profiles/traffic.json holds the per-frame DRAM bytes
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r = cpu_round_trips(seconds_budget=20, steps=3, warmup=1)
         cpu = {"value": r["value"], "unit": "Mpixels/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
+    configs = run_configs(lib, dev, sptr, stream, peak_gbs, rank) if not args.no_configs else None
     extras = run_extras(lib, dev, sptr, stream, peak_gbs) if args.extras else None
 
     line = {
-        "metric": "Mpixels/s YUV<->RGB (C2 round trip 3840x2160 4:4:4 10-bit + alpha premultiply)",
+        "metric": METRIC,
         "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 round trip: avifImageYUVToRGB + avifImageRGBToYUV, 3840x2160 YUV444 10-bit BT.709 full + alpha, RGBA10 premultiplied",
-                   "frames_per_step_per_gpu": B, "pixel_count": "each direction counts W*H",
-                   "l2": f"inputs larger than L2: {B} distinct frames x 265 MB per step", "sharding": "frames across ranks, no collective"},
+        "dtype": "f32", "data": "synthetic", "config": dict(CONFIG), "frames_per_step_per_gpu": B,
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "frames_per_step_per_gpu": Be, "steps": e2e_steps, "host_memory": "pinned", "host_threads": nthr, "api": "avifImageYUVToRGB / avifImageRGBToYUV (C-ABI, host pointers)"},
+                "frames_per_step_per_gpu": Be, "steps": e2e_steps, "host_memory": "pinned", "host_threads": nthr,
+                "device_affinity": "every worker thread: avifB200SetDevice(LOCAL_RANK); process pinned to the GPU's NUMA-local CPUs" if local_cpus else "every worker thread: avifB200SetDevice(LOCAL_RANK)",
+                "api": "avifImageYUVToRGB / avifImageRGBToYUV (C-ABI, host pointers)", "check": e2e_ok},
+        "e2e_pageable": {"value": pg_value, "unit": "Mpixels/s", "steps": pg_steps, "host_memory": "pageable (numpy / malloc), staged through the library's pinned ring",
+                         "host_threads": nthr, "frac_of_pinned": pg_value / e2e_value if e2e_value else None, "check": pg_ok},
         "gpu_launches": launches,
         "roofline": roofline,
+        "check": check,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }
+    if c5:
+        line["c5_batch"] = c5
+    if configs:
+        line["configs"] = configs
     if extras:
         line["extras"] = extras
     print(json.dumps(line), flush=True)
@@ -433,103 +676,8 @@ def run_b200(args):
 
 
 def run_extras(lib, dev, sptr, stream, peak_gbs):
-    """Kernel-only timings of the other BASELINE.json configurations (device-resident, CUDA events, 4 rotating frames)."""
-    import torch
-    from libavif_b200 import abi
-    from libavif_b200.images import RGBImage, YUVImage
-    A = abi
-    cfgs = {
-        # name: (w, h, depth, fmt, range, mc, alpha, img_premult, rgb_depth, rgb_fmt, upsampling, rgb_premult, alg bytes/px)
-        "NS_8K_444_10b_RGBA10": (7680, 4320, 10, A.AVIF_PIXEL_FORMAT_YUV444, 1, 1, False, False, 10, A.AVIF_RGB_FORMAT_RGBA, 0, False, 14),
-        "C1_1080p_420_8b_RGBA8_bilinear": (1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 0, 6, False, False, 8, A.AVIF_RGB_FORMAT_RGBA, 4, False, 5.5),
-        "C1_1080p_420_8b_RGBA8_nearest": (1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 0, 6, False, False, 8, A.AVIF_RGB_FORMAT_RGBA, 3, False, 5.5),
-        "C3_8K_420_12b_bilinear_unmultiply": (7680, 4320, 12, A.AVIF_PIXEL_FORMAT_YUV420, 0, 9, True, True, 12, A.AVIF_RGB_FORMAT_RGBA, 4, False, 13),
-        "C5_4K_420_10b_RGB16_bilinear": (3840, 2160, 10, A.AVIF_PIXEL_FORMAT_YUV420, 0, 1, False, False, 16, A.AVIF_RGB_FORMAT_RGB, 0, False, 9),
-        "C5_4K_420_10b_RGB16_nearest": (3840, 2160, 10, A.AVIF_PIXEL_FORMAT_YUV420, 0, 1, False, False, 16, A.AVIF_RGB_FORMAT_RGB, 3, False, 9),
-    }
-    out = {}
-    for name, (w, h, d, fmt, rng, mc, alpha, ip, rd, rf, ups, rp, bpp) in cfgs.items():
-        nf = 4 if w >= 3840 else 16
-        fr = []
-        for f in range(nf):
-            img = YUVImage(w, h, d, fmt, rng, mc, alpha=alpha, alpha_premultiplied=ip, device=dev)
-            for p in img.present_planes():
-                b = img.bufs[p]
-                g = torch.Generator(device=dev)
-                g.manual_seed(f * 13 + p)
-                if d > 8:
-                    v = torch.randint(0, 1 << d, (b.nbytes // 2,), generator=g, device=dev, dtype=torch.int32).to(torch.int16)
-                    b._t[:b.nbytes].view(torch.int16).copy_(v)
-                else:
-                    b._t[:b.nbytes].copy_(torch.randint(0, 256, (b.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
-            rgb = RGBImage(w, h, rd, rf, upsampling=ups, alpha_premultiplied=rp, device=dev)
-            fr.append((img, rgb))
-        from libavif_b200.images import pointer_array
-        pi, pr = pointer_array([f[0] for f in fr]), pointer_array([f[1] for f in fr])
-        res = {}
-        for mode in ("per_image_launch", "batch_launch"):
-            def go():
-                if mode == "batch_launch":
-                    assert lib.avifB200ImageYUVToRGBBatchAsync(pi, pr, nf, sptr) == 0
-                else:
-                    for img, rgb in fr:
-                        assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), rgb.ptr(), sptr) == 0
-            go()
-            torch.cuda.synchronize()
-            reps = 5
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(reps):
-                go()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            res[mode] = e0.elapsed_time(e1) / (reps * nf)
-        ms = res["batch_launch"]
-        gbs = bpp * w * h / (ms * 1e-3) / 1e9
-        out[name] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": nf, "us_per_frame_per_image_launches": res["per_image_launch"] * 1e3,
-                     "us_per_frame": ms * 1e3, "Mpixels_per_s": w * h / (ms * 1e-3) / 1e6,
-                     "alg_bytes_per_px": bpp, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
-        if name.startswith("C3"):
-            # the same frames back: RGBA16 (12-bit) -> 4:2:0 12-bit + alpha, premultiplying (image is premultiplied)
-            assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, nf, sptr) == 0
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(5):
-                assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, nf, sptr) == 0
-            e1.record(stream)
-            torch.cuda.synchronize()
-            bms = e0.elapsed_time(e1) / (5 * nf)
-            bgbs = bpp * w * h / (bms * 1e-3) / 1e9
-            out["C3_back_RGBA16_to_8K_420_12b_alpha"] = {
-                "kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": nf, "us_per_frame": bms * 1e3,
-                "Mpixels_per_s": w * h / (bms * 1e-3) / 1e6, "alg_bytes_per_px": bpp, "achieved_gbs": bgbs, "frac_of_peak": bgbs / peak_gbs}
-        del fr
-        torch.cuda.empty_cache()
-    # C4: the 16 cells (1920x1080 RGBA8) of the 4x4 grid -> 4:2:0 8-bit BT.601 full + alpha, one batched RGB->YUV launch
-    cells = []
-    for f in range(16):
-        rgb = RGBImage(1920, 1080, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
-        g = torch.Generator(device=dev)
-        g.manual_seed(400 + f)
-        rgb.buf._t[:rgb.buf.nbytes].copy_(torch.randint(0, 256, (rgb.buf.nbytes,), generator=g, device=dev, dtype=torch.int32).to(torch.uint8))
-        cells.append((YUVImage(1920, 1080, 8, A.AVIF_PIXEL_FORMAT_YUV420, 1, 6, alpha=True, device=dev), rgb))
-    from libavif_b200.images import pointer_array
-    pi, pr = pointer_array([c[0] for c in cells]), pointer_array([c[1] for c in cells])
-    assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(5):
-        lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    gbs = 6.5 * 16 * 1920 * 1080 / (ms * 1e-3) / 1e9
-    out["C4_16_cells_1080p_RGBA8_to_420_8b_alpha"] = {"kernel": lib.avifB200LastKernelName().decode(), "frames_per_launch": 16, "us_per_frame_per_image_launches": None,
-                                                       "us_per_frame": ms * 1e3 / 16, "us_per_canvas": ms * 1e3, "Mpixels_per_s": 16 * 1920 * 1080 / (ms * 1e-3) / 1e6,
-                                                       "alg_bytes_per_px": 6.5, "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs}
-    out["TM_4K_gainmap_sRGB8_to_PQ_RGBA10"] = run_tone_map(lib, dev, stream, peak_gbs)
+    """Rows beyond the reformat path: gain-map tone mapping and plane scaling, device-resident."""
+    out = {"TM_4K_gainmap_sRGB8_to_PQ_RGBA10": run_tone_map(lib, dev, stream, peak_gbs)}
     out.update(run_scale(lib, dev, stream, peak_gbs))
     return out
 

@@ -37,6 +37,34 @@ def main():
     print("wrote", path, len(out["y2r"]), len(out["r2y"]))
     tool_outputs()
     next_rows()
+    bench_vectors()
+
+
+def bench_vectors(ref=None):
+    """Digests of what the compiled reference produces for BASELINE.json's full-size configurations on the seeded inputs of
+    libavif_b200/workloads.py: what bench.py checks its own outputs against after the timed region, and what the full-size GPU
+    parity tests compare with (tests/test_gpu_workloads.py)."""
+    from libavif_b200 import workloads as wl
+    ref = ref or loader.load_reference()
+    out = {}
+    for name, cfg in wl.CONFIGS.items():
+        entry = {"seed": cfg["seed"]}
+        if cfg.get("back_only"):
+            rgb = wl.make_rgb(name)
+            wl.fill_rgb_seeded(rgb, cfg["seed"])
+        else:
+            img = wl.make_yuv(name)
+            wl.fill_yuv_seeded(img, cfg["seed"])
+            rgb = wl.make_rgb(name)
+            assert ref.avifImageYUVToRGB(img.ptr(), rgb.ptr()) == 0, name
+            entry["rgb"] = wl.rgb_digest(rgb)
+        if cfg.get("back") or cfg.get("back_only"):
+            dst = wl.make_yuv(name)
+            assert ref.avifImageRGBToYUV(dst.ptr(), rgb.ptr()) == 0, name
+            entry["yuv_back"] = wl.yuv_digest(dst)
+        out[name] = entry
+        print(name, entry, flush=True)
+    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "bench_vectors.json"), "w"), indent=1)
 
 
 def next_rows():
