@@ -333,6 +333,53 @@ typedef struct avifAlphaParams {
 } avifAlphaParams;
 AVIF_B200_API void avifFillAlpha(const avifAlphaParams * params);
 AVIF_B200_API void avifReformatAlpha(const avifAlphaParams * params);
+
+/* Colour-space descriptions and the per-pixel float accessors (include/avif/internal.h:281-348; src/reformat.c:32-159 and
+ * :1856-1939).  Host-side scalar helpers of the reference's internal API: what its gain-map code (src/gainmap.c) calls around the
+ * conversions.  Exported so that a reference build can drop src/reformat.c and src/alpha.c entirely and link this library instead
+ * (seam 1, link flavour).  They touch HOST memory one pixel at a time by definition; the hot path never uses them. */
+typedef enum avifReformatMode {
+    AVIF_REFORMAT_MODE_YUV_COEFFICIENTS = 0,
+    AVIF_REFORMAT_MODE_IDENTITY,
+    AVIF_REFORMAT_MODE_YCGCO,
+    AVIF_REFORMAT_MODE_YCGCO_RE,
+    AVIF_REFORMAT_MODE_YCGCO_RO
+} avifReformatMode;
+typedef enum avifAlphaMultiplyMode {
+    AVIF_ALPHA_MULTIPLY_MODE_NO_OP = 0,
+    AVIF_ALPHA_MULTIPLY_MODE_MULTIPLY,
+    AVIF_ALPHA_MULTIPLY_MODE_UNMULTIPLY
+} avifAlphaMultiplyMode;
+typedef struct avifRGBColorSpaceInfo {
+    uint32_t channelBytes;
+    uint32_t pixelBytes;
+    uint32_t offsetBytesR;
+    uint32_t offsetBytesG;
+    uint32_t offsetBytesB;
+    uint32_t offsetBytesA;
+    uint32_t offsetBytesGray;
+    int maxChannel;
+    float maxChannelF;
+} avifRGBColorSpaceInfo;
+typedef struct avifYUVColorSpaceInfo {
+    float kr;
+    float kg;
+    float kb;
+    uint32_t channelBytes;
+    uint32_t depth;
+    avifRange range;
+    int maxChannel;
+    float biasY;
+    float biasUV;
+    float rangeY;
+    float rangeUV;
+    avifPixelFormatInfo formatInfo;
+    avifReformatMode mode;
+} avifYUVColorSpaceInfo;
+AVIF_B200_API avifBool avifGetRGBColorSpaceInfo(const avifRGBImage * rgb, avifRGBColorSpaceInfo * info);
+AVIF_B200_API avifBool avifGetYUVColorSpaceInfo(const avifImage * image, avifYUVColorSpaceInfo * info);
+AVIF_B200_API void avifGetRGBAPixel(const avifRGBImage * src, uint32_t x, uint32_t y, const avifRGBColorSpaceInfo * info, float rgbaPixel[4]);
+AVIF_B200_API void avifSetRGBAPixel(const avifRGBImage * dst, uint32_t x, uint32_t y, const avifRGBColorSpaceInfo * info, const float rgbaPixel[4]);
 #endif
 
 /* ---- B200 extensions (not in the reference) ----------------------------------------------- */
@@ -411,6 +458,10 @@ AVIF_B200_API avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t 
  * [-65536, 65535] (csrc/pixel_math.cuh: div_int).  The host proves that by exhaustion for every divisor it meets; this
  * re-runs the proof on the device.  hostVerdict receives the host's result (1 = proven). */
 AVIF_B200_API avifResult avifB200SelfTestIntDivisor(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
+/* The same 2-operation quotient serves arbitrary float numerators for every verified divisor but one (csrc/verified_divisors.h,
+ * kAbNotTwoOpDivisors; proof: tools/verify_quant.c).  Re-runs that proof on the device: all 2^32 numerators against IEEE division.
+ * hostVerdict receives whether the library uses the form for this divisor. */
+AVIF_B200_API avifResult avifB200SelfTestDivisor2(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches);
 /* Gain-map tone mapping with everything resident: base pixels, the gain map's planes and toneMappedImage->pixels (allocated by
  * the caller: width, height, rowBytes set) are device pointers; nothing crosses PCIe except the 16 bytes of statistics. */
 AVIF_B200_API avifResult avifB200RGBImageApplyGainMapDevice(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,

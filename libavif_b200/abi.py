@@ -137,6 +137,20 @@ class avifPixelFormatInfo(C.Structure):
 
 # --- prototypes of every symbol include/avif_b200.h declares -------------------------------------------
 _PI, _PR, _PA = C.POINTER(avifImage), C.POINTER(avifRGBImage), C.POINTER(avifAlphaParams)
+
+
+class avifRGBColorSpaceInfo(C.Structure):  # include/avif/internal.h:297-309
+    _fields_ = [("channelBytes", C.c_uint32), ("pixelBytes", C.c_uint32), ("offsetBytesR", C.c_uint32), ("offsetBytesG", C.c_uint32),
+                ("offsetBytesB", C.c_uint32), ("offsetBytesA", C.c_uint32), ("offsetBytesGray", C.c_uint32), ("maxChannel", C.c_int),
+                ("maxChannelF", C.c_float)]
+
+
+class avifYUVColorSpaceInfo(C.Structure):  # include/avif/internal.h:314-332
+    _fields_ = [("kr", C.c_float), ("kg", C.c_float), ("kb", C.c_float), ("channelBytes", C.c_uint32), ("depth", C.c_uint32), ("range", C.c_int),
+                ("maxChannel", C.c_int), ("biasY", C.c_float), ("biasUV", C.c_float), ("rangeY", C.c_float), ("rangeUV", C.c_float),
+                ("formatInfo", avifPixelFormatInfo), ("mode", C.c_int)]
+
+
 PROTOTYPES = {
     # reference public ABI
     "avifImageYUVToRGB": (C.c_int, [_PI, _PR]),
@@ -150,6 +164,10 @@ PROTOTYPES = {
     "avifB200SetDevice": (C.c_int, [C.c_int]),
     "avifB200SetDevices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "avifB200GetDevice": (C.c_int, []),
+    "avifGetRGBColorSpaceInfo": (C.c_int, [_PR, C.POINTER(avifRGBColorSpaceInfo)]),
+    "avifGetYUVColorSpaceInfo": (C.c_int, [_PI, C.POINTER(avifYUVColorSpaceInfo)]),
+    "avifGetRGBAPixel": (None, [_PR, C.c_uint32, C.c_uint32, C.POINTER(avifRGBColorSpaceInfo), C.POINTER(C.c_float * 4)]),
+    "avifSetRGBAPixel": (None, [_PR, C.c_uint32, C.c_uint32, C.POINTER(avifRGBColorSpaceInfo), C.POINTER(C.c_float * 4)]),
     "avifRGBFormatChannelCount": (C.c_uint32, [C.c_int]),
     "avifRGBFormatHasAlpha": (C.c_int, [C.c_int]),
     "avifRGBFormatIsGray": (C.c_int, [C.c_int]),
@@ -186,6 +204,7 @@ PROTOTYPES = {
     "avifB200VerifiedDivisorBits": (C.c_uint32, [C.c_size_t]),
     "avifB200SelfTestDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_uint64)]),
     "avifB200SelfTestIntDivisor": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "avifB200SelfTestDivisor2": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "avifB200SelfTestAlphaDivision": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
     "avifRGBImageApplyGainMap": (C.c_int, [_PR, C.c_uint16, C.c_uint16, C.POINTER(avifGainMap), C.c_float, C.c_uint16, C.c_uint16, _PR,
                                            C.POINTER(avifContentLightLevelInformationBox), C.POINTER(avifDiagnostics)]),

@@ -836,6 +836,21 @@ __global__ void __launch_bounds__(256) div_selftest_kernel(float d, float r, uns
     if (bad) atomicAdd(mismatches, bad);
 }
 
+/* self-test of the 2-op quotient on div_const's whole float domain */
+__global__ void __launch_bounds__(256) div2_selftest_kernel(AbDiv dv, unsigned long long * mismatches)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += stride) {
+        const uint32_t u = (uint32_t)b;
+        const float x = __uint_as_float(u);
+        const float ax = fabsf(x);
+        if (!(u == 0u || (ax >= 8.6736173798840355e-19f && ax <= 1152921504606846976.0f))) continue;
+        if (__float_as_uint(div_int(x, dv)) != __float_as_uint(__fdiv_rn(x, dv.d))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 /* self-test of div_int: every integer numerator in [-65536, 65535] */
 __global__ void __launch_bounds__(256) int_div_selftest_kernel(AbDiv dv, unsigned long long * mismatches)
 {
@@ -1186,6 +1201,23 @@ int abIntDivSelfTest(const AbDiv * dv, unsigned long long * mismatches, void * s
     err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
     if (!err) {
         int_div_selftest_kernel<<<131072 / 256, 256, 0, st>>>(*dv, dev);
+        err = finish_launch();
+    }
+    if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);
+    if (!err) err = (int)cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return err;
+}
+
+int abDiv2SelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long * dev = nullptr;
+    int err = (int)cudaMalloc((void **)&dev, sizeof(*dev));
+    if (err) return err;
+    err = (int)cudaMemsetAsync(dev, 0, sizeof(*dev), st);
+    if (!err) {
+        div2_selftest_kernel<<<148 * 16, 256, 0, st>>>(*dv, dev);
         err = finish_launch();
     }
     if (!err) err = (int)cudaMemcpyAsync(mismatches, dev, sizeof(*dev), cudaMemcpyDeviceToHost, st);

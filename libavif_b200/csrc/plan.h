@@ -36,6 +36,8 @@ typedef struct AbDiv {
     int intExact; /* 1: fma(x, rh, RN(x*rl)) is proven == x/d for every INTEGER x in [-65536, 65535] (checked by exhaustion
                      on the host when the divisor is first seen: shim.c divisorIntVerified) -- the 2-op form used to
                      normalise sample codes */
+    int exact2;   /* 1: the same 2-op form fma(x, rh, RN(x*rl)) is proven == x/d for EVERY float x of div_const's domain
+                     (tools/verify_quant.c `div`: all 2^32 numerators; verified_divisors.h lists the one divisor that fails) */
 } AbDiv;
 
 typedef struct AbY2RJob {
@@ -267,6 +269,7 @@ int abLaunchCopyPad(const uint8_t * src, int64_t srcRB, uint32_t srcW, uint32_t 
 /* exhaustive device check of div_const's fast form for divisor d (counts x whose result differs from x/d) */
 int abDivSelfTest(float d, unsigned long long * mismatches, void * stream);
 int abIntDivSelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream);
+int abDiv2SelfTest(const AbDiv * dv, unsigned long long * mismatches, void * stream); /* 2-op form, every float numerator of the domain */
 int abPremulFmaSelfTest(uint32_t max, float r, float k, unsigned long long * mismatches, void * stream);
 int abAlphaDivSelfTest(uint32_t max, int mode, unsigned long long * mismatches, void * stream);
 /* number of kernel launches issued by the calling thread through the functions above */

@@ -73,10 +73,32 @@ struct RLoop {
 constexpr int kRTile = 256;
 constexpr int kRWarps = 8;
 
+/* Instruction diet of round 2 (each switch = one exact rewrite; 0 restores the round-1 form for A/B timing):
+ *   AB_R2Y_QMERGE  the rounding constant of the quantiser folded into the bias: floor(RN(p + (bias + 0.5))) equals the reference's
+ *                  floor(RN(RN(p + bias) + 0.5)) after the clamp for EVERY binary32 p = RN(v*range) and every (range, bias) pair of the
+ *                  path (tools/verify_quant.c `quant`: 16 pairs x 2^32 values, bad = 0) -- one FADD less per sample;
+ *   AB_R2Y_DIV2    x / d for the verified chroma divisors as fma(x, rh, RN(x*rl)) (AbDiv.exact2: tools/verify_quant.c `div`, all 2^32
+ *                  numerators per divisor) -- one operation less than Markstein's form;
+ *   (no switch)    R/B order and alpha copy-vs-fill resolved by warp-uniform branches around the tile body instead of per-pixel selects;
+ *   AB_R2Y_LIM     unmultiply: the three `a < 1 ? q : c` selects become one clamp limit (1, or +inf when a >= 1). */
+#ifndef AB_R2Y_QMERGE
+#define AB_R2Y_QMERGE 1
+#endif
+#ifndef AB_R2Y_DIV2
+#define AB_R2Y_DIV2 1
+#endif
+#ifndef AB_R2Y_LIM
+#define AB_R2Y_LIM 1
+#endif
+
 __device__ __forceinline__ float rdivx(float x, const AbDiv & dv)
 {
+#if AB_R2Y_DIV2
+    return __fmaf_rn(x, dv.rh, __fmul_rn(x, dv.rl)); /* launcher guarantees dv.exact2 */
+#else
     const float q = __fmul_rn(x, dv.r);
     return __fmaf_rn(__fmaf_rn(-q, dv.d, x), dv.r, q);
+#endif
 }
 
 /* channel value `v` (memory order, 0 .. 8*NCH-1) of the lane's packed pixels as a magic float 2^23 + code */
@@ -90,7 +112,11 @@ __device__ __forceinline__ float chan_magic(const uint32_t * w, int v, uint32_t 
 /* ref: src/reformat.c:197-219: clamp((int)floorf((v*range + bias) + 0.5f), 0, yuvMax), returned as 2^23 + code */
 __device__ __forceinline__ float quant_yuv_magic(float v, float range, float bias, float hiLimit)
 {
+#if AB_R2Y_QMERGE
+    const float t = __fadd_rn(__fmul_rn(v, range), bias); /* bias + 0.5, see AB_R2Y_QMERGE */
+#else
     const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+#endif
     return __fadd_rz(fminf(fmaxf(t, 0.0f), hiLimit), 8388608.0f); /* floor+clamp == trunc(clamp(t, 0, max + 0.5)) */
 }
 
@@ -98,7 +124,11 @@ __device__ __forceinline__ float quant_yuv_magic(float v, float range, float bia
  * whitelisted, all with kr, kg, kb >= 0), so t >= bias + 0.5 > 0 and only the upper clamp can act */
 __device__ __forceinline__ float quant_luma_magic(float v, float range, float bias, float hiLimit)
 {
+#if AB_R2Y_QMERGE
+    const float t = __fadd_rn(__fmul_rn(v, range), bias); /* bias + 0.5, see AB_R2Y_QMERGE */
+#else
     const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+#endif
     return __fadd_rz(fminf(t, hiLimit), 8388608.0f);
 }
 
@@ -112,7 +142,11 @@ __device__ __forceinline__ float quant_luma_magic(float v, float range, float bi
 template <typename YT>
 __device__ __forceinline__ float quant_code_sat(float v, float range, float bias)
 {
+#if AB_R2Y_QMERGE
+    const float t = __fadd_rn(__fmul_rn(v, range), bias); /* `bias` is bias + 0.5 here (see AB_R2Y_QMERGE) */
+#else
     const float t = __fadd_rn(__fadd_rn(__fmul_rn(v, range), bias), 0.5f);
+#endif
     uint32_t c;
     if (sizeof(YT) == 1) {
         asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(c) : "f"(t));
@@ -132,6 +166,22 @@ template <typename YT>
 __device__ __forceinline__ float quant_luma(float v, float range, float bias, float hiLimit)
 {
     return AB_R2Y_SATCVT ? quant_code_sat<YT>(v, range, bias) : quant_luma_magic(v, range, bias, hiLimit);
+}
+/* bias == 0 (full-range luma): floor(RN(fma(v, range, 0.5))) equals the reference's floor((v*range + 0) + 0.5) after the clamp for
+ * every binary32 v (tools/verify_quant.c `quant`, the "single fma" column: bad = 0 exactly for the four bias-0 pairs) */
+template <typename YT>
+__device__ __forceinline__ float quant_luma_fullrange(float v, float range)
+{
+    const float t = __fmaf_rn(v, range, 0.5f);
+    uint32_t c;
+    if (sizeof(YT) == 1) {
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(c) : "f"(t));
+    } else {
+        unsigned short h;
+        asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(h) : "f"(t));
+        c = h;
+    }
+    return __uint_as_float(c);
 }
 
 /* CLAMP: the containers hold saturated 16-bit codes that still have to be limited to yuvMax (mm = yuvMax in both halves) */
@@ -247,8 +297,10 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame 
 
 }
 
-template <class C, bool FULL>
-__device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
+/* SWAP: B precedes R in memory; COPYA: the alpha plane receives the pixel's alpha (else it is filled with yuvMax) -- both are
+ * call constants, resolved by the warp-uniform dispatch in convert_store_rtile so that the pixel loop carries no selects */
+template <class C, bool FULL, bool SWAP, bool COPYA, bool YFULL>
+__device__ __forceinline__ void convert_store_rtile_body(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
 {
     using RT = typename C::RT;
     using YT = typename C::YT;
@@ -261,13 +313,14 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
 
     /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
     const uint32_t K = J.magicK;
-    const bool copyAlpha = (C::NCH == 4) && (J.alphaWrite == AB_ALPHA_COPY), writeAlpha = (J.alphaWrite != AB_ALPHA_KEEP);
-    const float fillAlpha = __uint_as_float(0x4B000000u | J.yuvMax);
+    const bool writeAlpha = (J.alphaWrite != AB_ALPHA_KEEP);
     const float magicOne = 8388608.0f;
     const float hiLimit = __fadd_rn(J.yuvMaxF, 0.5f);
     constexpr bool QC = (AB_R2Y_SATCVT != 0) && (sizeof(YT) == 2); /* saturated 16-bit codes: min with yuvMax at the store */
     const uint32_t mm = J.yuvMax * 0x10001u;
-    const bool swap = J.swapRB != 0;
+    /* the quantiser's additive constant: bias, or bias + 0.5 with the rounding constant folded in (exact, AB_R2Y_QMERGE) */
+    const float qbY = AB_R2Y_QMERGE ? __fadd_rn(J.biasY, 0.5f) : J.biasY;
+    const float qbUV = AB_R2Y_QMERGE ? __fadd_rn(J.biasUV, 0.5f) : J.biasUV;
     float su[4], sv[4]; /* subsampled chroma: running sums of each 2x2 (4:2:0) / 2x1 (4:2:2) box, in the reference's order */
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -276,12 +329,12 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             constexpr int c0 = C::AFIRST ? 1 : 0;
-            const float x0 = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
+            const float x0n = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0, K), magicOne), J.rgbMaxDiv);
             const float gg = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 1, K), magicOne), J.rgbMaxDiv);
-            const float x2 = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
-            float R = swap ? x2 : x0, G = gg, B = swap ? x0 : x2;
+            const float x2n = div_int(__fsub_rn(chan_magic<RT>(in.w[r], t * C::NCH + c0 + 2, K), magicOne), J.rgbMaxDiv);
+            float R = SWAP ? x2n : x0n, G = gg, B = SWAP ? x0n : x2n;
             float am = 0.0f;
-            if (C::NCH == 4) am = chan_magic<RT>(in.w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
+            if (C::NCH == 4 && (COPYA || C::AM != AB_MUL_NONE)) am = chan_magic<RT>(in.w[r], t * C::NCH + (C::AFIRST ? 0 : 3), K);
             if (C::AM != AB_MUL_NONE) { /* ref: :325-358 */
                 const float a = div_int(__fsub_rn(am, magicOne), J.rgbMaxDiv);
                 if (C::AM == AB_MUL_FLOAT_MUL) {
@@ -293,25 +346,33 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
                 } else {
                     /* branch-free so that the 8 pixels of the lane interleave freely: a == 0 -> 0, 0 < a < 1 -> min(c/a, 1),
                      * a >= 1 -> untouched (the channel may hold more than 1 there: codes above max are not clamped).
-                     * a == 0 takes the quotient path with divisor 1 and a zero "reciprocal": div_by_rcp then returns +0
-                     * (q0 = x*0 = 0, remainder x, 0*x + 0 = 0). */
+                     * One quotient path for all three cases: the divisor is a when 0 < a < 1, else 1 (c/1 == c exactly, and
+                     * rcp_refined(1) == 1); a == 0 uses a zero "reciprocal", for which div_by_rcp returns +0 (q0 = c*0 = 0,
+                     * remainder c, 0*c + 0 = 0); the clamp limit is 1 below a == 1 and +inf from there on. */
                     const bool zero = (a == 0.0f), below = (a < 1.0f);
                     const float d = (below && !zero) ? a : 1.0f;
                     const float r1 = zero ? 0.0f : rcp_refined(d);
+#if AB_R2Y_LIM
+                    const float lim = below ? 1.0f : __uint_as_float(0x7F800000u);
+                    R = fminf(div_by_rcp(R, d, r1), lim);
+                    G = fminf(div_by_rcp(G, d, r1), lim);
+                    B = fminf(div_by_rcp(B, d, r1), lim);
+#else
                     const float qR = min1(div_by_rcp(R, d, r1)), qG = min1(div_by_rcp(G, d, r1)), qB = min1(div_by_rcp(B, d, r1));
                     R = below ? qR : R;
                     G = below ? qG : G;
                     B = below ? qB : B;
+#endif
                 }
             }
             const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
-            yq[t] = quant_luma<YT>(Y, J.rangeY, J.biasY, hiLimit);
+            yq[t] = (YFULL && AB_R2Y_QMERGE && AB_R2Y_SATCVT) ? quant_luma_fullrange<YT>(Y, J.rangeY) : quant_luma<YT>(Y, J.rangeY, qbY, hiLimit);
             if (C::SUB != SUB_400) {
                 const float U = rdivx(__fsub_rn(B, Y), J.du);
                 const float V = rdivx(__fsub_rn(R, Y), J.dv);
                 if (C::SUB == SUB_444) {
-                    uq[t] = quant_yuv<YT>(U, J.rangeUV, J.biasUV, hiLimit);
-                    vq[t] = quant_yuv<YT>(V, J.rangeUV, J.biasUV, hiLimit);
+                    uq[t] = quant_yuv<YT>(U, J.rangeUV, qbUV, hiLimit);
+                    vq[t] = quant_yuv<YT>(V, J.rangeUV, qbUV, hiLimit);
                 } else {
                     /* ref: :413-467 sums the samples that exist row by row, left to right, starting from 0 + first */
                     const int k = t >> 1;
@@ -324,7 +385,7 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
                     }
                 }
             }
-            aq[t] = copyAlpha ? am : fillAlpha; /* ref: :545-569 */
+            if (COPYA) aq[t] = am; /* ref: :545-569 */
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
@@ -333,7 +394,14 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
             store_samples8<YT, QC>(F.u + (int64_t)j * F.uRB, px0, ns, uq, mm);
             store_samples8<YT, QC>(F.v + (int64_t)j * F.vRB, px0, ns, vq, mm);
         }
-        if (writeAlpha) store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
+        if (COPYA) {
+            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
+        } else if (writeAlpha) { /* warp-uniform */
+            const float fillAlpha = __uint_as_float(J.yuvMax);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) aq[t] = fillAlpha;
+            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
+        }
     }
 
     /* ---- subsampled chroma: average of the box (a division by 1, 2 or 4: exact scaling), quantise, store ---- */
@@ -344,13 +412,34 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
         for (int k = 0; k < 4; ++k) {
             const bool two = fullTile || ((uint32_t)(2 * k + 1) < nValid); /* block width 2 */
             const float inv = (two ? 0.5f : 1.0f) * ((C::SUB == SUB_420 && nRows == 2) ? 0.5f : 1.0f);
-            uq[k] = quant_yuv<YT>(__fmul_rn(su[k], inv), J.rangeUV, J.biasUV, hiLimit);
-            vq[k] = quant_yuv<YT>(__fmul_rn(sv[k], inv), J.rangeUV, J.biasUV, hiLimit);
+            uq[k] = quant_yuv<YT>(__fmul_rn(su[k], inv), J.rangeUV, qbUV, hiLimit);
+            vq[k] = quant_yuv<YT>(__fmul_rn(sv[k], inv), J.rangeUV, qbUV, hiLimit);
         }
         const uint32_t uj = (C::SUB == SUB_420) ? (j0 >> 1) : j0;
         store_samples4<YT, QC>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq, mm);
         store_samples4<YT, QC>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq, mm);
     }
+}
+
+template <class C, bool FULL>
+__device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
+{
+    /* warp-uniform (block-uniform, launch-uniform) dispatch on three call constants; ragged edge tiles (FULL == false) are rare
+     * and keep one body per channel order */
+    const bool copyA = (C::NCH == 4) && (J.alphaWrite == AB_ALPHA_COPY);
+    const bool yFull = FULL && (J.biasY == 0.0f);
+#define AB_R2Y_BODY(SW, CA, YF) convert_store_rtile_body<C, FULL, SW, CA, YF>(J, F, x0, j0, lane, in)
+    if (J.swapRB) {
+        if (copyA) AB_R2Y_BODY(true, (C::NCH == 4), false);
+        else AB_R2Y_BODY(true, false, false);
+    } else if (copyA) {
+        if (yFull) AB_R2Y_BODY(false, (C::NCH == 4), FULL);
+        else AB_R2Y_BODY(false, (C::NCH == 4), false);
+    } else {
+        if (yFull) AB_R2Y_BODY(false, false, FULL);
+        else AB_R2Y_BODY(false, false, false);
+    }
+#undef AB_R2Y_BODY
 }
 
 /* Persistent, software-pipelined and batched like y2r_fast_kernel: a block strides over groups of 8 consecutive tiles of one
@@ -569,6 +658,7 @@ static bool rfast_eligible(const AbR2YJob & J)
     if (J.nChan != 3 && J.nChan != 4) return false;
     if (!J.rgbMaxDiv.intExact) return false;
     if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return false;
+    if (AB_R2Y_DIV2 && J.hasChroma && (!J.du.exact2 || !J.dv.exact2)) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return false;
     if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return false;
     if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;

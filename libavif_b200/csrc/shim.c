@@ -189,6 +189,7 @@ static avifResult cudaToResult(int err)
     } while (0)
 
 static AbDiv makeIntDiv(float d);
+static AbDiv makeDiv(float d);
 static avifResult ctxEnter(AbScope * sc, int pointerDevice);
 static avifResult ctxLeave(AbScope * sc, avifResult res);
 
@@ -233,6 +234,26 @@ avifResult avifB200SelfTestDivisor(uint32_t divisorBits, uint64_t * mismatches)
     if (res != AVIF_RESULT_OK) return res;
     unsigned long long bad = 0;
     res = cudaToResult(abDivSelfTest(d, &bad, cx->stream));
+    *mismatches = bad;
+    return ctxLeave(&sc, res);
+}
+
+/* the 2-operation quotient (AbDiv.exact2) against IEEE division for every float numerator of the domain; hostVerdict = whether
+ * the library would use it for this divisor */
+avifResult avifB200SelfTestDivisor2(uint32_t divisorBits, int * hostVerdict, uint64_t * mismatches)
+{
+    float d;
+    memcpy(&d, &divisorBits, sizeof(d));
+    AbScope sc;
+    avifResult res = ctxEnter(&sc, -1);
+    if (res != AVIF_RESULT_OK) return res;
+    const int saved = tlsExactDivision;
+    tlsExactDivision = 0;
+    AbDiv dv = makeDiv(d);
+    tlsExactDivision = saved;
+    if (hostVerdict) *hostVerdict = dv.exact2;
+    unsigned long long bad = 0;
+    res = cudaToResult(abDiv2SelfTest(&dv, &bad, cx->stream));
     *mismatches = bad;
     return ctxLeave(&sc, res);
 }
@@ -953,6 +974,25 @@ static void calcCoefficients(const avifImage * image, float * kr, float * kg, fl
     *kg = 1.0f - r - b;
 }
 
+/* the checks of avifGetYUVColorSpaceInfo, src/reformat.c:119-141 */
+static int yuvSideValid(const avifImage * image)
+{
+    const unsigned mc = image->matrixCoefficients;
+    if (image->depth != 8 && image->depth != 10 && image->depth != 12 && image->depth != 16) return 0;
+    if (image->yuvFormat < AVIF_PIXEL_FORMAT_YUV444 || image->yuvFormat >= AVIF_PIXEL_FORMAT_COUNT) return 0;
+    if (image->yuvRange != AVIF_RANGE_LIMITED && image->yuvRange != AVIF_RANGE_FULL) return 0;
+    const int ycgcoFamily = (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO);
+    if (mc == 3 || (ycgcoFamily && image->yuvRange == AVIF_RANGE_LIMITED) || mc == AVIF_MATRIX_COEFFICIENTS_BT2020_CL ||
+        mc == AVIF_MATRIX_COEFFICIENTS_SMPTE2085 || mc == AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_CL || mc == AVIF_MATRIX_COEFFICIENTS_ICTCP ||
+        mc >= AVIF_MATRIX_COEFFICIENTS_LAST) {
+        return 0;
+    }
+    if (mc == AVIF_MATRIX_COEFFICIENTS_IDENTITY && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV444 && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV400) {
+        return 0;
+    }
+    return 1;
+}
+
 static int prepareState(const avifImage * image, const avifRGBImage * rgb, AbState * s)
 {
     const unsigned mc = image->matrixCoefficients;
@@ -991,18 +1031,7 @@ static int prepareState(const avifImage * image, const avifRGBImage * rgb, AbSta
     s->rgbMax = (1 << rgb->depth) - 1;
     s->rgbMaxF = (float)s->rgbMax;
 
-    if (image->depth != 8 && image->depth != 10 && image->depth != 12 && image->depth != 16) return 0;
-    if (image->yuvFormat < AVIF_PIXEL_FORMAT_YUV444 || image->yuvFormat >= AVIF_PIXEL_FORMAT_COUNT) return 0;
-    if (image->yuvRange != AVIF_RANGE_LIMITED && image->yuvRange != AVIF_RANGE_FULL) return 0;
-    const int ycgcoFamily = (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO);
-    if (mc == 3 || (ycgcoFamily && image->yuvRange == AVIF_RANGE_LIMITED) || mc == AVIF_MATRIX_COEFFICIENTS_BT2020_CL ||
-        mc == AVIF_MATRIX_COEFFICIENTS_SMPTE2085 || mc == AVIF_MATRIX_COEFFICIENTS_CHROMA_DERIVED_CL || mc == AVIF_MATRIX_COEFFICIENTS_ICTCP ||
-        mc >= AVIF_MATRIX_COEFFICIENTS_LAST) {
-        return 0;
-    }
-    if (mc == AVIF_MATRIX_COEFFICIENTS_IDENTITY && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV444 && image->yuvFormat != AVIF_PIXEL_FORMAT_YUV400) {
-        return 0;
-    }
+    if (!yuvSideValid(image)) return 0;
     avifPixelFormatInfo fi;
     avifGetPixelFormatInfo(image->yuvFormat, &fi);
     s->shiftX = fi.chromaShiftX;
@@ -1022,6 +1051,133 @@ static int prepareState(const avifImage * image, const avifRGBImage * rgb, AbSta
     else if (mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RE || mc == AVIF_MATRIX_COEFFICIENTS_YCGCO_RO) s->mode = AB_MODE_YCGCO_R;
     if (s->mode != AB_MODE_COEFF) s->kr = s->kg = s->kb = 0.0f;
     return 1;
+}
+
+/* ---- the reference's internal colour-space descriptions and per-pixel accessors ----------------
+ * src/reformat.c:32-159 and :1842-1939.  Host-side scalar API (one pixel of HOST memory per call): what the reference's own
+ * gain-map code calls; exported so that src/reformat.c + src/alpha.c can be left out of a reference build altogether. */
+avifBool avifGetRGBColorSpaceInfo(const avifRGBImage * rgb, avifRGBColorSpaceInfo * info)
+{
+    /* same checks, in the same order, as prepareState's RGB half */
+    if (rgb->depth != 8 && rgb->depth != 10 && rgb->depth != 12 && rgb->depth != 16) return AVIF_FALSE;
+    if (rgb->isFloat && rgb->depth != 16) return AVIF_FALSE;
+    if (rgb->format == AVIF_RGB_FORMAT_RGB_565 && rgb->depth != 8) return AVIF_FALSE;
+    if ((int)rgb->format < AVIF_RGB_FORMAT_RGB || rgb->format >= AVIF_RGB_FORMAT_COUNT) return AVIF_FALSE;
+    avifImage probe;
+    memset(&probe, 0, sizeof(probe));
+    probe.depth = 8;
+    probe.yuvFormat = AVIF_PIXEL_FORMAT_YUV444;
+    probe.yuvRange = AVIF_RANGE_FULL;
+    probe.matrixCoefficients = AVIF_MATRIX_COEFFICIENTS_BT601;
+    AbState s;
+    if (!prepareState(&probe, rgb, &s)) return AVIF_FALSE;
+    info->channelBytes = s.rgbChanBytes;
+    info->pixelBytes = s.rgbPixBytes;
+    info->offsetBytesR = s.offR;
+    info->offsetBytesG = s.offG;
+    info->offsetBytesB = s.offB;
+    info->offsetBytesA = s.offA;
+    info->offsetBytesGray = s.offGray;
+    info->maxChannel = s.rgbMax;
+    info->maxChannelF = s.rgbMaxF;
+    return AVIF_TRUE;
+}
+
+avifBool avifGetYUVColorSpaceInfo(const avifImage * image, avifYUVColorSpaceInfo * info)
+{
+    if (!yuvSideValid(image)) return AVIF_FALSE;
+    avifGetPixelFormatInfo(image->yuvFormat, &info->formatInfo);
+    calcCoefficients(image, &info->kr, &info->kg, &info->kb);
+    const int limited = (image->yuvRange == AVIF_RANGE_LIMITED);
+    info->channelBytes = (image->depth > 8) ? 2 : 1;
+    info->depth = image->depth;
+    info->range = image->yuvRange;
+    info->maxChannel = (1 << image->depth) - 1;
+    info->biasY = limited ? (float)(16 << (image->depth - 8)) : 0.0f;
+    info->biasUV = (float)(1 << (image->depth - 1));
+    info->rangeY = (float)(limited ? (219 << (image->depth - 8)) : info->maxChannel);
+    info->rangeUV = (float)(limited ? (224 << (image->depth - 8)) : info->maxChannel);
+    /* info->mode is not assigned here: the reference's function leaves it to avifPrepareReformatState as well */
+    return AVIF_TRUE;
+}
+
+/* src/reformat.c:1411, :1842-1854 */
+static const float kF16Multiplier = 1.9259299444e-34f;
+static inline uint16_t floatToF16(float v)
+{
+    union { float f; uint32_t u; } c;
+    c.f = v * kF16Multiplier;
+    return (uint16_t)(c.u >> 13);
+}
+static inline float f16ToFloat(uint16_t v)
+{
+    union { float f; uint32_t u; } c;
+    c.u = (uint32_t)v << 13;
+    return c.f / kF16Multiplier;
+}
+
+void avifGetRGBAPixel(const avifRGBImage * src, uint32_t x, uint32_t y, const avifRGBColorSpaceInfo * info, float rgbaPixel[4])
+{
+    const uint8_t * const px = &src->pixels[(size_t)y * src->rowBytes + (size_t)x * info->pixelBytes];
+    const int hasAlpha = avifRGBFormatHasAlpha(src->format);
+    if (info->channelBytes > 1) {
+        uint16_t r, g, b, a = (uint16_t)info->maxChannel;
+        memcpy(&r, px + info->offsetBytesR, 2);
+        memcpy(&g, px + info->offsetBytesG, 2);
+        memcpy(&b, px + info->offsetBytesB, 2);
+        if (hasAlpha) memcpy(&a, px + info->offsetBytesA, 2);
+        if (src->isFloat) {
+            rgbaPixel[0] = f16ToFloat(r);
+            rgbaPixel[1] = f16ToFloat(g);
+            rgbaPixel[2] = f16ToFloat(b);
+            rgbaPixel[3] = hasAlpha ? f16ToFloat(a) : 1.0f;
+        } else {
+            rgbaPixel[0] = r / info->maxChannelF;
+            rgbaPixel[1] = g / info->maxChannelF;
+            rgbaPixel[2] = b / info->maxChannelF;
+            rgbaPixel[3] = a / info->maxChannelF;
+        }
+    } else if (src->format == AVIF_RGB_FORMAT_RGB_565) { /* src/reformat.c:621-632: 5/6/5 fields widened by bit replication */
+        uint16_t v;
+        memcpy(&v, px + info->offsetBytesR, 2);
+        const uint16_t r5 = (v >> 11) & 0x1F, g6 = (v >> 5) & 0x3F, b5 = v & 0x1F;
+        rgbaPixel[0] = (uint8_t)((r5 << 3) | (r5 >> 2)) / info->maxChannelF;
+        rgbaPixel[1] = (uint8_t)((g6 << 2) | (g6 >> 4)) / info->maxChannelF;
+        rgbaPixel[2] = (uint8_t)((b5 << 3) | (b5 >> 2)) / info->maxChannelF;
+        rgbaPixel[3] = 1.0f;
+    } else {
+        rgbaPixel[0] = px[info->offsetBytesR] / info->maxChannelF;
+        rgbaPixel[1] = px[info->offsetBytesG] / info->maxChannelF;
+        rgbaPixel[2] = px[info->offsetBytesB] / info->maxChannelF;
+        rgbaPixel[3] = hasAlpha ? (px[info->offsetBytesA] / info->maxChannelF) : 1.0f;
+    }
+}
+
+void avifSetRGBAPixel(const avifRGBImage * dst, uint32_t x, uint32_t y, const avifRGBColorSpaceInfo * info, const float rgbaPixel[4])
+{
+    uint8_t * const px = &dst->pixels[(size_t)y * dst->rowBytes + (size_t)x * info->pixelBytes];
+    const int hasAlpha = avifRGBFormatHasAlpha(dst->format);
+    if (dst->depth > 8) {
+        uint16_t v[4];
+        for (int c = 0; c < 4; ++c) v[c] = dst->isFloat ? floatToF16(rgbaPixel[c]) : (uint16_t)(0.5f + (rgbaPixel[c] * info->maxChannelF));
+        memcpy(px + info->offsetBytesR, &v[0], 2);
+        memcpy(px + info->offsetBytesG, &v[1], 2);
+        memcpy(px + info->offsetBytesB, &v[2], 2);
+        if (hasAlpha) memcpy(px + info->offsetBytesA, &v[3], 2);
+        return;
+    }
+    const uint8_t r = (uint8_t)(0.5f + (rgbaPixel[0] * info->maxChannelF));
+    const uint8_t g = (uint8_t)(0.5f + (rgbaPixel[1] * info->maxChannelF));
+    const uint8_t b = (uint8_t)(0.5f + (rgbaPixel[2] * info->maxChannelF));
+    if (dst->format == AVIF_RGB_FORMAT_RGB_565) { /* avifStoreRGB8Pixel, src/reformat.c:605-617 */
+        const uint16_t v = (uint16_t)((b >> 3) | ((g >> 2) << 5) | ((r >> 3) << 11));
+        memcpy(px + info->offsetBytesR, &v, 2);
+    } else {
+        px[info->offsetBytesR] = r;
+        px[info->offsetBytesG] = g;
+        px[info->offsetBytesB] = b;
+    }
+    if (hasAlpha) px[info->offsetBytesA] = (uint8_t)(0.5f + (rgbaPixel[3] * info->maxChannelF));
 }
 
 /* binary search of the exhaustively verified divisors (verified_divisors.h) */
@@ -1081,6 +1237,13 @@ static AbDiv makeDiv(float d)
     v.rl = (float)(inv - (double)v.rh);
     v.exact = !tlsExactDivision && divisorVerified(d);
     v.intExact = 0;
+    v.exact2 = v.exact;
+    {
+        uint32_t bits;
+        memcpy(&bits, &d, sizeof(bits));
+        for (size_t k = 0; k < sizeof(kAbNotTwoOpDivisors) / sizeof(kAbNotTwoOpDivisors[0]); ++k)
+            if (kAbNotTwoOpDivisors[k] == bits) v.exact2 = 0;
+    }
     return v;
 }
 

@@ -15,4 +15,8 @@ static const uint32_t kAbVerifiedDivisors[] = {
     0x3fee9263u, 0x3ff0d19au, 0x3ff0d1b7u, 0x40000000u, 0x435b0000u, 0x43600000u, 0x437f0000u, 0x445b0000u,
     0x44600000u, 0x447fc000u, 0x455b0000u, 0x45600000u, 0x457ff000u, 0x475b0000u, 0x47600000u, 0x477fff00u,
 };
+/* The 2-operation form fma(x, rh, RN(x*rl)) with rh + rl = 1/d in double precision equals IEEE division on the same domain for
+ * every divisor above EXCEPT these (tools/verify_quant.c `div`: bad = 240 for 0x3fee5bb7, 0 for the other 55; re-checked on the
+ * device by tests/test_gpu_division.py through avifB200SelfTestDivisor2). */
+static const uint32_t kAbNotTwoOpDivisors[] = { 0x3fee5bb7u };
 #endif

@@ -130,11 +130,37 @@ __device__ __forceinline__ float magic_scalar(const uint8_t * row, uint32_t col)
 
 /* ---- arithmetic on magic floats ------------------------------------------------------------------ */
 
-/* verified constant division, unconditional fast form (the launcher guarantees dv.exact) */
+/* Instruction diet of round 2 (0 restores the round-1 form for A/B timing):
+ *   AB_Y2R_DIV2  x / d and 2x / d for verified divisors as fma(x, rh, RN(x*rl)) (AbDiv.exact2; proof: tools/verify_quant.c `div`, all
+ *                2^32 numerators per divisor, re-run on the device by tests/test_gpu_division.py) -- one operation less than Markstein's;
+ *   AB_Y2R_QFMA  (T)(0.5f + c*rgbMaxF) with the product left unrounded: floor(RN(fma(c, max, 0.5))) == floor(RN(0.5 + RN(c*max))) for
+ *                EVERY float c in [0,1] and max = 2^8-1, 2^10-1, 2^12-1, 2^16-1 (tools/verify_quant.c `rgbquant`, 1.07e9 values each). */
+#ifndef AB_Y2R_DIV2
+#define AB_Y2R_DIV2 1
+#endif
+#ifndef AB_Y2R_QFMA
+#define AB_Y2R_QFMA 1
+#endif
+#ifndef AB_Y2R_P1FMA /* bilinear blend: the diagonal tap's (exact) 1/16 product folded into an FFMA */
+#define AB_Y2R_P1FMA 1
+#endif
+#ifndef AB_Y2R_TMA /* bilinear 4:2:0: input rows staged in shared memory by the TMA engine (cp.async.bulk + mbarrier), see y2r_fast_staged_kernel.
+                    * Off by default: measured 25-30 % SLOWER than the plain loop (profiles/r02_variants.md); `make variant VFLAGS=-DAB_Y2R_TMA=1` builds it */
+#define AB_Y2R_TMA 0
+#endif
+#ifndef AB_Y2R_TMA_STAGES
+#define AB_Y2R_TMA_STAGES 3
+#endif
+
+/* verified constant division, unconditional fast form (the launcher guarantees dv.exact, and dv.exact2 for the 2-op form) */
 __device__ __forceinline__ float divx(float x, const AbDiv & dv)
 {
+#if AB_Y2R_DIV2
+    return __fmaf_rn(x, dv.rh, __fmul_rn(x, dv.rl));
+#else
     const float q = __fmul_rn(x, dv.r);
     return __fmaf_rn(__fmaf_rn(-q, dv.d, x), dv.r, q);
+#endif
 }
 
 /* RN(2x / d) for a verified divisor with the doubling folded into the constants (r2 = 2r, dh = d/2): every intermediate of
@@ -142,8 +168,12 @@ __device__ __forceinline__ float divx(float x, const AbDiv & dv)
  * because doubling commutes with rounding away from the subnormal range -- |x| is 0 or far above 2^-60 here. */
 __device__ __forceinline__ float div2x(float x, float r2, float dh)
 {
+#if AB_Y2R_DIV2
+    return __fmaf_rn(x, r2, __fmul_rn(x, dh)); /* r2 = 2 rh, dh = 2 rl of the divisor (convert_store_tile) */
+#else
     const float q2 = __fmul_rn(x, r2);
     return __fmaf_rn(__fmaf_rn(-q2, dh, x), r2, q2);
+#endif
 }
 
 /* normalised value of a magic-float code: ((float)min(code, yuvMax) - bias) / range  (ref: src/reformat.c:583,:598,:1005) */
@@ -155,7 +185,14 @@ __device__ __forceinline__ float norm_magic(float mf, float magicMax, float magi
 }
 
 /* (T)(0.5f + c*max) as the bit pattern of 2^23 + code (low 16 bits = code) */
-__device__ __forceinline__ float quant_magic(float c, float maxF) { return __fadd_rz(__fadd_rn(0.5f, __fmul_rn(c, maxF)), 8388608.0f); }
+__device__ __forceinline__ float quant_magic(float c, float maxF)
+{
+#if AB_Y2R_QFMA
+    return __fadd_rz(__fmaf_rn(c, maxF, 0.5f), 8388608.0f); /* c in [0,1]: see AB_Y2R_QFMA */
+#else
+    return __fadd_rz(__fadd_rn(0.5f, __fmul_rn(c, maxF)), 8388608.0f);
+#endif
+}
 
 __device__ __forceinline__ float clamp01f(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); } /* == AVIF_CLAMP for non-NaN */
 
@@ -308,6 +345,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
             float p9[CROWS][4], p3[CROWS][6], p1[CROWS][6]; /* index 0 = left halo, 1..4 = own columns, 5 = right halo */
+            float nn[CROWS][6];
 #pragma unroll
             for (int c = 0; c < CROWS; ++c) {
                 float n[6];
@@ -325,7 +363,8 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
                     p3[c][k] = __fmul_rn(n[k], 0.1875f);
-                    p1[c][k] = __fmul_rn(n[k], 0.0625f);
+                    nn[c][k] = n[k];
+                    p1[c][k] = AB_Y2R_P1FMA ? 0.0f : __fmul_rn(n[k], 0.0625f);
                     if (k >= 1 && k <= 4) p9[c][k - 1] = __fmul_rn(n[k], 0.5625f);
                 }
             }
@@ -338,7 +377,12 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 for (int t = 0; t < 8; ++t) {
                     const int k = 1 + (t >> 1);                 /* own column index in the 6-wide arrays */
                     const int ka = (t & 1) ? k + 1 : k - 1;     /* adjacent column: right of odd pixels, left of even ones */
+#if AB_Y2R_P1FMA
+                    /* the 1/16 product is exact (a power of two times a normal float), so adding it is one FFMA: RN(s + n/16) */
+                    const float val = __fmaf_rn(nn[ca][ka], 0.0625f, __fadd_rn(__fadd_rn(p9[cn][k - 1], p3[cn][ka]), p3[ca][k]));
+#else
                     const float val = __fadd_rn(__fadd_rn(__fadd_rn(p9[cn][k - 1], p3[cn][ka]), p3[ca][k]), p1[ca][ka]);
+#endif
                     if (plane) cr[r][t] = val;
                     else cb[r][t] = val;
                 }
@@ -348,7 +392,12 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 
     /* ------------------------------ pixels ------------------------------ */
     const float magicOne = 8388608.0f;
+#if AB_Y2R_DIV2
+    /* RN(2x / kg) = 2 RN(x / kg) = fma(x, 2rh, RN(x * 2rl)): every intermediate of the 2-op quotient doubles exactly */
+    const float kgR2 = __fmul_rn(J.kg.rh, 2.0f), kgDh = __fmul_rn(J.kg.rl, 2.0f);
+#else
     const float kgR2 = __fmul_rn(J.kg.r, 2.0f), kgDh = __fmul_rn(J.kg.d, 0.5f); /* exact scalings: see div2x */
+#endif
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (!R.rowOn[r]) continue; /* warp-uniform */
@@ -632,6 +681,230 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
 #endif
 }
 
+/* ---- TMA-staged variant (bilinear 4:2:0) -------------------------------------------------------------------
+ * The plain loop above stalls whenever all resident warps of an SM sub-partition reach the loads of their next tile together
+ * (ncu r01s: 2.4 eligible warps per cycle on average, yet 26 % of the cycles without any: long_scoreboard in bursts), and a
+ * second register set for prefetching does not fit next to the two-row tile.  Here the TMA engine does the prefetching: one
+ * lane of each warp issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of the NEXT tiles' plane rows -- two luma rows (and
+ * alpha rows), two chroma rows per plane, 256 / 128 samples each -- into a ring of AB_Y2R_TMA_STAGES warp-private shared-memory
+ * stages, each guarded by an mbarrier that counts the bytes landed; the warp then reads a stage with one conflict-free
+ * LDS.128 / LDS.64 per row into the same TileIn registers and runs the unchanged convert_store_tile.  No registers are spent on
+ * data in flight, no __syncthreads: warps stay independent.  The filter's halo columns (one chroma sample left of lane 0 and
+ * right of lane 31) are two scalar loads by the edge lanes, issued one tile ahead into four registers: replicated at the picture
+ * edge as the reference does (src/reformat.c:768-795) -- which is also why a 2-D tensor map is not used: it would zero-fill
+ * there, and a batch of frames has no room for eight descriptors per frame in the kernel parameters.  Ragged last tiles of a
+ * row (fewer than 256 pixels) and planes whose rows are not 16-byte aligned take the plain loads. */
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void * dstSmem, const void * srcGlobal, uint32_t bytes, uint64_t * bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)), "l"(srcGlobal),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+} // namespace tma
+
+template <class C>
+struct StageLayout {
+    using T = TileTraits<C>;
+    using YT = typename T::YT;
+    static constexpr int YB = kTile * (int)sizeof(YT);       /* bytes of one luma / alpha row segment */
+    static constexpr int CB = (kTile / 2) * (int)sizeof(YT); /* bytes of one chroma row segment */
+    static constexpr int OFF_A = T::ROWS * YB;
+    static constexpr int OFF_U = OFF_A + (T::NEED_A ? T::ROWS * YB : 0);
+    static constexpr int OFF_V = OFF_U + T::CROWS * CB;
+    static constexpr int BYTES = OFF_V + T::CROWS * CB;
+    static constexpr int STAGES = AB_Y2R_TMA_STAGES;
+    static constexpr int WARP_BYTES = STAGES * BYTES;
+    static constexpr int BLOCK_BYTES = kWarps * WARP_BYTES + kWarps * STAGES * 8;
+};
+
+/* position of the i-th tile of this warp (tiles of a block's groups, one per warp) */
+struct WarpTile {
+    uint32_t unit, x0;
+    bool live, full;
+};
+__device__ __forceinline__ WarpTile warp_tile(const AbY2RFrame & F, uint32_t g, uint32_t warp)
+{
+    WarpTile w;
+    const uint32_t t = g * kWarps + warp;
+    w.live = (g < F.groups) && (t < F.tiles);
+    w.unit = w.live ? t / F.tilesX : 0;
+    w.x0 = w.live ? (t - w.unit * F.tilesX) * kTile : 0;
+    w.full = w.live && (w.x0 + kTile <= F.width);
+    return w;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_staged_kernel(const __grid_constant__ AbY2RBatch B)
+{
+    using T = TileTraits<C>;
+    using YT = typename T::YT;
+    using L = StageLayout<C>;
+    static_assert(C::CHROMA == CH_BIL420, "staged kernel: bilinear 4:2:0 tiles");
+    extern __shared__ __align__(128) uint8_t smemRaw[];
+    const AbY2RJob & J = B.common;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f;
+    const AbY2RFrame & F = B.frame[f];
+    const uint32_t gStride = F.blocks;
+    const uint32_t g0 = blockIdx.x - F.blockStart;
+    if (g0 >= F.groups) return;
+    uint8_t * ring = smemRaw + warp * L::WARP_BYTES;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smemRaw + kWarps * L::WARP_BYTES) + warp * L::STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < L::STAGES; ++k) tma::mbar_init(&bars[k], 1);
+        tma::fence_proxy_async(); /* make the initialised barriers visible to the async proxy */
+    }
+    __syncwarp();
+    const uint32_t cw = (F.width + 1) >> 1;
+
+    /* issue the bulk copies of tile (g) into stage `s` (lane 0); returns nothing: the consumer re-derives what was issued */
+    auto issue = [&](uint32_t g, int s) {
+        const WarpTile w = warp_tile(F, g, warp);
+        if (!w.full) return;
+        const TileRows<C> R = tile_rows<C>(J, F, w.unit);
+        if (!R.any) return;
+        if (lane == 0) {
+            uint8_t * st = ring + s * L::BYTES;
+            uint32_t bytes = 2u * T::CROWS * L::CB;
+#pragma unroll
+            for (int r = 0; r < T::ROWS; ++r)
+                if (R.rowOn[r]) bytes += (T::NEED_A ? 2u : 1u) * L::YB;
+            tma::mbar_expect_tx(&bars[s], bytes);
+#pragma unroll
+            for (int r = 0; r < T::ROWS; ++r) {
+                if (!R.rowOn[r]) continue;
+                tma::bulk_g2s(st + r * L::YB, F.y + (int64_t)R.jrow[r] * F.yRB + (size_t)w.x0 * sizeof(YT), L::YB, &bars[s]);
+                if (T::NEED_A) tma::bulk_g2s(st + L::OFF_A + r * L::YB, F.a + (int64_t)R.jrow[r] * F.aRB + (size_t)w.x0 * sizeof(YT), L::YB, &bars[s]);
+            }
+#pragma unroll
+            for (int c = 0; c < T::CROWS; ++c) {
+                const int crow = (c == 0) ? R.cA : R.cB;
+                tma::bulk_g2s(st + L::OFF_U + c * L::CB, F.u + (int64_t)crow * F.uRB + (size_t)(w.x0 >> 1) * sizeof(YT), L::CB, &bars[s]);
+                tma::bulk_g2s(st + L::OFF_V + c * L::CB, F.v + (int64_t)crow * F.vRB + (size_t)(w.x0 >> 1) * sizeof(YT), L::CB, &bars[s]);
+            }
+        }
+    };
+    /* halo columns of a full tile: magic floats, only meaningful in lanes 0 and 31 */
+    auto halo = [&](const WarpTile & w, const TileRows<C> & R, float hU[2], float hV[2]) {
+        hU[0] = hU[1] = hV[0] = hV[1] = 0.0f;
+        if (w.full && R.any && (lane == 0 || lane == 31)) {
+            const uint32_t m0 = (w.x0 + 8 * lane) >> 1;
+            const uint32_t col = (lane == 0) ? ((m0 > 0) ? m0 - 1 : 0) : min(m0 + 4, cw - 1);
+#pragma unroll
+            for (int c = 0; c < T::CROWS; ++c) {
+                const int crow = (c == 0) ? R.cA : R.cB;
+                hU[c] = magic_scalar<YT>(F.u + (int64_t)crow * F.uRB, col);
+                hV[c] = magic_scalar<YT>(F.v + (int64_t)crow * F.vRB, col);
+            }
+        }
+    };
+
+    /* prologue: fill the ring */
+#pragma unroll
+    for (int k = 0; k < L::STAGES; ++k) issue(g0 + (uint32_t)k * gStride, k);
+    uint32_t phase = 0; /* bit s = parity the consumer waits for on stage s */
+    float nhU[2], nhV[2];
+    {
+        const WarpTile w = warp_tile(F, g0, warp);
+        const TileRows<C> R0 = tile_rows<C>(J, F, w.unit);
+        halo(w, R0, nhU, nhV);
+    }
+    int s = 0;
+    for (uint32_t g = g0; g < F.groups; g += gStride) { /* block-uniform trip count */
+        const WarpTile w = warp_tile(F, g, warp);
+        const TileRows<C> R = tile_rows<C>(J, F, w.unit);
+        const bool staged = w.full && R.any;
+        TileIn<C> in;
+        if (staged) {
+            tma::mbar_wait(&bars[s], (phase >> s) & 1u);
+            phase ^= 1u << s;
+            const uint8_t * st = ring + s * L::BYTES;
+#pragma unroll
+            for (int r = 0; r < T::ROWS; ++r) {
+                in.yw[r][0] = in.yw[r][1] = in.yw[r][2] = in.yw[r][3] = 0;
+                if (T::NEED_A) in.aw[r][0] = in.aw[r][1] = in.aw[r][2] = in.aw[r][3] = 0;
+                if (R.rowOn[r]) {
+                    if (sizeof(YT) == 2) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(st + r * L::YB + lane * 16);
+                        in.yw[r][0] = v.x; in.yw[r][1] = v.y; in.yw[r][2] = v.z; in.yw[r][3] = v.w;
+                        if (T::NEED_A) {
+                            const uint4 a = *reinterpret_cast<const uint4 *>(st + L::OFF_A + r * L::YB + lane * 16);
+                            in.aw[r][0] = a.x; in.aw[r][1] = a.y; in.aw[r][2] = a.z; in.aw[r][3] = a.w;
+                        }
+                    } else {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(st + r * L::YB + lane * 8);
+                        in.yw[r][0] = v.x; in.yw[r][1] = v.y;
+                        if (T::NEED_A) {
+                            const uint2 a = *reinterpret_cast<const uint2 *>(st + L::OFF_A + r * L::YB + lane * 8);
+                            in.aw[r][0] = a.x; in.aw[r][1] = a.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < T::CROWS; ++c) {
+                if (sizeof(YT) == 2) {
+                    const uint2 u = *reinterpret_cast<const uint2 *>(st + L::OFF_U + c * L::CB + lane * 8);
+                    const uint2 v = *reinterpret_cast<const uint2 *>(st + L::OFF_V + c * L::CB + lane * 8);
+                    in.uw[c][0] = u.x; in.uw[c][1] = u.y;
+                    in.vw[c][0] = v.x; in.vw[c][1] = v.y;
+                } else {
+                    in.uw[c][0] = *reinterpret_cast<const uint32_t *>(st + L::OFF_U + c * L::CB + lane * 4);
+                    in.vw[c][0] = *reinterpret_cast<const uint32_t *>(st + L::OFF_V + c * L::CB + lane * 4);
+                    in.uw[c][1] = in.vw[c][1] = 0;
+                }
+                in.hU[c] = nhU[c];
+                in.hV[c] = nhV[c];
+            }
+        }
+        /* halo columns of the next tile: in flight while this one converts */
+        {
+            const WarpTile wn = warp_tile(F, g + gStride, warp);
+            const TileRows<C> Rn = tile_rows<C>(J, F, wn.unit);
+            halo(wn, Rn, nhU, nhV);
+        }
+        if (staged) {
+            convert_store_tile<C, true>(J, F, R, w.x0, lane, in);
+        } else if (w.live && R.any) { /* ragged last tile of a row: plain loads */
+            load_tile<C, false>(J, F, R, w.x0, lane, in);
+            convert_store_tile<C, false>(J, F, R, w.x0, lane, in);
+        }
+        /* every lane has consumed its shared-memory reads (their values fed the arithmetic above; an unstaged tile never used the
+         * stage): refill it with the tile STAGES steps ahead */
+        __syncwarp();
+        if (lane == 0) tma::fence_proxy_async();
+        issue(g + (uint32_t)L::STAGES * gStride, s);
+        s = (s + 1 == L::STAGES) ? 0 : s + 1;
+    }
+}
+
 /* share `blocksWanted` blocks among the frames in proportion to their group counts (every frame gets at least one) */
 template <class FrameT>
 static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups, uint32_t blocksWanted)
@@ -706,31 +979,84 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
     return 1;
 }
 
+/* bilinear 4:2:0 through the TMA-staged kernel: every plane row segment must be a legal bulk-copy source (16-byte aligned) */
+static inline bool tma_aligned(const AbY2RBatch & B, bool needA)
+{
+    for (uint32_t f = 0; f < B.nFrames; ++f) {
+        const AbY2RFrame & F = B.frame[f];
+        uintptr_t bits = (uintptr_t)F.y | (uintptr_t)F.yRB | (uintptr_t)F.u | (uintptr_t)F.uRB | (uintptr_t)F.v | (uintptr_t)F.vRB;
+        if (needA) bits |= (uintptr_t)F.a | (uintptr_t)F.aRB;
+        if (bits & 15) return false;
+    }
+    return true;
+}
+
+template <typename YT, typename RT, int NCH, bool AFIRST, int AW, int AM>
+static int launch_cfg_staged(AbY2RBatch & B, cudaStream_t st)
+{
+    using C = Cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>;
+    using L = StageLayout<C>;
+    if (!AB_Y2R_TMA || !tma_aligned(B, TileTraits<C>::NEED_A)) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>(B, st);
+    uint32_t groups = 0;
+    for (uint32_t f = 0; f < B.nFrames; ++f) {
+        AbY2RFrame & F = B.frame[f];
+        const uint32_t units = (F.rowEnd >> 1) - (F.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
+        F.tilesX = (F.width + kTile - 1) / kTile;
+        F.tiles = F.tilesX * units;
+        F.groups = (F.tiles + kWarps - 1) / kWarps;
+        groups += F.groups;
+    }
+    static int residentOf[16] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int resident = (dev >= 0 && dev < 16) ? residentOf[dev] : 0;
+    if (!resident) {
+        int sms = 0, perSm = 0;
+        cudaFuncSetAttribute(y2r_fast_staged_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BLOCK_BYTES);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_staged_kernel<C>, kWarps * 32, L::BLOCK_BYTES);
+        resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+        if (dev >= 0 && dev < 16) residentOf[dev] = resident;
+    }
+    /* the ring only pays when a warp sees several tiles: small launches keep one group per block on the plain kernel */
+    if (groups < 4u * (uint32_t)resident) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>(B, st);
+    B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, (uint32_t)resident);
+    y2r_fast_staged_kernel<C><<<B.totalBlocks, kWarps * 32, L::BLOCK_BYTES, st>>>(B);
+    return 1;
+}
+
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+static int launch_any(AbY2RBatch & B, cudaStream_t st)
+{
+    if constexpr (CHROMA == CH_BIL420) return launch_cfg_staged<YT, RT, NCH, AFIRST, AW, AM>(B, st);
+    else return launch_cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>(B, st);
+}
+
 template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST>
 static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
 {
     const AbY2RJob & J = B.common;
     constexpr bool slow = (CHROMA == CH_BIL420 || CHROMA == CH_BIL422); /* general loop: alpha math in float; fast loops: integer post-pass */
     if (NCH == 3) {
-        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE>(B, st);
-        if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_cfg<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL>(B, st);
+        if (J.alphaMul == AB_MUL_NONE) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE>(B, st);
+        if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL>(B, st);
         return 0;
     }
     if (J.alphaWrite == AB_ALPHA_FILL) {
-        if (J.alphaMul == AB_MUL_NONE) return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_FILL, AB_MUL_NONE>(B, st);
+        if (J.alphaMul == AB_MUL_NONE) return launch_any<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_FILL, AB_MUL_NONE>(B, st);
         return 0;
     }
     if (J.alphaWrite != AB_ALPHA_COPY) return 0;
     switch (J.alphaMul) {
-        case AB_MUL_NONE: return launch_cfg<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(B, st);
+        case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(B, st);
         case AB_MUL_INT_PREMUL:
             if (slow || AFIRST) return 0;
-            if (J.pmR != 0.0f) return launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL_FMA>(B, st);
+            if (J.pmR != 0.0f) return launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL_FMA>(B, st);
             /* 8-bit channels always have verified constants: the general form is only instantiated for 16-bit ones */
-            return (sizeof(RT) == 1) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(B, st);
-        case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(B, st);
-        case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(B, st);
-        case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_cfg<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(B, st);
+            return (sizeof(RT) == 1) ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL>(B, st);
+        case AB_MUL_INT_UNPREMUL: return (slow || AFIRST) ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_UNPREMUL>(B, st);
+        case AB_MUL_FLOAT_MUL: return (!slow || AFIRST) ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL>(B, st);
+        case AB_MUL_FLOAT_UNMUL: return (!slow || AFIRST) ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_UNMUL>(B, st);
         default: return 0;
     }
 }
@@ -744,7 +1070,8 @@ static bool fast_eligible(const AbY2RJob & J)
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return false;
     if (!J.rangeY.intExact || !J.rangeUV.intExact || !J.kg.exact) return false;
-    if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && !J.rgbMaxDiv.exact) return false;
+    if (AB_Y2R_DIV2 && !J.kg.exact2) return false;
+    if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && (!J.rgbMaxDiv.exact || (AB_Y2R_DIV2 && !J.rgbMaxDiv.exact2))) return false;
     if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
     const bool sub = (J.chroma != AB_CHROMA_FULL);

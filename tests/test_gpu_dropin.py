@@ -136,3 +136,56 @@ def test_b2_reference_library_equals_plain_reference(b2, reference, monkeypatch)
             n_r2y += 1
     assert n_y2r > 60 and n_r2y > 60
     assert gpu.avifB200KernelLaunchCount() >= (n_y2r + n_r2y) // 2
+
+
+# ---- Seam 1, link flavour: the reference WITHOUT reformat.c / alpha.c -----------------------------------------------------------
+# oracle/_ref/libavif_ref_s1.so = the reference's avif.c, colr.c, gainmap.c, scale.c ... compiled without src/reformat.c, src/alpha.c,
+# src/reformat_libyuv.c and src/reformat_libsharpyuv.c and linked (-Wl,--no-undefined) against libavif_b200.so, which therefore has
+# to provide avifImageYUVToRGB / avifImageRGBToYUV and the internal accessors of SURVEY row a14 (avifGetRGBColorSpaceInfo,
+# avifGetRGBAPixel, avifSetRGBAPixel).  avifyuv_s1 = the reference's stress tool on that build.
+TOOL_S1 = os.path.join(ROOT, "oracle", "_ref", "avifyuv_s1")
+LIB_S1 = os.path.join(ROOT, "oracle", "_ref", "libavif_ref_s1.so")
+
+
+@pytest.fixture(scope="module")
+def s1():
+    if not os.path.exists(TOOL_S1) or not os.path.exists(LIB_S1):
+        pytest.skip("oracle/_ref seam-1 build absent (reference tree absent at build time)")
+    return TOOL_S1
+
+
+def test_s1_link_replacement_runs_the_reference_tool(s1):
+    env = dict(os.environ, AVIF_B200_TRACE_CALLS="1")
+    out = subprocess.run([TOOL_S1, "-m", "rgb"], env=env, capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    assert out.stdout.decode() == _golden("avifyuv_rgb.txt")
+    launches = int(out.stderr.decode().split("avif_b200: kernel launches")[-1].split()[0])
+    assert launches >= 144 * 4
+    out = subprocess.run([TOOL_S1, "-m", "limited"], env=env, capture_output=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.decode() == _golden("avifyuv_limited.txt")
+    # the build really has no conversion code of its own
+    nm = subprocess.run(["nm", "-D", LIB_S1], capture_output=True, text=True, check=True).stdout
+    for sym in ("avifImageYUVToRGB", "avifImageRGBToYUV", "avifGetRGBAPixel", "avifSetRGBAPixel", "avifGetRGBColorSpaceInfo"):
+        assert f" U {sym}" in nm, sym
+
+
+def test_s1_reference_gain_map_code_on_the_library(s1, reference):
+    """The reference's OWN src/gainmap.c (CPU loops, host libm) inside the seam-1 build: its conversions and per-pixel accessors
+    are the library's.  Same libm, same loops -> the tone-mapped bytes must equal the plain reference's bit for bit."""
+    import ctypes
+    import numpy as np
+    from libavif_b200 import abi as A
+    from oracle import loader
+    from tests import test_gpu_gainmap as tg
+    linked = loader._Facade(ctypes.CDLL(LIB_S1), lambda n: n)
+    for k, (tc_in, tc_out, depth, fmt) in enumerate([(13, 16, 10, A.AVIF_RGB_FORMAT_RGBA), (1, 13, 8, A.AVIF_RGB_FORMAT_BGR), (18, 18, 12, A.AVIF_RGB_FORMAT_ARGB),
+                                                     (13, 8, 16, A.AVIF_RGB_FORMAT_RGB)]):
+        outs = []
+        for lib in (reference, linked):
+            gm, keep = tg.make_gain_map(64, 40, seed=300 + k)
+            base = tg.make_base(64, 40, 8, A.AVIF_RGB_FORMAT_RGBA, seed=400 + k)
+            res, data, clli, _ = tg.apply(lib, base, 1, tc_in, gm, 1.7, 9, tc_out, depth, fmt)
+            assert res == 0
+            outs.append((np.asarray(data).copy(), tuple(clli)))
+        assert np.array_equal(outs[0][0], outs[1][0]), (tc_in, tc_out, depth, fmt)
+        assert outs[0][1] == outs[1][1]

@@ -40,4 +40,13 @@ cat $OUT/ncu_cases.md $OUT/ncu_table.err
 # SASS/source pages: C2 fwd (kernel id 1), C2 back (3), C3 fwd (7), C5 (11)
 for ID in 1 3 7 11; do ncu -i $REP.ncu-rep --page source --csv --kernel-id :::$ID > $OUT/src_k$ID.csv 2>/dev/null; done
 if [ $(stat -c %s $REP.ncu-rep) -lt 40000000 ]; then cp $REP.ncu-rep $OUT/prof_cases.ncu-rep; fi
+# the TMA-staged variant of the bilinear 4:2:0 kernel (libavif_b200/csrc/variants/libavif_b200_tma.so, if built): same capture
+if [ -e libavif_b200/csrc/variants/libavif_b200_tma.so ]; then
+  AVIF_B200_LIB=$PWD/libavif_b200/csrc/variants/libavif_b200_tma.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:"y2r_" -c 8 -o ${REP}_tma \
+      python tools/profile_cases.py $OUT/cases_tma.json --only C3,C5 > $OUT/ncu_cases_tma.log 2>&1
+  ncu -i ${REP}_tma.ncu-rep --page raw --csv --print-units base > $OUT/prof_cases_tma_raw.csv 2>/dev/null
+  python tools/ncu_table.py $OUT/prof_cases_tma_raw.csv $OUT/cases_tma.json > $OUT/ncu_cases_tma.md 2>> $OUT/ncu_table.err
+  cat $OUT/ncu_cases_tma.md
+  ncu -i ${REP}_tma.ncu-rep --page source --csv --kernel-id :::1 > $OUT/src_tma_c3.csv 2>/dev/null
+fi
 ls -la $OUT

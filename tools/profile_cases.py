@@ -37,6 +37,9 @@ def fill(img, seed):
 
 
 PLAN = [("C2", 8), ("NS", 4), ("C3", 4), ("C5", 8), ("C5_nearest", 8), ("C1", 24), ("C1_nearest", 24), ("F16", 8), ("RGB565", 8)]
+ONLY = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
+if ONLY:
+    PLAN = [p for p in PLAN if p[0] in ONLY]
 for name, nf in PLAN:
     cfg = wl.CONFIGS[name]
     w, h = wl.dims(name)
@@ -62,6 +65,10 @@ for name, nf in PLAN:
     del imgs, rgbs
     torch.cuda.empty_cache()
 
+if ONLY:
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(order, open(out_path, "w"), indent=1)
+    sys.exit(0)
 # C4: the 16 cells of the 4x4 grid as views of one canvas, one batched RGB -> YUV launch
 canvas_rgb = RGBImage(7680, 4320, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
 canvas_rgb.buf._t[:canvas_rgb.buf.nbytes].copy_(torch.randint(0, 256, (canvas_rgb.buf.nbytes,), device=dev, dtype=torch.int32).to(torch.uint8))

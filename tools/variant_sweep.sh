@@ -1,23 +1,21 @@
 #!/bin/bash
-# Times every tuning variant built by `make -C libavif_b200/csrc variant NAME=.. VFLAGS=..` against the default build:
-# one `bench.py --extras` (device-resident kernel timings of every BASELINE configuration) per library.
-# usage: gpurun --timeout 1200 -- 'bash tools/variant_sweep.sh <tag>'
+# Times every tuning variant built by `make -C libavif_b200/csrc variant NAME=.. VFLAGS=..` against the default build with
+# tools/time_variants.py (batched launches of every BASELINE configuration, CUDA events, output digests checked).
+# usage: gpurun --timeout 1200 -- 'bash tools/variant_sweep.sh <tag> [cases]'
 TAG=${1:-sweep}
+CASES=${2:-all}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 cd $GRAFT_REPO_ROOT
 run() { # name, lib path ("" = default)
-  AVIF_B200_LIB=$2 timeout 300 python bench.py --extras --no-cpu-baseline --steps 10 > $OUT/variant_$1.json 2> $OUT/variant_$1.err
+  AVIF_B200_LIB=$2 timeout 300 python tools/time_variants.py $CASES > $OUT/variant_$1.json 2> $OUT/variant_$1.err || tail -3 $OUT/variant_$1.err
   python - "$OUT/variant_$1.json" "$1" <<'PY'
 import json, sys
-d = json.load(open(sys.argv[1]))
-k = d["roofline"]["kernels"]
-row = {"C2fwd": k["y2r_fast_444"]["ms_per_launch"] * 1e3 / d["roofline"]["frames_per_launch"], "C2back": k["r2y_fast"]["ms_per_launch"] * 1e3 / d["roofline"]["frames_per_launch"]}
-for n, e in d["extras"].items():
-    if not isinstance(e, dict) or "us_per_frame" not in e:
-        continue
-    row[n.split("_")[0] + ("_" + n.split("_")[-1] if n.startswith(("C1", "C5")) else "") + ("_back" if "back" in n else "")] = e["us_per_frame"]
-print(sys.argv[2].ljust(10), " ".join(f"{a}={b:.1f}" for a, b in row.items()))
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+except Exception as e:
+    print(sys.argv[2].ljust(12), "FAILED", e); sys.exit(0)
+print(sys.argv[2].ljust(12), " ".join(f"{k}={v['us']:.1f}{'' if v['ok'] else '!BAD'}" for k, v in d.items() if isinstance(v, dict)))
 PY
 }
 run default ""

@@ -40,8 +40,8 @@ int main(int argc, char ** argv)
                                         { (float)max, (float)(1 << (depth - 1)) } };
             for (int p = 0; p < 4; ++p) {
                 const float range = pairs[p][0], bias = pairs[p][1], bh = bias + 0.5f;
-                uint64_t bad = 0;
-#pragma omp parallel for reduction(+ : bad) schedule(static)
+                uint64_t bad = 0, bad_fma = 0;
+#pragma omp parallel for reduction(+ : bad, bad_fma) schedule(static)
                 for (int64_t b = 0; b < (1ll << 32); b++) {
                     uint32_t u = (uint32_t)b;
                     float v;
@@ -50,8 +50,10 @@ int main(int argc, char ** argv)
                     const float t1 = (pr + bias) + 0.5f;
                     const float t2 = pr + bh;
                     if (clampi(t1, max) != clampi(t2, max)) bad++;
+                    if (clampi(t1, max) != clampi(fmaf(v, range, bh), max)) bad_fma++;
                 }
-                printf("depth %2d range %g bias %g: bad=%llu\n", depth, range, bias, (unsigned long long)bad);
+                printf("depth %2d range %g bias %g: bad=%llu  (single fma(v, range, bias + 0.5): bad=%llu)\n", depth, range, bias, (unsigned long long)bad,
+                       (unsigned long long)bad_fma);
                 fflush(stdout);
             }
         }
@@ -83,6 +85,27 @@ int main(int argc, char ** argv)
         }
         return 0;
     }
-    fprintf(stderr, "usage: %s quant | div <hex divisor>...\n", argv[0]);
+    if (argc >= 2 && !strcmp(argv[1], "rgbquant")) {
+        /* (3) YUV->RGB quantiser (src/reformat.c:952, :1021): (T)(0.5f + c*rgbMaxF) for c in [0,1] -- is the product's own rounding
+         * redundant, i.e. floor(RN(0.5 + RN(c*max))) == floor(RN(fma(c, max, 0.5))) for EVERY float c in [0,1] and max = 2^depth - 1? */
+        const int depths[4] = { 8, 10, 12, 16 };
+        for (int di = 0; di < 4; ++di) {
+            const float max = (float)((1 << depths[di]) - 1);
+            uint64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+            for (int64_t b = 0; b <= 0x3F800000ll; b++) {
+                uint32_t u = (uint32_t)b;
+                float c;
+                memcpy(&c, &u, 4);
+                const float t1 = 0.5f + c * max;
+                const float t2 = fmaf(c, max, 0.5f);
+                if ((uint32_t)t1 != (uint32_t)t2) bad++;
+            }
+            printf("rgb depth %2d: bad=%llu\n", depths[di], (unsigned long long)bad);
+            fflush(stdout);
+        }
+        return 0;
+    }
+    fprintf(stderr, "usage: %s quant | rgbquant | div <hex divisor>...\n", argv[0]);
     return 2;
 }
