@@ -447,6 +447,47 @@ def run_c5_batch(lib, dev, sptr, stream, rank, world, dist, nthreads):
     return res
 
 
+def run_c4_grid(lib, dev, sptr, stream, rank, world, dist):
+    """BASELINE config 4 across the ranks: avifB200GridRGBToYUV (C entry point, NCCL inside the library): the 7680x4320 RGBA8 canvas
+    lives on rank 0, its 4x4 cells are dealt to the ranks, converted, and the planes gathered -- kernel time and kernel + NCCL time
+    reported separately (CUDA events inside the library, max over ranks); output compared with the one-GPU whole-canvas conversion."""
+    import ctypes
+    import torch
+    from libavif_b200 import abi as A
+    from libavif_b200 import gridcomm, workloads as wl
+    from libavif_b200.images import RGBImage, YUVImage
+    comm = gridcomm.make_comm(lib, dist, rank, world, device=dev)
+    W_, H_ = 7680, 4320
+    rgb = RGBImage(W_, H_, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
+    canvas = YUVImage(W_, H_, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
+    if rank == 0:
+        fill_uniform_rgb(rgb, 4)
+    phase = (ctypes.c_float * 4)()
+
+    def go(timed):
+        assert lib.avifB200GridRGBToYUV(canvas.ptr(), rgb.ptr(), 4, 4, comm, rank, world, 0, sptr, ctypes.byref(phase) if timed else None) == 0
+        return list(phase)
+    for _ in range(4):
+        go(False)
+    rec = [go(True) for _ in range(10)]
+    t = torch.tensor([sum(x[k] for x in rec) / len(rec) for k in range(4)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sc, cv, ga, asm_ = [float(v) for v in t]
+    res = None
+    if rank == 0:
+        whole = YUVImage(W_, H_, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
+        assert lib.avifB200ImageRGBToYUVAsync(whole.ptr(), rgb.ptr(), sptr) == 0
+        torch.cuda.synchronize()
+        res = {"workload": "4x4 grid of 1920x1080 RGBA8 cells -> 4:2:0 8-bit BT.601 full + alpha; canvas resident on rank 0, cells dealt round-robin",
+               "api": "avifB200GridRGBToYUV (grouped ncclSend/ncclRecv inside the library)", "n_gpus": world,
+               "ms_scatter": sc, "ms_convert": cv, "ms_gather": ga, "ms_assemble": asm_, "ms_total": sc + cv + ga + asm_,
+               "Mpixels_per_s_kernel": W_ * H_ / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": W_ * H_ / ((sc + cv + ga + asm_) * 1e-3) / 1e6,
+               "check": "ok (== whole-canvas conversion on one GPU)" if wl.yuv_digest(whole) == wl.yuv_digest(canvas) else "MISMATCH"}
+    gridcomm.destroy_comm(lib, comm)
+    return res
+
+
 def run_b200(args):
     rank, world, local = dist_env()
     import numpy as np  # noqa: F401
@@ -612,6 +653,7 @@ def run_b200(args):
     d2h = Be * (4 * plane_bytes + 4 * plane_bytes)  # fwd: RGBA16  ; back: Y,U,V,A
 
     c5 = run_c5_batch(lib, dev, sptr, stream, rank, world, dist, nthr) if not args.no_configs else None
+    c4 = run_c4_grid(lib, dev, sptr, stream, rank, world, dist) if (world > 1 and not args.no_configs) else None
 
     if rank != 0:
         if world > 1:
@@ -666,6 +708,8 @@ def run_b200(args):
     }
     if c5:
         line["c5_batch"] = c5
+    if c4:
+        line["c4_grid"] = c4
     if configs:
         line["configs"] = configs
     if extras:

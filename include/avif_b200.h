@@ -418,6 +418,37 @@ AVIF_B200_API avifResult avifB200ImageLimitedToFullAlpha(avifImage * image);
 AVIF_B200_API avifResult avifB200ImageCopySamplesAsync(avifImage * dst, const avifImage * src, avifPlanesFlags planes, void * stream);
 AVIF_B200_API avifResult avifB200ImageCopyAndPadAsync(avifImage * dst, const avifImage * src, void * stream);
 
+/* Rows [rowBegin, rowEnd) of a resident frame (a tile / band pipeline converts rows as they arrive).  image and rgb describe the
+ * WHOLE frame: edge replication of the bilinear filter happens at the real picture edges only (src/reformat.c:768-795).  Of the
+ * planes only the rows the range touches need to exist behind the pointers -- luma / alpha rows rowBegin..rowEnd-1, chroma rows
+ * (rowBegin >> shiftY) - 1 .. ((rowEnd - 1) >> shiftY) + 1 clipped to the plane -- so base pointers may be "virtual" (band buffer
+ * minus rowBegin * rowBytes).  rowBegin must be even for 4:2:0.  Device pointers, stream-ordered. */
+AVIF_B200_API avifResult avifB200ImageYUVToRGBRowsAsync(const avifImage * image, avifRGBImage * rgb, uint32_t rowBegin, uint32_t rowEnd, void * stream);
+
+/* ---- tile grids across GPUs (BASELINE config 4; reference: avifImageSplitGrid apps/shared/avifutil.c:546-605,
+ * avifEncoderAddImageGrid src/write.c:2147, tile copy + canvas conversion src/read.c:1823-1878, :6777-6866) --------------------
+ * One process per GPU.  `comm` is an ncclComm_t (void *) over the participating ranks, or NULL for a single GPU; the library
+ * reaches NCCL through dlopen("libnccl.so.2") and answers AVIF_RESULT_NOT_IMPLEMENTED where it is absent.  Every rank calls with
+ * the same descriptors (dimensions, formats, flags); plane / pixel pointers are device memory on `root` and unused elsewhere
+ * (for avifB200GridYUVToRGB the row strides tell the other ranks which planes exist).  All work is enqueued on `stream`.
+ *   avifB200GridCellRect      cell `cellIndex` (row-major) of the reference's split rule; INVALID_ARGUMENT where the rule fails
+ *   avifB200GridRGBToYUV      cells go to rank (root + cell) mod nranks: grouped ncclSend/ncclRecv of the cells' pixels, ONE batched
+ *                             launch per rank (root: views of the canvas, nothing copied), grouped exchange of the planes back,
+ *                             placement into the canvas planes.  Bit-identical to converting the whole canvas (cell sizes are even
+ *                             when chroma is subsampled).  phaseMs (may be NULL; synchronises when given): scatter, convert, gather,
+ *                             assemble in milliseconds on this rank.
+ *   avifB200GridYUVToRGB      decode side: the canvas is cut into nranks even row bands, each shipped with one chroma row of halo
+ *                             per inner seam and converted against whole-canvas geometry (bilinear upsampling is not tile-local).
+ *                             phaseMs: scatter, convert, gather. */
+AVIF_B200_API avifResult avifB200GridGetUniqueId(uint8_t id[128]);
+AVIF_B200_API avifResult avifB200GridCommInit(void ** comm, int nranks, int rank, const uint8_t id[128]);
+AVIF_B200_API avifResult avifB200GridCommDestroy(void * comm);
+AVIF_B200_API avifResult avifB200GridCellRect(const avifImage * canvas, uint32_t gridCols, uint32_t gridRows, uint32_t cellIndex, avifCropRect * rect);
+AVIF_B200_API avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasRgb, uint32_t gridCols, uint32_t gridRows, void * comm, int rank,
+                                              int nranks, int root, void * stream, float phaseMs[4]);
+AVIF_B200_API avifResult avifB200GridYUVToRGB(const avifImage * canvas, avifRGBImage * canvasRgb, void * comm, int rank, int nranks, int root, void * stream,
+                                              float phaseMs[3]);
+
 /* ---- which GPU serves a synchronous (host-pointer) call ----------------------------------------------------------------
  * The reference has no notion of a device; its own parallel unit is the per-call thread fan-out of
  * src/reformat.c:1679-1747.  Here several host threads may convert at once (avif.h:1012-1014), each on a GPU chosen as follows:

@@ -139,6 +139,10 @@ class avifPixelFormatInfo(C.Structure):
 _PI, _PR, _PA = C.POINTER(avifImage), C.POINTER(avifRGBImage), C.POINTER(avifAlphaParams)
 
 
+class avifCropRect(C.Structure):
+    _fields_ = [("x", C.c_uint32), ("y", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class avifRGBColorSpaceInfo(C.Structure):  # include/avif/internal.h:297-309
     _fields_ = [("channelBytes", C.c_uint32), ("pixelBytes", C.c_uint32), ("offsetBytesR", C.c_uint32), ("offsetBytesG", C.c_uint32),
                 ("offsetBytesB", C.c_uint32), ("offsetBytesA", C.c_uint32), ("offsetBytesGray", C.c_uint32), ("maxChannel", C.c_int),
@@ -161,6 +165,13 @@ PROTOTYPES = {
     "avifFullToLimitedUV": (C.c_int, [C.c_uint32, C.c_int]),
     "avifLimitedToFullY": (C.c_int, [C.c_uint32, C.c_int]),
     "avifLimitedToFullUV": (C.c_int, [C.c_uint32, C.c_int]),
+    "avifB200ImageYUVToRGBRowsAsync": (C.c_int, [_PI, _PR, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "avifB200GridGetUniqueId": (C.c_int, [C.POINTER(C.c_uint8 * 128)]),
+    "avifB200GridCommInit": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_uint8 * 128)]),
+    "avifB200GridCommDestroy": (C.c_int, [C.c_void_p]),
+    "avifB200GridCellRect": (C.c_int, [_PI, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(avifCropRect)]),
+    "avifB200GridRGBToYUV": (C.c_int, [_PI, _PR, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float * 4)]),
+    "avifB200GridYUVToRGB": (C.c_int, [_PI, _PR, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float * 3)]),
     "avifB200SetDevice": (C.c_int, [C.c_int]),
     "avifB200SetDevices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "avifB200GetDevice": (C.c_int, []),

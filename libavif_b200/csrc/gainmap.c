@@ -226,7 +226,8 @@ static int onDevice(const void * p)
 /* Scratch (converted gain map, staged base, output, tables) comes from a stream-ordered pool that keeps what it has been
  * given: the default pool hands freed memory back to the driver at every synchronisation (release threshold 0), which
  * turns each call into milliseconds of mapping work. */
-int abScratchAlloc(void ** p, size_t bytes)
+int abScratchAlloc(void ** p, size_t bytes) { return abScratchAllocOn(p, bytes, AB_STREAM); }
+int abScratchAllocOn(void ** p, size_t bytes, void * stream)
 {
     enum { kMaxDevices = 64 };
     static cudaMemPool_t pools[kMaxDevices];
@@ -234,7 +235,7 @@ int abScratchAlloc(void ** p, size_t bytes)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    if (dev < 0 || dev >= kMaxDevices) return (int)cudaMallocAsync(p, bytes, AB_STREAM);
+    if (dev < 0 || dev >= kMaxDevices) return (int)cudaMallocAsync(p, bytes, (cudaStream_t)stream);
     if (!__atomic_load_n(&made[dev], __ATOMIC_ACQUIRE)) {
         static int lock = 0;
         while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {
@@ -256,7 +257,7 @@ int abScratchAlloc(void ** p, size_t bytes)
         __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
         if (e != cudaSuccess) return (int)e;
     }
-    return (int)cudaMallocFromPoolAsync(p, bytes, pools[dev], AB_STREAM);
+    return (int)cudaMallocFromPoolAsync(p, bytes, pools[dev], (cudaStream_t)stream);
 }
 
 #define GM_CUDA(call)                                                        \

@@ -225,6 +225,7 @@ void abDeviceLeave(int prevDevice);
 /* Stream-ordered (AB_STREAM) device scratch from a per-device pool that keeps freed memory instead of returning it
  * to the driver at every synchronisation (gainmap.c); release with cudaFreeAsync(p, AB_STREAM).  Returns a cudaError_t value. */
 int abScratchAlloc(void ** p, size_t bytes);
+int abScratchAllocOn(void ** p, size_t bytes, void * stream); /* the same pool, ordered on `stream`; release with cudaFreeAsync(p, stream) */
 
 /* ---- plane scaling (scale_kernels.cu; src/scale.c over third_party/libyuv/source/scale*.c) ----
  * The host walks libyuv's 16.16 stepping state machines once per plane (scale.c here: O(width + height) integer work, no

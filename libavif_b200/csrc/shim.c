@@ -2180,6 +2180,49 @@ avifResult avifB200ImageYUVToRGBBatchAsync(const avifImage * const * images, avi
     return res;
 }
 
+/* Rows [rowBegin, rowEnd) of a resident frame: what a tile / band pipeline calls as decoded rows arrive.  The image and rgb
+ * structs describe the WHOLE frame (bilinear upsampling replicates chroma only at the real picture edges, src/reformat.c:768-795,
+ * and reads one chroma row beyond the band inside the picture); of the planes only the rows the band touches need to exist behind
+ * the pointers -- luma / alpha rows rowBegin..rowEnd-1, chroma rows (rowBegin >> shiftY) - 1 .. ((rowEnd - 1) >> shiftY) + 1 clipped
+ * to the plane -- so a caller may pass "virtual" base pointers (band buffer minus rowBegin * rowBytes).  rowBegin must be even for
+ * vertically subsampled formats.  Device pointers, stream-ordered. */
+avifResult avifB200ImageYUVToRGBRowsAsync(const avifImage * image, avifRGBImage * rgb, uint32_t rowBegin, uint32_t rowEnd, void * stream)
+{
+    AbY2RJob job;
+    AbY2RPlan plan;
+    avifResult res = y2rBuildJob(image, rgb, &job, &plan);
+    if (res != AVIF_RESULT_OK) return res;
+    if (rgb->width != image->width || rgb->height != image->height) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (rowBegin > rowEnd || rowEnd > image->height || (plan.s.shiftY && (rowBegin & 1))) return AVIF_RESULT_INVALID_ARGUMENT;
+    if (job.alphaWrite == AB_ALPHA_KEEP && plan.rgbHasAlpha) {
+        /* untouched alpha bytes: fine for resident buffers (nothing is staged), nothing to do */
+    }
+    if (!avifB200DeviceAvailable()) return AVIF_RESULT_UNKNOWN_ERROR;
+    if (rowBegin == rowEnd) return AVIF_RESULT_OK;
+    const int needSrcAlpha = (job.alphaWrite == AB_ALPHA_COPY) || job.alphaMul == AB_MUL_FLOAT_MUL || job.alphaMul == AB_MUL_FLOAT_UNMUL;
+    job.y = image->yuvPlanes[0];
+    job.yRB = image->yuvRowBytes[0];
+    job.u = plan.hasChroma ? image->yuvPlanes[1] : NULL;
+    job.uRB = image->yuvRowBytes[1];
+    job.v = plan.hasChroma ? image->yuvPlanes[2] : NULL;
+    job.vRB = image->yuvRowBytes[2];
+    job.a = needSrcAlpha ? image->alphaPlane : NULL;
+    job.aRB = job.a ? image->alphaRowBytes : 0;
+    job.rgb = rgb->pixels;
+    job.rgbRB = rgb->rowBytes;
+    job.rowBegin = rowBegin;
+    job.rowEnd = rowEnd;
+    const uintptr_t m = 2u * plan.s.yuvChanBytes - 1;
+    uintptr_t bits = (uintptr_t)job.y | (uintptr_t)job.yRB;
+    if (job.u) bits |= (uintptr_t)job.u | (uintptr_t)job.uRB | (uintptr_t)job.v | (uintptr_t)job.vRB;
+    if (job.a) bits |= (uintptr_t)job.a | (uintptr_t)job.aRB;
+    job.pairAligned = (uint8_t)((bits & m) == 0);
+    const char * kname = "";
+    res = cudaToResult(abLaunchY2R(&job, stream, tls.policy, &kname));
+    tls.lastKernel = kname;
+    return res;
+}
+
 avifResult avifB200ImageRGBToYUVBatchAsync(avifImage * const * images, const avifRGBImage * const * rgbs, uint32_t count, void * stream)
 {
     if (count == 0) return AVIF_RESULT_OK;
