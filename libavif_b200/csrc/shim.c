@@ -771,6 +771,49 @@ static unsigned gRingCursor(void)
     return cursor++;
 }
 
+/* Host copy between a caller's pageable buffer and a pinned chunk.  With several host threads converting at once the staging
+ * copies are bound by the socket's memory bandwidth, and an ordinary store stream costs a read-for-ownership of every destination
+ * line on top of the read and the write: non-temporal stores drop that third of the traffic (glibc's memcpy only switches to them
+ * above a threshold far larger than a chunk).  AVIF_B200_NT_COPY=0 falls back to memcpy. */
+#if defined(__x86_64__)
+#include <emmintrin.h>
+static void copyStreaming(uint8_t * dst, const uint8_t * src, size_t n)
+{
+    static int useNt = -1;
+    if (useNt < 0) {
+        const char * e = getenv("AVIF_B200_NT_COPY");
+        useNt = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!useNt || n < 4096) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t head = (size_t)(-(uintptr_t)dst) & 63;
+    if (head) {
+        memcpy(dst, src, head);
+        dst += head;
+        src += head;
+        n -= head;
+    }
+    const size_t blocks = n / 64;
+    const __m128i * s = (const __m128i *)src;
+    __m128i * d = (__m128i *)dst;
+    for (size_t k = 0; k < blocks; ++k) {
+        const __m128i a = _mm_loadu_si128(s + 0), b = _mm_loadu_si128(s + 1), c = _mm_loadu_si128(s + 2), e = _mm_loadu_si128(s + 3);
+        _mm_stream_si128(d + 0, a);
+        _mm_stream_si128(d + 1, b);
+        _mm_stream_si128(d + 2, c);
+        _mm_stream_si128(d + 3, e);
+        s += 4;
+        d += 4;
+    }
+    _mm_sfence(); /* the chunk is handed to the copy engine / the caller right after */
+    if (n & 63) memcpy(dst + blocks * 64, src + blocks * 64, n & 63);
+}
+#else
+static void copyStreaming(uint8_t * dst, const uint8_t * src, size_t n) { memcpy(dst, src, n); }
+#endif
+
 static avifResult stagedUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
 {
     const size_t pitch = (size_t)r->devRB; /* the chunk mirrors the arena layout: one 1-D DMA per chunk */
@@ -784,9 +827,9 @@ static avifResult stagedUpload(const AbRegion * r, uint32_t row0, uint32_t row1,
         AB_CUDA(cudaEventSynchronize(cx->evRing[slot])); /* the DMA that last used this chunk */
         const uint8_t * src = r->user + (int64_t)row * r->userRB;
         if ((size_t)r->userRB == pitch) {
-            memcpy(chunk, src, pitch * (n - 1) + r->rowUsed);
+            copyStreaming(chunk, src, pitch * (n - 1) + r->rowUsed);
         } else {
-            for (uint32_t k = 0; k < n; ++k) memcpy(chunk + (size_t)k * pitch, src + (int64_t)k * r->userRB, r->rowUsed);
+            for (uint32_t k = 0; k < n; ++k) copyStreaming(chunk + (size_t)k * pitch, src + (int64_t)k * r->userRB, r->rowUsed);
         }
         AB_CUDA(cudaMemcpyAsync(r->dev + (size_t)row * pitch, chunk, pitch * (n - 1) + r->rowUsed, cudaMemcpyHostToDevice, st));
         AB_CUDA(cudaEventRecord(cx->evRing[slot], st));
@@ -829,9 +872,9 @@ static avifResult stagedDownload(const AbRegion * r, uint32_t row0, uint32_t row
         const uint8_t * chunk = cx->ring + (size_t)slot * cx->ringSlotBytes;
         uint8_t * dst = r->user + (int64_t)prow * r->userRB;
         if ((size_t)r->userRB == pitch) {
-            memcpy(dst, chunk, pitch * (pn - 1) + r->rowUsed);
+            copyStreaming(dst, chunk, pitch * (pn - 1) + r->rowUsed);
         } else {
-            for (uint32_t k = 0; k < pn; ++k) memcpy(dst + (int64_t)k * r->userRB, chunk + (size_t)k * pitch, r->rowUsed);
+            for (uint32_t k = 0; k < pn; ++k) copyStreaming(dst + (int64_t)k * r->userRB, chunk + (size_t)k * pitch, r->rowUsed);
         }
     }
     return AVIF_RESULT_OK;
