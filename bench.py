@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--e2e-threads", type=int, default=8,
                     help="host threads of the host-buffer leg, each converting its own frames through the synchronous C-ABI "
                          "(the reference arm uses every host core; independent calls from different threads are legal, avif.h:1012)")
+    ap.add_argument("--stage-threads", type=int, default=3, help="rgb.maxThreads of the pageable host-buffer leg (calling thread + helpers of the staging copies)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration legs (NS, C3, C5, C1, C4 canvas, C5 batch)")
     ap.add_argument("--extras", action="store_true", help="also time the rows beyond the reformat path (tone mapping, scaling) into 'extras'")
@@ -609,7 +610,9 @@ def run_b200(args):
         for f in range(Be):
             src = wl.make_yuv("C2", pinned=pinned)
             fill_uniform(src, 500 + rank * 1000 + f)
-            hframes.append((src, wl.make_rgb("C2", pinned=pinned), wl.make_yuv("C2", pinned=pinned)))
+            # pageable leg: rgb.maxThreads = 3 lets the library share the staging copies with two helper threads per call
+            # (the reference spends maxThreads threads on the conversion itself, src/reformat.c:1679-1747)
+            hframes.append((src, wl.make_rgb("C2", pinned=pinned, max_threads=1 if pinned else args.stage_threads), wl.make_yuv("C2", pinned=pinned)))
 
         def e2e_frames(chunk):  # one host thread: its frames, one synchronous round trip after the other
             for src, rgb, back in chunk:
@@ -698,7 +701,7 @@ def run_b200(args):
                 "frames_per_step_per_gpu": Be, "steps": e2e_steps, "host_memory": "pinned", "host_threads": nthr,
                 "device_affinity": "every worker thread: avifB200SetDevice(LOCAL_RANK); process pinned to the GPU's NUMA-local CPUs" if local_cpus else "every worker thread: avifB200SetDevice(LOCAL_RANK)",
                 "api": "avifImageYUVToRGB / avifImageRGBToYUV (C-ABI, host pointers)", "check": e2e_ok},
-        "e2e_pageable": {"value": pg_value, "unit": "Mpixels/s", "steps": pg_steps, "host_memory": "pageable (numpy / malloc), staged through the library's pinned ring",
+        "e2e_pageable": {"value": pg_value, "unit": "Mpixels/s", "steps": pg_steps, "host_memory": "pageable (numpy / malloc), staged through the library's pinned ring", "rgb_maxThreads": args.stage_threads,
                          "host_threads": nthr, "frac_of_pinned": pg_value / e2e_value if e2e_value else None, "check": pg_ok},
         "gpu_launches": launches,
         "roofline": roofline,

@@ -248,18 +248,49 @@ struct RTileIn {
     uint32_t w[ROWS][NW];
 };
 
-/* tile = 256 pixels x ROWS rows starting at luma row j0 */
+/* lane-specific addresses of one tile: the lane's first pixel in the RGB buffer, its first sample in every plane row of the
+ * tile's first luma row (subsampled chroma: of the chroma row the tile's first luma row maps to) */
+struct RPtrs {
+    const uint8_t * rgb;
+    uint8_t * y;
+    uint8_t * u;
+    uint8_t * v;
+    uint8_t * a;
+};
+
+template <class C>
+__device__ __forceinline__ RPtrs rtile_ptrs(const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane)
+{
+    using RT = typename C::RT;
+    using YT = typename C::YT;
+    constexpr int PIXB = C::NCH * (int)sizeof(RT);
+    const uint32_t px0 = x0 + 8 * lane;
+    RPtrs P;
+    P.rgb = F.rgb + (int64_t)j0 * F.rgbRB + (int64_t)px0 * PIXB;
+    P.y = F.y + (int64_t)j0 * F.yRB + (size_t)px0 * sizeof(YT);
+    P.a = F.a ? F.a + (int64_t)j0 * F.aRB + (size_t)px0 * sizeof(YT) : nullptr;
+    P.u = P.v = nullptr;
+    if (C::SUB == SUB_444) {
+        P.u = F.u + (int64_t)j0 * F.uRB + (size_t)px0 * sizeof(YT);
+        P.v = F.v + (int64_t)j0 * F.vRB + (size_t)px0 * sizeof(YT);
+    } else if (C::SUB != SUB_400) {
+        const uint32_t uj = (C::SUB == SUB_420) ? (j0 >> 1) : j0;
+        P.u = F.u + (int64_t)uj * F.uRB + (size_t)(px0 >> 1) * sizeof(YT);
+        P.v = F.v + (int64_t)uj * F.vRB + (size_t)(px0 >> 1) * sizeof(YT);
+    }
+    return P;
+}
+
+/* tile = 256 pixels x ROWS rows; `rgb` = the lane's first pixel of the first row, nValid = pixels of the lane inside the
+ * picture (8 for FULL tiles), nRows = rows of the tile inside the picture */
 template <class C, bool FULL>
-__device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, RTileIn<C> & in)
+__device__ __forceinline__ void load_rtile_p(const AbR2YFrame & F, const uint8_t * rgb, uint32_t nValid, uint32_t nRows, RTileIn<C> & in)
 {
     using RT = typename C::RT;
     constexpr int ROWS = RTileIn<C>::ROWS;
     constexpr int PIXB = C::NCH * (int)sizeof(RT);
     constexpr int NW = RTileIn<C>::NW;
     constexpr bool fullTile = FULL;
-    const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
-    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
     /* ---- loads: 8 pixels x ROWS rows, issued before any arithmetic ---- */
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -267,7 +298,7 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame 
         for (int k = 0; k < NW; ++k)
             if (!FULL || r > 0) in.w[r][k] = 0; /* row 0 of a full tile is loaded unconditionally */
         if (r == 0 || (uint32_t)r < nRows) { /* the tile's first row always exists */
-            const uint8_t * p = F.rgb + (int64_t)(j0 + r) * F.rgbRB + (int64_t)px0 * PIXB;
+            const uint8_t * p = rgb + (int64_t)r * F.rgbRB;
             if (fullTile || nValid >= 8) {
                 if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
@@ -294,22 +325,31 @@ __device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame 
             }
         }
     }
+}
 
+template <class C, bool FULL>
+__device__ __forceinline__ void load_rtile(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, RTileIn<C> & in)
+{
+    constexpr int ROWS = RTileIn<C>::ROWS;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
+    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
+    const RPtrs P = rtile_ptrs<C>(F, x0, j0, lane);
+    load_rtile_p<C, FULL>(F, P.rgb, nValid, nRows, in);
 }
 
 /* SWAP: B precedes R in memory; COPYA: the alpha plane receives the pixel's alpha (else it is filled with yuvMax) -- both are
  * call constants, resolved by the warp-uniform dispatch in convert_store_rtile so that the pixel loop carries no selects */
 template <class C, bool FULL, bool SWAP, bool COPYA, bool YFULL>
-__device__ __forceinline__ void convert_store_rtile_body(const AbR2YJob & J, const AbR2YFrame & F, uint32_t x0, uint32_t j0, uint32_t lane, const RTileIn<C> & in)
+__device__ __forceinline__ void convert_store_rtile_p(const AbR2YJob & J, const AbR2YFrame & F, uint32_t px0, uint32_t j0, uint32_t nValidIn, uint32_t nRows,
+                                                      const RTileIn<C> & in)
 {
     using RT = typename C::RT;
     using YT = typename C::YT;
     constexpr int ROWS = RTileIn<C>::ROWS;
     constexpr bool fullTile = FULL;
-    const uint32_t px0 = x0 + 8 * lane;
-    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
+    const uint32_t nValid = FULL ? 8u : nValidIn;
     if (nValid == 0) return; /* no cross-lane traffic in this kernel */
-    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
 
     /* ---- per pixel: normalise, alpha, matrix (ref: src/reformat.c:311-387) ---- */
     const uint32_t K = J.magicK;
@@ -389,6 +429,7 @@ __device__ __forceinline__ void convert_store_rtile_body(const AbR2YJob & J, con
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
+        /* addresses are formed where they are used: carrying five row pointers would cost ten registers */
         store_samples8<YT, QC>(F.y + (int64_t)j * F.yRB, px0, ns, yq, mm);
         if (C::SUB == SUB_444) {
             store_samples8<YT, QC>(F.u + (int64_t)j * F.uRB, px0, ns, uq, mm);
@@ -426,9 +467,13 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
 {
     /* warp-uniform (block-uniform, launch-uniform) dispatch on three call constants; ragged edge tiles (FULL == false) are rare
      * and keep one body per channel order */
+    constexpr int ROWS = RTileIn<C>::ROWS;
+    const uint32_t px0 = x0 + 8 * lane;
+    const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
+    const uint32_t nRows = min((uint32_t)ROWS, F.height - j0);
     const bool copyA = (C::NCH == 4) && (J.alphaWrite == AB_ALPHA_COPY);
     const bool yFull = FULL && (J.biasY == 0.0f);
-#define AB_R2Y_BODY(SW, CA, YF) convert_store_rtile_body<C, FULL, SW, CA, YF>(J, F, x0, j0, lane, in)
+#define AB_R2Y_BODY(SW, CA, YF) convert_store_rtile_p<C, FULL, SW, CA, YF>(J, F, px0, j0, nValid, nRows, in)
     if (J.swapRB) {
         if (copyA) AB_R2Y_BODY(true, (C::NCH == 4), false);
         else AB_R2Y_BODY(true, false, false);
@@ -440,6 +485,113 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
         else AB_R2Y_BODY(false, false, false);
     }
 #undef AB_R2Y_BODY
+}
+
+/* ---- strip kernel ---------------------------------------------------------------------------------------------------
+ * Round-2 loop shape.  The group kernel below pays ~14 instructions per pixel for bookkeeping (ncu r02c, per source line: tile ->
+ * (row, column) by division, 64-bit address arithmetic for five streams at every tile, the register moves of "next tile becomes
+ * current"): a sixth of everything it executes.  Here a warp owns a CHUNK = one 256-pixel column strip x kRChunk consecutive
+ * row units: positions are derived once per chunk, then every stream advances by its row stride (one 64-bit add each), loads
+ * and stores use constant offsets from those pointers, and the prefetching loop is written out twice (two register sets that
+ * swap roles) so that nothing is moved.  Chunks are numbered row-major (adjacent strips of one row band are adjacent ids) and
+ * dealt to the warps exactly like the groups of tiles before: group g = chunks 8g..8g+7, one per warp, blocks stride over the
+ * groups of their frame. */
+#ifndef AB_R2Y_STRIP
+#define AB_R2Y_STRIP 1
+#endif
+#ifndef AB_R2Y_CHUNK
+#define AB_R2Y_CHUNK 8
+#endif
+#ifndef AB_R2Y_PINGPONG /* 1: the prefetching loop written out twice (register sets swap roles); 0: "next becomes current" by register moves */
+#define AB_R2Y_PINGPONG 0
+#endif
+constexpr uint32_t kRChunk = AB_R2Y_CHUNK;
+
+template <class C, bool SWAP, bool COPYA, bool YFULL>
+__device__ __forceinline__ void r2y_strip_run(const AbR2YJob & J, const AbR2YFrame & F, uint32_t g0, uint32_t gStride, uint32_t warp, uint32_t lane)
+{
+    constexpr int ROWS = RTileIn<C>::ROWS;
+    const uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
+#pragma unroll 1
+    for (uint32_t g = g0; g < F.groups; g += gStride) {
+        const uint32_t c = g * kRWarps + warp;
+        if (c >= F.tiles) continue; /* warp-uniform */
+        const uint32_t cy = c / F.tilesX, sx = c - cy * F.tilesX;
+        const uint32_t x0 = sx * kRTile;
+        const uint32_t u0 = cy * kRChunk;
+        const uint32_t jEnd = F.rowBegin + min(u0 + kRChunk, units) * ROWS; /* first luma row after the chunk (may exceed the picture by one) */
+        uint32_t j = F.rowBegin + u0 * ROWS;
+        /* the position is (x0, j): addresses are re-derived where they are used (two multiply-adds each) instead of being
+         * carried in ten registers -- the two tile register sets already fill the budget of 4 blocks per SM */
+        auto rowsAt = [&](uint32_t jj) { return (ROWS == 1) ? 1u : min((uint32_t)ROWS, F.height - jj); };
+        auto rgbAt = [&](uint32_t jj) { return F.rgb + (int64_t)jj * F.rgbRB + (int64_t)(x0 + 8 * lane) * (C::NCH * (int)sizeof(typename C::RT)); };
+        RTileIn<C> a, b;
+        if (x0 + kRTile <= F.width && RLoop<C>::PLAIN) { /* tiles whose second register set does not fit: plain loop */
+            for (; j < jEnd; j += ROWS) {
+                load_rtile_p<C, true>(F, rgbAt(j), 8u, rowsAt(j), a);
+                convert_store_rtile_p<C, true, SWAP, COPYA, YFULL>(J, F, x0 + 8 * lane, j, 8u, rowsAt(j), a);
+            }
+        } else if (x0 + kRTile <= F.width) {
+            load_rtile_p<C, true>(F, rgbAt(j), 8u, rowsAt(j), a);
+#if AB_R2Y_PINGPONG
+            while (true) {
+                bool more = (j + ROWS < jEnd);
+                if (more) load_rtile_p<C, true>(F, rgbAt(j + ROWS), 8u, rowsAt(j + ROWS), b);
+                convert_store_rtile_p<C, true, SWAP, COPYA, YFULL>(J, F, x0 + 8 * lane, j, 8u, rowsAt(j), a);
+                if (!more) break;
+                j += ROWS;
+                more = (j + ROWS < jEnd);
+                if (more) load_rtile_p<C, true>(F, rgbAt(j + ROWS), 8u, rowsAt(j + ROWS), a);
+                convert_store_rtile_p<C, true, SWAP, COPYA, YFULL>(J, F, x0 + 8 * lane, j, 8u, rowsAt(j), b);
+                if (!more) break;
+                j += ROWS;
+            }
+#else
+#pragma unroll 1
+            for (;;) {
+                const bool more = (j + ROWS < jEnd);
+                if (more) load_rtile_p<C, true>(F, rgbAt(j + ROWS), 8u, rowsAt(j + ROWS), b);
+                convert_store_rtile_p<C, true, SWAP, COPYA, YFULL>(J, F, x0 + 8 * lane, j, 8u, rowsAt(j), a);
+                if (!more) break;
+                j += ROWS;
+                a = b;
+            }
+#endif
+        } else { /* ragged last strip of the picture: no prefetch */
+            const uint32_t px0 = x0 + 8 * lane;
+            const uint32_t nValid = (px0 < F.width) ? min(8u, F.width - px0) : 0u;
+            for (; j < jEnd; j += ROWS) {
+                load_rtile_p<C, false>(F, rgbAt(j), nValid, rowsAt(j), a);
+                convert_store_rtile_p<C, false, SWAP, COPYA, false>(J, F, px0, j, nValid, rowsAt(j), a);
+            }
+        }
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_strip_kernel(const __grid_constant__ AbR2YBatch B)
+{
+    const AbR2YJob & J = B.common;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f; /* block-uniform, once per block */
+    const AbR2YFrame & F = B.frame[f];
+    const uint32_t gStride = F.blocks;
+    const uint32_t g0 = blockIdx.x - F.blockStart;
+    if (g0 >= F.groups) return;
+    /* launch-uniform dispatch on three call constants: each combination is its own straight-line loop */
+    const bool copyA = (C::NCH == 4) && (J.alphaWrite == AB_ALPHA_COPY);
+    const bool yFull = (J.biasY == 0.0f);
+    if (J.swapRB) {
+        if (copyA) r2y_strip_run<C, true, (C::NCH == 4), false>(J, F, g0, gStride, warp, lane);
+        else r2y_strip_run<C, true, false, false>(J, F, g0, gStride, warp, lane);
+    } else if (copyA) {
+        if (yFull) r2y_strip_run<C, false, (C::NCH == 4), true>(J, F, g0, gStride, warp, lane);
+        else r2y_strip_run<C, false, (C::NCH == 4), false>(J, F, g0, gStride, warp, lane);
+    } else {
+        if (yFull) r2y_strip_run<C, false, false, true>(J, F, g0, gStride, warp, lane);
+        else r2y_strip_run<C, false, false, false>(J, F, g0, gStride, warp, lane);
+    }
 }
 
 /* Persistent, software-pipelined and batched like y2r_fast_kernel: a block strides over groups of 8 consecutive tiles of one
@@ -608,7 +760,8 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbR2YFrame & F = B.frame[f];
-        const uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
+        uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
+        if (AB_R2Y_STRIP) units = (units + kRChunk - 1) / kRChunk; /* work items are chunks of kRChunk row units */
         F.tilesX = (F.width + kRTile - 1) / kRTile;
         F.tiles = F.tilesX * units;
         F.groups = (F.tiles + kRWarps - 1) / kRWarps;
@@ -622,13 +775,15 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
     if (!resident) {
         int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
+        if (AB_R2Y_STRIP) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_strip_kernel<C>, kRWarps * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);
-    r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
+    if (AB_R2Y_STRIP) r2y_strip_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
+    else r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
     return 1;
 }
 

@@ -151,6 +151,7 @@ typedef struct AbCtx {
     uint8_t * ring;
     size_t ringSlotBytes;
     cudaEvent_t evRing[AB_RING_SLOTS];
+    struct AbHelperPool * helpers; /* host threads that share the staging copies of this context (stagingHelpers) */
 } AbCtx;
 
 typedef struct AbThread {
@@ -370,6 +371,8 @@ static pthread_mutex_t gPolicyLock = PTHREAD_MUTEX_INITIALIZER;
 static pthread_key_t gThreadKey;
 static pthread_once_t gThreadKeyOnce = PTHREAD_ONCE_INIT;
 
+struct AbHelperPool;
+static void helpersDestroy(struct AbHelperPool * pool);
 static void ctxDestroy(AbCtx * c)
 {
     if (!c->ready) return;
@@ -393,6 +396,7 @@ static void ctxDestroy(AbCtx * c)
         if (c->arena) (void)cudaFree(c->arena);
         if (c->ring) (void)cudaFreeHost(c->ring);
     }
+    helpersDestroy(c->helpers);
     (void)cudaGetLastError(); /* e.g. cudaErrorCudartUnloading while the process is going down */
     memset(c, 0, sizeof(*c));
     if (prev >= 0) (void)cudaSetDevice(prev);
@@ -814,11 +818,167 @@ static void copyStreaming(uint8_t * dst, const uint8_t * src, size_t n)
 static void copyStreaming(uint8_t * dst, const uint8_t * src, size_t n) { memcpy(dst, src, n); }
 #endif
 
+/* ---- helper threads of the staging copies ------------------------------------------------------------------------
+ * One host thread copies ~6 GB/s between pageable memory and the pinned ring, an eighth of what the copy engines move.  The
+ * reference lets a caller spend rgb->maxThreads threads on a conversion (src/reformat.c:1679-1747); here the extra threads
+ * (maxThreads - 1, at most AB_MAX_HELPERS; AVIF_B200_STAGE_THREADS overrides) share every chunk copy of the call: rows are cut
+ * into equal slices, the calling thread takes the first.  The pool belongs to the (thread, device) context and dies with it. */
+#define AB_MAX_HELPERS 7
+typedef struct AbHelperPool {
+    int n;
+    pthread_t th[AB_MAX_HELPERS];
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    unsigned gen; /* job generation, written under mu, also polled */
+    int stop;
+    /* the job: a 2-D copy cut into `parts` row slices; helper k takes slice k + 1 */
+    uint8_t * dst;
+    const uint8_t * src;
+    size_t dstPitch, srcPitch, rowBytes;
+    uint32_t rows;
+    int parts;
+    int done; /* helpers that finished the current job */
+} AbHelperPool;
+typedef struct AbHelperArg {
+    AbHelperPool * pool;
+    int index;
+} AbHelperArg;
+
+static void copyRows(uint8_t * dst, size_t dstPitch, const uint8_t * src, size_t srcPitch, size_t rowBytes, uint32_t r0, uint32_t r1)
+{
+    if (r1 <= r0) return;
+    if (dstPitch == srcPitch && rowBytes == dstPitch) { /* dense rows: one run (row padding, where there is any, is never written) */
+        copyStreaming(dst + (size_t)r0 * dstPitch, src + (size_t)r0 * srcPitch, dstPitch * (r1 - r0));
+        return;
+    }
+    for (uint32_t k = r0; k < r1; ++k) copyStreaming(dst + (size_t)k * dstPitch, src + (size_t)k * srcPitch, rowBytes);
+}
+
+static void * helperMain(void * p)
+{
+    AbHelperArg * arg = (AbHelperArg *)p;
+    AbHelperPool * pool = arg->pool;
+    const int index = arg->index;
+    free(arg);
+    unsigned seen = 0;
+    for (;;) {
+        /* jobs of one call follow each other within microseconds: poll briefly before sleeping */
+        int spins = 0;
+        while (__atomic_load_n(&pool->gen, __ATOMIC_ACQUIRE) == seen && !__atomic_load_n(&pool->stop, __ATOMIC_ACQUIRE) && spins < 20000) {
+            ++spins;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        pthread_mutex_lock(&pool->mu);
+        while (pool->gen == seen && !pool->stop) pthread_cond_wait(&pool->cv, &pool->mu);
+        if (pool->stop) {
+            pthread_mutex_unlock(&pool->mu);
+            return NULL;
+        }
+        seen = pool->gen;
+        uint8_t * dst = pool->dst;
+        const uint8_t * src = pool->src;
+        const size_t dp = pool->dstPitch, sp = pool->srcPitch, rb = pool->rowBytes;
+        const uint32_t rows = pool->rows;
+        const int parts = pool->parts;
+        pthread_mutex_unlock(&pool->mu);
+        if (index + 1 < parts) {
+            const uint32_t r0 = (uint32_t)((uint64_t)rows * (uint32_t)(index + 1) / (uint32_t)parts);
+            const uint32_t r1 = (uint32_t)((uint64_t)rows * (uint32_t)(index + 2) / (uint32_t)parts);
+            copyRows(dst, dp, src, sp, rb, r0, r1);
+        }
+        __atomic_add_fetch(&pool->done, 1, __ATOMIC_RELEASE);
+    }
+}
+
+static void helpersDestroy(AbHelperPool * pool)
+{
+    if (!pool) return;
+    pthread_mutex_lock(&pool->mu);
+    pool->stop = 1;
+    pthread_cond_broadcast(&pool->cv);
+    pthread_mutex_unlock(&pool->mu);
+    for (int k = 0; k < pool->n; ++k) pthread_join(pool->th[k], NULL);
+    pthread_mutex_destroy(&pool->mu);
+    pthread_cond_destroy(&pool->cv);
+    free(pool);
+}
+
+/* how many helper threads the call in progress may use (set by the conversion entry points from rgb->maxThreads) */
+static _Thread_local int tlsStageHelpers = 0;
+static int stageHelperCount(int maxThreads)
+{
+    static int envCount = -2;
+    if (envCount == -2) {
+        const char * e = getenv("AVIF_B200_STAGE_THREADS");
+        envCount = (e && *e) ? atoi(e) : -1;
+    }
+    int n = ((envCount >= 0) ? envCount : maxThreads) - 1;
+    if (n < 0) n = 0;
+    return n > AB_MAX_HELPERS ? AB_MAX_HELPERS : n;
+}
+
+static void helpersEnsure(int want)
+{
+    if (want <= 0) return;
+    AbHelperPool * pool = cx->helpers;
+    if (!pool) {
+        pool = (AbHelperPool *)calloc(1, sizeof(AbHelperPool));
+        if (!pool) return;
+        pthread_mutex_init(&pool->mu, NULL);
+        pthread_cond_init(&pool->cv, NULL);
+        cx->helpers = pool;
+    }
+    while (pool->n < want) {
+        AbHelperArg * arg = (AbHelperArg *)malloc(sizeof(AbHelperArg));
+        if (!arg) return;
+        arg->pool = pool;
+        arg->index = pool->n;
+        if (pthread_create(&pool->th[pool->n], NULL, helperMain, arg) != 0) {
+            free(arg);
+            return;
+        }
+        ++pool->n;
+    }
+}
+
+/* 2-D host copy shared with the context's helper threads */
+static void copyRowsShared(uint8_t * dst, size_t dstPitch, const uint8_t * src, size_t srcPitch, size_t rowBytes, uint32_t rows)
+{
+    AbHelperPool * pool = cx->helpers;
+    int helpers = tlsStageHelpers;
+    if (pool && helpers > pool->n) helpers = pool->n;
+    if (!pool || helpers <= 0 || rows < 8 || (size_t)rows * rowBytes < ((size_t)256 << 10)) {
+        copyRows(dst, dstPitch, src, srcPitch, rowBytes, 0, rows);
+        return;
+    }
+    pthread_mutex_lock(&pool->mu);
+    pool->dst = dst;
+    pool->src = src;
+    pool->dstPitch = dstPitch;
+    pool->srcPitch = srcPitch;
+    pool->rowBytes = rowBytes;
+    pool->rows = rows;
+    pool->parts = helpers + 1;
+    __atomic_store_n(&pool->done, 0, __ATOMIC_RELAXED);
+    __atomic_add_fetch(&pool->gen, 1, __ATOMIC_RELEASE);
+    pthread_cond_broadcast(&pool->cv);
+    pthread_mutex_unlock(&pool->mu);
+    copyRows(dst, dstPitch, src, srcPitch, rowBytes, 0, (uint32_t)((uint64_t)rows / (uint32_t)(helpers + 1)));
+    while (__atomic_load_n(&pool->done, __ATOMIC_ACQUIRE) < pool->n) { /* every helper acknowledges every job */
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
 static avifResult stagedUpload(const AbRegion * r, uint32_t row0, uint32_t row1, cudaStream_t st)
 {
     const size_t pitch = (size_t)r->devRB; /* the chunk mirrors the arena layout: one 1-D DMA per chunk */
     avifResult res = ringReserve(pitch);
     if (res != AVIF_RESULT_OK) return res;
+    helpersEnsure(tlsStageHelpers);
     const uint32_t perChunk = (uint32_t)(cx->ringSlotBytes / pitch);
     for (uint32_t row = row0; row < row1; row += perChunk) {
         const uint32_t n = (row1 - row < perChunk) ? row1 - row : perChunk;
@@ -826,11 +986,7 @@ static avifResult stagedUpload(const AbRegion * r, uint32_t row0, uint32_t row1,
         uint8_t * chunk = cx->ring + (size_t)slot * cx->ringSlotBytes;
         AB_CUDA(cudaEventSynchronize(cx->evRing[slot])); /* the DMA that last used this chunk */
         const uint8_t * src = r->user + (int64_t)row * r->userRB;
-        if ((size_t)r->userRB == pitch) {
-            copyStreaming(chunk, src, pitch * (n - 1) + r->rowUsed);
-        } else {
-            for (uint32_t k = 0; k < n; ++k) copyStreaming(chunk + (size_t)k * pitch, src + (int64_t)k * r->userRB, r->rowUsed);
-        }
+        copyRowsShared(chunk, pitch, src, (size_t)r->userRB, r->rowUsed, n);
         AB_CUDA(cudaMemcpyAsync(r->dev + (size_t)row * pitch, chunk, pitch * (n - 1) + r->rowUsed, cudaMemcpyHostToDevice, st));
         AB_CUDA(cudaEventRecord(cx->evRing[slot], st));
     }
@@ -843,6 +999,7 @@ static avifResult stagedDownload(const AbRegion * r, uint32_t row0, uint32_t row
     const size_t pitch = (size_t)r->devRB;
     avifResult res = ringReserve(pitch);
     if (res != AVIF_RESULT_OK) return res;
+    helpersEnsure(tlsStageHelpers);
     const uint32_t perChunk = (uint32_t)(cx->ringSlotBytes / pitch);
     struct { uint32_t row, n; unsigned slot; } pending[AB_RING_SLOTS];
     int head = 0, count = 0;
@@ -871,11 +1028,7 @@ static avifResult stagedDownload(const AbRegion * r, uint32_t row0, uint32_t row
         AB_CUDA(cudaEventSynchronize(cx->evRing[slot]));
         const uint8_t * chunk = cx->ring + (size_t)slot * cx->ringSlotBytes;
         uint8_t * dst = r->user + (int64_t)prow * r->userRB;
-        if ((size_t)r->userRB == pitch) {
-            copyStreaming(dst, chunk, pitch * (pn - 1) + r->rowUsed);
-        } else {
-            for (uint32_t k = 0; k < pn; ++k) copyStreaming(dst + (int64_t)k * r->userRB, chunk + (size_t)k * pitch, r->rowUsed);
-        }
+        copyRowsShared(dst, (size_t)r->userRB, chunk, pitch, r->rowUsed, pn);
     }
     return AVIF_RESULT_OK;
 }
@@ -1769,6 +1922,7 @@ static avifResult yuvToRgbCommon(const avifImage * image, avifRGBImage * rgb, vo
     res = ctxEnter(&sc, deviceOfImages(image, rgb));
     if (res != AVIF_RESULT_OK) return res;
     __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    tlsStageHelpers = stageHelperCount(rgb->maxThreads);
     res = yuvToRgbBody(image, rgb, NULL, 0, job, &plan);
     __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
     return ctxLeave(&sc, res);
@@ -2062,6 +2216,7 @@ static avifResult rgbToYuvCommon(avifImage * image, const avifRGBImage * rgb, vo
     res = ctxEnter(&sc, deviceOfImages(image, rgb));
     if (res != AVIF_RESULT_OK) return res;
     __atomic_add_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
+    tlsStageHelpers = stageHelperCount(rgb->maxThreads);
     res = rgbToYuvBody(image, rgb, NULL, 0, job, &plan);
     __atomic_sub_fetch(&gHostCallsInFlight, 1, __ATOMIC_RELAXED);
     return ctxLeave(&sc, res);

@@ -20,107 +20,120 @@ namespace {
 
 __device__ __forceinline__ float clamp01(float v) { return (v < 0.0f) ? 0.0f : ((1.0f < v) ? 1.0f : v); } /* AVIF_CLAMP */
 
+/* The reference calls the host libm (glibc: powf / exp2f / expf / logf / log10f, each correctly rounded in all but rare cases);
+ * CUDA's single-precision versions are good to 1-2 ulp, which moves an 8..12-bit output code by at most one but a 16-bit code
+ * by several (PQ raises to the 78.84th power).  P = true evaluates the function in double and rounds once: the correctly rounded
+ * float except within ~2^-29 of a rounding boundary, i.e. the value glibc returns.  Used for the per-code tables (65536 entries at
+ * most: free) and, when the output has 16-bit channels, for the per-pixel output transfer function. */
+template <bool P> __device__ __forceinline__ float xpow(float a, float b) { return P ? (float)pow((double)a, (double)b) : powf(a, b); }
+template <bool P> __device__ __forceinline__ float xexp2(float a) { return P ? (float)exp2((double)a) : exp2f(a); }
+template <bool P> __device__ __forceinline__ float xexp(float a) { return P ? (float)exp((double)a) : expf(a); }
+template <bool P> __device__ __forceinline__ float xlog(float a) { return P ? (float)log((double)a) : logf(a); }
+template <bool P> __device__ __forceinline__ float xlog10(float a) { return P ? (float)log10((double)a) : log10f(a); }
+
 /* src/colr.c:216-467; id = avifTransferCharacteristics; unknown ids take BT.709 (:497, :508) */
+template <bool P>
 __device__ float to_linear(int id, float g)
 {
     switch (id) {
-        case 4: return powf(clamp01(g), 2.2f);
-        case 5: return powf(clamp01(g), 2.8f);
+        case 4: return xpow<P>(clamp01(g), 2.2f);
+        case 5: return xpow<P>(clamp01(g), 2.8f);
         case 7:
             if (g < 0.0f) return 0.0f;
             if (g < __fmul_rn(4.0f, 0.022821585529445f)) return __fdiv_rn(g, 4.0f);
-            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.111572195921731f), 1.111572195921731f), __fdiv_rn(1.0f, 0.45f));
+            if (g < 1.0f) return xpow<P>(__fdiv_rn(__fadd_rn(g, 0.111572195921731f), 1.111572195921731f), __fdiv_rn(1.0f, 0.45f));
             return 1.0f;
         case 8: return clamp01(g);
-        case 9: return (g <= 0.0f) ? __fdiv_rn(0.01f, 2.0f) : powf(10.0f, __fmul_rn(2.0f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
-        case 10: return (g <= 0.0f) ? __fdiv_rn(0.00316227766f, 2.0f) : powf(10.0f, __fmul_rn(2.5f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
+        case 9: return (g <= 0.0f) ? __fdiv_rn(0.01f, 2.0f) : xpow<P>(10.0f, __fmul_rn(2.0f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
+        case 10: return (g <= 0.0f) ? __fdiv_rn(0.00316227766f, 2.0f) : xpow<P>(10.0f, __fmul_rn(2.5f, __fsub_rn(fminf(g, 1.0f), 1.0f)));
         case 11:
-            if (g < __fmul_rn(-4.5f, 0.018053968510807f)) return -powf(__fdiv_rn(__fsub_rn(g, 0.09929682680944f), -1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            if (g < __fmul_rn(-4.5f, 0.018053968510807f)) return -xpow<P>(__fdiv_rn(__fsub_rn(g, 0.09929682680944f), -1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
             if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
-            return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            return xpow<P>(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
         case 12:
             if (g < -0.25f) return -0.25f;
-            if (g < 0.0f) return __fdiv_rn(powf(__fdiv_rn(__fsub_rn(g, 0.02482420670236f), -0.27482420670236f), __fdiv_rn(1.0f, 0.45f)), -4.0f);
+            if (g < 0.0f) return __fdiv_rn(xpow<P>(__fdiv_rn(__fsub_rn(g, 0.02482420670236f), -0.27482420670236f), __fdiv_rn(1.0f, 0.45f)), -4.0f);
             if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
-            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            if (g < 1.0f) return xpow<P>(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
             return 1.0f;
         case 13:
             if (g < 0.0f) return 0.0f;
             if (g < __fmul_rn(12.92f, 0.0030412825601275209f)) return __fdiv_rn(g, 12.92f);
-            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.0550107189475866f), 1.0550107189475866f), 2.4f);
+            if (g < 1.0f) return xpow<P>(__fdiv_rn(__fadd_rn(g, 0.0550107189475866f), 1.0550107189475866f), 2.4f);
             return 1.0f;
         case 16: {
             if (!(g > 0.0f)) return 0.0f;
-            const float pg = powf(g, __fdiv_rn(1.0f, 78.84375f));
+            const float pg = xpow<P>(g, __fdiv_rn(1.0f, 78.84375f));
             const float num = fmaxf(__fsub_rn(pg, 0.8359375f), 0.0f);
             const float den = fmaxf(__fsub_rn(18.8515625f, __fmul_rn(18.6875f, pg)), 1.17549435e-38f);
-            const float lin = powf(__fdiv_rn(num, den), __fdiv_rn(1.0f, 0.1593017578125f));
+            const float lin = xpow<P>(__fdiv_rn(num, den), __fdiv_rn(1.0f, 0.1593017578125f));
             return __fdiv_rn(__fmul_rn(lin, 10000.0f), 203.0f);
         }
-        case 17: return __fdiv_rn(powf(fmaxf(g, 0.0f), 2.6f), 0.91655527974030934f);
+        case 17: return __fdiv_rn(xpow<P>(fmaxf(g, 0.0f), 2.6f), 0.91655527974030934f);
         case 18: {
             if (g < 0.0f) return 0.0f;
             float lin;
-            if (g <= 0.5f) lin = powf(__fmul_rn(__fmul_rn(g, g), __fdiv_rn(1.0f, 3.0f)), 1.2f);
-            else lin = powf(__fdiv_rn(__fadd_rn(expf(__fdiv_rn(__fsub_rn(g, 0.55991073f), 0.17883277f)), 0.28466892f), 12.0f), 1.2f);
+            if (g <= 0.5f) lin = xpow<P>(__fmul_rn(__fmul_rn(g, g), __fdiv_rn(1.0f, 3.0f)), 1.2f);
+            else lin = xpow<P>(__fdiv_rn(__fadd_rn(xexp<P>(__fdiv_rn(__fsub_rn(g, 0.55991073f), 0.17883277f)), 0.28466892f), 12.0f), 1.2f);
             return __fdiv_rn(__fmul_rn(lin, 1000.0f), 203.0f);
         }
         default: /* 1, 6, 14, 15 and everything unknown: BT.709 */
             if (g < 0.0f) return 0.0f;
             if (g < __fmul_rn(4.5f, 0.018053968510807f)) return __fdiv_rn(g, 4.5f);
-            if (g < 1.0f) return powf(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
+            if (g < 1.0f) return xpow<P>(__fdiv_rn(__fadd_rn(g, 0.09929682680944f), 1.09929682680944f), __fdiv_rn(1.0f, 0.45f));
             return 1.0f;
     }
 }
 
+template <bool P>
 __device__ float to_gamma(int id, float l)
 {
     switch (id) {
-        case 4: return powf(clamp01(l), __fdiv_rn(1.0f, 2.2f));
-        case 5: return powf(clamp01(l), __fdiv_rn(1.0f, 2.8f));
+        case 4: return xpow<P>(clamp01(l), __fdiv_rn(1.0f, 2.2f));
+        case 5: return xpow<P>(clamp01(l), __fdiv_rn(1.0f, 2.8f));
         case 7:
             if (l < 0.0f) return 0.0f;
             if (l < 0.022821585529445f) return __fmul_rn(l, 4.0f);
-            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.111572195921731f, powf(l, 0.45f)), 0.111572195921731f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.111572195921731f, xpow<P>(l, 0.45f)), 0.111572195921731f);
             return 1.0f;
         case 8: return clamp01(l);
-        case 9: return (l <= 0.01f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(log10f(fminf(l, 1.0f)), 2.0f));
-        case 10: return (l <= 0.00316227766f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(log10f(fminf(l, 1.0f)), 2.5f));
+        case 9: return (l <= 0.01f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(xlog10<P>(fminf(l, 1.0f)), 2.0f));
+        case 10: return (l <= 0.00316227766f) ? 0.0f : __fadd_rn(1.0f, __fdiv_rn(xlog10<P>(fminf(l, 1.0f)), 2.5f));
         case 11:
-            if (l < -0.018053968510807f) return __fadd_rn(__fmul_rn(-1.09929682680944f, powf(-l, 0.45f)), 0.09929682680944f);
+            if (l < -0.018053968510807f) return __fadd_rn(__fmul_rn(-1.09929682680944f, xpow<P>(-l, 0.45f)), 0.09929682680944f);
             if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
-            return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+            return __fsub_rn(__fmul_rn(1.09929682680944f, xpow<P>(l, 0.45f)), 0.09929682680944f);
         case 12:
             if (l < -0.25f) return -0.25f;
-            if (l < 0.0f) return __fadd_rn(__fmul_rn(-0.27482420670236f, powf(__fmul_rn(-4.0f, l), 0.45f)), 0.02482420670236f);
+            if (l < 0.0f) return __fadd_rn(__fmul_rn(-0.27482420670236f, xpow<P>(__fmul_rn(-4.0f, l), 0.45f)), 0.02482420670236f);
             if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
-            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, xpow<P>(l, 0.45f)), 0.09929682680944f);
             return 1.0f;
         case 13:
             if (l < 0.0f) return 0.0f;
             if (l < 0.0030412825601275209f) return __fmul_rn(l, 12.92f);
-            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.0550107189475866f, powf(l, __fdiv_rn(1.0f, 2.4f))), 0.0550107189475866f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.0550107189475866f, xpow<P>(l, __fdiv_rn(1.0f, 2.4f))), 0.0550107189475866f);
             return 1.0f;
         case 16: {
             if (!(l > 0.0f)) return 0.0f;
             const float s = clamp01(__fdiv_rn(__fmul_rn(l, 203.0f), 10000.0f));
-            const float pl = powf(s, 0.1593017578125f);
+            const float pl = xpow<P>(s, 0.1593017578125f);
             const float num = __fsub_rn(__fmul_rn(0.1640625f, pl), 0.1640625f);
             const float den = __fadd_rn(1.0f, __fmul_rn(18.6875f, pl));
-            return powf(__fadd_rn(1.0f, __fdiv_rn(num, den)), 78.84375f);
+            return xpow<P>(__fadd_rn(1.0f, __fdiv_rn(num, den)), 78.84375f);
         }
-        case 17: return powf(__fmul_rn(0.91655527974030934f, fmaxf(l, 0.0f)), __fdiv_rn(1.0f, 2.6f));
+        case 17: return xpow<P>(__fmul_rn(0.91655527974030934f, fmaxf(l, 0.0f)), __fdiv_rn(1.0f, 2.6f));
         case 18: {
             float s = clamp01(__fdiv_rn(__fmul_rn(l, 203.0f), 1000.0f));
-            s = powf(s, __fdiv_rn(1.0f, 1.2f));
+            s = xpow<P>(s, __fdiv_rn(1.0f, 1.2f));
             if (s < 0.0f) return 0.0f;
             if (s <= __fdiv_rn(1.0f, 12.0f)) return sqrtf(__fmul_rn(3.0f, s));
-            return __fadd_rn(__fmul_rn(0.17883277f, logf(__fsub_rn(__fmul_rn(12.0f, s), 0.28466892f))), 0.55991073f);
+            return __fadd_rn(__fmul_rn(0.17883277f, xlog<P>(__fsub_rn(__fmul_rn(12.0f, s), 0.28466892f))), 0.55991073f);
         }
         default:
             if (l < 0.0f) return 0.0f;
             if (l < 0.018053968510807f) return __fmul_rn(l, 4.5f);
-            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, powf(l, 0.45f)), 0.09929682680944f);
+            if (l < 1.0f) return __fsub_rn(__fmul_rn(1.09929682680944f, xpow<P>(l, 0.45f)), 0.09929682680944f);
             return 1.0f;
     }
 }
@@ -212,18 +225,19 @@ __global__ void __launch_bounds__(256) tone_lut_kernel(const __grid_constant__ A
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < J.baseLutN) {
-        J.baseLut[i] = to_linear(J.tfIn, code_value(i, J.baseFmt));
+        J.baseLut[i] = to_linear<true>(J.tfIn, code_value(i, J.baseFmt));
         return;
     }
     const uint32_t k = i - J.baseLutN;
     if (k < 3u * J.gainLutN) {
         const uint32_t c = k / J.gainLutN, code = k - c * J.gainLutN;
-        const float w = powf(code_value(code, J.gainFmt), J.gammaInv[c]);
+        const float w = xpow<true>(code_value(code, J.gainFmt), J.gammaInv[c]);
         const float log2g = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, w), J.gmMin[c]), __fmul_rn(w, J.gmMax[c])); /* lerp, src/gainmap.c:66-69 */
-        J.gainLut[k] = exp2f(__fmul_rn(log2g, J.weight));
+        J.gainLut[k] = xexp2<true>(__fmul_rn(log2g, J.weight));
     }
 }
 
+template <bool P>
 __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ AbToneMapJob J)
 {
     const uint64_t total = (uint64_t)J.width * J.height;
@@ -241,10 +255,10 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
         if (!J.applyGain) { /* src/gainmap.c:152-167 */
             if (J.transcode) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear(J.tfIn, code_value(bc[c], J.baseFmt));
+                for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear<P>(J.tfIn, code_value(bc[c], J.baseFmt));
                 if (J.inConv) convert_primaries(base, J.inM);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) base[c] = fminf(1.0f, fmaxf(0.0f, to_gamma(J.tfOut, base[c])));
+                for (int c = 0; c < 3; ++c) base[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, base[c])));
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) base[c] = code_value(bc[c], J.baseFmt);
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
             uint32_t gc[4];
             load_codes(J.gain + (int64_t)y * J.gainRB, x, J.gainFmt, gc);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear(J.tfIn, code_value(bc[c], J.baseFmt));
+            for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear<P>(J.tfIn, code_value(bc[c], J.baseFmt));
             if (J.inConv) convert_primaries(base, J.inM);
             float pixelMax = 0.0f;
 #pragma unroll
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 bad = bad || isnan(out[c]);
-                out[c] = fminf(1.0f, fmaxf(0.0f, to_gamma(J.tfOut, out[c])));
+                out[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, out[c])));
             }
             if (bad && (uint32_t)i < localNan) localNan = (uint32_t)i;
             out[3] = base[3];
@@ -321,6 +335,9 @@ extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
     if (blocks > 148u * 16u) blocks = 148u * 16u; /* grid-stride: 8 resident blocks per SM, two waves */
     const uint32_t lutN = job->baseLutN + 3u * job->gainLutN;
     if (lutN) tone_lut_kernel<<<(lutN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*job);
-    tone_map_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
+    /* 16-bit integer channels resolve the last ulp of the output transfer function: evaluate it in double there */
+    const bool precise = (job->outFmt.chanBytes > 1 && !job->outFmt.isFloat && job->outFmt.maxF > 4095.5f);
+    if (precise) tone_map_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
+    else tone_map_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
     return (int)cudaGetLastError();
 }

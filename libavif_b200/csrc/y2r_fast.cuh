@@ -38,15 +38,19 @@ using namespace ab;
 
 enum { CH_FULL = 1, CH_NEAREST = 2, CH_BIL420 = 3, CH_BIL422 = 4 };
 
-template <typename YT_, typename RT_, int CHROMA_, int NCH_, bool AFIRST_, int AW_, int AM_>
+enum { OUT_INT = 0, OUT_F16 = 1, OUT_565 = 2 };
+
+template <typename YT_, typename RT_, int CHROMA_, int NCH_, bool AFIRST_, int AW_, int AM_, int OUT_ = OUT_INT>
 struct Cfg {
     using YT = YT_;
     using RT = RT_;
     static constexpr int CHROMA = CHROMA_; /* CH_* */
-    static constexpr int NCH = NCH_;       /* 3 or 4 channels */
+    static constexpr int NCH = NCH_;       /* 3 or 4 channels (RGB565: 3 computed, one 16-bit word stored) */
     static constexpr bool AFIRST = AFIRST_; /* alpha stored before colour */
     static constexpr int AW = AW_;         /* AB_ALPHA_FILL / AB_ALPHA_COPY (NCH == 4) */
     static constexpr int AM = AM_;         /* AB_MUL_* */
+    static constexpr int OUT = OUT_;       /* OUT_INT: integer codes; OUT_F16: half floats (src/reformat.c:1419-1443, RT = u16);
+                                              OUT_565: RGB565 words (src/reformat.c:619, RT = u8, NCH = 3) */
 };
 
 constexpr int kTile = 256;
@@ -206,8 +210,11 @@ struct TileTraits {
     static constexpr bool BIL = (C::CHROMA == CH_BIL420 || C::CHROMA == CH_BIL422);
     static constexpr int ROWS = (C::CHROMA == CH_BIL420) ? 2 : 1;
     static constexpr int CROWS = ROWS;
-    static constexpr int PIXB = C::NCH * (int)sizeof(RT);
+    static constexpr int PIXB = (C::OUT == OUT_565) ? 2 : C::NCH * (int)sizeof(RT);
     static constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
+    /* alpha plane depth != channel depth (src/alpha.c:93-97).  The specialised kernels meet it exactly when the containers
+     * differ (8-bit planes into 16-bit channels or the reverse); equal containers of different depth stay on the general kernel */
+    static constexpr bool RESC = HAS_A && (sizeof(YT) != sizeof(RT));
     static constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
     static constexpr int CW = SUB ? 2 : 4; /* words of one chroma row of the lane */
 };
@@ -415,6 +422,15 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
             Bv = clamp01f(Bv);
             float am = 0.0f; /* alpha sample as magic float */
             if (NEED_A) am = magic_sample<YT>(in.aw[r], t, K);
+            float qaCopy = am; /* what the alpha channel receives when it is copied */
+            if (T::RESC) {
+                /* ref: src/alpha.c:93-97 -- clamp((int)(0.5f + (a / srcMaxF) * dstMaxF), dstMax) on the raw sample.  8-bit samples
+                 * give a / 255 in [0,1], where the fused form is the proven one (AB_Y2R_QFMA); 16-bit containers may hold more than
+                 * srcMax, so the product keeps its own rounding there */
+                const float an = div_int(__fsub_rn(am, magicOne), J.yuvMaxDiv);
+                const float tt = (AB_Y2R_QFMA && sizeof(YT) == 1) ? __fmaf_rn(an, J.rgbMaxF, 0.5f) : __fadd_rn(0.5f, __fmul_rn(an, J.rgbMaxF));
+                qaCopy = __fadd_rz(fminf(tt, __fadd_rn(J.rgbMaxF, 0.5f)), magicOne);
+            }
             if (C::AM == AB_MUL_FLOAT_MUL || C::AM == AB_MUL_FLOAT_UNMUL) { /* ref: src/reformat.c:894-947 */
                 const float ac = (sizeof(YT) == 2) ? fminf(am, magicMax) : am;
                 const float Ac = clamp01f(div_int(__fsub_rn(ac, magicOne), J.yuvMaxDiv));
@@ -442,18 +458,18 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 /* a >= max leaves the code untouched and a == 0 zeroes it (src/alpha.c:180-186).  Both fall out of the
                  * arithmetic with a clamped to max: floor(RN(RN(c*max)/max) + 0.5) == c for every code c (the product's
                  * rounding error is < 2^-9 of a code even at 16 bits), and c*0 is 0 -- no per-channel selects needed. */
-                const float ac = fminf(__fsub_rn(am, magicOne), J.rgbMaxF); /* raw (unclamped) alpha code: what the channel holds */
+                const float ac = fminf(__fsub_rn(qaCopy, magicOne), J.rgbMaxF); /* the alpha code the channel holds */
                 qr = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qr, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
                 qg = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qg, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
                 qb = __fadd_rz(__fadd_rn(divx(__fmul_rn(__fsub_rn(qb, magicOne), ac), J.rgbMaxDiv), 0.5f), magicOne);
             } else if (C::AM == AB_MUL_INT_PREMUL_FMA) { /* the same function of (c, a) for depths <= 12: pixel_math.cuh */
-                const float ac = fminf(__fsub_rn(am, magicOne), J.rgbMaxF);
+                const float ac = fminf(__fsub_rn(qaCopy, magicOne), J.rgbMaxF);
                 const float negA23 = __fmul_rn(ac, -8388608.0f);
                 qr = premul_fma_magic(qr, ac, negA23, J.pmR, J.pmK);
                 qg = premul_fma_magic(qg, ac, negA23, J.pmR, J.pmK);
                 qb = premul_fma_magic(qb, ac, negA23, J.pmR, J.pmK);
             } else if (C::AM == AB_MUL_INT_UNPREMUL) { /* ref: src/alpha.c:366-381 */
-                const float af = __fsub_rn(am, magicOne);
+                const float af = __fsub_rn(qaCopy, magicOne);
                 const bool opaque = (af >= J.rgbMaxF), zero = (af == 0.0f);
                 const float lim = __fadd_rn(J.rgbMaxF, 0.5f);
                 const float d = (opaque || zero) ? 1.0f : af;
@@ -465,7 +481,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
                 qg = opaque ? qg : (zero ? magicOne : pg);
                 qb = opaque ? qb : (zero ? magicOne : pb);
             }
-            const float qa = HAS_A ? am : __uint_as_float(0x4B000000u | J.rgbMax);
+            const float qa = HAS_A ? qaCopy : __uint_as_float(0x4B000000u | J.rgbMax);
             if (C::NCH == 3) {
                 ch[t][0] = qr; ch[t][1] = qg; ch[t][2] = qb; ch[t][3] = 0.0f;
             } else if (C::AFIRST) {
@@ -479,7 +495,23 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
         uint32_t words[NW];
 #pragma unroll
         for (int wi = 0; wi < NW; ++wi) {
-            if (sizeof(RT) == 2) {
+            if (C::OUT == OUT_F16) {
+                /* ref: src/reformat.c:1419-1443 -- every channel (alpha included): bits((float)code * (2^-112 / max)) >> 13, the
+                 * multiplier itself a denormal float (so -ftz=false matters); two halves per word */
+                const int v0 = 2 * wi, v1 = 2 * wi + 1;
+                const uint32_t b0 = __float_as_uint(__fmul_rn(__fsub_rn(ch[v0 / C::NCH][v0 % C::NCH], magicOne), J.f16mul));
+                const uint32_t b1 = __float_as_uint(__fmul_rn(__fsub_rn(ch[v1 / C::NCH][v1 % C::NCH], magicOne), J.f16mul));
+                words[wi] = ((b0 >> 13) & 0xFFFFu) | ((b1 << 3) & 0xFFFF0000u);
+            } else if (C::OUT == OUT_565) {
+                /* ref: RGB565 macro, src/reformat.c:619: ((B >> 3) | ((G >> 2) << 5) | ((R >> 3) << 11)); two pixels per word */
+                uint32_t px2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t R8 = __float_as_uint(ch[2 * wi + h][0]), G8 = __float_as_uint(ch[2 * wi + h][1]), B8 = __float_as_uint(ch[2 * wi + h][2]);
+                    px2[h] = ((B8 >> 3) & 0x1Fu) | ((G8 << 3) & 0x7E0u) | ((R8 << 8) & 0xF800u);
+                }
+                words[wi] = px2[0] | (px2[1] << 16);
+            } else if (sizeof(RT) == 2) {
                 const int v0 = 2 * wi, v1 = 2 * wi + 1;
                 words[wi] = __byte_perm(__float_as_uint(ch[v0 / C::NCH][v0 % C::NCH]), __float_as_uint(ch[v1 / C::NCH][v1 % C::NCH]), 0x5410u);
             } else {
@@ -946,10 +978,10 @@ static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups,
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT>
 static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
-    using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>;
+    using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT>;
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbY2RFrame & F = B.frame[f];
@@ -991,12 +1023,12 @@ static inline bool tma_aligned(const AbY2RBatch & B, bool needA)
     return true;
 }
 
-template <typename YT, typename RT, int NCH, bool AFIRST, int AW, int AM>
+template <typename YT, typename RT, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT>
 static int launch_cfg_staged(AbY2RBatch & B, cudaStream_t st)
 {
-    using C = Cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>;
+    using C = Cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM, OUT>;
     using L = StageLayout<C>;
-    if (!AB_Y2R_TMA || !tma_aligned(B, TileTraits<C>::NEED_A)) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>(B, st);
+    if (!AB_Y2R_TMA || OUT != OUT_INT || !tma_aligned(B, TileTraits<C>::NEED_A)) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM, OUT>(B, st);
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbY2RFrame & F = B.frame[f];
@@ -1019,17 +1051,48 @@ static int launch_cfg_staged(AbY2RBatch & B, cudaStream_t st)
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     /* the ring only pays when a warp sees several tiles: small launches keep one group per block on the plain kernel */
-    if (groups < 4u * (uint32_t)resident) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM>(B, st);
+    if (groups < 4u * (uint32_t)resident) return launch_cfg<YT, RT, CH_BIL420, NCH, AFIRST, AW, AM, OUT>(B, st);
     B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, (uint32_t)resident);
     y2r_fast_staged_kernel<C><<<B.totalBlocks, kWarps * 32, L::BLOCK_BYTES, st>>>(B);
     return 1;
 }
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT>
 static int launch_any(AbY2RBatch & B, cudaStream_t st)
 {
-    if constexpr (CHROMA == CH_BIL420) return launch_cfg_staged<YT, RT, NCH, AFIRST, AW, AM>(B, st);
-    else return launch_cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM>(B, st);
+    if constexpr (CHROMA == CH_BIL420 && OUT == OUT_INT && AB_Y2R_TMA) return launch_cfg_staged<YT, RT, NCH, AFIRST, AW, AM, OUT>(B, st);
+    else return launch_cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT>(B, st);
+}
+
+/* half-float and RGB565 outputs (Android's RGBA_F16 / RGB_565 bitmaps, android_jni/.../libavif_jni.cc:206-223): the combinations
+ * real callers use -- colour-first layouts, alpha filled, copied or (pre)multiplied the way the reference's variant requires */
+template <typename YT, typename RT, int CHROMA>
+static int launch_special(AbY2RBatch & B, cudaStream_t st)
+{
+    const AbY2RJob & J = B.common;
+    constexpr bool slow = (CHROMA == CH_BIL420 || CHROMA == CH_BIL422);
+    if constexpr (sizeof(RT) == 1) {
+        if (J.is565) {
+            if (J.alphaMul == AB_MUL_NONE) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE, OUT_565>(B, st);
+            if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL, OUT_565>(B, st);
+        }
+        return 0;
+    } else {
+        if (!J.toF16 || J.alphaFirst) return 0;
+        if (J.nChan == 3) {
+            if (J.alphaMul == AB_MUL_NONE) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE, OUT_F16>(B, st);
+            if (J.alphaMul == AB_MUL_FLOAT_MUL) return launch_any<YT, RT, CHROMA, 3, false, AB_ALPHA_KEEP, AB_MUL_FLOAT_MUL, OUT_F16>(B, st);
+            return 0;
+        }
+        if (J.alphaWrite == AB_ALPHA_FILL) return (J.alphaMul == AB_MUL_NONE) ? launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, OUT_F16>(B, st) : 0;
+        if (J.alphaWrite != AB_ALPHA_COPY) return 0;
+        switch (J.alphaMul) {
+            case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_NONE, OUT_F16>(B, st);
+            case AB_MUL_INT_PREMUL: return slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, OUT_F16>(B, st); /* depth 16: no fma form */
+            case AB_MUL_FLOAT_MUL: return !slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_FLOAT_MUL, OUT_F16>(B, st);
+            default: return 0;
+        }
+    }
 }
 
 template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST>
@@ -1065,10 +1128,13 @@ static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
 template <typename YT, typename RT>
 static bool fast_eligible(const AbY2RJob & J)
 {
-    if (J.mode != AB_MODE_COEFF || J.isGray || J.is565 || J.toF16 || J.chroma == AB_CHROMA_NONE) return false;
-    if (J.nChan != 3 && J.nChan != 4) return false;
+    if (J.mode != AB_MODE_COEFF || J.isGray || J.chroma == AB_CHROMA_NONE) return false;
+    if (J.is565 && sizeof(RT) != 1) return false;
+    if (J.toF16 && (sizeof(RT) != 2 || J.alphaFirst)) return false;
+    if (!J.is565 && J.nChan != 3 && J.nChan != 4) return false;
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
-    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale) return false;
+    /* alpha depth rescale: only the 8 <-> 16-bit container pairs (TileTraits::RESC), whose depths always differ */
+    if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale != (sizeof(YT) != sizeof(RT)))) return false;
     if (!J.rangeY.intExact || !J.rangeUV.intExact || !J.kg.exact) return false;
     if (AB_Y2R_DIV2 && !J.kg.exact2) return false;
     if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && (!J.rgbMaxDiv.exact || (AB_Y2R_DIV2 && !J.rgbMaxDiv.exact2))) return false;
@@ -1132,8 +1198,10 @@ static int launch_y2r_fast_typed(const AbY2RJob * jobs, uint32_t n, cudaStream_t
     }
     const bool afirst = J.alphaFirst != 0;
     const int nch = J.nChan;
+    const bool special = J.is565 || J.toF16;
 #define ABF_DISPATCH(CH)                                                              \
     do {                                                                              \
+        if (special) return launch_special<YT, RT, CH>(B, st);                        \
         if (nch == 3) return launch_alpha<YT, RT, CH, 3, false>(B, st);               \
         return afirst ? launch_alpha<YT, RT, CH, 4, true>(B, st) : launch_alpha<YT, RT, CH, 4, false>(B, st); \
     } while (0)

@@ -110,10 +110,11 @@ def test_tone_map_matches_reference_for_every_transfer_function(gpu_product, ref
             rb, b, cb, err = apply(gpu_product, base, 1, tc_in, gm, 1.5, 1, tc_out, depth, A.AVIF_RGB_FORMAT_RGBA)
             assert ra == rb == 0, (ra, rb, err)
             worst, frac = compare(a, b, depth, False)
-            # PQ raises the linear value to the 78.84th power: an ulp of powf moves a 16-bit code by a few units
-            tol = 1 if depth < 16 else (8 if 16 in (tc_in, tc_out) else 2)
+            # 16-bit outputs evaluate the transfer function in double and round once (csrc/tonemap.cu: xpow<true>): +-1 code like the
+            # other depths; PQ raises the linear value to the 78.84th power, which multiplies what is left of the difference
+            tol = 1 if (depth < 16 or 16 not in (tc_in, tc_out)) else 2
             assert worst <= tol, (tc_in, tc_out, depth, worst, frac)
-            assert frac < (0.02 if depth < 16 else 0.35), (tc_in, tc_out, depth, worst, frac)
+            assert frac < 0.02, (tc_in, tc_out, depth, worst, frac)
             assert abs(ca[0] - cb[0]) <= 1 and abs(ca[1] - cb[1]) <= 1, (ca, cb)
 
 

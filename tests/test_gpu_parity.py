@@ -86,6 +86,29 @@ def test_y2r_fast_kernels_are_used_and_exact(gpu_product, oracle):
     assert served > 0.3 * k, f"only {served} of {k} aligned conversions ran on the specialised kernels"
 
 
+def test_y2r_fast_kernels_serve_android_outputs(gpu_product, oracle):
+    """What android_jni/.../libavif_jni.cc:206-223 asks for -- RGBA_F16 premultiplied, RGB_565, RGBA8 premultiplied from 10-bit --
+    plus every alpha-depth rescale between 8-bit and 16-bit containers: served by the specialised kernels, exact."""
+    sizes = [(264, 6), (520, 5), (1000, 4), (257, 7), (8, 3), (2056, 3)]
+    k = 0
+    for depth in (8, 10, 12):
+        for fmt, ups in [(1, 0), (2, 3), (2, 4), (3, 3), (3, 0)]:
+            for alpha, ip in [(False, False), (True, False), (True, True)]:
+                for (rgb_depth, rgb_fmt, is_float, rp) in [(16, abi.AVIF_RGB_FORMAT_RGBA, True, True), (16, abi.AVIF_RGB_FORMAT_BGRA, True, False),
+                                                           (16, abi.AVIF_RGB_FORMAT_RGB, True, False), (8, abi.AVIF_RGB_FORMAT_RGB_565, False, True),
+                                                           (8 if depth > 8 else 16, abi.AVIF_RGB_FORMAT_RGBA, False, True),
+                                                           (8 if depth > 8 else 12, abi.AVIF_RGB_FORMAT_BGRA, False, False)]:
+                    k += 1
+                    w, h = sizes[k % len(sizes)]
+                    spec = util.Spec(w=w, h=h, depth=depth, fmt=fmt, rng=k % 2, mc=[1, 6, 9][k % 3], alpha=alpha, img_premult=ip, rgb_depth=rgb_depth,
+                                     rgb_fmt=rgb_fmt, ups=ups, rgb_premult=rp, is_float=is_float, garbage=(k % 3 == 0))
+                    assert _check_y2r(gpu_product, oracle, spec, 9900 + k, device="cuda:0") == 0
+                    name = gpu_product.avifB200LastKernelName().decode()
+                    unmul = alpha and ip and not rp and abi.rgb_format_has_alpha(rgb_fmt)  # F16 / mixed-depth unmultiply: general kernel
+                    if not (unmul and (is_float or True)):
+                        assert name.startswith("y2r_fast"), (spec.ident(), name)
+
+
 def test_r2y_fast_kernels_are_used_and_exact(gpu_product, oracle):
     import itertools
     sizes = [(264, 6), (520, 5), (1000, 4), (257, 7), (8, 3), (2056, 3), (1, 1), (9, 2)]

@@ -35,3 +35,25 @@ def test_pageable_staging_ring_sizes(gpu_product, monkeypatch):
         assert got["rgb"] == VECTORS["C5"]["rgb"], mb
     monkeypatch.setenv("AVIF_B200_STAGING", "0")
     # (read once per process: this only documents the switch; the driver's own pageable path is what round 1 shipped)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_pageable_staging_keeps_row_padding_and_matches_oracle(gpu_product, oracle, threads):
+    """regions large enough for the pinned ring (>= 256 KB), odd row paddings on both sides, with and without helper threads:
+    every byte of the destination allocation, padding included, against the oracle"""
+    from libavif_b200 import abi
+    from tests import util
+    specs = [util.Spec(w=1203, h=611, depth=10, fmt=abi.AVIF_PIXEL_FORMAT_YUV420, rng=0, mc=abi.MC_BT709, alpha=True, rgb_depth=10, rgb_fmt=abi.AVIF_RGB_FORMAT_RGBA,
+                       ups=abi.AVIF_CHROMA_UPSAMPLING_BILINEAR, yuv_pad=6, rgb_pad=10, max_threads=threads),
+             util.Spec(w=2048, h=300, depth=8, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rgb_depth=8, rgb_fmt=abi.AVIF_RGB_FORMAT_BGRA, yuv_pad=0, rgb_pad=4, max_threads=threads)]
+    for k, spec in enumerate(specs):
+        ro, want = util.yuv_to_rgb(oracle, spec, 70 + k)
+        rp, got = util.yuv_to_rgb(gpu_product, spec, 70 + k)
+        assert ro == rp == 0 and util.first_mismatch(want, got) is None, spec.ident()
+        ro, wantp = util.rgb_to_yuv(oracle, spec, 80 + k)
+        rp, gotp = util.rgb_to_yuv(gpu_product, spec, 80 + k)
+        assert ro == rp == 0
+        for a, b in zip(wantp, gotp):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert util.first_mismatch(a, b) is None, spec.ident()

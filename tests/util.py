@@ -113,7 +113,7 @@ def make_rgb_dst(spec, device=None, pinned=False, w=None, h=None):
 def make_rgb_src(spec, seed, device=None, pinned=False):
     rgb = RGBImage(spec.w, spec.h, spec.rgb_depth, spec.rgb_fmt, upsampling=spec.ups, downsampling=spec.downs,
                    ignore_alpha=spec.ignore_alpha, alpha_premultiplied=spec.rgb_premult, is_float=spec.is_float,
-                   device=device, pinned=pinned, row_pad=spec.rgb_pad, offset=spec.rgb_off)
+                   max_threads=spec.max_threads, device=device, pinned=pinned, row_pad=spec.rgb_pad, offset=spec.rgb_off)
     rs = np.random.RandomState(seed)
     nch = rgb.pixel_bytes // (2 if spec.rgb_depth > 8 else 1)
     maxv = (1 << spec.rgb_depth) - 1
