@@ -496,9 +496,17 @@ __device__ __forceinline__ void convert_store_rtile(const AbR2YJob & J, const Ab
  * swap roles) so that nothing is moved.  Chunks are numbered row-major (adjacent strips of one row band are adjacent ids) and
  * dealt to the warps exactly like the groups of tiles before: group g = chunks 8g..8g+7, one per warp, blocks stride over the
  * groups of their frame. */
-#ifndef AB_R2Y_STRIP
+#ifndef AB_R2Y_STRIP /* one-row tiles (4:4:4, 4:2:2, 4:0:0) run the strip kernel; two-row tiles keep the group kernel (their
+                      * register sets leave no room: the strip form spills and measured 9 % slower, profiles/r02_variants.md) */
 #define AB_R2Y_STRIP 1
 #endif
+#ifndef AB_R2Y_STRIP_MINB /* 80 registers: at 4 blocks/SM (64) the strip loop spills ~28 registers and loses (26.7 vs 22.5 us on C2 back) */
+#define AB_R2Y_STRIP_MINB 3
+#endif
+template <class C>
+struct RStrip {
+    static constexpr bool ON = (AB_R2Y_STRIP != 0) && (C::SUB != SUB_420);
+};
 #ifndef AB_R2Y_CHUNK
 #define AB_R2Y_CHUNK 8
 #endif
@@ -569,7 +577,7 @@ __device__ __forceinline__ void r2y_strip_run(const AbR2YJob & J, const AbR2YFra
 }
 
 template <class C>
-__global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_strip_kernel(const __grid_constant__ AbR2YBatch B)
+__global__ void __launch_bounds__(kRWarps * 32, AB_R2Y_STRIP_MINB) r2y_strip_kernel(const __grid_constant__ AbR2YBatch B)
 {
     const AbR2YJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -761,7 +769,7 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbR2YFrame & F = B.frame[f];
         uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
-        if (AB_R2Y_STRIP) units = (units + kRChunk - 1) / kRChunk; /* work items are chunks of kRChunk row units */
+        if (RStrip<C>::ON) units = (units + kRChunk - 1) / kRChunk; /* work items are chunks of kRChunk row units */
         F.tilesX = (F.width + kRTile - 1) / kRTile;
         F.tiles = F.tilesX * units;
         F.groups = (F.tiles + kRWarps - 1) / kRWarps;
@@ -775,14 +783,18 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
     if (!resident) {
         int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (AB_R2Y_STRIP) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_strip_kernel<C>, kRWarps * 32, 0);
+        if (RStrip<C>::ON) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_strip_kernel<C>, kRWarps * 32, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
+        { /* never more blocks per SM than the loop shape was tuned for (see y2r_fast.cuh) */
+            const int tuned = RStrip<C>::ON ? AB_R2Y_STRIP_MINB : RLoop<C>::MIN_BLOCKS;
+            if (perSm > tuned) perSm = tuned;
+        }
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);
-    if (AB_R2Y_STRIP) r2y_strip_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
+    if (RStrip<C>::ON) r2y_strip_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
     else r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
     return 1;
 }

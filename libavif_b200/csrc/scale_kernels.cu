@@ -47,11 +47,11 @@ __device__ __forceinline__ int blend(int a, int b, int f)
 }
 
 /* one destination sample (i, j) of plane job J */
-template <typename T>
+template <typename T, int MODE>
 __device__ __forceinline__ int scale_sample(const AbScaleJob & J, const int32_t * R, int i, int j)
 {
     const int32_t * C = J.cols + 4 * i;
-    switch (J.mode) {
+    switch (MODE ? MODE : (int)J.mode) { /* MODE != 0: the loop is a compile-time constant and the other cases fold away */
         case AB_SCALE_VERTICAL: { /* rows: yi, yf */
             const int yi = R[0], yf = R[1];
             return interp(ld<T>(J, yi, i), (yf == 0) ? 0 : ld<T>(J, yi + 1, i), yf);
@@ -112,6 +112,45 @@ __device__ __forceinline__ int scale_sample(const AbScaleJob & J, const int32_t 
     }
 }
 
+/* ScalePlaneUp2_Linear / _Bilinear (scale.c:467-538, scale_any.c:27-78) for a thread's 8 (u8) or 4 (u16) consecutive outputs that
+ * all lie strictly inside the row (i0 >= 1 .. i0 + VEC - 1 <= dstW - 2): outputs i0..i0+VEC-1 read source columns
+ * (i0 - 1) / 2 .. (i0 + VEC - 2) / 2 + 1, i.e. VEC / 2 + 2 columns when i0 is even -- loaded once per row instead of four
+ * clamped byte loads per output. */
+template <typename T, bool BILINEAR>
+__device__ __forceinline__ void up2_group(const AbScaleJob & J, int i0, int j, int v[8 / sizeof(T)])
+{
+    constexpr int VEC = 8 / (int)sizeof(T);
+    constexpr int NC = VEC / 2 + 2;
+    int rs = 0, rt = 0; /* near row gets weights (9,3) / (3,1), far row (3,1); linear: one row */
+    if (BILINEAR) {
+        if (j != 0) {
+            const int r = (j - 1) >> 1;
+            if (r >= J.srcH - 1) rs = rt = J.srcH - 1;
+            else if ((j - 1) & 1) { rs = r + 1; rt = r; }
+            else { rs = r; rt = r + 1; }
+        }
+    } else {
+        rs = rt = j; /* the caller passes the source row */
+    }
+    const int k0 = (i0 - 1) >> 1; /* i0 even and >= 2: k0 = i0/2 - 1 >= 0 */
+    const T * ps = reinterpret_cast<const T *>(J.src + (int64_t)rs * J.srcRB) + k0;
+    const T * pt = reinterpret_cast<const T *>(J.src + (int64_t)rt * J.srcRB) + k0;
+    int a[NC], b[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        a[k] = (int)ps[k];
+        b[k] = BILINEAR ? (int)pt[k] : 0;
+    }
+#pragma unroll
+    for (int o = 0; o < VEC; ++o) {
+        const int i = i0 + o;
+        const int k = ((i - 1) >> 1) - k0;
+        const int kn = ((i - 1) & 1) ? k + 1 : k, kf = ((i - 1) & 1) ? k : k + 1;
+        if (BILINEAR) v[o] = (a[kn] * 9 + a[kf] * 3 + b[kn] * 3 + b[kf] + 8) >> 4;
+        else v[o] = ((i - 1) & 1) ? ((a[k] + 3 * a[k + 1] + 2) >> 2) : ((3 * a[k] + a[k + 1] + 2) >> 2);
+    }
+}
+
 /* All planes of one image in one launch.  A thread produces 8 bytes of one destination row (8 u8 or 4 u16 samples) and stores
  * them as one vector when the row is 8-byte aligned; consecutive threads take consecutive groups, so a warp writes 256
  * contiguous bytes.  Blocks are shared out over the planes by blockStart[]. */
@@ -130,8 +169,31 @@ __global__ void __launch_bounds__(256) scale_batch_kernel(const __grid_constant_
         const int j = (int)(u / groupsPerRow), i0 = (int)(u - (int64_t)j * groupsPerRow) * VEC;
         const int32_t * R = J.rows + 4 * j;
         int v[VEC];
+        /* the loop is a per-plane (block-uniform) constant: one specialised body per loop, the generic one as fallback */
+        const bool inner = (i0 >= 2) && (i0 + VEC <= J.dstW - 1);
+        if (J.mode == AB_SCALE_UP2_BILINEAR && inner) {
+            up2_group<T, true>(J, i0, j, v);
+        } else if (J.mode == AB_SCALE_UP2_LINEAR && inner) {
+            up2_group<T, false>(J, i0, R[0], v);
+        } else {
+#define AB_SCALE_CASE(M)                                                                                     \
+    case M:                                                                                                  \
+        _Pragma("unroll") for (int k = 0; k < VEC; ++k) v[k] = (i0 + k < J.dstW) ? scale_sample<T, M>(J, R, i0 + k, j) : 0; \
+        break;
+            switch (J.mode) {
+                AB_SCALE_CASE(AB_SCALE_VERTICAL)
+                AB_SCALE_CASE(AB_SCALE_SIMPLE)
+                AB_SCALE_CASE(AB_SCALE_BILINEAR_DOWN)
+                AB_SCALE_CASE(AB_SCALE_BILINEAR_UP)
+                AB_SCALE_CASE(AB_SCALE_UP2_LINEAR)
+                AB_SCALE_CASE(AB_SCALE_UP2_BILINEAR)
+                AB_SCALE_CASE(AB_SCALE_BOX)
+                default:
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] = (i0 + k < J.dstW) ? scale_sample<T>(J, R, i0 + k, j) : 0;
+                    for (int k = 0; k < VEC; ++k) v[k] = 0;
+            }
+#undef AB_SCALE_CASE
+        }
         T * out = reinterpret_cast<T *>(J.dst + (int64_t)j * J.dstRB) + i0;
         if (aligned && i0 + VEC <= J.dstW) {
             uint2 w;

@@ -315,8 +315,11 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
     }
 }
 
-template <class C, bool FULL>
-__device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in)
+/* CARRY (bilinear 4:2:0 strips): chroma row A of this unit is row B of the unit above, whose normalised columns (own 4 + the two
+ * neighbours) arrive in carry[plane][6] instead of being loaded and normalised again; either way carry leaves holding row B */
+template <class C, bool FULL, bool CARRY>
+__device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in,
+                                                     float (&carry)[2][6])
 {
     using T = TileTraits<C>;
     using YT = typename T::YT;
@@ -356,17 +359,26 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #pragma unroll
             for (int c = 0; c < CROWS; ++c) {
                 float n[6];
+                if (CARRY && c == 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    n[k + 1] = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(plane ? in.vw[c] : in.uw[c], k, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
+                    for (int k = 0; k < 6; ++k) n[k] = carry[plane][k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        n[k + 1] = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(plane ? in.vw[c] : in.uw[c], k, K, mm), magicMax, J.magicBiasUV, J.rangeUV);
+                    }
+                    float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
+                    float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
+                    const float halo = norm_magic<YT>(plane ? in.hV[c] : in.hU[c], magicMax, J.magicBiasUV, J.rangeUV);
+                    left = (lane == 0) ? halo : left;
+                    right = (lane == 31) ? halo : right;
+                    n[0] = left;
+                    n[5] = right;
                 }
-                float left = __shfl_up_sync(0xFFFFFFFFu, n[4], 1);
-                float right = __shfl_down_sync(0xFFFFFFFFu, n[1], 1);
-                const float halo = norm_magic<YT>(plane ? in.hV[c] : in.hU[c], magicMax, J.magicBiasUV, J.rangeUV);
-                left = (lane == 0) ? halo : left;
-                right = (lane == 31) ? halo : right;
-                n[0] = left;
-                n[5] = right;
+                if (c == CROWS - 1) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) carry[plane][k] = n[k];
+                }
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
                     p3[c][k] = __fmul_rn(n[k], 0.1875f);
@@ -544,6 +556,13 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
     }
 }
 
+template <class C, bool FULL>
+__device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in)
+{
+    float unused[2][6];
+    convert_store_tile_x<C, FULL, false>(J, F, R, x0, lane, in, unused);
+}
+
 /* ---- the kernel ------------------------------------------------------------------------------------- */
 
 /* Persistent, software-pipelined, batched.  Work unit = GROUP of 8 consecutive tiles of one frame (one per warp), so
@@ -569,6 +588,9 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #ifndef AB_Y2R_PLAIN_NEAREST
 #define AB_Y2R_PLAIN_NEAREST 1
 #endif
+#ifndef AB_Y2R_PREFETCH_BIL420 /* 1: second register set for the two-row bilinear tile too (needs AB_Y2R_MINB_BIL420=2: ~120 registers) */
+#define AB_Y2R_PREFETCH_BIL420 0
+#endif
 #ifndef AB_Y2R_UNROLL2 /* 1: the prefetching loop written out twice (ping-pong register sets, no copies) */
 #define AB_Y2R_UNROLL2 0
 #endif
@@ -577,7 +599,7 @@ __device__ __forceinline__ void convert_store_tile(const AbY2RJob & J, const AbY
 #endif
 template <class C>
 struct YLoop {
-    static constexpr bool PLAIN = (C::CHROMA == CH_BIL420) || (AB_Y2R_PLAIN != 0) || (C::CHROMA == CH_NEAREST && AB_Y2R_PLAIN_NEAREST != 0);
+    static constexpr bool PLAIN = (C::CHROMA == CH_BIL420 && AB_Y2R_PREFETCH_BIL420 == 0) || (AB_Y2R_PLAIN != 0) || (C::CHROMA == CH_NEAREST && AB_Y2R_PLAIN_NEAREST != 0);
     static constexpr int MIN_BLOCKS = (C::CHROMA == CH_BIL420) ? AB_Y2R_MINB_BIL420 : ((C::CHROMA == CH_NEAREST) ? AB_Y2R_MINB_NEAREST : AB_Y2R_MINB);
 };
 template <class C>
@@ -711,6 +733,101 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
         full = nfull;
     }
 #endif
+}
+
+/* ---- strip kernel (bilinear 4:2:0) -----------------------------------------------------------------------------------
+ * A warp walks DOWN a 256-pixel column strip, kYChunk row units at a time.  Unit r converts luma rows 2r-1 and 2r from chroma rows
+ * r-1 and r; unit r+1 needs rows r and r+1 -- so the lower chroma row of a unit, already loaded, clamped, normalised and joined
+ * with its two neighbour columns, is handed to the next unit in 12 registers instead of being fetched and prepared again (a quarter
+ * of the chroma work of the group kernel, which visits units in row-major order and shares nothing), and positions advance by
+ * rows instead of being re-derived from a tile number.  Units that touch the picture's top / bottom edge, a band limit of the
+ * host pipeline, or a ragged last strip take the general tile code. */
+#ifndef AB_Y2R_STRIP_BIL420
+#define AB_Y2R_STRIP_BIL420 1
+#endif
+#ifndef AB_Y2R_CHUNK
+#define AB_Y2R_CHUNK 8
+#endif
+constexpr uint32_t kYChunk = AB_Y2R_CHUNK;
+
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_bil420_strip_kernel(const __grid_constant__ AbY2RBatch B)
+{
+    using T = TileTraits<C>;
+    using YT = typename T::YT;
+    static_assert(C::CHROMA == CH_BIL420, "strip kernel: bilinear 4:2:0");
+    const AbY2RJob & J = B.common;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t f = 0;
+    while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f;
+    const AbY2RFrame & F = B.frame[f];
+    const uint32_t gStride = F.blocks;
+    const uint32_t g0 = blockIdx.x - F.blockStart;
+    if (g0 >= F.groups) return;
+    const uint32_t units = (F.rowEnd >> 1) - (F.rowBegin >> 1) + 1;
+    const uint32_t cw = (F.width + 1) >> 1;
+#pragma unroll 1
+    for (uint32_t g = g0; g < F.groups; g += gStride) {
+        const uint32_t c = g * kWarps + warp;
+        if (c >= F.tiles) continue; /* warp-uniform */
+        const uint32_t cy = c / F.tilesX, sx = c - cy * F.tilesX;
+        const uint32_t x0 = sx * kTile, px0 = x0 + 8 * lane, m0 = px0 >> 1;
+        const uint32_t u0 = cy * kYChunk, u1 = min(u0 + kYChunk, units);
+        const bool full = (x0 + kTile <= F.width);
+        float carry[2][6];
+        bool have = false;
+#pragma unroll 1
+        for (uint32_t unit = u0; unit < u1; ++unit) {
+            const TileRows<C> R = tile_rows<C>(J, F, unit);
+            if (!R.any) {
+                have = false;
+                continue;
+            }
+            const int ru = (int)(F.rowBegin >> 1) + (int)unit;
+            const bool interior = full && R.rowOn[0] && R.rowOn[1] && (R.cA == ru - 1) && (R.cB == ru);
+            TileIn<C> in;
+            if (!interior) { /* picture / band edge or ragged strip */
+                if (full) {
+                    load_tile<C, true>(J, F, R, x0, lane, in);
+                    convert_store_tile_x<C, true, false>(J, F, R, x0, lane, in, carry);
+                    have = (R.cB == ru); /* carry holds chroma row ru: what the unit below calls its row A */
+                } else {
+                    load_tile<C, false>(J, F, R, x0, lane, in);
+                    convert_store_tile_x<C, false, false>(J, F, R, x0, lane, in, carry);
+                    have = false;
+                }
+                continue;
+            }
+            /* interior unit of a full strip: two luma (and alpha) rows, chroma row B; row A only if the unit above did not leave it */
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                load8<YT>(F.y + (int64_t)R.jrow[r] * F.yRB, px0, 8u, in.yw[r]);
+                if (T::NEED_A) load8<YT>(F.a + (int64_t)R.jrow[r] * F.aRB, px0, 8u, in.aw[r]);
+            }
+#pragma unroll
+            for (int cr = 0; cr < 2; ++cr) {
+                if (cr == 0 && have) { /* warp-uniform */
+                    in.uw[0][0] = in.uw[0][1] = in.vw[0][0] = in.vw[0][1] = 0;
+                    in.hU[0] = in.hV[0] = 0.0f;
+                    continue;
+                }
+                const int crow = (cr == 0) ? R.cA : R.cB;
+                const uint8_t * ur = F.u + (int64_t)crow * F.uRB;
+                const uint8_t * vr = F.v + (int64_t)crow * F.vRB;
+                load4_clamped<YT>(ur, m0, m0 + 4, in.uw[cr]);
+                load4_clamped<YT>(vr, m0, m0 + 4, in.vw[cr]);
+                in.hU[cr] = in.hV[cr] = 0.0f;
+                if (lane == 0 || lane == 31) {
+                    const uint32_t col = (lane == 0) ? ((m0 > 0) ? m0 - 1 : 0) : min(m0 + 4, cw - 1);
+                    in.hU[cr] = magic_scalar<YT>(ur, col);
+                    in.hV[cr] = magic_scalar<YT>(vr, col);
+                }
+            }
+            if (have) convert_store_tile_x<C, true, true>(J, F, R, x0, lane, in, carry);
+            else convert_store_tile_x<C, true, false>(J, F, R, x0, lane, in, carry);
+            have = true;
+        }
+    }
 }
 
 /* ---- TMA-staged variant (bilinear 4:2:0) -------------------------------------------------------------------
@@ -982,12 +1099,14 @@ template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, in
 static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT>;
+    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0);
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbY2RFrame & F = B.frame[f];
         const uint32_t rows = F.rowEnd - F.rowBegin;
         uint32_t units = rows;
         if (CHROMA == CH_BIL420) units = (F.rowEnd >> 1) - (F.rowBegin >> 1) + 1; /* row pairs (2r-1, 2r) touching [rowBegin,rowEnd) */
+        if (STRIP) units = (units + kYChunk - 1) / kYChunk;                        /* work items: chunks of kYChunk units of one strip */
         F.tilesX = (F.width + kTile - 1) / kTile;
         F.tiles = F.tilesX * units;
         F.groups = (F.tiles + kWarps - 1) / kWarps;
@@ -1001,13 +1120,18 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
     if (!resident) {
         int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
+        if constexpr (STRIP) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_bil420_strip_kernel<C>, kWarps * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
+        /* the loop shapes were tuned at YLoop::MIN_BLOCKS blocks per SM; when the compiler needs fewer registers than the bound
+         * allows, more blocks would fit -- and measured slower (4:2:0 nearest: 6 blocks 14.8 us, 5 blocks 13.3 us per 4K frame) */
+        if (perSm > YLoop<C>::MIN_BLOCKS) perSm = YLoop<C>::MIN_BLOCKS;
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, wanted);
-    y2r_fast_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
+    if constexpr (STRIP) y2r_bil420_strip_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
+    else y2r_fast_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
     return 1;
 }
 

@@ -31,7 +31,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # full capture of every configuration's BATCHED kernel (2 launches each; the 2nd of each pair is the warm one).  The report itself
 # can exceed what gpurun copies back: keep it in /tmp and bring home the raw-page CSV (+ the SASS pages of selected kernels)
 REP=/tmp/prof_cases_$TAG
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"y2r_|r2y_|tone_map|scale_" -c 80 -o $REP \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"y2r_|r2y_|tone_map|scale_" -c 200 -o $REP \
     python tools/profile_cases.py $OUT/cases.json > $OUT/ncu_cases.log 2>&1
 tail -30 $OUT/ncu_cases.log
 ncu -i $REP.ncu-rep --page raw --csv --print-units base > $OUT/prof_cases_raw.csv 2>/dev/null

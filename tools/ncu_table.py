@@ -46,10 +46,13 @@ for c in cases:
             sys.exit(f"ncu_table: no kernel matching {match!r} captured for case {c['case']}")
         r = grp[-1]
     else:
-        if pos + 2 > len(ours):
-            sys.exit(f"ncu_table: capture ends before case {c['case']} ({len(ours)} kernels, needed {pos + 2})")
-        r = ours[pos + 1]  # the warm second launch
-        pos += 2
+        n = int(c.get("launches", 2))  # kernels the case launched (two calls); a case served by one fused launch per call has 2
+        if pos + n > len(ours):
+            sys.exit(f"ncu_table: capture ends before case {c['case']} ({len(ours)} kernels, needed {pos + n})")
+        r = ours[pos + n - 1]  # the last launch of the warm second call
+        if n != 2:
+            c = dict(c, frames=max(1, c["frames"] * 2 // n))  # unfused path: each launch covers frames * 2 / n frames
+        pos += n
     g = lambda m: float(r[ix[m]].replace(",", ""))
     px = c["px_per_frame"] * c["frames"]
     alg = c["alg_bytes_per_px"] * px

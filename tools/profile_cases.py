@@ -50,17 +50,21 @@ for name, nf in PLAN:
         imgs.append(img)
         rgbs.append(wl.make_rgb(name, device=dev))
     pi, pr = pointer_array(imgs), pointer_array(rgbs)
+    lib.avifB200ResetKernelLaunchCount()
     for _ in range(2):
         assert lib.avifB200ImageYUVToRGBBatchAsync(pi, pr, nf, sptr) == 0
     torch.cuda.synchronize()
-    order.append({"case": name, "kernel": lib.avifB200LastKernelName().decode(), "frames": nf, "px_per_frame": w * h, "alg_bytes_per_px": cfg["bytes_per_px"]})
+    order.append({"case": name, "kernel": lib.avifB200LastKernelName().decode(), "frames": nf, "px_per_frame": w * h, "alg_bytes_per_px": cfg["bytes_per_px"],
+                  "launches": int(lib.avifB200KernelLaunchCount())})
     if cfg.get("back"):
         dsts = [wl.make_yuv(name, device=dev) for _ in range(nf)]
         pd = pointer_array(dsts)
+        lib.avifB200ResetKernelLaunchCount()
         for _ in range(2):
             assert lib.avifB200ImageRGBToYUVBatchAsync(pd, pr, nf, sptr) == 0
         torch.cuda.synchronize()
-        order.append({"case": name + "_back", "kernel": lib.avifB200LastKernelName().decode(), "frames": nf, "px_per_frame": w * h, "alg_bytes_per_px": cfg["bytes_per_px"]})
+        order.append({"case": name + "_back", "kernel": lib.avifB200LastKernelName().decode(), "frames": nf, "px_per_frame": w * h, "alg_bytes_per_px": cfg["bytes_per_px"],
+                      "launches": int(lib.avifB200KernelLaunchCount())})
         del dsts
     del imgs, rgbs
     torch.cuda.empty_cache()
@@ -78,10 +82,12 @@ cy = [sharding.view_yuv(canvas.c, r) for r in rects]
 cr = [sharding.view_rgb(canvas_rgb.c, r) for r in rects]
 pi = (ctypes.POINTER(A.avifImage) * 16)(*[ctypes.pointer(c) for c in cy])
 pr = (ctypes.POINTER(A.avifRGBImage) * 16)(*[ctypes.pointer(c) for c in cr])
+lib.avifB200ResetKernelLaunchCount()
 for _ in range(2):
     assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
 torch.cuda.synchronize()
-order.append({"case": "C4_canvas", "kernel": lib.avifB200LastKernelName().decode(), "frames": 16, "px_per_frame": 1920 * 1080, "alg_bytes_per_px": 6.5})
+order.append({"case": "C4_canvas", "kernel": lib.avifB200LastKernelName().decode(), "frames": 16, "px_per_frame": 1920 * 1080, "alg_bytes_per_px": 6.5,
+              "launches": int(lib.avifB200KernelLaunchCount())})
 
 if "--reformat-only" not in sys.argv:
     # gain-map tone mapping: 4K sRGB RGBA8 base + 8-bit 4:4:4 gain map -> PQ RGBA10, device resident
