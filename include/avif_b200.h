@@ -296,9 +296,13 @@ typedef struct avifGainMap {
 
 /* src/gainmap.c:73-315 and :317-360: tone-maps baseImage with gainMap for a display of the given log2 HDR headroom.
  * Allocates toneMappedImage->pixels (width/height/rowBytes set here; format, depth, isFloat are the caller's request).
- * Arithmetic is binary32 with libm's powf/exp2f/logf in the reference and CUDA's on the device: results agree to +-1 output
- * code, not bit for bit.  A gain map of another size than the base image needs avifImageScale (libyuv
- * scaling, SURVEY 8f-4, not built): AVIF_RESULT_NOT_IMPLEMENTED with a diagnostic. */
+ * Arithmetic is binary32 with libm's powf/exp2f/logf in the reference and CUDA's on the device (evaluated in double and rounded
+ * once wherever a 16-bit code depends on the last ulp): results agree to +-1 output code, not bit for bit.
+ * clli->maxCLL follows the reference exactly up to that tolerance; clli->maxPALL is the average of the per-pixel maxima summed in
+ * DOUBLE precision, where the reference accumulates them sequentially in a float (src/gainmap.c:213,290) -- on multi-megapixel
+ * images the reference's running sum loses most of every addend, so its maxPALL can sit several nits below this (more accurate)
+ * value; the two agree to +-1 nit on images up to ~1 megapixel.  A gain map of another size than the base image is rescaled
+ * first with avifImageScale's arithmetic, like src/gainmap.c:186-201. */
 AVIF_B200_API avifResult avifRGBImageApplyGainMap(const avifRGBImage * baseImage, avifColorPrimaries baseColorPrimaries,
                                                   avifTransferCharacteristics baseTransferCharacteristics, const avifGainMap * gainMap,
                                                   float hdrHeadroom, avifColorPrimaries outputColorPrimaries,

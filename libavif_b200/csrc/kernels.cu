@@ -923,6 +923,20 @@ static int launch_y2r_typed(const AbY2RJob & J, cudaStream_t st, int forceGeneri
 {
     const uint32_t rows = J.rowEnd - J.rowBegin;
     if (rows == 0 || J.width == 0) return 0;
+    {
+        /* gridDim.y <= 65535: very tall images are converted in row slices (the reference has no such limit; slices start on even rows) */
+        const uint32_t maxRows = 65535u * 4u;
+        if (rows > maxRows) {
+            int err = 0;
+            for (uint32_t r0 = J.rowBegin; r0 < J.rowEnd && !err; r0 += maxRows) {
+                AbY2RJob S = J;
+                S.rowBegin = r0;
+                S.rowEnd = (J.rowEnd - r0 > maxRows) ? r0 + maxRows : J.rowEnd;
+                err = launch_y2r_typed<YT, RT>(S, st, forceGeneric, name);
+            }
+            return err;
+        }
+    }
     if (forceGeneric) {
         const dim3 block(64, 4);
         y2r_generic_kernel<YT, RT><<<grid2d(J.width, rows, block), block, 0, st>>>(J);
@@ -1087,6 +1101,19 @@ int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const cha
         }
     }
     forceGeneric &= 1;
+    {
+        const uint32_t maxRows = 65535u * 16u; /* gridDim.y limit: 8 thread rows x 2 luma rows per block row */
+        if (job->rowEnd - job->rowBegin > maxRows) {
+            int err = 0;
+            for (uint32_t r0 = job->rowBegin; r0 < job->rowEnd && !err; r0 += maxRows) {
+                AbR2YJob S = *job;
+                S.rowBegin = r0;
+                S.rowEnd = (job->rowEnd - r0 > maxRows) ? r0 + maxRows : job->rowEnd;
+                err = abLaunchR2Y(&S, stream, forceGeneric ? 1 : 4, kernelName); /* 4: skip the specialised kernels, keep the vector block kernel */
+            }
+            return err;
+        }
+    }
     const dim3 block(32, 8);
     const dim3 grid = grid2d((job->width + 1) / 2, (job->rowEnd - job->rowBegin + 1) / 2, block);
 #define AB_R2Y(RT, YT)                                                                      \
@@ -1106,10 +1133,23 @@ int abLaunchR2Y(const AbR2YJob * job, void * stream, int forceGeneric, const cha
     return finish_launch();
 }
 
+static const uint32_t kMaxRows2D = 65535u * 4u; /* gridDim.y limit of the (64, 4)-thread 2-D launches below */
+
 int abLaunchAlpha(const AbAlphaJob * job, void * stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->height == 0) return 0;
+    if (job->height > kMaxRows2D) { /* row slices */
+        int err = 0;
+        for (uint32_t r0 = 0; r0 < job->height && !err; r0 += kMaxRows2D) {
+            AbAlphaJob S = *job;
+            S.height = (job->height - r0 > kMaxRows2D) ? kMaxRows2D : job->height - r0;
+            if (S.src) S.src += (int64_t)r0 * S.srcRB;
+            S.dst += (int64_t)r0 * S.dstRB;
+            err = abLaunchAlpha(&S, stream);
+        }
+        return err;
+    }
     const dim3 block(64, 4);
     const dim3 grid = grid2d(job->width, job->height, block);
     const bool s16 = job->src && job->srcDepth > 8, d16 = job->dstDepth > 8;
@@ -1124,6 +1164,16 @@ int abLaunchPremultiply(const AbRgbPassJob * job, void * stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->height == 0) return 0;
+    if (job->height > kMaxRows2D) { /* row slices */
+        int err = 0;
+        for (uint32_t r0 = 0; r0 < job->height && !err; r0 += kMaxRows2D) {
+            AbRgbPassJob S = *job;
+            S.height = (job->height - r0 > kMaxRows2D) ? kMaxRows2D : job->height - r0;
+            S.pixels += (int64_t)r0 * S.rowBytes;
+            err = abLaunchPremultiply(&S, stream);
+        }
+        return err;
+    }
     const dim3 block(64, 4);
     const dim3 grid = grid2d(job->width, job->height, block);
     if (job->depth > 8) premultiply_kernel<uint16_t><<<grid, block, 0, st>>>(*job);
@@ -1135,6 +1185,16 @@ int abLaunchToF16(const AbRgbPassJob * job, void * stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (job->width == 0 || job->height == 0) return 0;
+    if (job->height > kMaxRows2D) { /* row slices */
+        int err = 0;
+        for (uint32_t r0 = 0; r0 < job->height && !err; r0 += kMaxRows2D) {
+            AbRgbPassJob S = *job;
+            S.height = (job->height - r0 > kMaxRows2D) ? kMaxRows2D : job->height - r0;
+            S.pixels += (int64_t)r0 * S.rowBytes;
+            err = abLaunchToF16(&S, stream);
+        }
+        return err;
+    }
     const dim3 block(64, 4);
     f16_kernel<<<grid2d(job->width * job->nChan, job->height, block), block, 0, st>>>(*job);
     return finish_launch();
@@ -1157,6 +1217,12 @@ int abLaunchFill8(uint8_t * dst, size_t count, uint32_t value, void * stream)
 int abLaunchLimitedToFull(uint8_t * plane, int64_t rowBytes, uint32_t width, uint32_t height, uint32_t depth, void * stream)
 {
     if (width == 0 || height == 0) return 0;
+    if (height > kMaxRows2D) {
+        int err = 0;
+        for (uint32_t r0 = 0; r0 < height && !err; r0 += kMaxRows2D)
+            err = abLaunchLimitedToFull(plane + (int64_t)r0 * rowBytes, rowBytes, width, (height - r0 > kMaxRows2D) ? kMaxRows2D : height - r0, depth, stream);
+        return err;
+    }
     const dim3 block(64, 4);
     const dim3 grid = grid2d(width, height, block);
     if (depth > 8) limited_to_full_kernel<uint16_t><<<grid, block, 0, (cudaStream_t)stream>>>(plane, rowBytes, width, height, depth);

@@ -23,8 +23,9 @@ using namespace ab;
 
 enum { SUB_444 = 0, SUB_422 = 1, SUB_420 = 2, SUB_400 = 3 };
 
-template <typename RT_, typename YT_, int SUB_, int NCH_, bool AFIRST_, int AM_>
+template <typename RT_, typename YT_, int SUB_, int NCH_, bool AFIRST_, int AM_, bool IDENT_ = false>
 struct RCfg {
+    static constexpr bool IDENT = IDENT_; /* identity matrix (lossless GBR): Y = G, U = B, V = R, all quantised with the luma range (src/reformat.c:361-365, :212-213) */
     using RT = RT_;
     using YT = YT_;
     static constexpr int SUB = SUB_;
@@ -405,11 +406,11 @@ __device__ __forceinline__ void convert_store_rtile_p(const AbR2YJob & J, const 
 #endif
                 }
             }
-            const float Y = __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386 */
+            const float Y = C::IDENT ? G : __fadd_rn(__fadd_rn(__fmul_rn(J.kr, R), __fmul_rn(J.kg, G)), __fmul_rn(J.kb, B)); /* ref: :383-386, :361-365 */
             yq[t] = (YFULL && AB_R2Y_QMERGE && AB_R2Y_SATCVT) ? quant_luma_fullrange<YT>(Y, J.rangeY) : quant_luma<YT>(Y, J.rangeY, qbY, hiLimit);
             if (C::SUB != SUB_400) {
-                const float U = rdivx(__fsub_rn(B, Y), J.du);
-                const float V = rdivx(__fsub_rn(R, Y), J.dv);
+                const float U = C::IDENT ? B : rdivx(__fsub_rn(B, Y), J.du);
+                const float V = C::IDENT ? R : rdivx(__fsub_rn(R, Y), J.dv);
                 if (C::SUB == SUB_444) {
                     uq[t] = quant_yuv<YT>(U, J.rangeUV, qbUV, hiLimit);
                     vq[t] = quant_yuv<YT>(V, J.rangeUV, qbUV, hiLimit);
@@ -760,10 +761,10 @@ static uint32_t rassign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups
     return start;
 }
 
-template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM>
+template <typename RT, typename YT, int SUB, int NCH, bool AFIRST, int AM, bool IDENT = false>
 static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
 {
-    using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM>;
+    using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM, IDENT>;
     constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
@@ -821,11 +822,13 @@ static int rlaunch_sub(AbR2YBatch & B, cudaStream_t st)
 template <typename RT, typename YT>
 static bool rfast_eligible(const AbR2YJob & J)
 {
-    if (J.mode != AB_MODE_COEFF || J.isGray) return false;
+    const bool identity = (J.mode == AB_MODE_IDENTITY);
+    if ((J.mode != AB_MODE_COEFF && !identity) || J.isGray) return false;
+    if (identity && (!J.hasChroma || J.shiftX || J.alphaMul != AB_MUL_NONE)) return false; /* 4:4:4, straight alpha */
     if (J.nChan != 3 && J.nChan != 4) return false;
     if (!J.rgbMaxDiv.intExact) return false;
-    if (J.hasChroma && (!J.du.exact || !J.dv.exact)) return false;
-    if (AB_R2Y_DIV2 && J.hasChroma && (!J.du.exact2 || !J.dv.exact2)) return false;
+    if (!identity && J.hasChroma && (!J.du.exact || !J.dv.exact)) return false;
+    if (!identity && AB_R2Y_DIV2 && J.hasChroma && (!J.du.exact2 || !J.dv.exact2)) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return false;
     if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return false;
     if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
@@ -870,6 +873,10 @@ static int launch_r2y_fast_typed(const AbR2YJob * jobs, uint32_t n, cudaStream_t
         F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = F.pad = 0;
     }
     const AbR2YJob & J = B.common;
+    if (J.mode == AB_MODE_IDENTITY) { /* lossless GBR: 4:4:4, no alpha arithmetic */
+        if (J.nChan == 3) return rlaunch_cfg<RT, YT, SUB_444, 3, false, AB_MUL_NONE, true>(B, st);
+        return J.alphaFirst ? rlaunch_cfg<RT, YT, SUB_444, 4, true, AB_MUL_NONE, true>(B, st) : rlaunch_cfg<RT, YT, SUB_444, 4, false, AB_MUL_NONE, true>(B, st);
+    }
     if (!J.hasChroma) return rlaunch_sub<RT, YT, SUB_400>(B, st);
     if (!J.shiftX) return rlaunch_sub<RT, YT, SUB_444>(B, st);
     return J.shiftY ? rlaunch_sub<RT, YT, SUB_420>(B, st) : rlaunch_sub<RT, YT, SUB_422>(B, st);

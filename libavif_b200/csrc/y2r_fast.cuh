@@ -40,7 +40,9 @@ enum { CH_FULL = 1, CH_NEAREST = 2, CH_BIL420 = 3, CH_BIL422 = 4 };
 
 enum { OUT_INT = 0, OUT_F16 = 1, OUT_565 = 2 };
 
-template <typename YT_, typename RT_, int CHROMA_, int NCH_, bool AFIRST_, int AW_, int AM_, int OUT_ = OUT_INT>
+enum { MX_COEFF = 0, MX_IDENTITY = 1, MX_IDENTITY8 = 2 };
+
+template <typename YT_, typename RT_, int CHROMA_, int NCH_, bool AFIRST_, int AW_, int AM_, int OUT_ = OUT_INT, int MX_ = MX_COEFF>
 struct Cfg {
     using YT = YT_;
     using RT = RT_;
@@ -49,6 +51,8 @@ struct Cfg {
     static constexpr bool AFIRST = AFIRST_; /* alpha stored before colour */
     static constexpr int AW = AW_;         /* AB_ALPHA_FILL / AB_ALPHA_COPY (NCH == 4) */
     static constexpr int AM = AM_;         /* AB_MUL_* */
+    static constexpr int MX = MX_;         /* MX_COEFF: the kr/kg/kb matrix; MX_IDENTITY: G=Y, B=U, R=V through the luma table (src/reformat.c:846-851,
+                                              :587-589: lossless GBR); MX_IDENTITY8: the 8-bit full-range byte shuffle (:1278-1309) */
     static constexpr int OUT = OUT_;       /* OUT_INT: integer codes; OUT_F16: half floats (src/reformat.c:1419-1443, RT = u16);
                                               OUT_565: RGB565 words (src/reformat.c:619, RT = u8, NCH = 3) */
 };
@@ -425,10 +429,16 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
         for (int t = 0; t < 8; ++t) {
             const float Y = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.yw[r], t, K, mm), magicMax, J.magicBiasY, J.rangeY);
             const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
-            /* ref: src/reformat.c:1014-1016 == :874-876 */
-            float Rv = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
-            float Bv = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
-            float Gv = __fsub_rn(Y, div2x(__fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb)), kgR2, kgDh));
+            float Rv, Gv, Bv;
+            if (C::MX == MX_COEFF) { /* ref: src/reformat.c:1014-1016 == :874-876 */
+                Rv = __fadd_rn(Y, __fmul_rn(J.c1, Cr));
+                Bv = __fadd_rn(Y, __fmul_rn(J.c2, Cb));
+                Gv = __fsub_rn(Y, div2x(__fadd_rn(__fmul_rn(J.c3, Cr), __fmul_rn(J.c4, Cb)), kgR2, kgDh));
+            } else { /* ref: :846-851 (chroma was normalised with the luma bias / range: the host passes them as the UV pair) */
+                Gv = Y;
+                Bv = Cb;
+                Rv = Cr;
+            }
             Rv = clamp01f(Rv);
             Gv = clamp01f(Gv);
             Bv = clamp01f(Bv);
@@ -466,6 +476,11 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
                 }
             }
             float qr = quant_magic(Rv, J.rgbMaxF), qg = quant_magic(Gv, J.rgbMaxF), qb = quant_magic(Bv, J.rgbMaxF);
+            if (C::MX == MX_IDENTITY8) { /* ref: :1278-1309 -- the samples themselves, no arithmetic (4:4:4 only) */
+                qg = magic_sample<YT>(in.yw[r], t, K);
+                qb = magic_sample<YT>(in.uw[0], t, K);
+                qr = magic_sample<YT>(in.vw[0], t, K);
+            }
             if (C::AM == AB_MUL_INT_PREMUL) { /* ref: src/alpha.c:179-192 on the quantised codes */
                 /* a >= max leaves the code untouched and a == 0 zeroes it (src/alpha.c:180-186).  Both fall out of the
                  * arithmetic with a clamped to max: floor(RN(RN(c*max)/max) + 0.5) == c for every code c (the product's
@@ -1095,10 +1110,10 @@ static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups,
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT, int MX = MX_COEFF>
 static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
-    using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT>;
+    using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT, MX>;
     constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0);
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
@@ -1188,6 +1203,32 @@ static int launch_any(AbY2RBatch & B, cudaStream_t st)
     else return launch_cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT>(B, st);
 }
 
+/* identity matrix (lossless GBR, 4:4:4): straight alpha or none, integer outputs */
+template <typename YT, typename RT>
+static int launch_identity(AbY2RBatch & B, cudaStream_t st)
+{
+    const AbY2RJob & J = B.common;
+    if (J.alphaMul != AB_MUL_NONE) return 0;
+    const bool afirst = J.alphaFirst != 0;
+#define ABF_ID(MXV)                                                                                                                     \
+    do {                                                                                                                                \
+        if (J.nChan == 3) return launch_cfg<YT, RT, CH_FULL, 3, false, AB_ALPHA_KEEP, AB_MUL_NONE, OUT_INT, MXV>(B, st);                 \
+        if (J.alphaWrite == AB_ALPHA_FILL)                                                                                              \
+            return afirst ? launch_cfg<YT, RT, CH_FULL, 4, true, AB_ALPHA_FILL, AB_MUL_NONE, OUT_INT, MXV>(B, st)                       \
+                          : launch_cfg<YT, RT, CH_FULL, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, OUT_INT, MXV>(B, st);                     \
+        if (J.alphaWrite == AB_ALPHA_COPY)                                                                                              \
+            return afirst ? launch_cfg<YT, RT, CH_FULL, 4, true, AB_ALPHA_COPY, AB_MUL_NONE, OUT_INT, MXV>(B, st)                       \
+                          : launch_cfg<YT, RT, CH_FULL, 4, false, AB_ALPHA_COPY, AB_MUL_NONE, OUT_INT, MXV>(B, st);                     \
+        return 0;                                                                                                                       \
+    } while (0)
+    if (J.mode == AB_MODE_IDENTITY8_SHUFFLE) {
+        if constexpr (sizeof(YT) == 1 && sizeof(RT) == 1) ABF_ID(MX_IDENTITY8);
+        else return 0;
+    }
+    ABF_ID(MX_IDENTITY);
+#undef ABF_ID
+}
+
 /* half-float and RGB565 outputs (Android's RGBA_F16 / RGB_565 bitmaps, android_jni/.../libavif_jni.cc:206-223): the combinations
  * real callers use -- colour-first layouts, alpha filled, copied or (pre)multiplied the way the reference's variant requires */
 template <typename YT, typename RT, int CHROMA>
@@ -1252,15 +1293,17 @@ static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
 template <typename YT, typename RT>
 static bool fast_eligible(const AbY2RJob & J)
 {
-    if (J.mode != AB_MODE_COEFF || J.isGray || J.chroma == AB_CHROMA_NONE) return false;
+    const bool identity = (J.mode == AB_MODE_IDENTITY || J.mode == AB_MODE_IDENTITY8_SHUFFLE);
+    if ((J.mode != AB_MODE_COEFF && !identity) || J.isGray || J.chroma == AB_CHROMA_NONE) return false;
+    if (identity && (J.chroma != AB_CHROMA_FULL || J.is565 || J.toF16 || J.alphaMul != AB_MUL_NONE)) return false;
     if (J.is565 && sizeof(RT) != 1) return false;
     if (J.toF16 && (sizeof(RT) != 2 || J.alphaFirst)) return false;
     if (!J.is565 && J.nChan != 3 && J.nChan != 4) return false;
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
     /* alpha depth rescale: only the 8 <-> 16-bit container pairs (TileTraits::RESC), whose depths always differ */
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale != (sizeof(YT) != sizeof(RT)))) return false;
-    if (!J.rangeY.intExact || !J.rangeUV.intExact || !J.kg.exact) return false;
-    if (AB_Y2R_DIV2 && !J.kg.exact2) return false;
+    if (!J.rangeY.intExact || !J.rangeUV.intExact) return false;
+    if (!identity && (!J.kg.exact || (AB_Y2R_DIV2 && !J.kg.exact2))) return false;
     if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && (!J.rgbMaxDiv.exact || (AB_Y2R_DIV2 && !J.rgbMaxDiv.exact2))) return false;
     if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
@@ -1323,6 +1366,7 @@ static int launch_y2r_fast_typed(const AbY2RJob * jobs, uint32_t n, cudaStream_t
     const bool afirst = J.alphaFirst != 0;
     const int nch = J.nChan;
     const bool special = J.is565 || J.toF16;
+    if (J.mode == AB_MODE_IDENTITY || J.mode == AB_MODE_IDENTITY8_SHUFFLE) return launch_identity<YT, RT>(B, st);
 #define ABF_DISPATCH(CH)                                                              \
     do {                                                                              \
         if (special) return launch_special<YT, RT, CH>(B, st);                        \

@@ -109,6 +109,27 @@ def test_y2r_fast_kernels_serve_android_outputs(gpu_product, oracle):
                         assert name.startswith("y2r_fast"), (spec.ident(), name)
 
 
+def test_identity_matrix_runs_on_the_fast_kernels(gpu_product, oracle):
+    """Lossless GBR (matrix coefficients 0, 4:4:4): both directions on the specialised kernels, every depth, limited and full range,
+    colour-first and alpha-first layouts, straight alpha."""
+    k = 0
+    for depth, rgb_depth in [(8, 8), (10, 10), (12, 12), (16, 16), (8, 16), (12, 8)]:
+        for rng in (0, 1):
+            for rgb_fmt in [abi.AVIF_RGB_FORMAT_RGB, abi.AVIF_RGB_FORMAT_RGBA, abi.AVIF_RGB_FORMAT_BGRA, abi.AVIF_RGB_FORMAT_ARGB, abi.AVIF_RGB_FORMAT_BGR]:
+                for alpha in (False, True):
+                    k += 1
+                    w, h = [(264, 6), (520, 5), (1000, 4), (2056, 3)][k % 4]
+                    spec = util.Spec(w=w, h=h, depth=depth, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rng=rng, mc=abi.MC_IDENTITY, alpha=alpha, rgb_depth=rgb_depth,
+                                     rgb_fmt=rgb_fmt, garbage=(k % 3 == 0))
+                    assert _check_y2r(gpu_product, oracle, spec, 9700 + k, device="cuda:0") == 0
+                    if not (alpha and abi.rgb_format_has_alpha(rgb_fmt) and depth != rgb_depth and (depth > 8) == (rgb_depth > 8)):
+                        assert gpu_product.avifB200LastKernelName().decode().startswith("y2r_fast"), spec.ident()
+                    if not alpha:
+                        assert _check_r2y(gpu_product, oracle, spec, 9800 + k, device="cuda:0") == 0
+                        if depth == rgb_depth or not abi.rgb_format_has_alpha(rgb_fmt):
+                            assert gpu_product.avifB200LastKernelName().decode().startswith("r2y_fast"), spec.ident()
+
+
 def test_r2y_fast_kernels_are_used_and_exact(gpu_product, oracle):
     import itertools
     sizes = [(264, 6), (520, 5), (1000, 4), (257, 7), (8, 3), (2056, 3), (1, 1), (9, 2)]
