@@ -97,11 +97,24 @@ __device__ __forceinline__ int scale_sample(const AbScaleJob & J, const int32_t 
         case AB_SCALE_BOX: { /* rows: iy, boxheight ; cols: ix, boxwidth, table index */
             const int iy = R[0], bh = R[1], ix = C[0], bw = C[1];
             uint32_t sum = 0;
-            for (int c = 0; c < bw; ++c) {
-                uint32_t col = 0; /* ScaleAddRow: one accumulator per source column */
-                for (int r = 0; r < bh; ++r) col += (uint32_t)ld<T>(J, iy + r, ix + c);
-                if (sizeof(T) == 1) col &= 0xFFFFu; /* uint16_t accumulators wrap (scale_common.c:316-328) */
-                sum += col;
+            if (iy >= 0 && ix >= 0 && iy + bh <= J.srcH && ix + bw <= J.srcW) {
+                /* the box lies inside the plane (always, for the positions libyuv generates): plain pointer walk instead of
+                 * a clamped address computation per tap */
+                const T * p0 = reinterpret_cast<const T *>(J.src + (int64_t)iy * J.srcRB) + ix;
+                for (int c = 0; c < bw; ++c) {
+                    uint32_t col = 0; /* ScaleAddRow: one accumulator per source column */
+                    const uint8_t * q = reinterpret_cast<const uint8_t *>(p0 + c);
+                    for (int r = 0; r < bh; ++r, q += J.srcRB) col += (uint32_t)*reinterpret_cast<const T *>(q);
+                    if (sizeof(T) == 1) col &= 0xFFFFu; /* uint16_t accumulators wrap (scale_common.c:316-328) */
+                    sum += col;
+                }
+            } else {
+                for (int c = 0; c < bw; ++c) {
+                    uint32_t col = 0;
+                    for (int r = 0; r < bh; ++r) col += (uint32_t)ld<T>(J, iy + r, ix + c);
+                    if (sizeof(T) == 1) col &= 0xFFFFu;
+                    sum += col;
+                }
             }
             int wdiv = J.minBoxWidth + C[2];
             if (wdiv < 1) wdiv = 1;

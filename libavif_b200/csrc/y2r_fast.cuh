@@ -39,6 +39,9 @@ using namespace ab;
 enum { CH_FULL = 1, CH_NEAREST = 2, CH_BIL420 = 3, CH_BIL422 = 4 };
 
 enum { OUT_INT = 0, OUT_F16 = 1, OUT_565 = 2 };
+/* AW value of the kernel templates only: alpha copied from a plane of another DEPTH in the same container size (10 / 12-bit planes
+ * into 16-bit channels, e.g. HDR images into half floats): src/alpha.c:93-97 rescale.  Containers of different size always rescale. */
+constexpr int AW_COPY_RESC = 3;
 
 enum { MX_COEFF = 0, MX_IDENTITY = 1, MX_IDENTITY8 = 2 };
 
@@ -215,10 +218,10 @@ struct TileTraits {
     static constexpr int ROWS = (C::CHROMA == CH_BIL420) ? 2 : 1;
     static constexpr int CROWS = ROWS;
     static constexpr int PIXB = (C::OUT == OUT_565) ? 2 : C::NCH * (int)sizeof(RT);
-    static constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY);
-    /* alpha plane depth != channel depth (src/alpha.c:93-97).  The specialised kernels meet it exactly when the containers
-     * differ (8-bit planes into 16-bit channels or the reverse); equal containers of different depth stay on the general kernel */
-    static constexpr bool RESC = HAS_A && (sizeof(YT) != sizeof(RT));
+    static constexpr bool HAS_A = (C::NCH == 4) && (C::AW == AB_ALPHA_COPY || C::AW == AW_COPY_RESC);
+    /* alpha plane depth != channel depth (src/alpha.c:93-97): always when the containers differ (8-bit planes into 16-bit channels
+     * or the reverse), by request (AW_COPY_RESC) for equal containers */
+    static constexpr bool RESC = HAS_A && (sizeof(YT) != sizeof(RT) || C::AW == AW_COPY_RESC);
     static constexpr bool NEED_A = HAS_A || (C::AM != AB_MUL_NONE);
     static constexpr int CW = SUB ? 2 : 4; /* words of one chroma row of the lane */
 };
@@ -1114,7 +1117,9 @@ template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, in
 static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT, MX>;
-    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0);
+    /* the strip kernel pays where the tile needs no alpha rows (C5 -3 %, C1 -7 %); with them its 12 carried registers spill and it
+     * measured 14 % SLOWER than the group kernel (C3 110 vs 96.6 us, profiles/r02_variants.md) */
+    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0) && !TileTraits<C>::NEED_A;
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbY2RFrame & F = B.frame[f];
@@ -1209,6 +1214,7 @@ static int launch_identity(AbY2RBatch & B, cudaStream_t st)
 {
     const AbY2RJob & J = B.common;
     if (J.alphaMul != AB_MUL_NONE) return 0;
+    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale && sizeof(YT) == sizeof(RT)) return 0;
     const bool afirst = J.alphaFirst != 0;
 #define ABF_ID(MXV)                                                                                                                     \
     do {                                                                                                                                \
@@ -1251,6 +1257,16 @@ static int launch_special(AbY2RBatch & B, cudaStream_t st)
         }
         if (J.alphaWrite == AB_ALPHA_FILL) return (J.alphaMul == AB_MUL_NONE) ? launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_FILL, AB_MUL_NONE, OUT_F16>(B, st) : 0;
         if (J.alphaWrite != AB_ALPHA_COPY) return 0;
+        if constexpr (sizeof(YT) == 2) {
+            if (J.alphaRescale) { /* 10 / 12-bit image into half floats: the usual HDR case */
+                switch (J.alphaMul) {
+                    case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_NONE, OUT_F16>(B, st);
+                    case AB_MUL_INT_PREMUL: return slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_INT_PREMUL, OUT_F16>(B, st);
+                    case AB_MUL_FLOAT_MUL: return !slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_FLOAT_MUL, OUT_F16>(B, st);
+                    default: return 0;
+                }
+            }
+        }
         switch (J.alphaMul) {
             case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_NONE, OUT_F16>(B, st);
             case AB_MUL_INT_PREMUL: return slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AB_ALPHA_COPY, AB_MUL_INT_PREMUL, OUT_F16>(B, st); /* depth 16: no fma form */
@@ -1275,6 +1291,19 @@ static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
         return 0;
     }
     if (J.alphaWrite != AB_ALPHA_COPY) return 0;
+    if constexpr (sizeof(YT) == 2 && sizeof(RT) == 2 && !AFIRST) {
+        if (J.alphaRescale) { /* 10 / 12-bit alpha plane into deeper 16-bit-container channels (or the reverse) */
+            switch (J.alphaMul) {
+                case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_NONE>(B, st);
+                case AB_MUL_INT_PREMUL:
+                    if (slow) return 0;
+                    if (J.pmR != 0.0f) return launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_INT_PREMUL_FMA>(B, st);
+                    return launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_INT_PREMUL>(B, st);
+                case AB_MUL_FLOAT_MUL: return !slow ? 0 : launch_any<YT, RT, CHROMA, 4, false, AW_COPY_RESC, AB_MUL_FLOAT_MUL>(B, st);
+                default: return 0;
+            }
+        }
+    }
     switch (J.alphaMul) {
         case AB_MUL_NONE: return launch_any<YT, RT, CHROMA, 4, AFIRST, AB_ALPHA_COPY, AB_MUL_NONE>(B, st);
         case AB_MUL_INT_PREMUL:
@@ -1301,11 +1330,13 @@ static bool fast_eligible(const AbY2RJob & J)
     if (!J.is565 && J.nChan != 3 && J.nChan != 4) return false;
     if (J.hasAlphaChan && J.alphaWrite == AB_ALPHA_KEEP) return false;
     /* alpha depth rescale: only the 8 <-> 16-bit container pairs (TileTraits::RESC), whose depths always differ */
-    if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale != (sizeof(YT) != sizeof(RT)))) return false;
+    if (J.alphaWrite == AB_ALPHA_COPY && sizeof(YT) != sizeof(RT) && !J.alphaRescale) return false; /* cannot happen: depths differ */
+    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale && sizeof(YT) == sizeof(RT) && (J.alphaFirst || sizeof(YT) == 1)) return false;
     if (!J.rangeY.intExact || !J.rangeUV.intExact) return false;
     if (!identity && (!J.kg.exact || (AB_Y2R_DIV2 && !J.kg.exact2))) return false;
     if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && (!J.rgbMaxDiv.exact || (AB_Y2R_DIV2 && !J.rgbMaxDiv.exact2))) return false;
     if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
+    if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale && !J.yuvMaxDiv.intExact) return false;
     const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
     const bool sub = (J.chroma != AB_CHROMA_FULL);
     uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;

@@ -139,6 +139,41 @@ def test_grid_plane_staging(gpu_product, fmt, depth):
         assert (dst.plane_samples(p) == exp).all(), f"plane {p}"
 
 
+@pytest.mark.parametrize("fmt", [A.AVIF_PIXEL_FORMAT_YUV444, A.AVIF_PIXEL_FORMAT_YUV422, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_PIXEL_FORMAT_YUV400])
+@pytest.mark.parametrize("depth", [8, 10])
+def test_copy_samples_against_the_compiled_reference(gpu_product, reference, fmt, depth):
+    """avifB200ImageCopySamplesAsync against the reference's own avifImageCopySamples (src/avif.c:187-225, compiled into
+    oracle/_ref): 3x2 tiles of a padded canvas, YUV-only / alpha-only / all planes, destination bytes outside the copied area untouched."""
+    import torch
+    from libavif_b200 import sharding
+    raw = reference.raw
+    raw.avifImageCopySamples.restype = None
+    raw.avifImageCopySamples.argtypes = [ctypes.POINTER(A.avifImage), ctypes.POINTER(A.avifImage), ctypes.c_uint32]
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rs = np.random.RandomState(100 + depth + fmt)
+    cw, ch = 334, 150
+    for planes in (A.AVIF_PLANES_ALL, A.AVIF_PLANES_YUV, A.AVIF_PLANES_A):
+        host = YUVImage(cw, ch, depth, fmt, alpha=True, row_pad=6)
+        dev = YUVImage(cw, ch, depth, fmt, alpha=True, device="cuda:0", row_pad=6)
+        for p in host.present_planes():
+            fill = rs.randint(0, 256, size=(host.bufs[p].rows, host.bufs[p].row_bytes)).astype(np.uint8)
+            host.bufs[p].set(fill)
+            dev.bufs[p].set(fill)
+        for r in sharding.split_grid(cw, ch, 3, 2, fmt):
+            t_host = YUVImage(r.width, r.height, depth, fmt, alpha=True, row_pad=2)
+            t_dev = YUVImage(r.width, r.height, depth, fmt, alpha=True, device="cuda:0", row_pad=2)
+            for p in t_host.present_planes():
+                data = rs.randint(0, 256, size=(t_host.bufs[p].rows, t_host.bufs[p].row_bytes)).astype(np.uint8)
+                t_host.bufs[p].set(data)
+                t_dev.bufs[p].set(data)
+            vh, vd = sharding.view_yuv(host.c, r), sharding.view_yuv(dev.c, r)
+            raw.avifImageCopySamples(ctypes.byref(vh), t_host.ptr(), planes)
+            assert gpu_product.avifB200ImageCopySamplesAsync(ctypes.byref(vd), t_dev.ptr(), planes, stream) == 0
+        torch.cuda.synchronize()
+        for p in host.present_planes():
+            assert np.array_equal(host.bufs[p].host(), dev.bufs[p].host()), (planes, p)
+
+
 def test_concurrent_host_threads(gpu_product, oracle):
     """The entry points are re-entrant (the reference is exercised under TSan with concurrent calls on different images):
     all library state is thread-local.  8 host threads convert different frames at once, host and device pointers mixed."""

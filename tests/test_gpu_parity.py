@@ -104,7 +104,7 @@ def test_y2r_fast_kernels_serve_android_outputs(gpu_product, oracle):
                                      rgb_fmt=rgb_fmt, ups=ups, rgb_premult=rp, is_float=is_float, garbage=(k % 3 == 0))
                     assert _check_y2r(gpu_product, oracle, spec, 9900 + k, device="cuda:0") == 0
                     name = gpu_product.avifB200LastKernelName().decode()
-                    unmul = alpha and ip and not rp and abi.rgb_format_has_alpha(rgb_fmt)  # F16 / mixed-depth unmultiply: general kernel
+                    unmul = alpha and ip and not rp and abi.rgb_format_has_alpha(rgb_fmt)  # F16 / rescaled unmultiply: general kernel
                     if not unmul and w != 257:  # 257-sample rows are not vector-aligned on the device: those stay on the general kernel
                         assert name.startswith("y2r_fast"), (spec.ident(), name)
 
