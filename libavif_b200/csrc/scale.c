@@ -9,6 +9,7 @@
 #include "avif_b200.h"
 
 #include <cuda_runtime_api.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -293,15 +294,98 @@ typedef struct PlaneIO { /* one plane, both ends on the device; strides in bytes
     int sw, sh, dw, dh;
 } PlaneIO;
 
+/* Position tables depend on the four dimensions (and the sample size) only, and a scaling service sees the same few geometries
+ * over and over (tiles of one size, gain maps of one size): the first call for a geometry replays libyuv's state machines on the
+ * host and uploads the tables, later calls find them resident.  Process-wide, per device, at most kPlanCacheSize geometries
+ * (a few megabytes); entries are immutable and live until the process exits; when the cache is full further geometries are
+ * planned and uploaded per call as before. */
+enum { kPlanCacheSize = 32 };
+typedef struct PlanCacheEntry {
+    int used, device, sw, sh, dw, dh, sixteen;
+    int mode, linearOnly, minBoxWidth;
+    int32_t * dRows;
+    int32_t * dCols;
+} PlanCacheEntry;
+static PlanCacheEntry gPlanCache[kPlanCacheSize];
+static pthread_mutex_t gPlanLock = PTHREAD_MUTEX_INITIALIZER;
+
+/* 1: *out is valid (found or inserted); 0: not cacheable now (cache full / no memory) -- the caller plans per call */
+static int planCacheGet(int sw, int sh, int dw, int dh, int sixteen, PlanCacheEntry * out)
+{
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int found = 0;
+    pthread_mutex_lock(&gPlanLock);
+    int freeSlot = -1;
+    for (int k = 0; k < kPlanCacheSize; ++k) {
+        PlanCacheEntry * c = &gPlanCache[k];
+        if (!c->used) {
+            if (freeSlot < 0) freeSlot = k;
+            continue;
+        }
+        if (c->device == device && c->sw == sw && c->sh == sh && c->dw == dw && c->dh == dh && c->sixteen == sixteen) {
+            *out = *c;
+            found = 1;
+            break;
+        }
+    }
+    if (!found && freeSlot >= 0) {
+        ScalePlan plan;
+        memset(&plan, 0, sizeof(plan));
+        if (planScale(sw, sh, dw, dh, sixteen, &plan)) {
+            PlanCacheEntry c;
+            memset(&c, 0, sizeof(c));
+            c.used = 1;
+            c.device = device;
+            c.sw = sw; c.sh = sh; c.dw = dw; c.dh = dh; c.sixteen = sixteen;
+            c.mode = plan.mode;
+            c.linearOnly = plan.linearOnly;
+            c.minBoxWidth = plan.minBoxWidth;
+            int ok = 1;
+            if (plan.mode) {
+                const size_t rb = (size_t)dh * 4 * sizeof(int32_t), cb = (size_t)dw * 4 * sizeof(int32_t);
+                ok = cudaMalloc((void **)&c.dRows, rb + cb) == cudaSuccess;
+                if (ok) {
+                    c.dCols = c.dRows + (size_t)dh * 4;
+                    ok = cudaMemcpy(c.dRows, plan.rows, rb, cudaMemcpyHostToDevice) == cudaSuccess &&
+                         cudaMemcpy(c.dCols, plan.cols, cb, cudaMemcpyHostToDevice) == cudaSuccess;
+                    if (!ok) (void)cudaFree(c.dRows);
+                }
+                if (!ok) (void)cudaGetLastError();
+            }
+            if (ok) {
+                gPlanCache[freeSlot] = c;
+                *out = c;
+                found = 1;
+            }
+        }
+        planFree(&plan);
+    }
+    pthread_mutex_unlock(&gPlanLock);
+    return found;
+}
+
 /* Up to four planes of one image: their position tables go up in ONE copy, the samples are produced by ONE launch. */
 static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, int * oom)
 {
     ScalePlan plans[AB_SCALE_MAX_PLANES];
+    PlanCacheEntry cached[AB_SCALE_MAX_PLANES];
+    int isCached[AB_SCALE_MAX_PLANES] = { 0, 0, 0, 0 };
     memset(plans, 0, sizeof(plans));
     size_t tableInts = 0;
     cudaError_t e = cudaSuccess;
     int32_t *hTab = NULL, *dTab = NULL;
     for (int k = 0; k < count; ++k) {
+        isCached[k] = planCacheGet(io[k].sw, io[k].sh, io[k].dw, io[k].dh, bps == 2, &cached[k]);
+        if (isCached[k]) {
+            plans[k].mode = cached[k].mode;
+            plans[k].linearOnly = cached[k].linearOnly;
+            plans[k].minBoxWidth = cached[k].minBoxWidth;
+            continue;
+        }
         if (!planScale(io[k].sw, io[k].sh, io[k].dw, io[k].dh, bps == 2, &plans[k])) {
             *oom = 1;
             goto done;
@@ -340,6 +424,11 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
         job->mode = (uint8_t)plans[k].mode;
         job->linearOnly = (uint8_t)plans[k].linearOnly;
         job->minBoxWidth = plans[k].minBoxWidth;
+        if (isCached[k]) {
+            job->rows = cached[k].dRows;
+            job->cols = cached[k].dCols;
+            continue;
+        }
         memcpy(hTab + at, plans[k].rows, (size_t)io[k].dh * 4 * sizeof(int32_t));
         job->rows = dTab + at;
         at += (size_t)io[k].dh * 4;
@@ -348,7 +437,7 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
         at += (size_t)io[k].dw * 4;
     }
     if (batch.count) {
-        e = cudaMemcpyAsync(dTab, hTab, tableInts * sizeof(int32_t), cudaMemcpyHostToDevice, AB_STREAM);
+        if (tableInts) e = cudaMemcpyAsync(dTab, hTab, tableInts * sizeof(int32_t), cudaMemcpyHostToDevice, AB_STREAM);
         if (e == cudaSuccess) e = (cudaError_t)abLaunchScaleBatch(&batch, AB_STREAM);
     }
     /* hTab is pageable: the copy has been staged when cudaMemcpyAsync returns, but one synchronisation per image keeps the

@@ -122,7 +122,9 @@ def test_identity_matrix_runs_on_the_fast_kernels(gpu_product, oracle):
                     spec = util.Spec(w=w, h=h, depth=depth, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rng=rng, mc=abi.MC_IDENTITY, alpha=alpha, rgb_depth=rgb_depth,
                                      rgb_fmt=rgb_fmt, garbage=(k % 3 == 0))
                     assert _check_y2r(gpu_product, oracle, spec, 9700 + k, device="cuda:0") == 0
-                    if not (alpha and abi.rgb_format_has_alpha(rgb_fmt) and depth != rgb_depth and (depth > 8) == (rgb_depth > 8)):
+                    rescale_same_container = alpha and abi.rgb_format_has_alpha(rgb_fmt) and depth != rgb_depth and (depth > 8) == (rgb_depth > 8)
+                    multiply_in_float = alpha and not abi.rgb_format_has_alpha(rgb_fmt)  # straight alpha folded into a colour-only output
+                    if not rescale_same_container and not multiply_in_float:
                         assert gpu_product.avifB200LastKernelName().decode().startswith("y2r_fast"), spec.ident()
                     if not alpha:
                         assert _check_r2y(gpu_product, oracle, spec, 9800 + k, device="cuda:0") == 0
