@@ -592,13 +592,16 @@ def run_b200(args):
     # ---------------- host-buffer (end-to-end) legs: pinned, then pageable ----------------
     Be = args.e2e_batch
     cpus_before = os.sched_getaffinity(0)
+    total_usable = usable_cpus()  # affinity mask capped by the cgroup quota, before the NUMA pinning below
     local_cpus = gpu_local_cpus(local)
     if local_cpus:
         os.sched_setaffinity(0, local_cpus)  # pinned buffers are first-touched, and the workers run, next to this rank's GPU
     from concurrent.futures import ThreadPoolExecutor
-    nthr = max(1, min(args.e2e_threads, Be, max(1, usable_cpus() // (world if not local_cpus else 1))))
-    if local_cpus and world > 1:
-        nthr = max(1, min(nthr, max(1, (os.cpu_count() or 8) // world)))
+    nthr = max(1, min(args.e2e_threads, Be, max(1, total_usable // world)))  # ranks share the host's cores
+
+    # helper threads of the pageable leg must fit next to the callers: rgb.maxThreads = calling thread + helpers
+    cpus_per_rank = max(1, total_usable // world)
+    stage_threads = max(1, min(args.stage_threads, cpus_per_rank // max(1, nthr)))
 
     def worker_init():
         # every worker thread of this rank talks to this rank's GPU (shim.c: a thread without a choice is dealt a device round-robin)
@@ -612,7 +615,7 @@ def run_b200(args):
             fill_uniform(src, 500 + rank * 1000 + f)
             # pageable leg: rgb.maxThreads = 3 lets the library share the staging copies with two helper threads per call
             # (the reference spends maxThreads threads on the conversion itself, src/reformat.c:1679-1747)
-            hframes.append((src, wl.make_rgb("C2", pinned=pinned, max_threads=1 if pinned else args.stage_threads), wl.make_yuv("C2", pinned=pinned)))
+            hframes.append((src, wl.make_rgb("C2", pinned=pinned, max_threads=1 if pinned else stage_threads), wl.make_yuv("C2", pinned=pinned)))
 
         def e2e_frames(chunk):  # one host thread: its frames, one synchronous round trip after the other
             for src, rgb, back in chunk:
@@ -701,7 +704,7 @@ def run_b200(args):
                 "frames_per_step_per_gpu": Be, "steps": e2e_steps, "host_memory": "pinned", "host_threads": nthr,
                 "device_affinity": "every worker thread: avifB200SetDevice(LOCAL_RANK); process pinned to the GPU's NUMA-local CPUs" if local_cpus else "every worker thread: avifB200SetDevice(LOCAL_RANK)",
                 "api": "avifImageYUVToRGB / avifImageRGBToYUV (C-ABI, host pointers)", "check": e2e_ok},
-        "e2e_pageable": {"value": pg_value, "unit": "Mpixels/s", "steps": pg_steps, "host_memory": "pageable (numpy / malloc), staged through the library's pinned ring", "rgb_maxThreads": args.stage_threads,
+        "e2e_pageable": {"value": pg_value, "unit": "Mpixels/s", "steps": pg_steps, "host_memory": "pageable (numpy / malloc), staged through the library's pinned ring", "rgb_maxThreads": stage_threads,
                          "host_threads": nthr, "frac_of_pinned": pg_value / e2e_value if e2e_value else None, "check": pg_ok},
         "gpu_launches": launches,
         "roofline": roofline,

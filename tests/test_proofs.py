@@ -1,0 +1,33 @@
+"""The exhaustive proofs behind the kernels' shorter arithmetic forms are programs in tools/:
+this runs the quick ones in full -- the YUV->RGB quantiser fusion over every float in [0,1] for all four channel maxima, the
+two-operation division over all 2^32 numerators for three divisors including the one it must refuse -- and checks that the
+exception list compiled into the library is exactly what the program finds.  (The 16-pair `quant` proof and the other 53 divisors
+take minutes: run `tools/verify_quant.c` by hand; the device re-runs the division proof in tests/test_gpu_division.py.)"""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "vq")
+    subprocess.run(["gcc", "-O2", "-mfma", "-fopenmp", "-ffp-contract=off", os.path.join(ROOT, "tools", "verify_quant.c"), "-o", exe, "-lm"], check=True)
+    return exe
+
+
+def test_rgb_quantiser_fusion_is_exact_on_the_whole_unit_interval(tmp_path):
+    out = subprocess.run([_build(tmp_path), "rgbquant"], check=True, capture_output=True, text=True, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.startswith("rgb depth")]
+    assert len(lines) == 4 and all(l.endswith("bad=0") for l in lines), out
+
+
+def test_two_operation_division_and_its_exception(tmp_path):
+    hdr = open(os.path.join(ROOT, "libavif_b200", "csrc", "verified_divisors.h")).read()
+    refused = re.search(r"kAbNotTwoOpDivisors\[\] = \{([^}]*)\}", hdr).group(1)
+    refused = [int(x.strip().rstrip("u"), 16) for x in refused.split(",") if x.strip()]
+    assert refused == [0x3FEE5BB7]
+    out = subprocess.run([_build(tmp_path), "div", "3fc9930c", "3fee5bb7", "477fff00"], check=True, capture_output=True, text=True, timeout=600).stdout
+    bad = {int(l.split()[0], 16): int(l.split("bad=")[1]) for l in out.splitlines() if "bad=" in l}
+    assert bad[0x3FC9930C] == 0 and bad[0x477FFF00] == 0
+    assert bad[0x3FEE5BB7] > 0  # the listed exception really fails: it keeps the three-operation form
