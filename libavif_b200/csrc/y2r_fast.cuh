@@ -1348,7 +1348,9 @@ static bool fast_eligible(const AbY2RJob & J)
     if (bits & lumaAlign) return false;
     const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
     if (cbits & (sub ? subAlign : lumaAlign)) return false;
-    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & 15) return false;
+    /* a lane stores its 8 pixels as 16-byte vectors, 3-byte pixels (24 bytes per lane) as 8-byte ones */
+    const uintptr_t pixb = J.is565 ? 2 : (uintptr_t)J.nChan * sizeof(RT);
+    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & (((8 * pixb) % 16 == 0) ? 15 : 7)) return false;
     if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
     return true;
 }

@@ -39,7 +39,8 @@ for c in cases:
         while pos < len(ours) and match not in ours[pos][ix["Kernel Name"]]:
             pos += 1
         grp = []
-        while pos < len(ours) and match in ours[pos][ix["Kernel Name"]]:
+        limit = int(c.get("launches", 0))  # helper cases that share a kernel name (the two scaling cases) say how many launches are theirs
+        while pos < len(ours) and match in ours[pos][ix["Kernel Name"]] and (not limit or len(grp) < limit):
             grp.append(ours[pos])
             pos += 1
         if not grp:

@@ -127,7 +127,7 @@ if "--reformat-only" not in sys.argv:
         for _ in range(2):
             assert lib.avifB200ImageScaleToDevice(s_img.ptr(), d_img.ptr()) == 0
         torch.cuda.synchronize()
-        order.append({"case": f"SC_{sw}x{sh}_to_{dw}x{dh}", "kernel": "scale", "frames": 1, "px_per_frame": sw * sh + dw * dh, "alg_bytes_per_px": 2.5, "match": "scale_"})
+        order.append({"case": f"SC_{sw}x{sh}_to_{dw}x{dh}", "kernel": "scale", "frames": 1, "px_per_frame": sw * sh + dw * dh, "alg_bytes_per_px": 2.5, "match": "scale_", "launches": 2})
 
 os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
 json.dump(order, open(out_path, "w"), indent=1)
