@@ -242,6 +242,7 @@ typedef struct AbScaleJob {
     uint8_t pad;
     int32_t minBoxWidth; /* box: dx >> 16 (or the constant box width) */
     int32_t segLen;      /* destination samples per unit of work (a multiple of 8 bytes); filled by the launcher */
+    int32_t rowsPerUnit; /* destination rows per unit of work; filled by the launcher */
     const int32_t * rows; /* 4 ints per destination row, meaning depends on mode (scale_kernels.cu) */
     const int32_t * cols; /* 4 ints per destination column */
 } AbScaleJob;

@@ -167,29 +167,25 @@ __device__ __forceinline__ void up2_group(const AbScaleJob & J, int i0, int j, i
 }
 
 /* ---- row-staged loops --------------------------------------------------------------------------------------------------
- * A block produces one SEGMENT of one destination row at a time.  Phase 1: the source columns the segment needs are read with
- * 16-byte loads, combined VERTICALLY the way the loop does it first (box: ScaleAddRow's column sums; bilinear down:
- * InterpolateRow; bilinear up / point sampling: the raw rows) and parked in shared memory, so every source byte is read from
- * HBM once and in full sectors.  Phase 2: each thread produces 8 bytes of the destination row from shared memory with the
- * loop's HORIZONTAL arithmetic and stores them as one vector.  Units that do not fit (ratios beyond the staging buffer, boxes
- * hanging over the plane) take the table-driven sampler above. */
-enum { kStageBytes = 24576, kScaleThreads = 128 };
+ * A WARP produces one segment (32 lanes x 8 bytes) of one destination row at a time, independently of the other warps of its
+ * block (its own slice of shared memory, __syncwarp only), so an SM keeps 40 units in flight.  Phase 1: the source columns the
+ * segment needs are read with 16-byte loads, combined VERTICALLY the way the loop does it first (box: ScaleAddRow's column
+ * sums; bilinear down: InterpolateRow; bilinear up, point sampling, 2x up-scaling: the raw rows) and parked in shared memory, so
+ * every source byte is read from HBM once and in full sectors.  Phase 2: each lane produces 8 bytes of the destination row from
+ * shared memory with the loop's HORIZONTAL arithmetic and stores them as one vector.  Units that do not fit (ratios beyond the
+ * staging slice, boxes hanging over the plane) take the table-driven sampler above. */
+enum { kScaleWarps = 8, kScaleThreads = kScaleWarps * 32, kStageBytes = 3072 /* per warp */ };
 
 template <typename T> struct Vec16; /* 16 bytes of samples */
 template <> struct Vec16<uint8_t> { enum { N = 16 }; };
 template <> struct Vec16<uint16_t> { enum { N = 8 }; };
 
+/* sample e of a 16-byte vector */
 template <typename T>
-__device__ __forceinline__ void unpack16(const uint4 & v, int s[16 / sizeof(T)])
+__device__ __forceinline__ uint32_t vec_sample(const uint4 & v, int e)
 {
-    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    if (sizeof(T) == 1) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) s[k % (16 / sizeof(T))] = (int)((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = (int)((w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu);
-    }
+    const uint32_t w = (sizeof(T) == 1) ? ((e < 4) ? v.x : (e < 8) ? v.y : (e < 12) ? v.z : v.w) : ((e < 2) ? v.x : (e < 4) ? v.y : (e < 6) ? v.z : v.w);
+    return (sizeof(T) == 1) ? ((w >> (8 * (e & 3))) & 0xFFu) : ((w >> (16 * (e & 1))) & 0xFFFFu);
 }
 
 template <typename T>
@@ -197,6 +193,23 @@ __device__ __forceinline__ const T * src_row(const AbScaleJob & J, int y)
 {
     y = min(max(y, 0), J.srcH - 1);
     return reinterpret_cast<const T *>(J.src + (int64_t)y * J.srcRB);
+}
+
+/* samples a0 + k .. a0 + k + VL of a source row as one vector (columns past the plane replicate the last one: they only ever meet
+ * zero weights) */
+template <typename T>
+__device__ __forceinline__ uint4 load_vec(const AbScaleJob & J, const T * row, int a, bool srcAligned)
+{
+    constexpr int VL = Vec16<T>::N;
+    if (srcAligned && a + VL <= J.srcW) return __ldg(reinterpret_cast<const uint4 *>(row + a));
+    uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int e = 0; e < VL; ++e) {
+        const uint32_t s = (uint32_t)row[min(a + e, J.srcW - 1)];
+        if (sizeof(T) == 1) w[e >> 2] |= s << (8 * (e & 3));
+        else w[e >> 1] |= s << (16 * (e & 1));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 /* 8 bytes of destination row j starting at sample i (i + VEC may run past i1: the tail is stored sample by sample) */
@@ -223,269 +236,384 @@ __device__ __forceinline__ void store_group(const AbScaleJob & J, int j, int i, 
     }
 }
 
-/* Phase 1 for NR source rows y[0..NR): samples a0 .. a0 + span of each, handed VL at a time to `sink(k, rows)`, rows[r][e] =
- * sample a0 + k + e of row r.  Vector loads where the rows are 16-byte aligned and the vector lies inside the plane. */
-template <typename T, int NR, typename Sink>
-__device__ __forceinline__ void stage_rows(const AbScaleJob & J, const int y[NR], int nr, int a0, int span, bool srcAligned, Sink sink)
+/* raw samples a0 .. a0 + span of one source row into a staging array of T */
+template <typename T>
+__device__ __forceinline__ void stage_raw(const AbScaleJob & J, int y, int a0, int span, bool srcAligned, T * st, uint32_t lane)
 {
     constexpr int VL = Vec16<T>::N;
-    const T * row[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) row[r] = src_row<T>(J, y[r < nr ? r : 0]);
-    for (int k = (int)threadIdx.x * VL; k < span; k += kScaleThreads * VL) {
-        int s[NR][VL];
-        if (srcAligned && a0 + k + VL <= J.srcW) {
-            uint4 v[NR];
-#pragma unroll
-            for (int r = 0; r < NR; ++r)
-                if (r < nr) v[r] = __ldg(reinterpret_cast<const uint4 *>(row[r] + a0 + k));
-#pragma unroll
-            for (int r = 0; r < NR; ++r)
-                if (r < nr) unpack16<T>(v[r], s[r]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < NR; ++r)
-#pragma unroll
-                for (int e = 0; e < VL; ++e) s[r][e] = (r < nr) ? (int)row[r][min(a0 + k + e, J.srcW - 1)] : 0;
-        }
-        sink(k, s);
-    }
+    const T * row = src_row<T>(J, y);
+    for (int k = (int)lane * VL; k < span; k += 32 * VL) *reinterpret_cast<uint4 *>(st + k) = load_vec<T>(J, row, a0 + k, srcAligned);
 }
+
+/* A unit of work: destination rows j0..j1 of the segment i0..i1 of one plane.  Whatever depends on the COLUMN only -- the source
+ * span of the segment, each output's staging offsets and fraction -- is derived once per unit and kept in one packed register per
+ * output; the row loop then only stages and filters. */
+struct Seg {
+    int i0, i1, j0, j1;
+    bool srcAligned, dstAligned;
+    uint32_t lane;
+};
+
+template <typename T>
+__device__ __noinline__ void rows_generic(const AbScaleJob & J, const Seg & S, int ja, int jb);
 
 /* ScalePlaneBox (scale.c:148-256): column sums of the box rows (ScaleAddRow; 8-bit sums live in uint16_t and wrap), then
- * ScaleAddCols0/1/2 (scale_common.c) over them */
+ * ScaleAddCols0/1/2 (scale_common.c) over them.  A box is minBoxWidth or minBoxWidth + 1 columns wide (x advances by dx). */
+template <typename T, int M>
+__device__ __forceinline__ uint32_t box_sum(const typename std::conditional<sizeof(T) == 1, uint16_t, uint32_t>::type * q, int m, uint32_t extra)
+{
+    uint32_t sum = 0;
+    if (M > 0) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) sum += (uint32_t)q[c];
+        sum += extra ? (uint32_t)q[M] : 0u;
+    } else {
+        for (int c = 0; c < m; ++c) sum += (uint32_t)q[c];
+        sum += extra ? (uint32_t)q[m] : 0u;
+    }
+    return sum;
+}
+
 template <typename T>
-__device__ bool unit_box(const AbScaleJob & J, const int32_t * R, int j, int i0, int i1, uint8_t * stage, bool srcAligned, bool dstAligned)
+__device__ bool seg_box(const AbScaleJob & J, const Seg & S, uint8_t * stage)
 {
     typedef typename std::conditional<sizeof(T) == 1, uint16_t, uint32_t>::type Acc;
-    constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T), MAXBH = 8;
-    const int iy = R[0], bh = R[1];
-    const int c0 = J.cols[4 * i0], cl = J.cols[4 * (i1 - 1)] + J.cols[4 * (i1 - 1) + 1];
-    const int a0 = srcAligned ? (c0 & ~(VL - 1)) : c0;
+    constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
+    const int m = J.minBoxWidth;
+    const int c0 = J.cols[4 * S.i0], cl = J.cols[4 * (S.i1 - 1)] + J.cols[4 * (S.i1 - 1) + 1];
+    const int a0 = S.srcAligned ? (c0 & ~(VL - 1)) : c0;
     const int span = cl - a0;
-    if (iy < 0 || c0 < 0 || iy + bh > J.srcH || cl > J.srcW || span > kStageBytes / (int)sizeof(Acc) - VL) return false;
+    if (m < 1 || c0 < 0 || cl > J.srcW || span > kStageBytes / (int)sizeof(Acc) - VL) return false;
     Acc * cs = reinterpret_cast<Acc *>(stage);
-    const int spanUp = (span + VL - 1) / VL * VL;
-    for (int k = (int)threadIdx.x * VL; k < spanUp; k += kScaleThreads * VL) {
-        uint32_t acc[VL];
+    const int i = S.i0 + (int)S.lane * VEC;
+    uint32_t info[VEC]; /* staging offset of the box | (one column more than minBoxWidth) << 16 | (inside the segment) << 17 */
+    bool odd = false;
 #pragma unroll
-        for (int e = 0; e < VL; ++e) acc[e] = 0;
-        const bool vec = srcAligned && a0 + k + VL <= J.srcW;
-        for (int r0 = 0; r0 < bh; r0 += MAXBH) { /* MAXBH independent loads in flight */
-            if (vec) {
-                uint4 v[MAXBH];
+    for (int o = 0; o < VEC; ++o) {
+        info[o] = 0;
+        if (i + o < S.i1) {
+            const int4 C = __ldg(reinterpret_cast<const int4 *>(J.cols) + i + o);
+            odd = odd || (C.y != m + C.z) || (C.z != 0 && C.z != 1) || (C.x < a0);
+            info[o] = (uint32_t)((C.x - a0) & 0xFFFF) | ((uint32_t)(C.z & 1) << 16) | (1u << 17);
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, odd)) return false; /* never for the tables of csrc/scale.c; the sampler would handle it */
+    int lastBh = -1;
+    uint32_t scale0 = 0, scale1 = 0;
+    for (int j = S.j0; j < S.j1; ++j) {
+        const int iy = J.rows[4 * j], bh = J.rows[4 * j + 1];
+        if (iy < 0 || bh < 1 || iy + bh > J.srcH || (sizeof(T) == 1 && bh > 257)) { /* 8-bit sums past 2^16 wrap (scale_common.c:316-328) */
+            rows_generic<T>(J, S, j, j + 1);
+            continue;
+        }
+        if (bh != lastBh) { /* scaletbl[0], [1] (scale.c:58-59 / ScaleAddCols2) */
+            scale0 = (uint32_t)(65536 / (m * bh));
+            scale1 = (uint32_t)(65536 / ((m + 1) * bh));
+            lastBh = bh;
+        }
+        for (int k = (int)S.lane * VL; k < span; k += 32 * VL) {
+            /* 8 words of sums, in memory order: 8-bit samples as pairs of 16-bit sums (no carry between the halves: bh * 255 < 2^16),
+             * 16-bit samples as 32-bit sums */
+            uint32_t acc[8];
 #pragma unroll
-                for (int r = 0; r < MAXBH; ++r)
-                    if (r0 + r < bh) v[r] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const T *>(J.src + (int64_t)(iy + r0 + r) * J.srcRB) + a0 + k));
+            for (int e = 0; e < 8; ++e) acc[e] = 0;
+            const T * row = reinterpret_cast<const T *>(J.src + (int64_t)iy * J.srcRB);
+#pragma unroll 4
+            for (int r = 0; r < bh; ++r) {
+                const uint4 v = load_vec<T>(J, row, a0 + k, S.srcAligned);
+                row = reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(row) + J.srcRB);
+                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-                for (int r = 0; r < MAXBH; ++r)
-                    if (r0 + r < bh) {
-                        int s[VL];
-                        unpack16<T>(v[r], s);
-#pragma unroll
-                        for (int e = 0; e < VL; ++e) acc[e] += (uint32_t)s[e];
+                for (int q = 0; q < 4; ++q) {
+                    if (sizeof(T) == 1) {
+                        acc[2 * q] += __byte_perm(w[q], 0u, 0x4140u);     /* bytes 0, 1 -> two 16-bit lanes */
+                        acc[2 * q + 1] += __byte_perm(w[q], 0u, 0x4342u); /* bytes 2, 3 */
+                    } else {
+                        acc[2 * q] += w[q] & 0xFFFFu;
+                        acc[2 * q + 1] += w[q] >> 16;
                     }
-            } else {
-                for (int r = r0; r < min(bh, r0 + MAXBH); ++r) {
-                    const T * q = reinterpret_cast<const T *>(J.src + (int64_t)(iy + r) * J.srcRB);
-#pragma unroll
-                    for (int e = 0; e < VL; ++e) acc[e] += (uint32_t)q[min(a0 + k + e, J.srcW - 1)];
                 }
             }
+            *reinterpret_cast<uint4 *>(cs + k) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<uint4 *>(cs + k + VL / 2) = make_uint4(acc[4], acc[5], acc[6], acc[7]);
         }
+        __syncwarp();
+        if (i < S.i1) {
+            int v[VEC];
 #pragma unroll
-        for (int e = 0; e < VL; ++e) cs[k + e] = (Acc)acc[e]; /* the compiler merges these into vector stores */
-    }
-    __syncthreads();
-    /* scaletbl[0], [1] (scale.c:58-59 / scale_common.c ScaleAddCols2): box widths minBoxWidth and minBoxWidth + 1 */
-    const uint32_t scale0 = (uint32_t)(65536 / (max(J.minBoxWidth, 1) * bh)), scale1 = (uint32_t)(65536 / (max(J.minBoxWidth + 1, 1) * bh));
-    for (int i = i0 + (int)threadIdx.x * VEC; i < i1; i += kScaleThreads * VEC) {
-        int v[VEC];
-#pragma unroll
-        for (int o = 0; o < VEC; ++o) {
-            v[o] = 0;
-            if (i + o < i1) {
-                const int4 C = __ldg(reinterpret_cast<const int4 *>(J.cols) + i + o);
-                uint32_t sum = 0;
-                const Acc * q = cs + (C.x - a0);
-                for (int c = 0; c < C.y; ++c) sum += (uint32_t)q[c];
-                const uint32_t scale = (C.z == 0) ? scale0 : ((C.z == 1) ? scale1 : (uint32_t)(65536 / (max(J.minBoxWidth + C.z, 1) * bh)));
-                v[o] = (int)((sum * scale) >> 16);
+            for (int o = 0; o < VEC; ++o) {
+                const Acc * q = cs + (info[o] & 0xFFFFu);
+                const uint32_t extra = (info[o] >> 16) & 1u;
+                uint32_t sum;
+                switch (m) { /* warp-uniform */
+                    case 2: sum = box_sum<T, 2>(q, m, extra); break;
+                    case 3: sum = box_sum<T, 3>(q, m, extra); break;
+                    case 4: sum = box_sum<T, 4>(q, m, extra); break;
+                    default: sum = box_sum<T, 0>(q, m, extra); break;
+                }
+                v[o] = (info[o] >> 17) ? (int)((sum * (extra ? scale1 : scale0)) >> 16) : 0;
             }
+            store_group<T>(J, j, i, S.i1, v, S.dstAligned);
         }
-        store_group<T>(J, j, i, i1, v, dstAligned);
+        __syncwarp();
     }
-    __syncthreads();
     return true;
 }
 
-/* ScalePlaneBilinearDown (scale.c:258-369): InterpolateRow of rows yi, yi + 1 into a row buffer, then ScaleFilterCols */
-template <typename T>
-__device__ bool unit_bilinear_down(const AbScaleJob & J, const int32_t * R, int j, int i0, int i1, uint8_t * stage, bool srcAligned, bool dstAligned)
+/* ScalePlaneBilinearDown (scale.c:258-369): InterpolateRow of rows yi, yi + 1 into a row buffer, then ScaleFilterCols;
+ * ScalePlaneSimple (scale.c:763-827) is the same walk without either filter */
+template <typename T, bool POINT>
+__device__ bool seg_bilinear_down(const AbScaleJob & J, const Seg & S, uint8_t * stage)
 {
     constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
-    const int yi = R[0], yf = J.linearOnly ? 0 : R[1];
-    const int c0 = min(max(J.cols[4 * i0], 0), J.srcW - 1), cl = min(J.cols[4 * (i1 - 1)] + 2, J.srcW);
-    const int a0 = srcAligned ? (c0 & ~(VL - 1)) : c0;
+    const int xmax = J.srcW - 1;
+    const int c0 = min(max(J.cols[4 * S.i0], 0), xmax), cl = min(J.cols[4 * (S.i1 - 1)] + (POINT ? 1 : 2), J.srcW);
+    const int a0 = S.srcAligned ? (c0 & ~(VL - 1)) : c0;
+    const int span = cl - a0;
+    if (span <= 0 || span > kStageBytes / (int)sizeof(T) - VL || J.cols[4 * (S.i1 - 1)] < J.cols[4 * S.i0]) return false;
+    T * sv = reinterpret_cast<T *>(stage);
+    const int i = S.i0 + (int)S.lane * VEC;
+    uint32_t info[VEC]; /* fraction | staging offset << 16 | (right neighbour is one further) << 31 */
+#pragma unroll
+    for (int o = 0; o < VEC; ++o) {
+        info[o] = 0;
+        if (i + o < S.i1) {
+            const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * (i + o)));
+            const int xa = min(max(C.x, 0), xmax);
+            info[o] = (uint32_t)(C.y & 0xFFFF) | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
+        }
+    }
+    for (int j = S.j0; j < S.j1; ++j) {
+        const int yi = J.rows[4 * j], yf = (POINT || J.linearOnly) ? 0 : J.rows[4 * j + 1];
+        const T * ra = src_row<T>(J, yi);
+        const T * rb = src_row<T>(J, yi + 1);
+        for (int k = (int)S.lane * VL; k < span; k += 32 * VL) {
+            uint4 a = load_vec<T>(J, ra, a0 + k, S.srcAligned);
+            if (yf) {
+                const uint4 b = load_vec<T>(J, rb, a0 + k, S.srcAligned);
+                uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+                for (int e = 0; e < VL; ++e) {
+                    const uint32_t t = (uint32_t)interp((int)vec_sample<T>(a, e), (int)vec_sample<T>(b, e), yf);
+                    if (sizeof(T) == 1) w[e >> 2] |= t << (8 * (e & 3));
+                    else w[e >> 1] |= t << (16 * (e & 1));
+                }
+                a = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4 *>(sv + k) = a;
+        }
+        __syncwarp();
+        if (i < S.i1) {
+            int v[VEC];
+#pragma unroll
+            for (int o = 0; o < VEC; ++o) {
+                const int xa = (int)((info[o] >> 16) & 0x7FFFu);
+                if (POINT) v[o] = (int)sv[xa];
+                else v[o] = blend<T>((int)sv[xa], (int)sv[xa + (int)(info[o] >> 31)], (int)(info[o] & 0xFFFFu));
+            }
+            store_group<T>(J, j, i, S.i1, v, S.dstAligned);
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+/* Up-scaling loops.  The reference filters every SOURCE row horizontally once (ScaleFilterCols into the two row buffers of
+ * ScalePlaneBilinearUp, scale.c:371-466; the (3,1) taps of ScaleRowUp2_(Bi)linear, scale.c:467-538 / scale_any.c:27-78) and then
+ * combines two such rows per destination row.  Same here: the lane keeps the horizontally filtered values of its 8 bytes of
+ * output for two source rows in registers (two slots tagged with their row number), re-filters a slot only when the walk down
+ * the destination rows needs a row neither slot holds, and each destination row costs one vertical combination per sample.
+ *   KIND 0  bilinear up     H = BLENDER(row[xi], row[xi+1], xf);  out = InterpolateRow(H(ra), H(rb), yf)
+ *   KIND 1  2x bilinear     H = 3 row[near] + row[far];           out = (3 H(near row) + H(far row) + 8) >> 4
+ *   KIND 2  2x linear       H = 3 row[near] + row[far];           out = (H(row) + 2) >> 2
+ * (edge columns of the 2x loops use one source column: near == far gives 4 row[k], and (12 a + 4 b + 8) >> 4 == (3 a + b + 2) >> 2,
+ * (4 a + 2) >> 2 == a.) */
+template <typename T, int KIND>
+__device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
+{
+    constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
+    const int xmax = J.srcW - 1;
+    int c0, cl;
+    if (KIND == 0) {
+        if (J.cols[4 * (S.i1 - 1)] < J.cols[4 * S.i0]) return false;
+        c0 = min(max(J.cols[4 * S.i0], 0), xmax);
+        cl = min(J.cols[4 * (S.i1 - 1)] + 2, J.srcW);
+    } else {
+        c0 = max((S.i0 - 1) >> 1, 0);
+        cl = min(max(((S.i1 - 2) >> 1) + 2, 1), J.srcW);
+        if (S.i1 == J.dstW) cl = max(cl, min((J.dstW - 1) / 2 + 1, J.srcW)); /* the last column's own source column */
+    }
+    const int a0 = S.srcAligned ? (c0 & ~(VL - 1)) : c0;
     const int span = cl - a0;
     if (span <= 0 || span > kStageBytes / (int)sizeof(T) - VL) return false;
-    T * sv = reinterpret_cast<T *>(stage);
-    const int y[2] = { yi, yi + 1 };
-    stage_rows<T, 2>(J, y, yf ? 2 : 1, a0, span, srcAligned, [&](int k, int s[2][VL]) {
+    T * st = reinterpret_cast<T *>(stage);
+    const int i = S.i0 + (int)S.lane * VEC;
+    uint32_t info[VEC]; /* KIND 0: fraction | offset << 16 | (neighbour one further) << 31;  else near offset | far offset << 16 */
 #pragma unroll
-        for (int e = 0; e < VL; ++e) sv[k + e] = (T)interp(s[0][e], yf ? s[1][e] : 0, yf);
-    });
-    __syncthreads();
-    const int xmax = J.srcW - 1;
-    for (int i = i0 + (int)threadIdx.x * VEC; i < i1; i += kScaleThreads * VEC) {
-        int v[VEC];
-#pragma unroll
-        for (int o = 0; o < VEC; ++o) {
-            v[o] = 0;
-            if (i + o < i1) {
-                const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * (i + o)));
-                const int xa = min(max(C.x, 0), xmax), xb = min(max(C.x + 1, 0), xmax);
-                v[o] = blend<T>((int)sv[xa - a0], (int)sv[xb - a0], C.y);
+    for (int o = 0; o < VEC; ++o) {
+        info[o] = 0;
+        const int x = i + o;
+        if (x < S.i1) {
+            if (KIND == 0) {
+                const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * x));
+                const int xa = min(max(C.x, 0), xmax);
+                info[o] = (uint32_t)(C.y & 0xFFFF) | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
+            } else if (x == 0 || x == J.dstW - 1) {
+                const int k = ((x == 0) ? 0 : (J.dstW - 1) / 2) - a0;
+                info[o] = (uint32_t)k | ((uint32_t)k << 16);
+            } else {
+                const int k = (x - 1) >> 1, k1 = min(k + 1, xmax);
+                const int kn = ((x - 1) & 1) ? k1 : k, kf = ((x - 1) & 1) ? k : k1; /* near / far column */
+                info[o] = (uint32_t)(kn - a0) | ((uint32_t)(kf - a0) << 16);
             }
         }
-        store_group<T>(J, j, i, i1, v, dstAligned);
     }
-    __syncthreads();
-    return true;
-}
-
-/* ScalePlaneBilinearUp (scale.c:371-466): ScaleFilterCols of the two cached rows, then InterpolateRow between them */
-template <typename T>
-__device__ bool unit_bilinear_up(const AbScaleJob & J, const int32_t * R, int j, int i0, int i1, uint8_t * stage, bool srcAligned, bool dstAligned)
-{
-    constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
-    const int ra = R[0], rb = R[1], yf = J.linearOnly ? 0 : R[2];
-    const int c0 = min(max(J.cols[4 * i0], 0), J.srcW - 1), cl = min(J.cols[4 * (i1 - 1)] + 2, J.srcW);
-    const int a0 = srcAligned ? (c0 & ~(VL - 1)) : c0;
-    const int span = cl - a0;
-    constexpr int half = kStageBytes / 2 / (int)sizeof(T);
-    if (span <= 0 || span > half - VL) return false;
-    T * sa = reinterpret_cast<T *>(stage);
-    T * sb = sa + half;
-    const int y[2] = { ra, rb };
-    stage_rows<T, 2>(J, y, yf ? 2 : 1, a0, span, srcAligned, [&](int k, int s[2][VL]) {
+    int h0[VEC], h1[VEC]; /* the two slots */
+    int id0 = -1, id1 = -1;
 #pragma unroll
-        for (int e = 0; e < VL; ++e) {
-            sa[k + e] = (T)s[0][e];
-            sb[k + e] = (T)s[1][e];
-        }
-    });
-    __syncthreads();
-    const int xmax = J.srcW - 1;
-    for (int i = i0 + (int)threadIdx.x * VEC; i < i1; i += kScaleThreads * VEC) {
-        int v[VEC];
-#pragma unroll
-        for (int o = 0; o < VEC; ++o) {
-            v[o] = 0;
-            if (i + o < i1) {
-                const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * (i + o)));
-                const int xa = min(max(C.x, 0), xmax) - a0, xb = min(max(C.x + 1, 0), xmax) - a0;
-                const int hA = blend<T>((int)sa[xa], (int)sa[xb], C.y);
-                const int hB = yf ? blend<T>((int)sb[xa], (int)sb[xb], C.y) : 0;
-                v[o] = interp(hA, hB, yf);
+    for (int o = 0; o < VEC; ++o) h0[o] = h1[o] = 0;
+    for (int j = S.j0; j < S.j1; ++j) {
+        int p, q, yf = 0; /* rows of the first / second operand */
+        if (KIND == 0) {
+            p = min(max(J.rows[4 * j], 0), J.srcH - 1);
+            yf = J.linearOnly ? 0 : J.rows[4 * j + 2];
+            q = yf ? min(max(J.rows[4 * j + 1], 0), J.srcH - 1) : p;
+        } else if (KIND == 1) { /* scale.c:503-538: row 0 and the last row of an even height come from one source row */
+            p = q = 0;
+            if (j != 0) {
+                const int r = (j - 1) >> 1;
+                if (r >= J.srcH - 1) p = q = J.srcH - 1;
+                else if ((j - 1) & 1) { p = r + 1; q = r; }
+                else { p = r; q = r + 1; }
             }
+        } else {
+            p = q = min(max(J.rows[4 * j], 0), J.srcH - 1);
         }
-        store_group<T>(J, j, i, i1, v, dstAligned);
+        /* which slot holds p, which q (all warp-uniform); a missing row replaces the slot the other operand does not need.  One
+         * rolled loop over the two operands: the filter below exists once in the code */
+        int sp = 0, sq = 0;
+#pragma unroll 1
+        for (int op = 0; op < 2; ++op) {
+            const int r = op ? q : p;
+            int slot;
+            if (op == 1 && q == p) slot = sp;
+            else if (id0 == r) slot = 0;
+            else if (id1 == r) slot = 1;
+            else {
+                slot = op ? (1 - sp) : ((id0 == q) ? 1 : 0);
+                stage_raw<T>(J, r, a0, span, S.srcAligned, st, S.lane);
+                __syncwarp();
+#pragma unroll
+                for (int o = 0; o < VEC; ++o) {
+                    int h;
+                    if (KIND == 0) {
+                        const int xa = (int)((info[o] >> 16) & 0x7FFFu);
+                        h = blend<T>((int)st[xa], (int)st[xa + (int)(info[o] >> 31)], (int)(info[o] & 0xFFFFu));
+                    } else {
+                        h = 3 * (int)st[info[o] & 0xFFFFu] + (int)st[info[o] >> 16];
+                    }
+                    if (slot == 0) h0[o] = h;
+                    else h1[o] = h;
+                }
+                __syncwarp();
+                if (slot == 0) id0 = r;
+                else id1 = r;
+            }
+            if (op == 0) sp = slot;
+            else sq = slot;
+        }
+        if (i < S.i1) {
+            int v[VEC];
+#pragma unroll
+            for (int o = 0; o < VEC; ++o) {
+                const int a = sp ? h1[o] : h0[o], b = sq ? h1[o] : h0[o];
+                if (KIND == 0) v[o] = interp(a, b, yf);
+                else if (KIND == 1) v[o] = (3 * a + b + 8) >> 4;
+                else v[o] = (a + 2) >> 2;
+            }
+            store_group<T>(J, j, i, S.i1, v, S.dstAligned);
+        }
     }
-    __syncthreads();
     return true;
 }
 
 /* ScalePlaneVertical (scale_common.c:348-426): InterpolateRow straight from the two source rows, no staging */
 template <typename T>
-__device__ void unit_vertical(const AbScaleJob & J, const int32_t * R, int j, int i0, int i1, bool srcAligned, bool dstAligned)
+__device__ void seg_vertical(const AbScaleJob & J, const Seg & S)
 {
     constexpr int VEC = 8 / (int)sizeof(T);
-    const int yi = R[0], yf = R[1];
-    const T * pa = src_row<T>(J, yi);
-    const T * pb = src_row<T>(J, yi + 1);
-    const bool vec = srcAligned && dstAligned; /* 16-byte aligned rows are 8-byte aligned too; i is a multiple of VEC */
-    for (int i = i0 + (int)threadIdx.x * VEC; i < i1; i += kScaleThreads * VEC) {
+    const int i = S.i0 + (int)S.lane * VEC;
+    if (i >= S.i1) return;
+    for (int j = S.j0; j < S.j1; ++j) {
+        const int yi = J.rows[4 * j], yf = J.rows[4 * j + 1];
+        const T * pa = src_row<T>(J, yi);
+        const T * pb = src_row<T>(J, yi + 1);
         int v[VEC];
-        if (vec && i + VEC <= i1) {
+        if (S.srcAligned && i + VEC <= S.i1) { /* 16-byte aligned rows are 8-byte aligned too; i is a multiple of VEC */
             const uint2 a = __ldg(reinterpret_cast<const uint2 *>(pa + i));
             const uint2 b = yf ? __ldg(reinterpret_cast<const uint2 *>(pb + i)) : make_uint2(0u, 0u);
-            const uint32_t wa[2] = { a.x, a.y }, wb[2] = { b.x, b.y };
+            const uint4 va = make_uint4(a.x, a.y, 0u, 0u), vb = make_uint4(b.x, b.y, 0u, 0u);
 #pragma unroll
-            for (int o = 0; o < VEC; ++o) {
-                const int sh = (int)(8 * sizeof(T)) * (o % (4 / (int)sizeof(T)));
-                const uint32_t m = (sizeof(T) == 1) ? 0xFFu : 0xFFFFu;
-                v[o] = interp((int)((wa[o / (4 / (int)sizeof(T))] >> sh) & m), (int)((wb[o / (4 / (int)sizeof(T))] >> sh) & m), yf);
-            }
+            for (int o = 0; o < VEC; ++o) v[o] = interp((int)vec_sample<T>(va, o), (int)vec_sample<T>(vb, o), yf);
         } else {
 #pragma unroll
-            for (int o = 0; o < VEC; ++o) v[o] = (i + o < i1) ? interp((int)pa[i + o], yf ? (int)pb[i + o] : 0, yf) : 0;
+            for (int o = 0; o < VEC; ++o) v[o] = (i + o < S.i1) ? interp((int)pa[i + o], yf ? (int)pb[i + o] : 0, yf) : 0;
         }
-        store_group<T>(J, j, i, i1, v, dstAligned);
+        store_group<T>(J, j, i, S.i1, v, S.dstAligned);
     }
 }
 
-/* the table-driven sampler for a whole unit (any loop; also the 2x up-scale groups) */
+/* the table-driven sampler for rows ja..jb of a segment (any loop): the fallback, sample by sample */
 template <typename T>
-__device__ void unit_generic(const AbScaleJob & J, const int32_t * R, int j, int i0, int i1, bool dstAligned)
+__device__ __noinline__ void rows_generic(const AbScaleJob & J, const Seg & S, int ja, int jb)
 {
     constexpr int VEC = 8 / (int)sizeof(T);
-    for (int i = i0 + (int)threadIdx.x * VEC; i < i1; i += kScaleThreads * VEC) {
-        int v[VEC];
-        const bool inner = (i >= 2) && (i + VEC <= J.dstW - 1);
-        if (J.mode == AB_SCALE_UP2_BILINEAR && inner) {
-            up2_group<T, true>(J, i, j, v);
-        } else if (J.mode == AB_SCALE_UP2_LINEAR && inner) {
-            up2_group<T, false>(J, i, R[0], v);
-        } else {
-#define AB_SCALE_CASE(M)                                                                                     \
-    case M:                                                                                                  \
-        _Pragma("unroll") for (int k = 0; k < VEC; ++k) v[k] = (i + k < i1) ? scale_sample<T, M>(J, R, i + k, j) : 0; \
-        break;
-            switch (J.mode) {
-                AB_SCALE_CASE(AB_SCALE_VERTICAL)
-                AB_SCALE_CASE(AB_SCALE_SIMPLE)
-                AB_SCALE_CASE(AB_SCALE_BILINEAR_DOWN)
-                AB_SCALE_CASE(AB_SCALE_BILINEAR_UP)
-                AB_SCALE_CASE(AB_SCALE_UP2_LINEAR)
-                AB_SCALE_CASE(AB_SCALE_UP2_BILINEAR)
-                AB_SCALE_CASE(AB_SCALE_BOX)
-                default:
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) v[k] = 0;
-            }
-#undef AB_SCALE_CASE
-        }
-        store_group<T>(J, j, i, i1, v, dstAligned);
+    const int i = S.i0 + (int)S.lane * VEC;
+    for (int j = ja; j < jb; ++j) {
+        const int32_t * R = J.rows + 4 * j;
+        T * out = reinterpret_cast<T *>(J.dst + (int64_t)j * J.dstRB);
+#pragma unroll 1
+        for (int k = i; k < min(i + VEC, S.i1); ++k) out[k] = (T)scale_sample<T, 0>(J, R, k, j);
     }
 }
 
-/* All planes of one image in one launch.  Blocks are shared out over the planes by blockStart[]; a block walks the units
- * (destination row, segment of segLen samples) of its plane. */
+/* All planes of one image in one launch.  Blocks are shared out over the planes by blockStart[]; the warps of a plane's blocks
+ * walk its units: (segment of segLen <= 32 x 8 bytes, block of rowsPerUnit destination rows), segments fastest. */
 template <typename T>
-__global__ void __launch_bounds__(kScaleThreads) scale_batch_kernel(const __grid_constant__ AbScaleBatch B)
+__global__ void __launch_bounds__(kScaleThreads, 3) scale_batch_kernel(const __grid_constant__ AbScaleBatch B)
 {
-    __shared__ __align__(16) uint8_t stage[kStageBytes];
+    __shared__ __align__(16) uint8_t stageAll[kScaleWarps][kStageBytes];
+    const uint32_t warp = threadIdx.x >> 5;
+    uint8_t * stage = stageAll[warp];
     uint32_t p = 0;
     while (p + 1 < B.count && blockIdx.x >= B.blockStart[p + 1]) ++p;
     const AbScaleJob & J = B.job[p];
-    const int segs = (J.dstW + J.segLen - 1) / J.segLen;
-    const int64_t total = (int64_t)segs * J.dstH;
-    const int64_t stride = (int64_t)(B.blockStart[p + 1] - B.blockStart[p]);
-    const bool dstAligned = ((((uintptr_t)J.dst) | (uintptr_t)J.dstRB) & 7u) == 0;
-    const bool srcAligned = ((((uintptr_t)J.src) | (uintptr_t)J.srcRB) & 15u) == 0;
-    for (int64_t u = (int64_t)(blockIdx.x - B.blockStart[p]); u < total; u += stride) {
-        const int j = (int)(u / segs), i0 = (int)(u - (int64_t)j * segs) * J.segLen, i1 = min(J.dstW, i0 + J.segLen);
-        const int32_t * R = J.rows + 4 * j;
-        bool done = false; /* block-uniform */
+    const uint32_t segs = (uint32_t)((J.dstW + J.segLen - 1) / J.segLen);
+    const uint32_t rowBlocks = (uint32_t)((J.dstH + J.rowsPerUnit - 1) / J.rowsPerUnit);
+    const uint32_t total = segs * rowBlocks; /* < 2^31: the launcher checked */
+    const uint32_t stride = (B.blockStart[p + 1] - B.blockStart[p]) * kScaleWarps;
+    Seg S;
+    S.lane = threadIdx.x & 31;
+    S.dstAligned = ((((uintptr_t)J.dst) | (uintptr_t)J.dstRB) & 7u) == 0;
+    S.srcAligned = ((((uintptr_t)J.src) | (uintptr_t)J.srcRB) & 15u) == 0;
+    for (uint32_t u = (blockIdx.x - B.blockStart[p]) * kScaleWarps + warp; u < total; u += stride) {
+        const uint32_t rb = u / segs, sg = u - rb * segs;
+        S.i0 = (int)sg * J.segLen;
+        S.i1 = min(J.dstW, S.i0 + J.segLen);
+        S.j0 = (int)rb * J.rowsPerUnit;
+        S.j1 = min(J.dstH, S.j0 + J.rowsPerUnit);
+        bool done = false; /* warp-uniform */
         switch (J.mode) {
-            case AB_SCALE_BOX: done = unit_box<T>(J, R, j, i0, i1, stage, srcAligned, dstAligned); break;
-            case AB_SCALE_BILINEAR_DOWN: done = unit_bilinear_down<T>(J, R, j, i0, i1, stage, srcAligned, dstAligned); break;
-            case AB_SCALE_BILINEAR_UP: done = unit_bilinear_up<T>(J, R, j, i0, i1, stage, srcAligned, dstAligned); break;
-            case AB_SCALE_VERTICAL: unit_vertical<T>(J, R, j, i0, i1, srcAligned, dstAligned); done = true; break;
+            case AB_SCALE_BOX: done = seg_box<T>(J, S, stage); break;
+            case AB_SCALE_BILINEAR_DOWN: done = seg_bilinear_down<T, false>(J, S, stage); break;
+            case AB_SCALE_SIMPLE: done = seg_bilinear_down<T, true>(J, S, stage); break;
+            case AB_SCALE_BILINEAR_UP: done = seg_up<T, 0>(J, S, stage); break;
+            case AB_SCALE_UP2_BILINEAR: done = seg_up<T, 1>(J, S, stage); break;
+            case AB_SCALE_UP2_LINEAR: done = seg_up<T, 2>(J, S, stage); break;
+            case AB_SCALE_VERTICAL: seg_vertical<T>(J, S); done = true; break;
             default: break;
         }
-        if (!done) unit_generic<T>(J, R, j, i0, i1, dstAligned);
+        if (!done) rows_generic<T>(J, S, S.j0, S.j1);
     }
 }
 
@@ -494,16 +622,21 @@ __global__ void __launch_bounds__(kScaleThreads) scale_batch_kernel(const __grid
 extern "C" int abLaunchScaleBatch(AbScaleBatch * batch, void * stream)
 {
     if (batch->count == 0) return 0;
-    /* units = (destination row, segment); a segment is at most one pass of the block (kScaleThreads x 8 bytes), rows are cut into
-     * equal segments, and a segment's source span has to fit the staging buffer (else the unit falls back to the sampler) */
+    /* units = (segment, block of destination rows).  A segment is at most one pass of a warp (32 lanes x 8 bytes), rows are cut
+     * into equal segments, and a segment's source span has to fit the warp's staging slice (else the unit falls back to the
+     * sampler).  Up-scaling loops reuse filtered source rows down a block of rows; the blocks shrink until there are enough units
+     * to fill the device a few times over. */
     int64_t units[AB_SCALE_MAX_PLANES], work[AB_SCALE_MAX_PLANES], all = 0;
     const int vec = 8 / batch->job[0].bps;
+    const int64_t residentWarps = 148 * 3 * kScaleWarps;
+    int64_t outputs = 0;
+    for (uint32_t p = 0; p < batch->count; ++p) outputs += (int64_t)batch->job[p].dstW * batch->job[p].dstH;
     for (uint32_t p = 0; p < batch->count; ++p) {
         AbScaleJob * j = &batch->job[p];
-        int maxSeg = kScaleThreads * vec;
-        if (j->dstW > 0 && j->srcW > j->dstW) { /* down-scaling: keep the span (~ seg * srcW / dstW columns) inside the buffer */
-            const int64_t elem = (j->mode == AB_SCALE_BOX) ? 2 * j->bps : ((j->mode == AB_SCALE_BILINEAR_UP) ? 2 * j->bps : j->bps);
-            const int64_t cap = kStageBytes / elem - 64;
+        int maxSeg = 32 * vec;
+        if (j->dstW > 0 && j->srcW > j->dstW) { /* down-scaling: keep the span (~ seg * srcW / dstW columns) inside the slice */
+            const int64_t elem = (j->mode == AB_SCALE_BOX) ? 2 * j->bps : j->bps;
+            const int64_t cap = kStageBytes / elem - 48;
             while (maxSeg > vec && ((int64_t)maxSeg * j->srcW + j->dstW - 1) / j->dstW + 4 > cap) maxSeg /= 2;
         }
         const int nseg = (j->dstW + maxSeg - 1) / maxSeg;
@@ -511,16 +644,25 @@ extern "C" int abLaunchScaleBatch(AbScaleBatch * batch, void * stream)
         seg = (seg + vec - 1) / vec * vec;
         if (seg < vec) seg = vec;
         j->segLen = seg;
-        units[p] = (int64_t)((j->dstW + seg - 1) / seg) * j->dstH;
-        work[p] = units[p] * ((int64_t)seg + (int64_t)seg * (j->srcW > j->dstW ? j->srcW / j->dstW : 1)); /* ~ bytes touched per unit */
+        const int64_t segs = (j->dstW + seg - 1) / seg;
+        const bool up = (j->mode == AB_SCALE_BILINEAR_UP || j->mode == AB_SCALE_UP2_BILINEAR || j->mode == AB_SCALE_UP2_LINEAR);
+        int rb = up ? 16 : 2;
+        /* this plane's share of the resident warps, two units each */
+        const int64_t wantUnits = 2 * residentWarps * ((int64_t)j->dstW * j->dstH) / (outputs > 0 ? outputs : 1);
+        while (rb > 1 && segs * ((j->dstH + rb - 1) / rb) < wantUnits) rb /= 2;
+        j->rowsPerUnit = rb;
+        units[p] = segs * ((j->dstH + rb - 1) / rb);
+        if (units[p] >= (1ll << 31)) return (int)cudaErrorInvalidValue;
+        work[p] = (int64_t)j->dstW * j->dstH + (int64_t)j->dstH * (j->srcW > j->dstW ? j->srcW : 0); /* ~ bytes touched */
+        if (work[p] < 1) work[p] = 1;
         all += work[p];
     }
-    if (all <= 0) return 0;
-    const int64_t budget = 148 * 8; /* resident blocks: 8 per SM (24 KB of staging each) */
+    const int64_t budget = 148 * 3 * 2; /* two rounds of resident blocks (3 per SM): the second hides the ragged end of the first */
     uint32_t start = 0;
     for (uint32_t p = 0; p < batch->count; ++p) {
         int64_t share = (work[p] * budget + all - 1) / all;
-        if (share > units[p]) share = units[p];
+        const int64_t need = (units[p] + kScaleWarps - 1) / kScaleWarps;
+        if (share > need) share = need;
         if (share < 1) share = 1;
         batch->blockStart[p] = start;
         start += (uint32_t)share;

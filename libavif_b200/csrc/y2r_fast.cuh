@@ -324,9 +324,25 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
 
 /* CARRY (bilinear 4:2:0 strips): chroma row A of this unit is row B of the unit above, whose normalised columns (own 4 + the two
  * neighbours) arrive in carry[plane][6] instead of being loaded and normalised again; either way carry leaves holding row B */
-template <class C, bool FULL, bool CARRY>
+/* LATE (fed strips, AB_Y2R_LATE): the luma / alpha words of a row are fetched from the warp's ring stage (lateStage: the lane's
+ * 16/8 bytes of row 0; rows are lateRow bytes apart, alpha lateAlpha bytes behind luma) only when that row is converted, and the
+ * blended chroma of the second row waits in the lane's spill slots (lateSpill, shared memory) while the first row is converted:
+ * ~24 registers less are live across the tile, which is what lets a fourth block onto the SM. */
+__device__ __forceinline__ void spill_st(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float spill_ld(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+struct LateFeed {
+    const uint8_t * stage; /* the lane's luma bytes of row 0 in the ring stage */
+    uint32_t row, alpha;   /* byte distance between the two rows / from a luma row to its alpha row */
+    uint32_t spill;        /* shared-space address of the lane's first spill slot; slot t is 128 bytes further */
+};
+template <class C, bool FULL, bool CARRY, bool LATE = false>
 __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const AbY2RFrame & F, const TileRows<C> & R, uint32_t x0, uint32_t lane, const TileIn<C> & in,
-                                                     float (&carry)[2][6])
+                                                     float (&carry)[2][6], const LateFeed & late = LateFeed{ nullptr, 0, 0, 0 })
 {
     using T = TileTraits<C>;
     using YT = typename T::YT;
@@ -409,7 +425,8 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
 #else
                     const float val = __fadd_rn(__fadd_rn(__fadd_rn(p9[cn][k - 1], p3[cn][ka]), p3[ca][k]), p1[ca][ka]);
 #endif
-                    if (plane) cr[r][t] = val;
+                    if (LATE && r == 1) spill_st(late.spill + (uint32_t)(plane * 8 + t) * 128u, val);
+                    else if (plane) cr[r][t] = val;
                     else cb[r][t] = val;
                 }
             }
@@ -427,10 +444,42 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (!R.rowOn[r]) continue; /* warp-uniform */
+        uint32_t ywr[4], awr[4];
+        if (LATE) {
+            const uint8_t * ys = late.stage + r * late.row;
+            if (sizeof(YT) == 2) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(ys);
+                ywr[0] = v.x; ywr[1] = v.y; ywr[2] = v.z; ywr[3] = v.w;
+                if (NEED_A) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(ys + late.alpha);
+                    awr[0] = a.x; awr[1] = a.y; awr[2] = a.z; awr[3] = a.w;
+                }
+            } else {
+                const uint2 v = *reinterpret_cast<const uint2 *>(ys);
+                ywr[0] = v.x; ywr[1] = v.y; ywr[2] = ywr[3] = 0;
+                if (NEED_A) {
+                    const uint2 a = *reinterpret_cast<const uint2 *>(ys + late.alpha);
+                    awr[0] = a.x; awr[1] = a.y; awr[2] = awr[3] = 0;
+                }
+            }
+            if (r == 1) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    cb[1][t] = spill_ld(late.spill + (uint32_t)t * 128u);
+                    cr[1][t] = spill_ld(late.spill + (uint32_t)(8 + t) * 128u);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                ywr[k] = in.yw[r][k];
+                awr[k] = NEED_A ? in.aw[r][k] : 0u;
+            }
+        }
         float ch[8][4];            /* per pixel, memory-order channel values as magic-float bit patterns (low 16 bits = code) */
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const float Y = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(in.yw[r], t, K, mm), magicMax, J.magicBiasY, J.rangeY);
+            const float Y = norm_magic<YT, !AB_Y2R_PACKED_CLAMP>(magic_sample_c<YT>(ywr, t, K, mm), magicMax, J.magicBiasY, J.rangeY);
             const float Cb = cb[SUB && !BIL ? 0 : r][t], Cr = cr[SUB && !BIL ? 0 : r][t];
             float Rv, Gv, Bv;
             if (C::MX == MX_COEFF) { /* ref: src/reformat.c:1014-1016 == :874-876 */
@@ -446,7 +495,7 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
             Gv = clamp01f(Gv);
             Bv = clamp01f(Bv);
             float am = 0.0f; /* alpha sample as magic float */
-            if (NEED_A) am = magic_sample<YT>(in.aw[r], t, K);
+            if (NEED_A) am = magic_sample<YT>(awr, t, K);
             float qaCopy = am; /* what the alpha channel receives when it is copied */
             if (T::RESC) {
                 /* ref: src/alpha.c:93-97 -- clamp((int)(0.5f + (a / srcMaxF) * dstMaxF), dstMax) on the raw sample.  8-bit samples
@@ -766,16 +815,67 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
 #ifndef AB_Y2R_CHUNK
 #define AB_Y2R_CHUNK 8
 #endif
+#ifndef AB_Y2R_MINB_STRIP /* resident blocks per SM the strip kernel is compiled for */
+#define AB_Y2R_MINB_STRIP AB_Y2R_MINB_BIL420
+#endif
+#ifndef AB_Y2R_STRIP_ALPHA /* 1: tiles with alpha rows take the strip kernel too (they stayed on the group kernel while their rows lived in registers) */
+#define AB_Y2R_STRIP_ALPHA 0
+#endif
 constexpr uint32_t kYChunk = AB_Y2R_CHUNK;
 
+/* AB_Y2R_FEED = D > 0: the interior units of a strip are fed through shared memory.  Each lane issues the 16/8-byte asynchronous
+ * copies (cp.async, SASS LDGSTS) of ITS OWN luma / alpha / chroma-row-B bytes of the unit D steps ahead into a per-warp ring of
+ * D + 1 stages, and reads its own bytes back D units later: no register holds a sample while it is in flight, no lane reads
+ * another lane's bytes (so there is no barrier and nothing to poll: cp.async.wait_group is a per-thread scoreboard wait), and
+ * a warp has D + 1 units of loads in flight instead of one.  The two halo columns of the edge lanes travel one unit ahead in
+ * two registers. */
+#ifndef AB_Y2R_FEED
+#define AB_Y2R_FEED 0
+#endif
+#ifndef AB_Y2R_LATE /* needs AB_Y2R_FEED: rows leave the ring only when they are converted; second-row chroma parked in shared memory */
+#define AB_Y2R_LATE 0
+#endif
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t smemAddr, const void * gptr)
+{
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr), "l"(gptr) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr), "l"(gptr) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smemAddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/* layout of one ring stage of one warp: luma rows 2r-1, 2r | alpha rows (if the tile needs them) | chroma row r of U, of V */
 template <class C>
-__global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_bil420_strip_kernel(const __grid_constant__ AbY2RBatch B)
+struct FeedLayout {
+    using T = TileTraits<C>;
+    static constexpr int LB = 8 * (int)sizeof(typename T::YT);  /* bytes of a lane's 8 luma samples */
+    static constexpr int CBL = 4 * (int)sizeof(typename T::YT); /* bytes of a lane's 4 chroma samples */
+    static constexpr int YROW = 32 * LB, CROW = 32 * CBL;
+    static constexpr int OFF_A = 2 * YROW;
+    static constexpr int OFF_U = (T::NEED_A ? 4 : 2) * YROW;
+    static constexpr int OFF_V = OFF_U + CROW;
+    static constexpr int STAGE = OFF_V + CROW;
+    static constexpr int STAGES = AB_Y2R_FEED + 1;
+    static constexpr int SPILL = AB_Y2R_LATE ? 16 * 128 : 0; /* 16 floats per lane, slot-major (AB_Y2R_LATE) */
+    static constexpr int WARP_BYTES = STAGES * STAGE + SPILL;
+    static constexpr int BLOCK_BYTES = kWarps * WARP_BYTES;
+};
+
+template <class C>
+__global__ void __launch_bounds__(kWarps * 32, AB_Y2R_MINB_STRIP) y2r_bil420_strip_kernel(const __grid_constant__ AbY2RBatch B)
 {
     using T = TileTraits<C>;
     using YT = typename T::YT;
     static_assert(C::CHROMA == CH_BIL420, "strip kernel: bilinear 4:2:0");
     const AbY2RJob & J = B.common;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#if AB_Y2R_FEED
+    extern __shared__ __align__(16) uint8_t feedSmem[];
+    const uint32_t feedBase = (uint32_t)__cvta_generic_to_shared(feedSmem);
+#endif
     uint32_t f = 0;
     while (f + 1 < B.nFrames && blockIdx.x >= B.frame[f + 1].blockStart) ++f;
     const AbY2RFrame & F = B.frame[f];
@@ -794,8 +894,56 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_bil420_
         const bool full = (x0 + kTile <= F.width);
         float carry[2][6];
         bool have = false;
+#if AB_Y2R_FEED
+        using L = FeedLayout<C>;
+        const uint32_t ring = feedBase + warp * (uint32_t)L::WARP_BYTES;
+        /* the copies of unit `pu` into stage pu % STAGES (nothing if the unit is not an interior one); always one commit group */
+        auto feed = [&](uint32_t pu) {
+            if (pu < u1) {
+                const TileRows<C> PR = tile_rows<C>(J, F, pu);
+                const int pru = (int)(F.rowBegin >> 1) + (int)pu;
+                if (full && PR.rowOn[0] && PR.rowOn[1] && (PR.cA == pru - 1) && (PR.cB == pru)) {
+                    const uint32_t st = ring + (pu % (uint32_t)L::STAGES) * (uint32_t)L::STAGE;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        cp_async<L::LB>(st + r * L::YROW + lane * L::LB, F.y + (int64_t)PR.jrow[r] * F.yRB + (size_t)px0 * sizeof(YT));
+                        if (T::NEED_A) cp_async<L::LB>(st + L::OFF_A + r * L::YROW + lane * L::LB, F.a + (int64_t)PR.jrow[r] * F.aRB + (size_t)px0 * sizeof(YT));
+                    }
+                    cp_async<L::CBL>(st + L::OFF_U + lane * L::CBL, F.u + (int64_t)PR.cB * F.uRB + (size_t)m0 * sizeof(YT));
+                    cp_async<L::CBL>(st + L::OFF_V + lane * L::CBL, F.v + (int64_t)PR.cB * F.vRB + (size_t)m0 * sizeof(YT));
+                }
+            }
+            cp_async_commit();
+        };
+        /* halo columns (edge lanes) of chroma row `crow`, as magic floats */
+        const uint32_t hcol = (lane == 0) ? ((m0 > 0) ? m0 - 1 : 0) : min(m0 + 4, cw - 1);
+        auto halo = [&](int crow, float & hu, float & hv) {
+            hu = hv = 0.0f;
+            if (lane == 0 || lane == 31) {
+                hu = magic_scalar<YT>(F.u + (int64_t)crow * F.uRB, hcol);
+                hv = magic_scalar<YT>(F.v + (int64_t)crow * F.vRB, hcol);
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < AB_Y2R_FEED; ++d) feed(u0 + (uint32_t)d);
+        float hUn = 0.0f, hVn = 0.0f; /* halos of chroma row B of the unit about to run (loaded one unit ahead) */
+        {
+            const int chromaH = (int)((F.height + 1) >> 1);
+            const int ru0 = (int)(F.rowBegin >> 1) + (int)u0;
+            if (full && ru0 < chromaH) halo(ru0, hUn, hVn);
+        }
+#endif
 #pragma unroll 1
         for (uint32_t unit = u0; unit < u1; ++unit) {
+#if AB_Y2R_FEED
+            feed(unit + AB_Y2R_FEED);
+            const float hUc = hUn, hVc = hVn;
+            {
+                const int chromaH = (int)((F.height + 1) >> 1);
+                const int run = (int)(F.rowBegin >> 1) + (int)unit + 1;
+                if (full && unit + 1 < u1 && run < chromaH) halo(run, hUn, hVn);
+            }
+#endif
             const TileRows<C> R = tile_rows<C>(J, F, unit);
             if (!R.any) {
                 have = false;
@@ -817,13 +965,51 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_bil420_
                 continue;
             }
             /* interior unit of a full strip: two luma (and alpha) rows, chroma row B; row A only if the unit above did not leave it */
+#if AB_Y2R_FEED
+            const uint8_t * lateStage = nullptr;
+            cp_async_wait<AB_Y2R_FEED>(); /* this unit's group (and every older one) has landed */
+            {
+                const uint8_t * st = feedSmem + (size_t)warp * L::WARP_BYTES + (size_t)(unit % (uint32_t)L::STAGES) * L::STAGE;
+                lateStage = st;
+#pragma unroll
+                for (int r = 0; r < (AB_Y2R_LATE ? 0 : 2); ++r) {
+                    if (sizeof(YT) == 2) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(st + r * L::YROW + lane * 16);
+                        in.yw[r][0] = v.x; in.yw[r][1] = v.y; in.yw[r][2] = v.z; in.yw[r][3] = v.w;
+                        if (T::NEED_A) {
+                            const uint4 a = *reinterpret_cast<const uint4 *>(st + L::OFF_A + r * L::YROW + lane * 16);
+                            in.aw[r][0] = a.x; in.aw[r][1] = a.y; in.aw[r][2] = a.z; in.aw[r][3] = a.w;
+                        }
+                    } else {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(st + r * L::YROW + lane * 8);
+                        in.yw[r][0] = v.x; in.yw[r][1] = v.y; in.yw[r][2] = in.yw[r][3] = 0;
+                        if (T::NEED_A) {
+                            const uint2 a = *reinterpret_cast<const uint2 *>(st + L::OFF_A + r * L::YROW + lane * 8);
+                            in.aw[r][0] = a.x; in.aw[r][1] = a.y; in.aw[r][2] = in.aw[r][3] = 0;
+                        }
+                    }
+                }
+                if (sizeof(YT) == 2) {
+                    const uint2 u = *reinterpret_cast<const uint2 *>(st + L::OFF_U + lane * 8);
+                    const uint2 v = *reinterpret_cast<const uint2 *>(st + L::OFF_V + lane * 8);
+                    in.uw[1][0] = u.x; in.uw[1][1] = u.y; in.vw[1][0] = v.x; in.vw[1][1] = v.y;
+                } else {
+                    in.uw[1][0] = *reinterpret_cast<const uint32_t *>(st + L::OFF_U + lane * 4);
+                    in.vw[1][0] = *reinterpret_cast<const uint32_t *>(st + L::OFF_V + lane * 4);
+                    in.uw[1][1] = in.vw[1][1] = 0;
+                }
+                in.hU[1] = hUc;
+                in.hV[1] = hVc;
+            }
+#else
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 load8<YT>(F.y + (int64_t)R.jrow[r] * F.yRB, px0, 8u, in.yw[r]);
                 if (T::NEED_A) load8<YT>(F.a + (int64_t)R.jrow[r] * F.aRB, px0, 8u, in.aw[r]);
             }
+#endif
 #pragma unroll
-            for (int cr = 0; cr < 2; ++cr) {
+            for (int cr = 0; cr < (AB_Y2R_FEED ? 1 : 2); ++cr) {
                 if (cr == 0 && have) { /* warp-uniform */
                     in.uw[0][0] = in.uw[0][1] = in.vw[0][0] = in.vw[0][1] = 0;
                     in.hU[0] = in.hV[0] = 0.0f;
@@ -841,8 +1027,17 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_bil420_
                     in.hV[cr] = magic_scalar<YT>(vr, col);
                 }
             }
+#if AB_Y2R_FEED && AB_Y2R_LATE
+            {
+                const LateFeed late = { lateStage + lane * L::LB, (uint32_t)L::YROW, (uint32_t)L::OFF_A,
+                                        ring + (uint32_t)(L::STAGES * L::STAGE) + lane * 4u };
+                if (have) convert_store_tile_x<C, true, true, true>(J, F, R, x0, lane, in, carry, late);
+                else convert_store_tile_x<C, true, false, true>(J, F, R, x0, lane, in, carry, late);
+            }
+#else
             if (have) convert_store_tile_x<C, true, true>(J, F, R, x0, lane, in, carry);
             else convert_store_tile_x<C, true, false>(J, F, R, x0, lane, in, carry);
+#endif
             have = true;
         }
     }
@@ -1119,7 +1314,8 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT, MX>;
     /* the strip kernel pays where the tile needs no alpha rows (C5 -3 %, C1 -7 %); with them its 12 carried registers spill and it
      * measured 14 % SLOWER than the group kernel (C3 110 vs 96.6 us, profiles/r02_variants.md) */
-    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0) && !TileTraits<C>::NEED_A;
+    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0) && (AB_Y2R_STRIP_ALPHA != 0 || !TileTraits<C>::NEED_A);
+    constexpr size_t stripSmem = (STRIP && AB_Y2R_FEED) ? (size_t)FeedLayout<C>::BLOCK_BYTES : 0; /* the cp.async ring of the strip kernel */
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
         AbY2RFrame & F = B.frame[f];
@@ -1140,17 +1336,22 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
     if (!resident) {
         int sms = 0, perSm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if constexpr (STRIP) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_bil420_strip_kernel<C>, kWarps * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
+        if constexpr (STRIP) {
+            if (stripSmem > 48 * 1024) cudaFuncSetAttribute(y2r_bil420_strip_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stripSmem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_bil420_strip_kernel<C>, kWarps * 32, stripSmem);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, y2r_fast_kernel<C>, kWarps * 32, 0);
+        }
         /* the loop shapes were tuned at YLoop::MIN_BLOCKS blocks per SM; when the compiler needs fewer registers than the bound
          * allows, more blocks would fit -- and measured slower (4:2:0 nearest: 6 blocks 14.8 us, 5 blocks 13.3 us per 4K frame) */
-        if (perSm > YLoop<C>::MIN_BLOCKS) perSm = YLoop<C>::MIN_BLOCKS;
+        constexpr int tuned = STRIP ? AB_Y2R_MINB_STRIP : YLoop<C>::MIN_BLOCKS;
+        if (perSm > tuned) perSm = tuned;
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, wanted);
-    if constexpr (STRIP) y2r_bil420_strip_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
+    if constexpr (STRIP) y2r_bil420_strip_kernel<C><<<B.totalBlocks, kWarps * 32, stripSmem, st>>>(B);
     else y2r_fast_kernel<C><<<B.totalBlocks, kWarps * 32, 0, st>>>(B);
     return 1;
 }

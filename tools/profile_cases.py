@@ -69,27 +69,39 @@ for name, nf in PLAN:
     del imgs, rgbs
     torch.cuda.empty_cache()
 
-if ONLY:
+if ONLY and not (ONLY & {"SC", "TM", "C4"}):
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     json.dump(order, open(out_path, "w"), indent=1)
     sys.exit(0)
-# C4: the 16 cells of the 4x4 grid as views of one canvas, one batched RGB -> YUV launch
-canvas_rgb = RGBImage(7680, 4320, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
-canvas_rgb.buf._t[:canvas_rgb.buf.nbytes].copy_(torch.randint(0, 256, (canvas_rgb.buf.nbytes,), device=dev, dtype=torch.int32).to(torch.uint8))
-canvas = YUVImage(7680, 4320, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
-rects = sharding.split_grid(7680, 4320, 4, 4, A.AVIF_PIXEL_FORMAT_YUV420)
-cy = [sharding.view_yuv(canvas.c, r) for r in rects]
-cr = [sharding.view_rgb(canvas_rgb.c, r) for r in rects]
-pi = (ctypes.POINTER(A.avifImage) * 16)(*[ctypes.pointer(c) for c in cy])
-pr = (ctypes.POINTER(A.avifRGBImage) * 16)(*[ctypes.pointer(c) for c in cr])
-lib.avifB200ResetKernelLaunchCount()
-for _ in range(2):
-    assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
-torch.cuda.synchronize()
-order.append({"case": "C4_canvas", "kernel": lib.avifB200LastKernelName().decode(), "frames": 16, "px_per_frame": 1920 * 1080, "alg_bytes_per_px": 6.5,
-              "launches": int(lib.avifB200KernelLaunchCount())})
 
-if "--reformat-only" not in sys.argv:
+
+def want(tag):
+    return ONLY is None or tag in ONLY
+
+
+# C4: the 16 cells of the 4x4 grid as views of one canvas, one batched RGB -> YUV launch
+def run_c4():
+    canvas_rgb = RGBImage(7680, 4320, 8, A.AVIF_RGB_FORMAT_RGBA, device=dev)
+    canvas_rgb.buf._t[:canvas_rgb.buf.nbytes].copy_(torch.randint(0, 256, (canvas_rgb.buf.nbytes,), device=dev, dtype=torch.int32).to(torch.uint8))
+    canvas = YUVImage(7680, 4320, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
+    rects = sharding.split_grid(7680, 4320, 4, 4, A.AVIF_PIXEL_FORMAT_YUV420)
+    cy = [sharding.view_yuv(canvas.c, r) for r in rects]
+    cr = [sharding.view_rgb(canvas_rgb.c, r) for r in rects]
+    pi = (ctypes.POINTER(A.avifImage) * 16)(*[ctypes.pointer(c) for c in cy])
+    pr = (ctypes.POINTER(A.avifRGBImage) * 16)(*[ctypes.pointer(c) for c in cr])
+    lib.avifB200ResetKernelLaunchCount()
+    for _ in range(2):
+        assert lib.avifB200ImageRGBToYUVBatchAsync(pi, pr, 16, sptr) == 0
+    torch.cuda.synchronize()
+    order.append({"case": "C4_canvas", "kernel": lib.avifB200LastKernelName().decode(), "frames": 16, "px_per_frame": 1920 * 1080, "alg_bytes_per_px": 6.5,
+                  "launches": int(lib.avifB200KernelLaunchCount())})
+
+
+
+if want("C4"):
+    run_c4()
+
+if "--reformat-only" not in sys.argv and want("TM"):
     # gain-map tone mapping: 4K sRGB RGBA8 base + 8-bit 4:4:4 gain map -> PQ RGBA10, device resident
     import numpy as np  # noqa: E402
     g = np.random.RandomState(77)
@@ -119,8 +131,9 @@ if "--reformat-only" not in sys.argv:
     torch.cuda.synchronize()
     order.append({"case": "TM_4K", "kernel": "tone_map (+ y2r of the gain map, + tone_lut)", "frames": 1, "px_per_frame": W * H, "alg_bytes_per_px": 15, "match": "tone_map_kernel"})
 
+if "--reformat-only" not in sys.argv and want("SC"):
     # avifImageScale's device scaler: 4K 4:2:0 8-bit + alpha -> 720p (box) and 1080p -> 4K (2x bilinear)
-    for (sw, sh, dw, dh) in ((3840, 2160, 1280, 720), (1920, 1080, 3840, 2160)):
+    for (sw, sh, dw, dh) in ((3840, 2160, 1280, 720), (1920, 1080, 3840, 2160), (3840, 2160, 1920, 1080), (1280, 720, 3840, 2160)):
         s_img = YUVImage(sw, sh, 8, 3, 1, 1, alpha=True, device=dev)
         fill(s_img, 9)
         d_img = YUVImage(dw, dh, 8, 3, 1, 1, alpha=True, device=dev)
