@@ -131,7 +131,9 @@ typedef struct AbY2RFrame {
     uint32_t groups;     /* ceil(tiles / 8) */
     uint32_t blockStart; /* blocks [blockStart, blockStart + blocks) of the launch work on this frame only, */
     uint32_t blocks;     /* striding over its groups: the frame is invariant for the whole life of a block */
-    uint32_t pad;
+    uint32_t vecWidth;   /* == width when every plane row and the pixel rows are vector-aligned; 0 when they are only sample-aligned
+                          * (views into larger images, odd strides): every tile then takes the ragged code with element-wise loads
+                          * and stores */
 } AbY2RFrame;
 
 typedef struct AbY2RBatch {
@@ -149,7 +151,8 @@ typedef struct AbR2YFrame {
     int64_t rgbRB, yRB, uRB, vRB, aRB;
     uint32_t width, height;
     uint32_t rowBegin, rowEnd;
-    uint32_t tilesX, tiles, groups, blockStart, blocks, pad;
+    uint32_t tilesX, tiles, groups, blockStart, blocks;
+    uint32_t vecWidth; /* as in AbY2RFrame */
 } AbR2YFrame;
 
 typedef struct AbR2YBatch {

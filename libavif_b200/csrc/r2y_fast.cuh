@@ -187,9 +187,9 @@ __device__ __forceinline__ float quant_luma_fullrange(float v, float range)
 
 /* CLAMP: the containers hold saturated 16-bit codes that still have to be limited to yuvMax (mm = yuvMax in both halves) */
 template <typename YT, bool CLAMP = false>
-__device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8], uint32_t mm = 0)
+__device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32_t n, const float q[8], uint32_t mm = 0, bool vec = true)
 {
-    if (n >= 8) {
+    if (n >= 8 && vec) {
         if (sizeof(YT) == 2) {
             uint4 v;
             v.x = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x5410u);
@@ -217,9 +217,9 @@ __device__ __forceinline__ void store_samples8(uint8_t * row, uint32_t x, uint32
 }
 
 template <typename YT, bool CLAMP = false>
-__device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32_t n, const float q[4], uint32_t mm = 0)
+__device__ __forceinline__ void store_samples4(uint8_t * row, uint32_t x, uint32_t n, const float q[4], uint32_t mm = 0, bool vec = true)
 {
-    if (n >= 4) {
+    if (n >= 4 && vec) {
         if (sizeof(YT) == 2) {
             uint2 v;
             v.x = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x5410u);
@@ -300,7 +300,7 @@ __device__ __forceinline__ void load_rtile_p(const AbR2YFrame & F, const uint8_t
             if (!FULL || r > 0) in.w[r][k] = 0; /* row 0 of a full tile is loaded unconditionally */
         if (r == 0 || (uint32_t)r < nRows) { /* the tile's first row always exists */
             const uint8_t * p = rgb + (int64_t)r * F.rgbRB;
-            if (fullTile || nValid >= 8) {
+            if (fullTile || (nValid >= 8 && F.vecWidth != 0)) { /* rows that are only sample-aligned: element by element */
                 if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
                     for (int q = 0; q < NW / 4; ++q) {
@@ -430,19 +430,20 @@ __device__ __forceinline__ void convert_store_rtile_p(const AbR2YJob & J, const 
         }
         const uint32_t j = j0 + r;
         const uint32_t ns = fullTile ? 8u : nValid;
+        const bool vec = fullTile || (F.vecWidth != 0);
         /* addresses are formed where they are used: carrying five row pointers would cost ten registers */
-        store_samples8<YT, QC>(F.y + (int64_t)j * F.yRB, px0, ns, yq, mm);
+        store_samples8<YT, QC>(F.y + (int64_t)j * F.yRB, px0, ns, yq, mm, vec);
         if (C::SUB == SUB_444) {
-            store_samples8<YT, QC>(F.u + (int64_t)j * F.uRB, px0, ns, uq, mm);
-            store_samples8<YT, QC>(F.v + (int64_t)j * F.vRB, px0, ns, vq, mm);
+            store_samples8<YT, QC>(F.u + (int64_t)j * F.uRB, px0, ns, uq, mm, vec);
+            store_samples8<YT, QC>(F.v + (int64_t)j * F.vRB, px0, ns, vq, mm, vec);
         }
         if (COPYA) {
-            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
+            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq, 0, vec);
         } else if (writeAlpha) { /* warp-uniform */
             const float fillAlpha = __uint_as_float(J.yuvMax);
 #pragma unroll
             for (int t = 0; t < 8; ++t) aq[t] = fillAlpha;
-            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq);
+            store_samples8<YT>(F.a + (int64_t)j * F.aRB, px0, ns, aq, 0, vec);
         }
     }
 
@@ -458,8 +459,8 @@ __device__ __forceinline__ void convert_store_rtile_p(const AbR2YJob & J, const 
             vq[k] = quant_yuv<YT>(__fmul_rn(sv[k], inv), J.rangeUV, qbUV, hiLimit);
         }
         const uint32_t uj = (C::SUB == SUB_420) ? (j0 >> 1) : j0;
-        store_samples4<YT, QC>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq, mm);
-        store_samples4<YT, QC>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq, mm);
+        store_samples4<YT, QC>(F.u + (int64_t)uj * F.uRB, px0 >> 1, nc, uq, mm, fullTile || (F.vecWidth != 0));
+        store_samples4<YT, QC>(F.v + (int64_t)uj * F.vRB, px0 >> 1, nc, vq, mm, fullTile || (F.vecWidth != 0));
     }
 }
 
@@ -535,12 +536,12 @@ __device__ __forceinline__ void r2y_strip_run(const AbR2YJob & J, const AbR2YFra
         auto rowsAt = [&](uint32_t jj) { return (ROWS == 1) ? 1u : min((uint32_t)ROWS, F.height - jj); };
         auto rgbAt = [&](uint32_t jj) { return F.rgb + (int64_t)jj * F.rgbRB + (int64_t)(x0 + 8 * lane) * (C::NCH * (int)sizeof(typename C::RT)); };
         RTileIn<C> a, b;
-        if (x0 + kRTile <= F.width && RLoop<C>::PLAIN) { /* tiles whose second register set does not fit: plain loop */
+        if (x0 + kRTile <= F.vecWidth && RLoop<C>::PLAIN) { /* tiles whose second register set does not fit: plain loop */
             for (; j < jEnd; j += ROWS) {
                 load_rtile_p<C, true>(F, rgbAt(j), 8u, rowsAt(j), a);
                 convert_store_rtile_p<C, true, SWAP, COPYA, YFULL>(J, F, x0 + 8 * lane, j, 8u, rowsAt(j), a);
             }
-        } else if (x0 + kRTile <= F.width) {
+        } else if (x0 + kRTile <= F.vecWidth) {
             load_rtile_p<C, true>(F, rgbAt(j), 8u, rowsAt(j), a);
 #if AB_R2Y_PINGPONG
             while (true) {
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
             if (t >= F.tiles) continue;
             const uint32_t unit = t / F.tilesX, tx0 = (t - unit * F.tilesX) * kRTile, tj0 = F.rowBegin + unit * ROWS;
             RTileIn<C> in;
-            if (tx0 + kRTile <= F.width) {
+            if (tx0 + kRTile <= F.vecWidth) {
                 load_rtile<C, true>(J, F, tx0, tj0, lane, in);
                 convert_store_rtile<C, true>(J, F, tx0, tj0, lane, in);
             } else {
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
             const uint32_t unit = t / F.tilesX;
             s.x0 = (t - unit * F.tilesX) * kRTile;
             s.j0 = F.rowBegin + unit * ROWS;
-            s.full = (s.x0 + kRTile <= F.width);
+            s.full = (s.x0 + kRTile <= F.vecWidth);
             if (s.full) load_rtile<C, true>(J, F, s.x0, s.j0, lane, s.in);
             else load_rtile<C, false>(J, F, s.x0, s.j0, lane, s.in);
         }
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
         const uint32_t unit = tile / F.tilesX;
         x0 = (tile - unit * F.tilesX) * kRTile;
         j0 = F.rowBegin + unit * ROWS;
-        full = (x0 + kRTile <= F.width);
+        full = (x0 + kRTile <= F.vecWidth);
         if (full) load_rtile<C, true>(J, F, x0, j0, lane, cur);
         else load_rtile<C, false>(J, F, x0, j0, lane, cur);
     }
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(kRWarps * 32, RLoop<C>::MIN_BLOCKS) r2y_fast_k
                 const uint32_t nunit = ntile / F.tilesX;
                 nx0 = (ntile - nunit * F.tilesX) * kRTile;
                 nj0 = F.rowBegin + nunit * ROWS;
-                nfull = (nx0 + kRTile <= F.width);
+                nfull = (nx0 + kRTile <= F.vecWidth);
                 if (nfull) load_rtile<C, true>(J, F, nx0, nj0, lane, nxt);
                 else load_rtile<C, false>(J, F, nx0, nj0, lane, nxt);
             }
@@ -766,37 +767,44 @@ static int rlaunch_cfg(AbR2YBatch & B, cudaStream_t st)
 {
     using C = RCfg<RT, YT, SUB, NCH, AFIRST, AM, IDENT>;
     constexpr int ROWS = (SUB == SUB_420) ? 2 : 1;
-    uint32_t groups = 0;
-    for (uint32_t f = 0; f < B.nFrames; ++f) {
-        AbR2YFrame & F = B.frame[f];
-        uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
-        if (RStrip<C>::ON) units = (units + kRChunk - 1) / kRChunk; /* work items are chunks of kRChunk row units */
-        F.tilesX = (F.width + kRTile - 1) / kRTile;
-        F.tiles = F.tilesX * units;
-        F.groups = (F.tiles + kRWarps - 1) / kRWarps;
-        groups += F.groups;
-    }
-    /* blocks that fit on the whole device at once: per instantiation and per device (a process may drive several GPUs) */
-    static int residentOf[16] = { 0 };
     int dev = 0;
     cudaGetDevice(&dev);
-    int resident = (dev >= 0 && dev < 16) ? residentOf[dev] : 0;
-    if (!resident) {
-        int sms = 0, perSm = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (RStrip<C>::ON) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_strip_kernel<C>, kRWarps * 32, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
-        { /* never more blocks per SM than the loop shape was tuned for (see y2r_fast.cuh) */
-            const int tuned = RStrip<C>::ON ? AB_R2Y_STRIP_MINB : RLoop<C>::MIN_BLOCKS;
-            if (perSm > tuned) perSm = tuned;
+    /* form 1 = strip kernel (chunks of kRChunk row units walked by one warp), form 0 = group kernel (independent units).  A lone small
+     * picture does not have enough chunks to fill the device and would wait behind those serial chains: the strip form needs at
+     * least two rounds of resident blocks, else the launch falls back to the group form. */
+    for (int form = RStrip<C>::ON ? 1 : 0; form >= 0; --form) {
+        uint32_t groups = 0;
+        for (uint32_t f = 0; f < B.nFrames; ++f) {
+            AbR2YFrame & F = B.frame[f];
+            uint32_t units = (F.rowEnd - F.rowBegin + ROWS - 1) / ROWS;
+            if (form) units = (units + kRChunk - 1) / kRChunk; /* work items are chunks of kRChunk row units */
+            F.tilesX = (F.width + kRTile - 1) / kRTile;
+            F.tiles = F.tilesX * units;
+            F.groups = (F.tiles + kRWarps - 1) / kRWarps;
+            groups += F.groups;
         }
-        resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
-        if (dev >= 0 && dev < 16) residentOf[dev] = resident;
+        /* blocks that fit on the whole device at once: per instantiation, form and device (a process may drive several GPUs) */
+        static int residentOf[2][16] = { { 0 }, { 0 } };
+        int resident = (dev >= 0 && dev < 16) ? residentOf[form][dev] : 0;
+        if (!resident) {
+            int sms = 0, perSm = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (form) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_strip_kernel<C>, kRWarps * 32, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, r2y_fast_kernel<C>, kRWarps * 32, 0);
+            { /* never more blocks per SM than the loop shape was tuned for (see y2r_fast.cuh) */
+                const int tuned = form ? AB_R2Y_STRIP_MINB : RLoop<C>::MIN_BLOCKS;
+                if (perSm > tuned) perSm = tuned;
+            }
+            resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
+            if (dev >= 0 && dev < 16) residentOf[form][dev] = resident;
+        }
+        if (form && groups < 2u * (uint32_t)resident) continue;
+        const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
+        B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);
+        if (form) r2y_strip_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
+        else r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
+        break;
     }
-    const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
-    B.totalBlocks = rassign_blocks(B.frame, B.nFrames, groups, wanted);
-    if (RStrip<C>::ON) r2y_strip_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
-    else r2y_fast_kernel<C><<<B.totalBlocks, kRWarps * 32, 0, st>>>(B);
     return 1;
 }
 
@@ -819,6 +827,23 @@ static int rlaunch_sub(AbR2YBatch & B, cudaStream_t st)
     }
 }
 
+/* 2: vector-aligned rows everywhere; 1: only sample-aligned (the specialised kernels run their ragged, element-wise code on every
+ * tile: AbR2YFrame::vecWidth == 0); 0: not even that.  See y2r_alignment. */
+template <typename RT, typename YT>
+static int r2y_alignment(const AbR2YJob & J)
+{
+    const uintptr_t rbits = (uintptr_t)J.rgb | (uintptr_t)J.rgbRB;
+    uintptr_t ybits = (uintptr_t)J.y | (uintptr_t)J.yRB;
+    if (J.alphaWrite != AB_ALPHA_KEEP) ybits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
+    const uintptr_t cbits = J.hasChroma ? ((uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB) : 0;
+    if ((rbits & (sizeof(RT) - 1)) || ((ybits | cbits) & (sizeof(YT) - 1))) return 0;
+    const uint32_t pixb = J.nChan * (uint32_t)sizeof(RT);
+    const uintptr_t srcAlign = ((8 * pixb) % 16 == 0) ? 15 : 7;
+    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1;
+    const bool vec = !(rbits & srcAlign) && !(ybits & lumaAlign) && !(cbits & (J.shiftX ? (4 * sizeof(YT) - 1) : lumaAlign));
+    return vec ? 2 : 1;
+}
+
 template <typename RT, typename YT>
 static bool rfast_eligible(const AbR2YJob & J)
 {
@@ -832,17 +857,7 @@ static bool rfast_eligible(const AbR2YJob & J)
     if (J.alphaWrite == AB_ALPHA_COPY && (J.alphaRescale || J.nChan != 4)) return false;
     if (J.alphaMul != AB_MUL_NONE && J.nChan != 4) return false;
     if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
-    const uint32_t pixb = J.nChan * (uint32_t)sizeof(RT);
-    const uintptr_t srcAlign = ((8 * pixb) % 16 == 0) ? 15 : 7;
-    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & srcAlign) return false;
-    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1;
-    uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
-    if (J.alphaWrite != AB_ALPHA_KEEP) bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
-    if (bits & lumaAlign) return false;
-    if (J.hasChroma) {
-        const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
-        if (cbits & (J.shiftX ? (4 * sizeof(YT) - 1) : lumaAlign)) return false;
-    }
+    if (r2y_alignment<RT, YT>(J) == 0) return false; /* not even sample-aligned: the byte-addressed kernel */
     return true;
 }
 
@@ -870,7 +885,8 @@ static int launch_r2y_fast_typed(const AbR2YJob * jobs, uint32_t n, cudaStream_t
         F.rgb = S.rgb; F.y = S.y; F.u = S.u; F.v = S.v; F.a = S.a;
         F.rgbRB = S.rgbRB; F.yRB = S.yRB; F.uRB = S.uRB; F.vRB = S.vRB; F.aRB = S.aRB;
         F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
-        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = F.pad = 0;
+        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = 0;
+        F.vecWidth = (r2y_alignment<RT, YT>(S) == 2) ? S.width : 0;
     }
     const AbR2YJob & J = B.common;
     if (J.mode == AB_MODE_IDENTITY) { /* lossless GBR: 4:4:4, no alpha arithmetic */

@@ -88,10 +88,10 @@ __device__ __forceinline__ float magic_sample_c(const uint32_t * w, int k, uint3
 
 /* 8 consecutive samples starting at x (x % 8 == 0, row 16/8-byte aligned); n = how many of them exist */
 template <typename T>
-__device__ __forceinline__ void load8(const uint8_t * row, uint32_t x, uint32_t n, uint32_t w[4])
+__device__ __forceinline__ void load8(const uint8_t * row, uint32_t x, uint32_t n, uint32_t w[4], bool vec = true)
 {
     w[0] = w[1] = w[2] = w[3] = 0;
-    if (n >= 8) {
+    if (n >= 8 && vec) { /* vec == false: rows that are only sample-aligned are read element by element */
         if (sizeof(T) == 2) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + (size_t)x * 2));
             w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
@@ -113,10 +113,10 @@ __device__ __forceinline__ void load8(const uint8_t * row, uint32_t x, uint32_t 
 
 /* 4 consecutive chroma samples starting at column m (m % 4 == 0), columns >= cw replicate column cw-1 */
 template <typename T>
-__device__ __forceinline__ void load4_clamped(const uint8_t * row, uint32_t m, uint32_t cw, uint32_t w[2])
+__device__ __forceinline__ void load4_clamped(const uint8_t * row, uint32_t m, uint32_t cw, uint32_t w[2], bool vec = true)
 {
     w[0] = w[1] = 0;
-    if (m + 3 < cw) {
+    if (m + 3 < cw && vec) {
         if (sizeof(T) == 2) {
             const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + (size_t)m * 2));
             w[0] = v.x; w[1] = v.y;
@@ -277,13 +277,14 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
     using YT = typename T::YT;
     const uint32_t px0 = x0 + 8 * lane;
     const uint32_t nValid = FULL ? 8u : ((px0 < F.width) ? min(8u, F.width - px0) : 0u);
+    const bool vec = FULL || (F.vecWidth != 0);
 #pragma unroll
     for (int r = 0; r < T::ROWS; ++r) {
         in.yw[r][0] = in.yw[r][1] = in.yw[r][2] = in.yw[r][3] = 0;
         if (T::NEED_A) in.aw[r][0] = in.aw[r][1] = in.aw[r][2] = in.aw[r][3] = 0;
         if (R.rowOn[r] && (FULL || nValid)) {
-            load8<YT>(F.y + (int64_t)R.jrow[r] * F.yRB, px0, nValid, in.yw[r]);
-            if (T::NEED_A) load8<YT>(F.a + (int64_t)R.jrow[r] * F.aRB, px0, nValid, in.aw[r]);
+            load8<YT>(F.y + (int64_t)R.jrow[r] * F.yRB, px0, nValid, in.yw[r], vec);
+            if (T::NEED_A) load8<YT>(F.a + (int64_t)R.jrow[r] * F.aRB, px0, nValid, in.aw[r], vec);
         }
     }
     const uint32_t cw = T::SUB ? ((F.width + 1) >> 1) : F.width;
@@ -298,8 +299,8 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
                 load4_clamped<YT>(ur, m0, m0 + 4, in.uw[c]);
                 load4_clamped<YT>(vr, m0, m0 + 4, in.vw[c]);
             } else {
-                load4_clamped<YT>(ur, m0, cw, in.uw[c]);
-                load4_clamped<YT>(vr, m0, cw, in.vw[c]);
+                load4_clamped<YT>(ur, m0, cw, in.uw[c], vec);
+                load4_clamped<YT>(vr, m0, cw, in.vw[c], vec);
             }
             if (T::BIL) {
                 /* only the two edge lanes need a column outside the warp's span (clamped at the picture edge): one
@@ -315,8 +316,8 @@ __device__ __forceinline__ void load_tile(const AbY2RJob & J, const AbY2RFrame &
 #pragma unroll
             for (int k = 0; k < T::CW; ++k) in.uw[c][k] = in.vw[c][k] = 0;
             if (FULL || nValid) {
-                load8<YT>(ur, px0, nValid, in.uw[c]);
-                load8<YT>(vr, px0, nValid, in.vw[c]);
+                load8<YT>(ur, px0, nValid, in.uw[c], vec);
+                load8<YT>(vr, px0, nValid, in.vw[c], vec);
             }
         }
     }
@@ -601,7 +602,7 @@ __device__ __forceinline__ void convert_store_tile_x(const AbY2RJob & J, const A
             }
         }
         uint8_t * d = F.rgb + (int64_t)R.jrow[r] * F.rgbRB + (int64_t)px0 * PIXB;
-        if (FULL || nValid == 8) {
+        if (FULL || (nValid == 8 && F.vecWidth != 0)) {
             if ((8 * PIXB) % 16 == 0) {
 #pragma unroll
                 for (int q = 0; q < NW / 4; ++q) reinterpret_cast<uint4 *>(d)[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
             const TileRows<C> TR = tile_rows<C>(J, F, unit);
             if (!TR.any) continue;
             TileIn<C> in;
-            if (tx0 + kTile <= F.width) {
+            if (tx0 + kTile <= F.vecWidth) {
                 load_tile<C, true>(J, F, TR, tx0, lane, in);
                 convert_store_tile<C, true>(J, F, TR, tx0, lane, in);
             } else {
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
             const uint32_t unit = t / F.tilesX;
             s.x0 = (t - unit * F.tilesX) * kTile;
             s.R = tile_rows<C>(J, F, unit);
-            s.full = (s.x0 + kTile <= F.width);
+            s.full = (s.x0 + kTile <= F.vecWidth);
             if (s.R.any) {
                 if (s.full) load_tile<C, true>(J, F, s.R, s.x0, lane, s.in);
                 else load_tile<C, false>(J, F, s.R, s.x0, lane, s.in);
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
         const uint32_t unit = tile / F.tilesX;
         x0 = (tile - unit * F.tilesX) * kTile;
         R = tile_rows<C>(J, F, unit);
-        full = (x0 + kTile <= F.width);
+        full = (x0 + kTile <= F.vecWidth);
         if (R.any) {
             if (full) load_tile<C, true>(J, F, R, x0, lane, cur);
             else load_tile<C, false>(J, F, R, x0, lane, cur);
@@ -780,7 +781,7 @@ __global__ void __launch_bounds__(kWarps * 32, YLoop<C>::MIN_BLOCKS) y2r_fast_ke
                 const uint32_t nunit = ntile / F.tilesX;
                 nx0 = (ntile - nunit * F.tilesX) * kTile;
                 NR = tile_rows<C>(J, F, nunit);
-                nfull = (nx0 + kTile <= F.width);
+                nfull = (nx0 + kTile <= F.vecWidth);
                 if (NR.any) {
                     if (nfull) load_tile<C, true>(J, F, NR, nx0, lane, nxt);
                     else load_tile<C, false>(J, F, NR, nx0, lane, nxt);
@@ -891,7 +892,7 @@ __global__ void __launch_bounds__(kWarps * 32, AB_Y2R_MINB_STRIP) y2r_bil420_str
         const uint32_t cy = c / F.tilesX, sx = c - cy * F.tilesX;
         const uint32_t x0 = sx * kTile, px0 = x0 + 8 * lane, m0 = px0 >> 1;
         const uint32_t u0 = cy * kYChunk, u1 = min(u0 + kYChunk, units);
-        const bool full = (x0 + kTile <= F.width);
+        const bool full = (x0 + kTile <= F.vecWidth);
         float carry[2][6];
         bool have = false;
 #if AB_Y2R_FEED
@@ -1116,7 +1117,7 @@ __device__ __forceinline__ WarpTile warp_tile(const AbY2RFrame & F, uint32_t g, 
     w.live = (g < F.groups) && (t < F.tiles);
     w.unit = w.live ? t / F.tilesX : 0;
     w.x0 = w.live ? (t - w.unit * F.tilesX) * kTile : 0;
-    w.full = w.live && (w.x0 + kTile <= F.width);
+    w.full = w.live && (w.x0 + kTile <= F.vecWidth);
     return w;
 }
 
@@ -1308,13 +1309,13 @@ static uint32_t assign_blocks(FrameT * frames, uint32_t n, uint32_t totalGroups,
 
 /* ---- eligibility + dispatch for one (YT, RT) pair ------------------------------------------------ */
 
-template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT, int MX = MX_COEFF>
+template <typename YT, typename RT, int CHROMA, int NCH, bool AFIRST, int AW, int AM, int OUT = OUT_INT, int MX = MX_COEFF, bool ALLOW_STRIP = true>
 static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
 {
     using C = Cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT, MX>;
     /* the strip kernel pays where the tile needs no alpha rows (C5 -3 %, C1 -7 %); with them its 12 carried registers spill and it
      * measured 14 % SLOWER than the group kernel (C3 110 vs 96.6 us, profiles/r02_variants.md) */
-    constexpr bool STRIP = (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0) && (AB_Y2R_STRIP_ALPHA != 0 || !TileTraits<C>::NEED_A);
+    constexpr bool STRIP = ALLOW_STRIP && (CHROMA == CH_BIL420) && (AB_Y2R_STRIP_BIL420 != 0) && (AB_Y2R_STRIP_ALPHA != 0 || !TileTraits<C>::NEED_A);
     constexpr size_t stripSmem = (STRIP && AB_Y2R_FEED) ? (size_t)FeedLayout<C>::BLOCK_BYTES : 0; /* the cp.async ring of the strip kernel */
     uint32_t groups = 0;
     for (uint32_t f = 0; f < B.nFrames; ++f) {
@@ -1348,6 +1349,12 @@ static int launch_cfg(AbY2RBatch & B, cudaStream_t st)
         if (perSm > tuned) perSm = tuned;
         resident = (sms > 0 && perSm > 0) ? sms * perSm : 148 * 2;
         if (dev >= 0 && dev < 16) residentOf[dev] = resident;
+    }
+    if constexpr (STRIP) {
+        /* a strip chunk is kYChunk units walked one after the other by one warp: a lone small picture (one 1080p frame: 68 groups for
+         * 444 resident blocks) leaves most of the device idle behind those serial chains -- 22.6 us against 11 us for the group kernel,
+         * whose units are independent.  The strip form needs at least two rounds of resident blocks. */
+        if (groups < 2u * (uint32_t)resident) return launch_cfg<YT, RT, CHROMA, NCH, AFIRST, AW, AM, OUT, MX, false>(B, st);
     }
     const uint32_t wanted = (groups >= 4u * (uint32_t)resident) ? (uint32_t)resident : groups;
     B.totalBlocks = assign_blocks(B.frame, B.nFrames, groups, wanted);
@@ -1519,6 +1526,28 @@ static int launch_alpha(AbY2RBatch & B, cudaStream_t st)
     }
 }
 
+/* 2: every plane row and every pixel row starts where the lanes' 16 / 8-byte vectors need it; 1: rows are only sample-aligned
+ * (views into larger images, odd strides, tightly packed 257-pixel rows): the specialised kernels still apply, every tile through
+ * their ragged code with element-wise loads and stores (AbY2RFrame::vecWidth == 0); 0: not even that */
+template <typename YT, typename RT>
+static int y2r_alignment(const AbY2RJob & J)
+{
+    const bool needA = (J.alphaWrite == AB_ALPHA_COPY) || (J.alphaMul != AB_MUL_NONE);
+    const bool sub = (J.chroma != AB_CHROMA_FULL);
+    uintptr_t ybits = (uintptr_t)J.y | (uintptr_t)J.yRB;
+    if (needA) ybits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
+    const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
+    const uintptr_t rbits = (uintptr_t)J.rgb | (uintptr_t)J.rgbRB;
+    const uintptr_t pixb = J.is565 ? 2 : (uintptr_t)J.nChan * sizeof(RT);
+    const uintptr_t rgbGran = (pixb % 2 == 0) ? 2 : 1; /* the ragged store is 16-bit granular for even pixel sizes, else byte-wise */
+    if (((ybits | cbits) & (sizeof(YT) - 1)) || (rbits & (rgbGran - 1))) return 0;
+    /* a lane reads 8 luma / 4 subsampled chroma samples per vector and stores its 8 pixels as 16-byte vectors (3-byte pixels, 24
+     * bytes per lane: 8-byte ones) */
+    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
+    const bool vec = !(ybits & lumaAlign) && !(cbits & (sub ? subAlign : lumaAlign)) && !(rbits & (((8 * pixb) % 16 == 0) ? 15 : 7));
+    return vec ? 2 : 1;
+}
+
 /* can this job run on a specialised kernel? (constants + alignment of its own planes) */
 template <typename YT, typename RT>
 static bool fast_eligible(const AbY2RJob & J)
@@ -1538,20 +1567,9 @@ static bool fast_eligible(const AbY2RJob & J)
     if ((J.alphaMul == AB_MUL_INT_PREMUL) && J.pmR == 0.0f && (!J.rgbMaxDiv.exact || (AB_Y2R_DIV2 && !J.rgbMaxDiv.exact2))) return false;
     if ((J.alphaMul == AB_MUL_FLOAT_MUL || J.alphaMul == AB_MUL_FLOAT_UNMUL) && !J.yuvMaxDiv.intExact) return false;
     if (J.alphaWrite == AB_ALPHA_COPY && J.alphaRescale && !J.yuvMaxDiv.intExact) return false;
-    const uintptr_t lumaAlign = 8 * sizeof(YT) - 1, subAlign = 4 * sizeof(YT) - 1;
-    const bool sub = (J.chroma != AB_CHROMA_FULL);
-    uintptr_t bits = (uintptr_t)J.y | (uintptr_t)J.yRB;
     const bool needA = (J.alphaWrite == AB_ALPHA_COPY) || (J.alphaMul != AB_MUL_NONE);
-    if (needA) {
-        if (!J.a) return false;
-        bits |= (uintptr_t)J.a | (uintptr_t)J.aRB;
-    }
-    if (bits & lumaAlign) return false;
-    const uintptr_t cbits = (uintptr_t)J.u | (uintptr_t)J.uRB | (uintptr_t)J.v | (uintptr_t)J.vRB;
-    if (cbits & (sub ? subAlign : lumaAlign)) return false;
-    /* a lane stores its 8 pixels as 16-byte vectors, 3-byte pixels (24 bytes per lane) as 8-byte ones */
-    const uintptr_t pixb = J.is565 ? 2 : (uintptr_t)J.nChan * sizeof(RT);
-    if (((uintptr_t)J.rgb | (uintptr_t)J.rgbRB) & (((8 * pixb) % 16 == 0) ? 15 : 7)) return false;
+    if (needA && !J.a) return false;
+    if (y2r_alignment<YT, RT>(J) == 0) return false; /* not even sample-aligned: the byte-addressed kernel */
     if (J.width == 0 || J.rowEnd <= J.rowBegin) return false;
     return true;
 }
@@ -1595,7 +1613,8 @@ static int launch_y2r_fast_typed(const AbY2RJob * jobs, uint32_t n, cudaStream_t
         F.uRB = swap ? S.vRB : S.uRB;
         F.vRB = swap ? S.uRB : S.vRB;
         F.width = S.width; F.height = S.height; F.rowBegin = S.rowBegin; F.rowEnd = S.rowEnd;
-        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = F.pad = 0;
+        F.tilesX = F.tiles = F.groups = F.blockStart = F.blocks = 0;
+        F.vecWidth = (y2r_alignment<YT, RT>(S) == 2) ? S.width : 0;
     }
     const bool afirst = J.alphaFirst != 0;
     const int nch = J.nChan;

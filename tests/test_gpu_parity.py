@@ -161,6 +161,37 @@ def test_y2r_unaligned_device_views(gpu_product, oracle):
         _check_y2r(gpu_product, oracle, spec, 6000 + k, device="cuda:0")
 
 
+def test_sample_aligned_views_stay_on_the_specialised_kernels(gpu_product, oracle):
+    """Rows that are only sample-aligned (a view into a larger image, a tightly packed 257-pixel row) keep the specialised kernels:
+    every tile goes through their ragged, element-wise code (frame.vecWidth == 0) instead of falling to the general kernel."""
+    import dataclasses
+    k = served_y2r = served_r2y = 0
+    for depth, rgb_depth in [(8, 8), (10, 10), (12, 16), (8, 16), (10, 8)]:
+        for fmt, ups in [(abi.AVIF_PIXEL_FORMAT_YUV444, 0), (abi.AVIF_PIXEL_FORMAT_YUV420, abi.AVIF_CHROMA_UPSAMPLING_BILINEAR),
+                         (abi.AVIF_PIXEL_FORMAT_YUV420, abi.AVIF_CHROMA_UPSAMPLING_NEAREST), (abi.AVIF_PIXEL_FORMAT_YUV422, abi.AVIF_CHROMA_UPSAMPLING_BILINEAR)]:
+            for rgb_fmt in [abi.AVIF_RGB_FORMAT_RGBA, abi.AVIF_RGB_FORMAT_RGB, abi.AVIF_RGB_FORMAT_BGRA]:
+                for alpha in (False, True):
+                    k += 1
+                    w, h = [(257, 5), (521, 4), (300, 7), (1031, 3)][k % 4]
+                    bps_y = 2 if depth > 8 else 1
+                    bps_r = 2 if rgb_depth > 8 else 1
+                    spec = util.Spec(w=w, h=h, depth=depth, fmt=fmt, rng=k % 2, mc=[1, 6, 9][k % 3], alpha=alpha, rgb_depth=rgb_depth, rgb_fmt=rgb_fmt,
+                                     ups=ups, garbage=(k % 3 == 0), yuv_off=bps_y * (1 + k % 3), rgb_off=2 * (1 + k % 3), yuv_pad=2 * (k % 4),
+                                     rgb_pad=2 * (k % 3))
+                    assert _check_y2r(gpu_product, oracle, spec, 9300 + k, device="cuda:0") == 0
+                    name = gpu_product.avifB200LastKernelName().decode()
+                    rescale_same_container = alpha and abi.rgb_format_has_alpha(rgb_fmt) and depth != rgb_depth and (depth > 8) == (rgb_depth > 8)
+                    if not rescale_same_container and not (alpha and not abi.rgb_format_has_alpha(rgb_fmt)):
+                        assert name.startswith("y2r_fast"), (spec.ident(), name)
+                        served_y2r += 1
+                    if not alpha:
+                        assert _check_r2y(gpu_product, oracle, spec, 9400 + k, device="cuda:0") == 0
+                        if depth == rgb_depth or not abi.rgb_format_has_alpha(rgb_fmt):
+                            assert gpu_product.avifB200LastKernelName().decode().startswith("r2y_fast"), spec.ident()
+                            served_r2y += 1
+    assert served_y2r > 60 and served_r2y > 30, (served_y2r, served_r2y, k)
+
+
 @pytest.mark.parametrize("policy", [0, 1, 2, 4], ids=["fast", "generic", "vec-ieee-div", "vec"])
 def test_r2y_sweep_host_pointers(gpu_product, oracle, policy):
     n_ok = 0

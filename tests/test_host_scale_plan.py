@@ -190,3 +190,34 @@ def test_position_tables_reproduce_the_committed_vectors(product, oracle):
             assert f"{util.fnv1a64(oracle, np.ascontiguousarray(data).reshape(-1)):016x}" == v["planes"][p], (v["src"], v["dst"], depth, fmt, p)
             checked += 1
     assert checked > 100
+
+
+def test_identities_behind_the_staged_kernel(product):
+    """scale_kernels.cu's row-staged loops lean on four facts; each is checked here over its whole domain (no GPU):
+    1. 2x bilinear factors through H = 3*near + far: (9a + 3b + 3c + d + 8) >> 4 == (3*(3a + b) + (3c + d) + 8) >> 4 (plain algebra), and
+       its edge columns, which read ONE source column, fall out of near == far: (3*(4a) + 4c + 8) >> 4 == (3a + c + 2) >> 2;
+    2. 2x linear likewise: (H + 2) >> 2 with H = 4a is a;
+    3. 8-bit box column sums of at most 257 rows fit 16 bits, so pairs of them can be added as packed halves of one register;
+    4. a box is minBoxWidth or minBoxWidth + 1 columns wide (cols[:, 2] in {0, 1}, cols[:, 1] == minBoxWidth + cols[:, 2]) for every
+       geometry the box loop serves."""
+    a = np.arange(0, 65536, dtype=np.int64)[:, None]
+    c = np.concatenate([np.arange(0, 65536, 257), [1, 2, 3, 65534, 65535]]).astype(np.int64)[None, :]
+    assert np.array_equal((3 * (4 * a) + 4 * c + 8) >> 4, (3 * a + c + 2) >> 2)
+    assert np.array_equal((4 * a + 2) >> 2, a)
+    assert 257 * 255 < 65536 <= 258 * 255
+    rng = np.random.RandomState(5)
+    seen = 0
+    for _ in range(300):
+        sw, sh = int(rng.randint(2, 4000)), int(rng.randint(2, 3000))
+        dw, dh = int(rng.randint(1, sw)), int(rng.randint(1, sh))
+        for sixteen in (False, True):
+            mode, lin, minbw, R, C = plan(product, sw, sh, dw, dh, sixteen)
+            if mode != BOX:
+                continue
+            seen += 1
+            assert minbw >= 1
+            assert set(np.unique(C[:, 2])) <= {0, 1}, (sw, sh, dw, dh)
+            assert np.array_equal(C[:, 1], minbw + C[:, 2]), (sw, sh, dw, dh)
+            assert np.all(np.diff(C[:, 0]) >= 0) and C[0, 0] >= 0 and C[-1, 0] + C[-1, 1] <= sw
+            assert np.all(R[:, 1] >= 1) and np.all(R[:, 0] >= 0) and np.all(R[:, 0] + R[:, 1] <= sh)
+    assert seen > 100
