@@ -741,7 +741,7 @@ def run_scale(lib, dev, stream, peak_gbs):
     from libavif_b200 import abi as A
     from libavif_b200.images import YUVImage
     res = {}
-    for name, (sw, sh, dw, dh) in {"SC_4K_to_1080p_box_420_8b_alpha": (3840, 2160, 1280, 720),
+    for name, (sw, sh, dw, dh) in {"SC_4K_to_720p_box_420_8b_alpha": (3840, 2160, 1280, 720),
                                    "SC_1080p_to_4K_up2_420_8b_alpha": (1920, 1080, 3840, 2160)}.items():
         g = torch.Generator(device=dev)
         g.manual_seed(5)

@@ -242,10 +242,11 @@ typedef struct AbScaleJob {
     uint8_t bps;        /* bytes per sample: 1 or 2 */
     uint8_t mode;       /* AB_SCALE_* */
     uint8_t linearOnly; /* kFilterLinear: horizontal filter only */
-    uint8_t pad;
+    uint8_t colsArith;  /* column i sits at x0 + i * dx (16.16): the kernel computes positions instead of reading cols[] */
     int32_t minBoxWidth; /* box: dx >> 16 (or the constant box width) */
     int32_t segLen;      /* destination samples per unit of work (a multiple of 8 bytes); filled by the launcher */
     int32_t rowsPerUnit; /* destination rows per unit of work; filled by the launcher */
+    int32_t x0, dx;      /* see colsArith */
     const int32_t * rows; /* 4 ints per destination row, meaning depends on mode (scale_kernels.cu) */
     const int32_t * cols; /* 4 ints per destination column */
 } AbScaleJob;

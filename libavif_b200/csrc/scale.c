@@ -86,6 +86,8 @@ typedef struct ScalePlan {
     int mode; /* 0 = straight copy */
     int linearOnly;
     int minBoxWidth;
+    int colsArith; /* 1: column positions are x0 + i * dx (16.16) -- the kernel may compute them instead of reading cols[] */
+    int32_t x0, dx;
     int32_t * rows; /* 4 per destination row */
     int32_t * cols; /* 4 per destination column */
 } ScalePlan;
@@ -100,6 +102,11 @@ static void planFree(ScalePlan * p)
 /* positions of ScaleFilterCols / ScaleCols: x, x+dx, ... (scale_common.c:114-130, :197-222) */
 static void colsStepped(ScalePlan * p, int dw, int x, int dx)
 {
+    if (x >= 0 && dx > 0 && (int64_t)x + (int64_t)dw * dx < 0x7fffffffll) { /* no 32-bit wrap on the way: closed form == the walk */
+        p->colsArith = 1;
+        p->x0 = x;
+        p->dx = dx;
+    }
     for (int i = 0; i < dw; ++i) {
         p->cols[4 * i + 0] = x >> 16;
         p->cols[4 * i + 1] = x & 0xffff;
@@ -163,6 +170,11 @@ static int planScale(int sw, int sh, int dw, int dh, int sixteen, ScalePlan * p)
                 if (y > maxY) y = maxY;
                 p->rows[4 * j + 0] = iy;
                 p->rows[4 * j + 1] = min1((y >> 16) - iy);
+            }
+            if (x == 0 && dx > 0 && (int64_t)(dw + 1) * dx < 0x7fffffffll) { /* box i spans columns (i*dx) >> 16 .. ((i+1)*dx) >> 16 in both forms below */
+                p->colsArith = 1;
+                p->x0 = 0;
+                p->dx = dx;
             }
             if (dx & 0xffff) { /* ScaleAddCols2: two box widths */
                 p->minBoxWidth = dx >> 16;
@@ -259,10 +271,22 @@ static int planScale(int sw, int sh, int dw, int dh, int sixteen, ScalePlan * p)
             }
             if (sw * 2 == dw && x < 0x8000) { /* ScaleColsUp2 */
                 for (int i = 0; i < dw; ++i) p->cols[4 * i + 0] = i >> 1;
+                p->colsArith = 1; /* i >> 1 == (i * 0x8000) >> 16 */
+                p->x0 = 0;
+                p->dx = 0x8000;
             } else {
                 colsStepped(p, dw, x, dx);
             }
             break;
+        }
+    }
+    if (p->colsArith) { /* the closed form has to reproduce the walk: checked once per plan, O(width) */
+        const int box = (mode == AB_SCALE_BOX), frac = (mode == AB_SCALE_BILINEAR_UP || mode == AB_SCALE_BILINEAR_DOWN);
+        for (int i = 0; i < dw && p->colsArith; ++i) {
+            const int64_t t = (int64_t)p->x0 + (int64_t)i * p->dx, t1 = t + p->dx;
+            if (p->cols[4 * i + 0] != (int32_t)(t >> 16)) p->colsArith = 0;
+            if (box && p->cols[4 * i + 1] != (int32_t)((t1 >> 16) - (t >> 16))) p->colsArith = 0;
+            if (frac && p->cols[4 * i + 1] != (int32_t)(t & 0xffff)) p->colsArith = 0;
         }
     }
     return 1;
@@ -302,7 +326,8 @@ typedef struct PlaneIO { /* one plane, both ends on the device; strides in bytes
 enum { kPlanCacheSize = 32 };
 typedef struct PlanCacheEntry {
     int used, device, sw, sh, dw, dh, sixteen;
-    int mode, linearOnly, minBoxWidth;
+    int mode, linearOnly, minBoxWidth, colsArith;
+    int32_t x0, dx;
     int32_t * dRows;
     int32_t * dCols;
 } PlanCacheEntry;
@@ -344,6 +369,9 @@ static int planCacheGet(int sw, int sh, int dw, int dh, int sixteen, PlanCacheEn
             c.mode = plan.mode;
             c.linearOnly = plan.linearOnly;
             c.minBoxWidth = plan.minBoxWidth;
+            c.colsArith = plan.colsArith;
+            c.x0 = plan.x0;
+            c.dx = plan.dx;
             int ok = 1;
             if (plan.mode) {
                 const size_t rb = (size_t)dh * 4 * sizeof(int32_t), cb = (size_t)dw * 4 * sizeof(int32_t);
@@ -384,6 +412,9 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
             plans[k].mode = cached[k].mode;
             plans[k].linearOnly = cached[k].linearOnly;
             plans[k].minBoxWidth = cached[k].minBoxWidth;
+            plans[k].colsArith = cached[k].colsArith;
+            plans[k].x0 = cached[k].x0;
+            plans[k].dx = cached[k].dx;
             continue;
         }
         if (!planScale(io[k].sw, io[k].sh, io[k].dw, io[k].dh, bps == 2, &plans[k])) {
@@ -424,6 +455,9 @@ static cudaError_t scalePlanesOnDevice(const PlaneIO * io, int count, int bps, i
         job->mode = (uint8_t)plans[k].mode;
         job->linearOnly = (uint8_t)plans[k].linearOnly;
         job->minBoxWidth = plans[k].minBoxWidth;
+        job->colsArith = (uint8_t)plans[k].colsArith;
+        job->x0 = plans[k].x0;
+        job->dx = plans[k].dx;
         if (isCached[k]) {
             job->rows = cached[k].dRows;
             job->cols = cached[k].dCols;

@@ -195,21 +195,32 @@ __device__ __forceinline__ const T * src_row(const AbScaleJob & J, int y)
     return reinterpret_cast<const T *>(J.src + (int64_t)y * J.srcRB);
 }
 
-/* samples a0 + k .. a0 + k + VL of a source row as one vector (columns past the plane replicate the last one: they only ever meet
- * zero weights) */
+/* samples a .. a + VL of a source row as one vector (columns past the plane replicate the last one: they only ever meet zero
+ * weights).  The element-wise form is rare (unaligned planes, the last vector of a row) and kept out of line: these loops run
+ * once per unit, so their code has to stay small enough for the instruction caches (ncu: no_instruction was the top stall) */
+template <typename T>
+__device__ __noinline__ uint4 load_vec_slow(const T * row, int a, int last)
+{
+    constexpr int VL = Vec16<T>::N;
+    uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll 1
+    for (int e = 0; e < VL; ++e) {
+        const uint32_t s = (uint32_t)row[min(a + e, last)];
+        const int word = (sizeof(T) == 1) ? (e >> 2) : (e >> 1);
+        const uint32_t v = (sizeof(T) == 1) ? (s << (8 * (e & 3))) : (s << (16 * (e & 1)));
+        if (word == 0) w[0] |= v;
+        else if (word == 1) w[1] |= v;
+        else if (word == 2) w[2] |= v;
+        else w[3] |= v;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
 template <typename T>
 __device__ __forceinline__ uint4 load_vec(const AbScaleJob & J, const T * row, int a, bool srcAligned)
 {
     constexpr int VL = Vec16<T>::N;
     if (srcAligned && a + VL <= J.srcW) return __ldg(reinterpret_cast<const uint4 *>(row + a));
-    uint32_t w[4] = { 0, 0, 0, 0 };
-#pragma unroll
-    for (int e = 0; e < VL; ++e) {
-        const uint32_t s = (uint32_t)row[min(a + e, J.srcW - 1)];
-        if (sizeof(T) == 1) w[e >> 2] |= s << (8 * (e & 3));
-        else w[e >> 1] |= s << (16 * (e & 1));
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    return load_vec_slow<T>(row, a, J.srcW - 1);
 }
 
 /* 8 bytes of destination row j starting at sample i (i + VEC may run past i1: the tail is stored sample by sample) */
@@ -274,86 +285,137 @@ __device__ __forceinline__ uint32_t box_sum(const typename std::conditional<size
     return sum;
 }
 
+/* column of the 16.16 position of destination sample i: from the closed form x0 + i * dx when the host vouches for it
+ * (AbScaleJob::colsArith -- no dependent table load on the unit's critical path), else from cols[] */
+__device__ __forceinline__ uint32_t col_pos(const AbScaleJob & J, int i) { return (uint32_t)J.x0 + (uint32_t)i * (uint32_t)J.dx; } /* < 2^31: csrc/scale.c checks before it sets colsArith */
+
 template <typename T>
 __device__ bool seg_box(const AbScaleJob & J, const Seg & S, uint8_t * stage)
 {
     typedef typename std::conditional<sizeof(T) == 1, uint16_t, uint32_t>::type Acc;
     constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
     const int m = J.minBoxWidth;
-    const int c0 = J.cols[4 * S.i0], cl = J.cols[4 * (S.i1 - 1)] + J.cols[4 * (S.i1 - 1) + 1];
+    const bool arith = J.colsArith != 0;
+    /* the first row's table entry: asked for before anything else so that its latency hides behind the column arithmetic */
+    int iyNext = J.rows[4 * S.j0], bhNext = J.rows[4 * S.j0 + 1];
+    const int c0 = arith ? (int)(col_pos(J, S.i0) >> 16) : J.cols[4 * S.i0];
+    const int cl = arith ? (int)(col_pos(J, S.i1) >> 16) : J.cols[4 * (S.i1 - 1)] + J.cols[4 * (S.i1 - 1) + 1];
     const int a0 = S.srcAligned ? (c0 & ~(VL - 1)) : c0;
     const int span = cl - a0;
     if (m < 1 || c0 < 0 || cl > J.srcW || span > kStageBytes / (int)sizeof(Acc) - VL) return false;
     Acc * cs = reinterpret_cast<Acc *>(stage);
     const int i = S.i0 + (int)S.lane * VEC;
-    uint32_t info[VEC]; /* staging offset of the box | (one column more than minBoxWidth) << 16 | (inside the segment) << 17 */
-    bool odd = false;
-#pragma unroll
-    for (int o = 0; o < VEC; ++o) {
-        info[o] = 0;
-        if (i + o < S.i1) {
+    /* staging offset of the lane's box o | (one column more than minBoxWidth) << 16 | (inside the segment) << 17; derived where it is
+     * used (a few integer operations from the closed form) instead of being held across the loads of the row */
+    auto box_info = [&](int o, bool & odd) -> uint32_t {
+        if (i + o >= S.i1) return 0u;
+        int ix, bw;
+        if (arith) { /* widths are minBoxWidth or one more by construction: (i + 1) * dx >> 16 minus i * dx >> 16, verified on the host */
+            const uint32_t t = col_pos(J, i + o);
+            ix = (int)(t >> 16);
+            bw = (int)((t + (uint32_t)J.dx) >> 16) - ix;
+        } else {
             const int4 C = __ldg(reinterpret_cast<const int4 *>(J.cols) + i + o);
-            odd = odd || (C.y != m + C.z) || (C.z != 0 && C.z != 1) || (C.x < a0);
-            info[o] = (uint32_t)((C.x - a0) & 0xFFFF) | ((uint32_t)(C.z & 1) << 16) | (1u << 17);
+            ix = C.x;
+            bw = C.y;
+            odd = odd || (C.y != m + C.z) || (bw != m && bw != m + 1) || (ix < a0);
         }
+        return (uint32_t)((ix - a0) & 0xFFFF) | ((uint32_t)((bw - m) & 1) << 16) | (1u << 17);
+    };
+    bool odd = false;
+    if (!arith) {
+#pragma unroll 1
+        for (int o = 0; o < VEC; ++o) (void)box_info(o, odd);
     }
     if (__any_sync(0xFFFFFFFFu, odd)) return false; /* never for the tables of csrc/scale.c; the sampler would handle it */
     int lastBh = -1;
     uint32_t scale0 = 0, scale1 = 0;
     for (int j = S.j0; j < S.j1; ++j) {
-        const int iy = J.rows[4 * j], bh = J.rows[4 * j + 1];
+        const int iy = iyNext, bh = bhNext;
+        if (j + 1 < S.j1) {
+            iyNext = J.rows[4 * (j + 1)];
+            bhNext = J.rows[4 * (j + 1) + 1];
+        }
         if (iy < 0 || bh < 1 || iy + bh > J.srcH || (sizeof(T) == 1 && bh > 257)) { /* 8-bit sums past 2^16 wrap (scale_common.c:316-328) */
             rows_generic<T>(J, S, j, j + 1);
             continue;
+        }
+        /* two vectors per lane and pass, two rows at a time: four loads in flight per lane */
+        for (int k = (int)S.lane * VL; k < span; k += 64 * VL) {
+            const int k1 = k + 32 * VL;
+            const bool second = k1 < span;
+            /* 8 words of sums per vector, in memory order: 8-bit samples as pairs of 16-bit sums (no carry between the halves:
+             * bh * 255 < 2^16), 16-bit samples as 32-bit sums */
+            uint32_t accA[8], accB[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) accA[e] = accB[e] = 0;
+            const uint8_t * row = J.src + (int64_t)iy * J.srcRB;
+            for (int r0 = 0; r0 < bh; r0 += 2) {
+                uint4 va[2], vb[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    va[r] = vb[r] = make_uint4(0u, 0u, 0u, 0u);
+                    if (r0 + r < bh) {
+                        const T * q = reinterpret_cast<const T *>(row + (int64_t)(r0 + r) * J.srcRB);
+                        va[r] = load_vec<T>(J, q, a0 + k, S.srcAligned);
+                        if (second) vb[r] = load_vec<T>(J, q, a0 + k1, S.srcAligned);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint32_t wa[4] = { va[r].x, va[r].y, va[r].z, va[r].w }, wb[4] = { vb[r].x, vb[r].y, vb[r].z, vb[r].w };
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (sizeof(T) == 1) {
+                            accA[2 * q] += __byte_perm(wa[q], 0u, 0x4140u);     /* bytes 0, 1 -> two 16-bit lanes */
+                            accA[2 * q + 1] += __byte_perm(wa[q], 0u, 0x4342u); /* bytes 2, 3 */
+                            accB[2 * q] += __byte_perm(wb[q], 0u, 0x4140u);
+                            accB[2 * q + 1] += __byte_perm(wb[q], 0u, 0x4342u);
+                        } else {
+                            accA[2 * q] += wa[q] & 0xFFFFu;
+                            accA[2 * q + 1] += wa[q] >> 16;
+                            accB[2 * q] += wb[q] & 0xFFFFu;
+                            accB[2 * q + 1] += wb[q] >> 16;
+                        }
+                    }
+                }
+            }
+            *reinterpret_cast<uint4 *>(cs + k) = make_uint4(accA[0], accA[1], accA[2], accA[3]);
+            *reinterpret_cast<uint4 *>(cs + k + VL / 2) = make_uint4(accA[4], accA[5], accA[6], accA[7]);
+            if (second) {
+                *reinterpret_cast<uint4 *>(cs + k1) = make_uint4(accB[0], accB[1], accB[2], accB[3]);
+                *reinterpret_cast<uint4 *>(cs + k1 + VL / 2) = make_uint4(accB[4], accB[5], accB[6], accB[7]);
+            }
         }
         if (bh != lastBh) { /* scaletbl[0], [1] (scale.c:58-59 / ScaleAddCols2) */
             scale0 = (uint32_t)(65536 / (m * bh));
             scale1 = (uint32_t)(65536 / ((m + 1) * bh));
             lastBh = bh;
         }
-        for (int k = (int)S.lane * VL; k < span; k += 32 * VL) {
-            /* 8 words of sums, in memory order: 8-bit samples as pairs of 16-bit sums (no carry between the halves: bh * 255 < 2^16),
-             * 16-bit samples as 32-bit sums */
-            uint32_t acc[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = 0;
-            const T * row = reinterpret_cast<const T *>(J.src + (int64_t)iy * J.srcRB);
-#pragma unroll 4
-            for (int r = 0; r < bh; ++r) {
-                const uint4 v = load_vec<T>(J, row, a0 + k, S.srcAligned);
-                row = reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(row) + J.srcRB);
-                const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (sizeof(T) == 1) {
-                        acc[2 * q] += __byte_perm(w[q], 0u, 0x4140u);     /* bytes 0, 1 -> two 16-bit lanes */
-                        acc[2 * q + 1] += __byte_perm(w[q], 0u, 0x4342u); /* bytes 2, 3 */
-                    } else {
-                        acc[2 * q] += w[q] & 0xFFFFu;
-                        acc[2 * q + 1] += w[q] >> 16;
-                    }
-                }
-            }
-            *reinterpret_cast<uint4 *>(cs + k) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<uint4 *>(cs + k + VL / 2) = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-        }
         __syncwarp();
         if (i < S.i1) {
-            int v[VEC];
-#pragma unroll
+            /* rolled on purpose (code size): the 8 outputs are packed into two words as they are produced */
+            uint32_t w0 = 0, w1 = 0;
+#pragma unroll 1
             for (int o = 0; o < VEC; ++o) {
-                const Acc * q = cs + (info[o] & 0xFFFFu);
-                const uint32_t extra = (info[o] >> 16) & 1u;
-                uint32_t sum;
-                switch (m) { /* warp-uniform */
-                    case 2: sum = box_sum<T, 2>(q, m, extra); break;
-                    case 3: sum = box_sum<T, 3>(q, m, extra); break;
-                    case 4: sum = box_sum<T, 4>(q, m, extra); break;
-                    default: sum = box_sum<T, 0>(q, m, extra); break;
-                }
-                v[o] = (info[o] >> 17) ? (int)((sum * (extra ? scale1 : scale0)) >> 16) : 0;
+                bool ignored = false;
+                const uint32_t inf = box_info(o, ignored);
+                const Acc * q = cs + (inf & 0xFFFFu);
+                uint32_t sum = ((inf >> 16) & 1u) ? (uint32_t)q[m] : 0u;
+                for (int c = 0; c < m; ++c) sum += (uint32_t)q[c]; /* m is warp-uniform */
+                const uint32_t val = (inf >> 17) ? (((sum * (((inf >> 16) & 1u) ? scale1 : scale0)) >> 16) & (sizeof(T) == 1 ? 0xFFu : 0xFFFFu)) : 0u;
+                const int sh = (int)(8 * sizeof(T)) * (o % (VEC / 2));
+                if (o < VEC / 2) w0 |= val << sh;
+                else w1 |= val << sh;
             }
-            store_group<T>(J, j, i, S.i1, v, S.dstAligned);
+            T * out = reinterpret_cast<T *>(J.dst + (int64_t)j * J.dstRB) + i;
+            if (S.dstAligned && i + VEC <= S.i1) {
+                *reinterpret_cast<uint2 *>(out) = make_uint2(w0, w1);
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < VEC; ++k)
+                    if (i + k < S.i1) out[k] = (T)(((k < VEC / 2) ? w0 : w1) >> ((int)(8 * sizeof(T)) * (k % (VEC / 2))));
+            }
         }
         __syncwarp();
     }
@@ -367,10 +429,14 @@ __device__ bool seg_bilinear_down(const AbScaleJob & J, const Seg & S, uint8_t *
 {
     constexpr int VL = Vec16<T>::N, VEC = 8 / (int)sizeof(T);
     const int xmax = J.srcW - 1;
-    const int c0 = min(max(J.cols[4 * S.i0], 0), xmax), cl = min(J.cols[4 * (S.i1 - 1)] + (POINT ? 1 : 2), J.srcW);
+    const bool arith = J.colsArith != 0;
+    int yiNext = J.rows[4 * S.j0], yfNext = (POINT || J.linearOnly) ? 0 : J.rows[4 * S.j0 + 1];
+    const int xFirst = arith ? (int)(col_pos(J, S.i0) >> 16) : J.cols[4 * S.i0];
+    const int xLast = arith ? (int)(col_pos(J, S.i1 - 1) >> 16) : J.cols[4 * (S.i1 - 1)];
+    const int c0 = min(max(xFirst, 0), xmax), cl = min(xLast + (POINT ? 1 : 2), J.srcW);
     const int a0 = S.srcAligned ? (c0 & ~(VL - 1)) : c0;
     const int span = cl - a0;
-    if (span <= 0 || span > kStageBytes / (int)sizeof(T) - VL || J.cols[4 * (S.i1 - 1)] < J.cols[4 * S.i0]) return false;
+    if (span <= 0 || span > kStageBytes / (int)sizeof(T) - VL || xLast < xFirst) return false;
     T * sv = reinterpret_cast<T *>(stage);
     const int i = S.i0 + (int)S.lane * VEC;
     uint32_t info[VEC]; /* fraction | staging offset << 16 | (right neighbour is one further) << 31 */
@@ -378,29 +444,52 @@ __device__ bool seg_bilinear_down(const AbScaleJob & J, const Seg & S, uint8_t *
     for (int o = 0; o < VEC; ++o) {
         info[o] = 0;
         if (i + o < S.i1) {
-            const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * (i + o)));
-            const int xa = min(max(C.x, 0), xmax);
-            info[o] = (uint32_t)(C.y & 0xFFFF) | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
+            int xi, xf;
+            if (arith) {
+                const uint32_t t = col_pos(J, i + o);
+                xi = (int)(t >> 16);
+                xf = (int)(t & 0xFFFFu);
+            } else {
+                const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * (i + o)));
+                xi = C.x;
+                xf = C.y & 0xFFFF;
+            }
+            const int xa = min(max(xi, 0), xmax);
+            info[o] = (uint32_t)xf | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
         }
     }
     for (int j = S.j0; j < S.j1; ++j) {
-        const int yi = J.rows[4 * j], yf = (POINT || J.linearOnly) ? 0 : J.rows[4 * j + 1];
+        const int yi = yiNext, yf = yfNext;
+        if (j + 1 < S.j1) {
+            yiNext = J.rows[4 * (j + 1)];
+            yfNext = (POINT || J.linearOnly) ? 0 : J.rows[4 * (j + 1) + 1];
+        }
         const T * ra = src_row<T>(J, yi);
         const T * rb = src_row<T>(J, yi + 1);
-        for (int k = (int)S.lane * VL; k < span; k += 32 * VL) {
-            uint4 a = load_vec<T>(J, ra, a0 + k, S.srcAligned);
+        for (int k = (int)S.lane * VL; k < span; k += 64 * VL) { /* two vectors per lane and pass: every load of the row in flight at once */
+            const int k1 = k + 32 * VL;
+            const bool second = k1 < span;
+            uint4 a[2], b[2];
+            a[0] = load_vec<T>(J, ra, a0 + k, S.srcAligned);
+            a[1] = second ? load_vec<T>(J, ra, a0 + k1, S.srcAligned) : make_uint4(0u, 0u, 0u, 0u);
             if (yf) {
-                const uint4 b = load_vec<T>(J, rb, a0 + k, S.srcAligned);
-                uint32_t w[4] = { 0, 0, 0, 0 };
+                b[0] = load_vec<T>(J, rb, a0 + k, S.srcAligned);
+                b[1] = second ? load_vec<T>(J, rb, a0 + k1, S.srcAligned) : make_uint4(0u, 0u, 0u, 0u);
+                auto lerp_vec = [&](const uint4 & va, const uint4 & vb) -> uint4 {
+                    uint32_t w[4] = { 0, 0, 0, 0 };
 #pragma unroll
-                for (int e = 0; e < VL; ++e) {
-                    const uint32_t t = (uint32_t)interp((int)vec_sample<T>(a, e), (int)vec_sample<T>(b, e), yf);
-                    if (sizeof(T) == 1) w[e >> 2] |= t << (8 * (e & 3));
-                    else w[e >> 1] |= t << (16 * (e & 1));
-                }
-                a = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < VL; ++e) {
+                        const uint32_t t = (uint32_t)interp((int)vec_sample<T>(va, e), (int)vec_sample<T>(vb, e), yf);
+                        if (sizeof(T) == 1) w[e >> 2] |= t << (8 * (e & 3));
+                        else w[e >> 1] |= t << (16 * (e & 1));
+                    }
+                    return make_uint4(w[0], w[1], w[2], w[3]);
+                };
+                a[0] = lerp_vec(a[0], b[0]);
+                if (second) a[1] = lerp_vec(a[1], b[1]);
             }
-            *reinterpret_cast<uint4 *>(sv + k) = a;
+            *reinterpret_cast<uint4 *>(sv + k) = a[0];
+            if (second) *reinterpret_cast<uint4 *>(sv + k1) = a[1];
         }
         __syncwarp();
         if (i < S.i1) {
@@ -435,9 +524,11 @@ __device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
     const int xmax = J.srcW - 1;
     int c0, cl;
     if (KIND == 0) {
-        if (J.cols[4 * (S.i1 - 1)] < J.cols[4 * S.i0]) return false;
-        c0 = min(max(J.cols[4 * S.i0], 0), xmax);
-        cl = min(J.cols[4 * (S.i1 - 1)] + 2, J.srcW);
+        const int xFirst = J.colsArith ? (int)(col_pos(J, S.i0) >> 16) : J.cols[4 * S.i0];
+        const int xLast = J.colsArith ? (int)(col_pos(J, S.i1 - 1) >> 16) : J.cols[4 * (S.i1 - 1)];
+        if (xLast < xFirst) return false;
+        c0 = min(max(xFirst, 0), xmax);
+        cl = min(xLast + 2, J.srcW);
     } else {
         c0 = max((S.i0 - 1) >> 1, 0);
         cl = min(max(((S.i1 - 2) >> 1) + 2, 1), J.srcW);
@@ -455,9 +546,18 @@ __device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
         const int x = i + o;
         if (x < S.i1) {
             if (KIND == 0) {
-                const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * x));
-                const int xa = min(max(C.x, 0), xmax);
-                info[o] = (uint32_t)(C.y & 0xFFFF) | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
+                int xi, xf;
+                if (J.colsArith) {
+                    const uint32_t t = col_pos(J, x);
+                    xi = (int)(t >> 16);
+                    xf = (int)(t & 0xFFFFu);
+                } else {
+                    const int2 C = __ldg(reinterpret_cast<const int2 *>(J.cols + 4 * x));
+                    xi = C.x;
+                    xf = C.y & 0xFFFF;
+                }
+                const int xa = min(max(xi, 0), xmax);
+                info[o] = (uint32_t)xf | ((uint32_t)(xa - a0) << 16) | ((xa < xmax) ? 0x80000000u : 0u);
             } else if (x == 0 || x == J.dstW - 1) {
                 const int k = ((x == 0) ? 0 : (J.dstW - 1) / 2) - a0;
                 info[o] = (uint32_t)k | ((uint32_t)k << 16);
@@ -472,6 +572,12 @@ __device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
     int id0 = -1, id1 = -1;
 #pragma unroll
     for (int o = 0; o < VEC; ++o) h0[o] = h1[o] = 0;
+    /* the walk goes down the source rows one at a time: right after a row has been filtered the lane asks for its 16 bytes of the
+     * NEXT row (one vector per lane covers the span of an up-scaling segment), so that the load is long done when that row is
+     * needed -- a destination row then costs arithmetic only */
+    const bool canPre = span <= 32 * VL;
+    uint4 pre = make_uint4(0u, 0u, 0u, 0u);
+    int preRow = -1;
     for (int j = S.j0; j < S.j1; ++j) {
         int p, q, yf = 0; /* rows of the first / second operand */
         if (KIND == 0) {
@@ -501,19 +607,25 @@ __device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
             else if (id1 == r) slot = 1;
             else {
                 slot = op ? (1 - sp) : ((id0 == q) ? 1 : 0);
-                stage_raw<T>(J, r, a0, span, S.srcAligned, st, S.lane);
+                if (canPre && preRow == r) {
+                    if ((int)S.lane * VL < span) *reinterpret_cast<uint4 *>(st + (int)S.lane * VL) = pre;
+                } else {
+                    stage_raw<T>(J, r, a0, span, S.srcAligned, st, S.lane);
+                }
                 __syncwarp();
-#pragma unroll
-                for (int o = 0; o < VEC; ++o) {
-                    int h;
+                auto hfilter = [&](int o) -> int {
                     if (KIND == 0) {
                         const int xa = (int)((info[o] >> 16) & 0x7FFFu);
-                        h = blend<T>((int)st[xa], (int)st[xa + (int)(info[o] >> 31)], (int)(info[o] & 0xFFFFu));
-                    } else {
-                        h = 3 * (int)st[info[o] & 0xFFFFu] + (int)st[info[o] >> 16];
+                        return blend<T>((int)st[xa], (int)st[xa + (int)(info[o] >> 31)], (int)(info[o] & 0xFFFFu));
                     }
-                    if (slot == 0) h0[o] = h;
-                    else h1[o] = h;
+                    return 3 * (int)st[info[o] & 0xFFFFu] + (int)st[info[o] >> 16];
+                };
+                if (slot == 0) { /* warp-uniform: two copies of the loop instead of a select per output */
+#pragma unroll
+                    for (int o = 0; o < VEC; ++o) h0[o] = hfilter(o);
+                } else {
+#pragma unroll
+                    for (int o = 0; o < VEC; ++o) h1[o] = hfilter(o);
                 }
                 __syncwarp();
                 if (slot == 0) id0 = r;
@@ -522,15 +634,41 @@ __device__ bool seg_up(const AbScaleJob & J, const Seg & S, uint8_t * stage)
             if (op == 0) sp = slot;
             else sq = slot;
         }
+        if (canPre) { /* ask for the row below everything the slots hold, once */
+            const int nxt = max(id0, id1) + 1;
+            if (nxt < J.srcH && nxt != preRow) {
+                preRow = nxt;
+                if ((int)S.lane * VL < span) pre = load_vec<T>(J, src_row<T>(J, nxt), a0 + (int)S.lane * VL, S.srcAligned);
+            }
+        }
         if (i < S.i1) {
             int v[VEC];
+            /* the vertical combination, written out per (slot of p, slot of q) and per class of the row's fraction -- all warp-uniform
+             * -- so that the 8 outputs are straight arithmetic without selects or per-sample branches */
+            auto combine = [&](const int (&a)[VEC], const int (&b)[VEC]) {
+                if (KIND == 0) { /* InterpolateRow_C, row_common.c:46-105 */
+                    if (yf == 0) {
 #pragma unroll
-            for (int o = 0; o < VEC; ++o) {
-                const int a = sp ? h1[o] : h0[o], b = sq ? h1[o] : h0[o];
-                if (KIND == 0) v[o] = interp(a, b, yf);
-                else if (KIND == 1) v[o] = (3 * a + b + 8) >> 4;
-                else v[o] = (a + 2) >> 2;
-            }
+                        for (int o = 0; o < VEC; ++o) v[o] = a[o];
+                    } else if (yf == 128) {
+#pragma unroll
+                        for (int o = 0; o < VEC; ++o) v[o] = (a[o] + b[o] + 1) >> 1;
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < VEC; ++o) v[o] = (a[o] * (256 - yf) + b[o] * yf + 128) >> 8;
+                    }
+                } else if (KIND == 1) {
+#pragma unroll
+                    for (int o = 0; o < VEC; ++o) v[o] = (3 * a[o] + b[o] + 8) >> 4;
+                } else {
+#pragma unroll
+                    for (int o = 0; o < VEC; ++o) v[o] = (a[o] + 2) >> 2;
+                }
+            };
+            if (sp == 0 && sq == 1) combine(h0, h1);
+            else if (sp == 1 && sq == 0) combine(h1, h0);
+            else if (sp == 0) combine(h0, h0);
+            else combine(h1, h1);
             store_group<T>(J, j, i, S.i1, v, S.dstAligned);
         }
     }

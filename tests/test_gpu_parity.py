@@ -314,11 +314,11 @@ def test_batch_yuv_to_rgb(gpu_product, oracle):
     name = _batch_case(gpu_product, oracle, [base] * 30, 100)
     assert name.startswith("y2r_fast") and gpu_product.avifB200KernelLaunchCount() == 2
     # same constants, different sizes (incl. ragged and tiny ones) still fuse; the 257-wide frame has 514-byte rows (not
-    # 16-byte aligned) and takes the general kernel on its own, splitting the batch into 3 launches
+    # 16-byte aligned): its tiles take the element-wise code of the same kernel (frame.vecWidth == 0), the batch stays ONE launch
     sizes = [(264, 6), (8, 3), (1000, 5), (257, 7), (2056, 2), (16, 16), (520, 9)]
     gpu_product.avifB200ResetKernelLaunchCount()
     _batch_case(gpu_product, oracle, [dataclasses.replace(base, w=w, h=h) for w, h in sizes], 200)
-    assert gpu_product.avifB200KernelLaunchCount() == 3
+    assert gpu_product.avifB200KernelLaunchCount() == 1
     # alpha + premultiply, 4:4:4
     c2 = util.Spec(w=512, h=33, depth=10, fmt=abi.AVIF_PIXEL_FORMAT_YUV444, rng=1, mc=abi.MC_BT709, alpha=True, rgb_depth=10,
                    rgb_fmt=abi.AVIF_RGB_FORMAT_RGBA, rgb_premult=True)

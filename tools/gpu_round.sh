@@ -10,7 +10,7 @@ nvidia-smi topo -m >> $OUT/gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket|NUMA" >> $OUT/gpu.txt
 NG=$(nvidia-smi -L | wc -l)
 if [ "$2" != "skiptests" ]; then
-  timeout 1500 python -m pytest tests -q -m gpu -x > $OUT/pytest_gpu.log 2>&1
+  timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1
   tail -25 $OUT/pytest_gpu.log
 fi
 timeout 900 python bench.py --extras > $OUT/bench.json 2> $OUT/bench.err
