@@ -14,6 +14,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "plan.h"
 
 namespace {
@@ -177,26 +181,20 @@ __device__ __forceinline__ float alpha_value(uint32_t code, const AbPixFmt & f)
     return code_value(code, f);
 }
 
-/* src/reformat.c:1899-1939; the float -> integer casts truncate */
-__device__ __forceinline__ void set_rgba(uint8_t * row, uint32_t x, const AbPixFmt & f, const float px[4])
+/* src/reformat.c:1899-1939; the float -> integer casts truncate.  Split in two -- the codes of a pixel, then the store -- so that
+ * the colour codes can also come from the threshold table (see tone_thresh_kernel). */
+__device__ __forceinline__ uint32_t quant_code(float v, float maxF) { return __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(v, maxF))); }
+
+__device__ __forceinline__ void store_codes(uint8_t * row, uint32_t x, const AbPixFmt & f, const uint32_t q[4])
 {
     uint8_t * p = row + (size_t)x * f.pixBytes;
     if (f.chanBytes > 1) {
-        if (f.isFloat) {
-            *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)(__float_as_uint(__fmul_rn(px[0], AB_F16_MULTIPLIER)) >> 13);
-            *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)(__float_as_uint(__fmul_rn(px[1], AB_F16_MULTIPLIER)) >> 13);
-            *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)(__float_as_uint(__fmul_rn(px[2], AB_F16_MULTIPLIER)) >> 13);
-            if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)(__float_as_uint(__fmul_rn(px[3], AB_F16_MULTIPLIER)) >> 13);
-        } else {
-            *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[0], f.maxF)));
-            *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[1], f.maxF)));
-            *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[2], f.maxF)));
-            if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[3], f.maxF)));
-        }
+        *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)q[0];
+        *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)q[1];
+        *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)q[2];
+        if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)q[3];
     } else {
-        const uint32_t R = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[0], f.maxF))) & 0xFFu;
-        const uint32_t G = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[1], f.maxF))) & 0xFFu;
-        const uint32_t B = __float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[2], f.maxF))) & 0xFFu;
+        const uint32_t R = q[0] & 0xFFu, G = q[1] & 0xFFu, B = q[2] & 0xFFu;
         if (f.is565) {
             *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)((B >> 3) | ((G >> 2) << 5) | ((R >> 3) << 11)); /* :619 */
             return; /* 565 has no alpha */
@@ -204,8 +202,65 @@ __device__ __forceinline__ void set_rgba(uint8_t * row, uint32_t x, const AbPixF
         p[f.offR] = (uint8_t)R;
         p[f.offG] = (uint8_t)G;
         p[f.offB] = (uint8_t)B;
-        if (f.hasAlpha) p[f.offA] = (uint8_t)(__float2uint_rz(__fadd_rn(0.5f, __fmul_rn(px[3], f.maxF))) & 0xFFu);
+        if (f.hasAlpha) p[f.offA] = (uint8_t)(q[3] & 0xFFu);
     }
+}
+
+__device__ __forceinline__ void set_rgba(uint8_t * row, uint32_t x, const AbPixFmt & f, const float px[4])
+{
+    if (f.chanBytes > 1 && f.isFloat) {
+        uint8_t * p = row + (size_t)x * f.pixBytes;
+        *reinterpret_cast<uint16_t *>(p + f.offR) = (uint16_t)(__float_as_uint(__fmul_rn(px[0], AB_F16_MULTIPLIER)) >> 13);
+        *reinterpret_cast<uint16_t *>(p + f.offG) = (uint16_t)(__float_as_uint(__fmul_rn(px[1], AB_F16_MULTIPLIER)) >> 13);
+        *reinterpret_cast<uint16_t *>(p + f.offB) = (uint16_t)(__float_as_uint(__fmul_rn(px[2], AB_F16_MULTIPLIER)) >> 13);
+        if (f.hasAlpha) *reinterpret_cast<uint16_t *>(p + f.offA) = (uint16_t)(__float_as_uint(__fmul_rn(px[3], AB_F16_MULTIPLIER)) >> 13);
+        return;
+    }
+    const uint32_t q[4] = { quant_code(px[0], f.maxF), quant_code(px[1], f.maxF), quant_code(px[2], f.maxF), f.hasAlpha ? quant_code(px[3], f.maxF) : 0u };
+    store_codes(row, x, f, q);
+}
+
+/* ---- output transfer function as a step function -----------------------------------------------------------------------
+ * For integer outputs the stored code is a monotone step function of the linear value:  code(x) = (T)(0.5 + clamp(g(x)) * max)
+ * with g non-decreasing for all 13 transfer functions.  So code(x) = number of thresholds t_k <= x, t_k = the smallest float whose
+ * code is >= k (k = 1..max).  The thresholds are found once per (device, transfer function, max) by bisection over the float bit
+ * patterns with g evaluated in double and rounded once (what glibc's correctly rounded powf / logf return), kept for the life of
+ * the process, copied into shared memory by every block and searched in log2(max + 1) steps: 8 / 10 / 12 shared loads and compares
+ * per channel instead of up to two powf.  Used for channel depths <= 12. */
+__device__ __forceinline__ uint32_t exact_code(int tf, float x, float maxF)
+{
+    const float g = fminf(1.0f, fmaxf(0.0f, to_gamma<true>(tf, x)));
+    return quant_code(g, maxF);
+}
+
+__global__ void __launch_bounds__(128) tone_thresh_kernel(float * T, uint32_t n, int tf, float maxF)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x + 1u; /* the code this threshold opens */
+    if (k > n) return;
+    float t;
+    if (exact_code(tf, 0.0f, maxF) >= k) {
+        t = -__int_as_float(0x7F800000); /* (no transfer function of the table does this) */
+    } else if (exact_code(tf, __int_as_float(0x7F800000), maxF) < k) {
+        t = __int_as_float(0x7FC00000); /* never reached: compares false against everything */
+    } else {
+        uint32_t lo = 0u, hi = 0x7F800000u; /* positive floats order like their bit patterns; code(lo) < k <= code(hi) */
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (exact_code(tf, __uint_as_float(mid), maxF) >= k) hi = mid;
+            else lo = mid;
+        }
+        t = __uint_as_float(hi);
+    }
+    T[k - 1u] = t;
+}
+
+/* number of thresholds <= x; n + 1 is a power of two */
+__device__ __forceinline__ uint32_t thresh_code(const float * sT, uint32_t n, float x)
+{
+    uint32_t pos = 0;
+    for (uint32_t s = (n + 1u) >> 1; s; s >>= 1)
+        if (sT[pos + s - 1u] <= x) pos += s;
+    return pos;
 }
 
 /* src/colrconvert.c:70-75, :178-186: y = M.x in double, left-to-right sums, back to float */
@@ -237,9 +292,14 @@ __global__ void __launch_bounds__(256) tone_lut_kernel(const __grid_constant__ A
     }
 }
 
-template <bool P>
-__global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ AbToneMapJob J)
+template <bool P, bool TAB>
+__global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ AbToneMapJob J, const float * __restrict__ thresh, uint32_t threshN)
 {
+    extern __shared__ float sThresh[];
+    if (TAB) {
+        for (uint32_t k = threadIdx.x; k < threshN; k += blockDim.x) sThresh[k] = thresh[k];
+        __syncthreads();
+    }
     const uint64_t total = (uint64_t)J.width * J.height;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     float localMax = 0.0f;  /* src/gainmap.c:213: starts at 0, only larger values replace it */
@@ -251,14 +311,22 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
         uint32_t bc[4];
         load_codes(J.base + (int64_t)y * J.baseRB, x, J.baseFmt, bc);
         float base[4], out[4];
+        bool stored = false; /* TAB: the pixel has been written from the threshold table */
         base[3] = alpha_value(bc[3], J.baseFmt);
         if (!J.applyGain) { /* src/gainmap.c:152-167 */
             if (J.transcode) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear<P>(J.tfIn, code_value(bc[c], J.baseFmt));
                 if (J.inConv) convert_primaries(base, J.inM);
+                if (TAB) { /* the codes straight from the step function */
+                    const uint32_t q[4] = { thresh_code(sThresh, threshN, base[0]), thresh_code(sThresh, threshN, base[1]), thresh_code(sThresh, threshN, base[2]),
+                                            J.outFmt.hasAlpha ? quant_code(base[3], J.outFmt.maxF) : 0u };
+                    store_codes(J.out + (int64_t)y * J.outRB, x, J.outFmt, q);
+                    stored = true;
+                } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) base[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, base[c])));
+                    for (int c = 0; c < 3; ++c) base[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, base[c])));
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) base[c] = code_value(bc[c], J.baseFmt);
@@ -282,15 +350,21 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
             if (J.outConv) convert_primaries(out, J.outM);
             bool bad = false;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                bad = bad || isnan(out[c]);
-                out[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, out[c])));
-            }
+            for (int c = 0; c < 3; ++c) bad = bad || isnan(out[c]);
             if (bad && (uint32_t)i < localNan) localNan = (uint32_t)i;
             out[3] = base[3];
             localSum += (double)pixelMax;
+            if (TAB) {
+                const uint32_t q[4] = { thresh_code(sThresh, threshN, out[0]), thresh_code(sThresh, threshN, out[1]), thresh_code(sThresh, threshN, out[2]),
+                                        J.outFmt.hasAlpha ? quant_code(out[3], J.outFmt.maxF) : 0u };
+                store_codes(J.out + (int64_t)y * J.outRB, x, J.outFmt, q);
+                stored = true;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) out[c] = fminf(1.0f, fmaxf(0.0f, to_gamma<P>(J.tfOut, out[c])));
+            }
         }
-        set_rgba(J.out + (int64_t)y * J.outRB, x, J.outFmt, out);
+        if (!stored) set_rgba(J.out + (int64_t)y * J.outRB, x, J.outFmt, out);
     }
     if (!J.applyGain) return;
     /* block reduction, then one atomic each */
@@ -327,6 +401,51 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
 
 } // namespace
 
+/* AVIF_B200_TONEMAP_TABLE=0 evaluates the output transfer function per pixel as before (A/B timing, tests of both forms) */
+static bool abToneMapNoThresholds()
+{
+    static int off = -1;
+    if (off < 0) {
+        const char * e = getenv("AVIF_B200_TONEMAP_TABLE");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    return off == 1;
+}
+
+/* thresholds of (device, transfer function, channel maximum): built on first use, immutable afterwards, never freed */
+struct ThreshEntry {
+    int device, tf;
+    uint32_t n;
+    float * d;
+};
+static ThreshEntry gThresh[64];
+static int gThreshCount = 0;
+static std::mutex gThreshLock;
+
+static const float * thresholds_for(int tf, uint32_t n, float maxF, cudaStream_t st)
+{
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> hold(gThreshLock);
+    for (int k = 0; k < gThreshCount; ++k)
+        if (gThresh[k].device == device && gThresh[k].tf == tf && gThresh[k].n == n) return gThresh[k].d;
+    if (gThreshCount >= 64) return nullptr;
+    float * d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)n * sizeof(float)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    tone_thresh_kernel<<<(n + 127u) / 128u, 128, 0, st>>>(d, n, tf, maxF);
+    /* other threads (other streams) may pick the entry up as soon as it is published: finish it first, once */
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        (void)cudaFree(d);
+        return nullptr;
+    }
+    gThresh[gThreshCount++] = ThreshEntry{ device, tf, n, d };
+    return d;
+}
+
 extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
 {
     const uint64_t total = (uint64_t)job->width * job->height;
@@ -337,7 +456,15 @@ extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
     if (lutN) tone_lut_kernel<<<(lutN + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*job);
     /* 16-bit integer channels resolve the last ulp of the output transfer function: evaluate it in double there */
     const bool precise = (job->outFmt.chanBytes > 1 && !job->outFmt.isFloat && job->outFmt.maxF > 4095.5f);
-    if (precise) tone_map_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
-    else tone_map_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job);
+    /* integer channels of at most 12 bits: the output transfer function as a searched step function (when a transfer function runs at all) */
+    const float * thresh = nullptr;
+    uint32_t threshN = 0;
+    if (!job->outFmt.isFloat && job->outFmt.maxF < 4095.5f && (job->applyGain || job->transcode) && !abToneMapNoThresholds()) {
+        threshN = (uint32_t)job->outFmt.maxF;
+        if (((threshN + 1u) & threshN) == 0u) thresh = thresholds_for(job->tfOut, threshN, job->outFmt.maxF, (cudaStream_t)stream);
+    }
+    if (thresh) tone_map_kernel<false, true><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (precise) tone_map_kernel<true, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
+    else tone_map_kernel<false, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
     return (int)cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 TAG=${1:-r02k}
 mkdir -p gpurun_out/$TAG
 timeout 900 python -m pytest tests/test_gpu_scale.py tests/test_gpu_gainmap.py tests/test_gpu_aux.py -q -m gpu 2>&1 | tail -15
+AVIF_B200_TONEMAP_TABLE=0 timeout 900 python -m pytest tests/test_gpu_gainmap.py -q -m gpu 2>&1 | tail -3
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scale_" --csv --log-file gpurun_out/$TAG/scale_launches.csv \
     python tools/profile_cases.py gpurun_out/$TAG/cases_sc.json --only SC > gpurun_out/$TAG/ncu_sc.log 2>&1
 grep -E "scale_batch" gpurun_out/$TAG/scale_launches.csv | awk -F'","' '{print $5, $(NF)}' | cut -c1-160
