@@ -306,8 +306,15 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
     double localSum = 0.0;
     uint32_t localNan = 0xFFFFFFFFu;
     const bool baseTab = (J.baseLutN != 0);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const uint32_t y = (uint32_t)(i / J.width), x = (uint32_t)(i - (uint64_t)y * J.width);
+    /* (x, y) advance by the grid stride incrementally: a 64-bit division per pixel costs more than a transfer function */
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stepY = (uint32_t)(stride / J.width), stepX = (uint32_t)(stride - (uint64_t)stepY * J.width);
+    uint32_t y = (uint32_t)(i0 / J.width), x = (uint32_t)(i0 - (uint64_t)y * J.width);
+    for (uint64_t i = i0; i < total; i += stride, x += stepX, y += stepY) {
+        if (x >= J.width) { /* at most one wrap: stepX < width */
+            x -= J.width;
+            ++y;
+        }
         uint32_t bc[4];
         load_codes(J.base + (int64_t)y * J.baseRB, x, J.baseFmt, bc);
         float base[4], out[4];
