@@ -254,12 +254,17 @@ __global__ void __launch_bounds__(128) tone_thresh_kernel(float * T, uint32_t n,
     T[k - 1u] = t;
 }
 
-/* number of thresholds <= x; n + 1 is a power of two */
-__device__ __forceinline__ uint32_t thresh_code(const float * sT, uint32_t n, float x)
+/* number of thresholds <= x among 2^STEPS - 1 sorted ones: STEPS shared loads at constant offsets from a running position,
+ * fully unrolled (a rolled loop cost 11 instructions per step, more than the powf calls it replaced: ncu r02t) */
+template <int STEPS>
+__device__ __forceinline__ uint32_t thresh_code(const float * sT, float x)
 {
     uint32_t pos = 0;
-    for (uint32_t s = (n + 1u) >> 1; s; s >>= 1)
+#pragma unroll
+    for (int k = STEPS - 1; k >= 0; --k) {
+        const uint32_t s = 1u << k;
         if (sT[pos + s - 1u] <= x) pos += s;
+    }
     return pos;
 }
 
@@ -292,9 +297,11 @@ __global__ void __launch_bounds__(256) tone_lut_kernel(const __grid_constant__ A
     }
 }
 
-template <bool P, bool TAB>
+/* STEPS > 0: integer outputs of STEPS-bit channels through the threshold table (2^STEPS - 1 entries) */
+template <bool P, int STEPS>
 __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ AbToneMapJob J, const float * __restrict__ thresh, uint32_t threshN)
 {
+    constexpr bool TAB = (STEPS > 0);
     extern __shared__ float sThresh[];
     if (TAB) {
         for (uint32_t k = threadIdx.x; k < threshN; k += blockDim.x) sThresh[k] = thresh[k];
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
                 for (int c = 0; c < 3; ++c) base[c] = baseTab ? J.baseLut[bc[c]] : to_linear<P>(J.tfIn, code_value(bc[c], J.baseFmt));
                 if (J.inConv) convert_primaries(base, J.inM);
                 if (TAB) { /* the codes straight from the step function */
-                    const uint32_t q[4] = { thresh_code(sThresh, threshN, base[0]), thresh_code(sThresh, threshN, base[1]), thresh_code(sThresh, threshN, base[2]),
+                    const uint32_t q[4] = { thresh_code<STEPS>(sThresh, base[0]), thresh_code<STEPS>(sThresh, base[1]), thresh_code<STEPS>(sThresh, base[2]),
                                             J.outFmt.hasAlpha ? quant_code(base[3], J.outFmt.maxF) : 0u };
                     store_codes(J.out + (int64_t)y * J.outRB, x, J.outFmt, q);
                     stored = true;
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
             out[3] = base[3];
             localSum += (double)pixelMax;
             if (TAB) {
-                const uint32_t q[4] = { thresh_code(sThresh, threshN, out[0]), thresh_code(sThresh, threshN, out[1]), thresh_code(sThresh, threshN, out[2]),
+                const uint32_t q[4] = { thresh_code<STEPS>(sThresh, out[0]), thresh_code<STEPS>(sThresh, out[1]), thresh_code<STEPS>(sThresh, out[2]),
                                         J.outFmt.hasAlpha ? quant_code(out[3], J.outFmt.maxF) : 0u };
                 store_codes(J.out + (int64_t)y * J.outRB, x, J.outFmt, q);
                 stored = true;
@@ -470,8 +477,10 @@ extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
         threshN = (uint32_t)job->outFmt.maxF;
         if (((threshN + 1u) & threshN) == 0u) thresh = thresholds_for(job->tfOut, threshN, job->outFmt.maxF, (cudaStream_t)stream);
     }
-    if (thresh) tone_map_kernel<false, true><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
-    else if (precise) tone_map_kernel<true, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
-    else tone_map_kernel<false, false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
+    if (thresh && threshN == 255u) tone_map_kernel<false, 8><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (thresh && threshN == 1023u) tone_map_kernel<false, 10><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (thresh && threshN == 4095u) tone_map_kernel<false, 12><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (precise) tone_map_kernel<true, 0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
+    else tone_map_kernel<false, 0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
     return (int)cudaGetLastError();
 }

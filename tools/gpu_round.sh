@@ -50,3 +50,6 @@ if [ -e libavif_b200/csrc/variants/libavif_b200_tma.so ]; then
   ncu -i ${REP}_tma.ncu-rep --page source --csv --kernel-id :::1 > $OUT/src_tma_c3.csv 2>/dev/null
 fi
 ls -la $OUT
+# the rows beyond the reformat path: their tests, kernel times of the scaling cases, tone mapping with and without the threshold table
+bash tools/gpu_rows.sh $TAG > $OUT/rows.log 2>&1
+tail -30 $OUT/rows.log
