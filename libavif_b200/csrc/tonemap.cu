@@ -254,19 +254,27 @@ __global__ void __launch_bounds__(128) tone_thresh_kernel(float * T, uint32_t n,
     T[k - 1u] = t;
 }
 
-/* number of thresholds <= x among 2^STEPS - 1 sorted ones: STEPS shared loads at constant offsets from a running position,
- * fully unrolled (a rolled loop cost 11 instructions per step, more than the powf calls it replaced: ncu r02t) */
+/* number of thresholds <= x among 2^STEPS - 1 sorted ones.  The block keeps them in LEVEL ORDER (Eytzinger: node i has children 2i and
+ * 2i + 1, level k occupies words 2^k .. 2^(k+1) - 1): the lanes of a warp then read neighbouring words at every level.  In sorted
+ * order the candidates of a level all sit a multiple of 32 words apart -- one shared-memory bank -- and the middle levels of the
+ * search serialised up to 32-fold (ncu r02z: short_scoreboard 11 warps per issue, issue utilisation 46 %).  STEPS loads at a running
+ * index, fully unrolled; the leaf index reached is the rank. */
 template <int STEPS>
-__device__ __forceinline__ uint32_t thresh_code(const float * sT, float x)
+__device__ __forceinline__ uint32_t thresh_code(const float * sE, float x)
 {
-    uint32_t pos = 0;
+    uint32_t i = 1;
 #pragma unroll
-    for (int k = STEPS - 1; k >= 0; --k) {
-        const uint32_t s = 1u << k;
-        if (sT[pos + s - 1u] <= x) pos += s;
-    }
-    return pos;
+    for (int k = 0; k < STEPS; ++k) i = 2u * i + ((sE[i] <= x) ? 1u : 0u);
+    return i - (1u << STEPS);
 }
+/* sorted index of level-order node i (1-based) of a complete tree with `steps` levels */
+__device__ __forceinline__ uint32_t eytzinger_source(uint32_t i, int steps)
+{
+    const int k = 31 - __clz((int)i);       /* depth of the node */
+    const uint32_t j = i - (1u << k);        /* its index within the level */
+    return ((2u * j + 1u) << (steps - 1 - k)) - 1u;
+}
+
 
 /* src/colrconvert.c:70-75, :178-186: y = M.x in double, left-to-right sums, back to float */
 __device__ __forceinline__ void convert_primaries(float px[4], const double * M)
@@ -303,8 +311,8 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
 {
     constexpr bool TAB = (STEPS > 0);
     extern __shared__ float sThresh[];
-    if (TAB) {
-        for (uint32_t k = threadIdx.x; k < threshN; k += blockDim.x) sThresh[k] = thresh[k];
+    if (TAB) { /* word 0 is unused; words 1 .. threshN hold the thresholds in level order */
+        for (uint32_t i = 1u + threadIdx.x; i <= threshN; i += blockDim.x) sThresh[i] = thresh[eytzinger_source(i, STEPS)];
         __syncthreads();
     }
     const uint64_t total = (uint64_t)J.width * J.height;
@@ -477,9 +485,9 @@ extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
         threshN = (uint32_t)job->outFmt.maxF;
         if (((threshN + 1u) & threshN) == 0u) thresh = thresholds_for(job->tfOut, threshN, job->outFmt.maxF, (cudaStream_t)stream);
     }
-    if (thresh && threshN == 255u) tone_map_kernel<false, 8><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
-    else if (thresh && threshN == 1023u) tone_map_kernel<false, 10><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
-    else if (thresh && threshN == 4095u) tone_map_kernel<false, 12><<<(unsigned)blocks, 256, threshN * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    if (thresh && threshN == 255u) tone_map_kernel<false, 8><<<(unsigned)blocks, 256, (threshN + 1u) * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (thresh && threshN == 1023u) tone_map_kernel<false, 10><<<(unsigned)blocks, 256, (threshN + 1u) * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
+    else if (thresh && threshN == 4095u) tone_map_kernel<false, 12><<<(unsigned)blocks, 256, (threshN + 1u) * sizeof(float), (cudaStream_t)stream>>>(*job, thresh, threshN);
     else if (precise) tone_map_kernel<true, 0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
     else tone_map_kernel<false, 0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*job, nullptr, 0u);
     return (int)cudaGetLastError();
