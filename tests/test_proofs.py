@@ -31,3 +31,30 @@ def test_two_operation_division_and_its_exception(tmp_path):
     bad = {int(l.split()[0], 16): int(l.split("bad=")[1]) for l in out.splitlines() if "bad=" in l}
     assert bad[0x3FC9930C] == 0 and bad[0x477FFF00] == 0
     assert bad[0x3FEE5BB7] > 0  # the listed exception really fails: it keeps the three-operation form
+
+
+def test_level_order_threshold_search_equals_a_sorted_search():
+    """csrc/tonemap.cu keeps the 2^d - 1 output-transfer-function thresholds of a depth in LEVEL order (Eytzinger) in shared memory and
+    walks i -> 2i + (E[i] <= x); the leaf reached minus 2^d must be the number of thresholds <= x (what a search of the sorted
+    array gives), NaN thresholds (codes the function never reaches) acting as +inf.  Restated in numpy for d = 8, 10, 12."""
+    import numpy as np
+    rng = np.random.RandomState(3)
+    for d in (8, 10, 12):
+        n = (1 << d) - 1
+        t = np.sort(rng.random_sample(n).astype(np.float32))
+        t[-5:] = np.nan  # unreachable codes sit at the tail
+        i = np.arange(1, n + 1)
+        k = np.floor(np.log2(i)).astype(np.int64)
+        j = i - (1 << k)
+        src = ((2 * j + 1) << (d - 1 - k)) - 1  # eytzinger_source()
+        assert np.array_equal(np.sort(src), np.arange(n))
+        e = np.empty(n + 1, dtype=np.float32)
+        e[0] = 0
+        e[1:] = t[src]
+        x = np.concatenate([rng.random_sample(5000).astype(np.float32) * 1.2 - 0.1, t[:200], [np.float32(np.inf), np.float32(-np.inf)]])
+        pos = np.ones(len(x), dtype=np.int64)
+        with np.errstate(invalid="ignore"):
+            for _ in range(d):
+                pos = 2 * pos + (e[pos] <= x)
+        want = np.searchsorted(t[:-5], x, side="right")  # NaN tail never counts
+        assert np.array_equal(pos - (1 << d), want), d
