@@ -1,5 +1,7 @@
 /*
- * scale_kernels.cu -- plane scaling with libyuv's integer arithmetic, one thread per destination sample.
+ * scale_kernels.cu -- plane scaling with libyuv's integer arithmetic.  A warp produces (segment of 32 x 8 bytes,
+ * block of destination rows) units through per-loop code that stages source rows in shared memory (further down); the table-driven
+ * one-sample-at-a-time form that follows first is the fallback and the second implementation.
  *
  * avifImageScale (src/scale.c:24-201) hands every plane to libyuv's ScalePlane / ScalePlane_12 with kFilterBox
  * (third_party/libyuv/source/scale.c:829-1007 in the reference tree).  After ScaleFilterReduce that is one of seven loops; each
@@ -127,45 +129,6 @@ __device__ __forceinline__ int scale_sample(const AbScaleJob & J, const int32_t 
     }
 }
 
-/* ScalePlaneUp2_Linear / _Bilinear (scale.c:467-538, scale_any.c:27-78) for a thread's 8 (u8) or 4 (u16) consecutive outputs that
- * all lie strictly inside the row (i0 >= 1 .. i0 + VEC - 1 <= dstW - 2): outputs i0..i0+VEC-1 read source columns
- * (i0 - 1) / 2 .. (i0 + VEC - 2) / 2 + 1, i.e. VEC / 2 + 2 columns when i0 is even -- loaded once per row instead of four
- * clamped byte loads per output. */
-template <typename T, bool BILINEAR>
-__device__ __forceinline__ void up2_group(const AbScaleJob & J, int i0, int j, int v[8 / sizeof(T)])
-{
-    constexpr int VEC = 8 / (int)sizeof(T);
-    constexpr int NC = VEC / 2 + 2;
-    int rs = 0, rt = 0; /* near row gets weights (9,3) / (3,1), far row (3,1); linear: one row */
-    if (BILINEAR) {
-        if (j != 0) {
-            const int r = (j - 1) >> 1;
-            if (r >= J.srcH - 1) rs = rt = J.srcH - 1;
-            else if ((j - 1) & 1) { rs = r + 1; rt = r; }
-            else { rs = r; rt = r + 1; }
-        }
-    } else {
-        rs = rt = j; /* the caller passes the source row */
-    }
-    const int k0 = (i0 - 1) >> 1; /* i0 even and >= 2: k0 = i0/2 - 1 >= 0 */
-    const T * ps = reinterpret_cast<const T *>(J.src + (int64_t)rs * J.srcRB) + k0;
-    const T * pt = reinterpret_cast<const T *>(J.src + (int64_t)rt * J.srcRB) + k0;
-    int a[NC], b[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        a[k] = (int)ps[k];
-        b[k] = BILINEAR ? (int)pt[k] : 0;
-    }
-#pragma unroll
-    for (int o = 0; o < VEC; ++o) {
-        const int i = i0 + o;
-        const int k = ((i - 1) >> 1) - k0;
-        const int kn = ((i - 1) & 1) ? k + 1 : k, kf = ((i - 1) & 1) ? k : k + 1;
-        if (BILINEAR) v[o] = (a[kn] * 9 + a[kf] * 3 + b[kn] * 3 + b[kf] + 8) >> 4;
-        else v[o] = ((i - 1) & 1) ? ((a[k] + 3 * a[k + 1] + 2) >> 2) : ((3 * a[k] + a[k + 1] + 2) >> 2);
-    }
-}
-
 /* ---- row-staged loops --------------------------------------------------------------------------------------------------
  * A WARP produces one segment (32 lanes x 8 bytes) of one destination row at a time, independently of the other warps of its
  * block (its own slice of shared memory, __syncwarp only), so an SM keeps 40 units in flight.  Phase 1: the source columns the
@@ -268,27 +231,12 @@ struct Seg {
 template <typename T>
 __device__ __noinline__ void rows_generic(const AbScaleJob & J, const Seg & S, int ja, int jb);
 
-/* ScalePlaneBox (scale.c:148-256): column sums of the box rows (ScaleAddRow; 8-bit sums live in uint16_t and wrap), then
- * ScaleAddCols0/1/2 (scale_common.c) over them.  A box is minBoxWidth or minBoxWidth + 1 columns wide (x advances by dx). */
-template <typename T, int M>
-__device__ __forceinline__ uint32_t box_sum(const typename std::conditional<sizeof(T) == 1, uint16_t, uint32_t>::type * q, int m, uint32_t extra)
-{
-    uint32_t sum = 0;
-    if (M > 0) {
-#pragma unroll
-        for (int c = 0; c < M; ++c) sum += (uint32_t)q[c];
-        sum += extra ? (uint32_t)q[M] : 0u;
-    } else {
-        for (int c = 0; c < m; ++c) sum += (uint32_t)q[c];
-        sum += extra ? (uint32_t)q[m] : 0u;
-    }
-    return sum;
-}
-
 /* column of the 16.16 position of destination sample i: from the closed form x0 + i * dx when the host vouches for it
  * (AbScaleJob::colsArith -- no dependent table load on the unit's critical path), else from cols[] */
 __device__ __forceinline__ uint32_t col_pos(const AbScaleJob & J, int i) { return (uint32_t)J.x0 + (uint32_t)i * (uint32_t)J.dx; } /* < 2^31: csrc/scale.c checks before it sets colsArith */
 
+/* ScalePlaneBox (scale.c:148-256): column sums of the box rows (ScaleAddRow; 8-bit sums live in uint16_t and wrap), then
+ * ScaleAddCols0/1/2 (scale_common.c) over them.  A box is minBoxWidth or minBoxWidth + 1 columns wide (x advances by dx). */
 template <typename T>
 __device__ bool seg_box(const AbScaleJob & J, const Seg & S, uint8_t * stage)
 {
