@@ -468,23 +468,51 @@ def run_c4_grid(lib, dev, sptr, stream, rank, world, dist):
     def go(timed):
         assert lib.avifB200GridRGBToYUV(canvas.ptr(), rgb.ptr(), 4, 4, comm, rank, world, 0, sptr, ctypes.byref(phase) if timed else None) == 0
         return list(phase)
-    for _ in range(4):
-        go(False)
-    rec = [go(True) for _ in range(10)]
-    t = torch.tensor([sum(x[k] for x in rec) / len(rec) for k in range(4)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sc, cv, ga, asm_ = [float(v) for v in t]
-    res = None
+
+    def measure():
+        for _ in range(4):
+            go(False)
+        rec = [go(True) for _ in range(10)]
+        t = torch.tensor([sum(x[k] for x in rec) / len(rec) for k in range(4)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t], int(lib.avifB200GridLastMode())
+
+    whole = None
     if rank == 0:
         whole = YUVImage(W_, H_, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
         assert lib.avifB200ImageRGBToYUVAsync(whole.ptr(), rgb.ptr(), sptr) == 0
         torch.cuda.synchronize()
+
+    def entry(phases, mode):
+        sc, cv, ga, asm_ = phases
+        names = ("ms_descriptor", "ms_convert_over_nvlink", "ms_tokens", "ms_assemble") if mode == 1 else ("ms_scatter", "ms_convert", "ms_gather", "ms_assemble")
+        e = dict(zip(names, phases))
+        e.update({"mode": "peer memory (CUDA IPC views of the root's canvas; NCCL carries descriptor + tokens)" if mode == 1 else "staged (grouped ncclSend/ncclRecv)",
+                  "ms_total": sc + cv + ga + asm_, "Mpixels_per_s_kernel": W_ * H_ / (cv * 1e-3) / 1e6,
+                  "Mpixels_per_s_kernel_plus_nccl": W_ * H_ / ((sc + cv + ga + asm_) * 1e-3) / 1e6})
+        if rank == 0:
+            e["check"] = "ok (== whole-canvas conversion on one GPU)" if wl.yuv_digest(whole) == wl.yuv_digest(canvas) else "MISMATCH"
+        return e
+
+    # default form first (peer memory where the canvas can be exported), then the staged NCCL exchange for the "kernel + NCCL" column
+    phases, mode = measure()
+    first = entry(phases, mode)
+    for p in canvas.present_planes():
+        canvas.bufs[p]._t.zero_()  # the second form has to produce every byte again
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    os.environ["AVIF_B200_GRID_PEER"] = "0"
+    phases2, mode2 = measure()
+    second = entry(phases2, mode2)
+    del os.environ["AVIF_B200_GRID_PEER"]
+    res = None
+    if rank == 0:
         res = {"workload": "4x4 grid of 1920x1080 RGBA8 cells -> 4:2:0 8-bit BT.601 full + alpha; canvas resident on rank 0, cells dealt round-robin",
-               "api": "avifB200GridRGBToYUV (grouped ncclSend/ncclRecv inside the library)", "n_gpus": world,
-               "ms_scatter": sc, "ms_convert": cv, "ms_gather": ga, "ms_assemble": asm_, "ms_total": sc + cv + ga + asm_,
-               "Mpixels_per_s_kernel": W_ * H_ / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": W_ * H_ / ((sc + cv + ga + asm_) * 1e-3) / 1e6,
-               "check": "ok (== whole-canvas conversion on one GPU)" if wl.yuv_digest(whole) == wl.yuv_digest(canvas) else "MISMATCH"}
+               "api": "avifB200GridRGBToYUV", "n_gpus": world}
+        res.update(first)
+        res["staged"] = second
     gridcomm.destroy_comm(lib, comm)
     return res
 

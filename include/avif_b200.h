@@ -436,11 +436,15 @@ AVIF_B200_API avifResult avifB200ImageYUVToRGBRowsAsync(const avifImage * image,
  * the same descriptors (dimensions, formats, flags); plane / pixel pointers are device memory on `root` and unused elsewhere
  * (for avifB200GridYUVToRGB the row strides tell the other ranks which planes exist).  All work is enqueued on `stream`.
  *   avifB200GridCellRect      cell `cellIndex` (row-major) of the reference's split rule; INVALID_ARGUMENT where the rule fails
- *   avifB200GridRGBToYUV      cells go to rank (root + cell) mod nranks: grouped ncclSend/ncclRecv of the cells' pixels, ONE batched
- *                             launch per rank (root: views of the canvas, nothing copied), grouped exchange of the planes back,
- *                             placement into the canvas planes.  Bit-identical to converting the whole canvas (cell sizes are even
- *                             when chroma is subsampled).  phaseMs (may be NULL; synchronises when given): scatter, convert, gather,
- *                             assemble in milliseconds on this rank.
+ *   avifB200GridRGBToYUV      cells go to rank (root + cell) mod nranks, ONE batched launch per rank.  Peer-memory form (default): every
+ *                             rank maps the root's canvas through CUDA IPC and converts views of it -- the kernel's loads and stores
+ *                             cross NVLink themselves, nothing is staged; NCCL carries the canvas descriptor and one completion
+ *                             token per rank.  Staged form (canvas memory that cannot be exported, AVIF_B200_GRID_PEER=0): grouped
+ *                             ncclSend/ncclRecv of the cells' pixels, exchange of the planes back, placement into the canvas planes.
+ *                             Either way bit-identical to converting the whole canvas (cell sizes are even when chroma is
+ *                             subsampled).  phaseMs (may be NULL; synchronises when given), milliseconds on this rank: scatter,
+ *                             convert, gather, assemble (staged) or descriptor, convert over NVLink, tokens, 0 (peer memory).
+ *   avifB200GridLastMode      1 if the calling thread's last avifB200GridRGBToYUV ran in the peer-memory form, else 0.
  *   avifB200GridYUVToRGB      decode side: the canvas is cut into nranks even row bands, each shipped with one chroma row of halo
  *                             per inner seam and converted against whole-canvas geometry (bilinear upsampling is not tile-local).
  *                             phaseMs: scatter, convert, gather. */
@@ -452,6 +456,7 @@ AVIF_B200_API avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBI
                                               int nranks, int root, void * stream, float phaseMs[4]);
 AVIF_B200_API avifResult avifB200GridYUVToRGB(const avifImage * canvas, avifRGBImage * canvasRgb, void * comm, int rank, int nranks, int root, void * stream,
                                               float phaseMs[3]);
+AVIF_B200_API int avifB200GridLastMode(void);
 
 /* ---- which GPU serves a synchronous (host-pointer) call ----------------------------------------------------------------
  * The reference has no notion of a device; its own parallel unit is the per-call thread fan-out of

@@ -172,6 +172,7 @@ PROTOTYPES = {
     "avifB200GridCellRect": (C.c_int, [_PI, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(avifCropRect)]),
     "avifB200GridRGBToYUV": (C.c_int, [_PI, _PR, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float * 4)]),
     "avifB200GridYUVToRGB": (C.c_int, [_PI, _PR, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float * 3)]),
+    "avifB200GridLastMode": (C.c_int, []),
     "avifB200SetDevice": (C.c_int, [C.c_int]),
     "avifB200SetDevices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "avifB200GetDevice": (C.c_int, []),

@@ -187,6 +187,94 @@ static void imageOverBuffer(const avifImage * canvas, const CellGeom * g, uint32
     v->alphaRowBytes = alpha ? g->r.width * bps : 0;
 }
 
+/* ---- peer-memory path of the encode grid ----------------------------------------------------------------------------------
+ * One process per GPU, NVSwitch between them: instead of packing cells, shipping them with NCCL, converting and shipping the planes
+ * back, every rank maps the ROOT's canvas (CUDA IPC: the pixel buffer and the four planes) and runs the fused conversion kernel on
+ * views of it -- its loads fetch the cell's pixels over NVLink and its stores put the planes where they belong, tile by tile, so the
+ * transfer overlaps the arithmetic and nothing is staged, packed or assembled.  NCCL carries two ordering points only: the
+ * descriptor of the canvas (IPC handles + offsets; stream-ordered behind whatever produced the canvas on the root), and a one-byte
+ * token per rank that tells the root its planes are complete.  Memory that cannot be exported (not from cudaMalloc), a driver
+ * without IPC or AVIF_B200_GRID_PEER=0 fall back to the staged exchange below, decided by the root and followed by every rank. */
+enum { kPeerBufs = 5 }; /* pixels, Y, U, V, A */
+typedef struct PeerCanvas {
+    uint8_t handle[kPeerBufs][64]; /* cudaIpcMemHandle_t of the allocation each buffer lives in */
+    uint64_t offset[kPeerBufs];    /* of the buffer inside its allocation */
+    uint8_t present[kPeerBufs];
+    uint8_t ok;                    /* root: every present buffer could be exported */
+    uint8_t pad[2];
+} PeerCanvas;
+
+typedef int (*AbMemGetAddressRange)(unsigned long long * base, size_t * size, unsigned long long ptr);
+static AbMemGetAddressRange peerRangeFn(void)
+{
+    static AbMemGetAddressRange fn = NULL;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        void * f = NULL;
+        enum cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (AbMemGetAddressRange)f;
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+static int peerExport(const void * ptr, uint8_t handle[64], uint64_t * offset)
+{
+    AbMemGetAddressRange range = peerRangeFn();
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (!range || range(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0 || !base) return 0;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    memcpy(handle, &h, 64);
+    *offset = (uint64_t)((uintptr_t)ptr - (uintptr_t)base);
+    return 1;
+}
+
+/* allocations of other processes this process has mapped: kept open for the life of the process (a canvas is reused frame after
+ * frame; opening costs a few hundred microseconds) */
+static struct { uint8_t handle[64]; void * base; int device; } gPeerOpen[64];
+static int gPeerOpenCount = 0;
+static pthread_mutex_t gPeerLock = PTHREAD_MUTEX_INITIALIZER;
+
+static void * peerOpen(const uint8_t handle[64])
+{
+    int device = 0;
+    (void)cudaGetDevice(&device);
+    void * base = NULL;
+    pthread_mutex_lock(&gPeerLock);
+    for (int k = 0; k < gPeerOpenCount; ++k)
+        if (gPeerOpen[k].device == device && memcmp(gPeerOpen[k].handle, handle, 64) == 0) base = gPeerOpen[k].base;
+    if (!base && gPeerOpenCount < 64) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+            memcpy(gPeerOpen[gPeerOpenCount].handle, handle, 64);
+            gPeerOpen[gPeerOpenCount].base = base;
+            gPeerOpen[gPeerOpenCount].device = device;
+            ++gPeerOpenCount;
+        } else {
+            (void)cudaGetLastError();
+            base = NULL;
+        }
+    }
+    pthread_mutex_unlock(&gPeerLock);
+    return base;
+}
+
+static __thread int gGridLastMode = 0; /* 0: one rank / staged NCCL exchange, 1: peer memory */
+int avifB200GridLastMode(void) { return gGridLastMode; }
+
+static int peerWanted(void)
+{
+    const char * e = getenv("AVIF_B200_GRID_PEER");
+    return !(e && e[0] == '0');
+}
+
 avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasRgb, uint32_t gridCols, uint32_t gridRows, void * comm, int rank, int nranks,
                                 int root, void * streamPtr, float phaseMs[4])
 {
@@ -220,6 +308,7 @@ avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasR
     uint8_t ** stageYuv = (uint8_t **)calloc(n, sizeof(void *)); /* owner: converted planes; root: received planes of a remote cell */
     cudaEvent_t ev[5] = { NULL, NULL, NULL, NULL, NULL };
     uint32_t mine = 0;
+    uint8_t *dDesc = NULL, *dTok = NULL; /* peer path: canvas descriptor, completion tokens */
     if (!cells || !imgs || !rgbs || !pImgs || !pRgbs || !stageRgb || !stageYuv) {
         res = AVIF_RESULT_OUT_OF_MEMORY;
         goto cleanup;
@@ -240,6 +329,110 @@ avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasR
     if (phaseMs) {
         for (int k = 0; k < 5; ++k) GR_CUDA(cudaEventCreate(&ev[k]));
         GR_CUDA(cudaEventRecord(ev[0], st));
+    }
+
+    gGridLastMode = 0;
+    if (nranks > 1) {
+        /* ---- peer-memory path: descriptor -> kernels on views of the root's canvas -> tokens ---- */
+        PeerCanvas pc;
+        memset(&pc, 0, sizeof(pc));
+        const void * bufs[kPeerBufs] = { NULL, NULL, NULL, NULL, NULL };
+        if (isRoot) {
+            bufs[0] = canvasRgb->pixels;
+            bufs[1] = canvas->yuvPlanes[0];
+            bufs[2] = mono ? NULL : canvas->yuvPlanes[1];
+            bufs[3] = mono ? NULL : canvas->yuvPlanes[2];
+            bufs[4] = alpha ? canvas->alphaPlane : NULL;
+            pc.ok = (uint8_t)peerWanted();
+            for (int b = 0; b < kPeerBufs && pc.ok; ++b) {
+                pc.present[b] = (bufs[b] != NULL);
+                if (bufs[b] && !peerExport(bufs[b], pc.handle[b], &pc.offset[b])) pc.ok = 0;
+            }
+        }
+        GR_CUDA((cudaError_t)abScratchAllocOn((void **)&dDesc, sizeof(pc) + 64, st));
+        if (isRoot) GR_CUDA(cudaMemcpyAsync(dDesc, &pc, sizeof(pc), cudaMemcpyHostToDevice, st));
+        GR_NCCL(nccl.GroupStart());
+        for (int r = 0; r < nranks; ++r) {
+            if (r == root) continue;
+            if (isRoot) GR_NCCL(nccl.Send(dDesc, sizeof(pc), kNcclUint8, r, comm, st));
+            else if (r == rank) GR_NCCL(nccl.Recv(dDesc, sizeof(pc), kNcclUint8, root, comm, st));
+        }
+        GR_NCCL(nccl.GroupEnd());
+        if (!isRoot) { /* the descriptor is behind everything the root had queued before the call: the canvas is ready when it arrives */
+            GR_CUDA(cudaMemcpyAsync(&pc, dDesc, sizeof(pc), cudaMemcpyDeviceToHost, st));
+            GR_CUDA(cudaStreamSynchronize(st));
+        }
+        if (pc.ok) {
+            uint8_t token = 1;
+            avifImage peerCanvas = *canvas;
+            avifRGBImage peerRgb = *canvasRgb;
+            if (!isRoot) {
+                uint8_t * mapped[kPeerBufs] = { NULL, NULL, NULL, NULL, NULL };
+                for (int b = 0; b < kPeerBufs; ++b) {
+                    if (!pc.present[b]) continue;
+                    uint8_t * base = (uint8_t *)peerOpen(pc.handle[b]);
+                    if (!base) token = 0; /* reported to the root below; this rank converts nothing */
+                    else mapped[b] = base + pc.offset[b];
+                }
+                peerRgb.pixels = mapped[0];
+                peerCanvas.yuvPlanes[0] = mapped[1];
+                peerCanvas.yuvPlanes[1] = mapped[2];
+                peerCanvas.yuvPlanes[2] = mapped[3];
+                peerCanvas.alphaPlane = mapped[4];
+                /* strides and extents of the views are the root's: every rank was handed the same canvas description */
+            }
+            if (phaseMs) GR_CUDA(cudaEventRecord(ev[1], st));
+            if (token) {
+                for (uint32_t u = 0; u < n; ++u) {
+                    const CellGeom * g = &cells[u];
+                    if (g->owner != rank) continue;
+                    avifRGBImage * r = &rgbs[mine];
+                    *r = peerRgb;
+                    r->width = g->r.width;
+                    r->height = g->r.height;
+                    r->pixels = peerRgb.pixels + (size_t)g->r.y * peerRgb.rowBytes + (size_t)g->r.x * pix;
+                    viewOfCanvas(&peerCanvas, g, bps, sx, sy, &imgs[mine]);
+                    pImgs[mine] = &imgs[mine];
+                    pRgbs[mine] = r;
+                    ++mine;
+                }
+                if (mine) {
+                    res = avifB200ImageRGBToYUVBatchAsync(pImgs, pRgbs, mine, st);
+                    if (res != AVIF_RESULT_OK) token = 0;
+                }
+            }
+            if (phaseMs) GR_CUDA(cudaEventRecord(ev[2], st));
+            /* tokens: stream-ordered behind each rank's kernel, so the root's stream continues only when every plane is complete */
+            GR_CUDA((cudaError_t)abScratchAllocOn((void **)&dTok, (size_t)nranks + 64, st));
+            if (!isRoot) GR_CUDA(cudaMemcpyAsync(dTok + rank, &token, 1, cudaMemcpyHostToDevice, st));
+            GR_NCCL(nccl.GroupStart());
+            for (int r = 0; r < nranks; ++r) {
+                if (r == root) continue;
+                if (isRoot) GR_NCCL(nccl.Recv(dTok + r, 1, kNcclUint8, r, comm, st));
+                else if (r == rank) GR_NCCL(nccl.Send(dTok + rank, 1, kNcclUint8, root, comm, st));
+            }
+            GR_NCCL(nccl.GroupEnd());
+            if (phaseMs) GR_CUDA(cudaEventRecord(ev[3], st));
+            if (isRoot) {
+                uint8_t toks[256];
+                const int m = nranks < 256 ? nranks : 256;
+                memset(toks, 1, sizeof(toks));
+                GR_CUDA(cudaMemcpyAsync(toks, dTok, (size_t)m, cudaMemcpyDeviceToHost, st));
+                GR_CUDA(cudaStreamSynchronize(st));
+                for (int r = 0; r < m; ++r)
+                    if (r != root && !toks[r]) res = AVIF_RESULT_UNKNOWN_ERROR; /* a rank could not map the canvas or failed to convert */
+            } else if (!token && res == AVIF_RESULT_OK) {
+                res = AVIF_RESULT_UNKNOWN_ERROR;
+            }
+            gGridLastMode = 1;
+            if (phaseMs) {
+                GR_CUDA(cudaEventRecord(ev[4], st));
+                GR_CUDA(cudaEventSynchronize(ev[4]));
+                for (int k = 0; k < 4; ++k) GR_CUDA(cudaEventElapsedTime(&phaseMs[k], ev[k], ev[k + 1])); /* descriptor, convert over NVLink, tokens, 0 */
+            }
+            goto cleanup;
+        }
+        /* the root could not (or was told not to) export its canvas: every rank takes the staged exchange */
     }
 
     /* ---- 1. scatter the pixels of remote cells (root packs each cell's rectangle into a contiguous staging buffer) ---- */
@@ -325,6 +518,8 @@ avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasR
     }
 
 cleanup:
+    if (dDesc) (void)cudaFreeAsync(dDesc, st);
+    if (dTok) (void)cudaFreeAsync(dTok, st);
     if (stageRgb)
         for (uint32_t u = 0; u < n; ++u)
             if (stageRgb[u]) (void)cudaFreeAsync(stageRgb[u], st);

@@ -73,28 +73,48 @@ def grid_encode(timed=None):
         timed.append(list(phase))
 
 
-grid_encode()
-torch.cuda.synchronize()
+def zero_canvas():
+    for p_ in canvas.present_planes():
+        canvas.bufs[p_]._t.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+
+whole = None
 if rank == 0:
     whole = YUVImage(W, H, 8, A.AVIF_PIXEL_FORMAT_YUV420, A.AVIF_RANGE_FULL, A.MC_BT601, alpha=True, device=dev)
     assert lib.avifB200ImageRGBToYUVAsync(whole.ptr(), rgb.ptr(), sptr) == 0
     torch.cuda.synchronize()
-    out["encode_check"] = "ok" if wl.yuv_digest(whole) == wl.yuv_digest(canvas) else "MISMATCH"
-if not check_only:
-    for _ in range(3):
-        grid_encode()
-    rec = []
-    for _ in range(10):
-        grid_encode(rec)
-    t = torch.tensor([[sum(x[k] for x in rec) / len(rec) for k in range(4)]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sc, cv, ga, asm_ = [float(v) for v in t[0]]
-    px = W * H
-    out["encode"] = {"workload": "C4: 4x4 grid of 1920x1080 cells, RGBA8 -> 4:2:0 8-bit BT.601 full + alpha, cells dealt to (cell mod N)",
-                     "ms_scatter": sc, "ms_convert": cv, "ms_gather": ga, "ms_assemble": asm_, "ms_total": sc + cv + ga + asm_,
-                     "Mpixels_per_s_kernel": px / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": px / ((sc + cv + ga + asm_) * 1e-3) / 1e6,
-                     "timing": "CUDA events inside avifB200GridRGBToYUV, mean of 10 calls, max over ranks per phase"}
+# both forms of the multi-rank path: peer memory (default where the canvas can be exported) and the staged NCCL exchange
+for form, env in (("", None), ("_staged", "0")):
+    if env is not None:
+        os.environ["AVIF_B200_GRID_PEER"] = env
+    zero_canvas()
+    grid_encode()
+    torch.cuda.synchronize()
+    mode = int(lib.avifB200GridLastMode())
+    if rank == 0:
+        out["encode_check" + form] = "ok" if wl.yuv_digest(whole) == wl.yuv_digest(canvas) else "MISMATCH"
+        out["encode_mode" + form] = "peer memory" if mode == 1 else ("staged NCCL exchange" if world > 1 else "one rank")
+    if not check_only:
+        for _ in range(3):
+            grid_encode()
+        rec = []
+        for _ in range(10):
+            grid_encode(rec)
+        t = torch.tensor([[sum(x[k] for x in rec) / len(rec) for k in range(4)]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sc, cv, ga, asm_ = [float(v) for v in t[0]]
+        px = W * H
+        out["encode" + form] = {"workload": "C4: 4x4 grid of 1920x1080 cells, RGBA8 -> 4:2:0 8-bit BT.601 full + alpha, cells dealt to (cell mod N)",
+                                "mode": out.get("encode_mode" + form),
+                                "ms_scatter_or_descriptor": sc, "ms_convert": cv, "ms_gather_or_tokens": ga, "ms_assemble": asm_, "ms_total": sc + cv + ga + asm_,
+                                "Mpixels_per_s_kernel": px / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": px / ((sc + cv + ga + asm_) * 1e-3) / 1e6,
+                                "timing": "CUDA events inside avifB200GridRGBToYUV, mean of 10 calls, max over ranks per phase"}
+    if env is not None:
+        del os.environ["AVIF_B200_GRID_PEER"]
 
 # ---------------- decode side: 8K 4:2:0 12-bit + alpha (premultiplied) -> RGBA12, bilinear: row bands with chroma halo ----------------
 img = wl.make_yuv("C3", device=dev)
