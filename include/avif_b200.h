@@ -444,10 +444,13 @@ AVIF_B200_API avifResult avifB200ImageYUVToRGBRowsAsync(const avifImage * image,
  *                             Either way bit-identical to converting the whole canvas (cell sizes are even when chroma is
  *                             subsampled).  phaseMs (may be NULL; synchronises when given), milliseconds on this rank: scatter,
  *                             convert, gather, assemble (staged) or descriptor, convert over NVLink, tokens, 0 (peer memory).
- *   avifB200GridLastMode      1 if the calling thread's last avifB200GridRGBToYUV ran in the peer-memory form, else 0.
- *   avifB200GridYUVToRGB      decode side: the canvas is cut into nranks even row bands, each shipped with one chroma row of halo
- *                             per inner seam and converted against whole-canvas geometry (bilinear upsampling is not tile-local).
- *                             phaseMs: scatter, convert, gather. */
+ *   avifB200GridLastMode      1 if the calling thread's last avifB200Grid* conversion ran in the peer-memory form, else 0.
+ *   avifB200GridYUVToRGB      decode side: the canvas is cut into nranks even row bands, each converted against whole-canvas geometry
+ *                             with one chroma row of halo per inner seam (bilinear upsampling is not tile-local); bands and results
+ *                             travel by grouped ncclSend/ncclRecv.  AVIF_B200_GRID_PEER_DECODE=1 (every rank alike) converts straight
+ *                             from and into the root's peer-mapped canvas instead -- measured slower (strided 16-byte pixel stores
+ *                             over NVLink), kept as a switch.  phaseMs: scatter, convert, gather (or descriptor, convert, tokens).
+ *   avifB200GridLastMode applies to both. */
 AVIF_B200_API avifResult avifB200GridGetUniqueId(uint8_t id[128]);
 AVIF_B200_API avifResult avifB200GridCommInit(void ** comm, int nranks, int rank, const uint8_t id[128]);
 AVIF_B200_API avifResult avifB200GridCommDestroy(void * comm);

@@ -274,6 +274,11 @@ static int peerWanted(void)
     const char * e = getenv("AVIF_B200_GRID_PEER");
     return !(e && e[0] == '0');
 }
+static int peerDecodeWanted(void)
+{
+    const char * e = getenv("AVIF_B200_GRID_PEER_DECODE");
+    return e && e[0] == '1';
+}
 
 avifResult avifB200GridRGBToYUV(avifImage * canvas, const avifRGBImage * canvasRgb, uint32_t gridCols, uint32_t gridRows, void * comm, int rank, int nranks,
                                 int root, void * streamPtr, float phaseMs[4])
@@ -573,7 +578,9 @@ avifResult avifB200GridYUVToRGB(const avifImage * canvas, avifRGBImage * canvasR
 
     avifResult res = AVIF_RESULT_OK;
     uint8_t * inBuf[64] = { 0 }, * outBuf[64] = { 0 };
+    uint8_t *dDesc = NULL, *dTok = NULL;
     cudaEvent_t ev[4] = { NULL, NULL, NULL, NULL };
+    gGridLastMode = 0;
     if (nranks > 64) return AVIF_RESULT_INVALID_ARGUMENT;
     struct Band { uint32_t r0, r1, c0, c1; size_t yB, cB, aB, inB, outB; int owner; } band[64];
     int nb = 0;
@@ -594,6 +601,89 @@ avifResult avifB200GridYUVToRGB(const avifImage * canvas, avifRGBImage * canvasR
     if (phaseMs) {
         for (int k = 0; k < 4; ++k) GR_CUDA(cudaEventCreate(&ev[k]));
         GR_CUDA(cudaEventRecord(ev[0], st));
+    }
+    if (nranks > 1 && peerDecodeWanted()) {
+        /* ---- peer-memory form (see avifB200GridRGBToYUV): every rank converts its band straight from the root's planes -- halo rows
+         * included, they are just rows of the mapped plane -- into the root's pixel buffer.  OPT-IN (AVIF_B200_GRID_PEER_DECODE=1, to
+         * be set on every rank alike): measured SLOWER than the staged exchange (2 GPUs, 8K RGBA16 output: 1.46 ms against 0.64 ms,
+         * profiles/r02_variants.md) -- the pixel stores of a warp are 32 separate 16-byte pieces 64 bytes apart, which NVLink carries
+         * at ~190 GB/s, where the encode side's plane stores are whole 256-byte runs ---- */
+        PeerCanvas pc;
+        memset(&pc, 0, sizeof(pc));
+        if (isRoot) {
+            const void * bufs[kPeerBufs] = { canvasRgb->pixels, canvas->yuvPlanes[0], haveC ? canvas->yuvPlanes[1] : NULL, haveC ? canvas->yuvPlanes[2] : NULL,
+                                             haveA ? canvas->alphaPlane : NULL };
+            pc.ok = (uint8_t)peerWanted();
+            for (int b = 0; b < kPeerBufs && pc.ok; ++b) {
+                pc.present[b] = (bufs[b] != NULL);
+                if (bufs[b] && !peerExport(bufs[b], pc.handle[b], &pc.offset[b])) pc.ok = 0;
+            }
+        }
+        GR_CUDA((cudaError_t)abScratchAllocOn((void **)&dDesc, sizeof(pc) + 64, st));
+        if (isRoot) GR_CUDA(cudaMemcpyAsync(dDesc, &pc, sizeof(pc), cudaMemcpyHostToDevice, st));
+        GR_NCCL(nccl.GroupStart());
+        for (int r = 0; r < nranks; ++r) {
+            if (r == root) continue;
+            if (isRoot) GR_NCCL(nccl.Send(dDesc, sizeof(pc), kNcclUint8, r, comm, st));
+            else if (r == rank) GR_NCCL(nccl.Recv(dDesc, sizeof(pc), kNcclUint8, root, comm, st));
+        }
+        GR_NCCL(nccl.GroupEnd());
+        if (!isRoot) {
+            GR_CUDA(cudaMemcpyAsync(&pc, dDesc, sizeof(pc), cudaMemcpyDeviceToHost, st));
+            GR_CUDA(cudaStreamSynchronize(st));
+        }
+        if (pc.ok) {
+            uint8_t token = 1;
+            avifImage v = *canvas;
+            avifRGBImage o = *canvasRgb;
+            if (!isRoot) {
+                uint8_t * mapped[kPeerBufs] = { NULL, NULL, NULL, NULL, NULL };
+                for (int b = 0; b < kPeerBufs; ++b) {
+                    if (!pc.present[b]) continue;
+                    uint8_t * base = (uint8_t *)peerOpen(pc.handle[b]);
+                    if (!base) token = 0;
+                    else mapped[b] = base + pc.offset[b];
+                }
+                o.pixels = mapped[0];
+                v.yuvPlanes[0] = mapped[1];
+                v.yuvPlanes[1] = mapped[2];
+                v.yuvPlanes[2] = mapped[3];
+                v.alphaPlane = mapped[4];
+            }
+            if (phaseMs) GR_CUDA(cudaEventRecord(ev[1], st));
+            for (int k = 0; k < nb && token; ++k) {
+                if (band[k].owner != rank) continue;
+                if (avifB200ImageYUVToRGBRowsAsync(&v, &o, band[k].r0, band[k].r1, st) != AVIF_RESULT_OK) token = 0;
+            }
+            if (phaseMs) GR_CUDA(cudaEventRecord(ev[2], st));
+            GR_CUDA((cudaError_t)abScratchAllocOn((void **)&dTok, (size_t)nranks + 64, st));
+            if (!isRoot) GR_CUDA(cudaMemcpyAsync(dTok + rank, &token, 1, cudaMemcpyHostToDevice, st));
+            GR_NCCL(nccl.GroupStart());
+            for (int r = 0; r < nranks; ++r) {
+                if (r == root) continue;
+                if (isRoot) GR_NCCL(nccl.Recv(dTok + r, 1, kNcclUint8, r, comm, st));
+                else if (r == rank) GR_NCCL(nccl.Send(dTok + rank, 1, kNcclUint8, root, comm, st));
+            }
+            GR_NCCL(nccl.GroupEnd());
+            if (isRoot) {
+                uint8_t toks[64];
+                memset(toks, 1, sizeof(toks));
+                GR_CUDA(cudaMemcpyAsync(toks, dTok, (size_t)nranks, cudaMemcpyDeviceToHost, st));
+                GR_CUDA(cudaStreamSynchronize(st));
+                for (int r = 0; r < nranks; ++r)
+                    if (r != root && !toks[r]) res = AVIF_RESULT_UNKNOWN_ERROR;
+                if (!token) res = AVIF_RESULT_UNKNOWN_ERROR;
+            } else if (!token) {
+                res = AVIF_RESULT_UNKNOWN_ERROR;
+            }
+            gGridLastMode = 1;
+            if (phaseMs) {
+                GR_CUDA(cudaEventRecord(ev[3], st));
+                GR_CUDA(cudaEventSynchronize(ev[3]));
+                for (int k = 0; k < 3; ++k) GR_CUDA(cudaEventElapsedTime(&phaseMs[k], ev[k], ev[k + 1])); /* descriptor, convert over NVLink, tokens */
+            }
+            goto cleanup;
+        }
     }
     /* ---- 1. scatter band inputs (packed [Y | U | V | A] rows) ---- */
     for (int k = 0; k < nb; ++k) {
@@ -701,6 +791,8 @@ avifResult avifB200GridYUVToRGB(const avifImage * canvas, avifRGBImage * canvasR
     }
 
 cleanup:
+    if (dDesc) (void)cudaFreeAsync(dDesc, st);
+    if (dTok) (void)cudaFreeAsync(dTok, st);
     for (int k = 0; k < 64; ++k) {
         if (inBuf[k]) (void)cudaFreeAsync(inBuf[k], st);
         if (outBuf[k]) (void)cudaFreeAsync(outBuf[k], st);

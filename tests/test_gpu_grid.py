@@ -94,5 +94,6 @@ def test_two_gpu_grid_over_nccl():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["n_gpus"] == 2 and line["encode_check"] == "ok" and line["encode_check_staged"] == "ok" and line["decode_check"] == "ok", line
+    assert line["n_gpus"] == 2 and line["encode_check"] == "ok" and line["encode_check_staged"] == "ok", line
+    assert line["decode_check"] == "ok" and line["decode_check_peer"] == "ok", line
     assert line["encode_mode_staged"] == "staged NCCL exchange", line  # AVIF_B200_GRID_PEER=0 is honoured; the default may be either form

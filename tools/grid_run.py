@@ -137,26 +137,41 @@ def grid_decode(timed=None):
         timed.append(list(phase3))
 
 
-grid_decode()
-torch.cuda.synchronize()
+ref = None
 if rank == 0:
     ref = wl.make_rgb("C3", device=dev)
     assert lib.avifB200ImageYUVToRGBAsync(img.ptr(), ref.ptr(), sptr) == 0
     torch.cuda.synchronize()
-    out["decode_check"] = "ok" if wl.rgb_digest(ref) == wl.rgb_digest(dst) else "MISMATCH"
-if not check_only:
-    for _ in range(3):
-        grid_decode()
-    rec = []
-    for _ in range(10):
-        grid_decode(rec)
-    t = torch.tensor([[sum(x[k] for x in rec) / len(rec) for k in range(3)]], device=dev, dtype=torch.float64)
+# default = staged exchange; the peer-memory form of the decode side is opt-in (measured slower: remote 16-byte strided pixel stores)
+for form, env in (("", None), ("_peer", "1")):
+    if env is not None:
+        os.environ["AVIF_B200_GRID_PEER_DECODE"] = env
+    dst.buf._t.zero_()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sc, cv, ga = [float(v) for v in t[0]]
-    out["decode"] = {"workload": "8K 4:2:0 12-bit + alpha -> RGBA12 bilinear + unmultiply (C3 geometry), N even row bands with one chroma row of halo",
-                     "ms_scatter": sc, "ms_convert": cv, "ms_gather": ga, "ms_total": sc + cv + ga,
-                     "Mpixels_per_s_kernel": 7680 * 4320 / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": 7680 * 4320 / ((sc + cv + ga) * 1e-3) / 1e6}
+        dist.barrier()
+    grid_decode()
+    torch.cuda.synchronize()
+    mode = int(lib.avifB200GridLastMode())
+    if rank == 0:
+        out["decode_check" + form] = "ok" if wl.rgb_digest(ref) == wl.rgb_digest(dst) else "MISMATCH"
+        out["decode_mode" + form] = "peer memory" if mode == 1 else ("staged NCCL exchange" if world > 1 else "one rank")
+    if not check_only:
+        for _ in range(3):
+            grid_decode()
+        rec = []
+        for _ in range(10):
+            grid_decode(rec)
+        t = torch.tensor([[sum(x[k] for x in rec) / len(rec) for k in range(3)]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sc, cv, ga = [float(v) for v in t[0]]
+        out["decode" + form] = {"workload": "8K 4:2:0 12-bit + alpha -> RGBA12 bilinear + unmultiply (C3 geometry), N even row bands with one chroma row of halo",
+                                "mode": out.get("decode_mode" + form),
+                                "ms_scatter": sc, "ms_convert": cv, "ms_gather": ga, "ms_total": sc + cv + ga,
+                                "Mpixels_per_s_kernel": 7680 * 4320 / (cv * 1e-3) / 1e6, "Mpixels_per_s_kernel_plus_nccl": 7680 * 4320 / ((sc + cv + ga) * 1e-3) / 1e6}
+    if env is not None:
+        del os.environ["AVIF_B200_GRID_PEER_DECODE"]
 gridcomm.destroy_comm(lib, comm)
 if rank == 0:
     print(json.dumps(out), flush=True)

@@ -17,6 +17,6 @@ print('   c4_grid', {k:(round(v,3) if isinstance(v,float) else v) for k,v in d['
 print('   c4_grid staged', {k:(round(v,3) if isinstance(v,float) else v) for k,v in d['c4_grid'].get('staged',{}).items() if k.startswith('ms_') or k in ('check','mode')})
 PY
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 tools/grid_run.py > $OUT/grid_n$N.json 2> $OUT/grid_n$N.err
-    python -c "import json; d=json.loads(open('$OUT/grid_n$N.json').read().strip().splitlines()[-1]); print('   grid N=$N', d['encode_check'], d.get('encode_mode'), d.get('encode_check_staged'), d['decode_check'], {k:round(v,3) for k,v in d['encode'].items() if k.startswith('ms_')}, {k:round(v,3) for k,v in d.get('encode_staged',{}).items() if k.startswith('ms_')}, {k:round(v,3) for k,v in d['decode'].items() if k.startswith('ms_')})" || tail -3 $OUT/grid_n$N.err
+    python -c "import json; d=json.loads(open('$OUT/grid_n$N.json').read().strip().splitlines()[-1]); print('   grid N=$N', d['encode_check'], d.get('encode_mode'), d.get('encode_check_staged'), d['decode_check'], {k:round(v,3) for k,v in d['encode'].items() if k.startswith('ms_')}, {k:round(v,3) for k,v in d.get('encode_staged',{}).items() if k.startswith('ms_')}, {k:round(v,3) for k,v in d['decode'].items() if k.startswith('ms_')}, d.get('decode_mode'), d.get('decode_check_peer'), {k:round(v,3) for k,v in d.get('decode_peer',{}).items() if k.startswith('ms_')})" || tail -3 $OUT/grid_n$N.err
   fi
 done
