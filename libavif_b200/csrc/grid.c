@@ -248,15 +248,29 @@ static void * peerOpen(const uint8_t handle[64])
     void * base = NULL;
     pthread_mutex_lock(&gPeerLock);
     for (int k = 0; k < gPeerOpenCount; ++k)
-        if (gPeerOpen[k].device == device && memcmp(gPeerOpen[k].handle, handle, 64) == 0) base = gPeerOpen[k].base;
-    if (!base && gPeerOpenCount < 64) {
+        if (gPeerOpen[k].base && gPeerOpen[k].device == device && memcmp(gPeerOpen[k].handle, handle, 64) == 0) base = gPeerOpen[k].base;
+    if (!base) {
+        int slot = gPeerOpenCount;
+        if (slot >= 64) { /* table full: unmap the oldest entry of this device and take its place (its allocation is long gone or idle) */
+            static int next = 0;
+            slot = -1;
+            for (int tries = 0; tries < 64 && slot < 0; ++tries, next = (next + 1) % 64)
+                if (gPeerOpen[next].device == device) slot = next;
+            if (slot >= 0) {
+                next = (slot + 1) % 64;
+                (void)cudaIpcCloseMemHandle(gPeerOpen[slot].base);
+                (void)cudaGetLastError();
+                memset(gPeerOpen[slot].handle, 0, 64); /* nothing matches the slot until it is filled again */
+                gPeerOpen[slot].base = NULL;
+            }
+        }
         cudaIpcMemHandle_t h;
         memcpy(&h, handle, 64);
-        if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
-            memcpy(gPeerOpen[gPeerOpenCount].handle, handle, 64);
-            gPeerOpen[gPeerOpenCount].base = base;
-            gPeerOpen[gPeerOpenCount].device = device;
-            ++gPeerOpenCount;
+        if (slot >= 0 && cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+            memcpy(gPeerOpen[slot].handle, handle, 64);
+            gPeerOpen[slot].base = base;
+            gPeerOpen[slot].device = device;
+            if (slot == gPeerOpenCount) ++gPeerOpenCount;
         } else {
             (void)cudaGetLastError();
             base = NULL;
