@@ -276,3 +276,19 @@ def test_committed_vectors(gpu_product):
         assert worst <= 1 and frac < 0.02, (name, worst, frac)
         want = g[name + "_clli"]
         assert abs(int(want[0]) - clli[0]) <= 1 and abs(int(want[1]) - clli[1]) <= 1
+
+
+@pytest.mark.gpu
+def test_per_pixel_form_of_the_output_transfer_function(gpu_product):
+    """The default build answers <= 12-bit outputs from the threshold table (csrc/tonemap.cu); AVIF_B200_TONEMAP_TABLE=0 evaluates the
+    output transfer function per pixel instead.  The switch is read once per process, so the other form runs in a child process:
+    the whole transfer-function sweep against the reference, same tolerances."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AVIF_B200_TONEMAP_TABLE="0")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gainmap.py"), "-q", "-m", "gpu", "-x",
+                          "-k", "every_transfer_function or rgb565 or formats_depths"],
+                         env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
