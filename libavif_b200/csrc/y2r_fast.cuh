@@ -833,7 +833,8 @@ constexpr uint32_t kYChunk = AB_Y2R_CHUNK;
 #ifndef AB_Y2R_FEED
 #define AB_Y2R_FEED 0
 #endif
-#ifndef AB_Y2R_LATE /* needs AB_Y2R_FEED: rows leave the ring only when they are converted; second-row chroma parked in shared memory */
+#ifndef AB_Y2R_LATE /* needs AB_Y2R_FEED: rows leave the ring only when they are converted; second-row chroma parked in shared memory.
+                    * Compiled and inspected with ptxas only (it did not reach 64 registers): NEVER run on a GPU, no parity result exists */
 #define AB_Y2R_LATE 0
 #endif
 
