@@ -466,13 +466,21 @@ def run_c4_grid(lib, dev, sptr, stream, rank, world, dist):
     phase = (ctypes.c_float * 4)()
 
     def go(timed):
-        assert lib.avifB200GridRGBToYUV(canvas.ptr(), rgb.ptr(), 4, 4, comm, rank, world, 0, sptr, ctypes.byref(phase) if timed else None) == 0
-        return list(phase)
+        r = lib.avifB200GridRGBToYUV(canvas.ptr(), rgb.ptr(), 4, 4, comm, rank, world, 0, sptr, ctypes.byref(phase) if timed else None)
+        return r, list(phase)
 
     def measure():
-        for _ in range(4):
+        """None if the form failed on any rank (every rank learns it: the verdict is all-reduced, nobody is left waiting)"""
+        r, _ = go(False)
+        torch.cuda.synchronize()
+        bad = torch.tensor([1.0 if r != 0 else 0.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if float(bad.item()) != 0.0:
+            return None, int(lib.avifB200GridLastMode())
+        for _ in range(3):
             go(False)
-        rec = [go(True) for _ in range(10)]
+        rec = [go(True)[1] for _ in range(10)]
         t = torch.tensor([sum(x[k] for x in rec) / len(rec) for k in range(4)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -485,6 +493,8 @@ def run_c4_grid(lib, dev, sptr, stream, rank, world, dist):
         torch.cuda.synchronize()
 
     def entry(phases, mode):
+        if phases is None:
+            return {"mode": "peer memory" if mode == 1 else "staged", "error": "avifB200GridRGBToYUV failed on at least one rank in this form"}
         sc, cv, ga, asm_ = phases
         names = ("ms_descriptor", "ms_convert_over_nvlink", "ms_tokens", "ms_assemble") if mode == 1 else ("ms_scatter", "ms_convert", "ms_gather", "ms_assemble")
         e = dict(zip(names, phases))
