@@ -222,7 +222,8 @@ __device__ __forceinline__ void set_rgba(uint8_t * row, uint32_t x, const AbPixF
 
 /* ---- output transfer function as a step function -----------------------------------------------------------------------
  * For integer outputs the stored code is a monotone step function of the linear value:  code(x) = (T)(0.5 + clamp(g(x)) * max)
- * with g non-decreasing for all 13 transfer functions.  So code(x) = number of thresholds t_k <= x, t_k = the smallest float whose
+ * never decreases and is 0 for x <= 0 (all transfer functions but BT.1361 extended: kAbNotStepFunctions below).  So code(x) =
+ * number of thresholds t_k <= x, t_k = the smallest float whose
  * code is >= k (k = 1..max).  The thresholds are found once per (device, transfer function, max) by bisection over the float bit
  * patterns with g evaluated in double and rounded once (what glibc's correctly rounded powf / logf return), kept for the life of
  * the process, copied into shared memory by every block and searched in log2(max + 1) steps: 8 / 10 / 12 shared loads and compares
@@ -423,6 +424,12 @@ __global__ void __launch_bounds__(256) tone_map_kernel(const __grid_constant__ A
 
 } // namespace
 
+/* Transfer functions whose stored code is NOT a non-decreasing function of the linear value with code(x <= 0) == 0 -- the premise of
+ * the threshold table.  BT.1361 extended (12): its negative branch -0.2748 (-4 l)^0.45 + 0.0248 is POSITIVE for -0.0012 < l < 0 (up to
+ * code 6 / 25 / 102 at 8 / 10 / 12 bits) and drops back to 0 at l = 0.  tests/test_proofs.py scans the compiled reference's thirteen
+ * functions and requires this list to be exactly the set that fails the premise; those keep the per-pixel evaluation. */
+static const int kAbNotStepFunctions[] = { 12 };
+
 /* AVIF_B200_TONEMAP_TABLE=0 evaluates the output transfer function per pixel as before (A/B timing, tests of both forms) */
 static bool abToneMapNoThresholds()
 {
@@ -481,7 +488,10 @@ extern "C" int abLaunchToneMap(const AbToneMapJob * job, void * stream)
     /* integer channels of at most 12 bits: the output transfer function as a searched step function (when a transfer function runs at all) */
     const float * thresh = nullptr;
     uint32_t threshN = 0;
-    if (!job->outFmt.isFloat && job->outFmt.maxF < 4095.5f && (job->applyGain || job->transcode) && !abToneMapNoThresholds()) {
+    bool stepFunction = true;
+    for (size_t k = 0; k < sizeof(kAbNotStepFunctions) / sizeof(kAbNotStepFunctions[0]); ++k)
+        if (job->tfOut == kAbNotStepFunctions[k]) stepFunction = false;
+    if (stepFunction && !job->outFmt.isFloat && job->outFmt.maxF < 4095.5f && (job->applyGain || job->transcode) && !abToneMapNoThresholds()) {
         threshN = (uint32_t)job->outFmt.maxF;
         if (((threshN + 1u) & threshN) == 0u) thresh = thresholds_for(job->tfOut, threshN, job->outFmt.maxF, (cudaStream_t)stream);
     }

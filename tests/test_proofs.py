@@ -58,3 +58,38 @@ def test_level_order_threshold_search_equals_a_sorted_search():
                 pos = 2 * pos + (e[pos] <= x)
         want = np.searchsorted(t[:-5], x, side="right")  # NaN tail never counts
         assert np.array_equal(pos - (1 << d), want), d
+
+
+def test_output_code_is_a_step_function_of_the_linear_value_except_where_listed():
+    """Premise of the tone mapper's threshold table (csrc/tonemap.cu): for integer outputs the stored code
+    (T)(0.5 + clamp(linearToGamma(x)) * max) never decreases as x grows and is 0 for x <= 0.  Scanned on the compiled reference's own
+    thirteen functions (avifTransferCharacteristicsGetLinearToGammaFunction, src/colr.c:216-491) over 1.2 M floats from -1e5 to 1e5:
+    it holds for every function except BT.1361 extended (its negative branch is positive just below zero), and the list of exclusions
+    compiled into the library must be exactly that set."""
+    import ctypes
+    import numpy as np
+    from oracle import loader
+    ref = loader.load_reference()
+    raw = getattr(ref, "raw", ref)
+    if raw is None or not hasattr(raw, "avifTransferCharacteristicsGetLinearToGammaFunction"):
+        import pytest
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    src = open(os.path.join(ROOT, "libavif_b200", "csrc", "tonemap.cu")).read()
+    listed = sorted(int(x) for x in re.search(r"kAbNotStepFunctions\[\] = \{([^}]*)\}", src).group(1).split(",") if x.strip())
+    fn_t = ctypes.CFUNCTYPE(ctypes.c_float, ctypes.c_float)
+    get = raw.avifTransferCharacteristicsGetLinearToGammaFunction
+    get.restype, get.argtypes = fn_t, [ctypes.c_int]
+    pos = np.geomspace(1e-12, 1e5, 400000)
+    xs = np.unique(np.concatenate([-pos, [0.0], pos, np.linspace(0, 1.2, 200001)]).astype(np.float32))
+    failing = []
+    for tc in [1, 4, 5, 7, 8, 9, 10, 11, 12, 13, 16, 17, 18]:
+        f = get(tc)
+        g = np.array([f(float(x)) for x in xs], dtype=np.float32)
+        g = np.minimum(np.float32(1.0), np.maximum(np.float32(0.0), g))
+        ok = True
+        for mx in (255.0, 1023.0, 4095.0):
+            code = np.floor(np.float32(0.5) + g * np.float32(mx)).astype(np.int64)
+            ok = ok and not (np.diff(code) < 0).any() and int(code[xs <= 0].max()) == 0
+        if not ok:
+            failing.append(tc)
+    assert failing == listed == [12], (failing, listed)
