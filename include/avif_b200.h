@@ -522,6 +522,9 @@ AVIF_B200_API avifResult avifB200ImageScaleToDevice(const avifImage * src, avifI
  * mapper's primaries matrix (row-major doubles; returns 0 where the reference's derivation fails). */
 AVIF_B200_API avifResult avifB200DebugScalePlan(int srcWidth, int srcHeight, int dstWidth, int dstHeight, int sixteenBit, int * mode,
                                                 int * linearOnly, int * minBoxWidth, int32_t * rows, int32_t * cols);
+/* ... and whether the kernel computes that plane's column positions in closed form (x0 + i * dx, 16.16) instead of reading the table */
+AVIF_B200_API avifResult avifB200DebugScalePlanColumns(int srcWidth, int srcHeight, int dstWidth, int dstHeight, int sixteenBit, int * closedForm,
+                                                       int32_t * x0, int32_t * dx);
 AVIF_B200_API int avifB200DebugPrimariesMatrix(avifColorPrimaries src, avifColorPrimaries dst, double out[9]);
 
 /* ---- B-2: the reference's internal seam (include/avif/internal.h:350-387) ------------------------------------------

@@ -222,6 +222,7 @@ PROTOTYPES = {
                                            C.POINTER(avifContentLightLevelInformationBox), C.POINTER(avifDiagnostics)]),
     "avifB200DebugScalePlan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "avifB200DebugScalePlanColumns": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "avifB200DebugPrimariesMatrix": (C.c_int, [C.c_uint16, C.c_uint16, C.POINTER(C.c_double)]),
     "avifImageScale": (C.c_int, [_PI, C.c_uint32, C.c_uint32, C.POINTER(avifDiagnostics)]),
     "avifB200ImageScaleToDevice": (C.c_int, [_PI, _PI]),

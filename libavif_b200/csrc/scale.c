@@ -318,6 +318,20 @@ typedef struct PlaneIO { /* one plane, both ends on the device; strides in bytes
     int sw, sh, dw, dh;
 } PlaneIO;
 
+/* Test hook, second half: whether the kernel may compute this plane's column positions in closed form (x0 + i * dx, 16.16) instead of
+ * reading cols[] -- what planScale decided after checking the closed form against its own walk. */
+avifResult avifB200DebugScalePlanColumns(int srcWidth, int srcHeight, int dstWidth, int dstHeight, int sixteenBit, int * closedForm, int32_t * x0, int32_t * dx)
+{
+    if (srcWidth <= 0 || srcHeight <= 0 || dstWidth <= 0 || dstHeight <= 0) return AVIF_RESULT_INVALID_ARGUMENT;
+    ScalePlan plan;
+    if (!planScale(srcWidth, srcHeight, dstWidth, dstHeight, sixteenBit, &plan)) return AVIF_RESULT_OUT_OF_MEMORY;
+    if (closedForm) *closedForm = plan.colsArith;
+    if (x0) *x0 = plan.x0;
+    if (dx) *dx = plan.dx;
+    planFree(&plan);
+    return AVIF_RESULT_OK;
+}
+
 /* Position tables depend on the four dimensions (and the sample size) only, and a scaling service sees the same few geometries
  * over and over (tiles of one size, gain maps of one size): the first call for a geometry replays libyuv's state machines on the
  * host and uploads the tables, later calls find them resident.  Process-wide, per device, at most kPlanCacheSize geometries

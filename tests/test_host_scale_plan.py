@@ -221,3 +221,34 @@ def test_identities_behind_the_staged_kernel(product):
             assert np.all(np.diff(C[:, 0]) >= 0) and C[0, 0] >= 0 and C[-1, 0] + C[-1, 1] <= sw
             assert np.all(R[:, 1] >= 1) and np.all(R[:, 0] >= 0) and np.all(R[:, 0] + R[:, 1] <= sh)
     assert seen > 100
+
+
+def test_column_positions_in_closed_form(product):
+    """The staged kernels compute column positions as x0 + i * dx (16.16) when the host vouches for it (AbScaleJob::colsArith): the
+    closed form has to reproduce the table for every geometry that claims it, and the everyday geometries have to claim it (else the
+    kernels silently fall back to dependent table loads)."""
+    def columns(sw, sh, dw, dh, sixteen):
+        cf, x0, dx = ctypes.c_int(), ctypes.c_int32(), ctypes.c_int32()
+        assert product.avifB200DebugScalePlanColumns(sw, sh, dw, dh, int(sixteen), ctypes.byref(cf), ctypes.byref(x0), ctypes.byref(dx)) == 0
+        return cf.value, x0.value, dx.value
+    rng = np.random.RandomState(11)
+    geoms = [(3840, 2160, 1280, 720), (1920, 1080, 640, 360), (3840, 2160, 1920, 1080), (1280, 720, 3840, 2160), (640, 360, 1920, 1080), (1000, 700, 333, 100)]
+    geoms += [(int(rng.randint(2, 3000)), int(rng.randint(2, 2000)), int(rng.randint(1, 3000)), int(rng.randint(1, 2000))) for _ in range(200)]
+    claimed = 0
+    for k, (sw, sh, dw, dh) in enumerate(geoms):
+        for sixteen in (False, True):
+            mode, lin, minbw, R, C = plan(product, sw, sh, dw, dh, sixteen)
+            cf, x0, dx = columns(sw, sh, dw, dh, sixteen)
+            if k < 6 and mode in (SIMPLE, BIL_DOWN, BIL_UP, BOX):
+                assert cf == 1, (sw, sh, dw, dh, sixteen, mode)
+            if not cf or mode == 0:
+                continue
+            claimed += 1
+            t = x0 + np.arange(dw, dtype=np.int64) * dx
+            assert t[-1] + dx < 2 ** 31
+            assert np.array_equal(C[:, 0], t >> 16), (sw, sh, dw, dh, mode)
+            if mode == BOX:
+                assert np.array_equal(C[:, 1], ((t + dx) >> 16) - (t >> 16))
+            if mode in (BIL_DOWN, BIL_UP):
+                assert np.array_equal(C[:, 1], t & 0xFFFF)
+    assert claimed > 150
