@@ -93,3 +93,51 @@ def test_output_code_is_a_step_function_of_the_linear_value_except_where_listed(
         if not ok:
             failing.append(tc)
     assert failing == listed == [12], (failing, listed)
+
+
+def test_threshold_search_reproduces_the_reference_code_function():
+    """The tone mapper's table algorithm restated on the CPU with the compiled reference's own float functions: thresholds by bisection
+    over positive float bit patterns (smallest x whose code is >= k), code(x) = number of thresholds <= x.  For every transfer function
+    the library serves this way the search must give EXACTLY the code the reference's formula gives, on random, log-spaced and negative
+    inputs (the device evaluates the function in double where the reference uses float libm: that difference, not the algorithm, is
+    what the +-1-code tolerance of tests/test_gpu_gainmap.py covers)."""
+    import ctypes
+    import numpy as np
+    from oracle import loader
+    raw = getattr(loader.load_reference(), "raw", None)
+    if raw is None or not hasattr(raw, "avifTransferCharacteristicsGetLinearToGammaFunction"):
+        import pytest
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    fn_t = ctypes.CFUNCTYPE(ctypes.c_float, ctypes.c_float)
+    get = raw.avifTransferCharacteristicsGetLinearToGammaFunction
+    get.restype, get.argtypes = fn_t, [ctypes.c_int]
+    rng = np.random.RandomState(1)
+
+    def as_float(b):
+        return np.array([b], dtype=np.uint32).view(np.float32)[0]
+    for tc, depth in [(1, 10), (4, 10), (5, 8), (7, 10), (8, 10), (9, 10), (10, 8), (11, 10), (13, 12), (13, 8), (16, 10), (17, 10), (18, 10)]:
+        f, mx = get(tc), np.float32((1 << depth) - 1)
+
+        def code(x):
+            g = min(np.float32(1.0), max(np.float32(0.0), np.float32(f(float(x)))))
+            return int(np.floor(np.float32(0.5) + g * mx))
+        top = code(np.float32(np.inf))
+        thresholds = []
+        for k in range(1, int(mx) + 1):
+            if top < k:
+                break  # codes the function never reaches: nothing is ever >= their thresholds
+            lo, hi = 0, 0x7F800000
+            while hi - lo > 1:
+                mid = lo + ((hi - lo) >> 1)
+                if code(as_float(mid)) >= k:
+                    hi = mid
+                else:
+                    lo = mid
+            thresholds.append(as_float(hi))
+        t = np.array(thresholds, dtype=np.float32)
+        assert np.all(np.diff(t) >= 0)
+        xs = np.concatenate([rng.random_sample(6000).astype(np.float32) * 1.5, (10.0 ** rng.uniform(-8, 2, 6000)).astype(np.float32),
+                             -rng.random_sample(500).astype(np.float32), t[:: max(1, len(t) // 200)]])
+        want = np.array([code(x) for x in xs])
+        got = np.searchsorted(t, xs, side="right")
+        assert np.array_equal(want, got), (tc, depth, int(np.abs(want - got).max()))
